@@ -1,0 +1,200 @@
+// internal.cuh — shared declarations of libcatt_b200 (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "catt_b200.h"
+
+namespace catt {
+
+// ---------------------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define CATT_CUDA(call)                                                         \
+  do {                                                                          \
+    cudaError_t e__ = (call);                                                   \
+    if (e__ != cudaSuccess) return ::catt::cuda_fail(e__, #call, __FILE__, __LINE__); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+// limits and packing
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int MAX_READ = CATT_MAX_READ_LEN;     // rows of the DP, positions of the seeding arrays
+constexpr int SEED_K = 10;                      // bwa mem -k 10
+constexpr int MAX_CW = 24;                      // candidate bitmap words per read: 2*nrec <= 768
+constexpr int MAX_REC = MAX_CW * 16;            // 384 records per reference set (IGHV has 376)
+constexpr int MAX_REC_LEN = 320;                // longest record the SW kernel tiles (TRGV 311)
+constexpr int MOTIF_MAX_ALT = 64;
+constexpr int MOTIF_MAX_LEN = 8;
+
+__host__ __device__ inline uint8_t nt_code(char c) {
+  switch (c) {
+    case 'A': case 'a': return 0;
+    case 'C': case 'c': return 1;
+    case 'G': case 'g': return 2;
+    case 'T': case 't': return 3;
+    default: return 4;
+  }
+}
+
+// Packed read layout in HBM (u32 words), per read at word offset off[i]:
+//   [ceil(len/16) words of 2-bit bases, base b at bits 2*(b%16) of word b/16]
+//   [ceil(len/32) words of N mask,      base b at bit  b%32     of word b/32]
+__host__ __device__ inline int read_base_words(int len) { return (len + 15) >> 4; }
+__host__ __device__ inline int read_mask_words(int len) { return (len + 31) >> 5; }
+__host__ __device__ inline int read_words(int len) { return read_base_words(len) + read_mask_words(len); }
+// words of the 2-bit packed 2-strand text (padded so 64-bit window reads and 16-byte bulk copies stay in bounds)
+__host__ __device__ inline int t2_words(int L) { return (((2 * L + 15) / 16) + 2 + 3) & ~3; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// reference set (V or J): host copy + device tables
+// ---------------------------------------------------------------------------------------------------------------
+struct RefDev {            // POD view handed to kernels
+  const uint32_t* T2;      // 2-bit packed 2-strand text (forward + reverse complement), 2L bases
+  const uint8_t* Tb;       // forward text, one byte per base (0..3): DP targets
+  const uint8_t* fa;       // forward FASTA codes (0..4, N kept): real_score compares against these
+  const uint32_t* bitmap;  // 2^20 bits: which 10-mers occur in the 2-strand text
+  const uint32_t* kstart;  // 2^20+1 CSR offsets
+  const uint32_t* kpos;    // text positions by 10-mer
+  const uint16_t* pos2rid; // forward position -> record
+  const int32_t* rec_off;
+  const int32_t* rec_len;
+  int32_t L, nrec, maxlen, CW;
+};
+
+struct RefSet {
+  std::vector<std::string> names;
+  std::vector<int32_t> off, len;
+  std::vector<uint8_t> fa;   // L
+  std::vector<uint8_t> T;    // 2L
+  int L = 0, maxlen = 0;
+  RefDev dev{};
+  std::vector<void*> allocs;
+  int load(const std::string& fasta);   // host side
+  int upload();                         // device tables
+  void release();
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// motif tables (compiled regexes of reference.jl) and the per-context device config
+// ---------------------------------------------------------------------------------------------------------------
+struct MotifDev {
+  int32_t len, nalt;
+  uint32_t mask[MOTIF_MAX_ALT * MOTIF_MAX_LEN];   // mask[alt*MOTIF_MAX_LEN + k]: allowed residues (bit = letter-'A', 26 = '*')
+};
+enum { M_C = 0, M_F = 1, M_INNER_C = 2, M_INNER_F = 3, M_HARD_C = 4, M_HARD_F = 5, M_COUNT = 6 };
+struct FinderDev {
+  MotifDev m[M_COUNT];
+  int32_t coffset, foffset;
+};
+int compile_motif(const char* re, MotifDev* out);   // host; returns 0 or CATT_E_ARG
+
+// ---------------------------------------------------------------------------------------------------------------
+// packed reads on the device
+// ---------------------------------------------------------------------------------------------------------------
+struct ReadsDev {
+  const uint32_t* words;
+  const uint32_t* off;     // word offset per read
+  const int32_t* len;
+  int64_t n;
+  int32_t max_len;
+};
+
+struct HostReads {          // views into caller memory (or owned buffers for catt_run_file)
+  int64_t n = 0;
+  const char* names = nullptr; const int64_t* name_off = nullptr;
+  const char* seqs = nullptr;  const int64_t* seq_off = nullptr;
+  const char* quals = nullptr;
+  std::string own_names, own_seqs, own_quals;
+  std::vector<int64_t> own_name_off, own_seq_off;
+};
+
+struct PackedReads {
+  std::vector<uint32_t> words;
+  std::vector<uint32_t> off;
+  std::vector<int32_t> len;
+  int max_len = 0;
+};
+int pack_reads(int64_t n, const char* seqs, const int64_t* seq_off, PackedReads* out);
+
+// ---------------------------------------------------------------------------------------------------------------
+// stage A device buffers and kernels
+// ---------------------------------------------------------------------------------------------------------------
+struct SwTask { uint32_t read; uint16_t a, b; };   // two same-strand candidates (cand = rid*2+strand; 0xFFFF = none)
+
+struct AlignBuffers {       // per reference set, sized for one batch
+  int64_t cap_reads = 0, cap_tasks = 0;
+  uint32_t* candbits = nullptr;    // n * CW
+  uint32_t* ntask = nullptr;       // n (+1): tasks per read, then exclusive offsets
+  uint32_t* task_off = nullptr;    // n+1
+  SwTask* tasks = nullptr;
+  uint32_t* task_res = nullptr;    // 2 per task: score<<20 | (1023-ei)<<10 | (1023-ej)
+  catt_aln* recs = nullptr;        // n
+  uint32_t* gapped_list = nullptr; // read indices whose winner needs the traceback kernel
+  unsigned long long* counters = nullptr;  // [0] cand, [1] cells, [2] n_gapped, [3] hits, [4] seed overflow, [5] ntasks
+  void* cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
+  uint32_t* seed_scratch = nullptr; size_t seed_scratch_runs = 0;
+};
+
+// seeding (seed.cu)
+int launch_seed(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int sm_count, cudaStream_t st, int* launches);
+// task expansion + SW scoring + selection + traceback (sw.cu)
+int launch_expand(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int64_t* ntasks_out, cudaStream_t st, int* launches);
+int launch_sw(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int64_t ntasks, int sm_count, cudaStream_t st, int* launches);
+int launch_select(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int64_t first_ordinal, int min_score,
+                  cudaStream_t st, int* launches);
+int launch_traceback(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int64_t n_gapped, cudaStream_t st, int* launches);
+int launch_sw_pairs(const RefDev& ref, const ReadsDev& reads, const int32_t* d_rid, const int32_t* d_strand, int32_t* d_out3,
+                    int sm_count, cudaStream_t st);
+int alu_peak(int sm_count, cudaStream_t st, double* ops_per_s, double* ms);
+
+// ---------------------------------------------------------------------------------------------------------------
+// stage B kernels (extract.cu, pool.cu)
+// ---------------------------------------------------------------------------------------------------------------
+struct ExtractItem {       // one SAM record (or V/J pair) to turn into a Myread
+  uint32_t read;           // index into the packed reads
+  int16_t kind;            // 0 V part, 1 J part, 2 both-mapped
+  int16_t strand;
+  int16_t qb, m_end, rb, rid;     // of the V record (kind 0,2) or the J record (kind 1)
+  int16_t j_m_end, j_rid;         // kind 2: GetEndCigar of the J record
+  int32_t pad_;
+};
+struct ExtractOut {
+  int16_t status;          // 0 dropped, 1 kept (able and passes the length / N filters)
+  int16_t seq_off, seq_len;       // slice of the SAM-oriented read
+  int16_t cdr3_off, cdr3_len;     // relative to the slice; -1 = "None"
+  int16_t able;
+  int32_t pad_;
+};
+int launch_extract(const RefDev& vref, const RefDev& jref, const ReadsDev& reads, const FinderDev* d_finder,
+                   const ExtractItem* d_items, ExtractOut* d_out, int64_t n, int kmer, int allow_v, int allow_j,
+                   cudaStream_t st, int* launches);
+int launch_finder_raw(const ReadsDev& reads, const FinderDev* d_finder, int array_version, int32_t* d_out3, cudaStream_t st);
+
+struct PoolItem {          // a Vpart/Jpart read as the k-mer table sees it
+  uint32_t read;
+  int16_t strand, seq_off, seq_len;
+  int16_t side;            // 0 = V list (last k+10 nt, extend right), 1 = J list (first k+10 nt, extend left)
+  uint32_t order;          // position in [Vpart; Jpart]: later writers win
+  int32_t partial;         // 1 = cdr3 == "None": run the extension + finder!(array)
+};
+struct ExtendOut {
+  int16_t n_ext;           // bases added
+  int16_t cdr3_off, cdr3_len;   // in the extended sequence; -1 = still "None"
+  int16_t able;
+  uint8_t ext[152];        // added bases as codes, in emission order
+};
+struct KmerTable { unsigned long long* keys; unsigned long long* vals; uint64_t mask; };
+int launch_pool(const ReadsDev& reads, const PoolItem* d_items, int64_t n, int kmer, KmerTable tab, cudaStream_t st, int* launches);
+int launch_extend(const ReadsDev& reads, const FinderDev* d_finder, const PoolItem* d_items, const uint32_t* d_partial_idx,
+                  int64_t n_partial, int kmer, KmerTable tab, ExtendOut* d_out, cudaStream_t st, int* launches);
+int launch_best_d(const char* d_cdr3, const int32_t* d_off, int64_t n, const char* d_dseq, const int32_t* d_doff, int nd,
+                  int32_t* d_out, cudaStream_t st);
+
+}  // namespace catt

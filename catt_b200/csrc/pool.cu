@@ -1,0 +1,221 @@
+// pool.cu — K6/K7/K8: the k-mer table ("pool"), the greedy extension of partial reads with finder!(array), and the
+// D-segment global alignment.
+//
+// Replaces convert2Dict / depcature / bbk / first_serveral / last_serveral (catt.jl:426-497, 544-548), ratio,
+// fillpo_*!, extend_right!, extend_left! (catt.jl:341-424), the array finder! call sites (catt.jl:552-577) and
+// selBestMatchD (Jtool.jl:40-52).
+//
+// The reference's table is NOT a histogram: convert2Dict stores res[kmer] = position (1..11) and per-read dicts are
+// merged last-writer-wins in list order (Vpart, then Jpart overriding).  On the GPU every (read, position) does
+// atomicMax(slot, order << 8 | position) into an open-addressing hash table in HBM, which yields exactly the
+// sequential last-writer value; pool['G'^k] = 0 (catt.jl:545-548) is applied at lookup.
+#include "finder.cuh"
+#include "internal.cuh"
+
+namespace catt {
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int PW = 4;   // warps per CTA
+constexpr unsigned long long EMPTY = ~0ull;
+
+__device__ __forceinline__ uint32_t sam_code(const uint32_t* __restrict__ w, const uint32_t* __restrict__ nm, int len, int i, int strand) {
+  const int p = strand ? len - 1 - i : i;
+  if ((nm[p >> 5] >> (p & 31)) & 1u) return 4u;
+  const uint32_t c = (w[p >> 4] >> ((p & 15) * 2)) & 3u;
+  return strand ? 3u - c : c;
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {      // table slot hash (murmur3 finaliser)
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+  return x;
+}
+
+__device__ __forceinline__ void table_put(const KmerTable& t, uint64_t key, unsigned long long val) {
+  uint64_t slot = mix64(key) & t.mask;
+  while (true) {
+    const unsigned long long prev = atomicCAS(&t.keys[slot], EMPTY, (unsigned long long)key);
+    if (prev == EMPTY || prev == key) { atomicMax(&t.vals[slot], val); return; }
+    slot = (slot + 1) & t.mask;
+  }
+}
+
+__device__ __forceinline__ int table_get(const KmerTable& t, uint64_t key, uint64_t gkey) {
+  if (key == gkey) return 0;
+  uint64_t slot = mix64(key) & t.mask;
+  while (true) {
+    const unsigned long long k = t.keys[slot];
+    if (k == EMPTY) return 0;
+    if (k == key) return (int)(t.vals[slot] & 0xff);
+    slot = (slot + 1) & t.mask;
+  }
+}
+
+// one warp per Vpart/Jpart read: lanes 0..10 insert the k-mers of the k+10 nt fragment
+__global__ void __launch_bounds__(PW * 32) pool_kernel(ReadsDev reads, const PoolItem* __restrict__ items, int64_t n, int k, KmerTable tab) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t it = (int64_t)blockIdx.x * PW + warp; it < n; it += (int64_t)gridDim.x * PW) {
+    const PoolItem pi = items[it];
+    const int m = reads.len[pi.read];
+    const uint32_t* __restrict__ w = reads.words + reads.off[pi.read];
+    const uint32_t* __restrict__ nm = w + read_base_words(m);
+    const int f = min((int)pi.seq_len, k + 10);
+    const int foff = pi.seq_off + (pi.side == 0 ? pi.seq_len - f : 0);     // last_serveral / first_serveral
+    const int npos = f - k + 1;
+    if (lane < npos) {
+      uint64_t key = 0;
+      for (int i = 0; i < k; i++) key = (key << 2) | sam_code(w, nm, m, foff + lane + i, pi.strand);
+      table_put(tab, key, ((unsigned long long)pi.order << 8) | (unsigned)(lane + 1));
+    }
+  }
+}
+
+struct ExtWarp {
+  uint8_t seq[MAX_READ + 160];
+  FinderScratch fs;
+};
+
+__device__ __forceinline__ bool ratio_ok(int x, int y) { return x > y ? (x <= 10 * y) : (10 * x >= y); }   // catt.jl:341
+
+// one warp per partial read (cdr3 == "None"): greedy walk over the table, then finder!(array) on the extended read
+__global__ void __launch_bounds__(PW * 32) extend_kernel(ReadsDev reads, const FinderDev* __restrict__ gfd, const PoolItem* __restrict__ items,
+                                                         const uint32_t* __restrict__ partial_idx, int64_t n_partial, int k, KmerTable tab,
+                                                         ExtendOut* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FinderDev* fd = reinterpret_cast<FinderDev*>(smem_raw);
+  ExtWarp* wsall = reinterpret_cast<ExtWarp*>(smem_raw + sizeof(FinderDev));
+  for (int i = threadIdx.x; i < (int)(sizeof(FinderDev) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(fd)[i] = reinterpret_cast<const uint32_t*>(gfd)[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  ExtWarp& ws = wsall[warp];
+  const uint64_t kmask = (k >= 32) ? ~0ull : ((1ull << (2 * k)) - 1);
+  uint64_t gkey = 0;
+  for (int i = 0; i < k; i++) gkey = (gkey << 2) | 2;
+  for (int64_t it = (int64_t)blockIdx.x * PW + warp; it < n_partial; it += (int64_t)gridDim.x * PW) {
+    const PoolItem pi = items[partial_idx[it]];
+    const int m = reads.len[pi.read];
+    const uint32_t* __restrict__ w = reads.words + reads.off[pi.read];
+    const uint32_t* __restrict__ nm = w + read_base_words(m);
+    const int len0 = pi.seq_len;
+    // the slice sits at offset 152 so that a left extension can be prepended in place
+    uint8_t* base = ws.seq + 152;
+    for (int i = lane; i < len0; i += 32) base[i] = (uint8_t)sam_code(w, nm, m, pi.seq_off + i, pi.strand);
+    __syncwarp();
+    ExtendOut* o = &out[it];
+    int n_ext = 0;
+    if (len0 >= k) {
+      uint64_t seg = 0;
+      const int s0 = pi.side == 0 ? len0 - k : 0;
+      for (int i = 0; i < k; i++) seg = (seg << 2) | base[s0 + i];
+      int cur = table_get(tab, seg, gkey);
+      int idx = 1;
+      bool flag = true;
+      while (idx < 151 - len0 && flag) {
+        // candidates c in A,C,G,T order: right -> bw_neighbors(seg) = c + seg[1:k-1]; left -> fw_neighbors(seg) = seg[2:k] + c
+        const int c = lane & 3;
+        const uint64_t cand = pi.side == 0 ? (((uint64_t)c << (2 * (k - 1))) | (seg >> 2)) : (((seg << 2) | (uint64_t)c) & kmask);
+        int val = 0;
+        if (lane < 4) val = table_get(tab, cand, gkey);
+        // stable sort by value descending, then the first that passes == max value among passing, ties -> smallest c
+        const bool pass = lane < 4 && val != 0 && ratio_ok(val, cur) && cand != seg;
+        int key = pass ? ((val << 2) | (3 - c)) : 0;
+        key = max(key, __shfl_xor_sync(FULL, key, 1));
+        key = max(key, __shfl_xor_sync(FULL, key, 2));
+        key = __shfl_sync(FULL, key, 0);
+        flag = false;
+        if (key) {
+          const int cw = 3 - (key & 3);
+          seg = pi.side == 0 ? (((uint64_t)cw << (2 * (k - 1))) | (seg >> 2)) : (((seg << 2) | (uint64_t)cw) & kmask);
+          cur = key >> 2;
+          if (lane == 0) o->ext[n_ext] = (uint8_t)cw;
+          n_ext++; idx++;
+          flag = true;
+        }
+      }
+    }
+    __syncwarp();
+    // build the extended read: right -> seq * ext ; left -> reverse(ext) * seq
+    uint8_t* ext_seq = base;
+    if (pi.side == 0) {
+      for (int i = lane; i < n_ext; i += 32) base[len0 + i] = o->ext[i];
+    } else {
+      ext_seq = base - n_ext;
+      for (int i = lane; i < n_ext; i += 32) ext_seq[i] = o->ext[n_ext - 1 - i];
+    }
+    __syncwarp();
+    int lo, l3;
+    const bool able = finder_warp(ext_seq, len0 + n_ext, *fd, true, ws.fs, lane, &lo, &l3);
+    if (lane == 0) { o->n_ext = (int16_t)n_ext; o->cdr3_off = (int16_t)lo; o->cdr3_len = (int16_t)l3; o->able = able; }
+    __syncwarp();
+  }
+}
+
+// selBestMatchD: global affine, match 5, mismatch -3, gap(k) = -(4+k); keep score+len(seq)-len(D)+4 > 35; first max wins
+constexpr int D_MAX = 32;
+__global__ void best_d_kernel(const char* __restrict__ cdr3, const int32_t* __restrict__ off, int64_t n, const char* __restrict__ dseq,
+                              const int32_t* __restrict__ doff, int nd, int32_t* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const char* a = cdr3 + off[t];
+  const int m = off[t + 1] - off[t];
+  int best = -1, best_score = 0;
+  for (int d = 0; d < nd; d++) {
+    const char* b = dseq + doff[d];
+    const int nb = doff[d + 1] - doff[d];
+    int H[D_MAX + 1], E[D_MAX + 1];
+    const int NEG = -1000000;
+    H[0] = 0; E[0] = NEG;
+    for (int j = 1; j <= nb; j++) { H[j] = -(4 + j); E[j] = NEG; }
+    for (int i = 1; i <= m; i++) {
+      int hdiag = H[0], f = NEG;
+      H[0] = -(4 + i);
+      const uint8_t ca = nt_code(a[i - 1]);
+      for (int j = 1; j <= nb; j++) {
+        const int e = max(H[j] - 5, E[j] - 1);
+        f = max(H[j - 1] - 5, f - 1);
+        const int s = (ca == nt_code(b[j - 1]) && ca < 4) ? 5 : -3;
+        const int h = max(hdiag + s, max(e, f));
+        hdiag = H[j]; H[j] = h; E[j] = e;
+      }
+    }
+    const int sc = H[nb];
+    if (!(sc + m - nb + 4 > 35)) continue;
+    if (best < 0 || sc > best_score) { best = d; best_score = sc; }
+  }
+  out[t] = best;
+}
+
+}  // namespace
+
+int launch_pool(const ReadsDev& reads, const PoolItem* d_items, int64_t n, int kmer, KmerTable tab, cudaStream_t st, int* launches) {
+  if (n == 0) return CATT_OK;
+  const int grid = (int)std::min<int64_t>((n + PW - 1) / PW, 148 * 16);
+  pool_kernel<<<grid, PW * 32, 0, st>>>(reads, d_items, n, kmer, tab);
+  CATT_CUDA(cudaGetLastError());
+  *launches += 1;
+  return CATT_OK;
+}
+
+int launch_extend(const ReadsDev& reads, const FinderDev* d_finder, const PoolItem* d_items, const uint32_t* d_partial_idx,
+                  int64_t n_partial, int kmer, KmerTable tab, ExtendOut* d_out, cudaStream_t st, int* launches) {
+  if (n_partial == 0) return CATT_OK;
+  const size_t smem = sizeof(FinderDev) + sizeof(ExtWarp) * PW;
+  static bool attr = false;
+  if (!attr) { CATT_CUDA(cudaFuncSetAttribute(extend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+  const int grid = (int)std::min<int64_t>((n_partial + PW - 1) / PW, 148 * 8);
+  extend_kernel<<<grid, PW * 32, smem, st>>>(reads, d_finder, d_items, d_partial_idx, n_partial, kmer, tab, d_out);
+  CATT_CUDA(cudaGetLastError());
+  *launches += 1;
+  return CATT_OK;
+}
+
+int launch_best_d(const char* d_cdr3, const int32_t* d_off, int64_t n, const char* d_dseq, const int32_t* d_doff, int nd,
+                  int32_t* d_out, cudaStream_t st) {
+  if (n == 0) return CATT_OK;
+  best_d_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_cdr3, d_off, n, d_dseq, d_doff, nd, d_out);
+  CATT_CUDA(cudaGetLastError());
+  return CATT_OK;
+}
+
+}  // namespace catt

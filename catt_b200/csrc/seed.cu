@@ -1,0 +1,336 @@
+// seed.cu — K1: k-mer seeding of reads against the 2-strand V or J text.
+//
+// Replaces the seeding half of `bwa mem -k 10` inside map2align (catt.jl:37-56): for every read, the set of
+// (record, strand) pairs that bwa-mem would extend.  Restated per SURVEY.md Appendix A3 from bwa-0.7.17's
+// mem_collect_intv (SMEMs, re-seeding, LAST-like tiling) and mem_chain's bridging discard:
+//   RUNS   = maximal exact-match runs of length >= 10 between the read and T = cat + revcomp(cat);
+//   pass 1 = runs whose query interval is not strictly inside another run's (the SMEM occurrences);
+//   pass 2 = for SMEMs of length >= 15 with <= 10 occurrences: maximal intervals around the middle that occur
+//            at least occ+1 times (length >= 10), all occurrences;
+//   pass 3 = phase-0 tiling: shortest prefix of length >= 11 with < 20 occurrences, all occurrences;
+//   a seed whose reference span crosses a record or the strand boundary is dropped.
+// One warp per read; run list, per-position arrays and the candidate bitmap live in shared memory (a global
+// scratch variant re-runs the rare reads whose run list overflows it).  The packed reads are read with
+// coalesced word loads; the 2-bit text is staged into shared memory by TMA when it fits; the 10-mer bitmap
+// (128 KB) and CSR index are probed through L1/L2.
+#include "internal.cuh"
+#include "tma.cuh"
+
+namespace catt {
+namespace {
+
+constexpr int SEED_WARPS = 4;
+constexpr int RUNS_SMEM = 512;
+constexpr int RUNS_GLOBAL = 16384;
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int T2_SMEM_MAX_BYTES = 56 * 1024;
+
+struct WarpScratch {
+  uint32_t M1[MAX_READ];      // max run end per start position
+  uint32_t Pm[MAX_READ];      // exclusive prefix max of M1; reused as the interval list of pass 2
+  uint32_t cnt[MAX_READ];     // occurrences of the SMEM that starts here
+  uint16_t starts[MAX_READ];  // distinct starts of the runs covering `mid` (pass 2)
+  uint32_t startbits[MAX_READ / 32];
+  uint32_t cand[MAX_CW];
+  uint8_t codes[MAX_READ];
+  int nruns, ncov, niv, pad_;
+  uint32_t runs_q[RUNS_SMEM];   // qs | qe << 16
+  uint32_t runs_t[RUNS_SMEM];   // start in T
+  uint16_t cov[RUNS_SMEM];
+};
+
+struct Scratch {
+  uint32_t* runs_q; uint32_t* runs_t; uint16_t* cov; int cap;
+};
+
+__device__ __forceinline__ uint32_t tbase(const uint32_t* T2, int p) { return (T2[p >> 4] >> ((p & 15) * 2)) & 3u; }
+
+__device__ __forceinline__ void mark_seed(const RefDev& ref, uint32_t* cand, int rb, int len) {
+  const int L = ref.L, re = rb + len;
+  if (rb < L && re > L) return;                       // bridges the forward/reverse boundary
+  const int b = rb < L ? rb : 2 * L - 1 - rb;
+  const int e = (re - 1) < L ? (re - 1) : 2 * L - 1 - (re - 1);
+  const int r1 = ref.pos2rid[b], r2 = ref.pos2rid[e];
+  if (r1 != r2) return;                               // bridges two records
+  const int bit = r1 * 2 + (rb >= L);
+  atomicOr(&cand[bit >> 5], 1u << (bit & 31));
+}
+
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+  #pragma unroll
+  for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+  return v;
+}
+
+// pass 2 for one SMEM: maximal intervals containing `mid` with >= m covering runs
+__device__ void reseed(const RefDev& ref, WarpScratch& ws, const Scratch& sc, int n, int mid, int m, int lane) {
+  if (lane == 0) { ws.ncov = 0; ws.niv = 0; }
+  if (lane < MAX_READ / 32) ws.startbits[lane] = 0;
+  __syncwarp();
+  for (int r = lane; r < n; r += 32) {
+    const uint32_t q = sc.runs_q[r];
+    const int qs = q & 0xffff, qe = q >> 16;
+    if (qs <= mid && qe > mid) {
+      const int idx = atomicAdd(&ws.ncov, 1);
+      sc.cov[idx] = (uint16_t)r;                      // cov capacity == run capacity
+      atomicOr(&ws.startbits[qs >> 5], 1u << (qs & 31));
+    }
+  }
+  __syncwarp();
+  const int nc = ws.ncov;
+  if (nc < m) return;
+  int ns = 0;
+  for (int w = 0; w < MAX_READ / 32; w++) {
+    const uint32_t bits = ws.startbits[w];
+    const int c = __popc(bits);
+    if (lane < c) ws.starts[ns + lane] = (uint16_t)(w * 32 + __fns(bits, 0, lane + 1));
+    ns += c;
+  }
+  __syncwarp();
+  uint32_t prev_run = 0;
+  for (int sb = 0; sb < ns; sb += 32) {
+    const int si = sb + lane;
+    const bool valid = si < ns;
+    const int sp = valid ? ws.starts[si] : -1;
+    uint32_t top[11];
+    #pragma unroll
+    for (int t = 0; t < 11; t++) top[t] = 0;
+    int c = 0;
+    for (int k = 0; k < nc; k++) {
+      const uint32_t q = sc.runs_q[sc.cov[k]];
+      const int qs = q & 0xffff;
+      uint32_t v = q >> 16;
+      if (qs <= sp) {
+        c++;
+        #pragma unroll
+        for (int t = 0; t < 11; t++) { const uint32_t a = max(top[t], v), b = min(top[t], v); top[t] = a; v = b; }
+      }
+    }
+    uint32_t e = 0;
+    if (c >= m) {
+      #pragma unroll
+      for (int t = 0; t < 11; t++) if (t == m - 1) e = top[t];
+    }
+    uint32_t incl = e;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl = max(incl, t); }
+    uint32_t excl = __shfl_up_sync(FULL, incl, 1);
+    if (lane == 0) excl = 0;
+    excl = max(excl, prev_run);
+    if (valid && e > excl && (int)e - sp >= SEED_K) {
+      const int idx = atomicAdd(&ws.niv, 1);
+      ws.Pm[idx] = (uint32_t)sp | (e << 16);
+    }
+    prev_run = max(prev_run, __shfl_sync(FULL, incl, 31));
+  }
+  __syncwarp();
+  const int nv = ws.niv;
+  for (int v = 0; v < nv; v++) {
+    const int s = ws.Pm[v] & 0xffff, e = ws.Pm[v] >> 16;
+    for (int k = lane; k < nc; k += 32) {
+      const int r = sc.cov[k];
+      const uint32_t q = sc.runs_q[r];
+      const int qs = q & 0xffff, qe = q >> 16;
+      if (qs <= s && qe >= e) mark_seed(ref, ws.cand, (int)sc.runs_t[r] + (s - qs), e - s);
+    }
+  }
+  __syncwarp();
+}
+
+// returns false when the run list overflowed the scratch capacity
+__device__ bool seed_one_read(const RefDev& ref, const uint32_t* __restrict__ T2, const ReadsDev& reads, int64_t r,
+                              WarpScratch& ws, const Scratch& sc, int lane) {
+  const int len = reads.len[r];
+  const uint32_t* __restrict__ w = reads.words + reads.off[r];
+  const uint32_t* __restrict__ nm = w + read_base_words(len);
+  const int n2 = 2 * ref.L;
+  for (int i = lane; i < len; i += 32) {
+    const uint32_t c = (w[i >> 4] >> ((i & 15) * 2)) & 3u;
+    ws.codes[i] = ((nm[i >> 5] >> (i & 31)) & 1u) ? 4 : (uint8_t)c;
+    ws.M1[i] = 0; ws.cnt[i] = 0;
+  }
+  if (lane < MAX_CW) ws.cand[lane] = 0;
+  if (lane == 0) ws.nruns = 0;
+  __syncwarp();
+  // ---- maximal runs >= 10 (each found once, from its left-maximal 10-mer window)
+  for (int s = lane; s + SEED_K <= len; s += 32) {
+    const uint64_t bw = ((uint64_t)w[(s >> 4) + 1] << 32) | w[s >> 4];
+    const uint32_t key = (uint32_t)(bw >> ((s & 15) * 2)) & 0xFFFFFu;
+    const uint64_t mw = ((uint64_t)nm[(s >> 5) + 1] << 32) | nm[s >> 5];
+    if ((uint32_t)(mw >> (s & 31)) & 0x3FFu) continue;                 // window holds an N
+    if (!((__ldg(&ref.bitmap[key >> 5]) >> (key & 31)) & 1u)) continue;
+    const uint32_t h0 = __ldg(&ref.kstart[key]), h1 = __ldg(&ref.kstart[key + 1]);
+    for (uint32_t h = h0; h < h1; h++) {
+      const int p = (int)__ldg(&ref.kpos[h]);
+      if (s > 0 && p > 0 && ws.codes[s - 1] == tbase(T2, p - 1)) continue;   // not left-maximal
+      int e = SEED_K;
+      while (s + e < len && p + e < n2 && ws.codes[s + e] == tbase(T2, p + e)) e++;
+      const int idx = atomicAdd(&ws.nruns, 1);
+      if (idx < sc.cap) { sc.runs_q[idx] = (uint32_t)s | ((uint32_t)(s + e) << 16); sc.runs_t[idx] = (uint32_t)p; }
+    }
+  }
+  __syncwarp();
+  const int n = ws.nruns;
+  if (n > sc.cap) return false;
+  if (n == 0) return true;
+  // ---- pass 1: SMEM occurrences
+  for (int k = lane; k < n; k += 32) { const uint32_t q = sc.runs_q[k]; atomicMax(&ws.M1[q & 0xffff], q >> 16); }
+  __syncwarp();
+  {
+    uint32_t carry = 0;
+    for (int base = 0; base < len; base += 32) {
+      const int i = base + lane;
+      uint32_t incl = i < len ? ws.M1[i] : 0;
+      #pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl = max(incl, t); }
+      uint32_t excl = __shfl_up_sync(FULL, incl, 1);
+      if (lane == 0) excl = 0;
+      excl = max(excl, carry);
+      if (i < len) ws.Pm[i] = excl;
+      carry = max(carry, __shfl_sync(FULL, incl, 31));
+    }
+  }
+  __syncwarp();
+  for (int k = lane; k < n; k += 32) {
+    const uint32_t q = sc.runs_q[k];
+    const uint32_t qs = q & 0xffff, qe = q >> 16;
+    if (qe == ws.M1[qs] && ws.Pm[qs] < qe) { mark_seed(ref, ws.cand, (int)sc.runs_t[k], (int)(qe - qs)); atomicAdd(&ws.cnt[qs], 1u); }
+  }
+  __syncwarp();
+  // ---- pass 2: re-seeding inside long, rare SMEMs
+  for (int base = 0; base < len; base += 32) {
+    const int i = base + lane;
+    const bool sel = i < len && ws.cnt[i] > 0 && ws.cnt[i] <= 10 && (int)ws.M1[i] - i >= 15;
+    uint32_t bal = __ballot_sync(FULL, sel);
+    while (bal) {
+      const int bit = __ffs(bal) - 1;
+      bal &= bal - 1;
+      const int a = base + bit, b = (int)ws.M1[a], m = (int)ws.cnt[a] + 1;
+      reseed(ref, ws, sc, n, (a + b) >> 1, m, lane);
+    }
+  }
+  // ---- pass 3: tiles
+  int x = 0;
+  while (x < len) {
+    if (ws.codes[x] > 3) { x++; continue; }
+    if (x + 11 > len) break;
+    {
+      const bool isn = lane < 10 && ws.codes[x + 1 + lane] > 3;
+      const uint32_t bal = __ballot_sync(FULL, isn);
+      if (bal) { x = x + 1 + (__ffs(bal) - 1) + 1; continue; }
+    }
+    int e = x + 11;
+    uint32_t c;
+    bool restart = false, stop = false;
+    while (true) {
+      uint32_t mine = 0;
+      for (int k = lane; k < n; k += 32) { const uint32_t q = sc.runs_q[k]; mine += ((int)(q & 0xffff) <= x && (int)(q >> 16) >= e); }
+      c = warp_sum(mine);
+      if (c < 20) break;
+      if (e >= len) { stop = true; break; }
+      if (ws.codes[e] > 3) { x = e + 1; restart = true; break; }
+      e++;
+    }
+    if (stop) break;
+    if (restart) continue;
+    if (c > 0) {
+      for (int k = lane; k < n; k += 32) {
+        const uint32_t q = sc.runs_q[k];
+        const int qs = q & 0xffff, qe = q >> 16;
+        if (qs <= x && qe >= e) mark_seed(ref, ws.cand, (int)sc.runs_t[k] + (x - qs), e - x);
+      }
+    }
+    x = e;
+  }
+  __syncwarp();
+  return true;
+}
+
+__device__ __forceinline__ void write_out(const RefDev& ref, WarpScratch& ws, int64_t r, uint32_t* candbits, uint32_t* ntask,
+                                          int lane) {
+  uint32_t nf = 0, nr = 0;
+  if (lane < ref.CW) {
+    const uint32_t b = ws.cand[lane];
+    candbits[r * ref.CW + lane] = b;
+    nf = __popc(b & 0x55555555u); nr = __popc(b & 0xAAAAAAAAu);
+  }
+  nf = warp_sum(nf); nr = warp_sum(nr);
+  if (lane == 0) ntask[r] = (nf + 1) / 2 + (nr + 1) / 2;
+}
+
+// GS = false: scratch in shared memory, all reads; overflowing reads are appended to `redo`.
+// GS = true : scratch in global memory, only the reads listed in `redo`.
+template <bool GS>
+__global__ void __launch_bounds__(SEED_WARPS * 32) seed_kernel(RefDev ref, ReadsDev reads, uint32_t* __restrict__ candbits,
+                                                               uint32_t* __restrict__ ntask, uint32_t* __restrict__ redo,
+                                                               unsigned long long* __restrict__ counters,
+                                                               uint32_t* __restrict__ gscratch, int t2_bytes_smem) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ uint64_t bar;
+  WarpScratch* all = reinterpret_cast<WarpScratch*>(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpScratch& ws = all[warp];
+  const uint32_t* T2 = ref.T2;
+  if (t2_bytes_smem > 0) {
+    uint32_t* t2s = reinterpret_cast<uint32_t*>(smem_raw + sizeof(WarpScratch) * SEED_WARPS);
+    stage_to_smem(t2s, ref.T2, (uint32_t)t2_bytes_smem, &bar);
+    T2 = t2s;
+  }
+  const int64_t gw = (int64_t)blockIdx.x * SEED_WARPS + warp, nw = (int64_t)gridDim.x * SEED_WARPS;
+  Scratch sc;
+  if (GS) {
+    uint32_t* base = gscratch + (size_t)gw * (RUNS_GLOBAL * 2 + RUNS_GLOBAL / 2);
+    sc.runs_q = base; sc.runs_t = base + RUNS_GLOBAL; sc.cov = reinterpret_cast<uint16_t*>(base + 2 * RUNS_GLOBAL); sc.cap = RUNS_GLOBAL;
+  } else {
+    sc.runs_q = ws.runs_q; sc.runs_t = ws.runs_t; sc.cov = ws.cov; sc.cap = RUNS_SMEM;
+  }
+  const int64_t total = GS ? (int64_t)counters[4] : reads.n;
+  for (int64_t it = gw; it < total; it += nw) {
+    const int64_t r = GS ? (int64_t)redo[it] : it;
+    const bool ok = seed_one_read(ref, T2, reads, r, ws, sc, lane);
+    if (ok) {
+      write_out(ref, ws, r, candbits, ntask, lane);
+    } else if (!GS) {
+      if (lane == 0) { const unsigned long long k = atomicAdd(&counters[4], 1ull); redo[k] = (uint32_t)r; ntask[r] = 0; }
+    } else {
+      if (lane == 0) { atomicAdd(&counters[6], 1ull); ntask[r] = 0; }    // hard overflow: reported to the host as an error
+      if (lane < ref.CW) candbits[r * ref.CW + lane] = 0;
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace
+
+int launch_seed(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int sm_count, cudaStream_t st, int* launches) {
+  const int t2_bytes = t2_words(ref.L) * 4;
+  const int t2_smem = t2_bytes <= T2_SMEM_MAX_BYTES ? t2_bytes : 0;
+  const size_t smem = sizeof(WarpScratch) * SEED_WARPS + t2_smem;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CATT_CUDA(cudaFuncSetAttribute(seed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CATT_CUDA(cudaFuncSetAttribute(seed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+  int per_sm = 0;
+  CATT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seed_kernel<false>, SEED_WARPS * 32, smem));
+  if (per_sm < 1) per_sm = 1;
+  const int64_t want = (reads.n + SEED_WARPS - 1) / SEED_WARPS;
+  int grid = (int)std::min<int64_t>((int64_t)sm_count * per_sm, std::max<int64_t>(want, 1));
+  seed_kernel<false><<<grid, SEED_WARPS * 32, smem, st>>>(ref, reads, ab.candbits, ab.ntask, ab.gapped_list, ab.counters, nullptr, t2_smem);
+  CATT_CUDA(cudaGetLastError());
+  // overflow pass (usually an empty list): global scratch sized for sm_count*2 CTAs
+  const int grid2 = sm_count * 2;
+  const size_t need = (size_t)grid2 * SEED_WARPS * (RUNS_GLOBAL * 2 + RUNS_GLOBAL / 2);
+  if (ab.seed_scratch_runs < need) {
+    if (ab.seed_scratch) cudaFree(ab.seed_scratch);
+    CATT_CUDA(cudaMalloc(&ab.seed_scratch, need * sizeof(uint32_t)));
+    ab.seed_scratch_runs = need;
+  }
+  seed_kernel<true><<<grid2, SEED_WARPS * 32, smem, st>>>(ref, reads, ab.candbits, ab.ntask, ab.gapped_list, ab.counters, ab.seed_scratch, t2_smem);
+  CATT_CUDA(cudaGetLastError());
+  *launches += 2;
+  return CATT_OK;
+}
+
+}  // namespace catt

@@ -1,0 +1,577 @@
+// sw.cu — K2/K3: affine-gap local alignment of each read against its candidate V/J records, hit selection and the
+// CIGAR facts the Julia side reads.
+//
+// Replaces the extension + output half of `bwa mem -A1 -B2 -O6 -E1 -L0 -T12` and the SAM fields consumed through
+// Jtool.jl:76-124 / catt.jl:69-132:
+//   score     = Smith-Waterman local, match +1, mismatch -2, gap(k) = -(6+k), N = -1, of the strand-normalised read
+//               against ONE record; end cell = first maximum in row-major order (read row, then record column);
+//   selection = best score over the candidates; ties broken by bwa's hash_64(read ordinal + rank in T order);
+//   facts     = soft clip (GetStartCigar), end of the first M block (GetEndCigar), POS, NM, sum(M+I).
+//
+// sw_score_kernel: G lanes cooperate on one (read, 2 candidates) task.  Each lane owns C record columns and keeps
+// H/E for them in registers as packed int16x2 — low half = candidate A, high half = candidate B, both on the same
+// strand of the same read, so one query row drives both.  Rows advance as a skewed wavefront (lane g works on row
+// t-g at step t); the last column's H and the running F cross to the next lane by warp shuffle.  The substitution
+// score of a cell-pair is one PRMT (byte permute with sign replication) from two per-column byte tables; the
+// recurrences use the DPX packed add-max instructions (VIADDMNMX/VIMNMX .S16x2).  No tensor cores: there is no
+// dense contraction in this recurrence.
+#include <cub/device/device_scan.cuh>
+
+#include "internal.cuh"
+#include "tma.cuh"
+
+namespace catt {
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int SW_THREADS = 128;
+constexpr uint32_t NEG1 = 0xFFFFFFFFu;   // (-1,-1)
+constexpr uint32_t NEG7 = 0xFFF9FFF9u;   // (-7,-7): first gap base = open 6 + extend 1
+constexpr uint32_t MINV = 0x80008000u;   // (-32768,-32768)
+constexpr uint32_t SEL_N = 0xFFFFu;      // row marker: the read base is N
+
+__device__ __forceinline__ uint64_t hash_64(uint64_t key) {   // bwa's tie-break hash
+  key += ~(key << 32);
+  key ^= (key >> 22);
+  key += ~(key << 13);
+  key ^= (key >> 8);
+  key += (key << 3);
+  key ^= (key >> 15);
+  key += ~(key << 27);
+  key ^= (key >> 31);
+  return key;
+}
+
+// SAM-oriented base of a packed read: strand 1 = reverse complement
+__device__ __forceinline__ uint32_t read_code(const uint32_t* __restrict__ w, const uint32_t* __restrict__ nm, int len, int i, int strand) {
+  const int p = strand ? len - 1 - i : i;
+  if ((nm[p >> 5] >> (p & 31)) & 1u) return 4u;
+  const uint32_t c = (w[p >> 4] >> ((p & 15) * 2)) & 3u;
+  return strand ? 3u - c : c;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// task expansion: candidate bitmap -> (read, candA, candB) tasks, pairing candidates of the same strand
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void expand_kernel(RefDev ref, int64_t n, const uint32_t* __restrict__ candbits, const uint32_t* __restrict__ task_off,
+                              SwTask* __restrict__ tasks) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  uint32_t o = task_off[r];
+  if (task_off[r + 1] == o) return;
+  for (int strand = 0; strand < 2; strand++) {
+    int pend = -1;
+    for (int w = 0; w < ref.CW; w++) {
+      uint32_t b = candbits[r * ref.CW + w] & (strand ? 0xAAAAAAAAu : 0x55555555u);
+      while (b) {
+        const int bit = __ffs(b) - 1;
+        b &= b - 1;
+        const int c = w * 32 + bit;
+        if (pend < 0) pend = c;
+        else { tasks[o++] = SwTask{(uint32_t)r, (uint16_t)pend, (uint16_t)c}; pend = -1; }
+      }
+    }
+    if (pend >= 0) tasks[o++] = SwTask{(uint32_t)r, (uint16_t)pend, (uint16_t)0xFFFF};
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the DP kernel
+// ---------------------------------------------------------------------------------------------------------------
+template <int C, bool NROW>
+__device__ __forceinline__ void sw_row(uint32_t (&Hp)[C], uint32_t (&E)[C], const uint32_t (&tabA)[C], const uint32_t (&tabB)[C],
+                                       uint32_t sel, uint32_t& hd, uint32_t& f, uint32_t& rowbest) {
+  #pragma unroll
+  for (int c = 0; c < C; c++) {
+    const uint32_t s = NROW ? NEG1 : __byte_perm(tabA[c], tabB[c], sel);
+    const uint32_t e = E[c];
+    uint32_t h = __viaddmax_s16x2_relu(hd, s, e);        // max(H(i-1,j-1)+s, E(i,j), 0)
+    h = __vimax_s16x2_relu(h, f);                            // ... and F(i,j)
+    hd = Hp[c];
+    Hp[c] = h;
+    const uint32_t hm7 = __viaddmax_s16x2(h, NEG7, MINV);   // H(i,j) - 7
+    E[c] = __viaddmax_s16x2(e, NEG1, hm7);              // E(i+1,j) = max(E(i,j)-1, H(i,j)-7)
+    f = __viaddmax_s16x2(f, NEG1, hm7);                 // F(i,j+1)
+    rowbest = __vimax_s16x2_relu(rowbest, h);
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_key(int score, int i, int j) {
+  return ((uint32_t)score << 20) | ((uint32_t)(1023 - i) << 10) | (uint32_t)(1023 - j);
+}
+
+// G lanes per task, C columns per lane; record length <= G*C
+template <int G, int C>
+__global__ void __launch_bounds__(SW_THREADS) sw_score_kernel(RefDev ref, ReadsDev reads, const SwTask* __restrict__ tasks,
+                                                              int64_t ntasks, uint32_t* __restrict__ task_res, int tb_bytes_smem) {
+  constexpr int GPW = 32 / G;                         // tasks per warp
+  constexpr int GPB = GPW * (SW_THREADS / 32);        // tasks per block
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ uint64_t bar;
+  uint16_t* sel_all = reinterpret_cast<uint16_t*>(smem_raw);              // [GPB][MAX_READ]
+  const uint8_t* Tb = ref.Tb;
+  if (tb_bytes_smem > 0) {
+    uint8_t* tbs = smem_raw + (size_t)GPB * MAX_READ * sizeof(uint16_t);
+    stage_to_smem(tbs, ref.Tb, (uint32_t)tb_bytes_smem, &bar);
+    Tb = tbs;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane % G, grp = lane / G;
+  uint16_t* sel_arr = sel_all + (size_t)(warp * GPW + grp) * MAX_READ;
+
+  for (int64_t base = ((int64_t)blockIdx.x * (SW_THREADS / 32) + warp) * GPW; base < ntasks;
+       base += (int64_t)gridDim.x * GPB) {
+    const int64_t t = base + grp;
+    const bool live = t < ntasks;
+    int m = 0, strand = 0;
+    uint32_t tabA[C], tabB[C], Hp[C], E[C];
+    #pragma unroll
+    for (int c = 0; c < C; c++) { tabA[c] = 0xFEFEFEFEu; tabB[c] = 0xFEFEFEFEu; Hp[c] = 0; E[c] = 0; }
+    if (live) {
+      const SwTask tk = tasks[t];
+      strand = tk.a & 1;
+      m = reads.len[tk.read];
+      const uint32_t* __restrict__ w = reads.words + reads.off[tk.read];
+      const uint32_t* __restrict__ nm = w + read_base_words(m);
+      for (int i = g; i < m; i += G) {
+        const uint32_t q = read_code(w, nm, m, i, strand);
+        sel_arr[i] = (uint16_t)(q > 3 ? SEL_N : 0xC480u + 0x1111u * q);   // bytes: {A[q], sign(A[q]), B[q], sign(B[q])}
+      }
+      // per-column byte tables: byte q = score of read base q against this column's record base
+      {
+        const int ra = tk.a >> 1, oa = ref.rec_off[ra], la = ref.rec_len[ra];
+        #pragma unroll
+        for (int c = 0; c < C; c++) {
+          const int j = g * C + c;
+          if (j < la) tabA[c] = 0xFEFEFEFEu ^ (0xFFu << (8 * Tb[oa + j]));      // -2 everywhere, +1 at the matching base
+        }
+        if (tk.b != 0xFFFF) {
+          const int rb = tk.b >> 1, ob = ref.rec_off[rb], lb = ref.rec_len[rb];
+          #pragma unroll
+          for (int c = 0; c < C; c++) {
+            const int j = g * C + c;
+            if (j < lb) tabB[c] = 0xFEFEFEFEu ^ (0xFFu << (8 * Tb[ob + j]));
+          }
+        }
+      }
+    }
+    __syncwarp();
+    int steps = live ? m + G - 1 : 0;
+    #pragma unroll
+    for (int d = 16; d; d >>= 1) steps = max(steps, __shfl_xor_sync(FULL, steps, d));
+
+    uint32_t lastH = 0, lastF = 0, diag_in = 0, best = 0;
+    int bi_lo = 0, bj_lo = 0, bi_hi = 0, bj_hi = 0;
+    for (int st = 0; st < steps; st++) {
+      uint32_t inH = __shfl_up_sync(FULL, lastH, 1, G);
+      uint32_t inF = __shfl_up_sync(FULL, lastF, 1, G);
+      if (g == 0) { inH = 0; inF = 0; }
+      const int i = st - g;
+      if (i >= 0 && i < m) {
+        const uint32_t sel = sel_arr[i];
+        uint32_t hd = diag_in, f = inF, rowbest = 0;
+        // F(i, first column) arrives already advanced from the left neighbour
+        if (sel == SEL_N) sw_row<C, true>(Hp, E, tabA, tabB, sel, hd, f, rowbest);
+        else sw_row<C, false>(Hp, E, tabA, tabB, sel, hd, f, rowbest);
+        diag_in = inH;
+        // the first column needs H(i, gC-1) only through F and the next row's diagonal; fold the incoming H into F's
+        // source: F(i,gC) = max(F(i,gC-1)-1, H(i,gC-1)-7) was computed by the neighbour (lastF), so nothing else here.
+        lastH = Hp[C - 1];
+        lastF = f;
+        const uint32_t nb = __vimax_s16x2_relu(best, rowbest);
+        if (nb != best) {                                 // a half improved: record the first cell reaching it
+          const int rl = (int)(short)(rowbest & 0xffff), bl = (int)(short)(best & 0xffff);
+          const int rh = (int)(short)(rowbest >> 16), bh = (int)(short)(best >> 16);
+          if (rl > bl) {
+            bi_lo = i;
+            int jj = 0;
+            #pragma unroll
+            for (int c = C - 1; c >= 0; c--) if ((int)(short)(Hp[c] & 0xffff) == rl) jj = c;
+            bj_lo = g * C + jj;
+          }
+          if (rh > bh) {
+            bi_hi = i;
+            int jj = 0;
+            #pragma unroll
+            for (int c = C - 1; c >= 0; c--) if ((int)(short)(Hp[c] >> 16) == rh) jj = c;
+            bj_hi = g * C + jj;
+          }
+          best = nb;
+        }
+      }
+    }
+    // reduce over the G lanes of the task: max score, then earliest row, then earliest column
+    uint32_t klo = pack_key((int)(short)(best & 0xffff), bi_lo, bj_lo);
+    uint32_t khi = pack_key((int)(short)(best >> 16), bi_hi, bj_hi);
+    #pragma unroll
+    for (int d = G / 2; d; d >>= 1) {
+      klo = max(klo, __shfl_xor_sync(FULL, klo, d, G));
+      khi = max(khi, __shfl_xor_sync(FULL, khi, d, G));
+    }
+    if (live && g == 0) { task_res[2 * t] = klo; task_res[2 * t + 1] = khi; }
+    __syncwarp();
+  }
+}
+
+template <int G, int C>
+int launch_sw_t(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks, int64_t ntasks, uint32_t* res, int sm_count,
+                cudaStream_t st) {
+  constexpr int GPB = (32 / G) * (SW_THREADS / 32);
+  const int tb_bytes = (ref.L + 64) & ~15;
+  const size_t sel_bytes = (size_t)GPB * MAX_READ * sizeof(uint16_t);
+  const int tb_smem = (sel_bytes + tb_bytes <= 100 * 1024) ? tb_bytes : 0;
+  const size_t smem = sel_bytes + tb_smem;
+  auto k = sw_score_kernel<G, C>;
+  static bool attr = false;
+  if (!attr) { CATT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+  int per_sm = 0;
+  CATT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, SW_THREADS, smem));
+  if (per_sm < 1) per_sm = 1;
+  const int64_t want = (ntasks + GPB - 1) / GPB;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)sm_count * per_sm, want));
+  k<<<grid, SW_THREADS, smem, st>>>(ref, reads, tasks, ntasks, res, tb_smem);
+  CATT_CUDA(cudaGetLastError());
+  return CATT_OK;
+}
+
+int dispatch_sw(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks, int64_t ntasks, uint32_t* res, int sm_count,
+                cudaStream_t st) {
+  const int n = ref.maxlen;
+  if (n <= 32) return launch_sw_t<4, 8>(ref, reads, tasks, ntasks, res, sm_count, st);
+  if (n <= 48) return launch_sw_t<4, 12>(ref, reads, tasks, ntasks, res, sm_count, st);
+  if (n <= 64) return launch_sw_t<8, 8>(ref, reads, tasks, ntasks, res, sm_count, st);
+  if (n <= 104) return launch_sw_t<8, 13>(ref, reads, tasks, ntasks, res, sm_count, st);
+  if (n <= 160) return launch_sw_t<16, 10>(ref, reads, tasks, ntasks, res, sm_count, st);
+  if (n <= 320) return launch_sw_t<32, 10>(ref, reads, tasks, ntasks, res, sm_count, st);
+  set_error("record length %d exceeds the SW kernel's tiling", n);
+  return CATT_E_LIMIT;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// selection + CIGAR facts (ungapped fast path).  One thread per read.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int sub_score(uint32_t a, uint32_t b) { return (a > 3 || b > 3) ? -1 : (a == b ? 1 : -2); }
+
+__global__ void select_kernel(RefDev ref, ReadsDev reads, const SwTask* __restrict__ tasks, const uint32_t* __restrict__ task_off,
+                              const uint32_t* __restrict__ task_res, int64_t first_ordinal, int min_score, catt_aln* __restrict__ recs,
+                              uint32_t* __restrict__ gapped_list, unsigned long long* __restrict__ counters) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long my_cand = 0, my_cells = 0, my_hit = 0;
+  if (r < reads.n) {
+    const uint32_t t0 = task_off[r], t1 = task_off[r + 1];
+    const int m = reads.len[r];
+    catt_aln a;
+    a.ordinal = (int32_t)(first_ordinal + r);
+    a.rid = -1; a.strand = 0; a.mapped = 0; a.as = 0; a.qb = 0; a.m_end = 0; a.rb = 0; a.qe = 0; a.re = 0; a.nm = 0; a.mi = 0;
+    a.ncand = 0; a.ntied = 0;
+    int mx = 0, ncand = 0;
+    for (uint32_t t = t0; t < t1; t++) {
+      const SwTask tk = tasks[t];
+      const int sa = (int)(task_res[2 * t] >> 20);
+      mx = max(mx, sa); ncand++;
+      my_cells += (unsigned long long)m * ref.rec_len[tk.a >> 1];
+      if (tk.b != 0xFFFF) {
+        const int sb = (int)(task_res[2 * t + 1] >> 20);
+        mx = max(mx, sb); ncand++;
+        my_cells += (unsigned long long)m * ref.rec_len[tk.b >> 1];
+      }
+    }
+    my_cand = ncand;
+    a.ncand = (int16_t)ncand;
+    a.as = (int16_t)mx;
+    if (ncand > 0 && mx >= min_score) {
+      // tied set in T order: forward records ascending, then reverse-strand records descending
+      const int L = ref.L;
+      int ntied = 0, win_c = -1;
+      uint32_t win_key = 0;
+      uint64_t win_h = ~0ull;
+      for (uint32_t t = t0; t < t1; t++) {
+        const SwTask tk = tasks[t];
+        for (int half = 0; half < 2; half++) {
+          const int c = half ? tk.b : tk.a;
+          if (c == 0xFFFF) continue;
+          const uint32_t key = task_res[2 * t + half];
+          if ((int)(key >> 20) != mx) continue;
+          ntied++;
+          const int rid = c >> 1, sd = c & 1;
+          const int tpos = sd ? 2 * L - (ref.rec_off[rid] + ref.rec_len[rid]) : ref.rec_off[rid];
+          int rank = 0;
+          for (uint32_t u = t0; u < t1; u++) {
+            const SwTask tu = tasks[u];
+            for (int h2 = 0; h2 < 2; h2++) {
+              const int c2 = h2 ? tu.b : tu.a;
+              if (c2 == 0xFFFF || (int)(task_res[2 * u + h2] >> 20) != mx) continue;
+              const int rid2 = c2 >> 1, sd2 = c2 & 1;
+              const int tpos2 = sd2 ? 2 * L - (ref.rec_off[rid2] + ref.rec_len[rid2]) : ref.rec_off[rid2];
+              rank += tpos2 < tpos;
+            }
+          }
+          const uint64_t h = hash_64((uint64_t)(first_ordinal + r) + (uint64_t)rank);
+          if (h < win_h) { win_h = h; win_c = c; win_key = key; }
+        }
+      }
+      const int rid = win_c >> 1, strand = win_c & 1;
+      const int ei = 1023 - (int)((win_key >> 10) & 1023), ej = 1023 - (int)(win_key & 1023);
+      a.rid = rid; a.strand = (int16_t)strand; a.mapped = 1; a.ntied = (int16_t)ntied;
+      a.qe = (int16_t)(ei + 1); a.re = (int16_t)(ej + 1);
+      my_hit = 1;
+      // ungapped fast path: walk back along the diagonal until the suffix sums to AS
+      const uint32_t* __restrict__ w = reads.words + reads.off[r];
+      const uint32_t* __restrict__ nm = w + read_base_words(m);
+      const uint8_t* __restrict__ tb = ref.Tb + ref.rec_off[rid];
+      int sum = 0, mism = 0, d = 0;
+      bool ok = false;
+      const int lim = min(ei, ej);
+      for (; d <= lim; d++) {
+        const uint32_t q = read_code(w, nm, m, ei - d, strand);
+        const uint32_t tt = tb[ej - d];
+        const int s = sub_score(q, tt);
+        sum += s; mism += (s != 1);
+        if (sum == mx) { ok = true; break; }
+      }
+      if (ok) {
+        a.qb = (int16_t)(ei - d); a.rb = (int16_t)(ej - d);
+        a.m_end = (int16_t)(ei + 1);
+        a.nm = (int16_t)mism; a.mi = (int16_t)(d + 1);
+      } else {
+        const unsigned long long k = atomicAdd(&counters[2], 1ull);
+        gapped_list[k] = (uint32_t)r;
+      }
+    }
+    recs[r] = a;
+  }
+  // block-level reduction of the work counters
+  __shared__ unsigned long long sh[3];
+  if (threadIdx.x < 3) sh[threadIdx.x] = 0;
+  __syncthreads();
+  #pragma unroll
+  for (int d = 16; d; d >>= 1) {
+    my_cand += __shfl_xor_sync(FULL, my_cand, d);
+    my_cells += __shfl_xor_sync(FULL, my_cells, d);
+    my_hit += __shfl_xor_sync(FULL, my_hit, d);
+  }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&sh[0], my_cand); atomicAdd(&sh[1], my_cells); atomicAdd(&sh[2], my_hit); }
+  __syncthreads();
+  if (threadIdx.x == 0) { atomicAdd(&counters[0], sh[0]); atomicAdd(&counters[1], sh[1]); atomicAdd(&counters[3], sh[2]); }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// traceback for the rare gapped winners: one warp per read.  The sub-matrix up to the end cell is filled by
+// anti-diagonals (three rolling H diagonals, two E/F) and only a 4-bit direction code per cell is kept in shared
+// memory; then one lane walks back.  Per-cell preference M, then D (record base skipped), then I; a gap prefers
+// "open" over "extend" on a tie; stops at the first H == 0.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int TB_NEG = -30000;
+__global__ void __launch_bounds__(32) traceback_kernel(RefDev ref, ReadsDev reads, const uint32_t* __restrict__ gapped_list,
+                                                       int64_t n_gapped, catt_aln* __restrict__ recs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x;
+  int16_t* Hb = reinterpret_cast<int16_t*>(smem_raw);          // 3 x (MAX_READ+2)
+  int16_t* Eb = Hb + 3 * (MAX_READ + 2);                       // 2 x
+  int16_t* Fb = Eb + 2 * (MAX_READ + 2);                       // 2 x
+  uint8_t* q = reinterpret_cast<uint8_t*>(Fb + 2 * (MAX_READ + 2));
+  uint8_t* dir = q + MAX_READ;
+  for (int64_t it = blockIdx.x; it < n_gapped; it += gridDim.x) {
+    const uint32_t r = gapped_list[it];
+    catt_aln a = recs[r];
+    const int m = reads.len[r];
+    const int rows = a.qe, cols = a.re;                 // sub-matrix [0,rows) x [0,cols); end cell = (rows-1, cols-1)
+    const uint32_t* __restrict__ w = reads.words + reads.off[r];
+    const uint32_t* __restrict__ nm = w + read_base_words(m);
+    const uint8_t* __restrict__ tb = ref.Tb + ref.rec_off[a.rid];
+    for (int i = lane; i < rows; i += 32) q[i] = (uint8_t)read_code(w, nm, m, i, a.strand);
+    __syncwarp();
+    for (int d = 0; d <= rows + cols; d++) {            // cells (i,j), 1-based with a 0 border, i + j == d
+      int16_t* Hc = Hb + (d % 3) * (MAX_READ + 2);
+      const int16_t* H1 = Hb + ((d + 2) % 3) * (MAX_READ + 2);
+      const int16_t* H2 = Hb + ((d + 1) % 3) * (MAX_READ + 2);
+      int16_t* Ec = Eb + (d & 1) * (MAX_READ + 2);
+      const int16_t* E1 = Eb + ((d + 1) & 1) * (MAX_READ + 2);
+      int16_t* Fc = Fb + (d & 1) * (MAX_READ + 2);
+      const int16_t* F1 = Fb + ((d + 1) & 1) * (MAX_READ + 2);
+      const int ilo = max(0, d - cols), ihi = min(rows, d);
+      for (int i = ilo + lane; i <= ihi; i += 32) {
+        const int j = d - i;
+        if (i == 0 || j == 0) { Hc[i] = 0; Ec[i] = TB_NEG; Fc[i] = TB_NEG; continue; }
+        const int eo = H1[i - 1] - 7, ee = E1[i - 1] - 1;      // vertical: consumes a read base (I)
+        const int fo = H1[i] - 7, fe = F1[i] - 1;              // horizontal: consumes a record base (D)
+        const int e = max(eo, ee), f = max(fo, fe);
+        const int dg = H2[i - 1] + sub_score(q[i - 1], tb[j - 1]);
+        const int h = max(max(0, dg), max(e, f));
+        const int src = h == 0 ? 0 : (h == dg ? 1 : (h == f ? 2 : 3));
+        dir[(size_t)(i - 1) * cols + (j - 1)] = (uint8_t)(src | ((fe > fo) << 2) | ((ee > eo) << 3));
+        Hc[i] = (int16_t)h; Ec[i] = (int16_t)max(e, TB_NEG); Fc[i] = (int16_t)max(f, TB_NEG);
+      }
+      __syncwarp();
+    }
+    if (lane == 0) {
+      int i = rows, j = cols, state = 0, nmm = 0, mi = 0, run_m = 0;
+      // ops are visited end -> start; the first M block is the LAST run of M's visited
+      while (i > 0 && j > 0) {
+        const uint8_t dc = dir[(size_t)(i - 1) * cols + (j - 1)];
+        if (state == 0) {
+          const int src = dc & 3;
+          if (src == 0) break;
+          if (src == 1) { nmm += (sub_score(q[i - 1], tb[j - 1]) != 1); mi++; run_m++; i--; j--; }
+          else if (src == 2) { state = 1; run_m = 0; }
+          else { state = 2; run_m = 0; }
+        } else if (state == 1) {                        // D
+          nmm++;
+          if (!(dc & 4)) state = 0;
+          j--;
+        } else {                                        // I
+          nmm++; mi++;
+          if (!(dc & 8)) state = 0;
+          i--;
+        }
+      }
+      a.qb = (int16_t)i; a.rb = (int16_t)j; a.m_end = (int16_t)(i + run_m); a.nm = (int16_t)nmm; a.mi = (int16_t)mi;
+      recs[r] = a;
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// integer-ALU peak microbenchmark: a dependent-free stream of the packed DPX add-max the DP is made of
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) alu_peak_kernel(uint32_t* out, int iters) {
+  uint32_t a[8];
+  #pragma unroll
+  for (int k = 0; k < 8; k++) a[k] = threadIdx.x * 2654435761u + k;
+  const uint32_t b = 0x00010001u + (blockIdx.x & 1), c = 0x00030002u;
+  for (int it = 0; it < iters; it++) {
+    #pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = __viaddmax_s16x2(a[k], b, c);
+    #pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = __vimax_s16x2_relu(a[k], a[(k + 1) & 7] ^ c);
+  }
+  uint32_t s = 0;
+  #pragma unroll
+  for (int k = 0; k < 8; k++) s ^= a[k];
+  if (s == 0x12345678u) out[0] = s;
+}
+
+// SW of explicit (read i, record rid[i], strand[i]) pairs — parity hook around the same kernel
+__global__ void make_pair_tasks(int64_t n, const int32_t* rid, const int32_t* strand, SwTask* tasks) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) tasks[i] = SwTask{(uint32_t)i, (uint16_t)(rid[i] * 2 + (strand[i] & 1)), (uint16_t)0xFFFF};
+}
+__global__ void unpack_pair_res(int64_t n, const uint32_t* res, int32_t* out3) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const uint32_t k = res[2 * i];
+    out3[3 * i] = (int32_t)(k >> 20);
+    out3[3 * i + 1] = 1023 - (int32_t)((k >> 10) & 1023);
+    out3[3 * i + 2] = 1023 - (int32_t)(k & 1023);
+  }
+}
+
+}  // namespace
+
+int launch_expand(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int64_t* ntasks_out, cudaStream_t st, int* launches) {
+  const int64_t n = reads.n;
+  size_t need = 0;
+  CATT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, ab.ntask, ab.task_off, (int)(n + 1), st));
+  if (need > ab.cub_tmp_bytes) {
+    if (ab.cub_tmp) cudaFree(ab.cub_tmp);
+    CATT_CUDA(cudaMalloc(&ab.cub_tmp, need));
+    ab.cub_tmp_bytes = need;
+  }
+  CATT_CUDA(cub::DeviceScan::ExclusiveSum(ab.cub_tmp, need, ab.ntask, ab.task_off, (int)(n + 1), st));
+  uint32_t total = 0;
+  CATT_CUDA(cudaMemcpyAsync(&total, ab.task_off + n, sizeof total, cudaMemcpyDeviceToHost, st));
+  CATT_CUDA(cudaStreamSynchronize(st));
+  *ntasks_out = total;
+  *launches += 1;
+  if ((int64_t)total > ab.cap_tasks) {
+    if (ab.tasks) cudaFree(ab.tasks);
+    if (ab.task_res) cudaFree(ab.task_res);
+    ab.cap_tasks = (int64_t)total + (int64_t)total / 8 + 1024;
+    CATT_CUDA(cudaMalloc(&ab.tasks, ab.cap_tasks * sizeof(SwTask)));
+    CATT_CUDA(cudaMalloc(&ab.task_res, ab.cap_tasks * 2 * sizeof(uint32_t)));
+  }
+  if (total > 0) {
+    expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ref, n, ab.candbits, ab.task_off, ab.tasks);
+    CATT_CUDA(cudaGetLastError());
+    *launches += 1;
+  }
+  return CATT_OK;
+}
+
+int launch_sw(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int64_t ntasks, int sm_count, cudaStream_t st, int* launches) {
+  if (ntasks == 0) return CATT_OK;
+  *launches += 1;
+  return dispatch_sw(ref, reads, ab.tasks, ntasks, ab.task_res, sm_count, st);
+}
+
+int launch_select(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int64_t first_ordinal, int min_score,
+                  cudaStream_t st, int* launches) {
+  if (reads.n == 0) return CATT_OK;
+  select_kernel<<<(unsigned)((reads.n + 127) / 128), 128, 0, st>>>(ref, reads, ab.tasks, ab.task_off, ab.task_res, first_ordinal,
+                                                                   min_score, ab.recs, ab.gapped_list, ab.counters);
+  CATT_CUDA(cudaGetLastError());
+  *launches += 1;
+  return CATT_OK;
+}
+
+int launch_traceback(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int64_t n_gapped, cudaStream_t st, int* launches) {
+  if (n_gapped == 0) return CATT_OK;
+  const size_t smem = (size_t)7 * (MAX_READ + 2) * sizeof(int16_t) + MAX_READ + (size_t)reads.max_len * ref.maxlen + 16;
+  if (smem > 220 * 1024) {
+    set_error("traceback tile (%zu bytes) exceeds shared memory", smem);
+    return CATT_E_LIMIT;
+  }
+  static size_t attr = 0;
+  if (smem > attr) { CATT_CUDA(cudaFuncSetAttribute(traceback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+  const int grid = (int)std::min<int64_t>(n_gapped, 148 * 8);
+  traceback_kernel<<<grid, 32, smem, st>>>(ref, reads, ab.gapped_list, n_gapped, ab.recs);
+  CATT_CUDA(cudaGetLastError());
+  *launches += 1;
+  return CATT_OK;
+}
+
+int launch_sw_pairs(const RefDev& ref, const ReadsDev& reads, const int32_t* d_rid, const int32_t* d_strand, int32_t* d_out3,
+                    int sm_count, cudaStream_t st) {
+  const int64_t n = reads.n;
+  if (n == 0) return CATT_OK;
+  SwTask* tasks = nullptr;
+  uint32_t* res = nullptr;
+  CATT_CUDA(cudaMalloc(&tasks, n * sizeof(SwTask)));
+  CATT_CUDA(cudaMalloc(&res, n * 2 * sizeof(uint32_t)));
+  make_pair_tasks<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, d_rid, d_strand, tasks);
+  int rc = dispatch_sw(ref, reads, tasks, n, res, sm_count, st);
+  if (rc == CATT_OK) {
+    unpack_pair_res<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, res, d_out3);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = cuda_fail(e, "sw_pairs", __FILE__, __LINE__);
+  }
+  cudaFree(tasks); cudaFree(res);
+  return rc;
+}
+
+int alu_peak(int sm_count, cudaStream_t st, double* ops_per_s, double* ms_out) {
+  uint32_t* d = nullptr;
+  CATT_CUDA(cudaMalloc(&d, 16));
+  const int iters = 4096, grid = sm_count * 8, block = 256;
+  cudaEvent_t e0, e1;
+  CATT_CUDA(cudaEventCreate(&e0)); CATT_CUDA(cudaEventCreate(&e1));
+  alu_peak_kernel<<<grid, block, 0, st>>>(d, 64);
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    CATT_CUDA(cudaEventRecord(e0, st));
+    alu_peak_kernel<<<grid, block, 0, st>>>(d, iters);
+    CATT_CUDA(cudaEventRecord(e1, st));
+    CATT_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    CATT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    best = std::min(best, ms);
+  }
+  const double ops = (double)grid * block * (double)iters * 16.0;   // packed s16x2 instructions (2 lanes each)
+  *ops_per_s = ops / (best * 1e-3);
+  *ms_out = best;
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  return CATT_OK;
+}
+
+}  // namespace catt

@@ -1,0 +1,268 @@
+"""Host-side mirror of the reference's interface for the CDR3 hot path, on top of the C ABI.
+
+The reference is Julia (absent from this image), so this layer is Python; INTEGRATION.md shows the equivalent
+`ccall` stubs for catt.jl.  Names and argument meaning follow the reference:
+
+  reference (catt.jl / Jtool.jl)                         here
+  ------------------------------------------------------------------------------------------
+  parsed_args + refg[species][chain][region]          -> Catt(species, chain, region, resource_dir, ...)
+  input_convert + read_alignrs + pool/extension part
+      of catt()   (catt.jl:134-151,186-339,544-577)   -> Catt.mainflow(path) / Catt.mainflow_reads(...)
+  Myread (Jtool.jl:12-19)                              -> Myread
+  selBestMatchD loop (catt.jl:676-683)                -> Catt.selBestMatchD(seqs)
+  the_ERR / args["kmer"] (catt.jl:26,162-171)         -> result.info["the_err"], result.info["kmer"]
+
+Everything computational happens in libcatt_b200.so on the GPU; this module only marshals buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from .refg import chain_config
+
+
+@dataclass
+class Myread:                      # Jtool.jl:12-19
+    seq: str
+    qual: str
+    vs: str
+    js: str
+    cdr3: str
+    able: bool
+    ordinal: int = -1
+    flags: int = 0
+
+
+class Result:
+    """Vpart / Jpart exactly as catt.jl:579 expects them, plus the log counters and per-read alignment records."""
+
+    def __init__(self, owner: "Catt", handle):
+        self._owner, self._h = owner, handle
+        L = _lib.load()
+        info = _lib.Info()
+        _lib.check(L.catt_result_info(handle, C.byref(info)))
+        self.info = info.as_dict()
+
+    def _part(self, which):
+        L = _lib.load()
+        p, n = C.POINTER(_lib.Read)(), C.c_int64()
+        _lib.check(L.catt_result_reads(self._h, which, C.byref(p), C.byref(n)))
+        vn, jn = self._owner.v_names, self._owner.j_names
+        out = []
+        for i in range(n.value):
+            r = p[i]
+            seq = C.string_at(r.seq, r.seq_len).decode()
+            qual = C.string_at(r.qual, r.qual_len).decode()
+            cdr3 = seq[r.cdr3_off:r.cdr3_off + r.cdr3_len] if r.cdr3_off >= 0 else "None"
+            out.append(Myread(seq, qual, vn[r.v_id] if r.v_id >= 0 else "None", jn[r.j_id] if r.j_id >= 0 else "None", cdr3,
+                              bool(r.able), r.ordinal, r.flags))
+        return out
+
+    @property
+    def Vpart(self):
+        return self._part(0)
+
+    @property
+    def Jpart(self):
+        return self._part(1)
+
+    def records(self, which) -> np.ndarray:
+        L = _lib.load()
+        p, n = C.c_void_p(), C.c_int64()
+        _lib.check(L.catt_align_records(self._h, which, C.byref(p), C.byref(n)))
+        if n.value == 0:
+            return np.zeros(0, dtype=_lib.ALN_DTYPE)
+        buf = (C.c_char * (n.value * _lib.ALN_DTYPE.itemsize)).from_address(p.value)
+        return np.frombuffer(buf, dtype=_lib.ALN_DTYPE).copy()
+
+    def close(self):
+        if self._h:
+            _lib.load().catt_result_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Batch:
+    """A shard of reads resident in HBM (bench.py / multi-GPU sharding)."""
+
+    def __init__(self, owner, handle, n):
+        self._owner, self._h, self.n = owner, handle, n
+
+    def align(self):
+        _lib.check(_lib.load().catt_batch_align(self._owner._h, self._h))
+
+    def sync(self) -> dict:
+        info = _lib.Info()
+        _lib.check(_lib.load().catt_batch_sync(self._owner._h, self._h, C.byref(info)))
+        return info.as_dict()
+
+    def download(self):
+        v = np.zeros(self.n, dtype=_lib.ALN_DTYPE)
+        j = np.zeros(self.n, dtype=_lib.ALN_DTYPE)
+        _lib.check(_lib.load().catt_batch_download(self._owner._h, self._h, v.ctypes.data, j.ctypes.data))
+        return v, j
+
+    def close(self):
+        if self._h:
+            _lib.load().catt_batch_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Catt:
+    """One CATT configuration bound to one GPU (catt_ctx)."""
+
+    def __init__(self, species="hs", chain="TRB", region="CDR3", resource_dir=None, bowsc=12, kmer=10000, thread=1,
+                 allow_v=3, allow_j=9, device=0, chain_cfg=None):
+        L = _lib.load()
+        cc = chain_cfg or chain_config(species, chain, region, resource_dir)
+        self.chain_cfg = cc
+        d = cc.get("Dregion", [])
+        self._keep = [(C.c_char_p * max(len(d), 1))(*[x[0].encode() for x in d]),
+                      (C.c_char_p * max(len(d), 1))(*[x[1].encode() for x in d])]
+        cfg = _lib.Config(cc["vregion"].encode(), cc["jregion"].encode(), cc["cmotif"].encode(), cc["fmotif"].encode(),
+                          cc["innerC"].encode(), cc["innerF"].encode(), cc["coffset"], cc["foffset"], bowsc, kmer, thread,
+                          allow_v, allow_j, device, len(d), self._keep[0], self._keep[1])
+        h = C.c_void_p()
+        _lib.check(L.catt_ctx_create(C.byref(h), C.byref(cfg)))
+        self._h = h
+        self.d_list = d
+        self.v_names = [L.catt_ref_name(h, 0, i).decode() for i in range(L.catt_ref_count(h, 0))]
+        self.j_names = [L.catt_ref_name(h, 1, i).decode() for i in range(L.catt_ref_count(h, 1))]
+
+    # -- reference records (alignment bases) -------------------------------------------------------------------
+    def ref_seq(self, which, i) -> str:
+        buf = C.create_string_buffer(1024)
+        n = _lib.load().catt_ref_seq(self._h, which, i, buf, 1024)
+        if n < 0:
+            _lib.check(n)
+        return buf.raw[:n].decode()
+
+    # -- the hot path ------------------------------------------------------------------------------------------
+    def mainflow(self, fastx_path: str) -> Result:
+        """input_convert + read_alignrs + pool/extension for one single-end file (catt.jl:767-768 up to :577)."""
+        h = C.c_void_p()
+        _lib.check(_lib.load().catt_run_file(self._h, fastx_path.encode(), C.byref(h)))
+        return Result(self, h)
+
+    def mainflow_reads(self, names, seqs, quals=None) -> Result:
+        nb, no = _lib.concat(names)
+        sb, so = _lib.concat(seqs)
+        qb = _lib.concat(quals)[0] if quals is not None else None
+        h = C.c_void_p()
+        _lib.check(_lib.load().catt_run_reads(self._h, len(seqs), nb, no.ctypes.data, sb, so.ctypes.data, qb, C.byref(h)))
+        return Result(self, h)
+
+    def mainflow_buffers(self, n, name_buf, name_off, seq_buf, seq_off, qual_buf) -> Result:
+        """Zero-copy variant for large inputs: bytes-like buffers + int64 offset arrays."""
+        h = C.c_void_p()
+        _lib.check(_lib.load().catt_run_reads(self._h, n, _addr(name_buf), name_off.ctypes.data, _addr(seq_buf), seq_off.ctypes.data,
+                                              _addr(qual_buf) if qual_buf is not None else None, C.byref(h)))
+        return Result(self, h)
+
+    def selBestMatchD(self, seqs):
+        """Jtool.jl:40-52 for a list of CDR3 nucleotide strings -> D segment names ("None" when nothing passes)."""
+        if not seqs:
+            return []
+        arr = (C.c_char_p * len(seqs))(*[s.encode() for s in seqs])
+        out = np.zeros(len(seqs), dtype=np.int32)
+        _lib.check(_lib.load().catt_best_d(self._h, arr, len(seqs), out.ctypes.data))
+        return ["None" if i < 0 else self.d_list[i][0] for i in out]
+
+    # -- stage level -------------------------------------------------------------------------------------------
+    def align_shard(self, seqs, first_ordinal=0):
+        sb, so = _lib.concat(seqs)
+        n = len(seqs)
+        v = np.zeros(n, dtype=_lib.ALN_DTYPE)
+        j = np.zeros(n, dtype=_lib.ALN_DTYPE)
+        _lib.check(_lib.load().catt_align_shard(self._h, n, sb, so.ctypes.data, first_ordinal, v.ctypes.data, j.ctypes.data))
+        return v, j
+
+    def align_shard_buffers(self, n, seq_buf, seq_off, first_ordinal=0):
+        v = np.zeros(n, dtype=_lib.ALN_DTYPE)
+        j = np.zeros(n, dtype=_lib.ALN_DTYPE)
+        _lib.check(_lib.load().catt_align_shard(self._h, n, _addr(seq_buf), seq_off.ctypes.data, first_ordinal, v.ctypes.data,
+                                                j.ctypes.data))
+        return v, j
+
+    def upload(self, n, seq_buf, seq_off, first_ordinal=0) -> Batch:
+        h = C.c_void_p()
+        _lib.check(_lib.load().catt_batch_upload(self._h, n, _addr(seq_buf), seq_off.ctypes.data, first_ordinal, C.byref(h)))
+        return Batch(self, h, n)
+
+    def assemble(self, names, seqs, quals, vrec, jrec) -> Result:
+        nb, no = _lib.concat(names)
+        sb, so = _lib.concat(seqs)
+        qb = _lib.concat(quals)[0] if quals is not None else None
+        h = C.c_void_p()
+        vrec = np.ascontiguousarray(vrec)
+        jrec = np.ascontiguousarray(jrec)
+        _lib.check(_lib.load().catt_assemble(self._h, len(seqs), nb, no.ctypes.data, sb, so.ctypes.data, qb, vrec.ctypes.data,
+                                             jrec.ctypes.data, C.byref(h)))
+        return Result(self, h)
+
+    def stream(self) -> int:
+        return _lib.load().catt_ctx_stream(self._h)
+
+    # -- parity hooks -------------------------------------------------------------------------------------------
+    def seed_candidates(self, which, seqs) -> np.ndarray:
+        sb, so = _lib.concat(seqs)
+        nrec = len(self.j_names if which else self.v_names)
+        out = np.zeros((len(seqs), nrec * 2), dtype=np.uint8)
+        _lib.check(_lib.load().catt_seed_candidates(self._h, which, len(seqs), sb, so.ctypes.data, out.ctypes.data))
+        return out
+
+    def sw_pairs(self, which, seqs, rid, strand) -> np.ndarray:
+        sb, so = _lib.concat(seqs)
+        rid = np.ascontiguousarray(rid, dtype=np.int32)
+        strand = np.ascontiguousarray(strand, dtype=np.int32)
+        out = np.zeros((len(seqs), 3), dtype=np.int32)
+        _lib.check(_lib.load().catt_sw_pairs(self._h, which, len(seqs), sb, so.ctypes.data, rid.ctypes.data, strand.ctypes.data,
+                                             out.ctypes.data))
+        return out
+
+    def finder(self, seqs, array_version=False) -> np.ndarray:
+        sb, so = _lib.concat(seqs)
+        out = np.zeros((len(seqs), 3), dtype=np.int32)
+        _lib.check(_lib.load().catt_finder(self._h, int(array_version), len(seqs), sb, so.ctypes.data, out.ctypes.data))
+        return out
+
+    def alu_peak(self):
+        ops, ms = C.c_double(), C.c_double()
+        _lib.check(_lib.load().catt_alu_peak(self._h, C.byref(ops), C.byref(ms)))
+        return ops.value, ms.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.load().catt_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _addr(buf):
+    if buf is None:
+        return None
+    if isinstance(buf, np.ndarray):
+        return buf.ctypes.data
+    if isinstance(buf, bytearray):
+        return C.addressof((C.c_char * len(buf)).from_buffer(buf))
+    return buf      # bytes: ctypes passes the address of the object's buffer for a c_void_p parameter

@@ -1,0 +1,174 @@
+/* catt_b200.h — C ABI of libcatt_b200.so, the B200-native replacement for CATT's per-read CDR3 extraction
+ * hot path.  Plain pointers and sizes only; no C++/torch types cross this boundary.
+ *
+ * The reference (GuoBioinfoLab/CATT, Julia) has no FFI for this path: today's boundary is a subprocess + SAM
+ * file (catt.jl:43-54) consumed by Julia functions.  Each entry point below cites the reference code it
+ * replaces; INTEGRATION.md shows the `ccall` stubs a maintainer adds to catt.jl.
+ *
+ * Conventions: every function returns 0 on success or a negative CATT_E_* code; catt_last_error() returns a
+ * thread-local message.  No exception crosses the ABI.  The library owns every buffer it returns until
+ * catt_result_free().  One context per (process, GPU); calls on a context are blocking and must not overlap.
+ * There is NO CPU fallback: without a usable CUDA device catt_ctx_create fails with CATT_E_CUDA.
+ */
+#ifndef CATT_B200_H
+#define CATT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CATT_OK 0
+#define CATT_E_ARG (-1)      /* bad argument / unsupported configuration (cf. catt.jl:712-722) */
+#define CATT_E_IO (-2)       /* unreadable FASTA/FASTQ (reference: Julia SystemError) */
+#define CATT_E_CUDA (-3)     /* no device, launch failure, out of device memory */
+#define CATT_E_LIMIT (-4)    /* input exceeds a compiled-in limit (read longer than CATT_MAX_READ_LEN, ...) */
+
+#define CATT_MAX_READ_LEN 512
+#define CATT_KMER_AUTO 10000 /* catt:18, catt.jl:156 */
+
+typedef struct catt_ctx catt_ctx;
+typedef struct catt_result catt_result;
+
+/* Everything read_alignrs()/catt() pull out of parsed_args and refg (catt.jl:187-205, 507-517; reference.jl). */
+typedef struct catt_config {
+  const char* v_fasta;      /* refg[..]["vregion"]; a sibling <fasta>.pac (bwa index) is used for N bases if present */
+  const char* j_fasta;      /* refg[..]["jregion"] */
+  const char* cmotif;       /* regex text, reference.jl */
+  const char* fmotif;
+  const char* inner_c;
+  const char* inner_f;
+  int32_t coffset;
+  int32_t foffset;
+  int32_t min_score;        /* args["bowsc"] -> bwa mem -T (catt.jl:43,145); default 12 */
+  int32_t kmer;             /* args["kmer"]; CATT_KMER_AUTO = adaptive (catt.jl:156-172) */
+  int32_t julia_nthreads;   /* Threads.nthreads(): fixes the record order of catt.jl:228,256-276 */
+  int32_t allow_v;          /* real_score allowance in assignV (catt.jl:100): 3 at HEAD, 0 reproduces the bundled golden */
+  int32_t allow_j;          /* real_score allowance in assignJ (catt.jl:121): 9 */
+  int32_t device;           /* CUDA device ordinal */
+  int32_t n_d;              /* refg[..]["Dregion"] length (0 = chain has no D segments) */
+  const char* const* d_names;
+  const char* const* d_seqs;
+} catt_config;
+
+/* One SAM-visible alignment record = the line `bwa mem | samtools ... | awk` would leave for one read against one
+ * reference set (catt.jl:43-51), reduced to the fields the Julia code reads (Jtool.jl:76-124, catt.jl:69-132). */
+typedef struct catt_aln {
+  int32_t ordinal;    /* 0-based read index in the input */
+  int32_t rid;        /* reference record index (RNAME), -1 if unmapped */
+  int16_t strand;     /* 1 = read was reverse-complemented (FLAG 16) */
+  int16_t mapped;     /* 1 if AS >= min_score */
+  int16_t as;         /* AS:i */
+  int16_t qb;         /* soft clip before the alignment; GetStartCigar = qb+1 */
+  int16_t m_end;      /* GetEndCigar: 1-based end of the first M block */
+  int16_t rb;         /* POS-1 (record-local) */
+  int16_t qe;         /* alignment end on the read (exclusive) */
+  int16_t re;         /* alignment end on the record (exclusive) */
+  int16_t nm;         /* NM:i */
+  int16_t mi;         /* sum of M and I lengths ("bases mapped (cigar)") */
+  int16_t ncand;      /* (record,strand) candidates scored for this read */
+  int16_t ntied;      /* candidates sharing the best score */
+} catt_aln;
+
+/* Myread (Jtool.jl:12-19) after finder!/extension. */
+typedef struct catt_read {
+  const char* seq;
+  const char* qual;
+  int32_t seq_len;
+  int32_t qual_len;     /* J-side reads carry a qual string of a different length (catt.jl:125-126) */
+  int32_t v_id;         /* index into the V reference names, -1 = "None" */
+  int32_t j_id;
+  int32_t cdr3_off;     /* 0-based offset of cdr3 in seq, -1 = "None" */
+  int32_t cdr3_len;
+  int32_t ordinal;      /* provenance: input read index */
+  uint8_t able;
+  uint8_t flags;        /* 1 V part read, 2 J part read, 4 both-mapped, 8 qual slice clipped (reference would throw) */
+  uint8_t pad_[2];
+} catt_read;
+
+/* The numbers the reference logs (catt.jl:331,503-524,580) plus work counters. */
+typedef struct catt_info {
+  int32_t kmer;               /* args["kmer"] after get_kmer_fromsam */
+  int32_t reserved_;
+  double the_err;             /* global the_ERR after get_err_fromsam (already %e-rounded) */
+  double avg_len;
+  int64_t n_reads, v_hits, j_hits, v_final, j_final, share, pair_seq_mismatch, full_pushed;
+  int64_t vpart, jpart, direct, left, rescued;
+  int64_t cand_v, cand_j;     /* scored (read, record, strand) pairs */
+  int64_t cells_v, cells_j;   /* DP cell updates: sum len(read) x len(record) */
+  int64_t gapped_v, gapped_j; /* winners that needed the traceback kernel */
+  int64_t kernel_launches;    /* CUDA kernels launched for this result */
+  double ms_seed, ms_sw, ms_select, ms_extract, ms_pool, ms_h2d, ms_d2h, ms_host;  /* device/host stage times */
+} catt_info;
+
+/* ---- lifecycle --------------------------------------------------------------------------------------------- */
+/* Loads the V/J references (what `bwa index` + FASTA.Reader do, catt.jl:198-205) and builds the device tables. */
+int catt_ctx_create(catt_ctx** out, const catt_config* cfg);
+void catt_ctx_destroy(catt_ctx* ctx);
+const char* catt_last_error(void);
+const char* catt_version(void);
+
+int catt_ref_count(const catt_ctx* ctx, int which /*0=V,1=J*/);
+const char* catt_ref_name(const catt_ctx* ctx, int which, int32_t id);      /* FASTA.identifier, catt.jl:202 */
+int catt_ref_seq(const catt_ctx* ctx, int which, int32_t id, char* out, int32_t cap); /* alignment bases; returns length */
+
+/* ---- the hot path ------------------------------------------------------------------------------------------- */
+/* Replaces input_convert (catt.jl:134-151) + read_alignrs (catt.jl:186-339) + the k-mer pool / extension /
+ * finder!(array) part of catt() (catt.jl:544-577) for one single-end FASTQ/FASTA(.gz) file. */
+int catt_run_file(catt_ctx* ctx, const char* fastx_path, catt_result** out);
+
+/* Same for reads already in host memory.  names/seqs/quals are concatenated, NOT NUL-terminated; *_off has n+1
+ * entries.  quals may be NULL (FASTA input).  Names are the raw header tokens; `/1` `/2` trimming is done inside. */
+int catt_run_reads(catt_ctx* ctx, int64_t n, const char* names, const int64_t* name_off, const char* seqs,
+                   const int64_t* seq_off, const char* quals, catt_result** out);
+
+int catt_result_info(const catt_result* r, catt_info* out);
+/* Vpart (which=0) / Jpart (1) in the reference's list order, ready for catt.jl:579 onwards. */
+int catt_result_reads(const catt_result* r, int which, const catt_read** reads, int64_t* n);
+/* Per-read alignment records (input order, one per read; unmapped reads have mapped=0): parity/diagnostics. */
+int catt_align_records(const catt_result* r, int which, const catt_aln** recs, int64_t* n);
+void catt_result_free(catt_result* r);
+
+/* Replaces the selBestMatchD loop (catt.jl:676-683, Jtool.jl:40-52): for each CDR3 string the index of the best D
+ * segment of the context's D list, or -1 for "None". */
+int catt_best_d(catt_ctx* ctx, const char* const* cdr3, int64_t n, int32_t* d_index_out);
+
+/* ---- stage-level entry points (sharding, benchmarks, parity tests) --------------------------------------------- */
+/* Stage A = map2align for a shard of reads: seeding + SW + hit selection.  `first_ordinal` is the global index of
+ * seqs[0] (bwa's hash tie-break uses the global read ordinal).  Writes n records per reference set. */
+int catt_align_shard(catt_ctx* ctx, int64_t n, const char* seqs, const int64_t* seq_off, int64_t first_ordinal,
+                     catt_aln* v_out, catt_aln* j_out);
+
+/* Device-resident variant used by bench.py: upload once, run Stage A repeatedly on the resident batch, read back. */
+typedef struct catt_batch catt_batch;
+int catt_batch_upload(catt_ctx* ctx, int64_t n, const char* seqs, const int64_t* seq_off, int64_t first_ordinal,
+                      catt_batch** out);
+int catt_batch_align(catt_ctx* ctx, catt_batch* b);                       /* async on the context's stream */
+int catt_batch_sync(catt_ctx* ctx, catt_batch* b, catt_info* stage_info); /* waits; fills counters and stage times */
+int catt_batch_download(catt_ctx* ctx, catt_batch* b, catt_aln* v_out, catt_aln* j_out);
+void catt_batch_free(catt_batch* b);
+/* The CUDA stream the context launches on, as an integer handle (cudaStream_t), for event timing by callers. */
+uint64_t catt_ctx_stream(const catt_ctx* ctx);
+
+/* Stage B = everything after the SAM files exist, given ALL reads of the sample and their records (gathered from
+ * the shards): ordering, dedup, V/J join, assignV/J, finder!, k-mer table, extension. */
+int catt_assemble(catt_ctx* ctx, int64_t n, const char* names, const int64_t* name_off, const char* seqs,
+                  const int64_t* seq_off, const char* quals, const catt_aln* v_recs, const catt_aln* j_recs,
+                  catt_result** out);
+
+/* ---- parity-test hooks (thin wrappers over single kernels) ----------------------------------------------------- */
+/* Seeding only: cand_out[n][2*nrec] bytes, 1 where (record,strand) survives bwa-mem's seed filters. */
+int catt_seed_candidates(catt_ctx* ctx, int which, int64_t n, const char* seqs, const int64_t* seq_off, uint8_t* cand_out);
+/* SW kernel only: score read i against record rid[i] on strand[i]; out[i] = {score, end_read, end_record}. */
+int catt_sw_pairs(catt_ctx* ctx, int which, int64_t n, const char* seqs, const int64_t* seq_off, const int32_t* rid,
+                  const int32_t* strand, int32_t* out3);
+/* finder! on raw nucleotide strings: out[i] = {able, cdr3_off (0-based, -1 none), cdr3_len}. */
+int catt_finder(catt_ctx* ctx, int array_version, int64_t n, const char* seqs, const int64_t* seq_off, int32_t* out3);
+/* Integer-ALU peak microbenchmark used as the DP roofline denominator: returns packed-s16x2 DPX op/s. */
+int catt_alu_peak(catt_ctx* ctx, double* dpx_ops_per_s, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CATT_B200_H */

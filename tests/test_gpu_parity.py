@@ -1,0 +1,255 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+Bit-exact: everything on this path is integer / byte / index work."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.util import myread_tuple, random_reads, revcomp, synth_reads
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+    return oracle
+
+
+@pytest.fixture(scope="module")
+def sample(fx):
+    names, seqs, quals = [], [], []
+    with open(os.path.join(fx, "testSample.fq")) as fh:
+        lines = fh.read().split("\n")
+    for i in range(0, len(lines) - 3, 4):
+        names.append(lines[i][1:].split()[0]); seqs.append(lines[i + 1]); quals.append(lines[i + 3])
+    assert len(seqs) == 7922
+    return names, seqs, quals
+
+
+@pytest.fixture(scope="module")
+def ctx(trb):
+    from catt_b200.host import Catt
+    c = Catt(chain_cfg=trb, device=0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def orefs(O, trb):
+    return O.RefSet(trb["vregion"]), O.RefSet(trb["jregion"])
+
+
+REC_KEYS = [("rid", "rid"), ("strand", "strand"), ("mapped", "mapped"), ("as", "AS"), ("qb", "qb"), ("m_end", "m_end"),
+            ("rb", "rb"), ("qe", "qe"), ("re", "re"), ("nm", "nm"), ("mi", "mi"), ("ncand", "ncand"), ("ntied", "ntied")]
+
+
+def assert_records_equal(gpu, ora, O):
+    cols = {k: i for i, k in enumerate(O.REC_FIELDS)}
+    mapped = ora[:, cols["mapped"]] == 1
+    assert np.array_equal(gpu["mapped"] == 1, mapped)
+    for gk, ok in REC_KEYS:
+        g, o = gpu[gk].astype(np.int64), ora[:, cols[ok]].astype(np.int64)
+        sel = mapped if gk not in ("mapped", "as", "ncand") else np.ones_like(mapped)
+        bad = np.nonzero((g != o) & sel)[0]
+        assert bad.size == 0, f"{gk}: {bad.size} mismatches, first at read {bad[:5]}: gpu {g[bad[:5]]} oracle {o[bad[:5]]}"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def test_sw_kernel_random_and_real_pairs(ctx, O, orefs, sample):
+    rng = np.random.default_rng(7)
+    seqs, rid, strand = [], [], []
+    V = orefs[0]
+    for s in sample[1][:1500]:                       # real reads against random records, both strands
+        seqs.append(s); rid.append(int(rng.integers(0, V.nrec))); strand.append(int(rng.integers(0, 2)))
+    recs = [V.record(i) for i in range(V.nrec)]
+    for i in range(1500):                            # mutated copies of records with indels
+        r = int(rng.integers(0, V.nrec))
+        t = list(recs[r])
+        for _ in range(int(rng.integers(0, 6))):
+            p = int(rng.integers(0, len(t)))
+            op = int(rng.integers(0, 3))
+            if op == 0: t[p] = "ACGT"[int(rng.integers(0, 4))]
+            elif op == 1: del t[p]
+            else: t.insert(p, "ACGT"[int(rng.integers(0, 4))])
+        s = "".join(random_reads(1, int(rng.integers(0, 40)), int(rng.integers(1 << 30)))[0:1]) + "".join(t) + \
+            random_reads(1, int(rng.integers(1, 40)), int(rng.integers(1 << 30)))[0]
+        sd = int(rng.integers(0, 2))
+        seqs.append(revcomp(s) if sd else s); rid.append(r); strand.append(sd)
+    out = ctx.sw_pairs(0, seqs, rid, strand)
+    for i, (s, r, sd) in enumerate(zip(seqs, rid, strand)):
+        q = revcomp(s) if sd else s
+        sc, qi, tj = O.sw(q, recs[r])
+        if sc == 0:
+            assert out[i, 0] == 0
+        else:
+            assert tuple(out[i]) == (sc, qi, tj), (i, tuple(out[i]), (sc, qi, tj))
+
+
+def test_sw_kernel_reads_with_n(ctx, O, orefs):
+    V = orefs[0]
+    rng = np.random.default_rng(11)
+    seqs, rid, strand = [], [], []
+    for i in range(300):
+        r = int(rng.integers(0, V.nrec))
+        t = list(V.record(r))
+        for _ in range(3):
+            t[int(rng.integers(0, len(t)))] = "N"
+        seqs.append("ACGTAC" + "".join(t) + "TTGACA"); rid.append(r); strand.append(0)
+    out = ctx.sw_pairs(0, seqs, rid, strand)
+    for i in range(300):
+        assert tuple(out[i]) == O.sw(seqs[i], V.record(rid[i]))
+
+
+@pytest.mark.parametrize("which", [0, 1])
+def test_seeding_matches_bwa_model(ctx, orefs, sample, which):
+    gpu = ctx.seed_candidates(which, sample[1])
+    ora = orefs[which].seed(sample[1])
+    bad = np.nonzero((gpu != ora).any(axis=1))[0]
+    assert bad.size == 0, f"{bad.size} reads differ, first {bad[:5]}"
+    assert int(ora.sum()) == (4137 if which else 54840)
+
+
+def test_alignment_records_testsample(ctx, O, orefs, sample):
+    v, j = ctx.align_shard(sample[1])
+    assert_records_equal(v, orefs[0].align(sample[1]), O)
+    assert_records_equal(j, orefs[1].align(sample[1]), O)
+    assert int(v["mapped"].sum()) == 2653 and int(j["mapped"].sum()) == 1752
+
+
+def test_first_ordinal_shifts_the_tie_break(ctx, O, orefs, sample):
+    """bwa's hash tie-break uses the GLOBAL read ordinal: a shard must reproduce it through first_ordinal."""
+    sub = sample[1][3000:3800]
+    v, _ = ctx.align_shard(sub, first_ordinal=3000)
+    assert_records_equal(v, orefs[0].align(sub, first_ordinal=3000), O)
+
+
+@pytest.mark.parametrize("allow_v,threads", [(0, 1), (3, 1), (3, 4)])
+def test_end_to_end_testsample(trb, fx, O, orefs, sample, allow_v, threads):
+    from catt_b200.host import Catt
+    from oracle import downstream as D
+    c = Catt(chain_cfg=trb, allow_v=allow_v, thread=threads)
+    res = c.mainflow(os.path.join(fx, "testSample.fq"))
+    ref = O.run_file(orefs[0], orefs[1], O.make_config(trb, allow_v=allow_v, nthreads=threads), os.path.join(fx, "testSample.fq"))
+    assert [myread_tuple(r) for r in res.Vpart] == [myread_tuple(r) for r in ref.Vpart]
+    assert [myread_tuple(r) for r in res.Jpart] == [myread_tuple(r) for r in ref.Jpart]
+    for k in ("kmer", "v_hits", "j_hits", "v_final", "j_final", "share", "pair_seq_mismatch", "full_pushed", "vpart", "jpart",
+              "direct", "left", "rescued", "cand_v", "cand_j", "cells_v", "cells_j"):
+        assert res.info[k] == ref.info[k], (k, res.info[k], ref.info[k])
+    assert res.info["the_err"] == ref.info["the_err"]
+    assert res.info["gapped_v"] == ref.info["v_gapped"] and res.info["gapped_j"] == ref.info["j_gapped"]
+    if allow_v == 0:      # the reference's own golden output, through the unchanged-Julia stand-in
+        gold, _ = D.load_golden_csv(os.path.join(fx, "aha.TRB.CDR3.CATT.csv"))
+        dnames = c.selBestMatchD
+        tab = D.clonotype_table(res.Vpart, res.Jpart, res.info["the_err"], trb["Dregion"], lambda nn, dl: dnames([nn])[0])
+        assert tab == gold
+    c.close()
+
+
+def test_selbestmatchd_golden(ctx, fx):
+    from oracle import downstream as D
+    gold, _ = D.load_golden_csv(os.path.join(fx, "aha.TRB.CDR3.CATT.csv"))
+    keys = list(gold)
+    got = ctx.selBestMatchD([k[1] for k in keys])
+    assert got == [k[4] for k in keys]
+
+
+@pytest.mark.parametrize("length,n", [(150, 6000), (100, 3000), (50, 3000)])
+def test_synthetic_trb_end_to_end(ctx, O, orefs, trb, length, n):
+    V, J = orefs
+    vrecs = [V.record(i) for i in range(V.nrec)]
+    jrecs = [J.record(i) for i in range(J.nrec)]
+    names, seqs, quals = synth_reads(n, vrecs, jrecs, length, with_n=True)
+    v, j = ctx.align_shard(seqs)
+    assert_records_equal(v, V.align(seqs), O)
+    assert_records_equal(j, J.align(seqs), O)
+    res = ctx.mainflow_reads(names, seqs, quals)
+    ref = O.run_mem(V, J, O.make_config(trb), names, seqs, quals)
+    assert [myread_tuple(r) for r in res.Vpart] == [myread_tuple(r) for r in ref.Vpart]
+    assert [myread_tuple(r) for r in res.Jpart] == [myread_tuple(r) for r in ref.Jpart]
+    for k in ("kmer", "vpart", "jpart", "direct", "left", "rescued"):
+        assert res.info[k] == ref.info[k], (k, res.info[k], ref.info[k])
+    assert res.info["the_err"] == ref.info["the_err"]
+
+
+@pytest.mark.parametrize("species,chain", [("hs", "TRA"), ("hs", "IGH"), ("hs", "TRG"), ("hs", "TRD"), ("ms", "TRB"), ("pig", "TRB")])
+def test_other_chains(fx, O, species, chain):
+    from catt_b200.host import Catt
+    from catt_b200.refg import chain_config
+    cc = chain_config(species, chain, "CDR3", os.path.join(fx, "resource"))
+    V, J = O.RefSet(cc["vregion"]), O.RefSet(cc["jregion"])
+    vrecs = [V.record(i) for i in range(V.nrec)]
+    jrecs = [J.record(i) for i in range(J.nrec)]
+    names, seqs, quals = synth_reads(1500, vrecs, jrecs, 150, seed=99)
+    c = Catt(chain_cfg=cc)
+    v, j = c.align_shard(seqs)
+    assert_records_equal(v, V.align(seqs), O)
+    assert_records_equal(j, J.align(seqs), O)
+    res = c.mainflow_reads(names, seqs, quals)
+    ref = O.run_mem(V, J, O.make_config(cc), names, seqs, quals)
+    assert [myread_tuple(r) for r in res.Vpart] == [myread_tuple(r) for r in ref.Vpart]
+    assert [myread_tuple(r) for r in res.Jpart] == [myread_tuple(r) for r in ref.Jpart]
+    if "Dregion" in cc:
+        cd = [r.cdr3 for r in res.Vpart if r.cdr3 != "None"][:200]
+        assert c.selBestMatchD(cd) == [O.best_d(s, cc["Dregion"]) for s in cd]
+    c.close()
+
+
+def test_finder_hook(ctx, O, trb, sample):
+    cfg = O.make_config(trb)
+    seqs = [s for s in sample[1][:1200] if "N" not in s]
+    for arr in (False, True):
+        out = ctx.finder(seqs, array_version=arr)
+        for i, s in enumerate(seqs):
+            able, rng_ = O.finder(cfg, s, arr)
+            assert bool(out[i, 0]) == able, (i, arr)
+            if rng_ is None:
+                assert out[i, 1] == -1
+            else:
+                assert (out[i, 1] + 1, out[i, 1] + out[i, 2]) == rng_, (i, arr, out[i], rng_)
+
+
+def test_edge_cases(ctx, O, orefs, trb):
+    from catt_b200 import _lib
+    # empty input
+    res = ctx.mainflow_reads([], [], [])
+    assert res.info["n_reads"] == 0 and res.Vpart == [] and res.Jpart == []
+    # reads shorter than a seed, all-N reads, ragged lengths, the maximum length
+    V = orefs[0]
+    rec = V.record(5)
+    seqs = ["ACGT", "N" * 30, rec[:9], rec[:10], rec, rec + "ACGT" * 100, ("ACGT" * 128)[:512], revcomp(rec) + "GG"]
+    names = [f"e{i}" for i in range(len(seqs))]
+    quals = ["I" * len(s) for s in seqs]
+    v, j = ctx.align_shard(seqs)
+    assert_records_equal(v, V.align(seqs), O)
+    assert_records_equal(j, orefs[1].align(seqs), O)
+    res = ctx.mainflow_reads(names, seqs, quals)
+    ref = O.run_mem(orefs[0], orefs[1], O.make_config(trb), names, seqs, quals)
+    assert [myread_tuple(r) for r in res.Vpart] == [myread_tuple(r) for r in ref.Vpart]
+    # longer than the compiled-in limit: loud error, not truncation
+    with pytest.raises(_lib.CattError) as ei:
+        ctx.align_shard(["A" * 513])
+    assert ei.value.code == -4
+
+
+def test_mate_names_collapse(ctx, O, orefs, trb, sample):
+    """/1 and /2 mates share a trimmed QNAME: the awk dedup keeps one record per name and SEQ-mismatching V/J pairs drop."""
+    names, seqs, quals = sample
+    idx = list(range(0, 600)) + list(range(4200, 4800))
+    n, s, q = [names[i] for i in idx], [seqs[i] for i in idx], [quals[i] for i in idx]
+    res = ctx.mainflow_reads(n, s, q)
+    ref = O.run_mem(orefs[0], orefs[1], O.make_config(trb), n, s, q)
+    assert [myread_tuple(r) for r in res.Vpart] == [myread_tuple(r) for r in ref.Vpart]
+    assert [myread_tuple(r) for r in res.Jpart] == [myread_tuple(r) for r in ref.Jpart]
+    assert res.info["pair_seq_mismatch"] == ref.info["pair_seq_mismatch"]
+
+
+def test_stage_split_equals_whole(ctx, trb, sample):
+    """catt_align_shard over two shards + catt_assemble == catt_run_reads (the multi-GPU decomposition)."""
+    names, seqs, quals = [x[:3000] for x in sample]
+    whole = ctx.mainflow_reads(names, seqs, quals)
+    v1, j1 = ctx.align_shard(seqs[:1700], first_ordinal=0)
+    v2, j2 = ctx.align_shard(seqs[1700:], first_ordinal=1700)
+    res = ctx.assemble(names, seqs, quals, np.concatenate([v1, v2]), np.concatenate([j1, j2]))
+    assert [myread_tuple(r) for r in res.Vpart] == [myread_tuple(r) for r in whole.Vpart]
+    assert [myread_tuple(r) for r in res.Jpart] == [myread_tuple(r) for r in whole.Jpart]
