@@ -42,6 +42,14 @@ __device__ __forceinline__ uint64_t hash_64(uint64_t key) {   // bwa's tie-break
   return key;
 }
 
+// prmt.b32 in its generic form: selector nibble = byte index (0..7) | 8 to replicate that byte's sign bit instead.
+// (__byte_perm() only honours 3 bits per nibble, so the sign-replicating form needs the raw instruction.)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+
 // SAM-oriented base of a packed read: strand 1 = reverse complement
 __device__ __forceinline__ uint32_t read_code(const uint32_t* __restrict__ w, const uint32_t* __restrict__ nm, int len, int i, int strand) {
   const int p = strand ? len - 1 - i : i;
@@ -83,7 +91,7 @@ __device__ __forceinline__ void sw_row(uint32_t (&Hp)[C], uint32_t (&E)[C], cons
                                        uint32_t sel, uint32_t& hd, uint32_t& f, uint32_t& rowbest) {
   #pragma unroll
   for (int c = 0; c < C; c++) {
-    const uint32_t s = NROW ? NEG1 : __byte_perm(tabA[c], tabB[c], sel);
+    const uint32_t s = NROW ? NEG1 : prmt(tabA[c], tabB[c], sel);
     const uint32_t e = E[c];
     uint32_t h = __viaddmax_s16x2_relu(hd, s, e);        // max(H(i-1,j-1)+s, E(i,j), 0)
     h = __vimax_s16x2_relu(h, f);                            // ... and F(i,j)

@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from tests.util import myread_tuple, random_reads, revcomp, synth_reads
+from util import myread_tuple, random_reads, revcomp, synth_reads
 
 pytestmark = pytest.mark.gpu
 
