@@ -1,0 +1,266 @@
+#!/usr/bin/env python3
+"""bench.py — reads/s and DP GCUPS of the CDR3 extraction hot path on synthetic hs-TRB reads (BASELINE.json configs[2]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--reads-per-step R] [--length 150] [--impl gpu|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A step = one pass of the whole hot path (seeding, SW, selection, ordering/dedup, assign/finder, k-mer table, extension)
+over one batch of R synthetic 150-bp reads per GPU (SURVEY §8d config-3 generator, read i drawn from splitmix64(seed+i)).
+  value : reads/s with the packed batch already resident in HBM (catt_batch_align + catt_batch_assemble)
+  e2e   : reads/s through the public call catt_run_reads with HOST buffers (packing, H2D, all kernels, D2H, host glue)
+  roofline : the SW kernel against the measured integer-ALU (packed DPX add-max) issue peak of this GPU
+  cpu_baseline : the CPU oracle (OpenMP restatement of the reference path, not the Julia program) on a bounded sample
+With N > 1 every rank runs its own shard of R reads (weak scaling, shards are independent samples, no data-path collective).
+`--impl reference` times the CPU restatement on all host cores on the same workload (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tarfile
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 20251019
+
+
+def fixture_dir():
+    d = tempfile.mkdtemp(prefix="catt_bench_")
+    with tarfile.open(os.path.join(ROOT, "tests", "golden", "catt_fixture.tar.gz")) as tar:
+        tar.extractall(d)
+    return d
+
+
+class ClockSampler(threading.Thread):
+    """SM clocks / throttle reasons during the timed region, sampled in-process through NVML (nvidia_ml_py): forking
+    nvidia-smi every 200 ms from a multi-GB process stalls the CUDA driver calls of the step being timed."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu_index, [], False
+
+    def run(self):
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].isdigit() else self.gpu
+            h = N.nvmlDeviceGetHandleByIndex(idx)
+            mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+        except Exception:
+            return
+        bits = {"hw_slowdown": getattr(N, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(N, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(N, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(N, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
+            try:
+                sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+                try:
+                    rs = N.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((sm, mx, [k for k, b in bits.items() if rs & b]))
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(r[0] for r in self.rows)
+        reasons = sorted({x for r in self.rows for x in r[2]})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.rows[0][1] if self.rows else None, "reasons": reasons,
+                "samples": len(self.rows), "how": "NVML in-process, 200 ms period, during both timed regions"}
+
+
+def cpu_reference_run(fx, length, n_sample, first_index=0):
+    """The CPU restatement (oracle) on n_sample reads with all host threads; returns (reads/s, seconds, info)."""
+    from catt_b200.refg import chain_config
+    from oracle import oracle as O
+    cc = chain_config("hs", "TRB", "CDR3", os.path.join(fx, "resource"))
+    V, J = O.RefSet(cc["vregion"]), O.RefSet(cc["jregion"])
+    seqs, quals = O.synth_reads(V, J, n_sample, length, first_index=first_index, seed=SEED)
+    cfg = O.make_config(cc)
+    t0 = time.perf_counter()
+    R = O.run_flat(V, J, cfg, seqs, quals, first_index=first_index)
+    dt = time.perf_counter() - t0
+    return n_sample / dt, dt, R.info
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--reads-per-step", type=int, default=2_000_000)
+    ap.add_argument("--length", type=int, default=150)
+    ap.add_argument("--impl", default="gpu", choices=["gpu", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU-baseline sample (0 = auto, ~15 s)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+    workload = f"synthetic hs TRB {args.length}bp reads from IMGT V/J with random CDR3 insertions (BASELINE configs[2], SURVEY 8d config 3)"
+
+    # ------------------------------------------------------------------------------------------------- reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        fx = fixture_dir()
+        import __graft_entry__ as g
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+        n = args.cpu_sample or max(2000, 600 * cores)          # ~ a few seconds per step on `cores` threads
+        for i in range(args.warmup):
+            cpu_reference_run(fx, args.length, max(1000, n // 8), first_index=i * n)
+        t_tot, cells = 0.0, 0
+        for i in range(args.steps):
+            rps, dt, info = cpu_reference_run(fx, args.length, n, first_index=i * n)
+            t_tot += dt
+            cells += info["cells_v"] + info["cells_j"]
+        value = n * args.steps / t_tot
+        line = {"impl": "reference", "metric": "reads_per_sec", "value": value, "unit": "reads/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+                "gcups": cells / t_tot / 1e9,
+                "config": {"workload": workload, "reads_per_step": n, "read_length": args.length, "chain": "hs TRB",
+                           "note": "CPU restatement of the reference path (oracle, OpenMP) - the Julia+bwa+samtools program cannot run here"},
+                "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": "port",
+                                 "sample": f"{args.steps} x {n} reads of the same generator"},
+                "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------------------------------------------- GPU arm
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: libcatt_b200 has no CPU fallback"}))
+        return 2
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    from catt_b200.host import Catt
+    from catt_b200.refg import chain_config
+    fx = fixture_dir()
+    cc = chain_config("hs", "TRB", "CDR3", os.path.join(fx, "resource"))
+    ctx = Catt(chain_cfg=cc, device=local_rank)
+    R = args.reads_per_step
+    first = rank * R
+    name_buf, name_off, seq_buf, seq_off, qual_buf = ctx.synth_reads(R, args.length, first_index=first, seed=SEED)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
+
+    peak_ops, peak_ms = ctx.alu_peak()            # packed DPX add-max thread-instructions per second
+
+    # ---- value: batch resident in HBM
+    batch = ctx.upload(R, seq_buf, seq_off, first_ordinal=first)
+
+    def step_resident():
+        batch.align()
+        res = batch.assemble(name_buf, name_off, seq_buf, seq_off, qual_buf)
+        info = res.info
+        res.close()
+        return info
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record(stream)
+    infos = [step_resident() for _ in range(args.steps)]
+    ev1.record(stream)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    ev_ms = ev0.elapsed_time(ev1)
+    dev_ms = max(wall_ms, ev_ms)
+
+    # ---- e2e: host buffers through the public call
+    def step_e2e():
+        res = ctx.mainflow_buffers(R, name_buf, name_off, seq_buf, seq_off, qual_buf)
+        info = res.info
+        res.close()
+        return info
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_infos = [step_e2e() for _ in range(args.steps)]
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    info = infos[-1]
+    cells = info["cells_v"] + info["cells_j"]
+    sw_ms = sum(i["ms_sw"] for i in infos) / len(infos)
+    achieved = 12.0 * cells / (sw_ms * 1e-3)                    # algorithmic int ops/s (12 per cell)
+    peak = peak_ops * 4.0                                       # a packed add-max retires 2 adds + 2 max per thread-instruction
+    ei = e2e_infos[-1]
+    packed_bytes = R * (4 * ((args.length + 15) // 16 + (args.length + 31) // 32) + 8)
+    h2d = packed_bytes + 24 * (ei["v_final"] + ei["j_final"]) + 20 * (ei["vpart"] + ei["jpart"]) + 4 * ei["left"]
+    d2h = 2 * 32 * R + 16 * (ei["v_final"] + ei["j_final"]) + 160 * ei["left"]
+
+    line = {
+        "metric": "reads_per_sec", "value": world * R * args.steps / (dev_ms * 1e-3), "unit": "reads/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+        "config": {"workload": workload, "reads_per_step_per_gpu": R, "read_length": args.length, "chain": "hs TRB",
+                   "l2": f"packed batch {packed_bytes >> 20} MiB per step vs 126 MB L2" + (" (larger than L2)" if packed_bytes > 126e6 else " (compute-bound kernel; see DESIGN.md)"),
+                   "multi_gpu": "shards are independent samples; no data-path collective"},
+        "gcups": world * cells / (sw_ms * 1e-3) / 1e9,
+        "gcups_note": "DP cell updates / SW-kernel time (CUDA events in the library), summed over GPUs",
+        "stage_ms": {k: sum(i[k] for i in infos) / len(infos) for k in ("ms_seed", "ms_sw", "ms_select", "ms_extract", "ms_pool", "ms_d2h", "ms_host")},
+        "timing": {"wall_ms_per_step": wall_ms / args.steps, "cuda_event_ms_per_step": ev_ms / args.steps},
+        "e2e": {"value": world * R * args.steps / (e2e_ms * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(sum(i["kernel_launches"] for i in infos)),
+        "clocks": sampler.summary(),
+        "roofline": {"bound": "alu", "kernel": "sw_score_kernel<8,13> (V) + <4,8> (J)", "achieved": achieved / 1e12, "peak": peak / 1e12,
+                     "unit": "Tiop/s", "frac": achieved / peak, "traffic": None,
+                     "note": "achieved = 12 int ops x DP cells / SW kernel time; peak = measured packed-DPX (VIADDMNMX.S16x2) issue rate x 4 "
+                             f"int16 ops per thread-instruction ({peak_ops / 1e12:.2f} T thread-instr/s, this GPU, in-repo microbenchmark); "
+                             "MEASURED_PEAKS.json has no integer entry"},
+        "counters": {k: info[k] for k in ("v_hits", "j_hits", "vpart", "jpart", "direct", "left", "rescued", "cand_v", "cand_j", "gapped_v")},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+        n = args.cpu_sample or max(4000, 1500 * cores)
+        rps, dt, cinfo = cpu_reference_run(fx, args.length, n)
+        line["cpu_baseline"] = {"value": rps, "unit": "reads/s", "cores": cores, "kind": "port",
+                                "sample": f"first {n} reads of the same generator, {dt:.1f} s; CPU restatement (oracle, OpenMP), not the Julia program",
+                                "gcups": (cinfo["cells_v"] + cinfo["cells_j"]) / dt / 1e9}
+    if rank == 0:
+        print(json.dumps(line))
+    batch.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -52,7 +52,7 @@ EXPORTS = ["catt_ctx_create", "catt_ctx_destroy", "catt_last_error", "catt_versi
            "catt_ref_seq", "catt_run_file", "catt_run_reads", "catt_result_info", "catt_result_reads", "catt_align_records",
            "catt_result_free", "catt_best_d", "catt_align_shard", "catt_batch_upload", "catt_batch_align", "catt_batch_sync",
            "catt_batch_download", "catt_batch_free", "catt_ctx_stream", "catt_assemble", "catt_seed_candidates", "catt_sw_pairs",
-           "catt_finder", "catt_alu_peak"]
+           "catt_finder", "catt_alu_peak", "catt_batch_assemble", "catt_synth_reads"]
 
 _lib = None
 
@@ -96,6 +96,8 @@ def load():
     L.catt_seed_candidates.argtypes = [vp, C.c_int, C.c_int64, vp, vp, vp]
     L.catt_sw_pairs.argtypes = [vp, C.c_int, C.c_int64, vp, vp, vp, vp, vp]
     L.catt_finder.argtypes = [vp, C.c_int, C.c_int64, vp, vp, vp]
+    L.catt_batch_assemble.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]
+    L.catt_synth_reads.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, C.c_uint64, C.c_double, C.c_int32, vp, vp, vp, vp]
     L.catt_alu_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _lib = L
     return L

@@ -1,26 +1,14 @@
-// api.cu — the C ABI of libcatt_b200 (include/catt_b200.h): context, Stage A (map2align on the GPU), Stage B
-// (read_alignrs + pool/extension) and result assembly.
-//
-// Host-side logic restated here (none of it is a CPU fallback for a kernel — it is the glue the reference does
-// with samtools/awk/Julia containers between the stages):
-//   * `samtools sort -t AS | view -F 2308 | tac | awk '!a[$1]++'` (catt.jl:45-48): descending (AS, tid, pos, strand)
-//     order, later input first on complete ties, first record per trimmed QNAME            [SURVEY A7]
-//   * get_kmer_fromsam / get_err_fromsam (catt.jl:153-184) as samtools stats prints them   [SURVEY A8]
-//   * share_name, the NR % nthreads chunk order, the name-sorted both-mapped pairing (catt.jl:221-319)
-//   * Myread string materialisation (catt.jl:104,125-126,302-304; Jtool.jl:364-365; catt.jl:378-379,420-421).
+// api.cu — the C ABI of libcatt_b200 (include/catt_b200.h): context, Stage A driver (map2align on the GPU), FASTQ input,
+// stage-level and parity entry points.  Stage B lives in assemble.cu.
 #include <stdio.h>
 #include <string.h>
-#include <zlib.h>
 
 #include <algorithm>
-#include <chrono>
 #include <memory>
 #include <string>
-#include <string_view>
-#include <unordered_map>
 #include <vector>
 
-#include "internal.cuh"
+#include "host_types.h"
 
 namespace catt {
 const char* last_error();
@@ -29,42 +17,7 @@ bool slurp_file(const std::string& path, std::string& out);
 
 using namespace catt;
 
-struct DeviceReads {
-  uint32_t* words = nullptr; uint32_t* off = nullptr; int32_t* len = nullptr;
-  int64_t n = 0; int max_len = 0;
-  ReadsDev view() const { return ReadsDev{words, off, len, n, max_len}; }
-  void release() { cudaFree(words); cudaFree(off); cudaFree(len); words = nullptr; off = nullptr; len = nullptr; }
-};
-
-struct catt_ctx {
-  RefSet V, J;
-  FinderDev finder{};
-  FinderDev* d_finder = nullptr;
-  int min_score = 12, kmer = CATT_KMER_AUTO, nthreads = 1, allow_v = 3, allow_j = 9, device = 0, sm_count = 148;
-  cudaStream_t stream = nullptr;
-  std::vector<std::string> d_names, d_seqs;
-  char* d_dseq = nullptr; int32_t* d_doff = nullptr;
-  AlignBuffers ab[2];
-  cudaEvent_t ev[8]{};
-};
-
-struct catt_batch {
-  DeviceReads dr;
-  int64_t first_ordinal = 0;
-  int64_t ntasks[2] = {0, 0};
-  catt_info info{};
-};
-
-struct catt_result {
-  catt_info info{};
-  std::vector<catt_read> part[2];
-  std::vector<catt_aln> rec[2];
-  std::vector<std::unique_ptr<std::string>> arena;
-};
-
 namespace {
-
-double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 int upload_reads(const PackedReads& pr, int64_t n, DeviceReads* dr, cudaStream_t st) {
   dr->n = n; dr->max_len = pr.max_len;
@@ -96,7 +49,7 @@ void free_align_buffers(AlignBuffers& ab) {
   ab = AlignBuffers{};
 }
 
-// Stage A for one reference set; records stay in ab.recs.  stage_ms[0..2] = seed, sw, select+traceback (device, ms).
+// Stage A for one reference set; the records stay in ab.recs.
 int align_refset(catt_ctx* c, int which, const ReadsDev& reads, int64_t first_ordinal, catt_info* info, int* launches) {
   RefSet& rs = which ? c->J : c->V;
   AlignBuffers& ab = c->ab[which];
@@ -177,277 +130,13 @@ int parse_fastx(const std::string& path, HostReads* hr) {
   return CATT_OK;
 }
 
-inline std::string_view trimmed_name(const HostReads& hr, int64_t i) {       // bwa trim_readno
-  const char* s = hr.names + hr.name_off[i];
-  size_t l = (size_t)(hr.name_off[i + 1] - hr.name_off[i]);
-  if (l > 2 && s[l - 2] == '/' && s[l - 1] >= '0' && s[l - 1] <= '9') l -= 2;
-  return std::string_view(s, l);
-}
-
-inline char sam_base(const HostReads& hr, int64_t r, int len, int i, int strand) {
-  const char* s = hr.seqs + hr.seq_off[r];
-  static const char NT[] = "ACGTN";
-  if (!strand) return NT[nt_code(s[i])];
-  const uint8_t c = nt_code(s[len - 1 - i]);
-  return c > 3 ? 'N' : NT[3 - c];
-}
-
-bool sam_seq_equal(const HostReads& hr, int64_t r1, int s1, int64_t r2, int s2) {
-  const int l1 = (int)(hr.seq_off[r1 + 1] - hr.seq_off[r1]), l2 = (int)(hr.seq_off[r2 + 1] - hr.seq_off[r2]);
-  if (l1 != l2) return false;
-  if (r1 == r2 && s1 == s2) return true;
-  for (int i = 0; i < l1; i++) if (sam_base(hr, r1, l1, i, s1) != sam_base(hr, r2, l2, i, s2)) return false;
-  return true;
-}
-
-// final SAM list of one reference set
-void final_order(const std::vector<catt_aln>& recs, const HostReads& hr, std::vector<int64_t>& fin) {
-  std::vector<std::pair<uint64_t, int64_t>> keyed;
-  for (int64_t i = 0; i < (int64_t)recs.size(); i++) {
-    const catt_aln& a = recs[i];
-    if (!a.mapped) continue;
-    const uint64_t k = ((uint64_t)(uint16_t)a.as << 48) | ((uint64_t)(uint16_t)a.rid << 32) | ((uint64_t)(uint16_t)a.rb << 16) | (uint64_t)(a.strand & 1);
-    keyed.emplace_back(k, i);
+int download_records(catt_ctx* c, int64_t n, catt_result* R) {
+  for (int which = 0; which < 2; which++) {
+    R->rec[which].resize(n);
+    const double td = now_ms();
+    CATT_CUDA(cudaMemcpy(R->rec[which].data(), c->ab[which].recs, n * sizeof(catt_aln), cudaMemcpyDeviceToHost));
+    R->info.ms_d2h += now_ms() - td;
   }
-  // ascending stable sort then reverse == descending by (key, input index)
-  std::sort(keyed.begin(), keyed.end(), [](const std::pair<uint64_t, int64_t>& x, const std::pair<uint64_t, int64_t>& y) {
-    return x.first != y.first ? x.first > y.first : x.second > y.second;
-  });
-  std::unordered_map<std::string_view, char> seen;
-  seen.reserve(keyed.size() * 2);
-  fin.clear();
-  for (auto& kv : keyed)
-    if (seen.emplace(trimmed_name(hr, kv.second), 1).second) fin.push_back(kv.second);
-}
-
-void chunk_order(const std::vector<int64_t>& fin, int T, std::vector<int64_t>& out) {    // catt.jl:228,256-276
-  out.clear();
-  if (T <= 1) { out = fin; return; }
-  for (int p = 0; p < T; p++)
-    for (size_t nr = 1; nr <= fin.size(); nr++)
-      if ((int)(nr % T) == p) out.push_back(fin[nr - 1]);
-}
-
-const char* arena_str(catt_result* R, std::string&& s) {
-  R->arena.emplace_back(new std::string(std::move(s)));
-  return R->arena.back()->c_str();
-}
-
-struct Pending {            // a Myread under construction on the host
-  int64_t read; int kind, strand; int seq_off, seq_len, cdr3_off, cdr3_len; int v_id, j_id;
-  int q_start1, j_pad;      // J part: qual = qual[1:start-1] * 'G'^j_pad
-  bool able;
-};
-
-int stage_b(catt_ctx* c, const HostReads& hr, const DeviceReads& dr, catt_result* R, int* launches) {
-  catt_info& info = R->info;
-  const std::vector<catt_aln>&vrec = R->rec[0], &jrec = R->rec[1];
-  const double t0 = now_ms();
-  std::vector<int64_t> vfin, jfin;
-  final_order(vrec, hr, vfin);
-  final_order(jrec, hr, jfin);
-  info.v_final = (int64_t)vfin.size(); info.j_final = (int64_t)jfin.size();
-  // get_kmer_fromsam / get_err_fromsam on the final V list, as samtools stats prints them
-  int k = c->kmer;
-  {
-    uint64_t tot = 0, nm = 0, mi = 0;
-    for (int64_t i : vfin) { tot += (uint64_t)(hr.seq_off[i + 1] - hr.seq_off[i]); nm += (uint64_t)vrec[i].nm; mi += (uint64_t)vrec[i].mi; }
-    const float avg = vfin.empty() ? 0.f : (float)(tot / (uint64_t)vfin.size());    // samtools: integer division, printed %.0f
-    char buf[64];
-    snprintf(buf, sizeof buf, "%.0f", avg);
-    const double avg_r = atof(buf);
-    info.avg_len = avg_r;
-    if (k == CATT_KMER_AUTO) {
-      if (avg_r >= 50) k = 15;
-      if (avg_r >= 75) k = 19;
-      if (avg_r >= 100) k = 23;
-      if (avg_r >= 150) k = 25;
-    }
-    const float er = mi ? (float)nm / (float)mi : 0.f;
-    snprintf(buf, sizeof buf, "%e", (double)er);
-    info.the_err = atof(buf);
-    if (!(info.the_err == info.the_err)) info.the_err = 0.0;
-  }
-  info.kmer = k;
-  // share_name = QNAMEs present in both final lists
-  std::unordered_map<std::string_view, int64_t> vname;
-  vname.reserve(vfin.size() * 2);
-  for (int64_t i : vfin) vname.emplace(trimmed_name(hr, i), i);
-  std::unordered_map<std::string_view, std::pair<int64_t, int64_t>> share;   // name -> (V read, J read)
-  for (int64_t j : jfin) {
-    auto it = vname.find(trimmed_name(hr, j));
-    if (it != vname.end()) share.emplace(it->first, std::make_pair(it->second, j));
-  }
-  info.share = (int64_t)share.size();
-  // work items in the reference's processing order
-  std::vector<ExtractItem> items;
-  std::vector<Pending> pend;
-  std::vector<int64_t> order;
-  auto add_part = [&](int which) {
-    const std::vector<catt_aln>& recs = which ? jrec : vrec;
-    chunk_order(which ? jfin : vfin, c->nthreads, order);
-    for (int64_t i : order) {
-      if (share.count(trimmed_name(hr, i))) continue;
-      const catt_aln& a = recs[i];
-      ExtractItem it{};
-      it.read = (uint32_t)i; it.kind = (int16_t)which; it.strand = a.strand; it.qb = a.qb; it.m_end = a.m_end; it.rb = a.rb; it.rid = (int16_t)a.rid;
-      items.push_back(it);
-      Pending p{};
-      p.read = i; p.kind = which; p.strand = a.strand; p.v_id = which ? -1 : a.rid; p.j_id = which ? a.rid : -1;
-      p.q_start1 = a.qb + 1; p.j_pad = which ? (c->J.len[a.rid] - (a.rb + 1)) : 0;
-      pend.push_back(p);
-    }
-  };
-  add_part(0);
-  const size_t n_vpart_items = items.size();
-  add_part(1);
-  const size_t n_jpart_end = items.size();
-  // both-mapped reads: sorted by name (stable: V record then J record), SEQ equality, clipping V start .. J first-M end
-  {
-    std::vector<std::pair<std::string_view, std::pair<int64_t, int64_t>>> pairs(share.begin(), share.end());
-    std::sort(pairs.begin(), pairs.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
-    for (auto& pr : pairs) {
-      const int64_t vi = pr.second.first, ji = pr.second.second;
-      const catt_aln &a = vrec[vi], &b = jrec[ji];
-      if (!sam_seq_equal(hr, vi, a.strand, ji, b.strand)) { info.pair_seq_mismatch++; continue; }
-      ExtractItem it{};
-      it.read = (uint32_t)vi; it.kind = 2; it.strand = a.strand; it.qb = a.qb; it.m_end = a.m_end; it.rb = a.rb; it.rid = (int16_t)a.rid;
-      it.j_m_end = b.m_end; it.j_rid = (int16_t)b.rid;
-      items.push_back(it);
-      Pending p{};
-      p.read = vi; p.kind = 2; p.strand = a.strand; p.v_id = a.rid; p.j_id = b.rid; p.q_start1 = a.qb + 1;
-      pend.push_back(p);
-    }
-  }
-  const int64_t n_items = (int64_t)items.size();
-  info.ms_host += now_ms() - t0;
-  // ---- K5 on the device
-  cudaStream_t st = c->stream;
-  ExtractItem* d_items = nullptr; ExtractOut* d_eout = nullptr;
-  std::vector<ExtractOut> eout(n_items);
-  CATT_CUDA(cudaEventRecord(c->ev[5], st));
-  if (n_items) {
-    CATT_CUDA(cudaMalloc(&d_items, n_items * sizeof(ExtractItem)));
-    CATT_CUDA(cudaMalloc(&d_eout, n_items * sizeof(ExtractOut)));
-    CATT_CUDA(cudaMemcpyAsync(d_items, items.data(), n_items * sizeof(ExtractItem), cudaMemcpyHostToDevice, st));
-    int rc = launch_extract(c->V.dev, c->J.dev, dr.view(), c->d_finder, d_items, d_eout, n_items, k, c->allow_v, c->allow_j, st, launches);
-    if (rc) return rc;
-    CATT_CUDA(cudaMemcpyAsync(eout.data(), d_eout, n_items * sizeof(ExtractOut), cudaMemcpyDeviceToHost, st));
-  }
-  CATT_CUDA(cudaEventRecord(c->ev[6], st));
-  CATT_CUDA(cudaStreamSynchronize(st));
-  cudaFree(d_items); cudaFree(d_eout);
-  { float ms = 0; cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]); info.ms_extract += ms; }
-  // ---- Vpart = kept V part reads, then kept both-mapped reads; Jpart = kept J part reads
-  const double t1 = now_ms();
-  std::vector<Pending> lists[2];
-  for (int64_t i = 0; i < n_items; i++) {
-    if (!eout[i].status) continue;
-    Pending p = pend[i];
-    p.seq_off = eout[i].seq_off; p.seq_len = eout[i].seq_len; p.cdr3_off = eout[i].cdr3_off; p.cdr3_len = eout[i].cdr3_len; p.able = eout[i].able != 0;
-    const bool is_j = (size_t)i >= n_vpart_items && (size_t)i < n_jpart_end;
-    if (!is_j && (size_t)i < n_vpart_items) lists[0].push_back(p);
-    else if (is_j) lists[1].push_back(p);
-  }
-  for (int64_t i = (int64_t)n_jpart_end; i < n_items; i++) {
-    if (!eout[i].status) continue;
-    Pending p = pend[i];
-    p.seq_off = eout[i].seq_off; p.seq_len = eout[i].seq_len; p.cdr3_off = eout[i].cdr3_off; p.cdr3_len = eout[i].cdr3_len; p.able = eout[i].able != 0;
-    lists[0].push_back(p);
-    info.full_pushed++;
-  }
-  info.vpart = (int64_t)lists[0].size(); info.jpart = (int64_t)lists[1].size();
-  // ---- K6/K7: pool + extension of the partial reads
-  std::vector<PoolItem> pitems;
-  std::vector<uint32_t> partial;
-  for (int side = 0; side < 2; side++)
-    for (const Pending& p : lists[side]) {
-      PoolItem pi{};
-      pi.read = (uint32_t)p.read; pi.strand = (int16_t)p.strand; pi.seq_off = (int16_t)p.seq_off; pi.seq_len = (int16_t)p.seq_len;
-      pi.side = (int16_t)side; pi.order = (uint32_t)pitems.size(); pi.partial = p.cdr3_off < 0;
-      if (pi.partial) partial.push_back((uint32_t)pitems.size()); else info.direct++;
-      pitems.push_back(pi);
-    }
-  info.left = (int64_t)partial.size();
-  info.ms_host += now_ms() - t1;
-  std::vector<ExtendOut> xout(partial.size());
-  if (!pitems.empty() && k <= 31 && !partial.empty()) {
-    uint64_t slots = 1024;
-    while (slots < pitems.size() * 11ull * 2ull) slots <<= 1;
-    KmerTable tab{};
-    PoolItem* d_pi = nullptr; uint32_t* d_partial = nullptr; ExtendOut* d_xout = nullptr;
-    CATT_CUDA(cudaEventRecord(c->ev[5], st));
-    CATT_CUDA(cudaMalloc(&tab.keys, slots * sizeof(unsigned long long)));
-    CATT_CUDA(cudaMalloc(&tab.vals, slots * sizeof(unsigned long long)));
-    tab.mask = slots - 1;
-    CATT_CUDA(cudaMemsetAsync(tab.keys, 0xff, slots * sizeof(unsigned long long), st));
-    CATT_CUDA(cudaMemsetAsync(tab.vals, 0, slots * sizeof(unsigned long long), st));
-    CATT_CUDA(cudaMalloc(&d_pi, pitems.size() * sizeof(PoolItem)));
-    CATT_CUDA(cudaMalloc(&d_partial, partial.size() * sizeof(uint32_t)));
-    CATT_CUDA(cudaMalloc(&d_xout, partial.size() * sizeof(ExtendOut)));
-    CATT_CUDA(cudaMemcpyAsync(d_pi, pitems.data(), pitems.size() * sizeof(PoolItem), cudaMemcpyHostToDevice, st));
-    CATT_CUDA(cudaMemcpyAsync(d_partial, partial.data(), partial.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    int rc = launch_pool(dr.view(), d_pi, (int64_t)pitems.size(), k, tab, st, launches);
-    if (!rc) rc = launch_extend(dr.view(), c->d_finder, d_pi, d_partial, (int64_t)partial.size(), k, tab, d_xout, st, launches);
-    if (rc) return rc;
-    CATT_CUDA(cudaMemcpyAsync(xout.data(), d_xout, partial.size() * sizeof(ExtendOut), cudaMemcpyDeviceToHost, st));
-    CATT_CUDA(cudaEventRecord(c->ev[6], st));
-    CATT_CUDA(cudaStreamSynchronize(st));
-    { float ms = 0; cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]); info.ms_pool += ms; }
-    cudaFree(tab.keys); cudaFree(tab.vals); cudaFree(d_pi); cudaFree(d_partial); cudaFree(d_xout);
-  } else {
-    for (auto& x : xout) { x.n_ext = 0; x.cdr3_off = -1; x.cdr3_len = 0; x.able = 1; }
-  }
-  // ---- materialise Myread strings
-  const double t2 = now_ms();
-  static const char NT[] = "ACGT";
-  size_t pidx = 0, xi = 0;
-  for (int side = 0; side < 2; side++) {
-    R->part[side].reserve(lists[side].size());
-    for (const Pending& p : lists[side]) {
-      const PoolItem& pi = pitems[pidx++];
-      const int len = (int)(hr.seq_off[p.read + 1] - hr.seq_off[p.read]);
-      std::string seq((size_t)p.seq_len, 'N');
-      for (int i = 0; i < p.seq_len; i++) seq[i] = sam_base(hr, p.read, len, p.seq_off + i, p.strand);
-      // quality in SAM orientation
-      const char* q = hr.quals ? hr.quals + hr.seq_off[p.read] : nullptr;
-      auto sq = [&](int i) { return q ? (p.strand ? q[len - 1 - i] : q[i]) : 'I'; };
-      std::string qual;
-      if (p.kind == 1) {                                   // catt.jl:126
-        for (int i = 0; i < p.q_start1 - 1; i++) qual.push_back(sq(i));
-        qual.append((size_t)std::max(0, p.j_pad), 'G');
-      } else {
-        for (int i = 0; i < p.seq_len; i++) qual.push_back(sq(p.seq_off + i));
-      }
-      int c_off = p.cdr3_off, c_len = p.cdr3_len;
-      if (pi.partial) {
-        const ExtendOut& x = xout[xi++];
-        if (x.n_ext > 0) {
-          std::string add((size_t)x.n_ext, 'A');
-          for (int i = 0; i < x.n_ext; i++) add[i] = NT[x.ext[i] & 3];
-          if (side == 0) { seq += add; qual.append((size_t)x.n_ext, 'G'); }
-          else { std::reverse(add.begin(), add.end()); seq = add + seq; qual = std::string((size_t)x.n_ext, 'G') + qual; }
-        }
-        c_off = x.cdr3_off; c_len = x.cdr3_len;
-        if (c_off >= 0) info.rescued++;
-      }
-      uint8_t flags = (uint8_t)(p.kind == 0 ? 1 : p.kind == 1 ? 2 : 4);
-      if (c_off >= 0) {                                    // rd.qual = rd.qual[range] (Jtool.jl:365,383)
-        std::string qn;
-        for (int i = c_off; i < c_off + c_len; i++) {
-          if (i < (int)qual.size()) qn.push_back(qual[i]); else { qn.push_back('G'); flags |= 8; }   // reference: BoundsError
-        }
-        qual.swap(qn);
-      }
-      catt_read rd{};
-      rd.seq_len = (int32_t)seq.size(); rd.qual_len = (int32_t)qual.size();
-      rd.seq = arena_str(R, std::move(seq)); rd.qual = arena_str(R, std::move(qual));
-      rd.v_id = p.v_id; rd.j_id = p.j_id; rd.cdr3_off = c_off; rd.cdr3_len = c_off >= 0 ? c_len : 0;
-      rd.ordinal = (int32_t)p.read; rd.able = 1; rd.flags = flags;
-      R->part[side].push_back(rd);
-    }
-  }
-  info.ms_host += now_ms() - t2;
   return CATT_OK;
 }
 
@@ -466,15 +155,8 @@ int run_all(catt_ctx* c, const HostReads& hr, catt_result** out) {
   CATT_CUDA(cudaStreamSynchronize(c->stream));
   { float ms = 0; cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]); R->info.ms_h2d += ms; }
   R->info.n_reads = hr.n;
-  for (int which = 0; which < 2 && rc == CATT_OK; which++) {
-    rc = align_refset(c, which, dr.view(), 0, &R->info, &launches);
-    if (rc) break;
-    R->rec[which].resize(hr.n);
-    const double td = now_ms();
-    cudaError_t e = cudaMemcpy(R->rec[which].data(), c->ab[which].recs, hr.n * sizeof(catt_aln), cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) rc = cuda_fail(e, "records D2H", __FILE__, __LINE__);
-    R->info.ms_d2h += now_ms() - td;
-  }
+  for (int which = 0; which < 2 && rc == CATT_OK; which++) rc = align_refset(c, which, dr.view(), 0, &R->info, &launches);
+  if (rc == CATT_OK) rc = download_records(c, hr.n, R.get());
   if (rc == CATT_OK) rc = stage_b(c, hr, dr, R.get(), &launches);
   dr.release();
   if (rc) return rc;
@@ -484,6 +166,14 @@ int run_all(catt_ctx* c, const HostReads& hr, catt_result** out) {
 }
 
 std::string dup(const char* s) { return s ? std::string(s) : std::string(); }
+
+inline uint64_t sm64(uint64_t& s) {
+  s += 0x9E3779B97F4A7C15ull;
+  uint64_t z = s;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
 
 }  // namespace
 
@@ -547,6 +237,7 @@ void catt_ctx_destroy(catt_ctx* c) {
   cudaSetDevice(c->device);
   c->V.release(); c->J.release();
   free_align_buffers(c->ab[0]); free_align_buffers(c->ab[1]);
+  for (auto& b : c->sb) b.release();
   cudaFree(c->d_finder); cudaFree(c->d_dseq); cudaFree(c->d_doff);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -598,7 +289,7 @@ int catt_align_records(const catt_result* r, int which, const catt_aln** recs, i
   *recs = r->rec[which].data(); *n = (int64_t)r->rec[which].size();
   return CATT_OK;
 }
-void catt_result_free(catt_result* r) { delete r; }
+void catt_result_free(catt_result* r) { Trace tr; delete r; tr.lap("result_free"); }
 
 int catt_best_d(catt_ctx* c, const char* const* cdr3, int64_t n, int32_t* out) {
   if (!c || !out || (n > 0 && !cdr3)) return CATT_E_ARG;
@@ -643,9 +334,11 @@ int catt_batch_align(catt_ctx* c, catt_batch* b) {
   b->info = catt_info{};
   b->info.n_reads = b->dr.n;
   int launches = 0, rc;
-  // the J records must survive the V pass and vice versa: each reference set has its own buffers
-  for (int which = 0; which < 2; which++)
+  Trace tr;
+  for (int which = 0; which < 2; which++) {
     if ((rc = align_refset(c, which, b->dr.view(), b->first_ordinal, &b->info, &launches))) return rc;
+    tr.lap(which ? "align J" : "align V");
+  }
   b->info.kernel_launches = launches;
   return CATT_OK;
 }
@@ -699,6 +392,95 @@ int catt_assemble(catt_ctx* c, int64_t n, const char* names, const int64_t* name
   if (rc) return rc;
   R->info.kernel_launches = launches;
   *out = R.release();
+  return CATT_OK;
+}
+
+// Stage B on a batch that is already resident in HBM and aligned (catt_batch_align): used for the device-resident
+// throughput number.  The host buffers are still needed for QNAME dedup and to materialise the Myread strings.
+int catt_batch_assemble(catt_ctx* c, catt_batch* b, const char* names, const int64_t* name_off, const char* seqs,
+                        const int64_t* seq_off, const char* quals, catt_result** out) {
+  if (!c || !b || !out) { set_error("catt_batch_assemble: bad argument"); return CATT_E_ARG; }
+  CATT_CUDA(cudaSetDevice(c->device));
+  const int64_t n = b->dr.n;
+  HostReads hr;
+  hr.n = n; hr.names = names; hr.name_off = name_off; hr.seqs = seqs; hr.seq_off = seq_off; hr.quals = quals;
+  std::unique_ptr<catt_result> R(new catt_result());
+  R->info = b->info;
+  Trace tr;
+  int rc = download_records(c, n, R.get());
+  if (rc) return rc;
+  tr.lap("records D2H");
+  int launches = (int)b->info.kernel_launches;
+  rc = stage_b(c, hr, b->dr, R.get(), &launches);
+  tr.lap("stage_b total");
+  if (rc) return rc;
+  R->info.kernel_launches = launches;
+  *out = R.release();
+  return CATT_OK;
+}
+
+// Synthetic read generator of SURVEY 8d config 3 (benchmarks and tests; tests/util.py holds the same algorithm in Python):
+// read i draws from splitmix64 seeded with seed+i, so any rank can generate its own shard.  Fixed-length output.
+int catt_synth_reads(const catt_ctx* c, int64_t n, int64_t first_index, int32_t length, uint64_t seed, double p_err, int32_t with_n,
+                     char* seqs, char* quals, char* names, int64_t* name_off) {
+  if (!c || !seqs || !quals || length < 20 || length > CATT_MAX_READ_LEN) { set_error("catt_synth_reads: bad argument"); return CATT_E_ARG; }
+  const RefSet &V = c->V, &J = c->J;
+  const int perr = (int)(p_err * 100000);
+  static const char NT[] = "ACGT";
+  #pragma omp parallel for schedule(static)
+  for (int64_t r = 0; r < n; r++) {
+    uint64_t st = seed + (uint64_t)(first_index + r);
+    auto below = [&](uint64_t m) { return sm64(st) % m; };
+    char tpl[1024];
+    int tl = 0;
+    const int vi = (int)below(V.names.size()), ji = (int)below(J.names.size());
+    const int vlen = V.len[vi] - (int)below(7);
+    const int jtrim = (int)below(7);
+    const int nins = (int)below(19);
+    char ins[32];
+    for (int k = 0; k < nins; k++) ins[k] = NT[below(4)];
+    for (int k = 0; k < 60; k++) tpl[tl++] = NT[below(4)];
+    char post[120];
+    for (int k = 0; k < 120; k++) post[k] = NT[below(4)];
+    const int v0 = tl;
+    for (int k = 0; k < vlen; k++) tpl[tl++] = NT[V.T[V.off[vi] + k]];
+    const int v1 = tl;
+    for (int k = 0; k < nins; k++) tpl[tl++] = ins[k];
+    const int j0 = tl;
+    for (int k = jtrim; k < J.len[ji]; k++) tpl[tl++] = NT[J.T[J.off[ji] + k]];
+    const int j1 = tl;
+    for (int k = 0; k < 120; k++) tpl[tl++] = post[k];
+    int start = 0;
+    for (int t = 0; t < 64; t++) {
+      start = (int)below((uint64_t)std::max(1, tl - length + 1));
+      const int en = start + length;
+      const int ovv = std::max(0, std::min(en, v1) - std::max(start, v0)), ovj = std::max(0, std::min(en, j1) - std::max(start, j0));
+      if (ovv >= 20 || ovj >= 12) break;
+    }
+    char* s = seqs + r * (int64_t)length;
+    char* q = quals + r * (int64_t)length;
+    for (int k = 0; k < length; k++) {
+      s[k] = start + k < tl ? tpl[start + k] : 'A';
+      q[k] = 'I';
+      const int x = (int)below(100000);
+      if (x < perr) { s[k] = NT[below(4)]; q[k] = '#'; }
+      else if (x < 5000 + perr) q[k] = 'G';
+    }
+    if (with_n && below(50) == 0) s[below((uint64_t)length)] = 'N';
+    if (below(2)) {
+      auto comp = [](char ch) { return ch == 'A' ? 'T' : ch == 'C' ? 'G' : ch == 'G' ? 'C' : ch == 'T' ? 'A' : 'N'; };
+      for (int a = 0, b2 = length - 1; a <= b2; a++, b2--) {
+        const char ca = comp(s[a]), cb = comp(s[b2]);
+        s[a] = cb; s[b2] = ca;
+        const char qa = q[a]; q[a] = q[b2]; q[b2] = qa;
+      }
+    }
+  }
+  if (names && name_off) {
+    int64_t o = 0;
+    for (int64_t r = 0; r < n; r++) { name_off[r] = o; o += snprintf(names + o, 24, "s%lld", (long long)(first_index + r)); }
+    name_off[n] = o;
+  }
   return CATT_OK;
 }
 

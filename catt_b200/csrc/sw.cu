@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(256) alu_peak_kernel(uint32_t* out, int iters)
     #pragma unroll
     for (int k = 0; k < 8; k++) a[k] = __viaddmax_s16x2(a[k], b, c);
     #pragma unroll
-    for (int k = 0; k < 8; k++) a[k] = __vimax_s16x2_relu(a[k], a[(k + 1) & 7] ^ c);
+    for (int k = 0; k < 8; k++) a[k] = __viaddmax_s16x2_relu(a[k], c, a[(k + 1) & 7]);
   }
   uint32_t s = 0;
   #pragma unroll

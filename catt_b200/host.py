@@ -111,6 +111,12 @@ class Batch:
         _lib.check(_lib.load().catt_batch_download(self._owner._h, self._h, v.ctypes.data, j.ctypes.data))
         return v, j
 
+    def assemble(self, name_buf, name_off, seq_buf, seq_off, qual_buf) -> "Result":
+        h = C.c_void_p()
+        _lib.check(_lib.load().catt_batch_assemble(self._owner._h, self._h, _addr(name_buf), name_off.ctypes.data, _addr(seq_buf),
+                                                   seq_off.ctypes.data, _addr(qual_buf), C.byref(h)))
+        return Result(self._owner, h)
+
     def close(self):
         if self._h:
             _lib.load().catt_batch_free(self._h)
@@ -214,6 +220,17 @@ class Catt:
         _lib.check(_lib.load().catt_assemble(self._h, len(seqs), nb, no.ctypes.data, sb, so.ctypes.data, qb, vrec.ctypes.data,
                                              jrec.ctypes.data, C.byref(h)))
         return Result(self, h)
+
+    def synth_reads(self, n, length=150, first_index=0, seed=20251019, p_err=0.003, with_n=False):
+        """SURVEY §8d config-3 generator.  Returns (name_buf, name_off, seq_buf, seq_off, qual_buf) as numpy arrays."""
+        seqs = np.empty(n * length, dtype=np.uint8)
+        quals = np.empty(n * length, dtype=np.uint8)
+        names = np.zeros(n * 24 + 24, dtype=np.uint8)
+        name_off = np.zeros(n + 1, dtype=np.int64)
+        _lib.check(_lib.load().catt_synth_reads(self._h, n, first_index, length, seed, p_err, int(with_n), seqs.ctypes.data,
+                                                quals.ctypes.data, names.ctypes.data, name_off.ctypes.data))
+        seq_off = np.arange(n + 1, dtype=np.int64) * length
+        return names, name_off, seqs, seq_off, quals
 
     def stream(self) -> int:
         return _lib.load().catt_ctx_stream(self._h)

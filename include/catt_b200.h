@@ -157,6 +157,15 @@ int catt_assemble(catt_ctx* ctx, int64_t n, const char* names, const int64_t* na
                   const int64_t* seq_off, const char* quals, const catt_aln* v_recs, const catt_aln* j_recs,
                   catt_result** out);
 
+/* Stage B on a resident, aligned batch (inputs already in HBM); host buffers are used for QNAME dedup and strings. */
+int catt_batch_assemble(catt_ctx* ctx, catt_batch* b, const char* names, const int64_t* name_off, const char* seqs,
+                        const int64_t* seq_off, const char* quals, catt_result** out);
+
+/* Synthetic read generator of the benchmark workload: read i is drawn from splitmix64(seed+i) from the
+ * context's V/J records; fixed length; seqs/quals hold n*length bytes; names ("s<i>", up to 24 bytes each) + n+1 offsets. */
+int catt_synth_reads(const catt_ctx* ctx, int64_t n, int64_t first_index, int32_t length, uint64_t seed, double p_err,
+                     int32_t with_n, char* seqs, char* quals, char* names, int64_t* name_off);
+
 /* ---- parity-test hooks (thin wrappers over single kernels) ----------------------------------------------------- */
 /* Seeding only: cand_out[n][2*nrec] bytes, 1 where (record,strand) survives bwa-mem's seed filters. */
 int catt_seed_candidates(catt_ctx* ctx, int which, int64_t n, const char* seqs, const int64_t* seq_off, uint8_t* cand_out);

@@ -1182,6 +1182,78 @@ void* co_run_mem(void* vref, void* jref, const co_config* c, int64_t n, const ch
   return run_pipeline(*(RefSet*)vref, *(RefSet*)jref, cf, reads, omp_threads, 0);
 }
 
+// Synthetic reads of SURVEY §8d config 3 (same algorithm as tests/util.py::synth_read): fixed length, read i drawn from
+// splitmix64(seed + i).  seqs/quals: n*length bytes.  Lets the CPU baseline build its own input without the GPU library.
+int co_synth_reads(void* vref, void* jref, int64_t n, int64_t first_index, int length, uint64_t seed, double p_err, int with_n,
+                   char* seqs, char* quals) {
+  const RefSet &V = *(RefSet*)vref, &J = *(RefSet*)jref;
+  const int perr = (int)(p_err * 100000);
+  #pragma omp parallel for schedule(static)
+  for (int64_t r = 0; r < n; r++) {
+    uint64_t st = seed + (uint64_t)(first_index + r);
+    auto below = [&](uint64_t m) {
+      st += 0x9E3779B97F4A7C15ull;
+      uint64_t z = st;
+      z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+      z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+      return (z ^ (z >> 31)) % m;
+    };
+    std::string tpl, ins, pre, post;
+    const int vi = (int)below(V.names.size()), ji = (int)below(J.names.size());
+    const int vlen = V.len[vi] - (int)below(7);
+    const int jtrim = (int)below(7);
+    const int nins = (int)below(19);
+    for (int k = 0; k < nins; k++) ins.push_back(NT[below(4)]);
+    for (int k = 0; k < 60; k++) pre.push_back(NT[below(4)]);
+    for (int k = 0; k < 120; k++) post.push_back(NT[below(4)]);
+    tpl = pre;
+    const int v0 = (int)tpl.size();
+    for (int k = 0; k < vlen; k++) tpl.push_back(NT[V.T[V.off[vi] + k]]);
+    const int v1 = (int)tpl.size();
+    tpl += ins;
+    const int j0 = (int)tpl.size();
+    for (int k = jtrim; k < J.len[ji]; k++) tpl.push_back(NT[J.T[J.off[ji] + k]]);
+    const int j1 = (int)tpl.size();
+    tpl += post;
+    int start = 0;
+    for (int t = 0; t < 64; t++) {
+      start = (int)below((uint64_t)std::max(1, (int)tpl.size() - length + 1));
+      const int en = start + length;
+      const int ovv = std::max(0, std::min(en, v1) - std::max(start, v0)), ovj = std::max(0, std::min(en, j1) - std::max(start, j0));
+      if (ovv >= 20 || ovj >= 12) break;
+    }
+    char* s = seqs + r * (int64_t)length;
+    char* q = quals + r * (int64_t)length;
+    for (int k = 0; k < length; k++) {
+      s[k] = start + k < (int)tpl.size() ? tpl[start + k] : 'A';
+      q[k] = 'I';
+      const int x = (int)below(100000);
+      if (x < perr) { s[k] = NT[below(4)]; q[k] = '#'; }
+      else if (x < 5000 + perr) q[k] = 'G';
+    }
+    if (with_n && below(50) == 0) s[below((uint64_t)length)] = 'N';
+    if (below(2)) {
+      std::string t(s, length);
+      for (int k = 0; k < length; k++) { uint8_t c = nt_code(t[length - 1 - k]); s[k] = c > 3 ? 'N' : NT[3 - c]; }
+      std::reverse(q, q + length);
+    }
+  }
+  return 0;
+}
+
+// whole pipeline on fixed-length reads held in flat buffers (names "s<first_index+i>")
+void* co_run_flat(void* vref, void* jref, const co_config* c, int64_t n, int64_t first_index, int length, const char* seqs,
+                  const char* quals, int omp_threads) {
+  std::vector<Read> reads((size_t)n);
+  for (int64_t i = 0; i < n; i++) {
+    reads[i].name = "s" + std::to_string(first_index + i);
+    reads[i].seq.assign(seqs + i * (int64_t)length, length);
+    reads[i].qual.assign(quals + i * (int64_t)length, length);
+  }
+  Config cf = make_config(c);
+  return run_pipeline(*(RefSet*)vref, *(RefSet*)jref, cf, reads, omp_threads, 0);
+}
+
 void co_result_free(void* r) { delete (RunResult*)r; }
 
 // info as doubles: see python binding for the field order

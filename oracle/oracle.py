@@ -239,3 +239,22 @@ def global_affine(a: str, b: str) -> int:
 def best_d(cdr3: str, dlist) -> str:
     i = lib().co_best_d(cdr3.encode(), len(dlist), _strarr([d[1] for d in dlist]))
     return "None" if i < 0 else dlist[i][0]
+
+
+def synth_reads(vref: RefSet, jref: RefSet, n, length=150, first_index=0, seed=20251019, p_err=0.003, with_n=False):
+    """SURVEY §8d config-3 generator (C++ twin of tests/util.py::synth_read).  Returns (seqs, quals) uint8 arrays [n, length]."""
+    L = lib()
+    L.co_synth_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_uint64, C.c_double, C.c_int,
+                                 C.c_void_p, C.c_void_p]
+    seqs = np.empty((n, length), dtype=np.uint8)
+    quals = np.empty((n, length), dtype=np.uint8)
+    L.co_synth_reads(vref.h, jref.h, n, first_index, length, seed, p_err, int(with_n), seqs.ctypes.data, quals.ctypes.data)
+    return seqs, quals
+
+
+def run_flat(vref: RefSet, jref: RefSet, cfg: CoConfig, seqs: np.ndarray, quals: np.ndarray, first_index=0, threads=0) -> RunResult:
+    L = lib()
+    L.co_run_flat.restype = C.c_void_p
+    L.co_run_flat.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(CoConfig), C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    n, length = seqs.shape
+    return RunResult(L.co_run_flat(vref.h, jref.h, C.byref(cfg), n, first_index, length, seqs.ctypes.data, quals.ctypes.data, threads))
