@@ -144,21 +144,29 @@ int run_all(catt_ctx* c, const HostReads& hr, catt_result** out) {
   std::unique_ptr<catt_result> R(new catt_result());
   int launches = 0;
   const double t0 = now_ms();
+  Trace tr0;
   PackedReads pr;
   int rc = pack_reads(hr.n, hr.seqs, hr.seq_off, &pr);
   if (rc) return rc;
   R->info.ms_host += now_ms() - t0;
+  tr0.lap("run_all: pack_reads");
   DeviceReads dr;
   CATT_CUDA(cudaEventRecord(c->ev[5], c->stream));
   if ((rc = upload_reads(pr, hr.n, &dr, c->stream))) return rc;
   CATT_CUDA(cudaEventRecord(c->ev[6], c->stream));
   CATT_CUDA(cudaStreamSynchronize(c->stream));
+  tr0.lap("run_all: alloc + H2D");
   { float ms = 0; cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]); R->info.ms_h2d += ms; }
   R->info.n_reads = hr.n;
+  Trace tr;
   for (int which = 0; which < 2 && rc == CATT_OK; which++) rc = align_refset(c, which, dr.view(), 0, &R->info, &launches);
+  tr.lap("run_all: align V+J");
   if (rc == CATT_OK) rc = download_records(c, hr.n, R.get());
+  tr.lap("run_all: records D2H");
   if (rc == CATT_OK) rc = stage_b(c, hr, dr, R.get(), &launches);
+  tr.lap("run_all: stage_b");
   dr.release();
+  tr.lap("run_all: free reads");
   if (rc) return rc;
   R->info.kernel_launches = launches;
   *out = R.release();
