@@ -42,7 +42,8 @@ class Info(C.Structure):
                [(k, C.c_int64) for k in ("n_reads", "v_hits", "j_hits", "v_final", "j_final", "share", "pair_seq_mismatch",
                                          "full_pushed", "vpart", "jpart", "direct", "left", "rescued", "cand_v", "cand_j",
                                          "cells_v", "cells_j", "gapped_v", "gapped_j", "kernel_launches")] + \
-               [(k, C.c_double) for k in ("ms_seed", "ms_sw", "ms_select", "ms_extract", "ms_pool", "ms_h2d", "ms_d2h", "ms_host")]
+               [(k, C.c_double) for k in ("ms_seed", "ms_sw", "ms_select", "ms_extract", "ms_pool", "ms_h2d", "ms_d2h", "ms_host")] + \
+               [(k, C.c_int64) for k in ("cells_computed_v", "cells_computed_j")]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved_"}

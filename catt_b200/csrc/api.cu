@@ -31,58 +31,77 @@ int upload_reads(const PackedReads& pr, int64_t n, DeviceReads* dr, cudaStream_t
 }
 
 int ensure_align_buffers(AlignBuffers& ab, const RefDev& ref, int64_t n) {
+  if (!ab.counters) CATT_CUDA(cudaMalloc(&ab.counters, N_COUNTERS * sizeof(unsigned long long)));
   if (n <= ab.cap_reads) return CATT_OK;
-  cudaFree(ab.candbits); cudaFree(ab.ntask); cudaFree(ab.task_off); cudaFree(ab.recs); cudaFree(ab.gapped_list);
+  cudaFree(ab.candbits); cudaFree(ab.canonbits); cudaFree(ab.ntask); cudaFree(ab.task_off); cudaFree(ab.recs); cudaFree(ab.gapped_list);
+  cudaFree(ab.wtasks); cudaFree(ab.wres);
   ab.cap_reads = n + n / 8 + 64;
   CATT_CUDA(cudaMalloc(&ab.candbits, ab.cap_reads * ref.CW * sizeof(uint32_t)));
+  CATT_CUDA(cudaMalloc(&ab.canonbits, ab.cap_reads * ref.CW * sizeof(uint32_t)));
   CATT_CUDA(cudaMalloc(&ab.ntask, (ab.cap_reads + 1) * sizeof(uint32_t)));
   CATT_CUDA(cudaMalloc(&ab.task_off, (ab.cap_reads + 1) * sizeof(uint32_t)));
   CATT_CUDA(cudaMalloc(&ab.recs, ab.cap_reads * sizeof(catt_aln)));
   CATT_CUDA(cudaMalloc(&ab.gapped_list, ab.cap_reads * sizeof(uint32_t)));
-  if (!ab.counters) CATT_CUDA(cudaMalloc(&ab.counters, 8 * sizeof(unsigned long long)));
+  CATT_CUDA(cudaMalloc(&ab.wtasks, ab.cap_reads * sizeof(SwTask)));
+  CATT_CUDA(cudaMalloc(&ab.wres, ab.cap_reads * 2 * sizeof(uint32_t)));
   return CATT_OK;
 }
 
 void free_align_buffers(AlignBuffers& ab) {
-  cudaFree(ab.candbits); cudaFree(ab.ntask); cudaFree(ab.task_off); cudaFree(ab.tasks); cudaFree(ab.task_res); cudaFree(ab.recs);
-  cudaFree(ab.gapped_list); cudaFree(ab.counters); cudaFree(ab.cub_tmp); cudaFree(ab.seed_scratch);
+  cudaFree(ab.candbits); cudaFree(ab.canonbits); cudaFree(ab.ntask); cudaFree(ab.task_off); cudaFree(ab.tasks); cudaFree(ab.task_score);
+  cudaFree(ab.recs); cudaFree(ab.gapped_list); cudaFree(ab.wtasks); cudaFree(ab.wres); cudaFree(ab.counters); cudaFree(ab.cub_tmp);
+  cudaFree(ab.seed_scratch);
   ab = AlignBuffers{};
 }
 
-// Stage A for one reference set; the records stay in ab.recs.
+// Stage A for one reference set; the records stay in ab.recs.  Everything is queued on the stream without a host round
+// trip (task counts, winner counts and the gapped list are consumed on the device); one sync at the end reads the
+// counters.  If the task buffer turned out too small the stage is re-run once with the exact size.
 int align_refset(catt_ctx* c, int which, const ReadsDev& reads, int64_t first_ordinal, catt_info* info, int* launches) {
   RefSet& rs = which ? c->J : c->V;
   AlignBuffers& ab = c->ab[which];
   cudaStream_t st = c->stream;
   int rc;
+  if (reads.n == 0) return CATT_OK;
   if ((rc = ensure_align_buffers(ab, rs.dev, reads.n))) return rc;
-  CATT_CUDA(cudaMemsetAsync(ab.counters, 0, 8 * sizeof(unsigned long long), st));
+  CATT_CUDA(cudaMemsetAsync(ab.counters, 0, N_COUNTERS * sizeof(unsigned long long), st));
   CATT_CUDA(cudaMemsetAsync(ab.ntask, 0, (reads.n + 1) * sizeof(uint32_t), st));
   CATT_CUDA(cudaEventRecord(c->ev[0], st));
   if ((rc = launch_seed(rs.dev, reads, ab, c->sm_count, st, launches))) return rc;
   CATT_CUDA(cudaEventRecord(c->ev[1], st));
-  int64_t ntasks = 0;
-  if ((rc = launch_expand(rs.dev, reads, ab, &ntasks, st, launches))) return rc;
-  CATT_CUDA(cudaEventRecord(c->ev[2], st));
-  if ((rc = launch_sw(rs.dev, reads, ab, ntasks, c->sm_count, st, launches))) return rc;
-  CATT_CUDA(cudaEventRecord(c->ev[3], st));
-  if ((rc = launch_select(rs.dev, reads, ab, first_ordinal, c->min_score, st, launches))) return rc;
-  unsigned long long cnt[8];
-  CATT_CUDA(cudaMemcpyAsync(cnt, ab.counters, sizeof cnt, cudaMemcpyDeviceToHost, st));
-  CATT_CUDA(cudaStreamSynchronize(st));
-  if (cnt[6] > 0) { set_error("%llu reads exceed the seeding run-list capacity", cnt[6]); return CATT_E_LIMIT; }
-  if ((rc = launch_traceback(rs.dev, reads, ab, (int64_t)cnt[2], st, launches))) return rc;
-  CATT_CUDA(cudaEventRecord(c->ev[4], st));
-  CATT_CUDA(cudaEventSynchronize(c->ev[4]));
+  unsigned long long cnt[N_COUNTERS];
   float ms_seed = 0, ms_exp = 0, ms_sw = 0, ms_sel = 0;
+  for (int attempt = 0; attempt < 2; attempt++) {
+    if (attempt) {
+      if ((rc = ensure_task_buffers(ab, (int64_t)cnt[9] + (int64_t)cnt[9] / 8 + 1024))) return rc;
+      unsigned long long z[N_COUNTERS] = {0};
+      z[4] = cnt[4]; z[6] = cnt[6];
+      CATT_CUDA(cudaMemcpyAsync(ab.counters, z, sizeof z, cudaMemcpyHostToDevice, st));
+      CATT_CUDA(cudaStreamSynchronize(st));
+    }
+    CATT_CUDA(cudaEventRecord(c->ev[7], st));
+    if ((rc = launch_expand(rs.dev, reads, ab, st, launches))) return rc;
+    CATT_CUDA(cudaEventRecord(c->ev[2], st));
+    if ((rc = launch_sw(rs.dev, reads, ab, c->sm_count, st, launches))) return rc;
+    CATT_CUDA(cudaEventRecord(c->ev[3], st));
+    if ((rc = launch_select(rs.dev, reads, ab, first_ordinal, c->min_score, c->sm_count, st, launches))) return rc;
+    CATT_CUDA(cudaEventRecord(c->ev[4], st));
+    CATT_CUDA(cudaMemcpyAsync(cnt, ab.counters, sizeof cnt, cudaMemcpyDeviceToHost, st));
+    CATT_CUDA(cudaStreamSynchronize(st));
+    if (cnt[6] > 0) { set_error("%llu reads exceed the seeding run-list capacity", cnt[6]); return CATT_E_LIMIT; }
+    float a = 0, b = 0, d = 0;
+    cudaEventElapsedTime(&a, c->ev[7], c->ev[2]);
+    cudaEventElapsedTime(&b, c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&d, c->ev[3], c->ev[4]);
+    ms_exp += a; ms_sw += b; ms_sel += d;
+    if (cnt[9] == 0) break;
+    if (attempt == 1) { set_error("SW task buffer overflow persists (%llu tasks)", cnt[9]); return CATT_E_LIMIT; }
+  }
   cudaEventElapsedTime(&ms_seed, c->ev[0], c->ev[1]);
-  cudaEventElapsedTime(&ms_exp, c->ev[1], c->ev[2]);
-  cudaEventElapsedTime(&ms_sw, c->ev[2], c->ev[3]);
-  cudaEventElapsedTime(&ms_sel, c->ev[3], c->ev[4]);
   if (info) {
     info->ms_seed += ms_seed + ms_exp; info->ms_sw += ms_sw; info->ms_select += ms_sel;
-    if (which) { info->cand_j = (int64_t)cnt[0]; info->cells_j = (int64_t)cnt[1]; info->gapped_j = (int64_t)cnt[2]; info->j_hits = (int64_t)cnt[3]; }
-    else { info->cand_v = (int64_t)cnt[0]; info->cells_v = (int64_t)cnt[1]; info->gapped_v = (int64_t)cnt[2]; info->v_hits = (int64_t)cnt[3]; }
+    if (which) { info->cand_j = (int64_t)cnt[0]; info->cells_j = (int64_t)cnt[1]; info->gapped_j = (int64_t)cnt[2]; info->j_hits = (int64_t)cnt[3]; info->cells_computed_j = (int64_t)cnt[8]; }
+    else { info->cand_v = (int64_t)cnt[0]; info->cells_v = (int64_t)cnt[1]; info->gapped_v = (int64_t)cnt[2]; info->v_hits = (int64_t)cnt[3]; info->cells_computed_v = (int64_t)cnt[8]; }
   }
   return CATT_OK;
 }
@@ -505,7 +524,7 @@ int catt_seed_candidates(catt_ctx* c, int which, int64_t n, const char* seqs, co
   AlignBuffers& ab = c->ab[which];
   int launches = 0;
   if ((rc = ensure_align_buffers(ab, rs.dev, n))) return rc;
-  CATT_CUDA(cudaMemsetAsync(ab.counters, 0, 8 * sizeof(unsigned long long), c->stream));
+  CATT_CUDA(cudaMemsetAsync(ab.counters, 0, N_COUNTERS * sizeof(unsigned long long), c->stream));
   if ((rc = launch_seed(rs.dev, dr.view(), ab, c->sm_count, c->stream, &launches))) return rc;
   std::vector<uint32_t> bits((size_t)n * rs.dev.CW);
   CATT_CUDA(cudaMemcpyAsync(bits.data(), ab.candbits, bits.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));

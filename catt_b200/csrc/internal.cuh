@@ -65,6 +65,7 @@ struct RefDev {            // POD view handed to kernels
   const uint16_t* pos2rid; // forward position -> record
   const int32_t* rec_off;
   const int32_t* rec_len;
+  const uint16_t* canon;   // candidate (rid*2+strand) -> candidate of the first byte-identical record (same strand)
   int32_t L, nrec, maxlen, CW;
 };
 
@@ -130,14 +131,18 @@ struct SwTask { uint32_t read; uint16_t a, b; };   // two same-strand candidates
 
 struct AlignBuffers {       // per reference set, sized for one batch
   int64_t cap_reads = 0, cap_tasks = 0;
-  uint32_t* candbits = nullptr;    // n * CW
+  uint32_t* candbits = nullptr;    // n * CW: (record, strand) pairs bwa-mem would extend
+  uint32_t* canonbits = nullptr;   // n * CW: the same set with byte-identical records folded onto their first copy
   uint32_t* ntask = nullptr;       // n (+1): tasks per read, then exclusive offsets
   uint32_t* task_off = nullptr;    // n+1
   SwTask* tasks = nullptr;
-  uint32_t* task_res = nullptr;    // 2 per task: score<<20 | (1023-ei)<<10 | (1023-ej)
+  uint32_t* task_score = nullptr;  // per task: scoreA | scoreB << 16
+  SwTask* wtasks = nullptr;        // n: the winning candidate of every mapped read (compacted), input of the TRACK pass
+  uint32_t* wres = nullptr;        // 2 per winner: score<<20 | (1023-ei)<<10 | (1023-ej)
   catt_aln* recs = nullptr;        // n
   uint32_t* gapped_list = nullptr; // read indices whose winner needs the traceback kernel
-  unsigned long long* counters = nullptr;  // [0] cand, [1] cells, [2] n_gapped, [3] hits, [4] seed overflow, [5] ntasks
+  unsigned long long* counters = nullptr;  // [0] cand, [1] cells, [2] n_gapped, [3] hits, [4] seed redo, [6] seed overflow,
+                                           // [7] winners, [8] cells computed (canonical records), [9] task-buffer overflow
   void* cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
   uint32_t* seed_scratch = nullptr; size_t seed_scratch_runs = 0;
 };
@@ -145,11 +150,12 @@ struct AlignBuffers {       // per reference set, sized for one batch
 // seeding (seed.cu)
 int launch_seed(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int sm_count, cudaStream_t st, int* launches);
 // task expansion + SW scoring + selection + traceback (sw.cu)
-int launch_expand(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int64_t* ntasks_out, cudaStream_t st, int* launches);
-int launch_sw(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int64_t ntasks, int sm_count, cudaStream_t st, int* launches);
-int launch_select(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int64_t first_ordinal, int min_score,
+constexpr int N_COUNTERS = 16;
+int ensure_task_buffers(AlignBuffers& ab, int64_t want);
+int launch_expand(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, cudaStream_t st, int* launches);
+int launch_sw(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int sm_count, cudaStream_t st, int* launches);
+int launch_select(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int64_t first_ordinal, int min_score, int sm_count,
                   cudaStream_t st, int* launches);
-int launch_traceback(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int64_t n_gapped, cudaStream_t st, int* launches);
 int launch_sw_pairs(const RefDev& ref, const ReadsDev& reads, const int32_t* d_rid, const int32_t* d_strand, int32_t* d_out3,
                     int sm_count, cudaStream_t st);
 int alu_peak(int sm_count, cudaStream_t st, double* ops_per_s, double* ms);

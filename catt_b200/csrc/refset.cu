@@ -124,6 +124,14 @@ int RefSet::upload() {
   }
   std::vector<uint16_t> pos2rid(L);
   for (size_t r = 0; r < names.size(); r++) for (int i = 0; i < len[r]; i++) pos2rid[off[r] + i] = (uint16_t)r;
+  // byte-identical records share one DP: canon[rid*2+strand] = (first identical rid)*2+strand
+  std::vector<uint16_t> canon(names.size() * 2);
+  for (size_t r = 0; r < names.size(); r++) {
+    size_t f = r;
+    for (size_t q = 0; q < r; q++)
+      if (len[q] == len[r] && std::equal(T.begin() + off[q], T.begin() + off[q] + len[q], T.begin() + off[r])) { f = q; break; }
+    canon[2 * r] = (uint16_t)(2 * f); canon[2 * r + 1] = (uint16_t)(2 * f + 1);
+  }
   std::vector<uint8_t> tb(T.begin(), T.begin() + L);
   tb.resize(L + 64, 0);
   int rc;
@@ -134,6 +142,7 @@ int RefSet::upload() {
   if ((rc = to_device(kstart, (const void**)&dev.kstart, allocs))) return rc;
   if ((rc = to_device(kpos, (const void**)&dev.kpos, allocs))) return rc;
   if ((rc = to_device(pos2rid, (const void**)&dev.pos2rid, allocs))) return rc;
+  if ((rc = to_device(canon, (const void**)&dev.canon, allocs))) return rc;
   if ((rc = to_device(off, (const void**)&dev.rec_off, allocs))) return rc;
   if ((rc = to_device(len, (const void**)&dev.rec_len, allocs))) return rc;
   dev.L = L; dev.nrec = (int)names.size(); dev.maxlen = maxlen; dev.CW = ((int)names.size() * 2 + 31) / 32;

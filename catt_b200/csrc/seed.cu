@@ -32,6 +32,7 @@ struct WarpScratch {
   uint16_t starts[MAX_READ];  // distinct starts of the runs covering `mid` (pass 2)
   uint32_t startbits[MAX_READ / 32];
   uint32_t cand[MAX_CW];
+  uint32_t canon[MAX_CW];     // cand with byte-identical records folded onto their first copy
   uint8_t codes[MAX_READ];
   int nruns, ncov, niv, pad_;
   uint32_t runs_q[RUNS_SMEM];   // qs | qe << 16
@@ -246,12 +247,25 @@ __device__ bool seed_one_read(const RefDev& ref, const uint32_t* __restrict__ T2
   return true;
 }
 
-__device__ __forceinline__ void write_out(const RefDev& ref, WarpScratch& ws, int64_t r, uint32_t* candbits, uint32_t* ntask,
-                                          int lane) {
+__device__ __forceinline__ void write_out(const RefDev& ref, WarpScratch& ws, int64_t r, uint32_t* candbits, uint32_t* canonbits,
+                                          uint32_t* ntask, int lane) {
   uint32_t nf = 0, nr = 0;
+  if (lane < MAX_CW) ws.canon[lane] = 0;
+  __syncwarp();
   if (lane < ref.CW) {
-    const uint32_t b = ws.cand[lane];
+    uint32_t b = ws.cand[lane];
     candbits[r * ref.CW + lane] = b;
+    while (b) {
+      const int c = lane * 32 + __ffs(b) - 1;
+      b &= b - 1;
+      const int cc = ref.canon[c];
+      atomicOr(&ws.canon[cc >> 5], 1u << (cc & 31));
+    }
+  }
+  __syncwarp();
+  if (lane < ref.CW) {
+    const uint32_t b = ws.canon[lane];
+    canonbits[r * ref.CW + lane] = b;
     nf = __popc(b & 0x55555555u); nr = __popc(b & 0xAAAAAAAAu);
   }
   nf = warp_sum(nf); nr = warp_sum(nr);
@@ -262,7 +276,7 @@ __device__ __forceinline__ void write_out(const RefDev& ref, WarpScratch& ws, in
 // GS = true : scratch in global memory, only the reads listed in `redo`.
 template <bool GS>
 __global__ void __launch_bounds__(SEED_WARPS * 32) seed_kernel(RefDev ref, ReadsDev reads, uint32_t* __restrict__ candbits,
-                                                               uint32_t* __restrict__ ntask, uint32_t* __restrict__ redo,
+                                                               uint32_t* __restrict__ canonbits, uint32_t* __restrict__ ntask, uint32_t* __restrict__ redo,
                                                                unsigned long long* __restrict__ counters,
                                                                uint32_t* __restrict__ gscratch, int t2_bytes_smem) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -289,12 +303,12 @@ __global__ void __launch_bounds__(SEED_WARPS * 32) seed_kernel(RefDev ref, Reads
     const int64_t r = GS ? (int64_t)redo[it] : it;
     const bool ok = seed_one_read(ref, T2, reads, r, ws, sc, lane);
     if (ok) {
-      write_out(ref, ws, r, candbits, ntask, lane);
+      write_out(ref, ws, r, candbits, canonbits, ntask, lane);
     } else if (!GS) {
       if (lane == 0) { const unsigned long long k = atomicAdd(&counters[4], 1ull); redo[k] = (uint32_t)r; ntask[r] = 0; }
     } else {
       if (lane == 0) { atomicAdd(&counters[6], 1ull); ntask[r] = 0; }    // hard overflow: reported to the host as an error
-      if (lane < ref.CW) candbits[r * ref.CW + lane] = 0;
+      if (lane < ref.CW) { candbits[r * ref.CW + lane] = 0; canonbits[r * ref.CW + lane] = 0; }
     }
     __syncwarp();
   }
@@ -317,7 +331,7 @@ int launch_seed(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int 
   if (per_sm < 1) per_sm = 1;
   const int64_t want = (reads.n + SEED_WARPS - 1) / SEED_WARPS;
   int grid = (int)std::min<int64_t>((int64_t)sm_count * per_sm, std::max<int64_t>(want, 1));
-  seed_kernel<false><<<grid, SEED_WARPS * 32, smem, st>>>(ref, reads, ab.candbits, ab.ntask, ab.gapped_list, ab.counters, nullptr, t2_smem);
+  seed_kernel<false><<<grid, SEED_WARPS * 32, smem, st>>>(ref, reads, ab.candbits, ab.canonbits, ab.ntask, ab.gapped_list, ab.counters, nullptr, t2_smem);
   CATT_CUDA(cudaGetLastError());
   // overflow pass (usually an empty list): global scratch sized for sm_count*2 CTAs
   const int grid2 = sm_count * 2;
@@ -327,7 +341,7 @@ int launch_seed(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int 
     CATT_CUDA(cudaMalloc(&ab.seed_scratch, need * sizeof(uint32_t)));
     ab.seed_scratch_runs = need;
   }
-  seed_kernel<true><<<grid2, SEED_WARPS * 32, smem, st>>>(ref, reads, ab.candbits, ab.ntask, ab.gapped_list, ab.counters, ab.seed_scratch, t2_smem);
+  seed_kernel<true><<<grid2, SEED_WARPS * 32, smem, st>>>(ref, reads, ab.candbits, ab.canonbits, ab.ntask, ab.gapped_list, ab.counters, ab.seed_scratch, t2_smem);
   CATT_CUDA(cudaGetLastError());
   *launches += 2;
   return CATT_OK;

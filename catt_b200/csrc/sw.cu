@@ -59,18 +59,23 @@ __device__ __forceinline__ uint32_t read_code(const uint32_t* __restrict__ w, co
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// task expansion: candidate bitmap -> (read, candA, candB) tasks, pairing candidates of the same strand
+// task expansion: canonical-candidate bitmap -> (read, candA, candB) tasks, pairing candidates of the same strand.
+// Byte-identical records (hs TRBV: 47 of 168 records in 22 groups) are scored once, through their first copy.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void expand_kernel(RefDev ref, int64_t n, const uint32_t* __restrict__ candbits, const uint32_t* __restrict__ task_off,
-                              SwTask* __restrict__ tasks) {
+__global__ void expand_kernel(RefDev ref, int64_t n, const uint32_t* __restrict__ canonbits, const uint32_t* __restrict__ task_off,
+                              SwTask* __restrict__ tasks, int64_t cap_tasks, unsigned long long* __restrict__ counters) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
+  if ((int64_t)task_off[n] > cap_tasks) {                 // task buffer too small: the host grows it and re-runs the stage
+    if (r == 0) counters[9] = task_off[n];
+    return;
+  }
   uint32_t o = task_off[r];
   if (task_off[r + 1] == o) return;
   for (int strand = 0; strand < 2; strand++) {
     int pend = -1;
     for (int w = 0; w < ref.CW; w++) {
-      uint32_t b = candbits[r * ref.CW + w] & (strand ? 0xAAAAAAAAu : 0x55555555u);
+      uint32_t b = canonbits[r * ref.CW + w] & (strand ? 0xAAAAAAAAu : 0x55555555u);
       while (b) {
         const int bit = __ffs(b) - 1;
         b &= b - 1;
@@ -100,7 +105,8 @@ __device__ __forceinline__ void sw_row(uint32_t (&Hp)[C], uint32_t (&E)[C], cons
     const uint32_t hm7 = __viaddmax_s16x2(h, NEG7, MINV);   // H(i,j) - 7
     E[c] = __viaddmax_s16x2(e, NEG1, hm7);              // E(i+1,j) = max(E(i,j)-1, H(i,j)-7)
     f = __viaddmax_s16x2(f, NEG1, hm7);                 // F(i,j+1)
-    rowbest = __vimax_s16x2_relu(rowbest, h);
+    if (c & 1) rowbest = __vimax3_s16x2_relu(rowbest, Hp[c - 1], h);
+    else if (c == C - 1) rowbest = __vimax_s16x2_relu(rowbest, h);
   }
 }
 
@@ -108,14 +114,22 @@ __device__ __forceinline__ uint32_t pack_key(int score, int i, int j) {
   return ((uint32_t)score << 20) | ((uint32_t)(1023 - i) << 10) | (uint32_t)(1023 - j);
 }
 
-// G lanes per task, C columns per lane; record length <= G*C
-template <int G, int C>
+// G lanes per task, C columns per lane; record length <= G*C.
+// TRACK = false: scores only (out[t] = scoreA | scoreB << 16) — the bulk pass over every candidate.
+// TRACK = true : also the first cell reaching the maximum in row-major order (out[2t], out[2t+1] = pack_key) — run on
+//                the one winning candidate per read, which is all the SAM record needs.
+// The task count is read on the device (*ntasks_dev) so the stage needs no host round trip.
+template <int G, int C, bool TRACK>
 __global__ void __launch_bounds__(SW_THREADS) sw_score_kernel(RefDev ref, ReadsDev reads, const SwTask* __restrict__ tasks,
-                                                              int64_t ntasks, uint32_t* __restrict__ task_res, int tb_bytes_smem) {
+                                                              const uint32_t* __restrict__ ntasks_dev, int64_t ntasks_cap,
+                                                              uint32_t* __restrict__ out, int tb_bytes_smem) {
   constexpr int GPW = 32 / G;                         // tasks per warp
   constexpr int GPB = GPW * (SW_THREADS / 32);        // tasks per block
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint64_t bar;
+  const int64_t ntasks = (int64_t)*ntasks_dev;
+  if (ntasks > ntasks_cap) return;                    // expand_kernel flagged the overflow; nothing valid to score
+  if ((int64_t)blockIdx.x * GPB >= ntasks) return;
   uint16_t* sel_all = reinterpret_cast<uint16_t*>(smem_raw);              // [GPB][MAX_READ]
   const uint8_t* Tb = ref.Tb;
   if (tb_bytes_smem > 0) {
@@ -177,190 +191,220 @@ __global__ void __launch_bounds__(SW_THREADS) sw_score_kernel(RefDev ref, ReadsD
       const int i = st - g;
       if (i >= 0 && i < m) {
         const uint32_t sel = sel_arr[i];
-        uint32_t hd = diag_in, f = inF, rowbest = 0;
-        // F(i, first column) arrives already advanced from the left neighbour
-        if (sel == SEL_N) sw_row<C, true>(Hp, E, tabA, tabB, sel, hd, f, rowbest);
-        else sw_row<C, false>(Hp, E, tabA, tabB, sel, hd, f, rowbest);
+        uint32_t hd = diag_in, f = inF;       // F(i, first column) arrives already advanced from the left neighbour
         diag_in = inH;
-        // the first column needs H(i, gC-1) only through F and the next row's diagonal; fold the incoming H into F's
-        // source: F(i,gC) = max(F(i,gC-1)-1, H(i,gC-1)-7) was computed by the neighbour (lastF), so nothing else here.
-        lastH = Hp[C - 1];
-        lastF = f;
-        const uint32_t nb = __vimax_s16x2_relu(best, rowbest);
-        if (nb != best) {                                 // a half improved: record the first cell reaching it
-          const int rl = (int)(short)(rowbest & 0xffff), bl = (int)(short)(best & 0xffff);
-          const int rh = (int)(short)(rowbest >> 16), bh = (int)(short)(best >> 16);
-          if (rl > bl) {
-            bi_lo = i;
-            int jj = 0;
-            #pragma unroll
-            for (int c = C - 1; c >= 0; c--) if ((int)(short)(Hp[c] & 0xffff) == rl) jj = c;
-            bj_lo = g * C + jj;
+        if (!TRACK) {
+          if (sel == SEL_N) sw_row<C, true>(Hp, E, tabA, tabB, sel, hd, f, best);
+          else sw_row<C, false>(Hp, E, tabA, tabB, sel, hd, f, best);
+          lastH = Hp[C - 1];
+          lastF = f;
+        } else {
+          uint32_t rowbest = 0;
+          if (sel == SEL_N) sw_row<C, true>(Hp, E, tabA, tabB, sel, hd, f, rowbest);
+          else sw_row<C, false>(Hp, E, tabA, tabB, sel, hd, f, rowbest);
+          lastH = Hp[C - 1];
+          lastF = f;
+          const uint32_t nb = __vimax_s16x2_relu(best, rowbest);
+          if (nb != best) {                                 // a half improved: record the first cell reaching it
+            const int rl = (int)(short)(rowbest & 0xffff), bl = (int)(short)(best & 0xffff);
+            const int rh = (int)(short)(rowbest >> 16), bh = (int)(short)(best >> 16);
+            if (rl > bl) {
+              bi_lo = i;
+              int jj = 0;
+              #pragma unroll
+              for (int c = C - 1; c >= 0; c--) if ((int)(short)(Hp[c] & 0xffff) == rl) jj = c;
+              bj_lo = g * C + jj;
+            }
+            if (rh > bh) {
+              bi_hi = i;
+              int jj = 0;
+              #pragma unroll
+              for (int c = C - 1; c >= 0; c--) if ((int)(short)(Hp[c] >> 16) == rh) jj = c;
+              bj_hi = g * C + jj;
+            }
+            best = nb;
           }
-          if (rh > bh) {
-            bi_hi = i;
-            int jj = 0;
-            #pragma unroll
-            for (int c = C - 1; c >= 0; c--) if ((int)(short)(Hp[c] >> 16) == rh) jj = c;
-            bj_hi = g * C + jj;
-          }
-          best = nb;
         }
       }
     }
-    // reduce over the G lanes of the task: max score, then earliest row, then earliest column
-    uint32_t klo = pack_key((int)(short)(best & 0xffff), bi_lo, bj_lo);
-    uint32_t khi = pack_key((int)(short)(best >> 16), bi_hi, bj_hi);
-    #pragma unroll
-    for (int d = G / 2; d; d >>= 1) {
-      klo = max(klo, __shfl_xor_sync(FULL, klo, d, G));
-      khi = max(khi, __shfl_xor_sync(FULL, khi, d, G));
+    if (!TRACK) {
+      #pragma unroll
+      for (int d = G / 2; d; d >>= 1) best = __vimax_s16x2_relu(best, __shfl_xor_sync(FULL, best, d, G));
+      if (live && g == 0) out[t] = best;
+    } else {
+      // reduce over the G lanes of the task: max score, then earliest row, then earliest column
+      uint32_t klo = pack_key((int)(short)(best & 0xffff), bi_lo, bj_lo);
+      uint32_t khi = pack_key((int)(short)(best >> 16), bi_hi, bj_hi);
+      #pragma unroll
+      for (int d = G / 2; d; d >>= 1) {
+        klo = max(klo, __shfl_xor_sync(FULL, klo, d, G));
+        khi = max(khi, __shfl_xor_sync(FULL, khi, d, G));
+      }
+      if (live && g == 0) { out[2 * t] = klo; out[2 * t + 1] = khi; }
     }
-    if (live && g == 0) { task_res[2 * t] = klo; task_res[2 * t + 1] = khi; }
     __syncwarp();
   }
 }
 
-template <int G, int C>
-int launch_sw_t(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks, int64_t ntasks, uint32_t* res, int sm_count,
-                cudaStream_t st) {
+template <int G, int C, bool TRACK>
+int launch_sw_t(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks, const uint32_t* ntasks_dev, int64_t cap, uint32_t* res,
+                int sm_count, cudaStream_t st) {
   constexpr int GPB = (32 / G) * (SW_THREADS / 32);
   const int tb_bytes = (ref.L + 64) & ~15;
   const size_t sel_bytes = (size_t)GPB * MAX_READ * sizeof(uint16_t);
   const int tb_smem = (sel_bytes + tb_bytes <= 100 * 1024) ? tb_bytes : 0;
   const size_t smem = sel_bytes + tb_smem;
-  auto k = sw_score_kernel<G, C>;
+  auto k = sw_score_kernel<G, C, TRACK>;
   static bool attr = false;
-  if (!attr) { CATT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
-  int per_sm = 0;
+  static int per_sm = 0;
+  if (!attr) {
+    CATT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
   CATT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, SW_THREADS, smem));
   if (per_sm < 1) per_sm = 1;
-  const int64_t want = (ntasks + GPB - 1) / GPB;
+  const int64_t want = (cap + GPB - 1) / GPB;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)sm_count * per_sm, want));
-  k<<<grid, SW_THREADS, smem, st>>>(ref, reads, tasks, ntasks, res, tb_smem);
+  k<<<grid, SW_THREADS, smem, st>>>(ref, reads, tasks, ntasks_dev, cap, res, tb_smem);
   CATT_CUDA(cudaGetLastError());
   return CATT_OK;
 }
 
-int dispatch_sw(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks, int64_t ntasks, uint32_t* res, int sm_count,
-                cudaStream_t st) {
+template <bool TRACK>
+int dispatch_sw(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks, const uint32_t* ntasks_dev, int64_t cap, uint32_t* res,
+                int sm_count, cudaStream_t st) {
   const int n = ref.maxlen;
-  if (n <= 32) return launch_sw_t<4, 8>(ref, reads, tasks, ntasks, res, sm_count, st);
-  if (n <= 48) return launch_sw_t<4, 12>(ref, reads, tasks, ntasks, res, sm_count, st);
-  if (n <= 64) return launch_sw_t<8, 8>(ref, reads, tasks, ntasks, res, sm_count, st);
-  if (n <= 104) return launch_sw_t<8, 13>(ref, reads, tasks, ntasks, res, sm_count, st);
-  if (n <= 160) return launch_sw_t<16, 10>(ref, reads, tasks, ntasks, res, sm_count, st);
-  if (n <= 320) return launch_sw_t<32, 10>(ref, reads, tasks, ntasks, res, sm_count, st);
+  if (n <= 32) return launch_sw_t<4, 8, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
+  if (n <= 48) return launch_sw_t<4, 12, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
+  if (n <= 64) return launch_sw_t<8, 8, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
+  if (n <= 104) return launch_sw_t<8, 13, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
+  if (n <= 160) return launch_sw_t<16, 10, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
+  if (n <= 320) return launch_sw_t<32, 10, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
   set_error("record length %d exceeds the SW kernel's tiling", n);
   return CATT_E_LIMIT;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// selection + CIGAR facts (ungapped fast path).  One thread per read.
+// selection.  One thread per read: best score over the candidates, bwa's tie-break, the winner's task for the
+// TRACK pass.
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int sub_score(uint32_t a, uint32_t b) { return (a > 3 || b > 3) ? -1 : (a == b ? 1 : -2); }
 
-__global__ void select_kernel(RefDev ref, ReadsDev reads, const SwTask* __restrict__ tasks, const uint32_t* __restrict__ task_off,
-                              const uint32_t* __restrict__ task_res, int64_t first_ordinal, int min_score, catt_aln* __restrict__ recs,
-                              uint32_t* __restrict__ gapped_list, unsigned long long* __restrict__ counters) {
+__global__ void select_kernel(RefDev ref, ReadsDev reads, const uint32_t* __restrict__ candbits, const SwTask* __restrict__ tasks,
+                              const uint32_t* __restrict__ task_off, const uint32_t* __restrict__ task_score, int64_t cap_tasks,
+                              int64_t first_ordinal, int min_score, catt_aln* __restrict__ recs, SwTask* __restrict__ wtasks,
+                              unsigned long long* __restrict__ counters) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned long long my_cand = 0, my_cells = 0, my_hit = 0;
-  if (r < reads.n) {
+  unsigned long long my_cand = 0, my_cells = 0, my_hit = 0, my_comp = 0;
+  if (r < reads.n && (int64_t)task_off[reads.n] <= cap_tasks) {
     const uint32_t t0 = task_off[r], t1 = task_off[r + 1];
     const int m = reads.len[r];
     catt_aln a;
     a.ordinal = (int32_t)(first_ordinal + r);
     a.rid = -1; a.strand = 0; a.mapped = 0; a.as = 0; a.qb = 0; a.m_end = 0; a.rb = 0; a.qe = 0; a.re = 0; a.nm = 0; a.mi = 0;
     a.ncand = 0; a.ntied = 0;
-    int mx = 0, ncand = 0;
+    int mx = 0;
     for (uint32_t t = t0; t < t1; t++) {
       const SwTask tk = tasks[t];
-      const int sa = (int)(task_res[2 * t] >> 20);
-      mx = max(mx, sa); ncand++;
-      my_cells += (unsigned long long)m * ref.rec_len[tk.a >> 1];
-      if (tk.b != 0xFFFF) {
-        const int sb = (int)(task_res[2 * t + 1] >> 20);
-        mx = max(mx, sb); ncand++;
-        my_cells += (unsigned long long)m * ref.rec_len[tk.b >> 1];
+      const uint32_t sc = task_score[t];
+      mx = max(mx, (int)(sc & 0xffff));
+      my_comp += (unsigned long long)m * ref.rec_len[tk.a >> 1];
+      if (tk.b != 0xFFFF) { mx = max(mx, (int)(sc >> 16)); my_comp += (unsigned long long)m * ref.rec_len[tk.b >> 1]; }
+    }
+    // candidates in T order (forward records ascending, then reverse-strand records descending): rank among the tied
+    const uint64_t ord = (uint64_t)(first_ordinal + r);
+    int ncand = 0, ntied = 0, win_c = -1;
+    uint64_t win_h = ~0ull;
+    auto consider = [&](int c) {
+      ncand++;
+      my_cells += (unsigned long long)m * ref.rec_len[c >> 1];
+      const int cc = ref.canon[c];
+      int sc = -1;
+      for (uint32_t t = t0; t < t1; t++) {
+        const SwTask tk = tasks[t];
+        if (tk.a == cc) { sc = (int)(task_score[t] & 0xffff); break; }
+        if (tk.b == cc) { sc = (int)(task_score[t] >> 16); break; }
+      }
+      if (sc == mx) {
+        const uint64_t h = hash_64(ord + (uint64_t)ntied);
+        ntied++;
+        if (h < win_h) { win_h = h; win_c = c; }
+      }
+    };
+    if (t1 > t0) {
+      for (int w = 0; w < ref.CW; w++) {
+        uint32_t b = candbits[r * ref.CW + w] & 0x55555555u;
+        while (b) { const int bit = __ffs(b) - 1; b &= b - 1; consider(w * 32 + bit); }
+      }
+      for (int w = ref.CW - 1; w >= 0; w--) {
+        uint32_t b = candbits[r * ref.CW + w] & 0xAAAAAAAAu;
+        while (b) { const int bit = 31 - __clz(b); b &= ~(1u << bit); consider(w * 32 + bit); }
       }
     }
     my_cand = ncand;
     a.ncand = (int16_t)ncand;
     a.as = (int16_t)mx;
     if (ncand > 0 && mx >= min_score) {
-      // tied set in T order: forward records ascending, then reverse-strand records descending
-      const int L = ref.L;
-      int ntied = 0, win_c = -1;
-      uint32_t win_key = 0;
-      uint64_t win_h = ~0ull;
-      for (uint32_t t = t0; t < t1; t++) {
-        const SwTask tk = tasks[t];
-        for (int half = 0; half < 2; half++) {
-          const int c = half ? tk.b : tk.a;
-          if (c == 0xFFFF) continue;
-          const uint32_t key = task_res[2 * t + half];
-          if ((int)(key >> 20) != mx) continue;
-          ntied++;
-          const int rid = c >> 1, sd = c & 1;
-          const int tpos = sd ? 2 * L - (ref.rec_off[rid] + ref.rec_len[rid]) : ref.rec_off[rid];
-          int rank = 0;
-          for (uint32_t u = t0; u < t1; u++) {
-            const SwTask tu = tasks[u];
-            for (int h2 = 0; h2 < 2; h2++) {
-              const int c2 = h2 ? tu.b : tu.a;
-              if (c2 == 0xFFFF || (int)(task_res[2 * u + h2] >> 20) != mx) continue;
-              const int rid2 = c2 >> 1, sd2 = c2 & 1;
-              const int tpos2 = sd2 ? 2 * L - (ref.rec_off[rid2] + ref.rec_len[rid2]) : ref.rec_off[rid2];
-              rank += tpos2 < tpos;
-            }
-          }
-          const uint64_t h = hash_64((uint64_t)(first_ordinal + r) + (uint64_t)rank);
-          if (h < win_h) { win_h = h; win_c = c; win_key = key; }
-        }
-      }
-      const int rid = win_c >> 1, strand = win_c & 1;
-      const int ei = 1023 - (int)((win_key >> 10) & 1023), ej = 1023 - (int)(win_key & 1023);
-      a.rid = rid; a.strand = (int16_t)strand; a.mapped = 1; a.ntied = (int16_t)ntied;
-      a.qe = (int16_t)(ei + 1); a.re = (int16_t)(ej + 1);
+      a.rid = win_c >> 1; a.strand = (int16_t)(win_c & 1); a.mapped = 1; a.ntied = (int16_t)ntied;
       my_hit = 1;
-      // ungapped fast path: walk back along the diagonal until the suffix sums to AS
-      const uint32_t* __restrict__ w = reads.words + reads.off[r];
-      const uint32_t* __restrict__ nm = w + read_base_words(m);
-      const uint8_t* __restrict__ tb = ref.Tb + ref.rec_off[rid];
-      int sum = 0, mism = 0, d = 0;
-      bool ok = false;
-      const int lim = min(ei, ej);
-      for (; d <= lim; d++) {
-        const uint32_t q = read_code(w, nm, m, ei - d, strand);
-        const uint32_t tt = tb[ej - d];
-        const int s = sub_score(q, tt);
-        sum += s; mism += (s != 1);
-        if (sum == mx) { ok = true; break; }
-      }
-      if (ok) {
-        a.qb = (int16_t)(ei - d); a.rb = (int16_t)(ej - d);
-        a.m_end = (int16_t)(ei + 1);
-        a.nm = (int16_t)mism; a.mi = (int16_t)(d + 1);
-      } else {
-        const unsigned long long k = atomicAdd(&counters[2], 1ull);
-        gapped_list[k] = (uint32_t)r;
-      }
+      const unsigned long long k = atomicAdd(&counters[7], 1ull);
+      wtasks[k] = SwTask{(uint32_t)r, (uint16_t)win_c, (uint16_t)0xFFFF};
     }
     recs[r] = a;
   }
   // block-level reduction of the work counters
-  __shared__ unsigned long long sh[3];
-  if (threadIdx.x < 3) sh[threadIdx.x] = 0;
+  __shared__ unsigned long long sh[4];
+  if (threadIdx.x < 4) sh[threadIdx.x] = 0;
   __syncthreads();
   #pragma unroll
   for (int d = 16; d; d >>= 1) {
     my_cand += __shfl_xor_sync(FULL, my_cand, d);
     my_cells += __shfl_xor_sync(FULL, my_cells, d);
     my_hit += __shfl_xor_sync(FULL, my_hit, d);
+    my_comp += __shfl_xor_sync(FULL, my_comp, d);
   }
-  if ((threadIdx.x & 31) == 0) { atomicAdd(&sh[0], my_cand); atomicAdd(&sh[1], my_cells); atomicAdd(&sh[2], my_hit); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&sh[0], my_cand); atomicAdd(&sh[1], my_cells); atomicAdd(&sh[2], my_hit); atomicAdd(&sh[3], my_comp); }
   __syncthreads();
-  if (threadIdx.x == 0) { atomicAdd(&counters[0], sh[0]); atomicAdd(&counters[1], sh[1]); atomicAdd(&counters[3], sh[2]); }
+  if (threadIdx.x == 0) {
+    atomicAdd(&counters[0], sh[0]); atomicAdd(&counters[1], sh[1]); atomicAdd(&counters[3], sh[2]); atomicAdd(&counters[8], sh[3]);
+  }
+}
+
+// CIGAR facts of the winner from its end cell (ungapped fast path): walk back along the diagonal until the suffix sums
+// to AS; otherwise the read goes to the traceback kernel.  One thread per winner.
+__global__ void finish_kernel(RefDev ref, ReadsDev reads, const SwTask* __restrict__ wtasks, const uint32_t* __restrict__ wres,
+                              catt_aln* __restrict__ recs, uint32_t* __restrict__ gapped_list, unsigned long long* __restrict__ counters) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= (int64_t)counters[7]) return;
+  const SwTask tk = wtasks[k];
+  const uint32_t r = tk.read;
+  const uint32_t key = wres[2 * k];
+  catt_aln a = recs[r];
+  const int mx = a.as, strand = a.strand, m = reads.len[r];
+  const int ei = 1023 - (int)((key >> 10) & 1023), ej = 1023 - (int)(key & 1023);
+  a.qe = (int16_t)(ei + 1); a.re = (int16_t)(ej + 1);
+  const uint32_t* __restrict__ w = reads.words + reads.off[r];
+  const uint32_t* __restrict__ nm = w + read_base_words(m);
+  const uint8_t* __restrict__ tb = ref.Tb + ref.rec_off[a.rid];
+  int sum = 0, mism = 0, d = 0;
+  bool ok = false;
+  const int lim = min(ei, ej);
+  for (; d <= lim; d++) {
+    const uint32_t q = read_code(w, nm, m, ei - d, strand);
+    const uint32_t tt = tb[ej - d];
+    const int s = sub_score(q, tt);
+    sum += s; mism += (s != 1);
+    if (sum == mx) { ok = true; break; }
+  }
+  if (ok) {
+    a.qb = (int16_t)(ei - d); a.rb = (int16_t)(ej - d);
+    a.m_end = (int16_t)(ei + 1);
+    a.nm = (int16_t)mism; a.mi = (int16_t)(d + 1);
+  } else {
+    const unsigned long long g = atomicAdd(&counters[2], 1ull);
+    gapped_list[g] = r;
+  }
+  recs[r] = a;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -371,7 +415,7 @@ __global__ void select_kernel(RefDev ref, ReadsDev reads, const SwTask* __restri
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int TB_NEG = -30000;
 __global__ void __launch_bounds__(32) traceback_kernel(RefDev ref, ReadsDev reads, const uint32_t* __restrict__ gapped_list,
-                                                       int64_t n_gapped, catt_aln* __restrict__ recs) {
+                                                       const unsigned long long* __restrict__ counters, catt_aln* __restrict__ recs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x;
   int16_t* Hb = reinterpret_cast<int16_t*>(smem_raw);          // 3 x (MAX_READ+2)
@@ -379,6 +423,7 @@ __global__ void __launch_bounds__(32) traceback_kernel(RefDev ref, ReadsDev read
   int16_t* Fb = Eb + 2 * (MAX_READ + 2);                       // 2 x
   uint8_t* q = reinterpret_cast<uint8_t*>(Fb + 2 * (MAX_READ + 2));
   uint8_t* dir = q + MAX_READ;
+  const int64_t n_gapped = (int64_t)counters[2];
   for (int64_t it = blockIdx.x; it < n_gapped; it += gridDim.x) {
     const uint32_t r = gapped_list[it];
     catt_aln a = recs[r];
@@ -477,8 +522,22 @@ __global__ void unpack_pair_res(int64_t n, const uint32_t* res, int32_t* out3) {
 
 }  // namespace
 
-int launch_expand(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int64_t* ntasks_out, cudaStream_t st, int* launches) {
+int ensure_task_buffers(AlignBuffers& ab, int64_t want) {
+  if (want <= ab.cap_tasks) return CATT_OK;
+  if (ab.tasks) cudaFree(ab.tasks);
+  if (ab.task_score) cudaFree(ab.task_score);
+  ab.tasks = nullptr; ab.task_score = nullptr; ab.cap_tasks = 0;
+  CATT_CUDA(cudaMalloc(&ab.tasks, want * sizeof(SwTask)));
+  CATT_CUDA(cudaMalloc(&ab.task_score, want * sizeof(uint32_t)));
+  ab.cap_tasks = want;
+  return CATT_OK;
+}
+
+// scan of the per-read task counts + task expansion; no host round trip (the task count stays on the device)
+int launch_expand(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, cudaStream_t st, int* launches) {
   const int64_t n = reads.n;
+  int rc;
+  if ((rc = ensure_task_buffers(ab, n * 10 + 4096))) return rc;     // grown (and the stage re-run) on overflow
   size_t need = 0;
   CATT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, ab.ntask, ab.task_off, (int)(n + 1), st));
   if (need > ab.cub_tmp_bytes) {
@@ -487,44 +546,28 @@ int launch_expand(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, in
     ab.cub_tmp_bytes = need;
   }
   CATT_CUDA(cub::DeviceScan::ExclusiveSum(ab.cub_tmp, need, ab.ntask, ab.task_off, (int)(n + 1), st));
-  uint32_t total = 0;
-  CATT_CUDA(cudaMemcpyAsync(&total, ab.task_off + n, sizeof total, cudaMemcpyDeviceToHost, st));
-  CATT_CUDA(cudaStreamSynchronize(st));
-  *ntasks_out = total;
-  *launches += 1;
-  if ((int64_t)total > ab.cap_tasks) {
-    if (ab.tasks) cudaFree(ab.tasks);
-    if (ab.task_res) cudaFree(ab.task_res);
-    ab.cap_tasks = (int64_t)total + (int64_t)total / 8 + 1024;
-    CATT_CUDA(cudaMalloc(&ab.tasks, ab.cap_tasks * sizeof(SwTask)));
-    CATT_CUDA(cudaMalloc(&ab.task_res, ab.cap_tasks * 2 * sizeof(uint32_t)));
-  }
-  if (total > 0) {
-    expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ref, n, ab.candbits, ab.task_off, ab.tasks);
-    CATT_CUDA(cudaGetLastError());
-    *launches += 1;
-  }
+  expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ref, n, ab.canonbits, ab.task_off, ab.tasks, ab.cap_tasks, ab.counters);
+  CATT_CUDA(cudaGetLastError());
+  *launches += 3;      // cub scan = 2 kernels
   return CATT_OK;
 }
 
-int launch_sw(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int64_t ntasks, int sm_count, cudaStream_t st, int* launches) {
-  if (ntasks == 0) return CATT_OK;
+int launch_sw(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int sm_count, cudaStream_t st, int* launches) {
   *launches += 1;
-  return dispatch_sw(ref, reads, ab.tasks, ntasks, ab.task_res, sm_count, st);
+  return dispatch_sw<false>(ref, reads, ab.tasks, ab.task_off + reads.n, ab.cap_tasks, ab.task_score, sm_count, st);
 }
 
-int launch_select(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int64_t first_ordinal, int min_score,
+// selection, the TRACK pass over the winners, CIGAR facts, traceback of the rare gapped winners
+int launch_select(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int64_t first_ordinal, int min_score, int sm_count,
                   cudaStream_t st, int* launches) {
   if (reads.n == 0) return CATT_OK;
-  select_kernel<<<(unsigned)((reads.n + 127) / 128), 128, 0, st>>>(ref, reads, ab.tasks, ab.task_off, ab.task_res, first_ordinal,
-                                                                   min_score, ab.recs, ab.gapped_list, ab.counters);
+  select_kernel<<<(unsigned)((reads.n + 127) / 128), 128, 0, st>>>(ref, reads, ab.candbits, ab.tasks, ab.task_off, ab.task_score,
+                                                                   ab.cap_tasks, first_ordinal, min_score, ab.recs, ab.wtasks, ab.counters);
   CATT_CUDA(cudaGetLastError());
-  *launches += 1;
-  return CATT_OK;
-}
-
-int launch_traceback(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int64_t n_gapped, cudaStream_t st, int* launches) {
-  if (n_gapped == 0) return CATT_OK;
+  int rc = dispatch_sw<true>(ref, reads, ab.wtasks, reinterpret_cast<const uint32_t*>(ab.counters + 7), reads.n, ab.wres, sm_count, st);
+  if (rc) return rc;
+  finish_kernel<<<(unsigned)((reads.n + 127) / 128), 128, 0, st>>>(ref, reads, ab.wtasks, ab.wres, ab.recs, ab.gapped_list, ab.counters);
+  CATT_CUDA(cudaGetLastError());
   const size_t smem = (size_t)7 * (MAX_READ + 2) * sizeof(int16_t) + MAX_READ + (size_t)reads.max_len * ref.maxlen + 16;
   if (smem > 220 * 1024) {
     set_error("traceback tile (%zu bytes) exceeds shared memory", smem);
@@ -532,10 +575,9 @@ int launch_traceback(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab,
   }
   static size_t attr = 0;
   if (smem > attr) { CATT_CUDA(cudaFuncSetAttribute(traceback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
-  const int grid = (int)std::min<int64_t>(n_gapped, 148 * 8);
-  traceback_kernel<<<grid, 32, smem, st>>>(ref, reads, ab.gapped_list, n_gapped, ab.recs);
+  traceback_kernel<<<sm_count * 4, 32, smem, st>>>(ref, reads, ab.gapped_list, ab.counters, ab.recs);
   CATT_CUDA(cudaGetLastError());
-  *launches += 1;
+  *launches += 4;
   return CATT_OK;
 }
 
@@ -545,16 +587,20 @@ int launch_sw_pairs(const RefDev& ref, const ReadsDev& reads, const int32_t* d_r
   if (n == 0) return CATT_OK;
   SwTask* tasks = nullptr;
   uint32_t* res = nullptr;
+  uint32_t* d_n = nullptr;
   CATT_CUDA(cudaMalloc(&tasks, n * sizeof(SwTask)));
   CATT_CUDA(cudaMalloc(&res, n * 2 * sizeof(uint32_t)));
+  CATT_CUDA(cudaMalloc(&d_n, sizeof(uint32_t)));
+  const uint32_t n32 = (uint32_t)n;
+  CATT_CUDA(cudaMemcpyAsync(d_n, &n32, sizeof n32, cudaMemcpyHostToDevice, st));
   make_pair_tasks<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, d_rid, d_strand, tasks);
-  int rc = dispatch_sw(ref, reads, tasks, n, res, sm_count, st);
+  int rc = dispatch_sw<true>(ref, reads, tasks, d_n, n, res, sm_count, st);
   if (rc == CATT_OK) {
     unpack_pair_res<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, res, d_out3);
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) rc = cuda_fail(e, "sw_pairs", __FILE__, __LINE__);
   }
-  cudaFree(tasks); cudaFree(res);
+  cudaFree(tasks); cudaFree(res); cudaFree(d_n);
   return rc;
 }
 

@@ -100,6 +100,7 @@ typedef struct catt_info {
   int64_t gapped_v, gapped_j; /* winners that needed the traceback kernel */
   int64_t kernel_launches;    /* CUDA kernels launched for this result */
   double ms_seed, ms_sw, ms_select, ms_extract, ms_pool, ms_h2d, ms_d2h, ms_host;  /* device/host stage times */
+  int64_t cells_computed_v, cells_computed_j; /* DP cells actually computed: byte-identical records are scored once */
 } catt_info;
 
 /* ---- lifecycle --------------------------------------------------------------------------------------------- */
