@@ -22,7 +22,7 @@ class Config(C.Structure):
                 ("inner_c", C.c_char_p), ("inner_f", C.c_char_p), ("coffset", C.c_int32), ("foffset", C.c_int32),
                 ("min_score", C.c_int32), ("kmer", C.c_int32), ("julia_nthreads", C.c_int32), ("allow_v", C.c_int32),
                 ("allow_j", C.c_int32), ("device", C.c_int32), ("n_d", C.c_int32), ("d_names", C.POINTER(C.c_char_p)),
-                ("d_seqs", C.POINTER(C.c_char_p))]
+                ("d_seqs", C.POINTER(C.c_char_p)), ("keep_records", C.c_int32), ("chunk_reads", C.c_int32)]
 
 
 ALN_DTYPE = np.dtype([("ordinal", "<i4"), ("rid", "<i4"), ("strand", "<i2"), ("mapped", "<i2"), ("as", "<i2"), ("qb", "<i2"),
@@ -43,7 +43,8 @@ class Info(C.Structure):
                                          "full_pushed", "vpart", "jpart", "direct", "left", "rescued", "cand_v", "cand_j",
                                          "cells_v", "cells_j", "gapped_v", "gapped_j", "kernel_launches")] + \
                [(k, C.c_double) for k in ("ms_seed", "ms_sw", "ms_select", "ms_extract", "ms_pool", "ms_h2d", "ms_d2h", "ms_host")] + \
-               [(k, C.c_int64) for k in ("cells_computed_v", "cells_computed_j")]
+               [(k, C.c_int64) for k in ("cells_computed_v", "cells_computed_j")] + \
+               [(k, C.c_double) for k in ("ms_order", "ms_pack")]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved_"}

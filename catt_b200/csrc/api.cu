@@ -8,6 +8,8 @@
 #include <string>
 #include <vector>
 
+#include <omp.h>
+
 #include "host_types.h"
 
 namespace catt {
@@ -33,14 +35,13 @@ int upload_reads(const PackedReads& pr, int64_t n, DeviceReads* dr, cudaStream_t
 int ensure_align_buffers(AlignBuffers& ab, const RefDev& ref, int64_t n) {
   if (!ab.counters) CATT_CUDA(cudaMalloc(&ab.counters, N_COUNTERS * sizeof(unsigned long long)));
   if (n <= ab.cap_reads) return CATT_OK;
-  cudaFree(ab.candbits); cudaFree(ab.canonbits); cudaFree(ab.ntask); cudaFree(ab.task_off); cudaFree(ab.recs); cudaFree(ab.gapped_list);
+  cudaFree(ab.candbits); cudaFree(ab.canonbits); cudaFree(ab.ntask); cudaFree(ab.task_off); cudaFree(ab.gapped_list);
   cudaFree(ab.wtasks); cudaFree(ab.wres);
   ab.cap_reads = n + n / 8 + 64;
   CATT_CUDA(cudaMalloc(&ab.candbits, ab.cap_reads * ref.CW * sizeof(uint32_t)));
   CATT_CUDA(cudaMalloc(&ab.canonbits, ab.cap_reads * ref.CW * sizeof(uint32_t)));
   CATT_CUDA(cudaMalloc(&ab.ntask, (ab.cap_reads + 1) * sizeof(uint32_t)));
   CATT_CUDA(cudaMalloc(&ab.task_off, (ab.cap_reads + 1) * sizeof(uint32_t)));
-  CATT_CUDA(cudaMalloc(&ab.recs, ab.cap_reads * sizeof(catt_aln)));
   CATT_CUDA(cudaMalloc(&ab.gapped_list, ab.cap_reads * sizeof(uint32_t)));
   CATT_CUDA(cudaMalloc(&ab.wtasks, ab.cap_reads * sizeof(SwTask)));
   CATT_CUDA(cudaMalloc(&ab.wres, ab.cap_reads * 2 * sizeof(uint32_t)));
@@ -49,15 +50,33 @@ int ensure_align_buffers(AlignBuffers& ab, const RefDev& ref, int64_t n) {
 
 void free_align_buffers(AlignBuffers& ab) {
   cudaFree(ab.candbits); cudaFree(ab.canonbits); cudaFree(ab.ntask); cudaFree(ab.task_off); cudaFree(ab.tasks); cudaFree(ab.task_score);
-  cudaFree(ab.recs); cudaFree(ab.gapped_list); cudaFree(ab.wtasks); cudaFree(ab.wres); cudaFree(ab.counters); cudaFree(ab.cub_tmp);
+  cudaFree(ab.gapped_list); cudaFree(ab.wtasks); cudaFree(ab.wres); cudaFree(ab.counters); cudaFree(ab.cub_tmp);
   cudaFree(ab.seed_scratch);
   ab = AlignBuffers{};
 }
 
-// Stage A for one reference set; the records stay in ab.recs.  Everything is queued on the stream without a host round
-// trip (task counts, winner counts and the gapped list are consumed on the device); one sync at the end reads the
-// counters.  If the task buffer turned out too small the stage is re-run once with the exact size.
-int align_refset(catt_ctx* c, int which, const ReadsDev& reads, int64_t first_ordinal, catt_info* info, int* launches) {
+// Stage A (map2align) of one reference set for one chunk of reads, queued on the stream without a host round trip: task
+// counts, winner counts and the gapped list are consumed on the device.  align_finish() reads the counters after the
+// caller's stream sync; if the task buffer turned out too small the chunk is re-run once with the exact size.
+int align_tail(catt_ctx* c, int which, const ReadsDev& reads, catt_aln* recs, int64_t first_ordinal, int* launches) {
+  RefSet& rs = which ? c->J : c->V;
+  AlignBuffers& ab = c->ab[which];
+  cudaStream_t st = c->stream;
+  cudaEvent_t* ev = c->ev_a[which];
+  int rc;
+  CATT_CUDA(cudaEventRecord(ev[2], st));
+  if ((rc = launch_expand(rs.dev, reads, ab, st, launches))) return rc;
+  CATT_CUDA(cudaEventRecord(ev[3], st));
+  if ((rc = launch_sw(rs.dev, reads, ab, c->sm_count, st, launches))) return rc;
+  CATT_CUDA(cudaEventRecord(ev[4], st));
+  if ((rc = launch_select(rs.dev, reads, ab, recs, first_ordinal, c->min_score, c->sm_count, st, launches))) return rc;
+  CATT_CUDA(cudaEventRecord(ev[5], st));
+  CATT_CUDA(cudaMemcpyAsync(c->pin[PIN_CNT].as<unsigned long long>() + which * N_COUNTERS, ab.counters, N_COUNTERS * sizeof(unsigned long long),
+                            cudaMemcpyDeviceToHost, st));
+  return CATT_OK;
+}
+
+int align_queue(catt_ctx* c, int which, const ReadsDev& reads, catt_aln* recs, int64_t first_ordinal, int* launches) {
   RefSet& rs = which ? c->J : c->V;
   AlignBuffers& ab = c->ab[which];
   cudaStream_t st = c->stream;
@@ -66,43 +85,119 @@ int align_refset(catt_ctx* c, int which, const ReadsDev& reads, int64_t first_or
   if ((rc = ensure_align_buffers(ab, rs.dev, reads.n))) return rc;
   CATT_CUDA(cudaMemsetAsync(ab.counters, 0, N_COUNTERS * sizeof(unsigned long long), st));
   CATT_CUDA(cudaMemsetAsync(ab.ntask, 0, (reads.n + 1) * sizeof(uint32_t), st));
-  CATT_CUDA(cudaEventRecord(c->ev[0], st));
+  CATT_CUDA(cudaEventRecord(c->ev_a[which][0], st));
   if ((rc = launch_seed(rs.dev, reads, ab, c->sm_count, st, launches))) return rc;
-  CATT_CUDA(cudaEventRecord(c->ev[1], st));
-  unsigned long long cnt[N_COUNTERS];
+  CATT_CUDA(cudaEventRecord(c->ev_a[which][1], st));
+  return align_tail(c, which, reads, recs, first_ordinal, launches);
+}
+
+int align_finish(catt_ctx* c, int which, const ReadsDev& reads, catt_aln* recs, int64_t first_ordinal, catt_info* info, int* launches) {
+  if (reads.n == 0) return CATT_OK;
+  AlignBuffers& ab = c->ab[which];
+  cudaStream_t st = c->stream;
+  cudaEvent_t* ev = c->ev_a[which];
+  unsigned long long* cnt = c->pin[PIN_CNT].as<unsigned long long>() + which * N_COUNTERS;
   float ms_seed = 0, ms_exp = 0, ms_sw = 0, ms_sel = 0;
-  for (int attempt = 0; attempt < 2; attempt++) {
-    if (attempt) {
-      if ((rc = ensure_task_buffers(ab, (int64_t)cnt[9] + (int64_t)cnt[9] / 8 + 1024))) return rc;
-      unsigned long long z[N_COUNTERS] = {0};
-      z[4] = cnt[4]; z[6] = cnt[6];
-      CATT_CUDA(cudaMemcpyAsync(ab.counters, z, sizeof z, cudaMemcpyHostToDevice, st));
-      CATT_CUDA(cudaStreamSynchronize(st));
-    }
-    CATT_CUDA(cudaEventRecord(c->ev[7], st));
-    if ((rc = launch_expand(rs.dev, reads, ab, st, launches))) return rc;
-    CATT_CUDA(cudaEventRecord(c->ev[2], st));
-    if ((rc = launch_sw(rs.dev, reads, ab, c->sm_count, st, launches))) return rc;
-    CATT_CUDA(cudaEventRecord(c->ev[3], st));
-    if ((rc = launch_select(rs.dev, reads, ab, first_ordinal, c->min_score, c->sm_count, st, launches))) return rc;
-    CATT_CUDA(cudaEventRecord(c->ev[4], st));
-    CATT_CUDA(cudaMemcpyAsync(cnt, ab.counters, sizeof cnt, cudaMemcpyDeviceToHost, st));
-    CATT_CUDA(cudaStreamSynchronize(st));
+  cudaEventElapsedTime(&ms_seed, ev[0], ev[1]);
+  int rc;
+  for (int attempt = 0;; attempt++) {
     if (cnt[6] > 0) { set_error("%llu reads exceed the seeding run-list capacity", cnt[6]); return CATT_E_LIMIT; }
     float a = 0, b = 0, d = 0;
-    cudaEventElapsedTime(&a, c->ev[7], c->ev[2]);
-    cudaEventElapsedTime(&b, c->ev[2], c->ev[3]);
-    cudaEventElapsedTime(&d, c->ev[3], c->ev[4]);
+    cudaEventElapsedTime(&a, ev[2], ev[3]);
+    cudaEventElapsedTime(&b, ev[3], ev[4]);
+    cudaEventElapsedTime(&d, ev[4], ev[5]);
     ms_exp += a; ms_sw += b; ms_sel += d;
     if (cnt[9] == 0) break;
     if (attempt == 1) { set_error("SW task buffer overflow persists (%llu tasks)", cnt[9]); return CATT_E_LIMIT; }
+    if ((rc = ensure_task_buffers(ab, (int64_t)cnt[9] + (int64_t)cnt[9] / 8 + 1024))) return rc;
+    unsigned long long z[N_COUNTERS] = {0};
+    z[4] = cnt[4]; z[6] = cnt[6];
+    CATT_CUDA(cudaMemcpyAsync(ab.counters, z, sizeof z, cudaMemcpyHostToDevice, st));
+    CATT_CUDA(cudaStreamSynchronize(st));
+    if ((rc = align_tail(c, which, reads, recs, first_ordinal, launches))) return rc;
+    CATT_CUDA(cudaStreamSynchronize(st));
   }
-  cudaEventElapsedTime(&ms_seed, c->ev[0], c->ev[1]);
   if (info) {
     info->ms_seed += ms_seed + ms_exp; info->ms_sw += ms_sw; info->ms_select += ms_sel;
-    if (which) { info->cand_j = (int64_t)cnt[0]; info->cells_j = (int64_t)cnt[1]; info->gapped_j = (int64_t)cnt[2]; info->j_hits = (int64_t)cnt[3]; info->cells_computed_j = (int64_t)cnt[8]; }
-    else { info->cand_v = (int64_t)cnt[0]; info->cells_v = (int64_t)cnt[1]; info->gapped_v = (int64_t)cnt[2]; info->v_hits = (int64_t)cnt[3]; info->cells_computed_v = (int64_t)cnt[8]; }
+    if (which) { info->cand_j += (int64_t)cnt[0]; info->cells_j += (int64_t)cnt[1]; info->gapped_j += (int64_t)cnt[2]; info->j_hits += (int64_t)cnt[3]; info->cells_computed_j += (int64_t)cnt[8]; }
+    else { info->cand_v += (int64_t)cnt[0]; info->cells_v += (int64_t)cnt[1]; info->gapped_v += (int64_t)cnt[2]; info->v_hits += (int64_t)cnt[3]; info->cells_computed_v += (int64_t)cnt[8]; }
   }
+  return CATT_OK;
+}
+
+int ensure_recs(catt_ctx* c, int64_t n) {
+  int rc;
+  for (int which = 0; which < 2; which++)
+    if ((rc = c->recs_all[which].ensure((size_t)std::max<int64_t>(n, 1) * sizeof(catt_aln)))) return rc;
+  return CATT_OK;
+}
+
+// Stage A over reads that are already resident: chunk by chunk (bounded scratch), records into ctx->recs_all
+int stage_a_resident(catt_ctx* c, const DeviceReads& dr, int64_t first_ordinal, catt_info* info, int* launches) {
+  int rc;
+  if ((rc = ensure_recs(c, dr.n))) return rc;
+  for (int64_t i0 = 0; i0 < dr.n; i0 += c->chunk_reads) {
+    const int64_t cnt = std::min<int64_t>(c->chunk_reads, dr.n - i0);
+    const ReadsDev rv = dr.view(i0, cnt);
+    for (int which = 0; which < 2; which++)
+      if ((rc = align_queue(c, which, rv, c->recs_all[which].as<catt_aln>() + i0, first_ordinal + i0, launches))) return rc;
+    CATT_CUDA(cudaStreamSynchronize(c->stream));
+    for (int which = 0; which < 2; which++)
+      if ((rc = align_finish(c, which, rv, c->recs_all[which].as<catt_aln>() + i0, first_ordinal + i0, info, launches))) return rc;
+  }
+  return CATT_OK;
+}
+
+// Host reads -> ctx->rd_* on the device, Stage A pipelined: while the kernels of chunk i run, the host threads pack chunk
+// i+1 into pinned staging and the copy stream moves it to HBM.
+int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool align, DeviceReads* view, catt_info* info, int* launches) {
+  const int64_t n = hr.n;
+  int rc;
+  const double t0 = now_ms();
+  if ((rc = c->pin[PIN_OFF].ensure((size_t)(n + 1) * sizeof(uint32_t))) || (rc = c->pin[PIN_LEN].ensure((size_t)std::max<int64_t>(n, 1) * sizeof(int32_t)))) return rc;
+  uint32_t* h_off = c->pin[PIN_OFF].as<uint32_t>();
+  int32_t* h_len = c->pin[PIN_LEN].as<int32_t>();
+  int max_len = 0;
+  if ((rc = pack_layout(n, hr.seq_off, h_off, h_len, &max_len))) return rc;
+  const uint64_t total_words = h_off[n];
+  if ((rc = c->rd_words.ensure((total_words + 4) * sizeof(uint32_t))) || (rc = c->rd_off.ensure((size_t)(n + 1) * sizeof(uint32_t))) ||
+      (rc = c->rd_len.ensure((size_t)std::max<int64_t>(n, 1) * sizeof(int32_t))) || (rc = ensure_recs(c, n))) return rc;
+  DeviceReads dr;
+  dr.words = c->rd_words.as<uint32_t>(); dr.off = c->rd_off.as<uint32_t>(); dr.len = c->rd_len.as<int32_t>(); dr.n = n; dr.max_len = max_len;
+  *view = dr;
+  cudaStream_t st = c->stream, cs = c->copy_stream;
+  CATT_CUDA(cudaMemcpyAsync(dr.off, h_off, (size_t)(n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  CATT_CUDA(cudaMemcpyAsync(dr.len, h_len, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  const int64_t chunk = c->chunk_reads;
+  const int64_t nchunks = (n + chunk - 1) / chunk;
+  auto stage_chunk = [&](int64_t ci) -> int {           // pack chunk ci into its staging buffer and start its H2D
+    const int64_t i0 = ci * chunk, i1 = std::min<int64_t>(n, i0 + chunk);
+    const size_t words = (size_t)(h_off[i1] - h_off[i0]);
+    PinBuf& pb = c->pin[PIN_PACK0 + (ci & 1)];
+    if (ci >= 2) CATT_CUDA(cudaEventSynchronize(c->ev_h2d[ci & 1]));      // the copy that last read this buffer
+    int r = pb.ensure((words + 4) * sizeof(uint32_t));
+    if (r) return r;
+    pack_range(i0, i1, hr.seqs, hr.seq_off, h_off, pb.as<uint32_t>());
+    CATT_CUDA(cudaMemcpyAsync(dr.words + h_off[i0], pb.p, words * sizeof(uint32_t), cudaMemcpyHostToDevice, cs));
+    CATT_CUDA(cudaEventRecord(c->ev_h2d[ci & 1], cs));
+    return CATT_OK;
+  };
+  if (nchunks > 0 && (rc = stage_chunk(0))) return rc;
+  if (info) info->ms_pack += now_ms() - t0;
+  for (int64_t ci = 0; ci < nchunks; ci++) {
+    const int64_t i0 = ci * chunk, cnt = std::min<int64_t>(chunk, n - i0);
+    const ReadsDev rv = dr.view(i0, cnt);
+    CATT_CUDA(cudaStreamWaitEvent(st, c->ev_h2d[ci & 1], 0));
+    if (align)
+      for (int which = 0; which < 2; which++)
+        if ((rc = align_queue(c, which, rv, c->recs_all[which].as<catt_aln>() + i0, first_ordinal + i0, launches))) return rc;
+    if (ci + 1 < nchunks && (rc = stage_chunk(ci + 1))) return rc;
+    CATT_CUDA(cudaStreamSynchronize(st));
+    if (align)
+      for (int which = 0; which < 2; which++)
+        if ((rc = align_finish(c, which, rv, c->recs_all[which].as<catt_aln>() + i0, first_ordinal + i0, info, launches))) return rc;
+  }
+  CATT_CUDA(cudaStreamSynchronize(st));
   return CATT_OK;
 }
 
@@ -153,7 +248,7 @@ int download_records(catt_ctx* c, int64_t n, catt_result* R) {
   for (int which = 0; which < 2; which++) {
     R->rec[which].resize(n);
     const double td = now_ms();
-    CATT_CUDA(cudaMemcpy(R->rec[which].data(), c->ab[which].recs, n * sizeof(catt_aln), cudaMemcpyDeviceToHost));
+    if (n) CATT_CUDA(cudaMemcpy(R->rec[which].data(), c->recs_all[which].p, n * sizeof(catt_aln), cudaMemcpyDeviceToHost));
     R->info.ms_d2h += now_ms() - td;
   }
   return CATT_OK;
@@ -162,30 +257,14 @@ int download_records(catt_ctx* c, int64_t n, catt_result* R) {
 int run_all(catt_ctx* c, const HostReads& hr, catt_result** out) {
   std::unique_ptr<catt_result> R(new catt_result());
   int launches = 0;
-  const double t0 = now_ms();
-  Trace tr0;
-  PackedReads pr;
-  int rc = pack_reads(hr.n, hr.seqs, hr.seq_off, &pr);
-  if (rc) return rc;
-  R->info.ms_host += now_ms() - t0;
-  tr0.lap("run_all: pack_reads");
-  DeviceReads dr;
-  CATT_CUDA(cudaEventRecord(c->ev[5], c->stream));
-  if ((rc = upload_reads(pr, hr.n, &dr, c->stream))) return rc;
-  CATT_CUDA(cudaEventRecord(c->ev[6], c->stream));
-  CATT_CUDA(cudaStreamSynchronize(c->stream));
-  tr0.lap("run_all: alloc + H2D");
-  { float ms = 0; cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]); R->info.ms_h2d += ms; }
-  R->info.n_reads = hr.n;
   Trace tr;
-  for (int which = 0; which < 2 && rc == CATT_OK; which++) rc = align_refset(c, which, dr.view(), 0, &R->info, &launches);
-  tr.lap("run_all: align V+J");
-  if (rc == CATT_OK) rc = download_records(c, hr.n, R.get());
-  tr.lap("run_all: records D2H");
-  if (rc == CATT_OK) rc = stage_b(c, hr, dr, R.get(), &launches);
+  R->info.n_reads = hr.n;
+  DeviceReads dr;
+  int rc = stage_a_stream(c, hr, 0, true, &dr, &R->info, &launches);
+  tr.lap("run_all: pack + H2D + align (pipelined)");
+  if (rc == CATT_OK && c->keep_records) rc = download_records(c, hr.n, R.get());
+  if (rc == CATT_OK) rc = stage_b(c, hr, dr.view(), R.get(), &launches);
   tr.lap("run_all: stage_b");
-  dr.release();
-  tr.lap("run_all: free reads");
   if (rc) return rc;
   R->info.kernel_launches = launches;
   *out = R.release();
@@ -253,8 +332,15 @@ int catt_ctx_create(catt_ctx** out, const catt_config* cfg) {
     CATT_CUDA(cudaMemcpy(c->d_dseq, cat.data(), cat.size(), cudaMemcpyHostToDevice));
     CATT_CUDA(cudaMemcpy(c->d_doff, off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   }
+  c->keep_records = cfg->keep_records != 0;
+  if (cfg->chunk_reads > 0) c->chunk_reads = cfg->chunk_reads;
+  if (const char* e = getenv("CATT_CHUNK_READS")) { const long long v = atoll(e); if (v > 0) c->chunk_reads = v; }
   CATT_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CATT_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   for (auto& ev : c->ev) CATT_CUDA(cudaEventCreate(&ev));
+  for (auto& row : c->ev_a) for (auto& ev : row) CATT_CUDA(cudaEventCreate(&ev));
+  for (auto& ev : c->ev_h2d) CATT_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  if ((rc = c->pin[PIN_CNT].ensure(1024))) return rc;
   *out = c.release();
   return CATT_OK;
 }
@@ -265,9 +351,15 @@ void catt_ctx_destroy(catt_ctx* c) {
   c->V.release(); c->J.release();
   free_align_buffers(c->ab[0]); free_align_buffers(c->ab[1]);
   for (auto& b : c->sb) b.release();
+  for (auto& b : c->pin) b.release();
+  for (auto& b : c->recs_all) b.release();
+  c->rd_words.release(); c->rd_off.release(); c->rd_len.release();
   cudaFree(c->d_finder); cudaFree(c->d_dseq); cudaFree(c->d_doff);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+  for (auto& row : c->ev_a) for (auto& ev : row) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : c->ev_h2d) if (ev) cudaEventDestroy(ev);
   if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   delete c;
 }
 
@@ -308,7 +400,7 @@ int catt_run_file(catt_ctx* c, const char* path, catt_result** out) {
 int catt_result_info(const catt_result* r, catt_info* out) { if (!r || !out) return CATT_E_ARG; *out = r->info; return CATT_OK; }
 int catt_result_reads(const catt_result* r, int which, const catt_read** reads, int64_t* n) {
   if (!r || !reads || !n || which < 0 || which > 1) return CATT_E_ARG;
-  *reads = r->part[which].data(); *n = (int64_t)r->part[which].size();
+  *reads = r->part[which]; *n = r->npart[which];
   return CATT_OK;
 }
 int catt_align_records(const catt_result* r, int which, const catt_aln** recs, int64_t* n) {
@@ -361,11 +453,7 @@ int catt_batch_align(catt_ctx* c, catt_batch* b) {
   b->info = catt_info{};
   b->info.n_reads = b->dr.n;
   int launches = 0, rc;
-  Trace tr;
-  for (int which = 0; which < 2; which++) {
-    if ((rc = align_refset(c, which, b->dr.view(), b->first_ordinal, &b->info, &launches))) return rc;
-    tr.lap(which ? "align J" : "align V");
-  }
+  if ((rc = stage_a_resident(c, b->dr, b->first_ordinal, &b->info, &launches))) return rc;
   b->info.kernel_launches = launches;
   return CATT_OK;
 }
@@ -379,8 +467,9 @@ int catt_batch_sync(catt_ctx* c, catt_batch* b, catt_info* info) {
 
 int catt_batch_download(catt_ctx* c, catt_batch* b, catt_aln* v_out, catt_aln* j_out) {
   if (!c || !b) return CATT_E_ARG;
-  if (v_out) CATT_CUDA(cudaMemcpy(v_out, c->ab[0].recs, b->dr.n * sizeof(catt_aln), cudaMemcpyDeviceToHost));
-  if (j_out) CATT_CUDA(cudaMemcpy(j_out, c->ab[1].recs, b->dr.n * sizeof(catt_aln), cudaMemcpyDeviceToHost));
+  if (b->dr.n == 0) return CATT_OK;
+  if (v_out) CATT_CUDA(cudaMemcpy(v_out, c->recs_all[0].p, b->dr.n * sizeof(catt_aln), cudaMemcpyDeviceToHost));
+  if (j_out) CATT_CUDA(cudaMemcpy(j_out, c->recs_all[1].p, b->dr.n * sizeof(catt_aln), cudaMemcpyDeviceToHost));
   return CATT_OK;
 }
 
@@ -388,34 +477,43 @@ void catt_batch_free(catt_batch* b) { if (b) { b->dr.release(); delete b; } }
 
 int catt_align_shard(catt_ctx* c, int64_t n, const char* seqs, const int64_t* seq_off, int64_t first_ordinal, catt_aln* v_out,
                      catt_aln* j_out) {
-  catt_batch* b = nullptr;
-  int rc = catt_batch_upload(c, n, seqs, seq_off, first_ordinal, &b);
-  if (rc) return rc;
-  rc = catt_batch_align(c, b);
-  if (!rc) rc = catt_batch_download(c, b, v_out, j_out);
-  catt_batch_free(b);
-  return rc;
+  if (!c || n < 0 || (n > 0 && (!seqs || !seq_off))) { set_error("catt_align_shard: bad argument"); return CATT_E_ARG; }
+  CATT_CUDA(cudaSetDevice(c->device));
+  HostReads hr;
+  hr.n = n; hr.seqs = seqs; hr.seq_off = seq_off;
+  DeviceReads dr;
+  catt_info info{};
+  int launches = 0;
+  int rc = stage_a_stream(c, hr, first_ordinal, true, &dr, &info, &launches);
+  if (rc || n == 0) return rc;
+  if (v_out) CATT_CUDA(cudaMemcpy(v_out, c->recs_all[0].p, n * sizeof(catt_aln), cudaMemcpyDeviceToHost));
+  if (j_out) CATT_CUDA(cudaMemcpy(j_out, c->recs_all[1].p, n * sizeof(catt_aln), cudaMemcpyDeviceToHost));
+  return CATT_OK;
 }
 
 int catt_assemble(catt_ctx* c, int64_t n, const char* names, const int64_t* name_off, const char* seqs, const int64_t* seq_off,
                   const char* quals, const catt_aln* v_recs, const catt_aln* j_recs, catt_result** out) {
-  if (!c || !out || !v_recs || !j_recs || n < 0) { set_error("catt_assemble: bad argument"); return CATT_E_ARG; }
+  if (!c || !out || n < 0 || (n > 0 && (!v_recs || !j_recs || !names || !name_off || !seqs || !seq_off))) { set_error("catt_assemble: bad argument"); return CATT_E_ARG; }
   CATT_CUDA(cudaSetDevice(c->device));
   HostReads hr;
   hr.n = n; hr.names = names; hr.name_off = name_off; hr.seqs = seqs; hr.seq_off = seq_off; hr.quals = quals;
   std::unique_ptr<catt_result> R(new catt_result());
   R->info.n_reads = n;
-  R->rec[0].assign(v_recs, v_recs + n); R->rec[1].assign(j_recs, j_recs + n);
-  for (int64_t i = 0; i < n; i++) { R->info.v_hits += v_recs[i].mapped; R->info.j_hits += j_recs[i].mapped; }
-  PackedReads pr;
-  int rc = pack_reads(n, seqs, seq_off, &pr);
-  if (rc) return rc;
+  int64_t vh = 0, jh = 0;
+  #pragma omp parallel for reduction(+ : vh, jh) schedule(static)
+  for (int64_t i = 0; i < n; i++) { vh += v_recs[i].mapped != 0; jh += j_recs[i].mapped != 0; }
+  R->info.v_hits = vh; R->info.j_hits = jh;
   DeviceReads dr;
-  if ((rc = upload_reads(pr, n, &dr, c->stream))) return rc;
-  CATT_CUDA(cudaStreamSynchronize(c->stream));
   int launches = 0;
-  rc = stage_b(c, hr, dr, R.get(), &launches);
-  dr.release();
+  int rc = stage_a_stream(c, hr, 0, false, &dr, &R->info, &launches);      // pack + upload only
+  if (rc) return rc;
+  if (n) {
+    CATT_CUDA(cudaMemcpyAsync(c->recs_all[0].p, v_recs, n * sizeof(catt_aln), cudaMemcpyHostToDevice, c->stream));
+    CATT_CUDA(cudaMemcpyAsync(c->recs_all[1].p, j_recs, n * sizeof(catt_aln), cudaMemcpyHostToDevice, c->stream));
+    CATT_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  if (c->keep_records) { R->rec[0].assign(v_recs, v_recs + n); R->rec[1].assign(j_recs, j_recs + n); }
+  rc = stage_b(c, hr, dr.view(), R.get(), &launches);
   if (rc) return rc;
   R->info.kernel_launches = launches;
   *out = R.release();
@@ -423,7 +521,7 @@ int catt_assemble(catt_ctx* c, int64_t n, const char* names, const int64_t* name
 }
 
 // Stage B on a batch that is already resident in HBM and aligned (catt_batch_align): used for the device-resident
-// throughput number.  The host buffers are still needed for QNAME dedup and to materialise the Myread strings.
+// throughput number.  The host buffers are still needed for the QNAMEs and to materialise the Myread strings.
 int catt_batch_assemble(catt_ctx* c, catt_batch* b, const char* names, const int64_t* name_off, const char* seqs,
                         const int64_t* seq_off, const char* quals, catt_result** out) {
   if (!c || !b || !out) { set_error("catt_batch_assemble: bad argument"); return CATT_E_ARG; }
@@ -433,13 +531,11 @@ int catt_batch_assemble(catt_ctx* c, catt_batch* b, const char* names, const int
   hr.n = n; hr.names = names; hr.name_off = name_off; hr.seqs = seqs; hr.seq_off = seq_off; hr.quals = quals;
   std::unique_ptr<catt_result> R(new catt_result());
   R->info = b->info;
-  Trace tr;
-  int rc = download_records(c, n, R.get());
+  int rc = CATT_OK;
+  if (c->keep_records) rc = download_records(c, n, R.get());
   if (rc) return rc;
-  tr.lap("records D2H");
   int launches = (int)b->info.kernel_launches;
-  rc = stage_b(c, hr, b->dr, R.get(), &launches);
-  tr.lap("stage_b total");
+  rc = stage_b(c, hr, b->dr.view(), R.get(), &launches);
   if (rc) return rc;
   R->info.kernel_launches = launches;
   *out = R.release();

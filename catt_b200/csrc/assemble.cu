@@ -1,148 +1,366 @@
 // assemble.cu — Stage B: from per-read alignment records to Vpart / Jpart (catt.jl:186-339 after the SAM files exist,
 // plus the pool / extension / finder!(array) part of catt(), catt.jl:544-577).
 //
-// Host-side glue restated here (what the reference does with samtools / awk / Julia containers between the stages; none
-// of it is a CPU fallback for a kernel):
-//   * `samtools sort -t AS | view -F 2308 | tac | awk '!a[$1]++'` (catt.jl:45-48): descending (AS, tid, pos, strand)
-//     order, later input first on complete ties, first record per trimmed QNAME                         [SURVEY A7]
-//   * get_kmer_fromsam / get_err_fromsam (catt.jl:153-184) as samtools stats prints them                [SURVEY A8]
-//   * share_name, the NR % nthreads chunk order, the name-sorted both-mapped pairing (catt.jl:221-319)
-//   * Myread string materialisation (catt.jl:104,125-126,302-304; Jtool.jl:364-365; catt.jl:378-379,420-421)
-// The per-record work (assignV/J, real_score, finder!, k-mer table, extension) runs in extract.cu / pool.cu.
-// Sorting and string work use all host threads (OpenMP); QNAMEs are compared through a 64-bit hash with an exact
-// string check on every hash hit.
+// Everything the reference does between the stages with samtools / awk / Julia containers is restated on the device, on
+// the alignment records Stage A left in HBM (ctx->recs_all), so no per-read data crosses PCIe until the final lists:
+//   * `samtools sort -t AS | view -F 2308 | tac | awk '!a[$1]++'` (catt.jl:45-48): one 61-bit radix key
+//     (AS, tid, pos, strand, input index) sorted descending == descending (AS, tid, pos, strand) with later input first
+//     on complete ties; the awk dedup is an atomicMin of the sorted rank per trimmed QNAME (QNAMEs live in a device
+//     hash set, compared byte-exactly on every hash hit)                                                  [SURVEY A7]
+//   * get_kmer_fromsam / get_err_fromsam (catt.jl:153-184): device sums, formatted on the host as samtools stats
+//     prints them                                                                                          [SURVEY A8]
+//   * share_name, the NR % nthreads chunk order (closed form), the name-sorted both-mapped pairing (LSD radix sort over
+//     8-byte name digits) (catt.jl:221-319)
+//   * assignV/J, real_score, finder!, k-mer table, extension: extract.cu / pool.cu
+// The host only formats two numbers and materialises the Myread strings (the quality strings never leave host memory).
 #include <omp.h>
 #include <stdio.h>
 #include <string.h>
 
 #include <algorithm>
-#include <parallel/algorithm>
-#include <string_view>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "host_types.h"
 
 namespace catt {
 namespace {
 
-inline std::string_view trimmed_name(const HostReads& hr, int64_t i) {       // bwa trim_readno
-  const char* s = hr.names + hr.name_off[i];
-  size_t l = (size_t)(hr.name_off[i + 1] - hr.name_off[i]);
+constexpr uint32_t INF = 0xFFFFFFFFu;
+constexpr unsigned FULL = 0xffffffffu;
+// device counters (SB_CNT, unsigned long long each)
+enum { C_NMAP_V = 0, C_NMAP_J, C_F_V, C_F_J, C_NV, C_NJ, C_NP, C_MAXNAME, C_SUM_LEN, C_SUM_NM, C_SUM_MI, C_MISMATCH, C_M, C_VPART,
+       C_FULL, C_NPARTIAL, C_RESCUED, C_COUNT = 24 };
+
+struct NamesDev { const char* s; const int64_t* off; };
+
+__device__ __forceinline__ int trimmed_len(const char* s, int l) {            // bwa trim_readno
   if (l > 2 && s[l - 2] == '/' && s[l - 1] >= '0' && s[l - 1] <= '9') l -= 2;
-  return std::string_view(s, l);
+  return l;
 }
 
-inline uint64_t name_hash(std::string_view s) {
+// ---- QNAME set: slot_of[i] = equivalence class of read i's trimmed name (only for reads with a V or J hit) ------------
+__global__ void name_kernel(int64_t n, NamesDev nd, const catt_aln* __restrict__ rv, const catt_aln* __restrict__ rj, int32_t* owner,
+                            uint32_t mask, uint32_t* __restrict__ slot_of) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (!(rv[i].mapped || rj[i].mapped)) { slot_of[i] = INF; return; }
+  const char* s = nd.s + nd.off[i];
+  const int l = trimmed_len(s, (int)(nd.off[i + 1] - nd.off[i]));
   uint64_t h = 0xcbf29ce484222325ull;
-  for (unsigned char c : s) { h ^= c; h *= 0x100000001b3ull; }
+  for (int k = 0; k < l; k++) { h ^= (unsigned char)s[k]; h *= 0x100000001b3ull; }
   h ^= h >> 32; h *= 0xd6e8feb86659fd93ull; h ^= h >> 32;
-  return h;
+  uint32_t slot = (uint32_t)h & mask;
+  while (true) {
+    int32_t o = atomicCAS(&owner[slot], -1, (int32_t)i);
+    if (o == -1 || o == (int32_t)i) break;
+    const char* t = nd.s + nd.off[o];
+    const int lt = trimmed_len(t, (int)(nd.off[o + 1] - nd.off[o]));
+    bool same = lt == l;
+    for (int k = 0; same && k < l; k++) same = s[k] == t[k];
+    if (same) break;
+    slot = (slot + 1) & mask;
+  }
+  slot_of[i] = slot;
 }
 
-// open-addressing set of read indices keyed by trimmed QNAME (hash + exact compare)
-struct NameTable {
-  std::vector<int32_t> slot;
-  uint64_t mask = 0;
-  const HostReads* hr = nullptr;
-  const uint64_t* nh = nullptr;
-  void init(size_t n, const HostReads* h, const uint64_t* hashes) {
-    size_t cap = 16;
-    while (cap < n * 2 + 2) cap <<= 1;
-    slot.assign(cap, -1); mask = cap - 1; hr = h; nh = hashes;
+// ---- sort keys of the mapped records --------------------------------------------------------------------------------
+__global__ void key_kernel(int64_t n, const catt_aln* __restrict__ recs, unsigned long long* __restrict__ keys,
+                           unsigned long long* __restrict__ counter) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool m = i < n && recs[i].mapped;
+  const unsigned bal = __ballot_sync(FULL, m);
+  if (!bal) return;
+  const int lane = threadIdx.x & 31;
+  unsigned long long base = 0;
+  if (lane == __ffs(bal) - 1) base = atomicAdd(counter, (unsigned long long)__popc(bal));
+  base = __shfl_sync(FULL, base, __ffs(bal) - 1);
+  if (m) {
+    const catt_aln a = recs[i];
+    keys[base + __popc(bal & ((1u << lane) - 1))] = ((unsigned long long)(uint16_t)a.as << 51) | ((unsigned long long)(uint32_t)a.rid << 42) |
+                                                    ((unsigned long long)(uint16_t)a.rb << 33) | ((unsigned long long)(a.strand & 1) << 32) |
+                                                    (unsigned long long)(uint32_t)i;
   }
-  // index already stored under the name of read i, or -1 (then i is inserted if `insert`)
-  int64_t lookup(int64_t i, bool insert) {
-    uint64_t s = nh[i] & mask;
-    const std::string_view name = trimmed_name(*hr, i);
-    while (true) {
-      const int32_t v = slot[s];
-      if (v < 0) { if (insert) slot[s] = (int32_t)i; return -1; }
-      if (nh[v] == nh[i] && trimmed_name(*hr, v) == name) return v;
-      s = (s + 1) & mask;
-    }
-  }
-};
-
-struct Keyed { uint64_t key; uint32_t idx; };
-
-// final SAM list of one reference set; `tab` ends up holding the kept names
-void final_order(const std::vector<catt_aln>& recs, const HostReads& hr, const uint64_t* nh, std::vector<int64_t>& fin, NameTable& tab) {
-  const int64_t n = (int64_t)recs.size();
-  std::vector<Keyed> keyed;
-  keyed.reserve(n / 2 + 16);
-  for (int64_t i = 0; i < n; i++) {
-    const catt_aln& a = recs[i];
-    if (!a.mapped) continue;
-    keyed.push_back(Keyed{((uint64_t)(uint16_t)a.as << 48) | ((uint64_t)(uint16_t)a.rid << 32) | ((uint64_t)(uint16_t)a.rb << 16) | (uint64_t)(a.strand & 1),
-                          (uint32_t)i});
-  }
-  // ascending stable sort followed by `tac` == descending by (key, input index)
-  __gnu_parallel::sort(keyed.begin(), keyed.end(), [](const Keyed& x, const Keyed& y) { return x.key != y.key ? x.key > y.key : x.idx > y.idx; });
-  tab.init(keyed.size(), &hr, nh);
-  fin.clear();
-  fin.reserve(keyed.size());
-  for (const Keyed& kv : keyed)
-    if (tab.lookup(kv.idx, true) < 0) fin.push_back(kv.idx);
 }
 
-void chunk_order(const std::vector<int64_t>& fin, int T, std::vector<int64_t>& out) {    // catt.jl:228,256-276
-  out.clear();
-  if (T <= 1) { out = fin; return; }
-  out.reserve(fin.size());
-  for (int p = 0; p < T; p++)
-    for (size_t nr = (p == 0 ? (size_t)T : (size_t)p); nr <= fin.size(); nr += T) out.push_back(fin[nr - 1]);
+__global__ void minrank_kernel(int64_t nm, const unsigned long long* __restrict__ sorted, const uint32_t* __restrict__ slot_of,
+                               uint32_t* __restrict__ minrank) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < nm) atomicMin(&minrank[slot_of[(uint32_t)sorted[r]]], (uint32_t)r);
+}
+
+// kept = first record of its QNAME in sorted order; the V list also feeds samtools stats' sums
+__global__ void flag_kernel(int64_t nm, const unsigned long long* __restrict__ sorted, const uint32_t* __restrict__ slot_of,
+                            const uint32_t* __restrict__ minrank, const catt_aln* __restrict__ recs, const int32_t* __restrict__ len,
+                            int stats, uint32_t* __restrict__ flag, unsigned long long* __restrict__ cnt) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long sl = 0, sn = 0, sm = 0;
+  if (r < nm) {
+    const uint32_t idx = (uint32_t)sorted[r];
+    const bool kept = minrank[slot_of[idx]] == (uint32_t)r;
+    flag[r] = kept;
+    if (kept && stats) { sl = (unsigned long long)len[idx]; sn = (unsigned long long)recs[idx].nm; sm = (unsigned long long)recs[idx].mi; }
+  } else if (r == nm) {
+    flag[r] = 0;
+  }
+  if (stats) {
+    #pragma unroll
+    for (int d = 16; d; d >>= 1) { sl += __shfl_xor_sync(FULL, sl, d); sn += __shfl_xor_sync(FULL, sn, d); sm += __shfl_xor_sync(FULL, sm, d); }
+    if ((threadIdx.x & 31) == 0 && sl) { atomicAdd(&cnt[C_SUM_LEN], sl); atomicAdd(&cnt[C_SUM_NM], sn); atomicAdd(&cnt[C_SUM_MI], sm); }
+  }
+}
+
+// position of the nr-th (1-based) line of the final SAM after the `NR % T` split + sequential read-back (catt.jl:228,256-276)
+__device__ __forceinline__ uint32_t chunk_pos(uint32_t nr, uint32_t F, uint32_t T) {
+  if (T <= 1) return nr - 1;
+  const uint32_t p = nr % T;
+  uint32_t start = 0;
+  if (p > 0) {
+    // file 0 holds NR = T, 2T, ...; file q >= 1 holds q, q+T, ...
+    start = F / T;
+    for (uint32_t q = 1; q < p; q++) start += F >= q ? (F - q) / T + 1 : 0;
+  }
+  const uint32_t first = p == 0 ? T : p;
+  return start + (nr - first) / T;
+}
+
+// kept records in the reference's processing order; records of shared QNAMEs leave the part lists and (J side) seed the pairs
+__global__ void order_kernel(int64_t nm, const unsigned long long* __restrict__ sorted, const uint32_t* __restrict__ flag,
+                             const uint32_t* __restrict__ kpos, int T, const uint32_t* __restrict__ slot_of,
+                             const uint32_t* __restrict__ minv, const uint32_t* __restrict__ minj, int which, NamesDev nd,
+                             uint32_t* __restrict__ ord_idx, uint32_t* __restrict__ ord_flag, uint32_t* __restrict__ pair_j,
+                             unsigned long long* __restrict__ cnt) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nm || !flag[r]) return;
+  const uint32_t F = kpos[nm];
+  const uint32_t idx = (uint32_t)sorted[r];
+  const uint32_t y = chunk_pos(kpos[r] + 1, F, (uint32_t)T);
+  const uint32_t slot = slot_of[idx];
+  const bool shared = minv[slot] != INF && minj[slot] != INF;
+  ord_idx[y] = idx;
+  ord_flag[y] = !shared;
+  if (which == 1 && shared) {
+    const unsigned long long p = atomicAdd(&cnt[C_NP], 1ull);
+    pair_j[p] = idx;
+    const char* s = nd.s + nd.off[idx];
+    atomicMax(&cnt[C_MAXNAME], (unsigned long long)trimmed_len(s, (int)(nd.off[idx + 1] - nd.off[idx])));
+  }
+}
+
+__global__ void collect_kernel(const uint32_t* kpos_v, int64_t nm_v, const uint32_t* kpos_j, int64_t nm_j, const uint32_t* opos_v,
+                               const uint32_t* opos_j, unsigned long long* cnt) {
+  cnt[C_F_V] = nm_v ? kpos_v[nm_v] : 0; cnt[C_F_J] = nm_j ? kpos_j[nm_j] : 0;
+  cnt[C_NV] = nm_v ? opos_v[nm_v] : 0; cnt[C_NJ] = nm_j ? opos_j[nm_j] : 0;
+}
+
+// 8-byte big-endian digit `d` of the trimmed QNAME, zero padded: LSD passes over these digits give Julia's String order
+__global__ void pair_key_kernel(int64_t np, const uint32_t* __restrict__ pair_j, NamesDev nd, int d, unsigned long long* __restrict__ keys) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= np) return;
+  const uint32_t idx = pair_j[p];
+  const char* s = nd.s + nd.off[idx];
+  const int l = trimmed_len(s, (int)(nd.off[idx + 1] - nd.off[idx]));
+  unsigned long long k = 0;
+  for (int b = 0; b < 8; b++) { const int pos = d * 8 + b; k = (k << 8) | (pos < l ? (unsigned char)s[pos] : 0u); }
+  keys[p] = k;
+}
+
+__device__ __forceinline__ ExtractItem make_item(const catt_aln& a, uint32_t read, int kind) {
+  ExtractItem it;
+  it.read = read; it.read2 = read; it.kind = (int16_t)kind; it.strand = a.strand; it.qb = a.qb; it.m_end = a.m_end; it.rb = a.rb;
+  it.rid = (int16_t)a.rid; it.j_m_end = 0; it.j_rid = 0; it.j_strand = 0; it.pad_ = 0;
+  return it;
+}
+
+__global__ void part_item_kernel(int64_t F, const uint32_t* __restrict__ ord_idx, const uint32_t* __restrict__ ord_flag,
+                                 const uint32_t* __restrict__ opos, const catt_aln* __restrict__ recs, int kind,
+                                 ExtractItem* __restrict__ items) {
+  const int64_t y = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (y >= F || !ord_flag[y]) return;
+  const uint32_t idx = ord_idx[y];
+  items[opos[y]] = make_item(recs[idx], idx, kind);
+}
+
+__global__ void pair_item_kernel(int64_t np, const uint32_t* __restrict__ pair_j, const uint32_t* __restrict__ slot_of,
+                                 const uint32_t* __restrict__ minv, const unsigned long long* __restrict__ sorted_v,
+                                 const catt_aln* __restrict__ rv, const catt_aln* __restrict__ rj, ExtractItem* __restrict__ items) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= np) return;
+  const uint32_t ji = pair_j[p];
+  const uint32_t vi = (uint32_t)sorted_v[minv[slot_of[ji]]];
+  ExtractItem it = make_item(rv[vi], vi, 2);
+  const catt_aln b = rj[ji];
+  it.read2 = ji; it.j_m_end = b.m_end; it.j_rid = (int16_t)b.rid; it.j_strand = b.strand;
+  items[p] = it;
+}
+
+__global__ void keep_kernel(int64_t n_items, const ExtractOut* __restrict__ eout, uint32_t* __restrict__ kflag, uint32_t* __restrict__ pflag,
+                            unsigned long long* __restrict__ cnt) {
+  const int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (it > n_items) return;
+  pflag[it] = 0;
+  if (it == n_items) { kflag[it] = 0; return; }
+  const int st = eout[it].status;
+  kflag[it] = st == 1;
+  if (st == 2) atomicAdd(&cnt[C_MISMATCH], 1ull);
+}
+
+// kept items -> PoolItem / OutDesc at their rank m (= position in [Vpart; Jpart])
+__global__ void pitem_kernel(int64_t n_items, int64_t n_v, int64_t n_p, const ExtractItem* __restrict__ items,
+                             const ExtractOut* __restrict__ eout, const uint32_t* __restrict__ kflag, const uint32_t* __restrict__ kpos2,
+                             const int32_t* __restrict__ jlen, PoolItem* __restrict__ pitems, OutDesc* __restrict__ desc,
+                             uint32_t* __restrict__ pflag, unsigned long long* __restrict__ cnt) {
+  const int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (it == 0) {
+    cnt[C_M] = kpos2[n_items]; cnt[C_VPART] = kpos2[n_v + n_p]; cnt[C_FULL] = kpos2[n_v + n_p] - kpos2[n_v];
+  }
+  if (it >= n_items || !kflag[it]) return;
+  const uint32_t m = kpos2[it];
+  const ExtractItem x = items[it];
+  const ExtractOut e = eout[it];
+  PoolItem pi;
+  pi.read = x.read; pi.strand = x.strand; pi.seq_off = e.seq_off; pi.seq_len = e.seq_len; pi.side = (int16_t)(it >= n_v + n_p);
+  pi.order = m; pi.partial = e.cdr3_off < 0;
+  pitems[m] = pi;
+  pflag[m] = pi.partial;
+  OutDesc d;
+  d.read = x.read; d.xi = -1; d.strand = x.strand; d.kind = x.kind; d.seq_off = e.seq_off; d.seq_len = e.seq_len;
+  d.cdr3_off = e.cdr3_off; d.cdr3_len = e.cdr3_len;
+  d.v_id = x.kind == 1 ? -1 : x.rid; d.j_id = x.kind == 0 ? -1 : (x.kind == 1 ? x.rid : x.j_rid);
+  d.q_start1 = (int16_t)(x.qb + 1); d.j_pad = x.kind == 1 ? (int16_t)(jlen[x.rid] - (x.rb + 1)) : 0; d.pad_ = 0;
+  desc[m] = d;
+}
+
+__global__ void partial_kernel(int64_t n_items, const uint32_t* __restrict__ pflag, const uint32_t* __restrict__ xpos,
+                               uint32_t* __restrict__ partial_idx, OutDesc* __restrict__ desc, unsigned long long* __restrict__ cnt) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m == 0) cnt[C_NPARTIAL] = xpos[n_items];
+  if (m >= n_items || !pflag[m]) return;
+  partial_idx[xpos[m]] = (uint32_t)m;
+  desc[m].xi = (int32_t)xpos[m];
+}
+
+inline unsigned nblk(int64_t n, int b = 256) { return (unsigned)std::max<int64_t>(1, (n + b - 1) / b); }
+
+template <class T> int ensure(catt_ctx* c, int slot, int64_t count, T** out) {
+  int rc = c->sb[slot].ensure((size_t)std::max<int64_t>(count, 1) * sizeof(T));
+  *out = c->sb[slot].as<T>();
+  return rc;
+}
+
+int ensure_cub(catt_ctx* c, size_t need) { return c->sb[SB_CUB].ensure(std::max<size_t>(need, 256)); }
+
+int scan_u32(catt_ctx* c, const uint32_t* in, uint32_t* out, int64_t count, cudaStream_t st) {
+  size_t need = 0;
+  CATT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, in, out, count, st));
+  int rc = ensure_cub(c, need);
+  if (rc) return rc;
+  need = c->sb[SB_CUB].cap;
+  CATT_CUDA(cub::DeviceScan::ExclusiveSum(c->sb[SB_CUB].p, need, in, out, count, st));
+  return CATT_OK;
 }
 
 const char FWD[6] = "ACGTN";
-inline char sam_base(const char* s, int len, int i, int strand) {
-  if (!strand) return FWD[nt_code(s[i])];
-  const uint8_t c = nt_code(s[len - 1 - i]);
-  return c > 3 ? 'N' : FWD[3 - c];
-}
-
-bool sam_seq_equal(const HostReads& hr, int64_t r1, int s1, int64_t r2, int s2) {
-  const int l1 = (int)(hr.seq_off[r1 + 1] - hr.seq_off[r1]), l2 = (int)(hr.seq_off[r2 + 1] - hr.seq_off[r2]);
-  if (l1 != l2) return false;
-  if (r1 == r2 && s1 == s2) return true;
-  const char *a = hr.seqs + hr.seq_off[r1], *b = hr.seqs + hr.seq_off[r2];
-  for (int i = 0; i < l1; i++) if (sam_base(a, l1, i, s1) != sam_base(b, l2, i, s2)) return false;
-  return true;
-}
-
-struct Pending {            // a Myread under construction on the host
-  int64_t read; int kind, strand; int seq_off, seq_len, cdr3_off, cdr3_len; int v_id, j_id;
-  int q_start1, j_pad;      // J part: qual = qual[1:start-1] * 'G'^j_pad
+const char RCV[6] = "TGCAN";
+struct StrLut {
+  char fwd[256], rc[256];
+  StrLut() { for (int i = 0; i < 256; i++) { const uint8_t c = nt_code((char)i); fwd[i] = FWD[c]; rc[i] = RCV[c]; } }
 };
-
-struct SharedPair { std::string_view name; int64_t vi, ji; };
+const StrLut SLUT;
 
 }  // namespace
 
-int stage_b(catt_ctx* c, const HostReads& hr, const DeviceReads& dr, catt_result* R, int* launches) {
+int stage_b(catt_ctx* c, const HostReads& hr, const ReadsDev& reads, catt_result* R, int* launches) {
   catt_info& info = R->info;
-  const std::vector<catt_aln>&vrec = R->rec[0], &jrec = R->rec[1];
   const int64_t n = hr.n;
-  const double t0 = now_ms();
+  info.kmer = c->kmer;
+  if (n == 0) return CATT_OK;
+  cudaStream_t st = c->stream;
   Trace tr;
-  std::vector<uint64_t> nh((size_t)n);
-  #pragma omp parallel for schedule(static)
-  for (int64_t i = 0; i < n; i++) nh[i] = (vrec[i].mapped || jrec[i].mapped) ? name_hash(trimmed_name(hr, i)) : 0;
-  std::vector<int64_t> vfin, jfin;
-  NameTable vtab, jtab;
-  tr.lap("name hashes");
-  final_order(vrec, hr, nh.data(), vfin, vtab);
-  final_order(jrec, hr, nh.data(), jfin, jtab);
-  tr.lap("final_order x2");
-  info.v_final = (int64_t)vfin.size(); info.j_final = (int64_t)jfin.size();
+  const catt_aln* rec[2] = {c->recs_all[0].as<catt_aln>(), c->recs_all[1].as<catt_aln>()};
+  const int64_t nm[2] = {info.v_hits, info.j_hits};
+  int rc;
+  unsigned long long* cnt; unsigned long long* hcnt;
+  if ((rc = ensure(c, SB_CNT, C_COUNT, &cnt))) return rc;
+  hcnt = c->pin[PIN_CNT].as<unsigned long long>() + 2 * N_COUNTERS;      // the first 2*N_COUNTERS entries belong to Stage A
+  CATT_CUDA(cudaMemsetAsync(cnt, 0, C_COUNT * sizeof(unsigned long long), st));
+  CATT_CUDA(cudaEventRecord(c->ev[5], st));
+
+  // ---- QNAMEs to the device, name classes
+  const int64_t name_bytes = hr.name_off[n];
+  char* d_names; int64_t* d_name_off; uint32_t* slot_of; int32_t* owner; uint32_t* minr[2];
+  uint64_t cap = 1024;
+  while (cap < (uint64_t)(nm[0] + nm[1]) * 2 + 2) cap <<= 1;
+  if (cap > 0x80000000ull) { set_error("too many mapped reads for the QNAME table"); return CATT_E_LIMIT; }
+  if ((rc = ensure(c, SB_NAMES, name_bytes + 16, &d_names)) || (rc = ensure(c, SB_NAME_OFF, n + 1, &d_name_off)) ||
+      (rc = ensure(c, SB_SLOT_OF, n, &slot_of)) || (rc = ensure(c, SB_OWNER, (int64_t)cap, &owner)) ||
+      (rc = ensure(c, SB_MINV, (int64_t)cap, &minr[0])) || (rc = ensure(c, SB_MINJ, (int64_t)cap, &minr[1]))) return rc;
+  NamesDev nd{d_names, d_name_off};
+  if (nm[0] + nm[1] > 0) {
+    CATT_CUDA(cudaMemcpyAsync(d_names, hr.names, (size_t)name_bytes, cudaMemcpyHostToDevice, st));
+    CATT_CUDA(cudaMemcpyAsync(d_name_off, hr.name_off, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    CATT_CUDA(cudaMemsetAsync(owner, 0xff, cap * sizeof(int32_t), st));
+    CATT_CUDA(cudaMemsetAsync(minr[0], 0xff, cap * sizeof(uint32_t), st));
+    CATT_CUDA(cudaMemsetAsync(minr[1], 0xff, cap * sizeof(uint32_t), st));
+    name_kernel<<<nblk(n), 256, 0, st>>>(n, nd, rec[0], rec[1], owner, (uint32_t)(cap - 1), slot_of);
+    CATT_CUDA(cudaGetLastError());
+    *launches += 1;
+  }
+
+  // ---- per reference set: sorted final SAM order, QNAME dedup
+  unsigned long long *keys_a, *sorted[2];
+  uint32_t *flag, *kpos[2], *ord_idx[2], *ord_flag[2], *opos[2], *pair_a, *pair_b;
+  const int64_t nmax = std::max(nm[0], nm[1]);
+  if ((rc = ensure(c, SB_KEYS_A, nmax, &keys_a)) || (rc = ensure(c, SB_SORT_V, nm[0], &sorted[0])) ||
+      (rc = ensure(c, SB_SORT_J, nm[1], &sorted[1])) || (rc = ensure(c, SB_FLAG, nmax + 1, &flag)) || (rc = ensure(c, SB_KPOS_V, nm[0] + 1, &kpos[0])) ||
+      (rc = ensure(c, SB_KPOS_J, nm[1] + 1, &kpos[1])) || (rc = ensure(c, SB_ORD_IDX_V, nm[0] + 1, &ord_idx[0])) ||
+      (rc = ensure(c, SB_ORD_IDX_J, nm[1] + 1, &ord_idx[1])) || (rc = ensure(c, SB_ORD_FLAG_V, nm[0] + 1, &ord_flag[0])) ||
+      (rc = ensure(c, SB_ORD_FLAG_J, nm[1] + 1, &ord_flag[1])) ||
+      (rc = ensure(c, SB_OPOS_V, nm[0] + 1, &opos[0])) || (rc = ensure(c, SB_OPOS_J, nm[1] + 1, &opos[1])) ||
+      (rc = ensure(c, SB_PAIR_A, nm[1] + 1, &pair_a)) || (rc = ensure(c, SB_PAIR_B, nm[1] + 1, &pair_b))) return rc;
+  for (int which = 0; which < 2; which++) {
+    if (nm[which] == 0) continue;
+    key_kernel<<<nblk(n), 256, 0, st>>>(n, rec[which], keys_a, cnt + C_NMAP_V + which);
+    CATT_CUDA(cudaGetLastError());
+    size_t need = 0;
+    CATT_CUDA(cub::DeviceRadixSort::SortKeysDescending(nullptr, need, keys_a, sorted[which], nm[which], 0, 61, st));
+    if ((rc = ensure_cub(c, need))) return rc;
+    need = c->sb[SB_CUB].cap;
+    CATT_CUDA(cub::DeviceRadixSort::SortKeysDescending(c->sb[SB_CUB].p, need, keys_a, sorted[which], nm[which], 0, 61, st));
+    minrank_kernel<<<nblk(nm[which]), 256, 0, st>>>(nm[which], sorted[which], slot_of, minr[which]);
+    CATT_CUDA(cudaGetLastError());
+    *launches += 10;     // key, radix sort (histogram + 7 onesweep passes), minrank
+  }
+  for (int which = 0; which < 2; which++) {
+    if (nm[which] == 0) continue;
+    flag_kernel<<<nblk(nm[which] + 1), 256, 0, st>>>(nm[which], sorted[which], slot_of, minr[which], rec[which], reads.len, which == 0, flag, cnt);
+    CATT_CUDA(cudaGetLastError());
+    if ((rc = scan_u32(c, flag, kpos[which], nm[which] + 1, st))) return rc;
+    CATT_CUDA(cudaMemsetAsync(ord_flag[which], 0, (size_t)(nm[which] + 1) * sizeof(uint32_t), st));
+    order_kernel<<<nblk(nm[which]), 256, 0, st>>>(nm[which], sorted[which], flag, kpos[which], c->nthreads, slot_of, minr[0], minr[1], which, nd,
+                                                  ord_idx[which], ord_flag[which], pair_a, cnt);
+    CATT_CUDA(cudaGetLastError());
+    if ((rc = scan_u32(c, ord_flag[which], opos[which], nm[which] + 1, st))) return rc;
+    *launches += 6;
+  }
+  collect_kernel<<<1, 1, 0, st>>>(kpos[0], nm[0], kpos[1], nm[1], opos[0], opos[1], cnt);
+  CATT_CUDA(cudaGetLastError());
+  *launches += 1;
+  CATT_CUDA(cudaMemcpyAsync(hcnt, cnt, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CATT_CUDA(cudaStreamSynchronize(st));
+  tr.lap("B: names + order + dedup");
+  if ((int64_t)hcnt[C_NMAP_V] != nm[0] || (int64_t)hcnt[C_NMAP_J] != nm[1]) {
+    set_error("stage B: mapped-record count mismatch (V %llu vs %lld, J %llu vs %lld)", hcnt[C_NMAP_V], (long long)nm[0], hcnt[C_NMAP_J], (long long)nm[1]);
+    return CATT_E_ARG;
+  }
+  const int64_t F[2] = {(int64_t)hcnt[C_F_V], (int64_t)hcnt[C_F_J]};
+  const int64_t n_v = (int64_t)hcnt[C_NV], n_j = (int64_t)hcnt[C_NJ], n_p = (int64_t)hcnt[C_NP];
+  info.v_final = F[0]; info.j_final = F[1]; info.share = n_p;
   // get_kmer_fromsam / get_err_fromsam on the final V list, as samtools stats prints them
   int k = c->kmer;
   {
-    uint64_t tot = 0, nm = 0, mi = 0;
-    #pragma omp parallel for reduction(+ : tot, nm, mi) schedule(static)
-    for (int64_t x = 0; x < (int64_t)vfin.size(); x++) {
-      const int64_t i = vfin[x];
-      tot += (uint64_t)(hr.seq_off[i + 1] - hr.seq_off[i]); nm += (uint64_t)vrec[i].nm; mi += (uint64_t)vrec[i].mi;
-    }
-    const float avg = vfin.empty() ? 0.f : (float)(tot / (uint64_t)vfin.size());    // samtools: integer division, printed %.0f
+    const uint64_t tot = hcnt[C_SUM_LEN], snm = hcnt[C_SUM_NM], smi = hcnt[C_SUM_MI];
+    const float avg = F[0] == 0 ? 0.f : (float)(tot / (uint64_t)F[0]);       // samtools: integer division, printed %.0f
     char buf[64];
     snprintf(buf, sizeof buf, "%.0f", avg);
     const double avg_r = atof(buf);
@@ -153,198 +371,159 @@ int stage_b(catt_ctx* c, const HostReads& hr, const DeviceReads& dr, catt_result
       if (avg_r >= 100) k = 23;
       if (avg_r >= 150) k = 25;
     }
-    const float er = mi ? (float)nm / (float)mi : 0.f;
+    const float er = smi ? (float)snm / (float)smi : 0.f;
     snprintf(buf, sizeof buf, "%e", (double)er);
     info.the_err = atof(buf);
     if (!(info.the_err == info.the_err)) info.the_err = 0.0;
   }
   info.kmer = k;
-  // share_name = QNAMEs present in both final lists
-  std::vector<uint8_t> shared((size_t)n, 0);       // bit 0: V record is shared, bit 1: J record is shared
-  std::vector<SharedPair> pairs;
-  for (int64_t j : jfin) {
-    const int64_t vi = vtab.lookup(j, false);
-    if (vi < 0) continue;
-    pairs.push_back(SharedPair{trimmed_name(hr, j), vi, j});
-    shared[vi] |= 1; shared[j] |= 2;
-  }
-  info.share = (int64_t)pairs.size();
-  tr.lap("stats + share");
-  // work items in the reference's processing order
-  std::vector<ExtractItem> items;
-  std::vector<Pending> pend;
-  std::vector<int64_t> order;
-  items.reserve(vfin.size() + jfin.size());
-  pend.reserve(vfin.size() + jfin.size());
-  auto add_part = [&](int which) {
-    const std::vector<catt_aln>& recs = which ? jrec : vrec;
-    chunk_order(which ? jfin : vfin, c->nthreads, order);
-    for (int64_t i : order) {
-      if (shared[i] & (which ? 2 : 1)) continue;
-      const catt_aln& a = recs[i];
-      ExtractItem it{};
-      it.read = (uint32_t)i; it.kind = (int16_t)which; it.strand = a.strand; it.qb = a.qb; it.m_end = a.m_end; it.rb = a.rb; it.rid = (int16_t)a.rid;
-      items.push_back(it);
-      Pending p{};
-      p.read = i; p.kind = which; p.strand = a.strand; p.v_id = which ? -1 : a.rid; p.j_id = which ? a.rid : -1;
-      p.q_start1 = a.qb + 1; p.j_pad = which ? (c->J.len[a.rid] - (a.rb + 1)) : 0;
-      pend.push_back(p);
-    }
-  };
-  add_part(0);
-  const size_t n_vpart_items = items.size();
-  add_part(1);
-  const size_t n_jpart_end = items.size();
-  tr.lap("part items");
-  // both-mapped reads: sorted by name (V record first, J record second), SEQ equality, clipping V start .. J first-M end
-  {
-    __gnu_parallel::sort(pairs.begin(), pairs.end(), [](const SharedPair& x, const SharedPair& y) { return x.name < y.name; });
-    std::vector<uint8_t> eq(pairs.size());
-    #pragma omp parallel for schedule(static)
-    for (int64_t x = 0; x < (int64_t)pairs.size(); x++)
-      eq[x] = sam_seq_equal(hr, pairs[x].vi, vrec[pairs[x].vi].strand, pairs[x].ji, jrec[pairs[x].ji].strand);
-    for (size_t x = 0; x < pairs.size(); x++) {
-      if (!eq[x]) { info.pair_seq_mismatch++; continue; }
-      const int64_t vi = pairs[x].vi, ji = pairs[x].ji;
-      const catt_aln &a = vrec[vi], &b = jrec[ji];
-      ExtractItem it{};
-      it.read = (uint32_t)vi; it.kind = 2; it.strand = a.strand; it.qb = a.qb; it.m_end = a.m_end; it.rb = a.rb; it.rid = (int16_t)a.rid;
-      it.j_m_end = b.m_end; it.j_rid = (int16_t)b.rid;
-      items.push_back(it);
-      Pending p{};
-      p.read = vi; p.kind = 2; p.strand = a.strand; p.v_id = a.rid; p.j_id = b.rid; p.q_start1 = a.qb + 1;
-      pend.push_back(p);
+
+  // ---- both-mapped pairs in QNAME order: LSD radix over 8-byte digits of the trimmed name
+  uint32_t* pairs = pair_a;
+  if (n_p > 1) {
+    unsigned long long *pk_a, *pk_b;
+    if ((rc = ensure(c, SB_PKEY_A, n_p, &pk_a)) || (rc = ensure(c, SB_PKEY_B, n_p, &pk_b))) return rc;
+    const int digits = std::max(1, (int)((hcnt[C_MAXNAME] + 7) / 8));
+    uint32_t* other = pair_b;
+    for (int d = digits - 1; d >= 0; d--) {
+      pair_key_kernel<<<nblk(n_p), 256, 0, st>>>(n_p, pairs, nd, d, pk_a);
+      CATT_CUDA(cudaGetLastError());
+      size_t need = 0;
+      CATT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, pk_a, pk_b, pairs, other, n_p, 0, 64, st));
+      if ((rc = ensure_cub(c, need))) return rc;
+      need = c->sb[SB_CUB].cap;
+      CATT_CUDA(cub::DeviceRadixSort::SortPairs(c->sb[SB_CUB].p, need, pk_a, pk_b, pairs, other, n_p, 0, 64, st));
+      std::swap(pairs, other);
+      *launches += 10;
     }
   }
-  const int64_t n_items = (int64_t)items.size();
-  info.ms_host += now_ms() - t0;
-  tr.lap("pair sort + items");
-  // ---- K5 on the device
-  cudaStream_t st = c->stream;
-  ExtractItem* d_items = nullptr; ExtractOut* d_eout = nullptr;
-  std::vector<ExtractOut> eout(n_items);
-  CATT_CUDA(cudaEventRecord(c->ev[5], st));
-  if (n_items) {
-    int rc0;
-    if ((rc0 = c->sb[SB_ITEMS].ensure(n_items * sizeof(ExtractItem))) || (rc0 = c->sb[SB_EOUT].ensure(n_items * sizeof(ExtractOut)))) return rc0;
-    d_items = (ExtractItem*)c->sb[SB_ITEMS].p; d_eout = (ExtractOut*)c->sb[SB_EOUT].p;
-    CATT_CUDA(cudaMemcpyAsync(d_items, items.data(), n_items * sizeof(ExtractItem), cudaMemcpyHostToDevice, st));
-    int rc = launch_extract(c->V.dev, c->J.dev, dr.view(), c->d_finder, d_items, d_eout, n_items, k, c->allow_v, c->allow_j, st, launches);
-    if (rc) return rc;
-    CATT_CUDA(cudaMemcpyAsync(eout.data(), d_eout, n_items * sizeof(ExtractOut), cudaMemcpyDeviceToHost, st));
+
+  // ---- work items in the reference's processing order: [V part | both-mapped | J part]
+  const int64_t n_items = n_v + n_p + n_j;
+  ExtractItem* items; ExtractOut* eout; uint32_t *kflag, *kpos2, *pflag, *xpos;
+  if ((rc = ensure(c, SB_ITEMS, n_items, &items)) || (rc = ensure(c, SB_EOUT, n_items, &eout)) || (rc = ensure(c, SB_KFLAG, n_items + 1, &kflag)) ||
+      (rc = ensure(c, SB_KPOS2, n_items + 1, &kpos2)) || (rc = ensure(c, SB_PFLAG, n_items + 1, &pflag)) || (rc = ensure(c, SB_XPOS, n_items + 1, &xpos))) return rc;
+  if (F[0] > 0) {
+    part_item_kernel<<<nblk(F[0]), 256, 0, st>>>(F[0], ord_idx[0], ord_flag[0], opos[0], rec[0], 0, items);
+    CATT_CUDA(cudaGetLastError());
+    *launches += 1;
+  }
+  if (n_p > 0) {
+    pair_item_kernel<<<nblk(n_p), 256, 0, st>>>(n_p, pairs, slot_of, minr[0], sorted[0], rec[0], rec[1], items + n_v);
+    CATT_CUDA(cudaGetLastError());
+    *launches += 1;
+  }
+  if (F[1] > 0) {
+    part_item_kernel<<<nblk(F[1]), 256, 0, st>>>(F[1], ord_idx[1], ord_flag[1], opos[1], rec[1], 1, items + n_v + n_p);
+    CATT_CUDA(cudaGetLastError());
+    *launches += 1;
   }
   CATT_CUDA(cudaEventRecord(c->ev[6], st));
+  // ---- K5: assignV/J, real_score, clipping, finder!
+  if ((rc = launch_extract(c->V.dev, c->J.dev, reads, c->d_finder, items, eout, n_items, k, c->allow_v, c->allow_j, st, launches))) return rc;
+  CATT_CUDA(cudaEventRecord(c->ev[7], st));
+  // ---- Vpart = kept V part reads then kept both-mapped reads; Jpart = kept J part reads
+  PoolItem* pitems; OutDesc* desc; uint32_t* partial_idx;
+  if ((rc = ensure(c, SB_PITEMS, n_items, &pitems)) || (rc = ensure(c, SB_DESC, n_items, &desc)) || (rc = ensure(c, SB_PARTIAL, n_items, &partial_idx))) return rc;
+  keep_kernel<<<nblk(n_items + 1), 256, 0, st>>>(n_items, eout, kflag, pflag, cnt);
+  CATT_CUDA(cudaGetLastError());
+  if ((rc = scan_u32(c, kflag, kpos2, n_items + 1, st))) return rc;
+  pitem_kernel<<<nblk(std::max<int64_t>(n_items, 1)), 256, 0, st>>>(n_items, n_v, n_p, items, eout, kflag, kpos2, c->J.dev.rec_len, pitems, desc, pflag, cnt);
+  CATT_CUDA(cudaGetLastError());
+  if ((rc = scan_u32(c, pflag, xpos, n_items + 1, st))) return rc;
+  partial_kernel<<<nblk(std::max<int64_t>(n_items, 1)), 256, 0, st>>>(n_items, pflag, xpos, partial_idx, desc, cnt);
+  CATT_CUDA(cudaGetLastError());
+  *launches += 7;
+  CATT_CUDA(cudaMemcpyAsync(hcnt, cnt, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   CATT_CUDA(cudaStreamSynchronize(st));
-  { float ms = 0; cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]); info.ms_extract += ms; }
-  tr.lap("extract (alloc+H2D+K5+D2H)");
-  // ---- Vpart = kept V part reads, then kept both-mapped reads; Jpart = kept J part reads
-  const double t1 = now_ms();
-  std::vector<uint32_t> lists[2];
-  for (int64_t i = 0; i < (int64_t)n_vpart_items; i++) if (eout[i].status) lists[0].push_back((uint32_t)i);
-  for (int64_t i = (int64_t)n_jpart_end; i < n_items; i++) if (eout[i].status) { lists[0].push_back((uint32_t)i); info.full_pushed++; }
-  for (int64_t i = (int64_t)n_vpart_items; i < (int64_t)n_jpart_end; i++) if (eout[i].status) lists[1].push_back((uint32_t)i);
-  info.vpart = (int64_t)lists[0].size(); info.jpart = (int64_t)lists[1].size();
-  const int64_t M = info.vpart + info.jpart;
-  // ---- K6/K7: pool + extension of the partial reads
-  std::vector<PoolItem> pitems((size_t)M);
-  std::vector<int32_t> xi_of((size_t)M, -1);
-  std::vector<uint32_t> partial;
-  {
-    int64_t m = 0;
-    for (int side = 0; side < 2; side++)
-      for (uint32_t it : lists[side]) {
-        Pending& p = pend[it];
-        const ExtractOut& e = eout[it];
-        p.seq_off = e.seq_off; p.seq_len = e.seq_len; p.cdr3_off = e.cdr3_off; p.cdr3_len = e.cdr3_len;
-        PoolItem pi{};
-        pi.read = (uint32_t)p.read; pi.strand = (int16_t)p.strand; pi.seq_off = (int16_t)p.seq_off; pi.seq_len = (int16_t)p.seq_len;
-        pi.side = (int16_t)side; pi.order = (uint32_t)m; pi.partial = p.cdr3_off < 0;
-        if (pi.partial) { xi_of[m] = (int32_t)partial.size(); partial.push_back((uint32_t)m); } else info.direct++;
-        pitems[m++] = pi;
-      }
-  }
-  info.left = (int64_t)partial.size();
-  info.ms_host += now_ms() - t1;
-  tr.lap("lists + pool items");
-  std::vector<ExtendOut> xout(partial.size());
-  if (M > 0 && k <= 31 && !partial.empty()) {
+  { float a = 0, b = 0; cudaEventElapsedTime(&a, c->ev[5], c->ev[6]); cudaEventElapsedTime(&b, c->ev[6], c->ev[7]); info.ms_order += a; info.ms_extract += b; }
+  tr.lap("B: items + extract + lists");
+  const int64_t M = (int64_t)hcnt[C_M], n_partial = (int64_t)hcnt[C_NPARTIAL];
+  info.vpart = (int64_t)hcnt[C_VPART]; info.jpart = M - info.vpart; info.full_pushed = (int64_t)hcnt[C_FULL];
+  info.pair_seq_mismatch = (int64_t)hcnt[C_MISMATCH];
+  info.left = n_partial; info.direct = M - n_partial;
+
+  // ---- K6/K7: k-mer table + extension of the partial reads
+  ExtendOut* xout = nullptr;
+  const bool run_pool = M > 0 && k <= 31 && n_partial > 0;
+  if ((rc = c->pin[PIN_DESC].ensure((size_t)std::max<int64_t>(M, 1) * sizeof(OutDesc))) ||
+      (rc = c->pin[PIN_XOUT].ensure((size_t)std::max<int64_t>(n_partial, 1) * sizeof(ExtendOut)))) return rc;
+  OutDesc* hdesc = c->pin[PIN_DESC].as<OutDesc>();
+  ExtendOut* hxout = c->pin[PIN_XOUT].as<ExtendOut>();
+  CATT_CUDA(cudaEventRecord(c->ev[5], st));
+  if (run_pool) {
     uint64_t slots = 1024;
     while (slots < (uint64_t)M * 11ull * 2ull) slots <<= 1;
     KmerTable tab{};
-    PoolItem* d_pi = nullptr; uint32_t* d_partial = nullptr; ExtendOut* d_xout = nullptr;
-    CATT_CUDA(cudaEventRecord(c->ev[5], st));
-    int rc0;
-    if ((rc0 = c->sb[SB_KEYS].ensure(slots * sizeof(unsigned long long))) || (rc0 = c->sb[SB_VALS].ensure(slots * sizeof(unsigned long long))) ||
-        (rc0 = c->sb[SB_PITEMS].ensure(pitems.size() * sizeof(PoolItem))) || (rc0 = c->sb[SB_PARTIAL].ensure(partial.size() * sizeof(uint32_t))) ||
-        (rc0 = c->sb[SB_XOUT].ensure(partial.size() * sizeof(ExtendOut)))) return rc0;
-    tab.keys = (unsigned long long*)c->sb[SB_KEYS].p; tab.vals = (unsigned long long*)c->sb[SB_VALS].p;
-    d_pi = (PoolItem*)c->sb[SB_PITEMS].p; d_partial = (uint32_t*)c->sb[SB_PARTIAL].p; d_xout = (ExtendOut*)c->sb[SB_XOUT].p;
+    if ((rc = ensure(c, SB_TAB_KEYS, (int64_t)slots, &tab.keys)) || (rc = ensure(c, SB_TAB_VALS, (int64_t)slots, &tab.vals)) ||
+        (rc = ensure(c, SB_XOUT, n_partial, &xout))) return rc;
     tab.mask = slots - 1;
     CATT_CUDA(cudaMemsetAsync(tab.keys, 0xff, slots * sizeof(unsigned long long), st));
     CATT_CUDA(cudaMemsetAsync(tab.vals, 0, slots * sizeof(unsigned long long), st));
-    CATT_CUDA(cudaMemcpyAsync(d_pi, pitems.data(), pitems.size() * sizeof(PoolItem), cudaMemcpyHostToDevice, st));
-    CATT_CUDA(cudaMemcpyAsync(d_partial, partial.data(), partial.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    int rc = launch_pool(dr.view(), d_pi, M, k, tab, st, launches);
-    if (!rc) rc = launch_extend(dr.view(), c->d_finder, d_pi, d_partial, (int64_t)partial.size(), k, tab, d_xout, st, launches);
-    if (rc) return rc;
-    CATT_CUDA(cudaMemcpyAsync(xout.data(), d_xout, partial.size() * sizeof(ExtendOut), cudaMemcpyDeviceToHost, st));
-    CATT_CUDA(cudaEventRecord(c->ev[6], st));
-    CATT_CUDA(cudaStreamSynchronize(st));
-    { float ms = 0; cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]); info.ms_pool += ms; }
-  } else {
-    for (auto& x : xout) { x.n_ext = 0; x.cdr3_off = -1; x.cdr3_len = 0; x.able = 1; }
+    if ((rc = launch_pool(reads, pitems, M, k, tab, st, launches))) return rc;
+    if ((rc = launch_extend(reads, c->d_finder, pitems, partial_idx, n_partial, k, tab, xout, reinterpret_cast<uint32_t*>(cnt + C_RESCUED), st, launches))) return rc;
+    CATT_CUDA(cudaMemcpyAsync(hxout, xout, (size_t)n_partial * sizeof(ExtendOut), cudaMemcpyDeviceToHost, st));
   }
-  tr.lap("pool + extend (alloc..D2H)");
-  // ---- materialise Myread strings: sizes, prefix sums, parallel fill into two flat arenas
+  CATT_CUDA(cudaEventRecord(c->ev[6], st));
+  if (M > 0) CATT_CUDA(cudaMemcpyAsync(hdesc, desc, (size_t)M * sizeof(OutDesc), cudaMemcpyDeviceToHost, st));
+  CATT_CUDA(cudaMemcpyAsync(hcnt, cnt, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CATT_CUDA(cudaEventRecord(c->ev[7], st));
+  CATT_CUDA(cudaStreamSynchronize(st));
+  { float a = 0, b = 0; cudaEventElapsedTime(&a, c->ev[5], c->ev[6]); cudaEventElapsedTime(&b, c->ev[6], c->ev[7]); info.ms_pool += a; info.ms_d2h += b; }
+  if (!run_pool) for (int64_t x = 0; x < n_partial; x++) { hxout[x].n_ext = 0; hxout[x].cdr3_off = -1; hxout[x].cdr3_len = 0; hxout[x].able = 1; }
+  info.rescued += (int64_t)(uint32_t)hcnt[C_RESCUED];
+  tr.lap("B: pool + extend + D2H");
+
+  // ---- materialise the Myread strings: sizes, prefix sums, parallel fill into two flat arenas
   const double t2 = now_ms();
-  std::vector<uint32_t> flat((size_t)M);
-  { int64_t m = 0; for (int side = 0; side < 2; side++) for (uint32_t it : lists[side]) flat[m++] = it; }
   std::vector<int64_t> soff((size_t)M + 1, 0), qoff((size_t)M + 1, 0);
-  int64_t rescued = 0;
-  #pragma omp parallel for schedule(static) reduction(+ : rescued)
+  #pragma omp parallel for schedule(static)
   for (int64_t m = 0; m < M; m++) {
-    const Pending& p = pend[flat[m]];
+    const OutDesc& p = hdesc[m];
     int n_ext = 0, c_off = p.cdr3_off, c_len = p.cdr3_len;
-    if (xi_of[m] >= 0) { const ExtendOut& x = xout[xi_of[m]]; n_ext = x.n_ext; c_off = x.cdr3_off; c_len = x.cdr3_len; rescued += c_off >= 0; }
-    const int base_q = p.kind == 1 ? (p.q_start1 - 1 + std::max(0, p.j_pad)) : p.seq_len;
+    if (p.xi >= 0) { const ExtendOut& x = hxout[p.xi]; n_ext = x.n_ext; c_off = x.cdr3_off; c_len = x.cdr3_len; }
+    const int base_q = p.kind == 1 ? (p.q_start1 - 1 + std::max(0, (int)p.j_pad)) : p.seq_len;
     soff[m + 1] = p.seq_len + n_ext + 1;
     qoff[m + 1] = (c_off >= 0 ? c_len : base_q + n_ext) + 1;
   }
-  info.rescued += rescued;
   for (int64_t m = 0; m < M; m++) { soff[m + 1] += soff[m]; qoff[m + 1] += qoff[m]; }
-  R->seq_arena.resize((size_t)soff[M] + 1);
-  R->qual_arena.resize((size_t)qoff[M] + 1);
-  R->part[0].resize((size_t)info.vpart);
-  R->part[1].resize((size_t)info.jpart);
+  R->seq_arena = (char*)malloc((size_t)soff[M] + 1);
+  R->qual_arena = (char*)malloc((size_t)qoff[M] + 1);
+  R->npart[0] = info.vpart; R->npart[1] = info.jpart;
+  R->part[0] = (catt_read*)malloc((size_t)std::max<int64_t>(info.vpart, 1) * sizeof(catt_read));
+  R->part[1] = (catt_read*)malloc((size_t)std::max<int64_t>(info.jpart, 1) * sizeof(catt_read));
+  if (!R->seq_arena || !R->qual_arena || !R->part[0] || !R->part[1]) { set_error("out of host memory for the result"); return CATT_E_LIMIT; }
   static const char NT[] = "ACGT";
   #pragma omp parallel for schedule(static)
   for (int64_t m = 0; m < M; m++) {
-    const Pending& p = pend[flat[m]];
+    const OutDesc& p = hdesc[m];
     const int side = m < info.vpart ? 0 : 1;
     const int len = (int)(hr.seq_off[p.read + 1] - hr.seq_off[p.read]);
-    const char* rs = hr.seqs + hr.seq_off[p.read];
+    const unsigned char* rs = reinterpret_cast<const unsigned char*>(hr.seqs + hr.seq_off[p.read]);
     const char* rq = hr.quals ? hr.quals + hr.seq_off[p.read] : nullptr;
     int n_ext = 0, c_off = p.cdr3_off, c_len = p.cdr3_len;
     const ExtendOut* x = nullptr;
-    if (xi_of[m] >= 0) { x = &xout[xi_of[m]]; n_ext = x->n_ext; c_off = x->cdr3_off; c_len = x->cdr3_len; }
+    if (p.xi >= 0) { x = &hxout[p.xi]; n_ext = x->n_ext; c_off = x->cdr3_off; c_len = x->cdr3_len; }
+    auto ext_at = [&](int i) { return NT[(x->ext2[i >> 4] >> (2 * (i & 15))) & 3u]; };
     const int lead = side == 1 ? n_ext : 0;                       // a left extension is prepended
-    char* s = &R->seq_arena[(size_t)soff[m]];
-    for (int i = 0; i < lead; i++) s[i] = NT[x->ext[n_ext - 1 - i] & 3];          // reverse(ext) * seq
-    for (int i = 0; i < p.seq_len; i++) s[lead + i] = sam_base(rs, len, p.seq_off + i, p.strand);
-    if (side == 0) for (int i = 0; i < n_ext; i++) s[p.seq_len + i] = NT[x->ext[i] & 3];
+    char* s = R->seq_arena + soff[m];
+    for (int i = 0; i < lead; i++) s[i] = ext_at(n_ext - 1 - i);                  // reverse(ext) * seq
+    if (!p.strand) for (int i = 0; i < p.seq_len; i++) s[lead + i] = SLUT.fwd[rs[p.seq_off + i]];
+    else for (int i = 0; i < p.seq_len; i++) s[lead + i] = SLUT.rc[rs[len - 1 - p.seq_off - i]];
+    if (side == 0) for (int i = 0; i < n_ext; i++) s[p.seq_len + i] = ext_at(i);
     const int slen = p.seq_len + n_ext;
     s[slen] = 0;
     // quality: the Myread's string before finder! slices it
-    const int base_q = p.kind == 1 ? (p.q_start1 - 1 + std::max(0, p.j_pad)) : p.seq_len;
+    const int base_q = p.kind == 1 ? (p.q_start1 - 1 + std::max(0, (int)p.j_pad)) : p.seq_len;
     const int qfull = base_q + n_ext;
     auto sq = [&](int i) { return rq ? (p.strand ? rq[len - 1 - i] : rq[i]) : 'I'; };
     auto qat = [&](int i) -> char {                               // i in [0, qfull)
-      int b = i - lead;
+      const int b = i - lead;
       if (b < 0 || b >= base_q) return 'G';                      // extension padding
       if (p.kind == 1) return b < p.q_start1 - 1 ? sq(b) : 'G';  // catt.jl:126
       return sq(p.seq_off + b);
     };
-    char* q = &R->qual_arena[(size_t)qoff[m]];
+    char* q = R->qual_arena + qoff[m];
     uint8_t flags = (uint8_t)(p.kind == 0 ? 1 : p.kind == 1 ? 2 : 4);
     int qlen;
     if (c_off >= 0) {                                             // rd.qual = rd.qual[range] (Jtool.jl:365,383)
@@ -364,7 +543,7 @@ int stage_b(catt_ctx* c, const HostReads& hr, const DeviceReads& dr, catt_result
     R->part[side][side == 0 ? m : m - info.vpart] = rd;
   }
   info.ms_host += now_ms() - t2;
-  tr.lap("materialise");
+  tr.lap("B: materialise");
   return CATT_OK;
 }
 

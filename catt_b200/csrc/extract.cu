@@ -75,9 +75,25 @@ __global__ void __launch_bounds__(EX_WARPS * 32) extract_kernel(RefDev vref, Ref
       if (start - 1 < 5) keep = false;
       if (keep && !real_score_warp(ws.seq, m, jref.fa + jref.rec_off[item.rid], r_lgt, start, item.m_end, r_pos, allow_j, lane)) keep = false;
       off = 0; slen = min(m, start + r_lgt);
-    } else {                                                         // both-mapped: seq[s:t]
+    } else {                                                         // both-mapped: SAM.sequence(p1) == SAM.sequence(p2), then seq[s:t]
+      bool same = true;
+      if (item.read2 != item.read || item.j_strand != item.strand) {
+        const int m2 = reads.len[item.read2];
+        same = (m2 == m);
+        if (same) {
+          const uint32_t* __restrict__ w2 = reads.words + reads.off[item.read2];
+          const uint32_t* __restrict__ nm2 = w2 + read_base_words(m2);
+          bool diff = false;
+          for (int base = 0; base < m; base += 32) {
+            const int i = base + lane;
+            diff |= __ballot_sync(FULL, i < m && ws.seq[i] != (uint8_t)sam_code(w2, nm2, m2, i, item.j_strand)) != 0;
+          }
+          same = !diff;
+        }
+      }
       off = start - 1; slen = item.j_m_end - start + 1;
-      if (slen < kmer) keep = false;
+      if (!same) { keep = false; o.status = 2; }
+      else if (slen < kmer) keep = false;
     }
     if (keep) {
       bool hasn = false;
@@ -95,7 +111,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32) extract_kernel(RefDev vref, Ref
       if (item.kind != 2 && !(slen > kmer)) keep = false;
       o.cdr3_off = (int16_t)lo; o.cdr3_len = (int16_t)l3;
     }
-    o.status = keep ? 1 : 0; o.seq_off = (int16_t)off; o.seq_len = (int16_t)slen;
+    o.status = keep ? 1 : (o.status == 2 ? 2 : 0); o.seq_off = (int16_t)off; o.seq_len = (int16_t)slen;
     if (lane == 0) out[it] = o;
     __syncwarp();
   }

@@ -13,10 +13,12 @@ struct DeviceReads {
   uint32_t* words = nullptr; uint32_t* off = nullptr; int32_t* len = nullptr;
   int64_t n = 0; int max_len = 0;
   catt::ReadsDev view() const { return catt::ReadsDev{words, off, len, n, max_len}; }
+  // reads [i0, i0+cnt): offsets stay global word offsets into `words`
+  catt::ReadsDev view(int64_t i0, int64_t cnt) const { return catt::ReadsDev{words, off + i0, len + i0, cnt, max_len}; }
   void release() { cudaFree(words); cudaFree(off); cudaFree(len); words = nullptr; off = nullptr; len = nullptr; }
 };
 
-// grow-only device scratch: Stage B reuses these across calls instead of cudaMalloc/cudaFree per call
+// grow-only device scratch: reused across calls instead of cudaMalloc/cudaFree per call
 struct DevBuf {
   void* p = nullptr; size_t cap = 0;
   int ensure(size_t bytes) {
@@ -29,21 +31,55 @@ struct DevBuf {
     cap = want;
     return CATT_OK;
   }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
-enum { SB_ITEMS = 0, SB_EOUT, SB_KEYS, SB_VALS, SB_PITEMS, SB_PARTIAL, SB_XOUT, SB_COUNT };
+// grow-only pinned host staging
+struct PinBuf {
+  void* p = nullptr; size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return CATT_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    const size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e != cudaSuccess) return catt::cuda_fail(e, "pinned cudaMallocHost", __FILE__, __LINE__);
+    cap = want;
+    return CATT_OK;
+  }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// Stage B device scratch slots (assemble.cu)
+enum {
+  SB_NAMES = 0, SB_NAME_OFF, SB_SLOT_OF, SB_OWNER, SB_MINV, SB_MINJ, SB_KEYS_A, SB_SORT_V, SB_SORT_J, SB_FLAG, SB_KPOS_V,
+  SB_KPOS_J, SB_ORD_IDX_V, SB_ORD_IDX_J, SB_ORD_FLAG_V, SB_ORD_FLAG_J, SB_OPOS_V, SB_OPOS_J, SB_PAIR_A, SB_PAIR_B, SB_PKEY_A, SB_PKEY_B, SB_ITEMS,
+  SB_EOUT, SB_KFLAG, SB_KPOS2, SB_PFLAG, SB_XPOS, SB_TAB_KEYS, SB_TAB_VALS, SB_PITEMS, SB_PARTIAL, SB_XOUT, SB_DESC, SB_CNT, SB_CUB,
+  SB_COUNT
+};
+enum { PIN_PACK0 = 0, PIN_PACK1, PIN_OFF, PIN_LEN, PIN_CNT, PIN_DESC, PIN_XOUT, PIN_COUNT };
+constexpr int EV_A = 6;     // per reference set: seed start, seed end, expand end, sw end, select end
 
 struct catt_ctx {
   catt::RefSet V, J;
   catt::FinderDev finder{};
   catt::FinderDev* d_finder = nullptr;
   int min_score = 12, kmer = CATT_KMER_AUTO, nthreads = 1, allow_v = 3, allow_j = 9, device = 0, sm_count = 148;
-  cudaStream_t stream = nullptr;
+  int keep_records = 0;                   // download the per-read alignment records into every result (diagnostics)
+  int64_t chunk_reads = 1 << 18;          // Stage A batch size of the pipelined path
+  cudaStream_t stream = nullptr;          // kernels
+  cudaStream_t copy_stream = nullptr;     // H2D of the packed chunks, under the kernels of the previous chunk
   std::vector<std::string> d_names, d_seqs;
   char* d_dseq = nullptr; int32_t* d_doff = nullptr;
   catt::AlignBuffers ab[2];
+  DevBuf rd_words, rd_off, rd_len;        // packed reads of the sample being run (catt_run_*, catt_assemble)
+  DevBuf recs_all[2];                     // one catt_aln per read and reference set, for the whole sample
   DevBuf sb[SB_COUNT];
+  PinBuf pin[PIN_COUNT];
   cudaEvent_t ev[8]{};
+  cudaEvent_t ev_a[2][EV_A]{};            // Stage A stage boundaries per reference set
+  cudaEvent_t ev_h2d[2]{};                // staging buffer c&1 has reached the device
 };
 
 struct catt_batch {
@@ -54,9 +90,11 @@ struct catt_batch {
 
 struct catt_result {
   catt_info info{};
-  std::vector<catt_read> part[2];
+  catt_read* part[2] = {nullptr, nullptr};
+  int64_t npart[2] = {0, 0};
   std::vector<catt_aln> rec[2];
-  std::vector<char> seq_arena, qual_arena;     // every Myread string, NUL-terminated, back to back
+  char* seq_arena = nullptr; char* qual_arena = nullptr;     // every Myread string, NUL-terminated, back to back
+  ~catt_result() { free(part[0]); free(part[1]); free(seq_arena); free(qual_arena); }
 };
 
 namespace catt {
@@ -67,6 +105,7 @@ struct Trace {
   Trace() : t(now_ms()), on(getenv("CATT_TRACE") != nullptr) {}
   void lap(const char* what) { if (on) { double n = now_ms(); fprintf(stderr, "[catt trace] %-28s %8.2f ms\n", what, n - t); t = n; } }
 };
-// Stage B (assemble.cu): everything after the per-read alignment records exist
-int stage_b(catt_ctx* c, const HostReads& hr, const DeviceReads& dr, catt_result* R, int* launches);
+// Stage B (assemble.cu): everything after the per-read alignment records exist.  The records are read from
+// c->recs_all[0/1] on the device; names/seqs/quals are host buffers (names are uploaded, strings are materialised on the host).
+int stage_b(catt_ctx* c, const HostReads& hr, const ReadsDev& reads, catt_result* R, int* launches);
 }  // namespace catt

@@ -123,6 +123,9 @@ struct PackedReads {
   int max_len = 0;
 };
 int pack_reads(int64_t n, const char* seqs, const int64_t* seq_off, PackedReads* out);
+// layout pass (lengths, word offsets; parallel) and the packing of reads [i0, i1) into dst (dst[0] = word off[i0])
+int pack_layout(int64_t n, const int64_t* seq_off, uint32_t* off, int32_t* len, int* max_len);
+void pack_range(int64_t i0, int64_t i1, const char* seqs, const int64_t* seq_off, const uint32_t* off, uint32_t* dst);
 
 // ---------------------------------------------------------------------------------------------------------------
 // stage A device buffers and kernels
@@ -139,7 +142,6 @@ struct AlignBuffers {       // per reference set, sized for one batch
   uint32_t* task_score = nullptr;  // per task: scoreA | scoreB << 16
   SwTask* wtasks = nullptr;        // n: the winning candidate of every mapped read (compacted), input of the TRACK pass
   uint32_t* wres = nullptr;        // 2 per winner: score<<20 | (1023-ei)<<10 | (1023-ej)
-  catt_aln* recs = nullptr;        // n
   uint32_t* gapped_list = nullptr; // read indices whose winner needs the traceback kernel
   unsigned long long* counters = nullptr;  // [0] cand, [1] cells, [2] n_gapped, [3] hits, [4] seed redo, [6] seed overflow,
                                            // [7] winners, [8] cells computed (canonical records), [9] task-buffer overflow
@@ -154,8 +156,8 @@ constexpr int N_COUNTERS = 16;
 int ensure_task_buffers(AlignBuffers& ab, int64_t want);
 int launch_expand(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, cudaStream_t st, int* launches);
 int launch_sw(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int sm_count, cudaStream_t st, int* launches);
-int launch_select(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int64_t first_ordinal, int min_score, int sm_count,
-                  cudaStream_t st, int* launches);
+int launch_select(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, catt_aln* recs, int64_t first_ordinal, int min_score,
+                  int sm_count, cudaStream_t st, int* launches);
 int launch_sw_pairs(const RefDev& ref, const ReadsDev& reads, const int32_t* d_rid, const int32_t* d_strand, int32_t* d_out3,
                     int sm_count, cudaStream_t st);
 int alu_peak(int sm_count, cudaStream_t st, double* ops_per_s, double* ms);
@@ -164,15 +166,15 @@ int alu_peak(int sm_count, cudaStream_t st, double* ops_per_s, double* ms);
 // stage B kernels (extract.cu, pool.cu)
 // ---------------------------------------------------------------------------------------------------------------
 struct ExtractItem {       // one SAM record (or V/J pair) to turn into a Myread
-  uint32_t read;           // index into the packed reads
+  uint32_t read;           // index into the packed reads (the V record's read for kind 2)
+  uint32_t read2;          // kind 2: the J record's read (SEQ equality, catt.jl:298)
   int16_t kind;            // 0 V part, 1 J part, 2 both-mapped
   int16_t strand;
   int16_t qb, m_end, rb, rid;     // of the V record (kind 0,2) or the J record (kind 1)
-  int16_t j_m_end, j_rid;         // kind 2: GetEndCigar of the J record
-  int32_t pad_;
+  int16_t j_m_end, j_rid, j_strand, pad_;   // kind 2: GetEndCigar / RNAME / strand of the J record
 };
 struct ExtractOut {
-  int16_t status;          // 0 dropped, 1 kept (able and passes the length / N filters)
+  int16_t status;          // 0 dropped, 1 kept (able and passes the length / N filters); 2 = dropped for SEQ mismatch
   int16_t seq_off, seq_len;       // slice of the SAM-oriented read
   int16_t cdr3_off, cdr3_len;     // relative to the slice; -1 = "None"
   int16_t able;
@@ -190,16 +192,24 @@ struct PoolItem {          // a Vpart/Jpart read as the k-mer table sees it
   uint32_t order;          // position in [Vpart; Jpart]: later writers win
   int32_t partial;         // 1 = cdr3 == "None": run the extension + finder!(array)
 };
-struct ExtendOut {
+constexpr int EXT_MAX = 152;                 // extension stops at 150 nt (catt.jl:349,389)
+constexpr int EXT_WORDS = (EXT_MAX + 15) / 16;
+struct ExtendOut {         // 48 bytes
   int16_t n_ext;           // bases added
   int16_t cdr3_off, cdr3_len;   // in the extended sequence; -1 = still "None"
   int16_t able;
-  uint8_t ext[152];        // added bases as codes, in emission order
+  uint32_t ext2[EXT_WORDS];     // added bases, 2 bits each, in emission order
+};
+struct OutDesc {           // everything the host needs to materialise one Myread (32 bytes)
+  uint32_t read;
+  int32_t xi;              // index into the ExtendOut array, -1 = not a partial read
+  int16_t strand, kind, seq_off, seq_len, cdr3_off, cdr3_len, v_id, j_id, q_start1, j_pad;
+  int32_t pad_;
 };
 struct KmerTable { unsigned long long* keys; unsigned long long* vals; uint64_t mask; };
 int launch_pool(const ReadsDev& reads, const PoolItem* d_items, int64_t n, int kmer, KmerTable tab, cudaStream_t st, int* launches);
 int launch_extend(const ReadsDev& reads, const FinderDev* d_finder, const PoolItem* d_items, const uint32_t* d_partial_idx,
-                  int64_t n_partial, int kmer, KmerTable tab, ExtendOut* d_out, cudaStream_t st, int* launches);
+                  int64_t n_partial, int kmer, KmerTable tab, ExtendOut* d_out, uint32_t* d_rescued, cudaStream_t st, int* launches);
 int launch_best_d(const char* d_cdr3, const int32_t* d_off, int64_t n, const char* d_dseq, const int32_t* d_doff, int nd,
                   int32_t* d_out, cudaStream_t st);
 

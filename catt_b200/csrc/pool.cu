@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(PW * 32) pool_kernel(ReadsDev reads, const Poo
 
 struct ExtWarp {
   uint8_t seq[MAX_READ + 160];
+  uint8_t ext[EXT_MAX + 8];
   FinderScratch fs;
 };
 
@@ -80,7 +81,7 @@ __device__ __forceinline__ bool ratio_ok(int x, int y) { return x > y ? (x <= 10
 // one warp per partial read (cdr3 == "None"): greedy walk over the table, then finder!(array) on the extended read
 __global__ void __launch_bounds__(PW * 32) extend_kernel(ReadsDev reads, const FinderDev* __restrict__ gfd, const PoolItem* __restrict__ items,
                                                          const uint32_t* __restrict__ partial_idx, int64_t n_partial, int k, KmerTable tab,
-                                                         ExtendOut* __restrict__ out) {
+                                                         ExtendOut* __restrict__ out, uint32_t* __restrict__ rescued) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FinderDev* fd = reinterpret_cast<FinderDev*>(smem_raw);
   ExtWarp* wsall = reinterpret_cast<ExtWarp*>(smem_raw + sizeof(FinderDev));
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(PW * 32) extend_kernel(ReadsDev reads, const F
           const int cw = 3 - (key & 3);
           seg = pi.side == 0 ? (((uint64_t)cw << (2 * (k - 1))) | (seg >> 2)) : (((seg << 2) | (uint64_t)cw) & kmask);
           cur = key >> 2;
-          if (lane == 0) o->ext[n_ext] = (uint8_t)cw;
+          if (lane == 0) ws.ext[n_ext] = (uint8_t)cw;
           n_ext++; idx++;
           flag = true;
         }
@@ -138,15 +139,23 @@ __global__ void __launch_bounds__(PW * 32) extend_kernel(ReadsDev reads, const F
     // build the extended read: right -> seq * ext ; left -> reverse(ext) * seq
     uint8_t* ext_seq = base;
     if (pi.side == 0) {
-      for (int i = lane; i < n_ext; i += 32) base[len0 + i] = o->ext[i];
+      for (int i = lane; i < n_ext; i += 32) base[len0 + i] = ws.ext[i];
     } else {
       ext_seq = base - n_ext;
-      for (int i = lane; i < n_ext; i += 32) ext_seq[i] = o->ext[n_ext - 1 - i];
+      for (int i = lane; i < n_ext; i += 32) ext_seq[i] = ws.ext[n_ext - 1 - i];
     }
     __syncwarp();
     int lo, l3;
     const bool able = finder_warp(ext_seq, len0 + n_ext, *fd, true, ws.fs, lane, &lo, &l3);
-    if (lane == 0) { o->n_ext = (int16_t)n_ext; o->cdr3_off = (int16_t)lo; o->cdr3_len = (int16_t)l3; o->able = able; }
+    if (lane == 0) {
+      o->n_ext = (int16_t)n_ext; o->cdr3_off = (int16_t)lo; o->cdr3_len = (int16_t)l3; o->able = able;
+      if (lo >= 0) atomicAdd(rescued, 1u);
+    }
+    if (lane < EXT_WORDS) {
+      uint32_t wv = 0;
+      for (int b = 0; b < 16; b++) { const int i = lane * 16 + b; if (i < n_ext) wv |= (uint32_t)(ws.ext[i] & 3) << (2 * b); }
+      o->ext2[lane] = wv;
+    }
     __syncwarp();
   }
 }
@@ -198,13 +207,13 @@ int launch_pool(const ReadsDev& reads, const PoolItem* d_items, int64_t n, int k
 }
 
 int launch_extend(const ReadsDev& reads, const FinderDev* d_finder, const PoolItem* d_items, const uint32_t* d_partial_idx,
-                  int64_t n_partial, int kmer, KmerTable tab, ExtendOut* d_out, cudaStream_t st, int* launches) {
+                  int64_t n_partial, int kmer, KmerTable tab, ExtendOut* d_out, uint32_t* d_rescued, cudaStream_t st, int* launches) {
   if (n_partial == 0) return CATT_OK;
   const size_t smem = sizeof(FinderDev) + sizeof(ExtWarp) * PW;
   static bool attr = false;
   if (!attr) { CATT_CUDA(cudaFuncSetAttribute(extend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
   const int grid = (int)std::min<int64_t>((n_partial + PW - 1) / PW, 148 * 8);
-  extend_kernel<<<grid, PW * 32, smem, st>>>(reads, d_finder, d_items, d_partial_idx, n_partial, kmer, tab, d_out);
+  extend_kernel<<<grid, PW * 32, smem, st>>>(reads, d_finder, d_items, d_partial_idx, n_partial, kmer, tab, d_out, d_rescued);
   CATT_CUDA(cudaGetLastError());
   *launches += 1;
   return CATT_OK;

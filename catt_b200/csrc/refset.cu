@@ -7,6 +7,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <omp.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -237,36 +238,88 @@ int compile_motif(const char* re, MotifDev* out) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// read packing (host).  TODO(next): move FASTQ parsing + packing onto the GPU.
+// read packing (host): ASCII -> 2-bit words + N mask, straight into pinned staging (api.cu pipelines it chunk by
+// chunk under the kernels of the previous chunk).
 // ---------------------------------------------------------------------------------------------------------------
-int pack_reads(int64_t n, const char* seqs, const int64_t* seq_off, PackedReads* out) {
-  out->off.resize(n + 1);
-  out->len.resize(n);
-  out->max_len = 0;
-  uint64_t w = 0;
-  for (int64_t i = 0; i < n; i++) {
-    int64_t l = seq_off[i + 1] - seq_off[i];
-    if (l > MAX_READ) { set_error("read %lld is %lld nt long; the limit is %d", (long long)i, (long long)l, MAX_READ); return CATT_E_LIMIT; }
-    out->off[i] = (uint32_t)w;
-    out->len[i] = (int32_t)l;
-    out->max_len = std::max(out->max_len, (int)l);
-    w += read_words((int)l);
-    if (w > 0xFFFFFFF0ull) { set_error("batch too large: packed reads exceed 2^32 words"); return CATT_E_LIMIT; }
-  }
-  out->off[n] = (uint32_t)w;
-  out->words.assign(w + 4, 0);
-  #pragma omp parallel for schedule(static)
-  for (int64_t i = 0; i < n; i++) {
-    const char* s = seqs + seq_off[i];
-    int l = out->len[i];
-    uint32_t* b = &out->words[out->off[i]];
-    uint32_t* m = b + read_base_words(l);
-    for (int k = 0; k < l; k++) {
-      uint8_t c = nt_code(s[k]);
-      if (c > 3) m[k >> 5] |= 1u << (k & 31);
-      else b[k >> 4] |= (uint32_t)c << ((k & 15) * 2);
+namespace {
+struct CodeLut {
+  uint8_t v[256];
+  CodeLut() { for (int i = 0; i < 256; i++) v[i] = nt_code((char)i); }
+};
+const CodeLut LUT;
+}  // namespace
+
+int pack_layout(int64_t n, const int64_t* seq_off, uint32_t* off, int32_t* len, int* max_len) {
+  const int nt = std::max(1, omp_get_max_threads());
+  std::vector<uint64_t> part((size_t)nt + 1, 0);
+  std::vector<int> pmax((size_t)nt, 0);
+  int64_t bad = -1;
+  #pragma omp parallel num_threads(nt)
+  {
+    const int t = omp_get_thread_num();
+    const int64_t lo = n * t / nt, hi = n * (t + 1) / nt;
+    uint64_t w = 0; int mx = 0;
+    for (int64_t i = lo; i < hi; i++) {
+      const int64_t l = seq_off[i + 1] - seq_off[i];
+      if (l > MAX_READ || l < 0) {
+        #pragma omp critical
+        { if (bad < 0 || i < bad) bad = i; }
+        continue;
+      }
+      len[i] = (int32_t)l; mx = std::max(mx, (int)l); w += read_words((int)l);
+    }
+    part[t + 1] = w; pmax[t] = mx;
+    #pragma omp barrier
+    #pragma omp single
+    { for (int k = 0; k < nt; k++) part[k + 1] += part[k]; }
+    if (bad < 0 && part[nt] <= 0xFFFFFFF0ull) {
+      uint64_t o = part[t];
+      for (int64_t i = lo; i < hi; i++) { off[i] = (uint32_t)o; o += read_words(len[i]); }
     }
   }
+  if (bad >= 0) {
+    set_error("read %lld is %lld nt long; the limit is %d", (long long)bad, (long long)(seq_off[bad + 1] - seq_off[bad]), MAX_READ);
+    return CATT_E_LIMIT;
+  }
+  if (part[nt] > 0xFFFFFFF0ull) { set_error("batch too large: packed reads exceed 2^32 words"); return CATT_E_LIMIT; }
+  off[n] = (uint32_t)part[nt];
+  int mx = 0;
+  for (int v : pmax) mx = std::max(mx, v);
+  *max_len = mx;
+  return CATT_OK;
+}
+
+void pack_range(int64_t i0, int64_t i1, const char* seqs, const int64_t* seq_off, const uint32_t* off, uint32_t* dst) {
+  const uint32_t base = i0 < i1 ? off[i0] : 0;
+  #pragma omp parallel for schedule(static)
+  for (int64_t i = i0; i < i1; i++) {
+    const unsigned char* s = reinterpret_cast<const unsigned char*>(seqs + seq_off[i]);
+    const int l = (int)(seq_off[i + 1] - seq_off[i]);
+    uint32_t* b = dst + (off[i] - base);
+    uint32_t* m = b + read_base_words(l);
+    for (int k = 0; k < l; k += 32) {
+      const int cnt = std::min(32, l - k);
+      uint64_t bw = 0; uint32_t mw = 0;
+      for (int j = 0; j < cnt; j++) {
+        const uint32_t c = LUT.v[s[k + j]];
+        bw |= (uint64_t)(c & 3u) << (2 * j);
+        mw |= (c >> 2) << j;
+      }
+      b[k >> 4] = (uint32_t)bw;
+      if (k + 16 < l) b[(k >> 4) + 1] = (uint32_t)(bw >> 32);
+      m[k >> 5] = mw;
+    }
+  }
+}
+
+int pack_reads(int64_t n, const char* seqs, const int64_t* seq_off, PackedReads* out) {
+  out->off.resize(n + 1);
+  out->len.resize(std::max<int64_t>(n, 1));
+  int rc = pack_layout(n, seq_off, out->off.data(), out->len.data(), &out->max_len);
+  if (rc) return rc;
+  out->len.resize(n);
+  out->words.assign((size_t)out->off[n] + 4, 0);
+  pack_range(0, n, seqs, seq_off, out->off.data(), out->words.data());
   return CATT_OK;
 }
 

@@ -558,15 +558,15 @@ int launch_sw(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int sm
 }
 
 // selection, the TRACK pass over the winners, CIGAR facts, traceback of the rare gapped winners
-int launch_select(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int64_t first_ordinal, int min_score, int sm_count,
-                  cudaStream_t st, int* launches) {
+int launch_select(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, catt_aln* recs, int64_t first_ordinal, int min_score,
+                  int sm_count, cudaStream_t st, int* launches) {
   if (reads.n == 0) return CATT_OK;
   select_kernel<<<(unsigned)((reads.n + 127) / 128), 128, 0, st>>>(ref, reads, ab.candbits, ab.tasks, ab.task_off, ab.task_score,
-                                                                   ab.cap_tasks, first_ordinal, min_score, ab.recs, ab.wtasks, ab.counters);
+                                                                   ab.cap_tasks, first_ordinal, min_score, recs, ab.wtasks, ab.counters);
   CATT_CUDA(cudaGetLastError());
   int rc = dispatch_sw<true>(ref, reads, ab.wtasks, reinterpret_cast<const uint32_t*>(ab.counters + 7), reads.n, ab.wres, sm_count, st);
   if (rc) return rc;
-  finish_kernel<<<(unsigned)((reads.n + 127) / 128), 128, 0, st>>>(ref, reads, ab.wtasks, ab.wres, ab.recs, ab.gapped_list, ab.counters);
+  finish_kernel<<<(unsigned)((reads.n + 127) / 128), 128, 0, st>>>(ref, reads, ab.wtasks, ab.wres, recs, ab.gapped_list, ab.counters);
   CATT_CUDA(cudaGetLastError());
   const size_t smem = (size_t)7 * (MAX_READ + 2) * sizeof(int16_t) + MAX_READ + (size_t)reads.max_len * ref.maxlen + 16;
   if (smem > 220 * 1024) {
@@ -575,7 +575,7 @@ int launch_select(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, in
   }
   static size_t attr = 0;
   if (smem > attr) { CATT_CUDA(cudaFuncSetAttribute(traceback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
-  traceback_kernel<<<sm_count * 4, 32, smem, st>>>(ref, reads, ab.gapped_list, ab.counters, ab.recs);
+  traceback_kernel<<<sm_count * 4, 32, smem, st>>>(ref, reads, ab.gapped_list, ab.counters, recs);
   CATT_CUDA(cudaGetLastError());
   *launches += 4;
   return CATT_OK;

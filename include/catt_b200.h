@@ -50,6 +50,10 @@ typedef struct catt_config {
   int32_t n_d;              /* refg[..]["Dregion"] length (0 = chain has no D segments) */
   const char* const* d_names;
   const char* const* d_seqs;
+  int32_t keep_records;     /* 1: every result also carries the per-read alignment records (catt_align_records); costs a
+                               64 B/read device->host copy, so it is off on the production path */
+  int32_t chunk_reads;      /* Stage A batch size of the pipelined path (0 = default 262144): host packing + H2D of chunk
+                               i+1 run under the kernels of chunk i */
 } catt_config;
 
 /* One SAM-visible alignment record = the line `bwa mem | samtools ... | awk` would leave for one read against one
@@ -101,6 +105,8 @@ typedef struct catt_info {
   int64_t kernel_launches;    /* CUDA kernels launched for this result */
   double ms_seed, ms_sw, ms_select, ms_extract, ms_pool, ms_h2d, ms_d2h, ms_host;  /* device/host stage times */
   int64_t cells_computed_v, cells_computed_j; /* DP cells actually computed: byte-identical records are scored once */
+  double ms_order;            /* device time of the SAM ordering / QNAME dedup / pairing kernels (samtools sort | tac | awk) */
+  double ms_pack;             /* host time packing reads that was NOT hidden under kernels */
 } catt_info;
 
 /* ---- lifecycle --------------------------------------------------------------------------------------------- */
@@ -127,7 +133,8 @@ int catt_run_reads(catt_ctx* ctx, int64_t n, const char* names, const int64_t* n
 int catt_result_info(const catt_result* r, catt_info* out);
 /* Vpart (which=0) / Jpart (1) in the reference's list order, ready for catt.jl:579 onwards. */
 int catt_result_reads(const catt_result* r, int which, const catt_read** reads, int64_t* n);
-/* Per-read alignment records (input order, one per read; unmapped reads have mapped=0): parity/diagnostics. */
+/* Per-read alignment records (input order, one per read; unmapped reads have mapped=0): parity/diagnostics.
+ * Only present when the context was created with keep_records = 1 (otherwise *n = 0). */
 int catt_align_records(const catt_result* r, int which, const catt_aln** recs, int64_t* n);
 void catt_result_free(catt_result* r);
 
