@@ -154,6 +154,7 @@ __device__ bool seed_one_read(const RefDev& ref, const uint32_t* __restrict__ T2
   if (lane == 0) ws.nruns = 0;
   __syncwarp();
   // ---- maximal runs >= 10 (each found once, from its left-maximal 10-mer window)
+  // step 1: every lane scans its window positions and queues the left-maximal (s, p) pairs
   for (int s = lane; s + SEED_K <= len; s += 32) {
     const uint64_t bw = ((uint64_t)w[(s >> 4) + 1] << 32) | w[s >> 4];
     const uint32_t key = (uint32_t)(bw >> ((s & 15) * 2)) & 0xFFFFFu;
@@ -161,13 +162,35 @@ __device__ bool seed_one_read(const RefDev& ref, const uint32_t* __restrict__ T2
     if ((uint32_t)(mw >> (s & 31)) & 0x3FFu) continue;                 // window holds an N
     if (!((__ldg(&ref.bitmap[key >> 5]) >> (key & 31)) & 1u)) continue;
     const uint32_t h0 = __ldg(&ref.kstart[key]), h1 = __ldg(&ref.kstart[key + 1]);
+    const uint32_t prev = s > 0 ? ws.codes[s - 1] : 5u;
     for (uint32_t h = h0; h < h1; h++) {
       const int p = (int)__ldg(&ref.kpos[h]);
-      if (s > 0 && p > 0 && ws.codes[s - 1] == tbase(T2, p - 1)) continue;   // not left-maximal
-      int e = SEED_K;
-      while (s + e < len && p + e < n2 && ws.codes[s + e] == tbase(T2, p + e)) e++;
+      if (p > 0 && prev == tbase(T2, p - 1)) continue;                  // not left-maximal
       const int idx = atomicAdd(&ws.nruns, 1);
-      if (idx < sc.cap) { sc.runs_q[idx] = (uint32_t)s | ((uint32_t)(s + e) << 16); sc.runs_t[idx] = (uint32_t)p; }
+      if (idx < sc.cap) { sc.runs_q[idx] = (uint32_t)s; sc.runs_t[idx] = (uint32_t)p; }
+    }
+  }
+  __syncwarp();
+  // step 2: the queued runs are extended by all lanes, 16 bases per step on the packed words
+  {
+    const int nq = min(ws.nruns, sc.cap);
+    for (int k = lane; k < nq; k += 32) {
+      const int s = (int)sc.runs_q[k], p = (int)sc.runs_t[k];
+      int e = SEED_K;
+      const int lim = min(len - s, n2 - p);
+      while (e < lim) {
+        const int a = s + e, b = p + e;
+        const uint32_t ra = (uint32_t)((((uint64_t)w[(a >> 4) + 1] << 32) | w[a >> 4]) >> ((a & 15) * 2));
+        const uint32_t tb = (uint32_t)((((uint64_t)T2[(b >> 4) + 1] << 32) | T2[b >> 4]) >> ((b & 15) * 2));
+        const uint32_t na = (uint32_t)((((uint64_t)nm[(a >> 5) + 1] << 32) | nm[a >> 5]) >> (a & 31)) & 0xFFFFu;
+        const uint32_t x = ra ^ tb;
+        int adv = x ? (__ffs(x) - 1) >> 1 : 16;
+        if (na) adv = min(adv, __ffs(na) - 1);
+        e += adv;
+        if (adv < 16) break;
+      }
+      e = min(e, lim);
+      sc.runs_q[k] = (uint32_t)s | ((uint32_t)(s + e) << 16);
     }
   }
   __syncwarp();
