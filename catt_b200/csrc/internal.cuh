@@ -61,7 +61,8 @@ struct RefDev {            // POD view handed to kernels
   const uint8_t* fa;       // forward FASTA codes (0..4, N kept): real_score compares against these
   const uint32_t* bitmap;  // 2^20 bits: which 10-mers occur in the 2-strand text
   const uint32_t* kstart;  // 2^20+1 CSR offsets
-  const uint32_t* kpos;    // text positions by 10-mer
+  const uint32_t* kpos;    // text positions by 10-mer, grouped by the text base preceding the occurrence
+  const unsigned long long* ksub;  // per 10-mer: cumulative sizes of the preceding-base groups 0..3 (4 x u16)
   const uint16_t* pos2rid; // forward position -> record
   const int32_t* rec_off;
   const int32_t* rec_len;

@@ -119,9 +119,33 @@ int RefSet::upload() {
   for (int p = 0; p + SEED_K <= n2; p++) kstart[key_at(p) + 1]++;
   for (int i = 0; i < NK; i++) kstart[i + 1] += kstart[i];
   std::vector<uint32_t> kpos(std::max(1, n2 - SEED_K + 1));
+  // every key's occurrence list is grouped by the text base BEFORE the occurrence (groups 0..3, then "none" for p = 0):
+  // a window whose previous read base is b starts a new maximal run exactly at the occurrences outside group b, so the
+  // seeding kernel skips group b wholesale.  ksub[key] = cumulative sizes of groups 0..3 (4 x u16).
+  std::vector<unsigned long long> ksub(NK, 0ull);
   {
-    std::vector<uint32_t> fill(kstart.begin(), kstart.end() - 1);
-    for (int p = 0; p + SEED_K <= n2; p++) { uint32_t k = key_at(p); kpos[fill[k]++] = (uint32_t)p; bitmap[k >> 5] |= 1u << (k & 31); }
+    std::vector<uint32_t> gcount((size_t)NK * 4, 0);
+    auto group_of = [&](int p) { return p == 0 ? 4 : (int)T[p - 1]; };
+    for (int p = 0; p + SEED_K <= n2; p++) { const int g = group_of(p); if (g < 4) gcount[(size_t)key_at(p) * 4 + g]++; }
+    std::vector<uint32_t> fill((size_t)NK * 5);
+    for (int k = 0; k < NK; k++) {
+      if (kstart[k + 1] == kstart[k]) continue;
+      uint32_t o = kstart[k], cum = 0;
+      unsigned long long sub = 0;
+      for (int g = 0; g < 4; g++) {
+        fill[(size_t)k * 5 + g] = o + cum;
+        cum += gcount[(size_t)k * 4 + g];
+        if (cum > 0xFFFFu) { set_error("10-mer with more than 65535 occurrences in the reference"); return CATT_E_LIMIT; }
+        sub |= (unsigned long long)cum << (16 * g);
+      }
+      fill[(size_t)k * 5 + 4] = o + cum;
+      ksub[k] = sub;
+    }
+    for (int p = 0; p + SEED_K <= n2; p++) {
+      const uint32_t k = key_at(p);
+      kpos[fill[(size_t)k * 5 + group_of(p)]++] = (uint32_t)p;
+      bitmap[k >> 5] |= 1u << (k & 31);
+    }
   }
   std::vector<uint16_t> pos2rid(L);
   for (size_t r = 0; r < names.size(); r++) for (int i = 0; i < len[r]; i++) pos2rid[off[r] + i] = (uint16_t)r;
@@ -142,6 +166,7 @@ int RefSet::upload() {
   if ((rc = to_device(bitmap, (const void**)&dev.bitmap, allocs))) return rc;
   if ((rc = to_device(kstart, (const void**)&dev.kstart, allocs))) return rc;
   if ((rc = to_device(kpos, (const void**)&dev.kpos, allocs))) return rc;
+  if ((rc = to_device(ksub, (const void**)&dev.ksub, allocs))) return rc;
   if ((rc = to_device(pos2rid, (const void**)&dev.pos2rid, allocs))) return rc;
   if ((rc = to_device(canon, (const void**)&dev.canon, allocs))) return rc;
   if ((rc = to_device(off, (const void**)&dev.rec_off, allocs))) return rc;

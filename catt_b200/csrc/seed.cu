@@ -162,10 +162,18 @@ __device__ bool seed_one_read(const RefDev& ref, const uint32_t* __restrict__ T2
     if ((uint32_t)(mw >> (s & 31)) & 0x3FFu) continue;                 // window holds an N
     if (!((__ldg(&ref.bitmap[key >> 5]) >> (key & 31)) & 1u)) continue;
     const uint32_t h0 = __ldg(&ref.kstart[key]), h1 = __ldg(&ref.kstart[key + 1]);
-    const uint32_t prev = s > 0 ? ws.codes[s - 1] : 5u;
+    // occurrences whose preceding text base equals the preceding read base continue a run found earlier: that whole
+    // group of the (grouped) occurrence list is skipped
+    const uint32_t prev = s > 0 ? ws.codes[s - 1] : 4u;
+    uint32_t ex0 = h1, ex1 = h1;
+    if (prev < 4) {
+      const unsigned long long sub = __ldg(&ref.ksub[key]);
+      ex0 = h0 + (prev ? (uint32_t)(sub >> (16 * (prev - 1))) & 0xFFFFu : 0u);
+      ex1 = h0 + ((uint32_t)(sub >> (16 * prev)) & 0xFFFFu);
+    }
     for (uint32_t h = h0; h < h1; h++) {
+      if (h == ex0) { h = ex1; if (h >= h1) break; }
       const int p = (int)__ldg(&ref.kpos[h]);
-      if (p > 0 && prev == tbase(T2, p - 1)) continue;                  // not left-maximal
       const int idx = atomicAdd(&ws.nruns, 1);
       if (idx < sc.cap) { sc.runs_q[idx] = (uint32_t)s; sc.runs_t[idx] = (uint32_t)p; }
     }
