@@ -19,26 +19,46 @@
 namespace catt {
 namespace {
 
-constexpr int SEED_WARPS = 4;
+constexpr int SEED_WARPS = 8;
 constexpr int RUNS_SMEM = 512;
 constexpr int RUNS_GLOBAL = 16384;
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int T2_SMEM_MAX_BYTES = 56 * 1024;
 
+// per-warp scratch, carved from dynamic shared memory; the per-position arrays are sized by the longest read of the batch
 struct WarpScratch {
-  uint32_t M1[MAX_READ];      // max run end per start position
-  uint32_t Pm[MAX_READ];      // exclusive prefix max of M1; reused as the interval list of pass 2
-  uint32_t cnt[MAX_READ];     // occurrences of the SMEM that starts here
-  uint16_t starts[MAX_READ];  // distinct starts of the runs covering `mid` (pass 2)
-  uint32_t startbits[MAX_READ / 32];
-  uint32_t cand[MAX_CW];
-  uint32_t canon[MAX_CW];     // cand with byte-identical records folded onto their first copy
-  uint8_t codes[MAX_READ];
-  int nruns, ncov, niv, pad_;
-  uint32_t runs_q[RUNS_SMEM];   // qs | qe << 16
-  uint32_t runs_t[RUNS_SMEM];   // start in T
-  uint16_t cov[RUNS_SMEM];
+  uint32_t* M1;         // [ml] max run end per start position
+  uint32_t* Pm;         // [ml] exclusive prefix max of M1; reused as the interval list of pass 2
+  uint32_t* cnt;        // [ml] occurrences of the SMEM that starts here
+  uint16_t* starts;     // [ml] distinct starts of the runs covering `mid` (pass 2)
+  uint8_t* codes;       // [ml]
+  uint32_t* startbits;  // [MAX_READ / 32]
+  uint32_t* cand;       // [MAX_CW]
+  uint32_t* canon;      // [MAX_CW] cand with byte-identical records folded onto their first copy
+  int* ctr;             // nruns, ncov, niv
+  uint32_t* runs_q;     // [RUNS_SMEM] qs | qe << 16
+  uint32_t* runs_t;     // [RUNS_SMEM] start in T
+  uint16_t* cov;        // [RUNS_SMEM]
 };
+__host__ __device__ inline size_t warp_scratch_bytes(int ml) {
+  return (size_t)ml * (4 * 3 + 2 + 1) + (MAX_READ / 32) * 4 + MAX_CW * 8 + 16 + (size_t)RUNS_SMEM * 10;
+}
+__device__ inline WarpScratch carve(unsigned char* base, int ml) {
+  WarpScratch ws;
+  ws.M1 = reinterpret_cast<uint32_t*>(base); base += 4 * ml;
+  ws.Pm = reinterpret_cast<uint32_t*>(base); base += 4 * ml;
+  ws.cnt = reinterpret_cast<uint32_t*>(base); base += 4 * ml;
+  ws.startbits = reinterpret_cast<uint32_t*>(base); base += (MAX_READ / 32) * 4;
+  ws.cand = reinterpret_cast<uint32_t*>(base); base += MAX_CW * 4;
+  ws.canon = reinterpret_cast<uint32_t*>(base); base += MAX_CW * 4;
+  ws.ctr = reinterpret_cast<int*>(base); base += 16;
+  ws.runs_q = reinterpret_cast<uint32_t*>(base); base += RUNS_SMEM * 4;
+  ws.runs_t = reinterpret_cast<uint32_t*>(base); base += RUNS_SMEM * 4;
+  ws.cov = reinterpret_cast<uint16_t*>(base); base += RUNS_SMEM * 2;
+  ws.starts = reinterpret_cast<uint16_t*>(base); base += 2 * ml;
+  ws.codes = base;
+  return ws;
+}
 
 struct Scratch {
   uint32_t* runs_q; uint32_t* runs_t; uint16_t* cov; int cap;
@@ -64,21 +84,21 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
 }
 
 // pass 2 for one SMEM: maximal intervals containing `mid` with >= m covering runs
-__device__ void reseed(const RefDev& ref, WarpScratch& ws, const Scratch& sc, int n, int mid, int m, int lane) {
-  if (lane == 0) { ws.ncov = 0; ws.niv = 0; }
+__device__ void reseed(const RefDev& ref, const WarpScratch& ws, const Scratch& sc, int n, int mid, int m, int lane) {
+  if (lane == 0) { ws.ctr[1] = 0; ws.ctr[2] = 0; }
   if (lane < MAX_READ / 32) ws.startbits[lane] = 0;
   __syncwarp();
   for (int r = lane; r < n; r += 32) {
     const uint32_t q = sc.runs_q[r];
     const int qs = q & 0xffff, qe = q >> 16;
     if (qs <= mid && qe > mid) {
-      const int idx = atomicAdd(&ws.ncov, 1);
+      const int idx = atomicAdd(&ws.ctr[1], 1);
       sc.cov[idx] = (uint16_t)r;                      // cov capacity == run capacity
       atomicOr(&ws.startbits[qs >> 5], 1u << (qs & 31));
     }
   }
   __syncwarp();
-  const int nc = ws.ncov;
+  const int nc = ws.ctr[1];
   if (nc < m) return;
   int ns = 0;
   for (int w = 0; w < MAX_READ / 32; w++) {
@@ -119,13 +139,13 @@ __device__ void reseed(const RefDev& ref, WarpScratch& ws, const Scratch& sc, in
     if (lane == 0) excl = 0;
     excl = max(excl, prev_run);
     if (valid && e > excl && (int)e - sp >= SEED_K) {
-      const int idx = atomicAdd(&ws.niv, 1);
+      const int idx = atomicAdd(&ws.ctr[2], 1);
       ws.Pm[idx] = (uint32_t)sp | (e << 16);
     }
     prev_run = max(prev_run, __shfl_sync(FULL, incl, 31));
   }
   __syncwarp();
-  const int nv = ws.niv;
+  const int nv = ws.ctr[2];
   for (int v = 0; v < nv; v++) {
     const int s = ws.Pm[v] & 0xffff, e = ws.Pm[v] >> 16;
     for (int k = lane; k < nc; k += 32) {
@@ -140,7 +160,7 @@ __device__ void reseed(const RefDev& ref, WarpScratch& ws, const Scratch& sc, in
 
 // returns false when the run list overflowed the scratch capacity
 __device__ bool seed_one_read(const RefDev& ref, const uint32_t* __restrict__ T2, const ReadsDev& reads, int64_t r,
-                              WarpScratch& ws, const Scratch& sc, int lane) {
+                              const WarpScratch& ws, const Scratch& sc, int lane) {
   const int len = reads.len[r];
   const uint32_t* __restrict__ w = reads.words + reads.off[r];
   const uint32_t* __restrict__ nm = w + read_base_words(len);
@@ -151,7 +171,7 @@ __device__ bool seed_one_read(const RefDev& ref, const uint32_t* __restrict__ T2
     ws.M1[i] = 0; ws.cnt[i] = 0;
   }
   if (lane < MAX_CW) ws.cand[lane] = 0;
-  if (lane == 0) ws.nruns = 0;
+  if (lane == 0) ws.ctr[0] = 0;
   __syncwarp();
   // ---- maximal runs >= 10 (each found once, from its left-maximal 10-mer window)
   // step 1: every lane scans its window positions and queues the left-maximal (s, p) pairs
@@ -174,14 +194,14 @@ __device__ bool seed_one_read(const RefDev& ref, const uint32_t* __restrict__ T2
     for (uint32_t h = h0; h < h1; h++) {
       if (h == ex0) { h = ex1; if (h >= h1) break; }
       const int p = (int)__ldg(&ref.kpos[h]);
-      const int idx = atomicAdd(&ws.nruns, 1);
+      const int idx = atomicAdd(&ws.ctr[0], 1);
       if (idx < sc.cap) { sc.runs_q[idx] = (uint32_t)s; sc.runs_t[idx] = (uint32_t)p; }
     }
   }
   __syncwarp();
   // step 2: the queued runs are extended by all lanes, 16 bases per step on the packed words
   {
-    const int nq = min(ws.nruns, sc.cap);
+    const int nq = min(ws.ctr[0], sc.cap);
     for (int k = lane; k < nq; k += 32) {
       const int s = (int)sc.runs_q[k], p = (int)sc.runs_t[k];
       int e = SEED_K;
@@ -202,7 +222,7 @@ __device__ bool seed_one_read(const RefDev& ref, const uint32_t* __restrict__ T2
     }
   }
   __syncwarp();
-  const int n = ws.nruns;
+  const int n = ws.ctr[0];
   if (n > sc.cap) return false;
   if (n == 0) return true;
   // ---- pass 1: SMEM occurrences
@@ -251,20 +271,27 @@ __device__ bool seed_one_read(const RefDev& ref, const uint32_t* __restrict__ T2
       const uint32_t bal = __ballot_sync(FULL, isn);
       if (bal) { x = x + 1 + (__ffs(bal) - 1) + 1; continue; }
     }
-    int e = x + 11;
-    uint32_t c;
-    bool restart = false, stop = false;
-    while (true) {
+    // shortest e >= x+11 with fewer than 20 runs covering [x, e): the count is non-increasing in e, so the end E of the
+    // last prefix that still has >= 20 covering runs is found by bisection instead of one warp-wide count per base
+    auto covering = [&](int e) {
       uint32_t mine = 0;
       for (int k = lane; k < n; k += 32) { const uint32_t q = sc.runs_q[k]; mine += ((int)(q & 0xffff) <= x && (int)(q >> 16) >= e); }
-      c = warp_sum(mine);
-      if (c < 20) break;
-      if (e >= len) { stop = true; break; }
-      if (ws.codes[e] > 3) { x = e + 1; restart = true; break; }
-      e++;
+      return warp_sum(mine);
+    };
+    int e = x + 11;
+    uint32_t c = covering(e);
+    if (c >= 20) {
+      int lo = e, hi = len;                                  // covering(lo) >= 20
+      uint32_t chi = lo < hi ? covering(hi) : c;
+      if (chi >= 20) break;                                  // the tile would run to the end of the read: stop
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        const uint32_t cm = covering(mid);
+        if (cm >= 20) lo = mid; else { hi = mid; chi = cm; }
+      }
+      if (ws.codes[lo] > 3) { x = lo + 1; continue; }       // the base that would extend the tile is an N
+      e = hi; c = chi;
     }
-    if (stop) break;
-    if (restart) continue;
     if (c > 0) {
       for (int k = lane; k < n; k += 32) {
         const uint32_t q = sc.runs_q[k];
@@ -278,7 +305,7 @@ __device__ bool seed_one_read(const RefDev& ref, const uint32_t* __restrict__ T2
   return true;
 }
 
-__device__ __forceinline__ void write_out(const RefDev& ref, WarpScratch& ws, int64_t r, uint32_t* candbits, uint32_t* canonbits,
+__device__ __forceinline__ void write_out(const RefDev& ref, const WarpScratch& ws, int64_t r, uint32_t* candbits, uint32_t* canonbits,
                                           uint32_t* ntask, int lane) {
   uint32_t nf = 0, nr = 0;
   if (lane < MAX_CW) ws.canon[lane] = 0;
@@ -312,12 +339,13 @@ __global__ void __launch_bounds__(SEED_WARPS * 32) seed_kernel(RefDev ref, Reads
                                                                uint32_t* __restrict__ gscratch, int t2_bytes_smem) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint64_t bar;
-  WarpScratch* all = reinterpret_cast<WarpScratch*>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  WarpScratch& ws = all[warp];
+  const int ml = (reads.max_len + 31) & ~31;
+  const size_t wbytes = (warp_scratch_bytes(ml) + 15) & ~(size_t)15;
+  const WarpScratch ws = carve(smem_raw + wbytes * warp, ml);
   const uint32_t* T2 = ref.T2;
   if (t2_bytes_smem > 0) {
-    uint32_t* t2s = reinterpret_cast<uint32_t*>(smem_raw + sizeof(WarpScratch) * SEED_WARPS);
+    uint32_t* t2s = reinterpret_cast<uint32_t*>(smem_raw + wbytes * SEED_WARPS);
     stage_to_smem(t2s, ref.T2, (uint32_t)t2_bytes_smem, &bar);
     T2 = t2s;
   }
@@ -350,11 +378,12 @@ __global__ void __launch_bounds__(SEED_WARPS * 32) seed_kernel(RefDev ref, Reads
 int launch_seed(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int sm_count, cudaStream_t st, int* launches) {
   const int t2_bytes = t2_words(ref.L) * 4;
   const int t2_smem = t2_bytes <= T2_SMEM_MAX_BYTES ? t2_bytes : 0;
-  const size_t smem = sizeof(WarpScratch) * SEED_WARPS + t2_smem;
+  const int ml = (reads.max_len + 31) & ~31;
+  const size_t smem = ((warp_scratch_bytes(ml) + 15) & ~(size_t)15) * SEED_WARPS + t2_smem;
   static bool attr_set = false;
   if (!attr_set) {
-    CATT_CUDA(cudaFuncSetAttribute(seed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    CATT_CUDA(cudaFuncSetAttribute(seed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CATT_CUDA(cudaFuncSetAttribute(seed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CATT_CUDA(cudaFuncSetAttribute(seed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   int per_sm = 0;
