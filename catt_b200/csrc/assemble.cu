@@ -17,7 +17,10 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <sys/mman.h>
+
 #include <algorithm>
+#include <mutex>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -260,6 +263,57 @@ int scan_u32(catt_ctx* c, const uint32_t* in, uint32_t* out, int64_t count, cuda
   return CATT_OK;
 }
 
+}  // namespace
+
+// ---- reusable host blocks (see host_types.h) -------------------------------------------------------------------------------
+namespace {
+struct BlockCache {
+  std::mutex mu;
+  struct Ent { void* p; size_t cap; };
+  std::vector<Ent> free_list;
+  size_t held = 0;
+  ~BlockCache() { for (auto& e : free_list) free(e.p); }
+};
+BlockCache g_blocks;
+constexpr size_t BLOCK_SMALL = 1 << 20;            // below this plain malloc/free is fine
+constexpr size_t BLOCK_KEEP_MAX = (size_t)6 << 30;  // never sit on more than this much freed memory
+}  // namespace
+
+void* block_get(size_t bytes, size_t* cap) {
+  if (bytes < BLOCK_SMALL) { *cap = bytes; return malloc(std::max<size_t>(bytes, 1)); }
+  {
+    std::lock_guard<std::mutex> lk(g_blocks.mu);
+    size_t best = SIZE_MAX;
+    for (size_t i = 0; i < g_blocks.free_list.size(); i++) {
+      const size_t c = g_blocks.free_list[i].cap;
+      if (c >= bytes && c <= bytes * 2 + (64u << 20) && (best == SIZE_MAX || c < g_blocks.free_list[best].cap)) best = i;
+    }
+    if (best != SIZE_MAX) {
+      const BlockCache::Ent e = g_blocks.free_list[best];
+      g_blocks.free_list.erase(g_blocks.free_list.begin() + best);
+      g_blocks.held -= e.cap;
+      *cap = e.cap;
+      return e.p;
+    }
+  }
+  const size_t want = (bytes + bytes / 8 + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
+  void* p = nullptr;
+  if (posix_memalign(&p, 2u << 20, want) != 0) return nullptr;
+  madvise(p, want, MADV_HUGEPAGE);
+  *cap = want;
+  return p;
+}
+
+void block_put(void* p, size_t cap) {
+  if (!p) return;
+  if (cap < BLOCK_SMALL) { free(p); return; }
+  std::lock_guard<std::mutex> lk(g_blocks.mu);
+  if (g_blocks.held + cap > BLOCK_KEEP_MAX || g_blocks.free_list.size() >= 16) { free(p); return; }
+  g_blocks.free_list.push_back({p, cap});
+  g_blocks.held += cap;
+}
+
+namespace {
 const char FWD[6] = "ACGTN";
 const char RCV[6] = "TGCAN";
 struct StrLut {
@@ -487,15 +541,26 @@ int stage_b(catt_ctx* c, const HostReads& hr, const ReadsDev& reads, catt_result
     qoff[m + 1] = (c_off >= 0 ? c_len : base_q + n_ext) + 1;
   }
   for (int64_t m = 0; m < M; m++) { soff[m + 1] += soff[m]; qoff[m + 1] += qoff[m]; }
-  R->seq_arena = (char*)malloc((size_t)soff[M] + 1);
-  R->qual_arena = (char*)malloc((size_t)qoff[M] + 1);
+  tr.lap("B: string sizes");
+  R->seq_arena = (char*)block_get((size_t)soff[M] + 1, &R->cap_seq);
+  R->qual_arena = (char*)block_get((size_t)qoff[M] + 1, &R->cap_qual);
   R->npart[0] = info.vpart; R->npart[1] = info.jpart;
-  R->part[0] = (catt_read*)malloc((size_t)std::max<int64_t>(info.vpart, 1) * sizeof(catt_read));
-  R->part[1] = (catt_read*)malloc((size_t)std::max<int64_t>(info.jpart, 1) * sizeof(catt_read));
+  R->part[0] = (catt_read*)block_get((size_t)std::max<int64_t>(info.vpart, 1) * sizeof(catt_read), &R->cap_part[0]);
+  R->part[1] = (catt_read*)block_get((size_t)std::max<int64_t>(info.jpart, 1) * sizeof(catt_read), &R->cap_part[1]);
   if (!R->seq_arena || !R->qual_arena || !R->part[0] || !R->part[1]) { set_error("out of host memory for the result"); return CATT_E_LIMIT; }
+  tr.lap("B: result blocks");
   static const char NT[] = "ACGT";
   #pragma omp parallel for schedule(static)
   for (int64_t m = 0; m < M; m++) {
+    // the lists are in alignment-score order, so the reads are visited at random: prefetch two levels ahead
+    // (offset table, then the sequence / quality lines) or every iteration stalls on ~6 DRAM misses
+    if (m + 32 < M) __builtin_prefetch(&hr.seq_off[hdesc[m + 32].read]);
+    if (m + 16 < M) {
+      const OutDesc& pn = hdesc[m + 16];
+      const int64_t o = hr.seq_off[pn.read] + (pn.strand ? 0 : pn.seq_off);
+      __builtin_prefetch(hr.seqs + o); __builtin_prefetch(hr.seqs + o + 64); __builtin_prefetch(hr.seqs + o + 128);
+      if (hr.quals) { __builtin_prefetch(hr.quals + o); __builtin_prefetch(hr.quals + o + 64); __builtin_prefetch(hr.quals + o + 128); }
+    }
     const OutDesc& p = hdesc[m];
     const int side = m < info.vpart ? 0 : 1;
     const int len = (int)(hr.seq_off[p.read + 1] - hr.seq_off[p.read]);
@@ -513,27 +578,32 @@ int stage_b(catt_ctx* c, const HostReads& hr, const ReadsDev& reads, catt_result
     if (side == 0) for (int i = 0; i < n_ext; i++) s[p.seq_len + i] = ext_at(i);
     const int slen = p.seq_len + n_ext;
     s[slen] = 0;
-    // quality: the Myread's string before finder! slices it
+    // quality: the Myread's string before finder! slices it = 'G' x lead | base part | 'G' x (n_ext - lead), where the
+    // base part is qual[seq_off ..] (V side, both-mapped) or qual[1:start-1] * 'G'^pad (J side, catt.jl:126), taken
+    // from the SAM-oriented quality string; emitted in runs (memset / memcpy / reversed copy), not per character
     const int base_q = p.kind == 1 ? (p.q_start1 - 1 + std::max(0, (int)p.j_pad)) : p.seq_len;
     const int qfull = base_q + n_ext;
-    auto sq = [&](int i) { return rq ? (p.strand ? rq[len - 1 - i] : rq[i]) : 'I'; };
-    auto qat = [&](int i) -> char {                               // i in [0, qfull)
-      const int b = i - lead;
-      if (b < 0 || b >= base_q) return 'G';                      // extension padding
-      if (p.kind == 1) return b < p.q_start1 - 1 ? sq(b) : 'G';  // catt.jl:126
-      return sq(p.seq_off + b);
-    };
+    const int real_lo = lead;                                                     // [real_lo, real_hi): characters that come from rq
+    const int real_hi = lead + (p.kind == 1 ? std::min(base_q, p.q_start1 - 1) : base_q);
+    const int src0 = p.kind == 1 ? 0 : p.seq_off;                                 // SAM-oriented index of the first real character
     char* q = R->qual_arena + qoff[m];
     uint8_t flags = (uint8_t)(p.kind == 0 ? 1 : p.kind == 1 ? 2 : 4);
-    int qlen;
-    if (c_off >= 0) {                                             // rd.qual = rd.qual[range] (Jtool.jl:365,383)
-      qlen = c_len;
-      for (int i = 0; i < c_len; i++) {
-        if (c_off + i < qfull) q[i] = qat(c_off + i); else { q[i] = 'G'; flags |= 8; }    // reference: BoundsError
+    const int a0 = c_off >= 0 ? c_off : 0;                                        // rd.qual = rd.qual[range] (Jtool.jl:365,383)
+    const int qlen = c_off >= 0 ? c_len : qfull;
+    if (c_off >= 0 && c_off + c_len > qfull) flags |= 8;                          // reference: BoundsError
+    {
+      const int lo = std::max(a0, real_lo), hi = std::min(a0 + qlen, real_hi);
+      if (hi > lo) {
+        if (lo > a0) memset(q, 'G', (size_t)(lo - a0));
+        const int j0 = src0 + (lo - real_lo), cntr = hi - lo;
+        char* d = q + (lo - a0);
+        if (!rq) memset(d, 'I', (size_t)cntr);
+        else if (!p.strand) memcpy(d, rq + j0, (size_t)cntr);
+        else { const char* sp = rq + (len - 1 - j0); for (int i = 0; i < cntr; i++) d[i] = sp[-i]; }
+        if (a0 + qlen > hi) memset(q + (hi - a0), 'G', (size_t)(a0 + qlen - hi));
+      } else {
+        memset(q, 'G', (size_t)qlen);
       }
-    } else {
-      qlen = qfull;
-      for (int i = 0; i < qfull; i++) q[i] = qat(i);
     }
     q[qlen] = 0;
     catt_read rd{};

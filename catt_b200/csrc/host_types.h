@@ -88,13 +88,25 @@ struct catt_batch {
   catt_info info{};
 };
 
+namespace catt {
+// Host blocks for the result lists.  A result holds ~250 B per kept read; freshly mapped memory costs one page fault per
+// 4 KiB on first touch, which dominated the materialisation step, so freed blocks are kept (bounded) and reused by the
+// next result of the process, and new blocks are 2 MiB aligned with MADV_HUGEPAGE.
+void* block_get(size_t bytes, size_t* cap);
+void block_put(void* p, size_t cap);
+}  // namespace catt
+
 struct catt_result {
   catt_info info{};
   catt_read* part[2] = {nullptr, nullptr};
   int64_t npart[2] = {0, 0};
   std::vector<catt_aln> rec[2];
   char* seq_arena = nullptr; char* qual_arena = nullptr;     // every Myread string, NUL-terminated, back to back
-  ~catt_result() { free(part[0]); free(part[1]); free(seq_arena); free(qual_arena); }
+  size_t cap_part[2] = {0, 0}, cap_seq = 0, cap_qual = 0;
+  ~catt_result() {
+    catt::block_put(part[0], cap_part[0]); catt::block_put(part[1], cap_part[1]);
+    catt::block_put(seq_arena, cap_seq); catt::block_put(qual_arena, cap_qual);
+  }
 };
 
 namespace catt {
