@@ -221,6 +221,16 @@ class Catt:
                                              jrec.ctypes.data, C.byref(h)))
         return Result(self, h)
 
+    def assemble_buffers(self, n, name_buf, name_off, seq_buf, seq_off, qual_buf, vrec, jrec) -> Result:
+        """catt_assemble on caller buffers (bytes-like + int64 offsets) and the gathered alignment records."""
+        h = C.c_void_p()
+        vrec = np.ascontiguousarray(vrec)
+        jrec = np.ascontiguousarray(jrec)
+        _lib.check(_lib.load().catt_assemble(self._h, n, _addr(name_buf), name_off.ctypes.data, _addr(seq_buf), seq_off.ctypes.data,
+                                             _addr(qual_buf) if qual_buf is not None else None, vrec.ctypes.data, jrec.ctypes.data,
+                                             C.byref(h)))
+        return Result(self, h)
+
     def synth_reads(self, n, length=150, first_index=0, seed=20251019, p_err=0.003, with_n=False):
         """SURVEY §8d config-3 generator.  Returns (name_buf, name_off, seq_buf, seq_off, qual_buf) as numpy arrays."""
         seqs = np.empty(n * length, dtype=np.uint8)

@@ -1,0 +1,83 @@
+"""One sample over N GPUs of one node: reads shard naturally, so every rank runs Stage A
+(`catt_align_shard`: seeding + SW + hit selection, > 70 % of the device time) on a contiguous block of the input with
+the GLOBAL `first_ordinal` (bwa's hash tie-break uses the global read ordinal), the 32-byte alignment records are
+all-gathered (NCCL over NVLink on GPUs, gloo in the CPU tests), and Stage B (`catt_assemble`: the SAM order / QNAME
+dedup / V-J join are global, the k-mer table is a global last-writer-wins map) runs once, on rank `root`.
+
+One process per GPU, launched with torchrun; `torch.distributed` is plumbing only - every computation is in
+libcatt_b200.so.  Independent samples (the weak-scaling mode of bench.py) need no exchange at all.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+
+
+def shard_bounds(n: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous block [lo, hi) of rank `rank`: sizes differ by at most one read, earlier ranks take the extra ones."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def gather_records(local: np.ndarray, n: int, group=None, device=None) -> np.ndarray:
+    """All-gather the per-read alignment records (ALN_DTYPE) of every rank's block into the full array of n records.
+
+    Blocks are padded to the largest block so one all_gather_into_tensor moves everything; `device` is the CUDA device
+    to stage through for the NCCL backend (None = CPU tensors, gloo)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rec = _lib.ALN_DTYPE.itemsize
+    cap = shard_bounds(n, world, 0)[1]                      # rank 0 owns the largest block
+    buf = np.zeros(max(cap, 1) * rec, dtype=np.uint8)
+    raw = np.ascontiguousarray(local).view(np.uint8).reshape(-1)
+    buf[:raw.size] = raw
+    t = torch.from_numpy(buf)
+    if device is not None:
+        t = t.to(device, non_blocking=False)
+    out = torch.empty(world * t.numel(), dtype=torch.uint8, device=t.device)
+    dist.all_gather_into_tensor(out, t, group=group)
+    flat = out.cpu().numpy().reshape(world, -1)
+    full = np.zeros(n, dtype=_lib.ALN_DTYPE)
+    for r in range(world):
+        lo, hi = shard_bounds(n, world, r)
+        full[lo:hi] = flat[r, :(hi - lo) * rec].view(_lib.ALN_DTYPE)
+    return full
+
+
+class ShardedCatt:
+    """`Catt.mainflow_buffers` for one sample spread over the ranks of a process group.
+
+    `align_fn(n, seq_view, seq_off_view, first_ordinal) -> (v_recs, j_recs)` and
+    `assemble_fn(n, names, name_off, seqs, seq_off, quals, v_recs, j_recs) -> result` default to the context's
+    `catt_align_shard` / `catt_assemble`; the CPU tests inject stand-ins so the sharding logic runs under gloo."""
+
+    def __init__(self, ctx=None, group=None, device=None, align_fn=None, assemble_fn=None, root=0):
+        self.ctx, self.group, self.device, self.root = ctx, group, device, root
+        self.align_fn = align_fn or self._align
+        self.assemble_fn = assemble_fn or self._assemble
+
+    def _align(self, n, seq_buf, seq_off, first_ordinal):
+        return self.ctx.align_shard_buffers(n, seq_buf, seq_off, first_ordinal=first_ordinal)
+
+    def _assemble(self, n, name_buf, name_off, seq_buf, seq_off, qual_buf, v, j):
+        return self.ctx.assemble_buffers(n, name_buf, name_off, seq_buf, seq_off, qual_buf, v, j)
+
+    def mainflow_buffers(self, n, name_buf, name_off, seq_buf, seq_off, qual_buf):
+        """Every rank passes the same whole-sample buffers; returns the Result on `root`, None elsewhere."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        lo, hi = shard_bounds(n, world, rank)
+        seq_off = np.asarray(seq_off, dtype=np.int64)
+        base = int(seq_off[lo])
+        sub_off = seq_off[lo:hi + 1] - base
+        sub_seq = np.frombuffer(seq_buf, dtype=np.uint8)[base:int(seq_off[hi])] if not isinstance(seq_buf, np.ndarray) else \
+            seq_buf[base:int(seq_off[hi])]
+        v, j = self.align_fn(hi - lo, np.ascontiguousarray(sub_seq), np.ascontiguousarray(sub_off), lo)
+        v_all = gather_records(v, n, self.group, self.device)
+        j_all = gather_records(j, n, self.group, self.device)
+        if rank != self.root:
+            return None
+        return self.assemble_fn(n, name_buf, name_off, seq_buf, seq_off, qual_buf, v_all, j_all)
