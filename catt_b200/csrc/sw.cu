@@ -28,7 +28,6 @@ constexpr int SW_THREADS = 128;
 constexpr uint32_t NEG1 = 0xFFFFFFFFu;   // (-1,-1)
 constexpr uint32_t NEG7 = 0xFFF9FFF9u;   // (-7,-7): first gap base = open 6 + extend 1
 constexpr uint32_t MINV = 0x80008000u;   // (-32768,-32768)
-constexpr uint32_t SEL_N = 0xFFFFu;      // row marker: the read base is N
 
 __device__ __forceinline__ uint64_t hash_64(uint64_t key) {   // bwa's tie-break hash
   key += ~(key << 32);
@@ -91,12 +90,15 @@ __global__ void expand_kernel(RefDev ref, int64_t n, const uint32_t* __restrict_
 // ---------------------------------------------------------------------------------------------------------------
 // the DP kernel
 // ---------------------------------------------------------------------------------------------------------------
-template <int C, bool NROW>
+// OVR: a half whose read base is N (or whose read has ended, TRACK pass) scores -1 against everything:
+// s = (table score & keep) | orv
+template <int C, bool OVR>
 __device__ __forceinline__ void sw_row(uint32_t (&Hp)[C], uint32_t (&E)[C], const uint32_t (&tabA)[C], const uint32_t (&tabB)[C],
-                                       uint32_t sel, uint32_t& hd, uint32_t& f, uint32_t& rowbest) {
+                                       uint32_t sel, uint32_t keep, uint32_t& hd, uint32_t& f, uint32_t& rowbest) {
   #pragma unroll
   for (int c = 0; c < C; c++) {
-    const uint32_t s = NROW ? NEG1 : prmt(tabA[c], tabB[c], sel);
+    uint32_t s = prmt(tabA[c], tabB[c], sel);
+    if (OVR) s = (s & keep) | ~keep;
     const uint32_t e = E[c];
     uint32_t h = __viaddmax_s16x2_relu(hd, s, e);        // max(H(i-1,j-1)+s, E(i,j), 0)
     h = __vimax_s16x2_relu(h, f);                            // ... and F(i,j)
@@ -115,60 +117,85 @@ __device__ __forceinline__ uint32_t pack_key(int score, int i, int j) {
 }
 
 // G lanes per task, C columns per lane; record length <= G*C.
-// TRACK = false: scores only (out[t] = scoreA | scoreB << 16) — the bulk pass over every candidate.
-// TRACK = true : also the first cell reaching the maximum in row-major order (out[2t], out[2t+1] = pack_key) — run on
-//                the one winning candidate per read, which is all the SAM record needs.
+// TRACK = false: scores only (out[t] = scoreA | scoreB << 16) - the bulk pass over every candidate; a task is one read
+//                against two of its candidates.
+// TRACK = true : also the first cell reaching the maximum in row-major order - run on the one winning candidate per read,
+//                which is all the SAM record needs.  `tasks` then holds one single-candidate entry per winner and a
+//                task pairs the winners 2t and 2t+1 (two different reads, each driving its own half); out[k] = pack_key
+//                of winner k.
 // The task count is read on the device (*ntasks_dev) so the stage needs no host round trip.
+// Per row the shared array holds the PRMT selector (low 16 bits) and one "scores -1" flag per half (bits 16, 17).
 template <int G, int C, bool TRACK>
 __global__ void __launch_bounds__(SW_THREADS) sw_score_kernel(RefDev ref, ReadsDev reads, const SwTask* __restrict__ tasks,
                                                               const uint32_t* __restrict__ ntasks_dev, int64_t ntasks_cap,
-                                                              uint32_t* __restrict__ out, int tb_bytes_smem) {
+                                                              uint32_t* __restrict__ out, int tb_bytes_smem, int ml) {
   constexpr int GPW = 32 / G;                         // tasks per warp
   constexpr int GPB = GPW * (SW_THREADS / 32);        // tasks per block
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint64_t bar;
-  const int64_t ntasks = (int64_t)*ntasks_dev;
-  if (ntasks > ntasks_cap) return;                    // expand_kernel flagged the overflow; nothing valid to score
+  const int64_t nent = (int64_t)*ntasks_dev;          // entries in `tasks`
+  if (nent > ntasks_cap) return;                      // expand_kernel flagged the overflow; nothing valid to score
+  const int64_t ntasks = TRACK ? (nent + 1) >> 1 : nent;
   if ((int64_t)blockIdx.x * GPB >= ntasks) return;
-  uint16_t* sel_all = reinterpret_cast<uint16_t*>(smem_raw);              // [GPB][MAX_READ]
+  uint32_t* sel_all = reinterpret_cast<uint32_t*>(smem_raw);              // [GPB][ml]
   const uint8_t* Tb = ref.Tb;
   if (tb_bytes_smem > 0) {
-    uint8_t* tbs = smem_raw + (size_t)GPB * MAX_READ * sizeof(uint16_t);
+    uint8_t* tbs = smem_raw + (size_t)GPB * ml * sizeof(uint32_t);
     stage_to_smem(tbs, ref.Tb, (uint32_t)tb_bytes_smem, &bar);
     Tb = tbs;
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane % G, grp = lane / G;
-  uint16_t* sel_arr = sel_all + (size_t)(warp * GPW + grp) * MAX_READ;
+  uint32_t* sel_arr = sel_all + (size_t)(warp * GPW + grp) * ml;
 
   for (int64_t base = ((int64_t)blockIdx.x * (SW_THREADS / 32) + warp) * GPW; base < ntasks;
        base += (int64_t)gridDim.x * GPB) {
     const int64_t t = base + grp;
     const bool live = t < ntasks;
-    int m = 0, strand = 0;
+    int m = 0;
     uint32_t tabA[C], tabB[C], Hp[C], E[C];
     #pragma unroll
     for (int c = 0; c < C; c++) { tabA[c] = 0xFEFEFEFEu; tabB[c] = 0xFEFEFEFEu; Hp[c] = 0; E[c] = 0; }
     if (live) {
-      const SwTask tk = tasks[t];
-      strand = tk.a & 1;
-      m = reads.len[tk.read];
-      const uint32_t* __restrict__ w = reads.words + reads.off[tk.read];
-      const uint32_t* __restrict__ nm = w + read_base_words(m);
-      for (int i = g; i < m; i += G) {
-        const uint32_t q = read_code(w, nm, m, i, strand);
-        sel_arr[i] = (uint16_t)(q > 3 ? SEL_N : 0xC480u + 0x1111u * q);   // bytes: {A[q], sign(A[q]), B[q], sign(B[q])}
+      int ca, cb = 0xFFFF;
+      if (!TRACK) {
+        const SwTask tk = tasks[t];
+        ca = tk.a; cb = tk.b;
+        const int strand = ca & 1;
+        m = reads.len[tk.read];
+        const uint32_t* __restrict__ w = reads.words + reads.off[tk.read];
+        const uint32_t* __restrict__ nm = w + read_base_words(m);
+        for (int i = g; i < m; i += G) {
+          const uint32_t q = read_code(w, nm, m, i, strand);
+          sel_arr[i] = q > 3 ? (0x30000u | 0xC480u) : 0xC480u + 0x1111u * q;   // bytes: {A[q], sign(A[q]), B[q], sign(B[q])}
+        }
+      } else {
+        const SwTask ta = tasks[2 * t];
+        const bool hasb = 2 * t + 1 < nent;
+        const SwTask tb2 = hasb ? tasks[2 * t + 1] : ta;
+        ca = ta.a; cb = hasb ? tb2.a : 0xFFFF;
+        const int ma = reads.len[ta.read], mb = hasb ? reads.len[tb2.read] : 0;
+        m = max(ma, mb);
+        const uint32_t* __restrict__ wa = reads.words + reads.off[ta.read];
+        const uint32_t* __restrict__ na = wa + read_base_words(ma);
+        const uint32_t* __restrict__ wb = reads.words + reads.off[tb2.read];
+        const uint32_t* __restrict__ nb = wb + read_base_words(reads.len[tb2.read]);
+        for (int i = g; i < m; i += G) {
+          const uint32_t qa = i < ma ? read_code(wa, na, ma, i, ca & 1) : 4u;
+          const uint32_t qb = i < mb ? read_code(wb, nb, mb, i, cb & 1) : 4u;
+          sel_arr[i] = (0x80u + 0x11u * (qa & 3u)) | ((0xC4u + 0x11u * (qb & 3u)) << 8) | (qa > 3 ? 0x10000u : 0u) | (qb > 3 ? 0x20000u : 0u);
+        }
       }
       // per-column byte tables: byte q = score of read base q against this column's record base
       {
-        const int ra = tk.a >> 1, oa = ref.rec_off[ra], la = ref.rec_len[ra];
+        const int ra = ca >> 1, oa = ref.rec_off[ra], la = ref.rec_len[ra];
         #pragma unroll
         for (int c = 0; c < C; c++) {
           const int j = g * C + c;
           if (j < la) tabA[c] = 0xFEFEFEFEu ^ (0xFFu << (8 * Tb[oa + j]));      // -2 everywhere, +1 at the matching base
         }
-        if (tk.b != 0xFFFF) {
-          const int rb = tk.b >> 1, ob = ref.rec_off[rb], lb = ref.rec_len[rb];
+        if (cb != 0xFFFF) {
+          const int rb = cb >> 1, ob = ref.rec_off[rb], lb = ref.rec_len[rb];
           #pragma unroll
           for (int c = 0; c < C; c++) {
             const int j = g * C + c;
@@ -190,18 +217,19 @@ __global__ void __launch_bounds__(SW_THREADS) sw_score_kernel(RefDev ref, ReadsD
       if (g == 0) { inH = 0; inF = 0; }
       const int i = st - g;
       if (i >= 0 && i < m) {
-        const uint32_t sel = sel_arr[i];
+        const uint32_t selw = sel_arr[i];
+        const uint32_t sel = selw & 0xffffu, fl = selw >> 16;
         uint32_t hd = diag_in, f = inF;       // F(i, first column) arrives already advanced from the left neighbour
         diag_in = inH;
         if (!TRACK) {
-          if (sel == SEL_N) sw_row<C, true>(Hp, E, tabA, tabB, sel, hd, f, best);
-          else sw_row<C, false>(Hp, E, tabA, tabB, sel, hd, f, best);
+          if (fl) sw_row<C, true>(Hp, E, tabA, tabB, sel, 0u, hd, f, best);
+          else sw_row<C, false>(Hp, E, tabA, tabB, sel, 0u, hd, f, best);
           lastH = Hp[C - 1];
           lastF = f;
         } else {
           uint32_t rowbest = 0;
-          if (sel == SEL_N) sw_row<C, true>(Hp, E, tabA, tabB, sel, hd, f, rowbest);
-          else sw_row<C, false>(Hp, E, tabA, tabB, sel, hd, f, rowbest);
+          if (fl) sw_row<C, true>(Hp, E, tabA, tabB, sel, ((fl & 1u) ? 0u : 0xFFFFu) | ((fl & 2u) ? 0u : 0xFFFF0000u), hd, f, rowbest);
+          else sw_row<C, false>(Hp, E, tabA, tabB, sel, 0u, hd, f, rowbest);
           lastH = Hp[C - 1];
           lastF = f;
           const uint32_t nb = __vimax_s16x2_relu(best, rowbest);
@@ -240,7 +268,7 @@ __global__ void __launch_bounds__(SW_THREADS) sw_score_kernel(RefDev ref, ReadsD
         klo = max(klo, __shfl_xor_sync(FULL, klo, d, G));
         khi = max(khi, __shfl_xor_sync(FULL, khi, d, G));
       }
-      if (live && g == 0) { out[2 * t] = klo; out[2 * t + 1] = khi; }
+      if (live && g == 0) { out[2 * t] = klo; if (2 * t + 1 < nent) out[2 * t + 1] = khi; }
     }
     __syncwarp();
   }
@@ -250,8 +278,9 @@ template <int G, int C, bool TRACK>
 int launch_sw_t(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks, const uint32_t* ntasks_dev, int64_t cap, uint32_t* res,
                 int sm_count, cudaStream_t st) {
   constexpr int GPB = (32 / G) * (SW_THREADS / 32);
+  const int ml = (reads.max_len + 3) & ~3;
   const int tb_bytes = (ref.L + 64) & ~15;
-  const size_t sel_bytes = (size_t)GPB * MAX_READ * sizeof(uint16_t);
+  const size_t sel_bytes = (size_t)GPB * ml * sizeof(uint32_t);
   const int tb_smem = (sel_bytes + tb_bytes <= 100 * 1024) ? tb_bytes : 0;
   const size_t smem = sel_bytes + tb_smem;
   auto k = sw_score_kernel<G, C, TRACK>;
@@ -263,9 +292,10 @@ int launch_sw_t(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks, c
   }
   CATT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, SW_THREADS, smem));
   if (per_sm < 1) per_sm = 1;
-  const int64_t want = (cap + GPB - 1) / GPB;
+  const int64_t ntasks_max = TRACK ? (cap + 1) / 2 : cap;
+  const int64_t want = (ntasks_max + GPB - 1) / GPB;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)sm_count * per_sm, want));
-  k<<<grid, SW_THREADS, smem, st>>>(ref, reads, tasks, ntasks_dev, cap, res, tb_smem);
+  k<<<grid, SW_THREADS, smem, st>>>(ref, reads, tasks, ntasks_dev, cap, res, tb_smem, ml);
   CATT_CUDA(cudaGetLastError());
   return CATT_OK;
 }
@@ -378,7 +408,7 @@ __global__ void finish_kernel(RefDev ref, ReadsDev reads, const SwTask* __restri
   if (k >= (int64_t)counters[7]) return;
   const SwTask tk = wtasks[k];
   const uint32_t r = tk.read;
-  const uint32_t key = wres[2 * k];
+  const uint32_t key = wres[k];
   catt_aln a = recs[r];
   const int mx = a.as, strand = a.strand, m = reads.len[r];
   const int ei = 1023 - (int)((key >> 10) & 1023), ej = 1023 - (int)(key & 1023);
@@ -513,7 +543,7 @@ __global__ void make_pair_tasks(int64_t n, const int32_t* rid, const int32_t* st
 __global__ void unpack_pair_res(int64_t n, const uint32_t* res, int32_t* out3) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    const uint32_t k = res[2 * i];
+    const uint32_t k = res[i];
     out3[3 * i] = (int32_t)(k >> 20);
     out3[3 * i + 1] = 1023 - (int32_t)((k >> 10) & 1023);
     out3[3 * i + 2] = 1023 - (int32_t)(k & 1023);
