@@ -28,6 +28,7 @@ constexpr int SW_THREADS = 128;
 constexpr uint32_t NEG1 = 0xFFFFFFFFu;   // (-1,-1)
 constexpr uint32_t NEG7 = 0xFFF9FFF9u;   // (-7,-7): first gap base = open 6 + extend 1
 constexpr uint32_t MINV = 0x80008000u;   // (-32768,-32768)
+constexpr uint32_t TWO2 = 0x00020002u;   // the +2 bias of every DP quantity
 
 __device__ __forceinline__ uint64_t hash_64(uint64_t key) {   // bwa's tie-break hash
   key += ~(key << 32);
@@ -90,24 +91,33 @@ __global__ void expand_kernel(RefDev ref, int64_t n, const uint32_t* __restrict_
 // ---------------------------------------------------------------------------------------------------------------
 // the DP kernel
 // ---------------------------------------------------------------------------------------------------------------
-// OVR: a half whose read base is N (or whose read has ended, TRACK pass) scores -1 against everything:
-// s = (table score & keep) | orv
-template <int C, bool OVR>
+// One DP row over this lane's C columns, two candidates per register (int16x2).  Everything is kept biased by +2
+// (H2 = H+2, E2 = max(E,0)+2, F2 = max(F,0)+2; flooring E and F at 0 never changes H = max(0, ., E, F)):
+//   * the diagonal add t = H2(i-1,j-1) + s becomes a plain 32-bit add, because the low half H2 + s >= 0 never borrows and
+//     its carry (present exactly when s_A < 0) is pre-compensated in candidate B's byte table - so the add can issue on
+//     the FMA pipe (IMAD) while the ALU pipe, the bottleneck of this kernel, keeps the DPX min/max work;
+//   * H2 = max3(t, E2, F2) needs no separate zero floor.
+// MODE 0: bulk pass, both halves driven by the same read base (the carry compensation in tabB assumes that).
+// MODE 1: TRACK pass (two different reads): plain tables, packed 16x2 add.
+// MODE 2: a half whose read base is N (or whose read has ended) scores -1 against everything (rare rows; in the bulk
+//         pass both halves at once, keep = 0).
+template <int C, int MODE>
 __device__ __forceinline__ void sw_row(uint32_t (&Hp)[C], uint32_t (&E)[C], const uint32_t (&tabA)[C], const uint32_t (&tabB)[C],
                                        uint32_t sel, uint32_t keep, uint32_t& hd, uint32_t& f, uint32_t& rowbest) {
   #pragma unroll
   for (int c = 0; c < C; c++) {
-    uint32_t s = prmt(tabA[c], tabB[c], sel);
-    if (OVR) s = (s & keep) | ~keep;
-    const uint32_t e = E[c];
-    uint32_t h = __viaddmax_s16x2_relu(hd, s, e);        // max(H(i-1,j-1)+s, E(i,j), 0)
-    h = __vimax_s16x2_relu(h, f);                            // ... and F(i,j)
+    const uint32_t s = prmt(tabA[c], tabB[c], sel);
+    uint32_t t;
+    if (MODE == 0) t = hd + s;                               // 32-bit add == packed add here (see above)
+    else if (MODE == 1) t = __vadd2(hd, s);
+    else t = __vadd2(hd, (s & keep) | ~keep);
+    const uint32_t h = __vimax3_s16x2(t, E[c], f);          // H2 = max(H(i-1,j-1)+s, E, F, 0) + 2
     hd = Hp[c];
     Hp[c] = h;
-    const uint32_t hm7 = __viaddmax_s16x2(h, NEG7, MINV);   // H(i,j) - 7
-    E[c] = __viaddmax_s16x2(e, NEG1, hm7);              // E(i+1,j) = max(E(i,j)-1, H(i,j)-7)
+    const uint32_t hm7 = __viaddmax_s16x2(h, NEG7, TWO2);   // max(H-7, 0) + 2
+    E[c] = __viaddmax_s16x2(E[c], NEG1, hm7);           // E(i+1,j)
     f = __viaddmax_s16x2(f, NEG1, hm7);                 // F(i,j+1)
-    if (c & 1) rowbest = __vimax3_s16x2_relu(rowbest, Hp[c - 1], h);
+    if (c & 1) rowbest = __vimax3_s16x2(rowbest, Hp[c - 1], h);
     else if (c == C - 1) rowbest = __vimax_s16x2_relu(rowbest, h);
   }
 }
@@ -155,7 +165,7 @@ __global__ void __launch_bounds__(SW_THREADS) sw_score_kernel(RefDev ref, ReadsD
     int m = 0;
     uint32_t tabA[C], tabB[C], Hp[C], E[C];
     #pragma unroll
-    for (int c = 0; c < C; c++) { tabA[c] = 0xFEFEFEFEu; tabB[c] = 0xFEFEFEFEu; Hp[c] = 0; E[c] = 0; }
+    for (int c = 0; c < C; c++) { tabA[c] = 0xFEFEFEFEu; tabB[c] = TRACK ? 0xFEFEFEFEu : 0xFDFDFDFDu; Hp[c] = TWO2; E[c] = TWO2; }
     if (live) {
       int ca, cb = 0xFFFF;
       if (!TRACK) {
@@ -186,21 +196,20 @@ __global__ void __launch_bounds__(SW_THREADS) sw_score_kernel(RefDev ref, ReadsD
           sel_arr[i] = (0x80u + 0x11u * (qa & 3u)) | ((0xC4u + 0x11u * (qb & 3u)) << 8) | (qa > 3 ? 0x10000u : 0u) | (qb > 3 ? 0x20000u : 0u);
         }
       }
-      // per-column byte tables: byte q = score of read base q against this column's record base
+      // per-column byte tables: byte q of tabA = score of read base q against candidate A's base in this column (+1 / -2);
+      // byte q of tabB = candidate B's score minus 1 where A's score is negative (the carry the 32-bit add will produce)
       {
         const int ra = ca >> 1, oa = ref.rec_off[ra], la = ref.rec_len[ra];
+        int rb = 0, ob = 0, lb = 0;
+        if (cb != 0xFFFF) { rb = cb >> 1; ob = ref.rec_off[rb]; lb = ref.rec_len[rb]; }
         #pragma unroll
         for (int c = 0; c < C; c++) {
           const int j = g * C + c;
-          if (j < la) tabA[c] = 0xFEFEFEFEu ^ (0xFFu << (8 * Tb[oa + j]));      // -2 everywhere, +1 at the matching base
-        }
-        if (cb != 0xFFFF) {
-          const int rb = cb >> 1, ob = ref.rec_off[rb], lb = ref.rec_len[rb];
-          #pragma unroll
-          for (int c = 0; c < C; c++) {
-            const int j = g * C + c;
-            if (j < lb) tabB[c] = 0xFEFEFEFEu ^ (0xFFu << (8 * Tb[ob + j]));
-          }
+          uint32_t amask = 0;                                                    // 0xFF in the byte of A's base
+          if (j < la) { amask = 0xFFu << (8 * Tb[oa + j]); tabA[c] = 0xFEFEFEFEu ^ amask; }
+          uint32_t tb = 0xFEFEFEFEu;
+          if (j < lb) tb ^= 0xFFu << (8 * Tb[ob + j]);
+          tabB[c] = TRACK ? tb : tb - (0x01010101u & ~amask);
         }
       }
     }
@@ -209,12 +218,12 @@ __global__ void __launch_bounds__(SW_THREADS) sw_score_kernel(RefDev ref, ReadsD
     #pragma unroll
     for (int d = 16; d; d >>= 1) steps = max(steps, __shfl_xor_sync(FULL, steps, d));
 
-    uint32_t lastH = 0, lastF = 0, diag_in = 0, best = 0;
+    uint32_t lastH = TWO2, lastF = TWO2, diag_in = TWO2, best = TWO2;
     int bi_lo = 0, bj_lo = 0, bi_hi = 0, bj_hi = 0;
     for (int st = 0; st < steps; st++) {
       uint32_t inH = __shfl_up_sync(FULL, lastH, 1, G);
       uint32_t inF = __shfl_up_sync(FULL, lastF, 1, G);
-      if (g == 0) { inH = 0; inF = 0; }
+      if (g == 0) { inH = TWO2; inF = TWO2; }
       const int i = st - g;
       if (i >= 0 && i < m) {
         const uint32_t selw = sel_arr[i];
@@ -222,14 +231,14 @@ __global__ void __launch_bounds__(SW_THREADS) sw_score_kernel(RefDev ref, ReadsD
         uint32_t hd = diag_in, f = inF;       // F(i, first column) arrives already advanced from the left neighbour
         diag_in = inH;
         if (!TRACK) {
-          if (fl) sw_row<C, true>(Hp, E, tabA, tabB, sel, 0u, hd, f, best);
-          else sw_row<C, false>(Hp, E, tabA, tabB, sel, 0u, hd, f, best);
+          if (fl) sw_row<C, 2>(Hp, E, tabA, tabB, sel, 0u, hd, f, best);
+          else sw_row<C, 0>(Hp, E, tabA, tabB, sel, 0u, hd, f, best);
           lastH = Hp[C - 1];
           lastF = f;
         } else {
-          uint32_t rowbest = 0;
-          if (fl) sw_row<C, true>(Hp, E, tabA, tabB, sel, ((fl & 1u) ? 0u : 0xFFFFu) | ((fl & 2u) ? 0u : 0xFFFF0000u), hd, f, rowbest);
-          else sw_row<C, false>(Hp, E, tabA, tabB, sel, 0u, hd, f, rowbest);
+          uint32_t rowbest = TWO2;
+          if (fl) sw_row<C, 2>(Hp, E, tabA, tabB, sel, ((fl & 1u) ? 0u : 0xFFFFu) | ((fl & 2u) ? 0u : 0xFFFF0000u), hd, f, rowbest);
+          else sw_row<C, 1>(Hp, E, tabA, tabB, sel, 0u, hd, f, rowbest);
           lastH = Hp[C - 1];
           lastF = f;
           const uint32_t nb = __vimax_s16x2_relu(best, rowbest);
@@ -258,11 +267,11 @@ __global__ void __launch_bounds__(SW_THREADS) sw_score_kernel(RefDev ref, ReadsD
     if (!TRACK) {
       #pragma unroll
       for (int d = G / 2; d; d >>= 1) best = __vimax_s16x2_relu(best, __shfl_xor_sync(FULL, best, d, G));
-      if (live && g == 0) out[t] = best;
+      if (live && g == 0) out[t] = best - TWO2;
     } else {
       // reduce over the G lanes of the task: max score, then earliest row, then earliest column
-      uint32_t klo = pack_key((int)(short)(best & 0xffff), bi_lo, bj_lo);
-      uint32_t khi = pack_key((int)(short)(best >> 16), bi_hi, bj_hi);
+      uint32_t klo = pack_key((int)(short)(best & 0xffff) - 2, bi_lo, bj_lo);
+      uint32_t khi = pack_key((int)(short)(best >> 16) - 2, bi_hi, bj_hi);
       #pragma unroll
       for (int d = G / 2; d; d >>= 1) {
         klo = max(klo, __shfl_xor_sync(FULL, klo, d, G));
