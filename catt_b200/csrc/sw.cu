@@ -103,7 +103,7 @@ __global__ void expand_kernel(RefDev ref, int64_t n, const uint32_t* __restrict_
 //         pass both halves at once, keep = 0).
 template <int C, int MODE>
 __device__ __forceinline__ void sw_row(uint32_t (&Hp)[C], uint32_t (&E)[C], const uint32_t (&tabA)[C], const uint32_t (&tabB)[C],
-                                       uint32_t sel, uint32_t keep, uint32_t& hd, uint32_t& f, uint32_t& rowbest) {
+                                       uint32_t sel, uint32_t keep, uint32_t neg7, uint32_t& hd, uint32_t& f, uint32_t& rowbest) {
   #pragma unroll
   for (int c = 0; c < C; c++) {
     const uint32_t s = prmt(tabA[c], tabB[c], sel);
@@ -114,7 +114,7 @@ __device__ __forceinline__ void sw_row(uint32_t (&Hp)[C], uint32_t (&E)[C], cons
     const uint32_t h = __vimax3_s16x2(t, E[c], f);          // H2 = max(H(i-1,j-1)+s, E, F, 0) + 2
     hd = Hp[c];
     Hp[c] = h;
-    const uint32_t hm7 = __viaddmax_s16x2(h, NEG7, TWO2);   // max(H-7, 0) + 2
+    const uint32_t hm7 = __viaddmax_s16x2(h, neg7, TWO2);   // max(H-7, 0) + 2
     E[c] = __viaddmax_s16x2(E[c], NEG1, hm7);           // E(i+1,j)
     f = __viaddmax_s16x2(f, NEG1, hm7);                 // F(i,j+1)
     if (c & 1) rowbest = __vimax3_s16x2(rowbest, Hp[c - 1], h);
@@ -219,6 +219,9 @@ __global__ void __launch_bounds__(SW_THREADS) sw_score_kernel(RefDev ref, ReadsD
     for (int d = 16; d; d >>= 1) steps = max(steps, __shfl_xor_sync(FULL, steps, d));
 
     uint32_t lastH = TWO2, lastF = TWO2, diag_in = TWO2, best = TWO2;
+    uint32_t neg7;                                          // kept in a register: as an immediate ptxas re-materialises it per cell
+    neg7 = NEG7 ^ (uint32_t)((unsigned long long)ntasks_cap >> 62);   // == NEG7; opaque to constant propagation
+    const uint32_t sel_base = smem_u32(sel_arr);            // shared-window address, so the row load is one LDS off a running index
     int bi_lo = 0, bj_lo = 0, bi_hi = 0, bj_hi = 0;
     for (int st = 0; st < steps; st++) {
       uint32_t inH = __shfl_up_sync(FULL, lastH, 1, G);
@@ -226,19 +229,20 @@ __global__ void __launch_bounds__(SW_THREADS) sw_score_kernel(RefDev ref, ReadsD
       if (g == 0) { inH = TWO2; inF = TWO2; }
       const int i = st - g;
       if (i >= 0 && i < m) {
-        const uint32_t selw = sel_arr[i];
+        uint32_t selw;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(selw) : "r"(sel_base + 4u * (uint32_t)i));
         const uint32_t sel = selw & 0xffffu, fl = selw >> 16;
         uint32_t hd = diag_in, f = inF;       // F(i, first column) arrives already advanced from the left neighbour
         diag_in = inH;
         if (!TRACK) {
-          if (fl) sw_row<C, 2>(Hp, E, tabA, tabB, sel, 0u, hd, f, best);
-          else sw_row<C, 0>(Hp, E, tabA, tabB, sel, 0u, hd, f, best);
+          if (fl) sw_row<C, 2>(Hp, E, tabA, tabB, sel, 0u, neg7, hd, f, best);
+          else sw_row<C, 0>(Hp, E, tabA, tabB, sel, 0u, neg7, hd, f, best);
           lastH = Hp[C - 1];
           lastF = f;
         } else {
           uint32_t rowbest = TWO2;
-          if (fl) sw_row<C, 2>(Hp, E, tabA, tabB, sel, ((fl & 1u) ? 0u : 0xFFFFu) | ((fl & 2u) ? 0u : 0xFFFF0000u), hd, f, rowbest);
-          else sw_row<C, 1>(Hp, E, tabA, tabB, sel, 0u, hd, f, rowbest);
+          if (fl) sw_row<C, 2>(Hp, E, tabA, tabB, sel, ((fl & 1u) ? 0u : 0xFFFFu) | ((fl & 2u) ? 0u : 0xFFFF0000u), neg7, hd, f, rowbest);
+          else sw_row<C, 1>(Hp, E, tabA, tabB, sel, 0u, neg7, hd, f, rowbest);
           lastH = Hp[C - 1];
           lastF = f;
           const uint32_t nb = __vimax_s16x2_relu(best, rowbest);
