@@ -15,6 +15,8 @@
 // score of a cell-pair is one PRMT (byte permute with sign replication) from two per-column byte tables; the
 // recurrences use the DPX packed add-max instructions (VIADDMNMX/VIMNMX .S16x2).  No tensor cores: there is no
 // dense contraction in this recurrence.
+#include <stdlib.h>
+
 #include <cub/device/device_scan.cuh>
 
 #include "internal.cuh"
@@ -313,6 +315,150 @@ int launch_sw_t(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks, c
   return CATT_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// the bulk score pass with a shared-memory query profile.
+// Same recurrence, layout and +2 bias as sw_score_kernel<G, C, false>, but the substitution scores of a row come from a
+// per-task profile in shared memory instead of one PRMT per cell: prof[q][column] = (s_B - [s_A < 0]) << 16 | s_A for
+// read base q = 0..3 and q = 4 (N: -1 against everything), laid out so that the G lanes of a task read one contiguous
+// 16-byte word each per LDS.128 (conflict free, also across the skewed rows, whose profile rows are 128-byte multiples
+// apart).  That moves 1 of the 5.5 ALU-pipe instructions per cell pair to the otherwise idle LSU pipe.
+// ---------------------------------------------------------------------------------------------------------------
+template <int G, int C>
+__global__ void __launch_bounds__(SW_THREADS) sw_bulk_kernel(RefDev ref, ReadsDev reads, const SwTask* __restrict__ tasks,
+                                                             const uint32_t* __restrict__ ntasks_dev, int64_t ntasks_cap,
+                                                             uint32_t* __restrict__ out, int ml) {
+  constexpr int GPW = 32 / G;
+  constexpr int GPB = GPW * (SW_THREADS / 32);
+  constexpr int CH = (C + 3) / 4;                       // 16-byte chunks per lane and profile row
+  constexpr int ROWW = G * CH * 4;                      // words per profile row
+  constexpr int PROFW = 5 * ROWW;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int64_t ntasks = (int64_t)*ntasks_dev;
+  if (ntasks > ntasks_cap) return;                      // expand_kernel flagged the overflow; nothing valid to score
+  if ((int64_t)blockIdx.x * GPB >= ntasks) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane % G, grp = lane / G;
+  const int slot = warp * GPW + grp;
+  uint32_t* prof = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)slot * PROFW;
+  uint8_t* qarr = smem_raw + (size_t)GPB * PROFW * 4 + (size_t)slot * ml;
+  const uint32_t prof_base = smem_u32(prof) + (uint32_t)g * 16u;
+  const uint8_t* __restrict__ Tb = ref.Tb;
+  const uint32_t neg7 = NEG7 ^ (uint32_t)((unsigned long long)ntasks_cap >> 62);   // == NEG7, opaque to constant propagation
+
+  for (int64_t base = ((int64_t)blockIdx.x * (SW_THREADS / 32) + warp) * GPW; base < ntasks;
+       base += (int64_t)gridDim.x * GPB) {
+    const int64_t t = base + grp;
+    const bool live = t < ntasks;
+    int m = 0;
+    if (live) {
+      const SwTask tk = tasks[t];
+      const int strand = tk.a & 1;
+      m = reads.len[tk.read];
+      const uint32_t* __restrict__ w = reads.words + reads.off[tk.read];
+      const uint32_t* __restrict__ nm = w + read_base_words(m);
+      for (int i = g; i < m; i += G) qarr[i] = (uint8_t)read_code(w, nm, m, i, strand);
+      const int ra = tk.a >> 1, oa = ref.rec_off[ra], la = ref.rec_len[ra];
+      int ob = 0, lb = 0;
+      if (tk.b != 0xFFFF) { const int rb = tk.b >> 1; ob = ref.rec_off[rb]; lb = ref.rec_len[rb]; }
+      #pragma unroll
+      for (int c = 0; c < C; c++) {
+        const int j = g * C + c;
+        const int ba = j < la ? (int)Tb[oa + j] : 7, bb = j < lb ? (int)Tb[ob + j] : 7;
+        uint32_t* dst = prof + ((c >> 2) * G + g) * 4 + (c & 3);
+        #pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int sa = q == ba ? 1 : -2, sb = (q == bb ? 1 : -2) - (sa < 0);
+          dst[q * ROWW] = ((uint32_t)sb << 16) | ((uint32_t)sa & 0xFFFFu);
+        }
+        dst[4 * ROWW] = 0xFFFEFFFFu;                    // N: (-1, -1) with the carry of the low half taken out of the high half
+      }
+    }
+    __syncwarp();
+    int steps = live ? m + G - 1 : 0;
+    #pragma unroll
+    for (int d = 16; d; d >>= 1) steps = max(steps, __shfl_xor_sync(FULL, steps, d));
+
+    uint32_t Hp[C], E[C];
+    #pragma unroll
+    for (int c = 0; c < C; c++) { Hp[c] = TWO2; E[c] = TWO2; }
+    uint32_t lastH = TWO2, lastF = TWO2, diag_in = TWO2, best = TWO2;
+    const uint32_t q_base = smem_u32(qarr);
+    for (int st = 0; st < steps; st++) {
+      uint32_t inH = __shfl_up_sync(FULL, lastH, 1, G);
+      uint32_t inF = __shfl_up_sync(FULL, lastF, 1, G);
+      if (g == 0) { inH = TWO2; inF = TWO2; }
+      const int i = st - g;
+      if (i >= 0 && i < m) {
+        uint32_t q;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(q) : "r"(q_base + (uint32_t)i));
+        const uint32_t row = prof_base + q * (uint32_t)(ROWW * 4);
+        uint32_t sv[CH * 4];
+        #pragma unroll
+        for (int ch = 0; ch < CH; ch++)
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(sv[4 * ch]), "=r"(sv[4 * ch + 1]), "=r"(sv[4 * ch + 2]), "=r"(sv[4 * ch + 3])
+                       : "r"(row + (uint32_t)(ch * G * 16)));
+        uint32_t hd = diag_in, f = inF;       // F(i, first column) arrives already advanced from the left neighbour
+        diag_in = inH;
+        #pragma unroll
+        for (int c = 0; c < C; c++) {
+          const uint32_t tt = hd + sv[c];                        // packed add as a plain 32-bit add (see sw_row)
+          const uint32_t h = __vimax3_s16x2(tt, E[c], f);
+          hd = Hp[c];
+          Hp[c] = h;
+          const uint32_t hm7 = __viaddmax_s16x2(h, neg7, TWO2);
+          E[c] = __viaddmax_s16x2(E[c], NEG1, hm7);
+          f = __viaddmax_s16x2(f, NEG1, hm7);
+          if (c & 1) best = __vimax3_s16x2(best, Hp[c - 1], h);
+          else if (c == C - 1) best = __vimax_s16x2_relu(best, h);
+        }
+        lastH = Hp[C - 1];
+        lastF = f;
+      }
+    }
+    #pragma unroll
+    for (int d = G / 2; d; d >>= 1) best = __vimax_s16x2_relu(best, __shfl_xor_sync(FULL, best, d, G));
+    if (live && g == 0) out[t] = best - TWO2;
+    __syncwarp();
+  }
+}
+
+template <int G, int C>
+int launch_sw_bulk(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks, const uint32_t* ntasks_dev, int64_t cap, uint32_t* res,
+                   int sm_count, cudaStream_t st) {
+  constexpr int GPB = (32 / G) * (SW_THREADS / 32);
+  constexpr int PROFW = 5 * G * ((C + 3) / 4) * 4;
+  const int ml = (reads.max_len + 15) & ~15;
+  const size_t smem = (size_t)GPB * (PROFW * 4 + ml);
+  auto k = sw_bulk_kernel<G, C>;
+  static bool attr = false;
+  static int per_sm = 0;
+  if (!attr) {
+    CATT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  CATT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, SW_THREADS, smem));
+  if (per_sm < 1) per_sm = 1;
+  const int64_t want = (cap + GPB - 1) / GPB;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)sm_count * per_sm, want));
+  k<<<grid, SW_THREADS, smem, st>>>(ref, reads, tasks, ntasks_dev, cap, res, ml);
+  CATT_CUDA(cudaGetLastError());
+  return CATT_OK;
+}
+
+int dispatch_sw_bulk(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks, const uint32_t* ntasks_dev, int64_t cap, uint32_t* res,
+                     int sm_count, cudaStream_t st) {
+  const int n = ref.maxlen;
+  if (n <= 32) return launch_sw_bulk<4, 8>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
+  if (n <= 48) return launch_sw_bulk<4, 12>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
+  if (n <= 64) return launch_sw_bulk<8, 8>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
+  if (n <= 104) return launch_sw_bulk<8, 13>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
+  if (n <= 160) return launch_sw_bulk<16, 10>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
+  if (n <= 320) return launch_sw_bulk<32, 10>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
+  set_error("record length %d exceeds the SW kernel's tiling", n);
+  return CATT_E_LIMIT;
+}
+
 template <bool TRACK>
 int dispatch_sw(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks, const uint32_t* ntasks_dev, int64_t cap, uint32_t* res,
                 int sm_count, cudaStream_t st) {
@@ -597,7 +743,8 @@ int launch_expand(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, cu
 
 int launch_sw(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int sm_count, cudaStream_t st, int* launches) {
   *launches += 1;
-  return dispatch_sw<false>(ref, reads, ab.tasks, ab.task_off + reads.n, ab.cap_tasks, ab.task_score, sm_count, st);
+  if (getenv("CATT_SW_PRMT")) return dispatch_sw<false>(ref, reads, ab.tasks, ab.task_off + reads.n, ab.cap_tasks, ab.task_score, sm_count, st);
+  return dispatch_sw_bulk(ref, reads, ab.tasks, ab.task_off + reads.n, ab.cap_tasks, ab.task_score, sm_count, st);
 }
 
 // selection, the TRACK pass over the winners, CIGAR facts, traceback of the rare gapped winners
