@@ -8,7 +8,7 @@
 //     for xc descending, xf ascending: 6 <= xf-xc <= 34, not (7 <= xf - nextC <= 35), no '*' in aa[xc:xf] -> code 3,
 //     range (xc-1)*3+1 : xf*3, break the inner loop only (so the leftmost qualifying C wins)
 //   able |= code > 0; the first frame with code 3 sets cdr3.
-// Motifs are compiled on the host into alternatives of per-position residue masks (MotifDev).
+// Motifs are compiled on the host into per-position tables of alternative sets (MotifDev).
 #pragma once
 #include "internal.cuh"
 
@@ -27,14 +27,9 @@ struct FinderScratch {        // per warp, shared memory
 static __device__ __constant__ char FINDER_CODON[65] = "KNKNTTTTRSRSIIMIQHQHPPPPRRRRLLLLEDEDAAAAGGGGVVVV*Y*YSSSS*CWCLFLF";
 
 __device__ __forceinline__ bool motif_at(const MotifDev& m, const uint8_t* aa, int p) {
-  for (int a = 0; a < m.nalt; a++) {
-    bool ok = true;
-    for (int k = 0; k < m.len; k++) {
-      if (!((m.mask[a * MOTIF_MAX_LEN + k] >> aa[p + k]) & 1u)) { ok = false; break; }
-    }
-    if (ok) return true;
-  }
-  return false;
+  unsigned long long live = ~0ull;                       // alternatives still matching
+  for (int k = 0; k < m.len; k++) live &= m.alt[k][aa[p + k]];
+  return live != 0;
 }
 
 // match bitmask over amino-acid positions (bit p = the motif matches at p), written to `words`; returns any-match

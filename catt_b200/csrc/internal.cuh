@@ -88,7 +88,9 @@ struct RefSet {
 // ---------------------------------------------------------------------------------------------------------------
 struct MotifDev {
   int32_t len, nalt;
-  uint32_t mask[MOTIF_MAX_ALT * MOTIF_MAX_LEN];   // mask[alt*MOTIF_MAX_LEN + k]: allowed residues (bit = letter-'A', 26 = '*')
+  // alt[k][r]: the set of alternatives (bit a) that accept residue r (letter-'A', 26 = '*') at position k; the motif
+  // matches at p iff the AND over k of alt[k][aa[p+k]] is non-zero - len table reads instead of nalt x len tests
+  unsigned long long alt[MOTIF_MAX_LEN][28];
 };
 enum { M_C = 0, M_F = 1, M_INNER_C = 2, M_INNER_F = 3, M_HARD_C = 4, M_HARD_F = 5, M_COUNT = 6 };
 struct FinderDev {

@@ -258,7 +258,10 @@ int compile_motif(const char* re, MotifDev* out) {
   if (L0 > MOTIF_MAX_LEN || L0 == 0) { set_error("motif '%s': length %zu unsupported", re, L0); return CATT_E_ARG; }
   if (live.size() > MOTIF_MAX_ALT) { set_error("motif '%s': %zu alternatives exceed %d", re, live.size(), MOTIF_MAX_ALT); return CATT_E_ARG; }
   out->len = (int)L0; out->nalt = (int)live.size();
-  for (size_t i = 0; i < live.size(); i++) for (size_t k = 0; k < L0; k++) out->mask[i * MOTIF_MAX_LEN + k] = live[i][k];
+  for (size_t i = 0; i < live.size(); i++)
+    for (size_t k = 0; k < L0; k++)
+      for (int r = 0; r < 27; r++)
+        if ((live[i][k] >> r) & 1u) out->alt[k][r] |= 1ull << i;
   return CATT_OK;
 }
 
