@@ -452,6 +452,7 @@ int dispatch_sw_bulk(const RefDev& ref, const ReadsDev& reads, const SwTask* tas
   if (n <= 32) return launch_sw_bulk<4, 8>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
   if (n <= 48) return launch_sw_bulk<4, 12>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
   if (n <= 64) return launch_sw_bulk<8, 8>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
+  if (n <= 100 && !getenv("CATT_SW_G8")) return launch_sw_bulk<4, 25>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
   if (n <= 104) return launch_sw_bulk<8, 13>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
   if (n <= 160) return launch_sw_bulk<16, 10>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
   if (n <= 320) return launch_sw_bulk<32, 10>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
