@@ -79,6 +79,16 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows), "how": "NVML in-process, 200 ms period, during both timed regions"}
 
 
+def ncu_traffic():
+    """dram bytes read + written per launch of the dominant kernel, from the committed ncu --set full capture
+    (profiles/traffic.json, written by profiles/summarize_ncu.py); None when no capture is committed."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            return json.load(fh)["sw_bulk_kernel"]
+    except Exception:
+        return None
+
+
 def cpu_reference_run(fx, length, n_sample, first_index=0):
     """The CPU restatement (oracle) on n_sample reads with all host threads; returns (reads/s, seconds, info)."""
     from catt_b200.refg import chain_config
@@ -118,7 +128,7 @@ def main():
         fx = fixture_dir()
         import __graft_entry__ as g
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
-        n = args.cpu_sample or max(2000, 600 * cores)          # ~ a few seconds per step on `cores` threads
+        n = args.cpu_sample or max(8000, 5000 * cores)         # ~5 s per step on `cores` threads
         for i in range(args.warmup):
             cpu_reference_run(fx, args.length, max(1000, n // 8), first_index=i * n)
         t_tot, cells = 0.0, 0
@@ -242,16 +252,18 @@ def main():
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(sum(i["kernel_launches"] for i in infos)),
         "clocks": sampler.summary(),
-        "roofline": {"bound": "alu", "kernel": "sw_score_kernel<8,13> (V) + <4,8> (J)", "achieved": achieved / 1e12, "peak": peak / 1e12,
-                     "unit": "Tiop/s", "frac": achieved / peak, "traffic": None,
-                     "note": "achieved = 12 int ops x DP cells / SW kernel time; peak = measured packed-DPX (VIADDMNMX.S16x2) issue rate x 4 "
+        "roofline": {"bound": "alu", "kernel": "sw_bulk_kernel<4,25> (V) + <4,8> (J)", "achieved": achieved / 1e12, "peak": peak / 1e12,
+                     "unit": "Tiop/s", "frac": achieved / peak, "traffic": ncu_traffic(),
+                     "note": "achieved = 12 int ops x algorithmic DP cells (every scored (read, record, strand) pair, len x len) / SW kernel time; "
+                             "byte-identical records are computed once and the kernel issues 4.5 ALU-pipe instructions per cell pair, so frac can "
+                             "approach or pass 1; peak = measured packed-DPX (VIADDMNMX.S16x2) issue rate x 4 "
                              f"int16 ops per thread-instruction ({peak_ops / 1e12:.2f} T thread-instr/s, this GPU, in-repo microbenchmark); "
                              "MEASURED_PEAKS.json has no integer entry"},
         "counters": {k: info[k] for k in ("v_hits", "j_hits", "vpart", "jpart", "direct", "left", "rescued", "cand_v", "cand_j", "gapped_v")},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
-        n = args.cpu_sample or max(4000, 1500 * cores)
+        n = args.cpu_sample or max(16000, 15000 * cores)       # ~15 s of CPU work on `cores` threads
         rps, dt, cinfo = cpu_reference_run(fx, args.length, n)
         line["cpu_baseline"] = {"value": rps, "unit": "reads/s", "cores": cores, "kind": "port",
                                 "sample": f"first {n} reads of the same generator, {dt:.1f} s; CPU restatement (oracle, OpenMP), not the Julia program",
