@@ -149,8 +149,10 @@ int stage_a_resident(catt_ctx* c, const DeviceReads& dr, int64_t first_ordinal, 
 }
 
 // Host reads -> ctx->rd_* on the device, Stage A pipelined: while the kernels of chunk i run, the host threads pack chunk
-// i+1 into pinned staging and the copy stream moves it to HBM.
-int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool align, DeviceReads* view, catt_info* info, int* launches) {
+// i+1 into pinned staging and the copy stream moves it to HBM.  `fh->start` lists the input files of the sample: chunks never
+// straddle a file and bwa's read ordinal restarts at every file (each file is one `bwa mem` run, catt.jl:143-147).
+int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool align, DeviceReads* view, FileHits* fh, catt_info* info,
+                   int* launches) {
   const int64_t n = hr.n;
   int rc;
   const double t0 = now_ms();
@@ -168,10 +170,16 @@ int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool
   cudaStream_t st = c->stream, cs = c->copy_stream;
   CATT_CUDA(cudaMemcpyAsync(dr.off, h_off, (size_t)(n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   CATT_CUDA(cudaMemcpyAsync(dr.len, h_len, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  const int64_t chunk = c->chunk_reads;
-  const int64_t nchunks = (n + chunk - 1) / chunk;
+  struct Chunk { int64_t i0, cnt, ordinal; int file; };
+  std::vector<Chunk> chunks;
+  const int nfiles = (int)fh->start.size() - 1;
+  fh->v.assign(nfiles, 0); fh->j.assign(nfiles, 0);
+  for (int f = 0; f < nfiles; f++)
+    for (int64_t i0 = fh->start[f]; i0 < fh->start[f + 1]; i0 += c->chunk_reads)
+      chunks.push_back(Chunk{i0, std::min<int64_t>(c->chunk_reads, fh->start[f + 1] - i0), first_ordinal + (i0 - fh->start[f]), f});
+  const int64_t nchunks = (int64_t)chunks.size();
   auto stage_chunk = [&](int64_t ci) -> int {           // pack chunk ci into its staging buffer and start its H2D
-    const int64_t i0 = ci * chunk, i1 = std::min<int64_t>(n, i0 + chunk);
+    const int64_t i0 = chunks[ci].i0, i1 = i0 + chunks[ci].cnt;
     const size_t words = (size_t)(h_off[i1] - h_off[i0]);
     PinBuf& pb = c->pin[PIN_PACK0 + (ci & 1)];
     if (ci >= 2) CATT_CUDA(cudaEventSynchronize(c->ev_h2d[ci & 1]));      // the copy that last read this buffer
@@ -184,20 +192,30 @@ int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool
   };
   if (nchunks > 0 && (rc = stage_chunk(0))) return rc;
   if (info) info->ms_pack += now_ms() - t0;
+  catt_info local{};
   for (int64_t ci = 0; ci < nchunks; ci++) {
-    const int64_t i0 = ci * chunk, cnt = std::min<int64_t>(chunk, n - i0);
-    const ReadsDev rv = dr.view(i0, cnt);
+    const Chunk ch = chunks[ci];
+    const ReadsDev rv = dr.view(ch.i0, ch.cnt);
     CATT_CUDA(cudaStreamWaitEvent(st, c->ev_h2d[ci & 1], 0));
     if (align)
       for (int which = 0; which < 2; which++)
-        if ((rc = align_queue(c, which, rv, c->recs_all[which].as<catt_aln>() + i0, first_ordinal + i0, launches))) return rc;
+        if ((rc = align_queue(c, which, rv, c->recs_all[which].as<catt_aln>() + ch.i0, ch.ordinal, launches))) return rc;
     if (ci + 1 < nchunks && (rc = stage_chunk(ci + 1))) return rc;
     CATT_CUDA(cudaStreamSynchronize(st));
-    if (align)
+    if (align) {
+      const int64_t v0 = local.v_hits, j0 = local.j_hits;
       for (int which = 0; which < 2; which++)
-        if ((rc = align_finish(c, which, rv, c->recs_all[which].as<catt_aln>() + i0, first_ordinal + i0, info, launches))) return rc;
+        if ((rc = align_finish(c, which, rv, c->recs_all[which].as<catt_aln>() + ch.i0, ch.ordinal, &local, launches))) return rc;
+      fh->v[ch.file] += local.v_hits - v0; fh->j[ch.file] += local.j_hits - j0;
+    }
   }
   CATT_CUDA(cudaStreamSynchronize(st));
+  if (info && align) {
+    info->ms_seed += local.ms_seed; info->ms_sw += local.ms_sw; info->ms_select += local.ms_select;
+    info->cand_v += local.cand_v; info->cand_j += local.cand_j; info->cells_v += local.cells_v; info->cells_j += local.cells_j;
+    info->gapped_v += local.gapped_v; info->gapped_j += local.gapped_j; info->v_hits += local.v_hits; info->j_hits += local.j_hits;
+    info->cells_computed_v += local.cells_computed_v; info->cells_computed_j += local.cells_computed_j;
+  }
   return CATT_OK;
 }
 
@@ -215,7 +233,7 @@ int parse_fastx(const std::string& path, HostReads* hr) {
     if (e > b && txt[e - 1] == '\r') e--;
     return true;
   };
-  hr->own_name_off.push_back(0); hr->own_seq_off.push_back(0);
+  if (hr->own_name_off.empty()) { hr->own_name_off.push_back(0); hr->own_seq_off.push_back(0); }   // appends when called per input file
   size_t b, e;
   while (line(b, e)) {
     if (e == b) continue;
@@ -228,6 +246,14 @@ int parse_fastx(const std::string& path, HostReads* hr) {
     size_t sb, se;
     if (!line(sb, se)) { set_error("%s: truncated record", path.c_str()); return CATT_E_IO; }
     hr->own_seqs.append(txt, sb, se - sb);
+    if (tag == '>') {                                    // multi-line FASTA: the sequence runs to the next header (kseq)
+      while (p < N && txt[p] != '>') {
+        size_t cb, ce;
+        if (!line(cb, ce)) break;
+        hr->own_seqs.append(txt, cb, ce - cb);
+        se += ce - cb;
+      }
+    }
     hr->own_seq_off.push_back((int64_t)hr->own_seqs.size());
     if (tag == '@') {
       size_t pb, pe, qb, qe;
@@ -254,16 +280,18 @@ int download_records(catt_ctx* c, int64_t n, catt_result* R) {
   return CATT_OK;
 }
 
-int run_all(catt_ctx* c, const HostReads& hr, catt_result** out) {
+int run_all(catt_ctx* c, const HostReads& hr, const std::vector<int64_t>& file_start, catt_result** out) {
   std::unique_ptr<catt_result> R(new catt_result());
   int launches = 0;
   Trace tr;
   R->info.n_reads = hr.n;
   DeviceReads dr;
-  int rc = stage_a_stream(c, hr, 0, true, &dr, &R->info, &launches);
+  FileHits fh;
+  fh.start = file_start;
+  int rc = stage_a_stream(c, hr, 0, true, &dr, &fh, &R->info, &launches);
   tr.lap("run_all: pack + H2D + align (pipelined)");
   if (rc == CATT_OK && c->keep_records) rc = download_records(c, hr.n, R.get());
-  if (rc == CATT_OK) rc = stage_b(c, hr, dr.view(), R.get(), &launches);
+  if (rc == CATT_OK) rc = stage_b(c, hr, dr.view(), fh, R.get(), &launches);
   tr.lap("run_all: stage_b");
   if (rc) return rc;
   R->info.kernel_launches = launches;
@@ -385,16 +413,41 @@ int catt_run_reads(catt_ctx* c, int64_t n, const char* names, const int64_t* nam
   CATT_CUDA(cudaSetDevice(c->device));
   HostReads hr;
   hr.n = n; hr.names = names; hr.name_off = name_off; hr.seqs = seqs; hr.seq_off = seq_off; hr.quals = quals;
-  return run_all(c, hr, out);
+  return run_all(c, hr, {0, n}, out);
+}
+
+int catt_run_reads_files(catt_ctx* c, int64_t n, const char* names, const int64_t* name_off, const char* seqs, const int64_t* seq_off,
+                         const char* quals, int32_t nfiles, const int64_t* file_start, catt_result** out) {
+  if (!c || !out || n < 0 || nfiles < 1 || !file_start || (n > 0 && (!names || !name_off || !seqs || !seq_off))) {
+    set_error("catt_run_reads_files: bad argument");
+    return CATT_E_ARG;
+  }
+  std::vector<int64_t> fs(file_start, file_start + nfiles + 1);
+  if (fs.front() != 0 || fs.back() != n || !std::is_sorted(fs.begin(), fs.end())) { set_error("catt_run_reads_files: file_start must run from 0 to n"); return CATT_E_ARG; }
+  CATT_CUDA(cudaSetDevice(c->device));
+  HostReads hr;
+  hr.n = n; hr.names = names; hr.name_off = name_off; hr.seqs = seqs; hr.seq_off = seq_off; hr.quals = quals;
+  return run_all(c, hr, fs, out);
 }
 
 int catt_run_file(catt_ctx* c, const char* path, catt_result** out) {
   if (!c || !path || !out) { set_error("catt_run_file: null argument"); return CATT_E_ARG; }
+  const char* paths[1] = {path};
+  return catt_run_files(c, 1, paths, out);
+}
+
+int catt_run_files(catt_ctx* c, int32_t nfiles, const char* const* paths, catt_result** out) {
+  if (!c || !paths || !out || nfiles < 1) { set_error("catt_run_files: bad argument"); return CATT_E_ARG; }
   CATT_CUDA(cudaSetDevice(c->device));
   HostReads hr;
-  int rc = parse_fastx(path, &hr);
-  if (rc) return rc;
-  return run_all(c, hr, out);
+  std::vector<int64_t> fs{0};
+  for (int f = 0; f < nfiles; f++) {
+    if (!paths[f]) { set_error("catt_run_files: null path"); return CATT_E_ARG; }
+    int rc = parse_fastx(paths[f], &hr);
+    if (rc) return rc;
+    fs.push_back(hr.n);
+  }
+  return run_all(c, hr, fs, out);
 }
 
 int catt_result_info(const catt_result* r, catt_info* out) { if (!r || !out) return CATT_E_ARG; *out = r->info; return CATT_OK; }
@@ -484,7 +537,9 @@ int catt_align_shard(catt_ctx* c, int64_t n, const char* seqs, const int64_t* se
   DeviceReads dr;
   catt_info info{};
   int launches = 0;
-  int rc = stage_a_stream(c, hr, first_ordinal, true, &dr, &info, &launches);
+  FileHits fh;
+  fh.start = {0, n};
+  int rc = stage_a_stream(c, hr, first_ordinal, true, &dr, &fh, &info, &launches);
   if (rc || n == 0) return rc;
   if (v_out) CATT_CUDA(cudaMemcpy(v_out, c->recs_all[0].p, n * sizeof(catt_aln), cudaMemcpyDeviceToHost));
   if (j_out) CATT_CUDA(cudaMemcpy(j_out, c->recs_all[1].p, n * sizeof(catt_aln), cudaMemcpyDeviceToHost));
@@ -505,7 +560,10 @@ int catt_assemble(catt_ctx* c, int64_t n, const char* names, const int64_t* name
   R->info.v_hits = vh; R->info.j_hits = jh;
   DeviceReads dr;
   int launches = 0;
-  int rc = stage_a_stream(c, hr, 0, false, &dr, &R->info, &launches);      // pack + upload only
+  FileHits fh;
+  fh.start = {0, n};
+  int rc = stage_a_stream(c, hr, 0, false, &dr, &fh, &R->info, &launches);      // pack + upload only
+  fh.single(n, vh, jh);
   if (rc) return rc;
   if (n) {
     CATT_CUDA(cudaMemcpyAsync(c->recs_all[0].p, v_recs, n * sizeof(catt_aln), cudaMemcpyHostToDevice, c->stream));
@@ -513,7 +571,7 @@ int catt_assemble(catt_ctx* c, int64_t n, const char* names, const int64_t* name
     CATT_CUDA(cudaStreamSynchronize(c->stream));
   }
   if (c->keep_records) { R->rec[0].assign(v_recs, v_recs + n); R->rec[1].assign(j_recs, j_recs + n); }
-  rc = stage_b(c, hr, dr.view(), R.get(), &launches);
+  rc = stage_b(c, hr, dr.view(), fh, R.get(), &launches);
   if (rc) return rc;
   R->info.kernel_launches = launches;
   *out = R.release();
@@ -535,7 +593,9 @@ int catt_batch_assemble(catt_ctx* c, catt_batch* b, const char* names, const int
   if (c->keep_records) rc = download_records(c, n, R.get());
   if (rc) return rc;
   int launches = (int)b->info.kernel_launches;
-  rc = stage_b(c, hr, b->dr.view(), R.get(), &launches);
+  FileHits fh;
+  fh.single(n, b->info.v_hits, b->info.j_hits);
+  rc = stage_b(c, hr, b->dr.view(), fh, R.get(), &launches);
   if (rc) return rc;
   R->info.kernel_launches = launches;
   *out = R.release();

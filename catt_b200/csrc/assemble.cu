@@ -176,53 +176,58 @@ __device__ __forceinline__ ExtractItem make_item(const catt_aln& a, uint32_t rea
 }
 
 __global__ void part_item_kernel(int64_t F, const uint32_t* __restrict__ ord_idx, const uint32_t* __restrict__ ord_flag,
-                                 const uint32_t* __restrict__ opos, const catt_aln* __restrict__ recs, int kind,
+                                 const uint32_t* __restrict__ opos, const catt_aln* __restrict__ recs, int kind, uint32_t lo,
                                  ExtractItem* __restrict__ items) {
   const int64_t y = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (y >= F || !ord_flag[y]) return;
   const uint32_t idx = ord_idx[y];
-  items[opos[y]] = make_item(recs[idx], idx, kind);
+  items[opos[y]] = make_item(recs[idx], lo + idx, kind);
 }
 
 __global__ void pair_item_kernel(int64_t np, const uint32_t* __restrict__ pair_j, const uint32_t* __restrict__ slot_of,
                                  const uint32_t* __restrict__ minv, const unsigned long long* __restrict__ sorted_v,
-                                 const catt_aln* __restrict__ rv, const catt_aln* __restrict__ rj, ExtractItem* __restrict__ items) {
+                                 const catt_aln* __restrict__ rv, const catt_aln* __restrict__ rj, uint32_t lo,
+                                 ExtractItem* __restrict__ items) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= np) return;
   const uint32_t ji = pair_j[p];
   const uint32_t vi = (uint32_t)sorted_v[minv[slot_of[ji]]];
-  ExtractItem it = make_item(rv[vi], vi, 2);
+  ExtractItem it = make_item(rv[vi], lo + vi, 2);
   const catt_aln b = rj[ji];
-  it.read2 = ji; it.j_m_end = b.m_end; it.j_rid = (int16_t)b.rid; it.j_strand = b.strand;
+  it.read2 = lo + ji; it.j_m_end = b.m_end; it.j_rid = (int16_t)b.rid; it.j_strand = b.strand;
   items[p] = it;
 }
 
-__global__ void keep_kernel(int64_t n_items, const ExtractOut* __restrict__ eout, uint32_t* __restrict__ kflag, uint32_t* __restrict__ pflag,
+// kept items by list: kind 0 / 2 -> Vpart (flag0), kind 1 -> Jpart (flag1)
+__global__ void keep_kernel(int64_t n_items, const ExtractItem* __restrict__ items, const ExtractOut* __restrict__ eout,
+                            uint32_t* __restrict__ kflag0, uint32_t* __restrict__ kflag1, uint32_t* __restrict__ pflag,
                             unsigned long long* __restrict__ cnt) {
   const int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (it > n_items) return;
   pflag[it] = 0;
-  if (it == n_items) { kflag[it] = 0; return; }
-  const int st = eout[it].status;
-  kflag[it] = st == 1;
+  if (it == n_items) { kflag0[it] = 0; kflag1[it] = 0; return; }
+  const int st = eout[it].status, kind = items[it].kind;
+  kflag0[it] = st == 1 && kind != 1;
+  kflag1[it] = st == 1 && kind == 1;
   if (st == 2) atomicAdd(&cnt[C_MISMATCH], 1ull);
+  if (st == 1 && kind == 2) atomicAdd(&cnt[C_FULL], 1ull);
 }
 
 // kept items -> PoolItem / OutDesc at their rank m (= position in [Vpart; Jpart])
-__global__ void pitem_kernel(int64_t n_items, int64_t n_v, int64_t n_p, const ExtractItem* __restrict__ items,
-                             const ExtractOut* __restrict__ eout, const uint32_t* __restrict__ kflag, const uint32_t* __restrict__ kpos2,
-                             const int32_t* __restrict__ jlen, PoolItem* __restrict__ pitems, OutDesc* __restrict__ desc,
-                             uint32_t* __restrict__ pflag, unsigned long long* __restrict__ cnt) {
+__global__ void pitem_kernel(int64_t n_items, const ExtractItem* __restrict__ items, const ExtractOut* __restrict__ eout,
+                             const uint32_t* __restrict__ kflag0, const uint32_t* __restrict__ kflag1, const uint32_t* __restrict__ kpos0,
+                             const uint32_t* __restrict__ kpos1, const int32_t* __restrict__ jlen, PoolItem* __restrict__ pitems,
+                             OutDesc* __restrict__ desc, uint32_t* __restrict__ pflag, unsigned long long* __restrict__ cnt) {
   const int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (it == 0) {
-    cnt[C_M] = kpos2[n_items]; cnt[C_VPART] = kpos2[n_v + n_p]; cnt[C_FULL] = kpos2[n_v + n_p] - kpos2[n_v];
-  }
-  if (it >= n_items || !kflag[it]) return;
-  const uint32_t m = kpos2[it];
+  const uint32_t vpart = kpos0[n_items];
+  if (it == 0) { cnt[C_VPART] = vpart; cnt[C_M] = vpart + kpos1[n_items]; }
+  if (it >= n_items || !(kflag0[it] | kflag1[it])) return;
   const ExtractItem x = items[it];
   const ExtractOut e = eout[it];
+  const int side = x.kind == 1;
+  const uint32_t m = side ? vpart + kpos1[it] : kpos0[it];
   PoolItem pi;
-  pi.read = x.read; pi.strand = x.strand; pi.seq_off = e.seq_off; pi.seq_len = e.seq_len; pi.side = (int16_t)(it >= n_v + n_p);
+  pi.read = x.read; pi.strand = x.strand; pi.seq_off = e.seq_off; pi.seq_len = e.seq_len; pi.side = (int16_t)side;
   pi.order = m; pi.partial = e.cdr3_off < 0;
   pitems[m] = pi;
   pflag[m] = pi.partial;
@@ -324,174 +329,196 @@ const StrLut SLUT;
 
 }  // namespace
 
-int stage_b(catt_ctx* c, const HostReads& hr, const ReadsDev& reads, catt_result* R, int* launches) {
+int stage_b(catt_ctx* c, const HostReads& hr, const ReadsDev& reads, const FileHits& fh, catt_result* R, int* launches) {
   catt_info& info = R->info;
   const int64_t n = hr.n;
   info.kmer = c->kmer;
   if (n == 0) return CATT_OK;
   cudaStream_t st = c->stream;
   Trace tr;
-  const catt_aln* rec[2] = {c->recs_all[0].as<catt_aln>(), c->recs_all[1].as<catt_aln>()};
-  const int64_t nm[2] = {info.v_hits, info.j_hits};
   int rc;
   unsigned long long* cnt; unsigned long long* hcnt;
   if ((rc = ensure(c, SB_CNT, C_COUNT, &cnt))) return rc;
   hcnt = c->pin[PIN_CNT].as<unsigned long long>() + 2 * N_COUNTERS;      // the first 2*N_COUNTERS entries belong to Stage A
-  CATT_CUDA(cudaMemsetAsync(cnt, 0, C_COUNT * sizeof(unsigned long long), st));
-  CATT_CUDA(cudaEventRecord(c->ev[5], st));
-
-  // ---- QNAMEs to the device, name classes
+  const int nfiles = (int)fh.start.size() - 1;
+  int64_t tot_hits = 0, max_v = 0, max_j = 0, max_reads = 0;
+  for (int f = 0; f < nfiles; f++) {
+    tot_hits += fh.v[f] + fh.j[f];
+    max_v = std::max(max_v, fh.v[f]); max_j = std::max(max_j, fh.j[f]); max_reads = std::max(max_reads, fh.start[f + 1] - fh.start[f]);
+  }
+  // ---- QNAMEs to the device (once); work items of all files accumulate in `items` (n_items <= mapped records)
   const int64_t name_bytes = hr.name_off[n];
   char* d_names; int64_t* d_name_off; uint32_t* slot_of; int32_t* owner; uint32_t* minr[2];
   uint64_t cap = 1024;
-  while (cap < (uint64_t)(nm[0] + nm[1]) * 2 + 2) cap <<= 1;
+  while (cap < (uint64_t)(max_v + max_j) * 2 + 2) cap <<= 1;
   if (cap > 0x80000000ull) { set_error("too many mapped reads for the QNAME table"); return CATT_E_LIMIT; }
   if ((rc = ensure(c, SB_NAMES, name_bytes + 16, &d_names)) || (rc = ensure(c, SB_NAME_OFF, n + 1, &d_name_off)) ||
-      (rc = ensure(c, SB_SLOT_OF, n, &slot_of)) || (rc = ensure(c, SB_OWNER, (int64_t)cap, &owner)) ||
+      (rc = ensure(c, SB_SLOT_OF, max_reads, &slot_of)) || (rc = ensure(c, SB_OWNER, (int64_t)cap, &owner)) ||
       (rc = ensure(c, SB_MINV, (int64_t)cap, &minr[0])) || (rc = ensure(c, SB_MINJ, (int64_t)cap, &minr[1]))) return rc;
-  NamesDev nd{d_names, d_name_off};
-  if (nm[0] + nm[1] > 0) {
+  if (tot_hits > 0) {
     CATT_CUDA(cudaMemcpyAsync(d_names, hr.names, (size_t)name_bytes, cudaMemcpyHostToDevice, st));
     CATT_CUDA(cudaMemcpyAsync(d_name_off, hr.name_off, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-    CATT_CUDA(cudaMemsetAsync(owner, 0xff, cap * sizeof(int32_t), st));
-    CATT_CUDA(cudaMemsetAsync(minr[0], 0xff, cap * sizeof(uint32_t), st));
-    CATT_CUDA(cudaMemsetAsync(minr[1], 0xff, cap * sizeof(uint32_t), st));
-    name_kernel<<<nblk(n), 256, 0, st>>>(n, nd, rec[0], rec[1], owner, (uint32_t)(cap - 1), slot_of);
-    CATT_CUDA(cudaGetLastError());
-    *launches += 1;
   }
-
-  // ---- per reference set: sorted final SAM order, QNAME dedup
   unsigned long long *keys_a, *sorted[2];
   uint32_t *flag, *kpos[2], *ord_idx[2], *ord_flag[2], *opos[2], *pair_a, *pair_b;
-  const int64_t nmax = std::max(nm[0], nm[1]);
-  if ((rc = ensure(c, SB_KEYS_A, nmax, &keys_a)) || (rc = ensure(c, SB_SORT_V, nm[0], &sorted[0])) ||
-      (rc = ensure(c, SB_SORT_J, nm[1], &sorted[1])) || (rc = ensure(c, SB_FLAG, nmax + 1, &flag)) || (rc = ensure(c, SB_KPOS_V, nm[0] + 1, &kpos[0])) ||
-      (rc = ensure(c, SB_KPOS_J, nm[1] + 1, &kpos[1])) || (rc = ensure(c, SB_ORD_IDX_V, nm[0] + 1, &ord_idx[0])) ||
-      (rc = ensure(c, SB_ORD_IDX_J, nm[1] + 1, &ord_idx[1])) || (rc = ensure(c, SB_ORD_FLAG_V, nm[0] + 1, &ord_flag[0])) ||
-      (rc = ensure(c, SB_ORD_FLAG_J, nm[1] + 1, &ord_flag[1])) ||
-      (rc = ensure(c, SB_OPOS_V, nm[0] + 1, &opos[0])) || (rc = ensure(c, SB_OPOS_J, nm[1] + 1, &opos[1])) ||
-      (rc = ensure(c, SB_PAIR_A, nm[1] + 1, &pair_a)) || (rc = ensure(c, SB_PAIR_B, nm[1] + 1, &pair_b))) return rc;
-  for (int which = 0; which < 2; which++) {
-    if (nm[which] == 0) continue;
-    key_kernel<<<nblk(n), 256, 0, st>>>(n, rec[which], keys_a, cnt + C_NMAP_V + which);
-    CATT_CUDA(cudaGetLastError());
-    size_t need = 0;
-    CATT_CUDA(cub::DeviceRadixSort::SortKeysDescending(nullptr, need, keys_a, sorted[which], nm[which], 0, 61, st));
-    if ((rc = ensure_cub(c, need))) return rc;
-    need = c->sb[SB_CUB].cap;
-    CATT_CUDA(cub::DeviceRadixSort::SortKeysDescending(c->sb[SB_CUB].p, need, keys_a, sorted[which], nm[which], 0, 61, st));
-    minrank_kernel<<<nblk(nm[which]), 256, 0, st>>>(nm[which], sorted[which], slot_of, minr[which]);
-    CATT_CUDA(cudaGetLastError());
-    *launches += 10;     // key, radix sort (histogram + 7 onesweep passes), minrank
-  }
-  for (int which = 0; which < 2; which++) {
-    if (nm[which] == 0) continue;
-    flag_kernel<<<nblk(nm[which] + 1), 256, 0, st>>>(nm[which], sorted[which], slot_of, minr[which], rec[which], reads.len, which == 0, flag, cnt);
-    CATT_CUDA(cudaGetLastError());
-    if ((rc = scan_u32(c, flag, kpos[which], nm[which] + 1, st))) return rc;
-    CATT_CUDA(cudaMemsetAsync(ord_flag[which], 0, (size_t)(nm[which] + 1) * sizeof(uint32_t), st));
-    order_kernel<<<nblk(nm[which]), 256, 0, st>>>(nm[which], sorted[which], flag, kpos[which], c->nthreads, slot_of, minr[0], minr[1], which, nd,
-                                                  ord_idx[which], ord_flag[which], pair_a, cnt);
-    CATT_CUDA(cudaGetLastError());
-    if ((rc = scan_u32(c, ord_flag[which], opos[which], nm[which] + 1, st))) return rc;
-    *launches += 6;
-  }
-  collect_kernel<<<1, 1, 0, st>>>(kpos[0], nm[0], kpos[1], nm[1], opos[0], opos[1], cnt);
-  CATT_CUDA(cudaGetLastError());
-  *launches += 1;
-  CATT_CUDA(cudaMemcpyAsync(hcnt, cnt, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-  CATT_CUDA(cudaStreamSynchronize(st));
-  tr.lap("B: names + order + dedup");
-  if ((int64_t)hcnt[C_NMAP_V] != nm[0] || (int64_t)hcnt[C_NMAP_J] != nm[1]) {
-    set_error("stage B: mapped-record count mismatch (V %llu vs %lld, J %llu vs %lld)", hcnt[C_NMAP_V], (long long)nm[0], hcnt[C_NMAP_J], (long long)nm[1]);
-    return CATT_E_ARG;
-  }
-  const int64_t F[2] = {(int64_t)hcnt[C_F_V], (int64_t)hcnt[C_F_J]};
-  const int64_t n_v = (int64_t)hcnt[C_NV], n_j = (int64_t)hcnt[C_NJ], n_p = (int64_t)hcnt[C_NP];
-  info.v_final = F[0]; info.j_final = F[1]; info.share = n_p;
-  // get_kmer_fromsam / get_err_fromsam on the final V list, as samtools stats prints them
+  const int64_t nmax = std::max(max_v, max_j);
+  if ((rc = ensure(c, SB_KEYS_A, nmax, &keys_a)) || (rc = ensure(c, SB_SORT_V, max_v, &sorted[0])) ||
+      (rc = ensure(c, SB_SORT_J, max_j, &sorted[1])) || (rc = ensure(c, SB_FLAG, nmax + 1, &flag)) || (rc = ensure(c, SB_KPOS_V, max_v + 1, &kpos[0])) ||
+      (rc = ensure(c, SB_KPOS_J, max_j + 1, &kpos[1])) || (rc = ensure(c, SB_ORD_IDX_V, max_v + 1, &ord_idx[0])) ||
+      (rc = ensure(c, SB_ORD_IDX_J, max_j + 1, &ord_idx[1])) || (rc = ensure(c, SB_ORD_FLAG_V, max_v + 1, &ord_flag[0])) ||
+      (rc = ensure(c, SB_ORD_FLAG_J, max_j + 1, &ord_flag[1])) ||
+      (rc = ensure(c, SB_OPOS_V, max_v + 1, &opos[0])) || (rc = ensure(c, SB_OPOS_J, max_j + 1, &opos[1])) ||
+      (rc = ensure(c, SB_PAIR_A, max_j + 1, &pair_a)) || (rc = ensure(c, SB_PAIR_B, max_j + 1, &pair_b))) return rc;
+  ExtractItem* items; ExtractOut* eout; uint32_t *kflag0, *kflag1, *kpos0, *kpos1, *pflag, *xpos;
+  if ((rc = ensure(c, SB_ITEMS, tot_hits, &items)) || (rc = ensure(c, SB_EOUT, tot_hits, &eout)) || (rc = ensure(c, SB_KFLAG, tot_hits + 1, &kflag0)) ||
+      (rc = ensure(c, SB_KFLAG1, tot_hits + 1, &kflag1)) || (rc = ensure(c, SB_KPOS2, tot_hits + 1, &kpos0)) || (rc = ensure(c, SB_KPOS3, tot_hits + 1, &kpos1)) ||
+      (rc = ensure(c, SB_PFLAG, tot_hits + 1, &pflag)) || (rc = ensure(c, SB_XPOS, tot_hits + 1, &xpos))) return rc;
+  int64_t n_items = 0;
   int k = c->kmer;
-  {
-    const uint64_t tot = hcnt[C_SUM_LEN], snm = hcnt[C_SUM_NM], smi = hcnt[C_SUM_MI];
-    const float avg = F[0] == 0 ? 0.f : (float)(tot / (uint64_t)F[0]);       // samtools: integer division, printed %.0f
-    char buf[64];
-    snprintf(buf, sizeof buf, "%.0f", avg);
-    const double avg_r = atof(buf);
-    info.avg_len = avg_r;
-    if (k == CATT_KMER_AUTO) {
-      if (avg_r >= 50) k = 15;
-      if (avg_r >= 75) k = 19;
-      if (avg_r >= 100) k = 23;
-      if (avg_r >= 150) k = 25;
-    }
-    const float er = smi ? (float)snm / (float)smi : 0.f;
-    snprintf(buf, sizeof buf, "%e", (double)er);
-    info.the_err = atof(buf);
-    if (!(info.the_err == info.the_err)) info.the_err = 0.0;
-  }
-  info.kmer = k;
+  float ms_order = 0, ms_extract = 0;
 
-  // ---- both-mapped pairs in QNAME order: LSD radix over 8-byte digits of the trimmed name
-  uint32_t* pairs = pair_a;
-  if (n_p > 1) {
-    unsigned long long *pk_a, *pk_b;
-    if ((rc = ensure(c, SB_PKEY_A, n_p, &pk_a)) || (rc = ensure(c, SB_PKEY_B, n_p, &pk_b))) return rc;
-    const int digits = std::max(1, (int)((hcnt[C_MAXNAME] + 7) / 8));
-    uint32_t* other = pair_b;
-    for (int d = digits - 1; d >= 0; d--) {
-      pair_key_kernel<<<nblk(n_p), 256, 0, st>>>(n_p, pairs, nd, d, pk_a);
+  // ---- read_alignrs, once per input file (catt.jl:210-326): the SAM order, the QNAME dedup, share_name and the both-mapped
+  //      pairing are per file; args["kmer"] is fixed by the first file that reaches a mean length of 50, the_ERR by the last
+  for (int f = 0; f < nfiles; f++) {
+    const int64_t lo = fh.start[f], nf = fh.start[f + 1] - lo;
+    const int64_t nm[2] = {fh.v[f], fh.j[f]};
+    const catt_aln* rec[2] = {c->recs_all[0].as<catt_aln>() + lo, c->recs_all[1].as<catt_aln>() + lo};
+    NamesDev nd{d_names, d_name_off + lo};
+    CATT_CUDA(cudaMemsetAsync(cnt, 0, C_COUNT * sizeof(unsigned long long), st));
+    CATT_CUDA(cudaEventRecord(c->ev[5], st));
+    if (nm[0] + nm[1] > 0) {
+      CATT_CUDA(cudaMemsetAsync(owner, 0xff, cap * sizeof(int32_t), st));
+      CATT_CUDA(cudaMemsetAsync(minr[0], 0xff, cap * sizeof(uint32_t), st));
+      CATT_CUDA(cudaMemsetAsync(minr[1], 0xff, cap * sizeof(uint32_t), st));
+      name_kernel<<<nblk(nf), 256, 0, st>>>(nf, nd, rec[0], rec[1], owner, (uint32_t)(cap - 1), slot_of);
+      CATT_CUDA(cudaGetLastError());
+      *launches += 1;
+    }
+    // per reference set: sorted final SAM order, QNAME dedup
+    for (int which = 0; which < 2; which++) {
+      if (nm[which] == 0) continue;
+      key_kernel<<<nblk(nf), 256, 0, st>>>(nf, rec[which], keys_a, cnt + C_NMAP_V + which);
       CATT_CUDA(cudaGetLastError());
       size_t need = 0;
-      CATT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, pk_a, pk_b, pairs, other, n_p, 0, 64, st));
+      CATT_CUDA(cub::DeviceRadixSort::SortKeysDescending(nullptr, need, keys_a, sorted[which], nm[which], 0, 61, st));
       if ((rc = ensure_cub(c, need))) return rc;
       need = c->sb[SB_CUB].cap;
-      CATT_CUDA(cub::DeviceRadixSort::SortPairs(c->sb[SB_CUB].p, need, pk_a, pk_b, pairs, other, n_p, 0, 64, st));
-      std::swap(pairs, other);
-      *launches += 10;
+      CATT_CUDA(cub::DeviceRadixSort::SortKeysDescending(c->sb[SB_CUB].p, need, keys_a, sorted[which], nm[which], 0, 61, st));
+      minrank_kernel<<<nblk(nm[which]), 256, 0, st>>>(nm[which], sorted[which], slot_of, minr[which]);
+      CATT_CUDA(cudaGetLastError());
+      *launches += 10;     // key, radix sort (histogram + 7 onesweep passes), minrank
     }
+    for (int which = 0; which < 2; which++) {
+      if (nm[which] == 0) continue;
+      flag_kernel<<<nblk(nm[which] + 1), 256, 0, st>>>(nm[which], sorted[which], slot_of, minr[which], rec[which], reads.len + lo, which == 0, flag, cnt);
+      CATT_CUDA(cudaGetLastError());
+      if ((rc = scan_u32(c, flag, kpos[which], nm[which] + 1, st))) return rc;
+      CATT_CUDA(cudaMemsetAsync(ord_flag[which], 0, (size_t)(nm[which] + 1) * sizeof(uint32_t), st));
+      order_kernel<<<nblk(nm[which]), 256, 0, st>>>(nm[which], sorted[which], flag, kpos[which], c->nthreads, slot_of, minr[0], minr[1], which, nd,
+                                                    ord_idx[which], ord_flag[which], pair_a, cnt);
+      CATT_CUDA(cudaGetLastError());
+      if ((rc = scan_u32(c, ord_flag[which], opos[which], nm[which] + 1, st))) return rc;
+      *launches += 6;
+    }
+    collect_kernel<<<1, 1, 0, st>>>(kpos[0], nm[0], kpos[1], nm[1], opos[0], opos[1], cnt);
+    CATT_CUDA(cudaGetLastError());
+    *launches += 1;
+    CATT_CUDA(cudaMemcpyAsync(hcnt, cnt, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CATT_CUDA(cudaStreamSynchronize(st));
+    if ((int64_t)hcnt[C_NMAP_V] != nm[0] || (int64_t)hcnt[C_NMAP_J] != nm[1]) {
+      set_error("stage B: mapped-record count mismatch (V %llu vs %lld, J %llu vs %lld)", hcnt[C_NMAP_V], (long long)nm[0], hcnt[C_NMAP_J], (long long)nm[1]);
+      return CATT_E_ARG;
+    }
+    const int64_t F[2] = {(int64_t)hcnt[C_F_V], (int64_t)hcnt[C_F_J]};
+    const int64_t n_v = (int64_t)hcnt[C_NV], n_j = (int64_t)hcnt[C_NJ], n_p = (int64_t)hcnt[C_NP];
+    info.v_final += F[0]; info.j_final += F[1]; info.share += n_p;
+    // get_kmer_fromsam / get_err_fromsam on this file's final V list, as samtools stats prints them
+    {
+      const uint64_t tot = hcnt[C_SUM_LEN], snm = hcnt[C_SUM_NM], smi = hcnt[C_SUM_MI];
+      const float avg = F[0] == 0 ? 0.f : (float)(tot / (uint64_t)F[0]);       // samtools: integer division, printed %.0f
+      char buf[64];
+      snprintf(buf, sizeof buf, "%.0f", avg);
+      const double avg_r = atof(buf);
+      info.avg_len = avg_r;
+      if (k == CATT_KMER_AUTO) {
+        if (avg_r >= 50) k = 15;
+        if (avg_r >= 75) k = 19;
+        if (avg_r >= 100) k = 23;
+        if (avg_r >= 150) k = 25;
+      }
+      const float er = smi ? (float)snm / (float)smi : 0.f;
+      snprintf(buf, sizeof buf, "%e", (double)er);
+      info.the_err = atof(buf);
+      if (!(info.the_err == info.the_err)) info.the_err = 0.0;
+    }
+    // both-mapped pairs in QNAME order: LSD radix over 8-byte digits of the trimmed name
+    uint32_t* pairs = pair_a;
+    if (n_p > 1) {
+      unsigned long long *pk_a, *pk_b;
+      if ((rc = ensure(c, SB_PKEY_A, n_p, &pk_a)) || (rc = ensure(c, SB_PKEY_B, n_p, &pk_b))) return rc;
+      const int digits = std::max(1, (int)((hcnt[C_MAXNAME] + 7) / 8));
+      uint32_t* other = pair_b;
+      for (int d = digits - 1; d >= 0; d--) {
+        pair_key_kernel<<<nblk(n_p), 256, 0, st>>>(n_p, pairs, nd, d, pk_a);
+        CATT_CUDA(cudaGetLastError());
+        size_t need = 0;
+        CATT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, pk_a, pk_b, pairs, other, n_p, 0, 64, st));
+        if ((rc = ensure_cub(c, need))) return rc;
+        need = c->sb[SB_CUB].cap;
+        CATT_CUDA(cub::DeviceRadixSort::SortPairs(c->sb[SB_CUB].p, need, pk_a, pk_b, pairs, other, n_p, 0, 64, st));
+        std::swap(pairs, other);
+        *launches += 10;
+      }
+    }
+    // work items in the reference's processing order: [V part | both-mapped | J part] of this file
+    const int64_t nseg = n_v + n_p + n_j;
+    if (n_items + nseg > tot_hits) { set_error("stage B: item count exceeds the mapped-record bound"); return CATT_E_ARG; }
+    ExtractItem* seg = items + n_items;
+    if (F[0] > 0) {
+      part_item_kernel<<<nblk(F[0]), 256, 0, st>>>(F[0], ord_idx[0], ord_flag[0], opos[0], rec[0], 0, (uint32_t)lo, seg);
+      CATT_CUDA(cudaGetLastError());
+      *launches += 1;
+    }
+    if (n_p > 0) {
+      pair_item_kernel<<<nblk(n_p), 256, 0, st>>>(n_p, pairs, slot_of, minr[0], sorted[0], rec[0], rec[1], (uint32_t)lo, seg + n_v);
+      CATT_CUDA(cudaGetLastError());
+      *launches += 1;
+    }
+    if (F[1] > 0) {
+      part_item_kernel<<<nblk(F[1]), 256, 0, st>>>(F[1], ord_idx[1], ord_flag[1], opos[1], rec[1], 1, (uint32_t)lo, seg + n_v + n_p);
+      CATT_CUDA(cudaGetLastError());
+      *launches += 1;
+    }
+    CATT_CUDA(cudaEventRecord(c->ev[6], st));
+    // K5: assignV/J, real_score, clipping, finder! with the k that is current for this file (catt.jl:279,301)
+    if ((rc = launch_extract(c->V.dev, c->J.dev, reads, c->d_finder, seg, eout + n_items, nseg, k, c->allow_v, c->allow_j, st, launches))) return rc;
+    CATT_CUDA(cudaEventRecord(c->ev[7], st));
+    CATT_CUDA(cudaStreamSynchronize(st));
+    { float a = 0, b = 0; cudaEventElapsedTime(&a, c->ev[5], c->ev[6]); cudaEventElapsedTime(&b, c->ev[6], c->ev[7]); ms_order += a; ms_extract += b; }
+    n_items += nseg;
   }
+  info.kmer = k;
+  tr.lap("B: names + order + dedup + extract");
 
-  // ---- work items in the reference's processing order: [V part | both-mapped | J part]
-  const int64_t n_items = n_v + n_p + n_j;
-  ExtractItem* items; ExtractOut* eout; uint32_t *kflag, *kpos2, *pflag, *xpos;
-  if ((rc = ensure(c, SB_ITEMS, n_items, &items)) || (rc = ensure(c, SB_EOUT, n_items, &eout)) || (rc = ensure(c, SB_KFLAG, n_items + 1, &kflag)) ||
-      (rc = ensure(c, SB_KPOS2, n_items + 1, &kpos2)) || (rc = ensure(c, SB_PFLAG, n_items + 1, &pflag)) || (rc = ensure(c, SB_XPOS, n_items + 1, &xpos))) return rc;
-  if (F[0] > 0) {
-    part_item_kernel<<<nblk(F[0]), 256, 0, st>>>(F[0], ord_idx[0], ord_flag[0], opos[0], rec[0], 0, items);
-    CATT_CUDA(cudaGetLastError());
-    *launches += 1;
-  }
-  if (n_p > 0) {
-    pair_item_kernel<<<nblk(n_p), 256, 0, st>>>(n_p, pairs, slot_of, minr[0], sorted[0], rec[0], rec[1], items + n_v);
-    CATT_CUDA(cudaGetLastError());
-    *launches += 1;
-  }
-  if (F[1] > 0) {
-    part_item_kernel<<<nblk(F[1]), 256, 0, st>>>(F[1], ord_idx[1], ord_flag[1], opos[1], rec[1], 1, items + n_v + n_p);
-    CATT_CUDA(cudaGetLastError());
-    *launches += 1;
-  }
-  CATT_CUDA(cudaEventRecord(c->ev[6], st));
-  // ---- K5: assignV/J, real_score, clipping, finder!
-  if ((rc = launch_extract(c->V.dev, c->J.dev, reads, c->d_finder, items, eout, n_items, k, c->allow_v, c->allow_j, st, launches))) return rc;
-  CATT_CUDA(cudaEventRecord(c->ev[7], st));
-  // ---- Vpart = kept V part reads then kept both-mapped reads; Jpart = kept J part reads
+  // ---- Vpart = kept V part reads and kept both-mapped reads, file by file; Jpart = kept J part reads
   PoolItem* pitems; OutDesc* desc; uint32_t* partial_idx;
   if ((rc = ensure(c, SB_PITEMS, n_items, &pitems)) || (rc = ensure(c, SB_DESC, n_items, &desc)) || (rc = ensure(c, SB_PARTIAL, n_items, &partial_idx))) return rc;
-  keep_kernel<<<nblk(n_items + 1), 256, 0, st>>>(n_items, eout, kflag, pflag, cnt);
+  CATT_CUDA(cudaMemsetAsync(cnt, 0, C_COUNT * sizeof(unsigned long long), st));
+  CATT_CUDA(cudaEventRecord(c->ev[5], st));
+  keep_kernel<<<nblk(n_items + 1), 256, 0, st>>>(n_items, items, eout, kflag0, kflag1, pflag, cnt);
   CATT_CUDA(cudaGetLastError());
-  if ((rc = scan_u32(c, kflag, kpos2, n_items + 1, st))) return rc;
-  pitem_kernel<<<nblk(std::max<int64_t>(n_items, 1)), 256, 0, st>>>(n_items, n_v, n_p, items, eout, kflag, kpos2, c->J.dev.rec_len, pitems, desc, pflag, cnt);
+  if ((rc = scan_u32(c, kflag0, kpos0, n_items + 1, st)) || (rc = scan_u32(c, kflag1, kpos1, n_items + 1, st))) return rc;
+  pitem_kernel<<<nblk(std::max<int64_t>(n_items, 1)), 256, 0, st>>>(n_items, items, eout, kflag0, kflag1, kpos0, kpos1, c->J.dev.rec_len, pitems, desc, pflag, cnt);
   CATT_CUDA(cudaGetLastError());
   if ((rc = scan_u32(c, pflag, xpos, n_items + 1, st))) return rc;
   partial_kernel<<<nblk(std::max<int64_t>(n_items, 1)), 256, 0, st>>>(n_items, pflag, xpos, partial_idx, desc, cnt);
   CATT_CUDA(cudaGetLastError());
-  *launches += 7;
+  *launches += 9;
+  CATT_CUDA(cudaEventRecord(c->ev[6], st));
   CATT_CUDA(cudaMemcpyAsync(hcnt, cnt, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   CATT_CUDA(cudaStreamSynchronize(st));
-  { float a = 0, b = 0; cudaEventElapsedTime(&a, c->ev[5], c->ev[6]); cudaEventElapsedTime(&b, c->ev[6], c->ev[7]); info.ms_order += a; info.ms_extract += b; }
-  tr.lap("B: items + extract + lists");
+  { float a = 0; cudaEventElapsedTime(&a, c->ev[5], c->ev[6]); info.ms_order += ms_order + a; info.ms_extract += ms_extract; }
+  tr.lap("B: lists");
   const int64_t M = (int64_t)hcnt[C_M], n_partial = (int64_t)hcnt[C_NPARTIAL];
   info.vpart = (int64_t)hcnt[C_VPART]; info.jpart = M - info.vpart; info.full_pushed = (int64_t)hcnt[C_FULL];
   info.pair_seq_mismatch = (int64_t)hcnt[C_MISMATCH];

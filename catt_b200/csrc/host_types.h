@@ -55,7 +55,7 @@ struct PinBuf {
 enum {
   SB_NAMES = 0, SB_NAME_OFF, SB_SLOT_OF, SB_OWNER, SB_MINV, SB_MINJ, SB_KEYS_A, SB_SORT_V, SB_SORT_J, SB_FLAG, SB_KPOS_V,
   SB_KPOS_J, SB_ORD_IDX_V, SB_ORD_IDX_J, SB_ORD_FLAG_V, SB_ORD_FLAG_J, SB_OPOS_V, SB_OPOS_J, SB_PAIR_A, SB_PAIR_B, SB_PKEY_A, SB_PKEY_B, SB_ITEMS,
-  SB_EOUT, SB_KFLAG, SB_KPOS2, SB_PFLAG, SB_XPOS, SB_TAB_KEYS, SB_TAB_VALS, SB_PITEMS, SB_PARTIAL, SB_XOUT, SB_DESC, SB_CNT, SB_CUB,
+  SB_EOUT, SB_KFLAG, SB_KFLAG1, SB_KPOS2, SB_KPOS3, SB_PFLAG, SB_XPOS, SB_TAB_KEYS, SB_TAB_VALS, SB_PITEMS, SB_PARTIAL, SB_XOUT, SB_DESC, SB_CNT, SB_CUB,
   SB_COUNT
 };
 enum { PIN_PACK0 = 0, PIN_PACK1, PIN_OFF, PIN_LEN, PIN_CNT, PIN_DESC, PIN_XOUT, PIN_COUNT };
@@ -119,5 +119,10 @@ struct Trace {
 };
 // Stage B (assemble.cu): everything after the per-read alignment records exist.  The records are read from
 // c->recs_all[0/1] on the device; names/seqs/quals are host buffers (names are uploaded, strings are materialised on the host).
-int stage_b(catt_ctx* c, const HostReads& hr, const ReadsDev& reads, catt_result* R, int* launches);
+// per input file of the sample (paired-end = two files, catt.jl:738-745): first read, mapped V / J records
+struct FileHits {
+  std::vector<int64_t> start, v, j;
+  void single(int64_t n, int64_t vh, int64_t jh) { start = {0, n}; v = {vh}; j = {jh}; }
+};
+int stage_b(catt_ctx* c, const HostReads& hr, const ReadsDev& reads, const FileHits& fh, catt_result* R, int* launches);
 }  // namespace catt

@@ -165,6 +165,26 @@ class Catt:
         _lib.check(_lib.load().catt_run_file(self._h, fastx_path.encode(), C.byref(h)))
         return Result(self, h)
 
+    def mainflow_paired(self, *fastx_paths: str) -> Result:
+        """Paired-end sample (--f1/--f2, catt.jl:738-745): each mate file goes through input_convert + the read_alignrs loop on
+        its own, then one pool/extension pass over the joined lists."""
+        arr = (C.c_char_p * len(fastx_paths))(*[p.encode() for p in fastx_paths])
+        h = C.c_void_p()
+        _lib.check(_lib.load().catt_run_files(self._h, len(fastx_paths), arr, C.byref(h)))
+        return Result(self, h)
+
+    def mainflow_reads_files(self, files) -> Result:
+        """In-memory form of mainflow_paired: files = [(names, seqs, quals), ...]."""
+        nb, no = _lib.concat([x for f in files for x in f[0]])
+        sb, so = _lib.concat([x for f in files for x in f[1]])
+        qb = _lib.concat([x for f in files for x in f[2]])[0]
+        fs = np.zeros(len(files) + 1, dtype=np.int64)
+        np.cumsum([len(f[1]) for f in files], out=fs[1:])
+        h = C.c_void_p()
+        _lib.check(_lib.load().catt_run_reads_files(self._h, int(fs[-1]), nb, no.ctypes.data, sb, so.ctypes.data, qb, len(files),
+                                                    fs.ctypes.data, C.byref(h)))
+        return Result(self, h)
+
     def mainflow_reads(self, names, seqs, quals=None) -> Result:
         nb, no = _lib.concat(names)
         sb, so = _lib.concat(seqs)

@@ -130,6 +130,15 @@ int catt_run_file(catt_ctx* ctx, const char* fastx_path, catt_result** out);
 int catt_run_reads(catt_ctx* ctx, int64_t n, const char* names, const int64_t* name_off, const char* seqs,
                    const int64_t* seq_off, const char* quals, catt_result** out);
 
+/* Paired-end samples (--f1/--f2, catt.jl:738-745).  The reference aligns each mate file on its own (two `bwa mem` runs, read
+ * ordinals restart at 0) and runs the read_alignrs loop once per file - SAM order, QNAME dedup, share_name and the both-mapped
+ * pairing are per file, args["kmer"] comes from the first file whose mean mapped length reaches 50, the_ERR from the last -
+ * and then ONE k-mer table / extension pass over the joined Vpart / Jpart lists.  `paths` in --f1, --f2 order. */
+int catt_run_files(catt_ctx* ctx, int32_t nfiles, const char* const* paths, catt_result** out);
+/* Same for reads in host memory: the reads of all files back to back, file f = reads [file_start[f], file_start[f+1]). */
+int catt_run_reads_files(catt_ctx* ctx, int64_t n, const char* names, const int64_t* name_off, const char* seqs,
+                         const int64_t* seq_off, const char* quals, int32_t nfiles, const int64_t* file_start, catt_result** out);
+
 int catt_result_info(const catt_result* r, catt_info* out);
 /* Vpart (which=0) / Jpart (1) in the reference's list order, ready for catt.jl:579 onwards. */
 int catt_result_reads(const catt_result* r, int which, const catt_read** reads, int64_t* n);

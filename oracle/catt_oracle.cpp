@@ -815,9 +815,9 @@ double now_s() {
 }
 
 // final SAM list of one reference set: AS-sorted, reversed, first record per QNAME   SURVEY A7
-std::vector<int> final_sam_order(const std::vector<AlnRec>& recs, const std::vector<Read>& reads) {
+std::vector<int> final_sam_order(const std::vector<AlnRec>& recs, const std::vector<Read>& reads, size_t lo, size_t hi) {
   std::vector<int> idx;
-  for (size_t i = 0; i < recs.size(); i++) if (recs[i].mapped) idx.push_back((int)i);
+  for (size_t i = lo; i < hi; i++) if (recs[i].mapped) idx.push_back((int)i);
   std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
     const AlnRec &x = recs[a], &y = recs[b];
     if (x.AS != y.AS) return x.AS < y.AS;
@@ -842,12 +842,17 @@ std::vector<int> chunk_order(const std::vector<int>& fin, int T) {
   return out;
 }
 
+// `file_start` (nullptr = one file) lists the first read of every input file plus the total: the reference runs
+// map2align and the read_alignrs loop once per file of a paired-end sample (catt.jl:134-151, 210-326: bwa numbers the
+// reads of each file from 0, the awk dedup / share_name / both-mapped pairing are per file, args["kmer"] is fixed by the
+// first file whose mean length reaches 50, the_ERR is overwritten per file) and then catt() once over the joined lists.
 RunResult* run_pipeline(const RefSet& V, const RefSet& J, const Config& cf0, const std::vector<Read>& reads,
-                        int omp_threads, int want_dump) {
+                        int omp_threads, int want_dump, const std::vector<int64_t>* file_start = nullptr) {
   Config cf = cf0;
   RunResult* R = new RunResult();
   RunInfo& info = R->info;
   const int64_t n = (int64_t)reads.size();
+  std::vector<int64_t> fs = file_start ? *file_start : std::vector<int64_t>{0, n};
   info.n_reads = n;
   R->vrec.resize(n); R->jrec.resize(n);
   double t0 = now_s();
@@ -855,14 +860,16 @@ RunResult* run_pipeline(const RefSet& V, const RefSet& J, const Config& cf0, con
 #ifdef _OPENMP
   if (omp_threads > 0) omp_set_num_threads(omp_threads);
 #endif
+  std::vector<int64_t> file_base((size_t)n, 0);
+  for (size_t f = 0; f + 1 < fs.size(); f++) for (int64_t i = fs[f]; i < fs[f + 1]; i++) file_base[i] = fs[f];
   #pragma omp parallel
   {
     std::vector<uint8_t> candV(V.names.size() * 2), candJ(J.names.size() * 2);
     std::vector<Run> runs;
     #pragma omp for schedule(dynamic, 64)
     for (int64_t i = 0; i < n; i++) {
-      R->vrec[i] = align_read(V, reads[i].seq, i, cf.min_score, candV, runs, nullptr, nullptr);
-      R->jrec[i] = align_read(J, reads[i].seq, i, cf.min_score, candJ, runs, nullptr, nullptr);
+      R->vrec[i] = align_read(V, reads[i].seq, i - file_base[i], cf.min_score, candV, runs, nullptr, nullptr);
+      R->jrec[i] = align_read(J, reads[i].seq, i - file_base[i], cf.min_score, candJ, runs, nullptr, nullptr);
     }
   }
   for (int64_t i = 0; i < n; i++) {
@@ -873,9 +880,11 @@ RunResult* run_pipeline(const RefSet& V, const RefSet& J, const Config& cf0, con
   }
   double t1 = now_s();
   info.t_align = t1 - t0;
-  // ---------------- stage 3a: read_alignrs (catt.jl:186-339)
-  std::vector<int> vfin = final_sam_order(R->vrec, reads), jfin = final_sam_order(R->jrec, reads);
-  info.v_final = (long)vfin.size(); info.j_final = (long)jfin.size();
+  // ---------------- stage 3a: read_alignrs (catt.jl:186-339), once per input file
+  for (size_t f = 0; f + 1 < fs.size(); f++) {
+  std::vector<int> vfin = final_sam_order(R->vrec, reads, (size_t)fs[f], (size_t)fs[f + 1]);
+  std::vector<int> jfin = final_sam_order(R->jrec, reads, (size_t)fs[f], (size_t)fs[f + 1]);
+  info.v_final += (long)vfin.size(); info.j_final += (long)jfin.size();
   // get_kmer_fromsam / get_err_fromsam (catt.jl:153-184) on the final V list
   {
     double tot = 0; long nm = 0, mi = 0;
@@ -901,7 +910,7 @@ RunResult* run_pipeline(const RefSet& V, const RefSet& J, const Config& cf0, con
   std::unordered_set<std::string> vnames, share;
   for (int i : vfin) vnames.insert(reads[i].name);
   for (int i : jfin) if (vnames.count(reads[i].name)) share.insert(reads[i].name);
-  info.share = (long)share.size();
+  info.share += (long)share.size();
 
   struct Full { std::string name; int idx; int which; };
   std::vector<Full> full;
@@ -962,6 +971,8 @@ RunResult* run_pipeline(const RefSet& V, const RefSet& J, const Config& cf0, con
     }
     g = h;
   }
+  }  // per input file
+  const int k = cf.kmer;
   double t2 = now_s();
   info.t_extract = t2 - t1;
   info.vpart = (long)R->Vpart.size(); info.jpart = (long)R->Jpart.size();
@@ -1180,6 +1191,23 @@ void* co_run_mem(void* vref, void* jref, const co_config* c, int64_t n, const ch
   }
   Config cf = make_config(c);
   return run_pipeline(*(RefSet*)vref, *(RefSet*)jref, cf, reads, omp_threads, 0);
+}
+
+// paired-end / multi-file sample from memory: file_start has nfiles+1 entries
+void* co_run_mem_files(void* vref, void* jref, const co_config* c, int64_t n, const char* const* names, const char* const* seqs,
+                       const char* const* quals, int nfiles, const int64_t* file_start, int omp_threads) {
+  std::vector<Read> reads((size_t)n);
+  for (int64_t i = 0; i < n; i++) {
+    Read& r = reads[i];
+    r.name = names[i];
+    size_t l = r.name.size();
+    if (l > 2 && r.name[l - 2] == '/' && isdigit((unsigned char)r.name[l - 1])) r.name.resize(l - 2);
+    r.seq = seqs[i];
+    r.qual = quals ? quals[i] : std::string(r.seq.size(), 'I');
+  }
+  Config cf = make_config(c);
+  std::vector<int64_t> fs(file_start, file_start + nfiles + 1);
+  return run_pipeline(*(RefSet*)vref, *(RefSet*)jref, cf, reads, omp_threads, 0, &fs);
 }
 
 // Synthetic reads of SURVEY §8d config 3 (same algorithm as tests/util.py::synth_read): fixed length, read i drawn from

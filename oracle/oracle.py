@@ -204,6 +204,21 @@ def run_mem(vref: RefSet, jref: RefSet, cfg: CoConfig, names, seqs, quals, threa
                                       _strarr(seqs), _strarr(quals) if quals is not None else None, threads))
 
 
+def run_mem_files(vref: RefSet, jref: RefSet, cfg: CoConfig, files, threads=0) -> RunResult:
+    """Paired-end / multi-file sample: `files` = [(names, seqs, quals), ...] in --f1, --f2 order (catt.jl:738-745)."""
+    names = [x for f in files for x in f[0]]
+    seqs = [x for f in files for x in f[1]]
+    quals = [x for f in files for x in f[2]]
+    fs = np.zeros(len(files) + 1, dtype=np.int64)
+    np.cumsum([len(f[1]) for f in files], out=fs[1:])
+    L = lib()
+    L.co_run_mem_files.restype = C.c_void_p
+    L.co_run_mem_files.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(CoConfig), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                   C.c_void_p, C.c_int]
+    return RunResult(L.co_run_mem_files(vref.h, jref.h, C.byref(cfg), len(seqs), _strarr(names), _strarr(seqs), _strarr(quals),
+                                        len(files), fs.ctypes.data, threads))
+
+
 def sw(q: str, t: str):
     a, b = C.c_int(), C.c_int()
     s = lib().co_sw(q.encode(), t.encode(), C.byref(a), C.byref(b))

@@ -253,3 +253,49 @@ def test_stage_split_equals_whole(ctx, trb, sample):
     res = ctx.assemble(names, seqs, quals, np.concatenate([v1, v2]), np.concatenate([j1, j2]))
     assert [myread_tuple(r) for r in res.Vpart] == [myread_tuple(r) for r in whole.Vpart]
     assert [myread_tuple(r) for r in res.Jpart] == [myread_tuple(r) for r in whole.Jpart]
+
+
+def test_paired_end_files(trb, fx, O, orefs, sample, tmp_path):
+    """--f1/--f2 (catt.jl:738-745): each mate file is aligned and de-duplicated on its own, kmer comes from the first file, the_ERR
+    from the last, and one k-mer table / extension pass runs over the joined lists.  Also reads .gz input."""
+    import gzip
+    from catt_b200.host import Catt
+    names, seqs, quals = sample
+    f1 = [(n, s, q) for n, s, q in zip(names, seqs, quals) if n.endswith("/1")][:1500]
+    f2 = [(n, s, q) for n, s, q in zip(names, seqs, quals) if n.endswith("/2")][:1400]
+    assert len(f1) > 1000 and len(f2) > 1000
+    files = [tuple(map(list, zip(*f1))), tuple(map(list, zip(*f2)))]
+    for threads in (1, 3):
+        c = Catt(chain_cfg=trb, thread=threads)
+        ref = O.run_mem_files(orefs[0], orefs[1], O.make_config(trb, nthreads=threads), files)
+        res = c.mainflow_reads_files(files)
+        assert [myread_tuple(r) for r in res.Vpart] == [myread_tuple(r) for r in ref.Vpart]
+        assert [myread_tuple(r) for r in res.Jpart] == [myread_tuple(r) for r in ref.Jpart]
+        for k in ("kmer", "v_hits", "j_hits", "v_final", "j_final", "share", "pair_seq_mismatch", "full_pushed", "vpart", "jpart",
+                  "direct", "left", "rescued"):
+            assert res.info[k] == ref.info[k], (k, res.info[k], ref.info[k])
+        assert res.info["the_err"] == ref.info["the_err"]
+        if threads == 1:                      # the same sample from two files on disk, the second one gzip-compressed
+            p1, p2 = str(tmp_path / "m_1.fq"), str(tmp_path / "m_2.fq.gz")
+            with open(p1, "w") as fh:
+                fh.write("".join(f"@{n}\n{s}\n+\n{q}\n" for n, s, q in f1))
+            with gzip.open(p2, "wt") as fh:
+                fh.write("".join(f"@{n}\n{s}\n+\n{q}\n" for n, s, q in f2))
+            res2 = c.mainflow_paired(p1, p2)
+            assert [myread_tuple(r) for r in res2.Vpart] == [myread_tuple(r) for r in ref.Vpart]
+            assert [myread_tuple(r) for r in res2.Jpart] == [myread_tuple(r) for r in ref.Jpart]
+        # joining the mates into one file is NOT the same thing (the dedup and the V/J pairing would cross the files)
+        c.close()
+
+
+def test_fasta_input_multiline(ctx, O, orefs, trb, sample, tmp_path):
+    """FASTA input (no qualities -> 'I'), sequences wrapped over several lines."""
+    names, seqs, _ = [x[:800] for x in sample]
+    p = str(tmp_path / "s.fa")
+    with open(p, "w") as fh:
+        for n, s in zip(names, seqs):
+            fh.write(f">{n} some comment\n" + "\n".join(s[i:i + 60] for i in range(0, len(s), 60)) + "\n")
+    res = ctx.mainflow(p)
+    ref = O.run_mem(orefs[0], orefs[1], O.make_config(trb), names, seqs, ["I" * len(s) for s in seqs])
+    assert [myread_tuple(r) for r in res.Vpart] == [myread_tuple(r) for r in ref.Vpart]
+    assert [myread_tuple(r) for r in res.Jpart] == [myread_tuple(r) for r in ref.Jpart]
