@@ -98,7 +98,7 @@ def cpu_reference_run(fx, length, n_sample, first_index=0):
     seqs, quals = O.synth_reads(V, J, n_sample, length, first_index=first_index, seed=SEED)
     cfg = O.make_config(cc)
     t0 = time.perf_counter()
-    R = O.run_flat(V, J, cfg, seqs, quals, first_index=first_index)
+    R = O.run_flat(V, J, cfg, seqs, quals, first_index=first_index, threads=len(os.sched_getaffinity(0)))   # explicit: torchrun exports OMP_NUM_THREADS=1
     dt = time.perf_counter() - t0
     return n_sample / dt, dt, R.info
 
@@ -118,7 +118,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) or 1
     workload = f"synthetic hs TRB {args.length}bp reads from IMGT V/J with random CDR3 insertions (BASELINE configs[2], SURVEY 8d config 3)"
 
     # ------------------------------------------------------------------------------------------------- reference arm
@@ -166,10 +166,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    from catt_b200.host import Catt
+    from catt_b200.host import Catt, set_host_threads
     from catt_b200.refg import chain_config
     fx = fixture_dir()
     cc = chain_config("hs", "TRB", "CDR3", os.path.join(fx, "resource"))
+    # one process per GPU: every rank gets its share of the host cores (torchrun exports OMP_NUM_THREADS=1)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    host_threads = max(1, len(os.sched_getaffinity(0)) // max(1, local_world))
+    set_host_threads(host_threads)
     ctx = Catt(chain_cfg=cc, device=local_rank)
     R = args.reads_per_step
     first = rank * R
@@ -242,7 +246,7 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
         "config": {"workload": workload, "reads_per_step_per_gpu": R, "read_length": args.length, "chain": "hs TRB",
                    "l2": f"packed batch {packed_bytes >> 20} MiB per step vs 126 MB L2" + (" (larger than L2)" if packed_bytes > 126e6 else " (compute-bound kernel; see DESIGN.md)"),
-                   "multi_gpu": "shards are independent samples; no data-path collective"},
+                   "multi_gpu": "shards are independent samples; no data-path collective", "host_threads_per_rank": host_threads},
         "gcups": world * cells / (sw_ms * 1e-3) / 1e9,
         "gcups_note": "DP cell updates / SW-kernel time (CUDA events in the library), summed over GPUs",
         "stage_ms": {k: sum(i[k] for i in infos) / len(infos) for k in ("ms_seed", "ms_sw", "ms_select", "ms_order", "ms_extract", "ms_pool", "ms_d2h", "ms_host", "ms_pack")},

@@ -391,6 +391,12 @@ void catt_ctx_destroy(catt_ctx* c) {
   delete c;
 }
 
+int catt_set_host_threads(int32_t n) {
+  if (n < 0) { set_error("catt_set_host_threads: negative thread count"); return CATT_E_ARG; }
+  omp_set_num_threads(n > 0 ? n : omp_get_num_procs());
+  return CATT_OK;
+}
+
 int catt_ref_count(const catt_ctx* c, int which) { return c ? (int)(which ? c->J : c->V).names.size() : 0; }
 const char* catt_ref_name(const catt_ctx* c, int which, int32_t id) {
   if (!c) return nullptr;

@@ -129,6 +129,11 @@ class Batch:
             pass
 
 
+def set_host_threads(n: int = 0):
+    """Host threads for read packing / result materialisation (0 = all hardware threads); one process per GPU -> cores // ranks."""
+    _lib.check(_lib.load().catt_set_host_threads(n))
+
+
 class Catt:
     """One CATT configuration bound to one GPU (catt_ctx)."""
 

@@ -116,6 +116,10 @@ void catt_ctx_destroy(catt_ctx* ctx);
 const char* catt_last_error(void);
 const char* catt_version(void);
 
+/* Host threads the library uses for packing reads and materialising the result strings (process-wide; 0 = all hardware
+ * threads).  One process per GPU: give each rank its share of the cores (launchers such as torchrun export OMP_NUM_THREADS=1). */
+int catt_set_host_threads(int32_t n);
+
 int catt_ref_count(const catt_ctx* ctx, int which /*0=V,1=J*/);
 const char* catt_ref_name(const catt_ctx* ctx, int which, int32_t id);      /* FASTA.identifier, catt.jl:202 */
 int catt_ref_seq(const catt_ctx* ctx, int which, int32_t id, char* out, int32_t cap); /* alignment bases; returns length */
