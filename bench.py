@@ -158,6 +158,8 @@ def main():
         print(json.dumps({"error": "no CUDA device: libcatt_b200 has no CPU fallback"}))
         return 2
     torch.cuda.set_device(local_rank)
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's banner off stdout: rank 0 prints exactly one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
