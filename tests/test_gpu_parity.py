@@ -299,3 +299,48 @@ def test_fasta_input_multiline(ctx, O, orefs, trb, sample, tmp_path):
     ref = O.run_mem(orefs[0], orefs[1], O.make_config(trb), names, seqs, ["I" * len(s) for s in seqs])
     assert [myread_tuple(r) for r in res.Vpart] == [myread_tuple(r) for r in ref.Vpart]
     assert [myread_tuple(r) for r in res.Jpart] == [myread_tuple(r) for r in ref.Jpart]
+
+
+@pytest.mark.parametrize("chain", ["TRA", "IGH"])
+def test_short_reads_other_chains(fx, O, chain):
+    """BASELINE configs[3]: 50-bp reads (k = 15 path, most reads are partial -> k-mer table + extension) on hs TRA / IGH."""
+    from catt_b200.host import Catt
+    from catt_b200.refg import chain_config
+    cc = chain_config("hs", chain, "CDR3", os.path.join(fx, "resource"))
+    V, J = O.RefSet(cc["vregion"]), O.RefSet(cc["jregion"])
+    names, seqs, quals = synth_reads(2500, [V.record(i) for i in range(V.nrec)], [J.record(i) for i in range(J.nrec)], 50, seed=404, with_n=True)
+    c = Catt(chain_cfg=cc)
+    res = c.mainflow_reads(names, seqs, quals)
+    ref = O.run_mem(V, J, O.make_config(cc), names, seqs, quals)
+    assert res.info["kmer"] == ref.info["kmer"] == 15
+    assert [myread_tuple(r) for r in res.Vpart] == [myread_tuple(r) for r in ref.Vpart]
+    assert [myread_tuple(r) for r in res.Jpart] == [myread_tuple(r) for r in ref.Jpart]
+    for k in ("vpart", "jpart", "direct", "left", "rescued", "cand_v", "cand_j"):
+        assert res.info[k] == ref.info[k], (k, res.info[k], ref.info[k])
+    c.close()
+
+
+def test_rnaseq_like_mix(ctx, O, orefs, trb):
+    """BASELINE configs[1] substitute (the SRR11799691 input is not shipped): 1 % TRB-derived 100-bp reads among
+    uniform-random reads, seed 11799691.  Almost every read has no seed; a few random reads hit by chance."""
+    V, J = orefs
+    vrecs = [V.record(i) for i in range(V.nrec)]
+    jrecs = [J.record(i) for i in range(J.nrec)]
+    rng = np.random.default_rng(11799691)
+    n = 20000
+    tn, ts, tq = synth_reads(n // 100, vrecs, jrecs, 100, seed=11799691)
+    names, seqs, quals = [], [], []
+    t = 0
+    for i in range(n):
+        if i % 100 == 37:
+            names.append(f"t{t}"); seqs.append(ts[t]); quals.append(tq[t]); t += 1
+        else:
+            names.append(f"r{i}"); seqs.append("".join("ACGT"[x] for x in rng.integers(0, 4, 100))); quals.append("I" * 100)
+    v, j = ctx.align_shard(seqs)
+    assert_records_equal(v, V.align(seqs), O)
+    assert_records_equal(j, J.align(seqs), O)
+    res = ctx.mainflow_reads(names, seqs, quals)
+    ref = O.run_mem(V, J, O.make_config(trb), names, seqs, quals)
+    assert [myread_tuple(r) for r in res.Vpart] == [myread_tuple(r) for r in ref.Vpart]
+    assert [myread_tuple(r) for r in res.Jpart] == [myread_tuple(r) for r in ref.Jpart]
+    assert res.info["v_hits"] == ref.info["v_hits"] and res.info["v_hits"] < n // 10     # chance hits with AS >= 12 included
