@@ -89,6 +89,32 @@ def ncu_traffic():
         return None
 
 
+def roofline_other(infos, length, world):
+    """The two HBM-side kernels of SURVEY 8d against the measured copy bandwidth (MEASURED_PEAKS.json, else the recipe's fallback).
+    Algorithmic bytes: seeding = packed read in (ceil(L/4) + ceil(L/8) B) + the two candidate bitmaps and the task count out per
+    read and reference set; k-mer table = 16 B per insert, 11 inserts per Vpart/Jpart read.  Both kernels are latency / random-
+    access bound by design (tables are L2-resident), so the fractions are small; they are reported, not optimised for."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peak, src = float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        peak, src = 6650.0, "fallback (B200_PROFILING.md)"
+    i = infos[-1]
+    n = i["n_reads"]
+    ms_seed = sum(x["ms_seed_kernel"] for x in infos) / len(infos)
+    ms_pool = sum(x["ms_pool_kernel"] for x in infos) / len(infos)
+    seed_bytes = n * ((-(-length // 4) + -(-length // 8)) * 2 + 2 * 4 * (11 + 1) + 2 * 4)      # CW = 11 words (V) + 1 (J)
+    pool_bytes = 16 * 11 * (i["vpart"] + i["jpart"])
+    out = {}
+    if ms_seed > 0:
+        a = world * seed_bytes / (ms_seed * 1e-3) / 1e9
+        out["seed_kernel"] = {"bound": "hbm", "achieved": a, "peak": peak * world, "unit": "GB/s", "frac": a / (peak * world), "peak_source": src}
+    if ms_pool > 0:
+        a = world * pool_bytes / (ms_pool * 1e-3) / 1e9
+        out["pool_kernel"] = {"bound": "hbm", "achieved": a, "peak": peak * world, "unit": "GB/s", "frac": a / (peak * world), "peak_source": src}
+    return out
+
+
 def cpu_reference_run(fx, length, n_sample, first_index=0):
     """The CPU restatement (oracle) on n_sample reads with all host threads; returns (reads/s, seconds, info)."""
     from catt_b200.refg import chain_config
@@ -265,6 +291,7 @@ def main():
                              "approach or pass 1; peak = measured packed-DPX (VIADDMNMX.S16x2) issue rate x 4 "
                              f"int16 ops per thread-instruction ({peak_ops / 1e12:.2f} T thread-instr/s, this GPU, in-repo microbenchmark); "
                              "MEASURED_PEAKS.json has no integer entry"},
+        "roofline_other": roofline_other(infos, args.length, world),
         "counters": {k: info[k] for k in ("v_hits", "j_hits", "vpart", "jpart", "direct", "left", "rescued", "cand_v", "cand_j", "gapped_v")},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

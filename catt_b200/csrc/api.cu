@@ -118,7 +118,7 @@ int align_finish(catt_ctx* c, int which, const ReadsDev& reads, catt_aln* recs, 
     CATT_CUDA(cudaStreamSynchronize(st));
   }
   if (info) {
-    info->ms_seed += ms_seed + ms_exp; info->ms_sw += ms_sw; info->ms_select += ms_sel;
+    info->ms_seed += ms_seed + ms_exp; info->ms_seed_kernel += ms_seed; info->ms_sw += ms_sw; info->ms_select += ms_sel;
     if (which) { info->cand_j += (int64_t)cnt[0]; info->cells_j += (int64_t)cnt[1]; info->gapped_j += (int64_t)cnt[2]; info->j_hits += (int64_t)cnt[3]; info->cells_computed_j += (int64_t)cnt[8]; }
     else { info->cand_v += (int64_t)cnt[0]; info->cells_v += (int64_t)cnt[1]; info->gapped_v += (int64_t)cnt[2]; info->v_hits += (int64_t)cnt[3]; info->cells_computed_v += (int64_t)cnt[8]; }
   }
@@ -211,7 +211,7 @@ int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool
   }
   CATT_CUDA(cudaStreamSynchronize(st));
   if (info && align) {
-    info->ms_seed += local.ms_seed; info->ms_sw += local.ms_sw; info->ms_select += local.ms_select;
+    info->ms_seed += local.ms_seed; info->ms_seed_kernel += local.ms_seed_kernel; info->ms_sw += local.ms_sw; info->ms_select += local.ms_select;
     info->cand_v += local.cand_v; info->cand_j += local.cand_j; info->cells_v += local.cells_v; info->cells_j += local.cells_j;
     info->gapped_v += local.gapped_v; info->gapped_j += local.gapped_j; info->v_hits += local.v_hits; info->j_hits += local.j_hits;
     info->cells_computed_v += local.cells_computed_v; info->cells_computed_j += local.cells_computed_j;

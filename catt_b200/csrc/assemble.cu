@@ -541,7 +541,9 @@ int stage_b(catt_ctx* c, const HostReads& hr, const ReadsDev& reads, const FileH
     tab.mask = slots - 1;
     CATT_CUDA(cudaMemsetAsync(tab.keys, 0xff, slots * sizeof(unsigned long long), st));
     CATT_CUDA(cudaMemsetAsync(tab.vals, 0, slots * sizeof(unsigned long long), st));
+    CATT_CUDA(cudaEventRecord(c->ev[0], st));
     if ((rc = launch_pool(reads, pitems, M, k, tab, st, launches))) return rc;
+    CATT_CUDA(cudaEventRecord(c->ev[1], st));
     if ((rc = launch_extend(reads, c->d_finder, pitems, partial_idx, n_partial, k, tab, xout, reinterpret_cast<uint32_t*>(cnt + C_RESCUED), st, launches))) return rc;
     CATT_CUDA(cudaMemcpyAsync(hxout, xout, (size_t)n_partial * sizeof(ExtendOut), cudaMemcpyDeviceToHost, st));
   }
@@ -551,6 +553,7 @@ int stage_b(catt_ctx* c, const HostReads& hr, const ReadsDev& reads, const FileH
   CATT_CUDA(cudaEventRecord(c->ev[7], st));
   CATT_CUDA(cudaStreamSynchronize(st));
   { float a = 0, b = 0; cudaEventElapsedTime(&a, c->ev[5], c->ev[6]); cudaEventElapsedTime(&b, c->ev[6], c->ev[7]); info.ms_pool += a; info.ms_d2h += b; }
+  if (run_pool) { float a = 0; cudaEventElapsedTime(&a, c->ev[0], c->ev[1]); info.ms_pool_kernel += a; }
   if (!run_pool) for (int64_t x = 0; x < n_partial; x++) { hxout[x].n_ext = 0; hxout[x].cdr3_off = -1; hxout[x].cdr3_len = 0; hxout[x].able = 1; }
   info.rescued += (int64_t)(uint32_t)hcnt[C_RESCUED];
   tr.lap("B: pool + extend + D2H");

@@ -107,6 +107,8 @@ typedef struct catt_info {
   int64_t cells_computed_v, cells_computed_j; /* DP cells actually computed: byte-identical records are scored once */
   double ms_order;            /* device time of the SAM ordering / QNAME dedup / pairing kernels (samtools sort | tac | awk) */
   double ms_pack;             /* host time packing reads that was NOT hidden under kernels */
+  double ms_seed_kernel;      /* seed_kernel alone (ms_seed also holds the task scan / expansion) */
+  double ms_pool_kernel;      /* pool_kernel alone (ms_pool also holds the extension kernel) */
 } catt_info;
 
 /* ---- lifecycle --------------------------------------------------------------------------------------------- */

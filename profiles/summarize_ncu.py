@@ -64,5 +64,26 @@ def full(path):
                 print(f"  {m:80s} {r[i]:>18s} {units[i]}")
 
 
+def traffic(path):
+    """profiles/traffic.json: dram bytes (read + write) per launch of the dominant kernel, largest launch of each name."""
+    import json
+    import os
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = csv_rows(out)
+    hdr, units = rows[0], rows[1]
+    kn, rd, wr, du = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    res = {}
+    for r in rows[2:]:
+        name = r[kn].split("<")[0].split("::")[-1].split("(")[0]
+        b = float(r[rd].replace(",", "")) * scale[units[rd]] + float(r[wr].replace(",", "")) * scale[units[wr]]
+        if name not in res or b > res[name]:
+            res[name] = b
+    res["_source"] = os.path.basename(path) + " (ncu --set full, 262144 x 150 bp reads per launch)"
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "traffic.json"), "w") as fh:
+        json.dump(res, fh, indent=1)
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])
