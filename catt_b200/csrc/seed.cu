@@ -88,6 +88,7 @@ __device__ void reseed(const RefDev& ref, const WarpScratch& ws, const Scratch& 
   if (lane == 0) { ws.ctr[1] = 0; ws.ctr[2] = 0; }
   if (lane < MAX_READ / 32) ws.startbits[lane] = 0;
   __syncwarp();
+  #pragma unroll 1
   for (int r = lane; r < n; r += 32) {
     const uint32_t q = sc.runs_q[r];
     const int qs = q & 0xffff, qe = q >> 16;
@@ -101,6 +102,7 @@ __device__ void reseed(const RefDev& ref, const WarpScratch& ws, const Scratch& 
   const int nc = ws.ctr[1];
   if (nc < m) return;
   int ns = 0;
+  #pragma unroll 1
   for (int w = 0; w < MAX_READ / 32; w++) {
     const uint32_t bits = ws.startbits[w];
     const int c = __popc(bits);
@@ -109,6 +111,7 @@ __device__ void reseed(const RefDev& ref, const WarpScratch& ws, const Scratch& 
   }
   __syncwarp();
   uint32_t prev_run = 0;
+  #pragma unroll 1
   for (int sb = 0; sb < ns; sb += 32) {
     const int si = sb + lane;
     const bool valid = si < ns;
@@ -117,6 +120,7 @@ __device__ void reseed(const RefDev& ref, const WarpScratch& ws, const Scratch& 
     #pragma unroll
     for (int t = 0; t < 11; t++) top[t] = 0;
     int c = 0;
+    #pragma unroll 1
     for (int k = 0; k < nc; k++) {
       const uint32_t q = sc.runs_q[sc.cov[k]];
       const int qs = q & 0xffff;
@@ -146,8 +150,10 @@ __device__ void reseed(const RefDev& ref, const WarpScratch& ws, const Scratch& 
   }
   __syncwarp();
   const int nv = ws.ctr[2];
+  #pragma unroll 1
   for (int v = 0; v < nv; v++) {
     const int s = ws.Pm[v] & 0xffff, e = ws.Pm[v] >> 16;
+    #pragma unroll 1
     for (int k = lane; k < nc; k += 32) {
       const int r = sc.cov[k];
       const uint32_t q = sc.runs_q[r];
@@ -165,6 +171,7 @@ __device__ bool seed_one_read(const RefDev& ref, const uint32_t* __restrict__ T2
   const uint32_t* __restrict__ w = reads.words + reads.off[r];
   const uint32_t* __restrict__ nm = w + read_base_words(len);
   const int n2 = 2 * ref.L;
+  #pragma unroll 1
   for (int i = lane; i < len; i += 32) {
     const uint32_t c = (w[i >> 4] >> ((i & 15) * 2)) & 3u;
     ws.codes[i] = ((nm[i >> 5] >> (i & 31)) & 1u) ? 4 : (uint8_t)c;
@@ -175,6 +182,7 @@ __device__ bool seed_one_read(const RefDev& ref, const uint32_t* __restrict__ T2
   __syncwarp();
   // ---- maximal runs >= 10 (each found once, from its left-maximal 10-mer window)
   // step 1: every lane scans its window positions and queues the left-maximal (s, p) pairs
+  #pragma unroll 1
   for (int s = lane; s + SEED_K <= len; s += 32) {
     const uint64_t bw = ((uint64_t)w[(s >> 4) + 1] << 32) | w[s >> 4];
     const uint32_t key = (uint32_t)(bw >> ((s & 15) * 2)) & 0xFFFFFu;
@@ -191,6 +199,7 @@ __device__ bool seed_one_read(const RefDev& ref, const uint32_t* __restrict__ T2
       ex0 = h0 + (prev ? (uint32_t)(sub >> (16 * (prev - 1))) & 0xFFFFu : 0u);
       ex1 = h0 + ((uint32_t)(sub >> (16 * prev)) & 0xFFFFu);
     }
+    #pragma unroll 1
     for (uint32_t h = h0; h < h1; h++) {
       if (h == ex0) { h = ex1; if (h >= h1) break; }
       const int p = (int)__ldg(&ref.kpos[h]);
@@ -202,10 +211,12 @@ __device__ bool seed_one_read(const RefDev& ref, const uint32_t* __restrict__ T2
   // step 2: the queued runs are extended by all lanes, 16 bases per step on the packed words
   {
     const int nq = min(ws.ctr[0], sc.cap);
+    #pragma unroll 1
     for (int k = lane; k < nq; k += 32) {
       const int s = (int)sc.runs_q[k], p = (int)sc.runs_t[k];
       int e = SEED_K;
       const int lim = min(len - s, n2 - p);
+      #pragma unroll 1
       while (e < lim) {
         const int a = s + e, b = p + e;
         const uint32_t ra = (uint32_t)((((uint64_t)w[(a >> 4) + 1] << 32) | w[a >> 4]) >> ((a & 15) * 2));
@@ -226,10 +237,12 @@ __device__ bool seed_one_read(const RefDev& ref, const uint32_t* __restrict__ T2
   if (n > sc.cap) return false;
   if (n == 0) return true;
   // ---- pass 1: SMEM occurrences
+  #pragma unroll 1
   for (int k = lane; k < n; k += 32) { const uint32_t q = sc.runs_q[k]; atomicMax(&ws.M1[q & 0xffff], q >> 16); }
   __syncwarp();
   {
     uint32_t carry = 0;
+    #pragma unroll 1
     for (int base = 0; base < len; base += 32) {
       const int i = base + lane;
       uint32_t incl = i < len ? ws.M1[i] : 0;
@@ -243,6 +256,7 @@ __device__ bool seed_one_read(const RefDev& ref, const uint32_t* __restrict__ T2
     }
   }
   __syncwarp();
+  #pragma unroll 1
   for (int k = lane; k < n; k += 32) {
     const uint32_t q = sc.runs_q[k];
     const uint32_t qs = q & 0xffff, qe = q >> 16;
@@ -250,6 +264,7 @@ __device__ bool seed_one_read(const RefDev& ref, const uint32_t* __restrict__ T2
   }
   __syncwarp();
   // ---- pass 2: re-seeding inside long, rare SMEMs
+  #pragma unroll 1
   for (int base = 0; base < len; base += 32) {
     const int i = base + lane;
     const bool sel = i < len && ws.cnt[i] > 0 && ws.cnt[i] <= 10 && (int)ws.M1[i] - i >= 15;
@@ -263,6 +278,7 @@ __device__ bool seed_one_read(const RefDev& ref, const uint32_t* __restrict__ T2
   }
   // ---- pass 3: tiles
   int x = 0;
+  #pragma unroll 1
   while (x < len) {
     if (ws.codes[x] > 3) { x++; continue; }
     if (x + 11 > len) break;
@@ -275,6 +291,7 @@ __device__ bool seed_one_read(const RefDev& ref, const uint32_t* __restrict__ T2
     // last prefix that still has >= 20 covering runs is found by bisection instead of one warp-wide count per base
     auto covering = [&](int e) {
       uint32_t mine = 0;
+      #pragma unroll 1
       for (int k = lane; k < n; k += 32) { const uint32_t q = sc.runs_q[k]; mine += ((int)(q & 0xffff) <= x && (int)(q >> 16) >= e); }
       return warp_sum(mine);
     };
@@ -284,6 +301,7 @@ __device__ bool seed_one_read(const RefDev& ref, const uint32_t* __restrict__ T2
       int lo = e, hi = len;                                  // covering(lo) >= 20
       uint32_t chi = lo < hi ? covering(hi) : c;
       if (chi >= 20) break;                                  // the tile would run to the end of the read: stop
+      #pragma unroll 1
       while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
         const uint32_t cm = covering(mid);
@@ -293,6 +311,7 @@ __device__ bool seed_one_read(const RefDev& ref, const uint32_t* __restrict__ T2
       e = hi; c = chi;
     }
     if (c > 0) {
+      #pragma unroll 1
       for (int k = lane; k < n; k += 32) {
         const uint32_t q = sc.runs_q[k];
         const int qs = q & 0xffff, qe = q >> 16;
