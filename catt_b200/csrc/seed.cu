@@ -20,7 +20,7 @@ namespace catt {
 namespace {
 
 constexpr int SEED_WARPS = 8;
-constexpr int RUNS_SMEM = 512;
+constexpr int RUNS_SMEM = 256;
 constexpr int RUNS_GLOBAL = 16384;
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int T2_SMEM_MAX_BYTES = 56 * 1024;
