@@ -263,10 +263,9 @@ def main():
     peak = peak_ops * 4.0                                       # a packed add-max retires 2 adds + 2 max per thread-instruction
     ei = e2e_infos[-1]
     packed_bytes = R * (4 * ((args.length + 15) // 16 + (args.length + 31) // 32) + 8)
-    # H2D: packed reads (+ offsets/lengths), QNAMEs + their offsets.  D2H: one 32-byte descriptor per Vpart/Jpart read, one
-    # 48-byte extension record per partial read, the counters.  (Counted from the buffers the library copies.)
-    h2d = packed_bytes + int(name_off[-1]) + 8 * (R + 1)
-    d2h = 32 * (ei["vpart"] + ei["jpart"]) + 48 * ei["left"] + 3 * 24 * 8 + 2 * 16 * 8 * -(-R // 262144)
+    # counted by the library from the buffers it copies: H2D = packed reads + offsets/lengths, quality strings, QNAMEs + offsets;
+    # D2H = the two string arenas + one 48-byte catt_read per Vpart/Jpart read + the counters
+    h2d, d2h = ei["bytes_h2d"], ei["bytes_d2h"]
 
     line = {
         "metric": "reads_per_sec", "value": world * R * args.steps / (dev_ms * 1e-3), "unit": "reads/s", "n_gpus": world,
@@ -277,9 +276,9 @@ def main():
                    "multi_gpu": "shards are independent samples; no data-path collective", "host_threads_per_rank": host_threads},
         "gcups": world * cells / (sw_ms * 1e-3) / 1e9,
         "gcups_note": "DP cell updates / SW-kernel time (CUDA events in the library), summed over GPUs",
-        "stage_ms": {k: sum(i[k] for i in infos) / len(infos) for k in ("ms_seed", "ms_sw", "ms_select", "ms_order", "ms_extract", "ms_pool", "ms_d2h", "ms_host", "ms_pack")},
+        "stage_ms": {k: sum(i[k] for i in infos) / len(infos) for k in ("ms_seed", "ms_sw", "ms_select", "ms_order", "ms_extract", "ms_pool", "ms_strings", "ms_d2h", "ms_host", "ms_pack")},
         "timing": {"wall_ms_per_step": wall_ms / args.steps, "cuda_event_ms_per_step": ev_ms / args.steps},
-        "e2e_stage_ms": {k: sum(i[k] for i in e2e_infos) / len(e2e_infos) for k in ("ms_seed", "ms_sw", "ms_select", "ms_order", "ms_extract", "ms_pool", "ms_d2h", "ms_host", "ms_pack")},
+        "e2e_stage_ms": {k: sum(i[k] for i in e2e_infos) / len(e2e_infos) for k in ("ms_seed", "ms_sw", "ms_select", "ms_order", "ms_extract", "ms_pool", "ms_strings", "ms_d2h", "ms_host", "ms_pack")},
         "e2e": {"value": world * R * args.steps / (e2e_ms * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(sum(i["kernel_launches"] for i in infos)),

@@ -151,8 +151,8 @@ int stage_a_resident(catt_ctx* c, const DeviceReads& dr, int64_t first_ordinal, 
 // Host reads -> ctx->rd_* on the device, Stage A pipelined: while the kernels of chunk i run, the host threads pack chunk
 // i+1 into pinned staging and the copy stream moves it to HBM.  `fh->start` lists the input files of the sample: chunks never
 // straddle a file and bwa's read ordinal restarts at every file (each file is one `bwa mem` run, catt.jl:143-147).
-int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool align, DeviceReads* view, FileHits* fh, catt_info* info,
-                   int* launches) {
+int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool align, bool want_quals, DeviceReads* view, DeviceQuals* dq,
+                   FileHits* fh, catt_info* info, int* launches) {
   const int64_t n = hr.n;
   int rc;
   const double t0 = now_ms();
@@ -168,15 +168,34 @@ int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool
   dr.words = c->rd_words.as<uint32_t>(); dr.off = c->rd_off.as<uint32_t>(); dr.len = c->rd_len.as<int32_t>(); dr.n = n; dr.max_len = max_len;
   *view = dr;
   cudaStream_t st = c->stream, cs = c->copy_stream;
+  // the quality strings follow their chunk to HBM on the copy stream (the result strings are written on the device)
+  char* d_quals = nullptr;
+  if (dq) *dq = DeviceQuals{};
+  if (want_quals && dq && n > 0) {
+    if ((rc = c->rd_seqoff.ensure((size_t)(n + 1) * sizeof(int64_t)))) return rc;
+    CATT_CUDA(cudaMemcpyAsync(c->rd_seqoff.p, hr.seq_off, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    dq->seq_off = c->rd_seqoff.as<int64_t>();
+    if (hr.quals) {
+      if ((rc = c->rd_quals.ensure((size_t)hr.seq_off[n] + 16))) return rc;
+      d_quals = c->rd_quals.as<char>();
+      dq->quals = d_quals;
+    }
+  }
   CATT_CUDA(cudaMemcpyAsync(dr.off, h_off, (size_t)(n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   CATT_CUDA(cudaMemcpyAsync(dr.len, h_len, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  if (info) info->bytes_h2d += (int64_t)((n + 1) * 4 + n * 4 + (dq && dq->seq_off ? (n + 1) * 8 : 0));
   struct Chunk { int64_t i0, cnt, ordinal; int file; };
   std::vector<Chunk> chunks;
   const int nfiles = (int)fh->start.size() - 1;
   fh->v.assign(nfiles, 0); fh->j.assign(nfiles, 0);
+  // the very first chunk is small: nothing hides its packing / upload, so the GPU should get work as early as possible
   for (int f = 0; f < nfiles; f++)
-    for (int64_t i0 = fh->start[f]; i0 < fh->start[f + 1]; i0 += c->chunk_reads)
-      chunks.push_back(Chunk{i0, std::min<int64_t>(c->chunk_reads, fh->start[f + 1] - i0), first_ordinal + (i0 - fh->start[f]), f});
+    for (int64_t i0 = fh->start[f]; i0 < fh->start[f + 1];) {
+      const int64_t want = chunks.empty() ? std::max<int64_t>(c->chunk_reads / 8, 1024) : c->chunk_reads;
+      const int64_t cnt = std::min<int64_t>(want, fh->start[f + 1] - i0);
+      chunks.push_back(Chunk{i0, cnt, first_ordinal + (i0 - fh->start[f]), f});
+      i0 += cnt;
+    }
   const int64_t nchunks = (int64_t)chunks.size();
   auto stage_chunk = [&](int64_t ci) -> int {           // pack chunk ci into its staging buffer and start its H2D
     const int64_t i0 = chunks[ci].i0, i1 = i0 + chunks[ci].cnt;
@@ -188,6 +207,12 @@ int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool
     pack_range(i0, i1, hr.seqs, hr.seq_off, h_off, pb.as<uint32_t>());
     CATT_CUDA(cudaMemcpyAsync(dr.words + h_off[i0], pb.p, words * sizeof(uint32_t), cudaMemcpyHostToDevice, cs));
     CATT_CUDA(cudaEventRecord(c->ev_h2d[ci & 1], cs));
+    if (info) info->bytes_h2d += (int64_t)(words * sizeof(uint32_t));
+    if (d_quals && hr.seq_off[i1] > hr.seq_off[i0]) {     // pageable source: staged by the driver while the previous chunk computes
+      if (info) info->bytes_h2d += hr.seq_off[i1] - hr.seq_off[i0];
+      CATT_CUDA(cudaMemcpyAsync(d_quals + hr.seq_off[i0], hr.quals + hr.seq_off[i0], (size_t)(hr.seq_off[i1] - hr.seq_off[i0]),
+                                cudaMemcpyHostToDevice, cs));
+    }
     return CATT_OK;
   };
   if (nchunks > 0 && (rc = stage_chunk(0))) return rc;
@@ -210,6 +235,7 @@ int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool
     }
   }
   CATT_CUDA(cudaStreamSynchronize(st));
+  CATT_CUDA(cudaStreamSynchronize(cs));
   if (info && align) {
     info->ms_seed += local.ms_seed; info->ms_seed_kernel += local.ms_seed_kernel; info->ms_sw += local.ms_sw; info->ms_select += local.ms_select;
     info->cand_v += local.cand_v; info->cand_j += local.cand_j; info->cells_v += local.cells_v; info->cells_j += local.cells_j;
@@ -286,12 +312,13 @@ int run_all(catt_ctx* c, const HostReads& hr, const std::vector<int64_t>& file_s
   Trace tr;
   R->info.n_reads = hr.n;
   DeviceReads dr;
+  DeviceQuals dq;
   FileHits fh;
   fh.start = file_start;
-  int rc = stage_a_stream(c, hr, 0, true, &dr, &fh, &R->info, &launches);
+  int rc = stage_a_stream(c, hr, 0, true, true, &dr, &dq, &fh, &R->info, &launches);
   tr.lap("run_all: pack + H2D + align (pipelined)");
   if (rc == CATT_OK && c->keep_records) rc = download_records(c, hr.n, R.get());
-  if (rc == CATT_OK) rc = stage_b(c, hr, dr.view(), fh, R.get(), &launches);
+  if (rc == CATT_OK) rc = stage_b(c, hr, dr.view(), dq, fh, R.get(), &launches);
   tr.lap("run_all: stage_b");
   if (rc) return rc;
   R->info.kernel_launches = launches;
@@ -381,7 +408,7 @@ void catt_ctx_destroy(catt_ctx* c) {
   for (auto& b : c->sb) b.release();
   for (auto& b : c->pin) b.release();
   for (auto& b : c->recs_all) b.release();
-  c->rd_words.release(); c->rd_off.release(); c->rd_len.release();
+  c->rd_words.release(); c->rd_off.release(); c->rd_len.release(); c->rd_quals.release(); c->rd_seqoff.release();
   cudaFree(c->d_finder); cudaFree(c->d_dseq); cudaFree(c->d_doff);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   for (auto& row : c->ev_a) for (auto& ev : row) if (ev) cudaEventDestroy(ev);
@@ -532,7 +559,7 @@ int catt_batch_download(catt_ctx* c, catt_batch* b, catt_aln* v_out, catt_aln* j
   return CATT_OK;
 }
 
-void catt_batch_free(catt_batch* b) { if (b) { b->dr.release(); delete b; } }
+void catt_batch_free(catt_batch* b) { if (b) { b->dr.release(); b->quals.release(); b->seqoff.release(); delete b; } }
 
 int catt_align_shard(catt_ctx* c, int64_t n, const char* seqs, const int64_t* seq_off, int64_t first_ordinal, catt_aln* v_out,
                      catt_aln* j_out) {
@@ -545,7 +572,7 @@ int catt_align_shard(catt_ctx* c, int64_t n, const char* seqs, const int64_t* se
   int launches = 0;
   FileHits fh;
   fh.start = {0, n};
-  int rc = stage_a_stream(c, hr, first_ordinal, true, &dr, &fh, &info, &launches);
+  int rc = stage_a_stream(c, hr, first_ordinal, true, false, &dr, nullptr, &fh, &info, &launches);
   if (rc || n == 0) return rc;
   if (v_out) CATT_CUDA(cudaMemcpy(v_out, c->recs_all[0].p, n * sizeof(catt_aln), cudaMemcpyDeviceToHost));
   if (j_out) CATT_CUDA(cudaMemcpy(j_out, c->recs_all[1].p, n * sizeof(catt_aln), cudaMemcpyDeviceToHost));
@@ -568,7 +595,8 @@ int catt_assemble(catt_ctx* c, int64_t n, const char* names, const int64_t* name
   int launches = 0;
   FileHits fh;
   fh.start = {0, n};
-  int rc = stage_a_stream(c, hr, 0, false, &dr, &fh, &R->info, &launches);      // pack + upload only
+  DeviceQuals dq;
+  int rc = stage_a_stream(c, hr, 0, false, true, &dr, &dq, &fh, &R->info, &launches);      // pack + upload only
   fh.single(n, vh, jh);
   if (rc) return rc;
   if (n) {
@@ -577,7 +605,7 @@ int catt_assemble(catt_ctx* c, int64_t n, const char* names, const int64_t* name
     CATT_CUDA(cudaStreamSynchronize(c->stream));
   }
   if (c->keep_records) { R->rec[0].assign(v_recs, v_recs + n); R->rec[1].assign(j_recs, j_recs + n); }
-  rc = stage_b(c, hr, dr.view(), fh, R.get(), &launches);
+  rc = stage_b(c, hr, dr.view(), dq, fh, R.get(), &launches);
   if (rc) return rc;
   R->info.kernel_launches = launches;
   *out = R.release();
@@ -601,7 +629,19 @@ int catt_batch_assemble(catt_ctx* c, catt_batch* b, const char* names, const int
   int launches = (int)b->info.kernel_launches;
   FileHits fh;
   fh.single(n, b->info.v_hits, b->info.j_hits);
-  rc = stage_b(c, hr, b->dr.view(), fh, R.get(), &launches);
+  if (!b->have_quals && n > 0) {                       // first assemble of this batch: the quality strings join the resident input
+    if ((rc = b->seqoff.ensure((size_t)(n + 1) * sizeof(int64_t)))) return rc;
+    CATT_CUDA(cudaMemcpyAsync(b->seqoff.p, seq_off, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    if (quals) {
+      if ((rc = b->quals.ensure((size_t)seq_off[n] + 16))) return rc;
+      CATT_CUDA(cudaMemcpyAsync(b->quals.p, quals, (size_t)seq_off[n], cudaMemcpyHostToDevice, c->stream));
+    }
+    CATT_CUDA(cudaStreamSynchronize(c->stream));
+    b->have_quals = true;
+  }
+  DeviceQuals dq;
+  dq.seq_off = b->seqoff.as<int64_t>(); dq.quals = quals ? b->quals.as<char>() : nullptr;
+  rc = stage_b(c, hr, b->dr.view(), dq, fh, R.get(), &launches);
   if (rc) return rc;
   R->info.kernel_launches = launches;
   *out = R.release();

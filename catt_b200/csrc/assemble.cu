@@ -248,6 +248,101 @@ __global__ void partial_kernel(int64_t n_items, const uint32_t* __restrict__ pfl
   desc[m].xi = (int32_t)xpos[m];
 }
 
+// ---- Myread strings on the device ------------------------------------------------------------------------------------------
+// What catt.jl:104,125-126,302-304 (assign*), Jtool.jl:364-365,382-383 (finder! slices qual) and catt.jl:378-379,420-421
+// (extension pads qual with 'G') leave in Myread.seq / Myread.qual, written straight into the result arenas.
+struct StrSrc {
+  const OutDesc* desc; const ExtendOut* xout;     // xout == nullptr: no extension pass ran (every partial read keeps n_ext = 0)
+  const char* quals; const int64_t* seq_off;      // quals == nullptr: FASTA input, 'I' everywhere
+  int64_t M, vpart;
+};
+__device__ __forceinline__ void str_dims(const StrSrc& S, int64_t m, int* n_ext, int* c_off, int* c_len, int* slen, int* qlen, int* base_q) {
+  const OutDesc p = S.desc[m];
+  *n_ext = 0; *c_off = p.cdr3_off; *c_len = p.cdr3_len;
+  if (p.xi >= 0) {
+    if (S.xout) { const ExtendOut& x = S.xout[p.xi]; *n_ext = x.n_ext; *c_off = x.cdr3_off; *c_len = x.cdr3_len; }
+    else { *c_off = -1; *c_len = 0; }
+  }
+  *base_q = p.kind == 1 ? (p.q_start1 - 1 + max(0, (int)p.j_pad)) : p.seq_len;
+  *slen = p.seq_len + *n_ext;
+  *qlen = *c_off >= 0 ? *c_len : *base_q + *n_ext;
+}
+
+__global__ void strsize_kernel(StrSrc S, unsigned long long* __restrict__ ssz, unsigned long long* __restrict__ qsz) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m > S.M) return;
+  if (m == S.M) { ssz[m] = 0; qsz[m] = 0; return; }
+  int n_ext, c_off, c_len, slen, qlen, base_q;
+  str_dims(S, m, &n_ext, &c_off, &c_len, &slen, &qlen, &base_q);
+  ssz[m] = (unsigned long long)slen + 1; qsz[m] = (unsigned long long)qlen + 1;
+}
+
+constexpr int MW = 8;   // warps per CTA
+__global__ void __launch_bounds__(MW * 32) materialise_kernel(StrSrc S, ReadsDev reads, const unsigned long long* __restrict__ soff,
+                                                              const unsigned long long* __restrict__ qoff, char* __restrict__ seq_arena,
+                                                              char* __restrict__ qual_arena, catt_read* __restrict__ part,
+                                                              const char* host_seq, const char* host_qual) {
+  const int lane = threadIdx.x & 31;
+  const char NT[5] = {'A', 'C', 'G', 'T', 'N'};
+  for (int64_t m = (int64_t)blockIdx.x * MW + (threadIdx.x >> 5); m < S.M; m += (int64_t)gridDim.x * MW) {
+    const OutDesc p = S.desc[m];
+    int n_ext, c_off, c_len, slen, qlen, base_q;
+    str_dims(S, m, &n_ext, &c_off, &c_len, &slen, &qlen, &base_q);
+    const ExtendOut* x = (p.xi >= 0 && S.xout) ? &S.xout[p.xi] : nullptr;
+    const int side = m < S.vpart ? 0 : 1;
+    const int lead = side == 1 ? n_ext : 0;                       // a left extension is prepended
+    const int len = reads.len[p.read];
+    const uint32_t* __restrict__ w = reads.words + reads.off[p.read];
+    const uint32_t* __restrict__ nm = w + read_base_words(len);
+    char* s = seq_arena + soff[m];
+    for (int i = lane; i <= slen; i += 32) {
+      char ch = 0;
+      if (i < slen) {
+        const int b = i - lead;
+        if (b >= 0 && b < p.seq_len) {
+          const int pos0 = p.seq_off + b, pp = p.strand ? len - 1 - pos0 : pos0;
+          uint32_t code = (w[pp >> 4] >> ((pp & 15) * 2)) & 3u;
+          if (p.strand) code = 3u - code;
+          if ((nm[pp >> 5] >> (pp & 31)) & 1u) code = 4u;
+          ch = NT[code];
+        } else {
+          const int e = b < 0 ? n_ext - 1 - i : b - p.seq_len;   // reverse(ext) * seq  |  seq * ext
+          ch = NT[(x->ext2[e >> 4] >> (2 * (e & 15))) & 3u];
+        }
+      }
+      s[i] = ch;
+    }
+    // quality: 'G' x lead | base part | 'G' x (n_ext - lead), sliced to the CDR3 range when one was found
+    const int qfull = base_q + n_ext;
+    const int real_lo = lead, real_hi = lead + (p.kind == 1 ? min(base_q, p.q_start1 - 1) : base_q);
+    const int src0 = p.kind == 1 ? 0 : p.seq_off;
+    const int a0 = c_off >= 0 ? c_off : 0;
+    const char* rq = S.quals ? S.quals + S.seq_off[p.read] : nullptr;
+    char* q = qual_arena + qoff[m];
+    for (int i = lane; i <= qlen; i += 32) {
+      char ch = 0;
+      if (i < qlen) {
+        const int fi = a0 + i;
+        ch = 'G';
+        if (fi >= real_lo && fi < real_hi) {
+          const int j = src0 + (fi - real_lo);
+          ch = rq ? (p.strand ? rq[len - 1 - j] : rq[j]) : 'I';
+        }
+      }
+      q[i] = ch;
+    }
+    if (lane == 0) {
+      catt_read rd;
+      rd.seq = host_seq + soff[m]; rd.qual = host_qual + qoff[m]; rd.seq_len = slen; rd.qual_len = qlen;
+      rd.v_id = p.v_id; rd.j_id = p.j_id; rd.cdr3_off = c_off; rd.cdr3_len = c_off >= 0 ? c_len : 0;
+      rd.ordinal = (int32_t)p.read; rd.able = 1;
+      rd.flags = (uint8_t)((p.kind == 0 ? 1 : p.kind == 1 ? 2 : 4) | ((c_off >= 0 && c_off + c_len > qfull) ? 8 : 0));   // 8: reference BoundsError
+      rd.pad_[0] = 0; rd.pad_[1] = 0;
+      part[m] = rd;
+    }
+  }
+}
+
 inline unsigned nblk(int64_t n, int b = 256) { return (unsigned)std::max<int64_t>(1, (n + b - 1) / b); }
 
 template <class T> int ensure(catt_ctx* c, int slot, int64_t count, T** out) {
@@ -277,7 +372,7 @@ struct BlockCache {
   struct Ent { void* p; size_t cap; };
   std::vector<Ent> free_list;
   size_t held = 0;
-  ~BlockCache() { for (auto& e : free_list) free(e.p); }
+  ~BlockCache() { for (auto& e : free_list) free(e.p); }     // process exit: the CUDA context may be gone, no unregister
 };
 BlockCache g_blocks;
 constexpr size_t BLOCK_SMALL = 1 << 20;            // below this plain malloc/free is fine
@@ -305,6 +400,8 @@ void* block_get(size_t bytes, size_t* cap) {
   void* p = nullptr;
   if (posix_memalign(&p, 2u << 20, want) != 0) return nullptr;
   madvise(p, want, MADV_HUGEPAGE);
+  memset(p, 0, want);                                    // touch once, then pin: the arenas arrive as bulk device->host copies
+  if (cudaHostRegister(p, want, cudaHostRegisterPortable) != cudaSuccess) cudaGetLastError();   // unpinned still works, slower
   *cap = want;
   return p;
 }
@@ -313,7 +410,11 @@ void block_put(void* p, size_t cap) {
   if (!p) return;
   if (cap < BLOCK_SMALL) { free(p); return; }
   std::lock_guard<std::mutex> lk(g_blocks.mu);
-  if (g_blocks.held + cap > BLOCK_KEEP_MAX || g_blocks.free_list.size() >= 16) { free(p); return; }
+  if (g_blocks.held + cap > BLOCK_KEEP_MAX || g_blocks.free_list.size() >= 16) {
+    if (cudaHostUnregister(p) != cudaSuccess) cudaGetLastError();
+    free(p);
+    return;
+  }
   g_blocks.free_list.push_back({p, cap});
   g_blocks.held += cap;
 }
@@ -329,7 +430,7 @@ const StrLut SLUT;
 
 }  // namespace
 
-int stage_b(catt_ctx* c, const HostReads& hr, const ReadsDev& reads, const FileHits& fh, catt_result* R, int* launches) {
+int stage_b(catt_ctx* c, const HostReads& hr, const ReadsDev& reads, const DeviceQuals& dq, const FileHits& fh, catt_result* R, int* launches) {
   catt_info& info = R->info;
   const int64_t n = hr.n;
   info.kmer = c->kmer;
@@ -358,6 +459,7 @@ int stage_b(catt_ctx* c, const HostReads& hr, const ReadsDev& reads, const FileH
   if (tot_hits > 0) {
     CATT_CUDA(cudaMemcpyAsync(d_names, hr.names, (size_t)name_bytes, cudaMemcpyHostToDevice, st));
     CATT_CUDA(cudaMemcpyAsync(d_name_off, hr.name_off, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    info.bytes_h2d += name_bytes + (n + 1) * 8;
   }
   unsigned long long *keys_a, *sorted[2];
   uint32_t *flag, *kpos[2], *ord_idx[2], *ord_flag[2], *opos[2], *pair_a, *pair_b;
@@ -527,10 +629,6 @@ int stage_b(catt_ctx* c, const HostReads& hr, const ReadsDev& reads, const FileH
   // ---- K6/K7: k-mer table + extension of the partial reads
   ExtendOut* xout = nullptr;
   const bool run_pool = M > 0 && k <= 31 && n_partial > 0;
-  if ((rc = c->pin[PIN_DESC].ensure((size_t)std::max<int64_t>(M, 1) * sizeof(OutDesc))) ||
-      (rc = c->pin[PIN_XOUT].ensure((size_t)std::max<int64_t>(n_partial, 1) * sizeof(ExtendOut)))) return rc;
-  OutDesc* hdesc = c->pin[PIN_DESC].as<OutDesc>();
-  ExtendOut* hxout = c->pin[PIN_XOUT].as<ExtendOut>();
   CATT_CUDA(cudaEventRecord(c->ev[5], st));
   if (run_pool) {
     uint64_t slots = 1024;
@@ -545,105 +643,61 @@ int stage_b(catt_ctx* c, const HostReads& hr, const ReadsDev& reads, const FileH
     if ((rc = launch_pool(reads, pitems, M, k, tab, st, launches))) return rc;
     CATT_CUDA(cudaEventRecord(c->ev[1], st));
     if ((rc = launch_extend(reads, c->d_finder, pitems, partial_idx, n_partial, k, tab, xout, reinterpret_cast<uint32_t*>(cnt + C_RESCUED), st, launches))) return rc;
-    CATT_CUDA(cudaMemcpyAsync(hxout, xout, (size_t)n_partial * sizeof(ExtendOut), cudaMemcpyDeviceToHost, st));
   }
   CATT_CUDA(cudaEventRecord(c->ev[6], st));
-  if (M > 0) CATT_CUDA(cudaMemcpyAsync(hdesc, desc, (size_t)M * sizeof(OutDesc), cudaMemcpyDeviceToHost, st));
+  // ---- the Myread strings: sizes -> offsets (scans) -> one warp per read writes both strings and the catt_read entry; the
+  //      arenas go to the host as three bulk copies into pinned result blocks
+  StrSrc S{desc, xout, dq.quals, dq.seq_off, M, info.vpart};
+  unsigned long long *ssz, *qsz, *soff, *qoff;
+  if ((rc = ensure(c, SB_SSZ, M + 1, &ssz)) || (rc = ensure(c, SB_QSZ, M + 1, &qsz)) || (rc = ensure(c, SB_SOFF, M + 1, &soff)) ||
+      (rc = ensure(c, SB_QOFF, M + 1, &qoff))) return rc;
+  strsize_kernel<<<nblk(M + 1), 256, 0, st>>>(S, ssz, qsz);
+  CATT_CUDA(cudaGetLastError());
+  for (int which = 0; which < 2; which++) {
+    size_t need = 0;
+    CATT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, which ? qsz : ssz, which ? qoff : soff, M + 1, st));
+    if ((rc = ensure_cub(c, need))) return rc;
+    need = c->sb[SB_CUB].cap;
+    CATT_CUDA(cub::DeviceScan::ExclusiveSum(c->sb[SB_CUB].p, need, which ? qsz : ssz, which ? qoff : soff, M + 1, st));
+  }
+  *launches += 5;
   CATT_CUDA(cudaMemcpyAsync(hcnt, cnt, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-  CATT_CUDA(cudaEventRecord(c->ev[7], st));
+  CATT_CUDA(cudaMemcpyAsync(hcnt + C_COUNT, soff + M, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CATT_CUDA(cudaMemcpyAsync(hcnt + C_COUNT + 1, qoff + M, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   CATT_CUDA(cudaStreamSynchronize(st));
-  { float a = 0, b = 0; cudaEventElapsedTime(&a, c->ev[5], c->ev[6]); cudaEventElapsedTime(&b, c->ev[6], c->ev[7]); info.ms_pool += a; info.ms_d2h += b; }
+  { float a = 0; cudaEventElapsedTime(&a, c->ev[5], c->ev[6]); info.ms_pool += a; }
   if (run_pool) { float a = 0; cudaEventElapsedTime(&a, c->ev[0], c->ev[1]); info.ms_pool_kernel += a; }
-  if (!run_pool) for (int64_t x = 0; x < n_partial; x++) { hxout[x].n_ext = 0; hxout[x].cdr3_off = -1; hxout[x].cdr3_len = 0; hxout[x].able = 1; }
   info.rescued += (int64_t)(uint32_t)hcnt[C_RESCUED];
-  tr.lap("B: pool + extend + D2H");
-
-  // ---- materialise the Myread strings: sizes, prefix sums, parallel fill into two flat arenas
+  tr.lap("B: pool + extend + string sizes");
   const double t2 = now_ms();
-  std::vector<int64_t> soff((size_t)M + 1, 0), qoff((size_t)M + 1, 0);
-  #pragma omp parallel for schedule(static)
-  for (int64_t m = 0; m < M; m++) {
-    const OutDesc& p = hdesc[m];
-    int n_ext = 0, c_off = p.cdr3_off, c_len = p.cdr3_len;
-    if (p.xi >= 0) { const ExtendOut& x = hxout[p.xi]; n_ext = x.n_ext; c_off = x.cdr3_off; c_len = x.cdr3_len; }
-    const int base_q = p.kind == 1 ? (p.q_start1 - 1 + std::max(0, (int)p.j_pad)) : p.seq_len;
-    soff[m + 1] = p.seq_len + n_ext + 1;
-    qoff[m + 1] = (c_off >= 0 ? c_len : base_q + n_ext) + 1;
-  }
-  for (int64_t m = 0; m < M; m++) { soff[m + 1] += soff[m]; qoff[m + 1] += qoff[m]; }
-  tr.lap("B: string sizes");
-  R->seq_arena = (char*)block_get((size_t)soff[M] + 1, &R->cap_seq);
-  R->qual_arena = (char*)block_get((size_t)qoff[M] + 1, &R->cap_qual);
+  const size_t seq_bytes = (size_t)hcnt[C_COUNT] + 1, qual_bytes = (size_t)hcnt[C_COUNT + 1] + 1, part_bytes = (size_t)std::max<int64_t>(M, 1) * sizeof(catt_read);
+  R->seq_arena = (char*)block_get(seq_bytes, &R->cap_seq);
+  R->qual_arena = (char*)block_get(qual_bytes, &R->cap_qual);
+  R->part[0] = (catt_read*)block_get(part_bytes, &R->cap_part[0]);
+  if (!R->seq_arena || !R->qual_arena || !R->part[0]) { set_error("out of host memory for the result"); return CATT_E_LIMIT; }
   R->npart[0] = info.vpart; R->npart[1] = info.jpart;
-  R->part[0] = (catt_read*)block_get((size_t)std::max<int64_t>(info.vpart, 1) * sizeof(catt_read), &R->cap_part[0]);
-  R->part[1] = (catt_read*)block_get((size_t)std::max<int64_t>(info.jpart, 1) * sizeof(catt_read), &R->cap_part[1]);
-  if (!R->seq_arena || !R->qual_arena || !R->part[0] || !R->part[1]) { set_error("out of host memory for the result"); return CATT_E_LIMIT; }
-  tr.lap("B: result blocks");
-  static const char NT[] = "ACGT";
-  #pragma omp parallel for schedule(static)
-  for (int64_t m = 0; m < M; m++) {
-    // the lists are in alignment-score order, so the reads are visited at random: prefetch two levels ahead
-    // (offset table, then the sequence / quality lines) or every iteration stalls on ~6 DRAM misses
-    if (m + 32 < M) __builtin_prefetch(&hr.seq_off[hdesc[m + 32].read]);
-    if (m + 16 < M) {
-      const OutDesc& pn = hdesc[m + 16];
-      const int64_t o = hr.seq_off[pn.read] + (pn.strand ? 0 : pn.seq_off);
-      __builtin_prefetch(hr.seqs + o); __builtin_prefetch(hr.seqs + o + 64); __builtin_prefetch(hr.seqs + o + 128);
-      if (hr.quals) { __builtin_prefetch(hr.quals + o); __builtin_prefetch(hr.quals + o + 64); __builtin_prefetch(hr.quals + o + 128); }
-    }
-    const OutDesc& p = hdesc[m];
-    const int side = m < info.vpart ? 0 : 1;
-    const int len = (int)(hr.seq_off[p.read + 1] - hr.seq_off[p.read]);
-    const unsigned char* rs = reinterpret_cast<const unsigned char*>(hr.seqs + hr.seq_off[p.read]);
-    const char* rq = hr.quals ? hr.quals + hr.seq_off[p.read] : nullptr;
-    int n_ext = 0, c_off = p.cdr3_off, c_len = p.cdr3_len;
-    const ExtendOut* x = nullptr;
-    if (p.xi >= 0) { x = &hxout[p.xi]; n_ext = x->n_ext; c_off = x->cdr3_off; c_len = x->cdr3_len; }
-    auto ext_at = [&](int i) { return NT[(x->ext2[i >> 4] >> (2 * (i & 15))) & 3u]; };
-    const int lead = side == 1 ? n_ext : 0;                       // a left extension is prepended
-    char* s = R->seq_arena + soff[m];
-    for (int i = 0; i < lead; i++) s[i] = ext_at(n_ext - 1 - i);                  // reverse(ext) * seq
-    if (!p.strand) for (int i = 0; i < p.seq_len; i++) s[lead + i] = SLUT.fwd[rs[p.seq_off + i]];
-    else for (int i = 0; i < p.seq_len; i++) s[lead + i] = SLUT.rc[rs[len - 1 - p.seq_off - i]];
-    if (side == 0) for (int i = 0; i < n_ext; i++) s[p.seq_len + i] = ext_at(i);
-    const int slen = p.seq_len + n_ext;
-    s[slen] = 0;
-    // quality: the Myread's string before finder! slices it = 'G' x lead | base part | 'G' x (n_ext - lead), where the
-    // base part is qual[seq_off ..] (V side, both-mapped) or qual[1:start-1] * 'G'^pad (J side, catt.jl:126), taken
-    // from the SAM-oriented quality string; emitted in runs (memset / memcpy / reversed copy), not per character
-    const int base_q = p.kind == 1 ? (p.q_start1 - 1 + std::max(0, (int)p.j_pad)) : p.seq_len;
-    const int qfull = base_q + n_ext;
-    const int real_lo = lead;                                                     // [real_lo, real_hi): characters that come from rq
-    const int real_hi = lead + (p.kind == 1 ? std::min(base_q, p.q_start1 - 1) : base_q);
-    const int src0 = p.kind == 1 ? 0 : p.seq_off;                                 // SAM-oriented index of the first real character
-    char* q = R->qual_arena + qoff[m];
-    uint8_t flags = (uint8_t)(p.kind == 0 ? 1 : p.kind == 1 ? 2 : 4);
-    const int a0 = c_off >= 0 ? c_off : 0;                                        // rd.qual = rd.qual[range] (Jtool.jl:365,383)
-    const int qlen = c_off >= 0 ? c_len : qfull;
-    if (c_off >= 0 && c_off + c_len > qfull) flags |= 8;                          // reference: BoundsError
-    {
-      const int lo = std::max(a0, real_lo), hi = std::min(a0 + qlen, real_hi);
-      if (hi > lo) {
-        if (lo > a0) memset(q, 'G', (size_t)(lo - a0));
-        const int j0 = src0 + (lo - real_lo), cntr = hi - lo;
-        char* d = q + (lo - a0);
-        if (!rq) memset(d, 'I', (size_t)cntr);
-        else if (!p.strand) memcpy(d, rq + j0, (size_t)cntr);
-        else { const char* sp = rq + (len - 1 - j0); for (int i = 0; i < cntr; i++) d[i] = sp[-i]; }
-        if (a0 + qlen > hi) memset(q + (hi - a0), 'G', (size_t)(a0 + qlen - hi));
-      } else {
-        memset(q, 'G', (size_t)qlen);
-      }
-    }
-    q[qlen] = 0;
-    catt_read rd{};
-    rd.seq = s; rd.qual = q; rd.seq_len = slen; rd.qual_len = qlen;
-    rd.v_id = p.v_id; rd.j_id = p.j_id; rd.cdr3_off = c_off; rd.cdr3_len = c_off >= 0 ? c_len : 0;
-    rd.ordinal = (int32_t)p.read; rd.able = 1; rd.flags = flags;
-    R->part[side][side == 0 ? m : m - info.vpart] = rd;
-  }
+  R->part[1] = R->part[0] + info.vpart;             // one block: Vpart entries, then Jpart entries
   info.ms_host += now_ms() - t2;
-  tr.lap("B: materialise");
+  tr.lap("B: result blocks");
+  if (M > 0) {
+    char *d_seq, *d_qual; catt_read* d_part;
+    if ((rc = ensure(c, SB_OUT_SEQ, (int64_t)seq_bytes, &d_seq)) || (rc = ensure(c, SB_OUT_QUAL, (int64_t)qual_bytes, &d_qual)) ||
+        (rc = ensure(c, SB_OUT_PART, M, &d_part))) return rc;
+    CATT_CUDA(cudaEventRecord(c->ev[5], st));
+    const int grid = (int)std::min<int64_t>((M + MW - 1) / MW, (int64_t)c->sm_count * 16);
+    materialise_kernel<<<grid, MW * 32, 0, st>>>(S, reads, soff, qoff, d_seq, d_qual, d_part, R->seq_arena, R->qual_arena);
+    CATT_CUDA(cudaGetLastError());
+    *launches += 1;
+    CATT_CUDA(cudaEventRecord(c->ev[6], st));
+    CATT_CUDA(cudaMemcpyAsync(R->seq_arena, d_seq, seq_bytes - 1, cudaMemcpyDeviceToHost, st));
+    CATT_CUDA(cudaMemcpyAsync(R->qual_arena, d_qual, qual_bytes - 1, cudaMemcpyDeviceToHost, st));
+    CATT_CUDA(cudaMemcpyAsync(R->part[0], d_part, (size_t)M * sizeof(catt_read), cudaMemcpyDeviceToHost, st));
+    CATT_CUDA(cudaEventRecord(c->ev[7], st));
+    CATT_CUDA(cudaStreamSynchronize(st));
+    info.bytes_d2h += (int64_t)(seq_bytes + qual_bytes - 2) + M * (int64_t)sizeof(catt_read) + (2 + nfiles) * C_COUNT * 8;
+    { float a = 0, b2 = 0; cudaEventElapsedTime(&a, c->ev[5], c->ev[6]); cudaEventElapsedTime(&b2, c->ev[6], c->ev[7]); info.ms_strings += a; info.ms_d2h += b2; }
+  }
+  tr.lap("B: strings + D2H");
   return CATT_OK;
 }
 

@@ -55,7 +55,7 @@ struct PinBuf {
 enum {
   SB_NAMES = 0, SB_NAME_OFF, SB_SLOT_OF, SB_OWNER, SB_MINV, SB_MINJ, SB_KEYS_A, SB_SORT_V, SB_SORT_J, SB_FLAG, SB_KPOS_V,
   SB_KPOS_J, SB_ORD_IDX_V, SB_ORD_IDX_J, SB_ORD_FLAG_V, SB_ORD_FLAG_J, SB_OPOS_V, SB_OPOS_J, SB_PAIR_A, SB_PAIR_B, SB_PKEY_A, SB_PKEY_B, SB_ITEMS,
-  SB_EOUT, SB_KFLAG, SB_KFLAG1, SB_KPOS2, SB_KPOS3, SB_PFLAG, SB_XPOS, SB_TAB_KEYS, SB_TAB_VALS, SB_PITEMS, SB_PARTIAL, SB_XOUT, SB_DESC, SB_CNT, SB_CUB,
+  SB_EOUT, SB_KFLAG, SB_KFLAG1, SB_KPOS2, SB_KPOS3, SB_PFLAG, SB_XPOS, SB_TAB_KEYS, SB_TAB_VALS, SB_PITEMS, SB_PARTIAL, SB_XOUT, SB_DESC, SB_SSZ, SB_QSZ, SB_SOFF, SB_QOFF, SB_OUT_SEQ, SB_OUT_QUAL, SB_OUT_PART, SB_CNT, SB_CUB,
   SB_COUNT
 };
 enum { PIN_PACK0 = 0, PIN_PACK1, PIN_OFF, PIN_LEN, PIN_CNT, PIN_DESC, PIN_XOUT, PIN_COUNT };
@@ -74,6 +74,7 @@ struct catt_ctx {
   char* d_dseq = nullptr; int32_t* d_doff = nullptr;
   catt::AlignBuffers ab[2];
   DevBuf rd_words, rd_off, rd_len;        // packed reads of the sample being run (catt_run_*, catt_assemble)
+  DevBuf rd_quals, rd_seqoff;             // its quality strings (as given) and int64 offsets, for the string kernel
   DevBuf recs_all[2];                     // one catt_aln per read and reference set, for the whole sample
   DevBuf sb[SB_COUNT];
   PinBuf pin[PIN_COUNT];
@@ -82,7 +83,11 @@ struct catt_ctx {
   cudaEvent_t ev_h2d[2]{};                // staging buffer c&1 has reached the device
 };
 
+// quality strings of the sample in HBM (uploaded under the Stage A kernels); quals == nullptr for FASTA input
+struct DeviceQuals { const char* quals = nullptr; const int64_t* seq_off = nullptr; };
+
 struct catt_batch {
+  DevBuf quals, seqoff; bool have_quals = false;
   DeviceReads dr;
   int64_t first_ordinal = 0;
   catt_info info{};
@@ -104,7 +109,7 @@ struct catt_result {
   char* seq_arena = nullptr; char* qual_arena = nullptr;     // every Myread string, NUL-terminated, back to back
   size_t cap_part[2] = {0, 0}, cap_seq = 0, cap_qual = 0;
   ~catt_result() {
-    catt::block_put(part[0], cap_part[0]); catt::block_put(part[1], cap_part[1]);
+    catt::block_put(part[0], cap_part[0]);      // part[1] points into the same block
     catt::block_put(seq_arena, cap_seq); catt::block_put(qual_arena, cap_qual);
   }
 };
@@ -124,5 +129,5 @@ struct FileHits {
   std::vector<int64_t> start, v, j;
   void single(int64_t n, int64_t vh, int64_t jh) { start = {0, n}; v = {vh}; j = {jh}; }
 };
-int stage_b(catt_ctx* c, const HostReads& hr, const ReadsDev& reads, const FileHits& fh, catt_result* R, int* launches);
+int stage_b(catt_ctx* c, const HostReads& hr, const ReadsDev& reads, const DeviceQuals& dq, const FileHits& fh, catt_result* R, int* launches);
 }  // namespace catt

@@ -109,6 +109,8 @@ typedef struct catt_info {
   double ms_pack;             /* host time packing reads that was NOT hidden under kernels */
   double ms_seed_kernel;      /* seed_kernel alone (ms_seed also holds the task scan / expansion) */
   double ms_pool_kernel;      /* pool_kernel alone (ms_pool also holds the extension kernel) */
+  double ms_strings;          /* the kernel that writes the Myread strings into the result arenas */
+  int64_t bytes_h2d, bytes_d2h; /* bytes the library copied host->device / device->host for this result */
 } catt_info;
 
 /* ---- lifecycle --------------------------------------------------------------------------------------------- */
