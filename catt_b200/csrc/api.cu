@@ -8,7 +8,9 @@
 #include <string>
 #include <vector>
 
+#include <fcntl.h>
 #include <omp.h>
+#include <unistd.h>
 
 #include "host_types.h"
 
@@ -132,19 +134,26 @@ int ensure_recs(catt_ctx* c, int64_t n) {
   return CATT_OK;
 }
 
-// Stage A over reads that are already resident: chunk by chunk (bounded scratch), records into ctx->recs_all
-int stage_a_resident(catt_ctx* c, const DeviceReads& dr, int64_t first_ordinal, catt_info* info, int* launches) {
+// Stage A over reads that are already resident: chunk by chunk (bounded scratch), records into ctx->recs_all.  `fh->start`
+// lists the input files: chunks never straddle a file and the read ordinal restarts at every file.
+int stage_a_resident(catt_ctx* c, const DeviceReads& dr, int64_t first_ordinal, FileHits* fh, catt_info* info, int* launches) {
   int rc;
   if ((rc = ensure_recs(c, dr.n))) return rc;
-  for (int64_t i0 = 0; i0 < dr.n; i0 += c->chunk_reads) {
-    const int64_t cnt = std::min<int64_t>(c->chunk_reads, dr.n - i0);
-    const ReadsDev rv = dr.view(i0, cnt);
-    for (int which = 0; which < 2; which++)
-      if ((rc = align_queue(c, which, rv, c->recs_all[which].as<catt_aln>() + i0, first_ordinal + i0, launches))) return rc;
-    CATT_CUDA(cudaStreamSynchronize(c->stream));
-    for (int which = 0; which < 2; which++)
-      if ((rc = align_finish(c, which, rv, c->recs_all[which].as<catt_aln>() + i0, first_ordinal + i0, info, launches))) return rc;
-  }
+  const int nfiles = (int)fh->start.size() - 1;
+  fh->v.assign(nfiles, 0); fh->j.assign(nfiles, 0);
+  for (int f = 0; f < nfiles; f++)
+    for (int64_t i0 = fh->start[f]; i0 < fh->start[f + 1]; i0 += c->chunk_reads) {
+      const int64_t cnt = std::min<int64_t>(c->chunk_reads, fh->start[f + 1] - i0);
+      const int64_t ord = first_ordinal + (i0 - fh->start[f]);
+      const ReadsDev rv = dr.view(i0, cnt);
+      for (int which = 0; which < 2; which++)
+        if ((rc = align_queue(c, which, rv, c->recs_all[which].as<catt_aln>() + i0, ord, launches))) return rc;
+      CATT_CUDA(cudaStreamSynchronize(c->stream));
+      const int64_t v0 = info->v_hits, j0 = info->j_hits;
+      for (int which = 0; which < 2; which++)
+        if ((rc = align_finish(c, which, rv, c->recs_all[which].as<catt_aln>() + i0, ord, info, launches))) return rc;
+      fh->v[f] += info->v_hits - v0; fh->j[f] += info->j_hits - j0;
+    }
   return CATT_OK;
 }
 
@@ -306,6 +315,105 @@ int download_records(catt_ctx* c, int64_t n, catt_result* R) {
   return CATT_OK;
 }
 
+// ---- catt_run_file(s) without host parsing: the raw FASTQ text goes to HBM and ingest.cu indexes, validates and packs it there.
+// Returns CATT_OK with *handled = false when the input is not strict 4-line FASTQ (FASTA, wrapped or blank lines, ...): the host
+// parser then takes over (and owns the error messages).
+bool read_whole(const char* path, std::string* gz_out, int64_t* plain_size, bool* is_gz) {
+  FILE* f = fopen(path, "rb");
+  if (!f) return false;
+  unsigned char magic[2] = {0, 0};
+  const size_t got = fread(magic, 1, 2, f);
+  *is_gz = got == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+  if (!*is_gz) { fseeko(f, 0, SEEK_END); *plain_size = (int64_t)ftello(f); }
+  fclose(f);
+  if (*is_gz) return slurp_file(path, *gz_out);
+  return true;
+}
+
+int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_result** out, bool* handled) {
+  *handled = false;
+  Trace tr;
+  std::vector<std::string> gz((size_t)nfiles);
+  std::vector<int64_t> size((size_t)nfiles, 0), tpos((size_t)nfiles + 1, 0);
+  std::vector<char> isgz((size_t)nfiles, 0);
+  for (int f = 0; f < nfiles; f++) {
+    bool g = false;
+    if (!read_whole(paths[f], &gz[f], &size[f], &g)) { set_error("cannot read %s", paths[f]); return CATT_E_IO; }
+    isgz[f] = g;
+    if (g) size[f] = (int64_t)gz[f].size();
+    tpos[f + 1] = tpos[f] + size[f] + 16;                          // room for the terminating newline, 16-byte aligned starts
+    tpos[f + 1] = (tpos[f + 1] + 15) & ~(int64_t)15;
+  }
+  int rc;
+  if ((rc = c->pin[PIN_TEXT].ensure((size_t)tpos[nfiles] + 16)) || (rc = c->rd_text.ensure((size_t)tpos[nfiles] + 16))) return rc;
+  char* h = c->pin[PIN_TEXT].as<char>();
+  char* d_text = c->rd_text.as<char>();
+  std::vector<int64_t> tend((size_t)nfiles, 0);
+  for (int f = 0; f < nfiles; f++) {
+    char* dst = h + tpos[f];
+    if (isgz[f]) {
+      memcpy(dst, gz[f].data(), (size_t)size[f]);
+      std::string().swap(gz[f]);
+    } else {
+      const int fd = open(paths[f], O_RDONLY);
+      if (fd < 0) { set_error("cannot read %s", paths[f]); return CATT_E_IO; }
+      const int64_t piece = 8 << 20, np = (size[f] + piece - 1) / piece;
+      bool ok = true;
+      #pragma omp parallel for schedule(dynamic, 1) reduction(&& : ok)
+      for (int64_t p = 0; p < np; p++) {
+        int64_t o = p * piece;
+        const int64_t e = std::min(size[f], o + piece);
+        while (o < e) {
+          const ssize_t r = pread(fd, dst + o, (size_t)(e - o), (off_t)o);
+          if (r <= 0) { ok = false; break; }
+          o += r;
+        }
+      }
+      close(fd);
+      if (!ok) { set_error("short read on %s", paths[f]); return CATT_E_IO; }
+    }
+    int64_t e = size[f];
+    while (e > 0 && (dst[e - 1] == '\n' || dst[e - 1] == '\r' || dst[e - 1] == ' ' || dst[e - 1] == '\t')) e--;
+    if (e == 0 || dst[0] != '@') return CATT_OK;                  // empty or not FASTQ: host path
+    dst[e++] = '\n';
+    tend[f] = tpos[f] + e;
+    CATT_CUDA(cudaMemcpyAsync(d_text + tpos[f], dst, (size_t)e, cudaMemcpyHostToDevice, c->stream));
+  }
+  tr.lap("run_files: read + H2D text");
+  std::unique_ptr<catt_result> R(new catt_result());
+  int launches = 0;
+  FileHits fh;
+  fh.start = {0};
+  int64_t n = 0;
+  uint64_t words = 0;
+  int max_len = 0;
+  for (int f = 0; f < nfiles; f++) {
+    int64_t nf = 0; uint64_t wf = 0; int fb = 0;
+    rc = ingest_fastq(c, d_text, tpos[f], tend[f], n, words, &nf, &wf, &max_len, &fb, &launches);
+    if (rc) { if (fb) return CATT_OK; return rc; }                 // fallback: *handled stays false
+    n += nf; words += wf;
+    fh.start.push_back(n);
+    R->info.bytes_h2d += tend[f] - tpos[f];
+  }
+  tr.lap("run_files: index + pack on the device");
+  R->info.n_reads = n;
+  DeviceReads dr;
+  dr.words = c->rd_words.as<uint32_t>(); dr.off = c->rd_off.as<uint32_t>(); dr.len = c->rd_len.as<int32_t>(); dr.n = n; dr.max_len = max_len;
+  if ((rc = stage_a_resident(c, dr, 0, &fh, &R->info, &launches))) return rc;
+  tr.lap("run_files: align");
+  if (c->keep_records && (rc = download_records(c, n, R.get()))) return rc;
+  NamesDev nd;
+  nd.s = d_text; nd.beg = reinterpret_cast<const int64_t*>(c->rd_name_beg.p); nd.end = reinterpret_cast<const int64_t*>(c->rd_name_end.p);
+  DeviceQuals dq;
+  dq.quals = d_text; dq.seq_off = reinterpret_cast<const int64_t*>(c->rd_qual_beg.p);
+  if ((rc = stage_b(c, n, nd, dr.view(), dq, fh, R.get(), &launches))) return rc;
+  tr.lap("run_files: stage_b");
+  R->info.kernel_launches = launches;
+  *out = R.release();
+  *handled = true;
+  return CATT_OK;
+}
+
 int run_all(catt_ctx* c, const HostReads& hr, const std::vector<int64_t>& file_start, catt_result** out) {
   std::unique_ptr<catt_result> R(new catt_result());
   int launches = 0;
@@ -318,7 +426,9 @@ int run_all(catt_ctx* c, const HostReads& hr, const std::vector<int64_t>& file_s
   int rc = stage_a_stream(c, hr, 0, true, true, &dr, &dq, &fh, &R->info, &launches);
   tr.lap("run_all: pack + H2D + align (pipelined)");
   if (rc == CATT_OK && c->keep_records) rc = download_records(c, hr.n, R.get());
-  if (rc == CATT_OK) rc = stage_b(c, hr, dr.view(), dq, fh, R.get(), &launches);
+  NamesDev nd;
+  if (rc == CATT_OK) rc = upload_names(c, hr.n, hr.names, hr.name_off, &nd, &R->info);
+  if (rc == CATT_OK) rc = stage_b(c, hr.n, nd, dr.view(), dq, fh, R.get(), &launches);
   tr.lap("run_all: stage_b");
   if (rc) return rc;
   R->info.kernel_launches = launches;
@@ -409,6 +519,8 @@ void catt_ctx_destroy(catt_ctx* c) {
   for (auto& b : c->pin) b.release();
   for (auto& b : c->recs_all) b.release();
   c->rd_words.release(); c->rd_off.release(); c->rd_len.release(); c->rd_quals.release(); c->rd_seqoff.release();
+  c->rd_text.release(); c->rd_nl.release(); c->rd_name_beg.release(); c->rd_name_end.release(); c->rd_seq_beg.release();
+  c->rd_qual_beg.release(); c->rd_nwords.release();
   cudaFree(c->d_finder); cudaFree(c->d_dseq); cudaFree(c->d_doff);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   for (auto& row : c->ev_a) for (auto& ev : row) if (ev) cudaEventDestroy(ev);
@@ -472,14 +584,21 @@ int catt_run_file(catt_ctx* c, const char* path, catt_result** out) {
 int catt_run_files(catt_ctx* c, int32_t nfiles, const char* const* paths, catt_result** out) {
   if (!c || !paths || !out || nfiles < 1) { set_error("catt_run_files: bad argument"); return CATT_E_ARG; }
   CATT_CUDA(cudaSetDevice(c->device));
+  if (!getenv("CATT_HOST_PARSE")) {
+    bool handled = false;
+    int rc = run_files_device(c, nfiles, paths, out, &handled);
+    if (rc || handled) return rc;
+  }
   HostReads hr;
   std::vector<int64_t> fs{0};
+  Trace tr;
   for (int f = 0; f < nfiles; f++) {
     if (!paths[f]) { set_error("catt_run_files: null path"); return CATT_E_ARG; }
     int rc = parse_fastx(paths[f], &hr);
     if (rc) return rc;
     fs.push_back(hr.n);
   }
+  tr.lap("run_files: read + parse");
   return run_all(c, hr, fs, out);
 }
 
@@ -539,7 +658,9 @@ int catt_batch_align(catt_ctx* c, catt_batch* b) {
   b->info = catt_info{};
   b->info.n_reads = b->dr.n;
   int launches = 0, rc;
-  if ((rc = stage_a_resident(c, b->dr, b->first_ordinal, &b->info, &launches))) return rc;
+  FileHits fh;
+  fh.start = {0, b->dr.n};
+  if ((rc = stage_a_resident(c, b->dr, b->first_ordinal, &fh, &b->info, &launches))) return rc;
   b->info.kernel_launches = launches;
   return CATT_OK;
 }
@@ -605,7 +726,9 @@ int catt_assemble(catt_ctx* c, int64_t n, const char* names, const int64_t* name
     CATT_CUDA(cudaStreamSynchronize(c->stream));
   }
   if (c->keep_records) { R->rec[0].assign(v_recs, v_recs + n); R->rec[1].assign(j_recs, j_recs + n); }
-  rc = stage_b(c, hr, dr.view(), dq, fh, R.get(), &launches);
+  NamesDev nd;
+  if ((rc = upload_names(c, n, names, name_off, &nd, &R->info))) return rc;
+  rc = stage_b(c, n, nd, dr.view(), dq, fh, R.get(), &launches);
   if (rc) return rc;
   R->info.kernel_launches = launches;
   *out = R.release();
@@ -641,7 +764,9 @@ int catt_batch_assemble(catt_ctx* c, catt_batch* b, const char* names, const int
   }
   DeviceQuals dq;
   dq.seq_off = b->seqoff.as<int64_t>(); dq.quals = quals ? b->quals.as<char>() : nullptr;
-  rc = stage_b(c, hr, b->dr.view(), dq, fh, R.get(), &launches);
+  NamesDev nd;
+  if ((rc = upload_names(c, n, names, name_off, &nd, &R->info))) return rc;
+  rc = stage_b(c, n, nd, b->dr.view(), dq, fh, R.get(), &launches);
   if (rc) return rc;
   R->info.kernel_launches = launches;
   *out = R.release();

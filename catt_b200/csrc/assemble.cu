@@ -35,7 +35,6 @@ constexpr unsigned FULL = 0xffffffffu;
 enum { C_NMAP_V = 0, C_NMAP_J, C_F_V, C_F_J, C_NV, C_NJ, C_NP, C_MAXNAME, C_SUM_LEN, C_SUM_NM, C_SUM_MI, C_MISMATCH, C_M, C_VPART,
        C_FULL, C_NPARTIAL, C_RESCUED, C_COUNT = 24 };
 
-struct NamesDev { const char* s; const int64_t* off; };
 
 __device__ __forceinline__ int trimmed_len(const char* s, int l) {            // bwa trim_readno
   if (l > 2 && s[l - 2] == '/' && s[l - 1] >= '0' && s[l - 1] <= '9') l -= 2;
@@ -48,8 +47,8 @@ __global__ void name_kernel(int64_t n, NamesDev nd, const catt_aln* __restrict__
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (!(rv[i].mapped || rj[i].mapped)) { slot_of[i] = INF; return; }
-  const char* s = nd.s + nd.off[i];
-  const int l = trimmed_len(s, (int)(nd.off[i + 1] - nd.off[i]));
+  const char* s = nd.s + nd.beg[i];
+  const int l = trimmed_len(s, (int)(nd.end[i] - nd.beg[i]));
   uint64_t h = 0xcbf29ce484222325ull;
   for (int k = 0; k < l; k++) { h ^= (unsigned char)s[k]; h *= 0x100000001b3ull; }
   h ^= h >> 32; h *= 0xd6e8feb86659fd93ull; h ^= h >> 32;
@@ -57,8 +56,8 @@ __global__ void name_kernel(int64_t n, NamesDev nd, const catt_aln* __restrict__
   while (true) {
     int32_t o = atomicCAS(&owner[slot], -1, (int32_t)i);
     if (o == -1 || o == (int32_t)i) break;
-    const char* t = nd.s + nd.off[o];
-    const int lt = trimmed_len(t, (int)(nd.off[o + 1] - nd.off[o]));
+    const char* t = nd.s + nd.beg[o];
+    const int lt = trimmed_len(t, (int)(nd.end[o] - nd.beg[o]));
     bool same = lt == l;
     for (int k = 0; same && k < l; k++) same = s[k] == t[k];
     if (same) break;
@@ -145,8 +144,8 @@ __global__ void order_kernel(int64_t nm, const unsigned long long* __restrict__ 
   if (which == 1 && shared) {
     const unsigned long long p = atomicAdd(&cnt[C_NP], 1ull);
     pair_j[p] = idx;
-    const char* s = nd.s + nd.off[idx];
-    atomicMax(&cnt[C_MAXNAME], (unsigned long long)trimmed_len(s, (int)(nd.off[idx + 1] - nd.off[idx])));
+    const char* s = nd.s + nd.beg[idx];
+    atomicMax(&cnt[C_MAXNAME], (unsigned long long)trimmed_len(s, (int)(nd.end[idx] - nd.beg[idx])));
   }
 }
 
@@ -161,8 +160,8 @@ __global__ void pair_key_kernel(int64_t np, const uint32_t* __restrict__ pair_j,
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= np) return;
   const uint32_t idx = pair_j[p];
-  const char* s = nd.s + nd.off[idx];
-  const int l = trimmed_len(s, (int)(nd.off[idx + 1] - nd.off[idx]));
+  const char* s = nd.s + nd.beg[idx];
+  const int l = trimmed_len(s, (int)(nd.end[idx] - nd.beg[idx]));
   unsigned long long k = 0;
   for (int b = 0; b < 8; b++) { const int pos = d * 8 + b; k = (k << 8) | (pos < l ? (unsigned char)s[pos] : 0u); }
   keys[p] = k;
@@ -430,9 +429,23 @@ const StrLut SLUT;
 
 }  // namespace
 
-int stage_b(catt_ctx* c, const HostReads& hr, const ReadsDev& reads, const DeviceQuals& dq, const FileHits& fh, catt_result* R, int* launches) {
+int upload_names(catt_ctx* c, int64_t n, const char* names, const int64_t* name_off, NamesDev* out, catt_info* info) {
+  *out = NamesDev{};
+  if (n == 0) return CATT_OK;
+  char* d_names; int64_t* d_off;
+  int rc;
+  const int64_t name_bytes = name_off[n];
+  if ((rc = ensure(c, SB_NAMES, name_bytes + 16, &d_names)) || (rc = ensure(c, SB_NAME_OFF, n + 1, &d_off))) return rc;
+  CATT_CUDA(cudaMemcpyAsync(d_names, names, (size_t)name_bytes, cudaMemcpyHostToDevice, c->stream));
+  CATT_CUDA(cudaMemcpyAsync(d_off, name_off, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+  if (info) info->bytes_h2d += name_bytes + (n + 1) * 8;
+  out->s = d_names; out->beg = d_off; out->end = d_off + 1;
+  return CATT_OK;
+}
+
+int stage_b(catt_ctx* c, int64_t n, const NamesDev& names, const ReadsDev& reads, const DeviceQuals& dq, const FileHits& fh, catt_result* R,
+            int* launches) {
   catt_info& info = R->info;
-  const int64_t n = hr.n;
   info.kmer = c->kmer;
   if (n == 0) return CATT_OK;
   cudaStream_t st = c->stream;
@@ -447,20 +460,13 @@ int stage_b(catt_ctx* c, const HostReads& hr, const ReadsDev& reads, const Devic
     tot_hits += fh.v[f] + fh.j[f];
     max_v = std::max(max_v, fh.v[f]); max_j = std::max(max_j, fh.j[f]); max_reads = std::max(max_reads, fh.start[f + 1] - fh.start[f]);
   }
-  // ---- QNAMEs to the device (once); work items of all files accumulate in `items` (n_items <= mapped records)
-  const int64_t name_bytes = hr.name_off[n];
-  char* d_names; int64_t* d_name_off; uint32_t* slot_of; int32_t* owner; uint32_t* minr[2];
+  // ---- per-file QNAME classes; work items of all files accumulate in `items` (n_items <= mapped records)
+  uint32_t* slot_of; int32_t* owner; uint32_t* minr[2];
   uint64_t cap = 1024;
   while (cap < (uint64_t)(max_v + max_j) * 2 + 2) cap <<= 1;
   if (cap > 0x80000000ull) { set_error("too many mapped reads for the QNAME table"); return CATT_E_LIMIT; }
-  if ((rc = ensure(c, SB_NAMES, name_bytes + 16, &d_names)) || (rc = ensure(c, SB_NAME_OFF, n + 1, &d_name_off)) ||
-      (rc = ensure(c, SB_SLOT_OF, max_reads, &slot_of)) || (rc = ensure(c, SB_OWNER, (int64_t)cap, &owner)) ||
+  if ((rc = ensure(c, SB_SLOT_OF, max_reads, &slot_of)) || (rc = ensure(c, SB_OWNER, (int64_t)cap, &owner)) ||
       (rc = ensure(c, SB_MINV, (int64_t)cap, &minr[0])) || (rc = ensure(c, SB_MINJ, (int64_t)cap, &minr[1]))) return rc;
-  if (tot_hits > 0) {
-    CATT_CUDA(cudaMemcpyAsync(d_names, hr.names, (size_t)name_bytes, cudaMemcpyHostToDevice, st));
-    CATT_CUDA(cudaMemcpyAsync(d_name_off, hr.name_off, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-    info.bytes_h2d += name_bytes + (n + 1) * 8;
-  }
   unsigned long long *keys_a, *sorted[2];
   uint32_t *flag, *kpos[2], *ord_idx[2], *ord_flag[2], *opos[2], *pair_a, *pair_b;
   const int64_t nmax = std::max(max_v, max_j);
@@ -485,7 +491,7 @@ int stage_b(catt_ctx* c, const HostReads& hr, const ReadsDev& reads, const Devic
     const int64_t lo = fh.start[f], nf = fh.start[f + 1] - lo;
     const int64_t nm[2] = {fh.v[f], fh.j[f]};
     const catt_aln* rec[2] = {c->recs_all[0].as<catt_aln>() + lo, c->recs_all[1].as<catt_aln>() + lo};
-    NamesDev nd{d_names, d_name_off + lo};
+    const NamesDev nd{names.s, names.beg + lo, names.end + lo};
     CATT_CUDA(cudaMemsetAsync(cnt, 0, C_COUNT * sizeof(unsigned long long), st));
     CATT_CUDA(cudaEventRecord(c->ev[5], st));
     if (nm[0] + nm[1] > 0) {

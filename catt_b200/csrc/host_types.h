@@ -31,6 +31,21 @@ struct DevBuf {
     cap = want;
     return CATT_OK;
   }
+  // grow, keeping the contents (appending the reads of the next input file)
+  int ensure_keep(size_t bytes, cudaStream_t st) {
+    if (bytes <= cap) return CATT_OK;
+    void* old = p; const size_t old_cap = cap;
+    p = nullptr; cap = 0;
+    int rc = ensure(bytes);
+    if (rc) { p = old; cap = old_cap; return rc; }
+    if (old) {
+      cudaError_t e = cudaMemcpyAsync(p, old, old_cap, cudaMemcpyDeviceToDevice, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      cudaFree(old);
+      if (e != cudaSuccess) return catt::cuda_fail(e, "scratch grow copy", __FILE__, __LINE__);
+    }
+    return CATT_OK;
+  }
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
@@ -53,12 +68,12 @@ struct PinBuf {
 
 // Stage B device scratch slots (assemble.cu)
 enum {
-  SB_NAMES = 0, SB_NAME_OFF, SB_SLOT_OF, SB_OWNER, SB_MINV, SB_MINJ, SB_KEYS_A, SB_SORT_V, SB_SORT_J, SB_FLAG, SB_KPOS_V,
+  SB_NAMES = 0, SB_NAME_OFF, SB_NAME_END, SB_SLOT_OF, SB_OWNER, SB_MINV, SB_MINJ, SB_KEYS_A, SB_SORT_V, SB_SORT_J, SB_FLAG, SB_KPOS_V,
   SB_KPOS_J, SB_ORD_IDX_V, SB_ORD_IDX_J, SB_ORD_FLAG_V, SB_ORD_FLAG_J, SB_OPOS_V, SB_OPOS_J, SB_PAIR_A, SB_PAIR_B, SB_PKEY_A, SB_PKEY_B, SB_ITEMS,
   SB_EOUT, SB_KFLAG, SB_KFLAG1, SB_KPOS2, SB_KPOS3, SB_PFLAG, SB_XPOS, SB_TAB_KEYS, SB_TAB_VALS, SB_PITEMS, SB_PARTIAL, SB_XOUT, SB_DESC, SB_SSZ, SB_QSZ, SB_SOFF, SB_QOFF, SB_OUT_SEQ, SB_OUT_QUAL, SB_OUT_PART, SB_CNT, SB_CUB,
   SB_COUNT
 };
-enum { PIN_PACK0 = 0, PIN_PACK1, PIN_OFF, PIN_LEN, PIN_CNT, PIN_DESC, PIN_XOUT, PIN_COUNT };
+enum { PIN_PACK0 = 0, PIN_PACK1, PIN_OFF, PIN_LEN, PIN_CNT, PIN_DESC, PIN_XOUT, PIN_TEXT, PIN_COUNT };
 constexpr int EV_A = 6;     // per reference set: seed start, seed end, expand end, sw end, select end
 
 struct catt_ctx {
@@ -75,6 +90,7 @@ struct catt_ctx {
   catt::AlignBuffers ab[2];
   DevBuf rd_words, rd_off, rd_len;        // packed reads of the sample being run (catt_run_*, catt_assemble)
   DevBuf rd_quals, rd_seqoff;             // its quality strings (as given) and int64 offsets, for the string kernel
+  DevBuf rd_text, rd_nl, rd_name_beg, rd_name_end, rd_seq_beg, rd_qual_beg, rd_nwords;   // FASTQ text ingested on the device (ingest.cu)
   DevBuf recs_all[2];                     // one catt_aln per read and reference set, for the whole sample
   DevBuf sb[SB_COUNT];
   PinBuf pin[PIN_COUNT];
@@ -82,6 +98,10 @@ struct catt_ctx {
   cudaEvent_t ev_a[2][EV_A]{};            // Stage A stage boundaries per reference set
   cudaEvent_t ev_h2d[2]{};                // staging buffer c&1 has reached the device
 };
+
+// QNAMEs in HBM: name i = s[beg[i], end[i]).  Host-supplied names are contiguous (beg = off, end = off + 1); names parsed on the
+// device point into the FASTQ text.
+struct NamesDev { const char* s = nullptr; const int64_t* beg = nullptr; const int64_t* end = nullptr; };
 
 // quality strings of the sample in HBM (uploaded under the Stage A kernels); quals == nullptr for FASTA input
 struct DeviceQuals { const char* quals = nullptr; const int64_t* seq_off = nullptr; };
@@ -129,5 +149,11 @@ struct FileHits {
   std::vector<int64_t> start, v, j;
   void single(int64_t n, int64_t vh, int64_t jh) { start = {0, n}; v = {vh}; j = {jh}; }
 };
-int stage_b(catt_ctx* c, const HostReads& hr, const ReadsDev& reads, const DeviceQuals& dq, const FileHits& fh, catt_result* R, int* launches);
+int stage_b(catt_ctx* c, int64_t n, const NamesDev& names, const ReadsDev& reads, const DeviceQuals& dq, const FileHits& fh, catt_result* R,
+            int* launches);
+// FASTQ text of one input file, resident at d_text[t0, t1) -> spans + packed reads appended at read index `base` (ingest.cu)
+int ingest_fastq(catt_ctx* c, const char* d_text, int64_t t0, int64_t t1, int64_t base, uint64_t word_base, int64_t* n_out,
+                 uint64_t* words_out, int* max_len, int* fallback, int* launches);
+// uploads host QNAMEs (contiguous, n+1 offsets) into the context's name buffers
+int upload_names(catt_ctx* c, int64_t n, const char* names, const int64_t* name_off, NamesDev* out, catt_info* info);
 }  // namespace catt

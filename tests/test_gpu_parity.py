@@ -344,3 +344,42 @@ def test_rnaseq_like_mix(ctx, O, orefs, trb):
     assert [myread_tuple(r) for r in res.Vpart] == [myread_tuple(r) for r in ref.Vpart]
     assert [myread_tuple(r) for r in res.Jpart] == [myread_tuple(r) for r in ref.Jpart]
     assert res.info["v_hits"] == ref.info["v_hits"] and res.info["v_hits"] < n // 10     # chance hits with AS >= 12 included
+
+
+def test_fastq_ingest_on_device_equals_host_parser(ctx, O, orefs, trb, sample, tmp_path):
+    """catt_run_file indexes, validates and packs strict 4-line FASTQ on the device (ingest.cu); everything else falls back to the
+    host parser.  Both must give the oracle's lists: CRLF line ends, header comments, missing / extra trailing newlines."""
+    from catt_b200 import _lib
+    names, seqs, quals = [x[:1200] for x in sample]
+    ref = O.run_mem(orefs[0], orefs[1], O.make_config(trb), names, seqs, quals)
+    want = ([myread_tuple(r) for r in ref.Vpart], [myread_tuple(r) for r in ref.Jpart])
+    body = lambda nl, tail="": "".join(f"@{n} 1:N:0 some\tcomment{nl}{s}{nl}+{n}{nl}{q}{nl}" for n, s, q in zip(names, seqs, quals)) + tail
+    variants = {"plain.fq": body("\n"), "crlf.fq": body("\r\n"), "notail.fq": body("\n")[:-1], "blanktail.fq": body("\n", "\n\n \n"),
+                "blankmid.fq": body("\n").replace("\n@", "\n\n@", 3)}          # blank lines inside: host parser (kseq skips them)
+    for fn, txt in variants.items():
+        p = str(tmp_path / fn)
+        with open(p, "w", newline="") as fh:
+            fh.write(txt)
+        for host in (False, True):
+            if host:
+                os.environ["CATT_HOST_PARSE"] = "1"
+            try:
+                res = ctx.mainflow(p)
+            finally:
+                os.environ.pop("CATT_HOST_PARSE", None)
+            assert ([myread_tuple(r) for r in res.Vpart], [myread_tuple(r) for r in res.Jpart]) == want, (fn, host)
+            assert res.info["n_reads"] == len(seqs)
+    # a read longer than the compiled-in limit: loud error from either path
+    p = str(tmp_path / "long.fq")
+    with open(p, "w") as fh:
+        fh.write(f"@x\n{'A' * 600}\n+\n{'I' * 600}\n")
+    with pytest.raises(_lib.CattError) as ei:
+        ctx.mainflow(p)
+    assert ei.value.code == -4
+    # truncated record: the device path declines, the host parser reports it
+    p = str(tmp_path / "trunc.fq")
+    with open(p, "w") as fh:
+        fh.write(body("\n")[:-200])
+    with pytest.raises(_lib.CattError) as ei:
+        ctx.mainflow(p)
+    assert ei.value.code == -2
