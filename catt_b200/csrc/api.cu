@@ -271,7 +271,9 @@ int parse_fastx(const std::string& path, HostReads* hr) {
   if (hr->own_name_off.empty()) { hr->own_name_off.push_back(0); hr->own_seq_off.push_back(0); }   // appends when called per input file
   size_t b, e;
   while (line(b, e)) {
-    if (e == b) continue;
+    size_t nb = b;
+    while (nb < e && (txt[nb] == ' ' || txt[nb] == '\t')) nb++;
+    if (nb == e) continue;                               // blank line (kseq skips to the next '@' / '>')
     const char tag = txt[b];
     if (tag != '@' && tag != '>') { set_error("%s: malformed FASTA/FASTQ record near byte %zu", path.c_str(), b); return CATT_E_IO; }
     size_t k = b + 1;
