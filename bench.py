@@ -115,6 +115,37 @@ def roofline_other(infos, length, world):
     return out
 
 
+def file_e2e(ctx, np, R, length, seq_buf, qual_buf, first):
+    """The same batch as a FASTQ file on local disk through catt_run_file - the call the patched Julia driver makes
+    (INTEGRATION.md): parallel pread into pinned memory, text to HBM, indexing / validation / 2-bit packing on the device."""
+    d = tempfile.mkdtemp(prefix="catt_bench_fq_")
+    path = os.path.join(d, "synth.fq")
+    w = 10
+    rec = np.empty((R, 1 + 1 + w + 1 + length + 3 + length + 1), dtype=np.uint8)
+    rec[:, 0] = ord("@"); rec[:, 1] = ord("s")
+    rec[:, 2:2 + w] = np.frombuffer("".join(np.char.zfill((np.arange(R) + first).astype(str), w).tolist()).encode(), dtype=np.uint8).reshape(R, w)
+    o = 2 + w
+    rec[:, o] = 10
+    rec[:, o + 1:o + 1 + length] = seq_buf.reshape(R, length)
+    o += 1 + length
+    rec[:, o] = 10; rec[:, o + 1] = ord("+"); rec[:, o + 2] = 10
+    rec[:, o + 3:o + 3 + length] = qual_buf.reshape(R, length)
+    rec[:, o + 3 + length] = 10
+    rec.tofile(path)
+    size = os.path.getsize(path)
+    ctx.mainflow(path).close()
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        res = ctx.mainflow(path)
+        ts.append(time.perf_counter() - t0)
+        res.close()
+    os.remove(path)
+    dt = sorted(ts)[1]
+    return {"value": R / dt, "unit": "reads/s", "ms_per_call": dt * 1e3, "file_bytes": size,
+            "note": "catt_run_file on a FASTQ in the page cache, median of 3 calls after 1 warm-up; QNAMEs are zero-padded read numbers"}
+
+
 def cpu_reference_run(fx, length, n_sample, first_index=0):
     """The CPU restatement (oracle) on n_sample reads with all host threads; returns (reads/s, seconds, info)."""
     from catt_b200.refg import chain_config
@@ -139,6 +170,7 @@ def main():
     ap.add_argument("--impl", default="gpu", choices=["gpu", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU-baseline sample (0 = auto, ~15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-file-e2e", action="store_true", help="skip the catt_run_file measurement (FASTQ written to a temp file)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -293,6 +325,8 @@ def main():
         "roofline_other": roofline_other(infos, args.length, world),
         "counters": {k: info[k] for k in ("v_hits", "j_hits", "vpart", "jpart", "direct", "left", "rescued", "cand_v", "cand_j", "gapped_v")},
     }
+    if rank == 0 and world == 1 and not args.no_file_e2e:
+        line["e2e_file"] = file_e2e(ctx, np, R, args.length, seq_buf, qual_buf, first)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
         n = args.cpu_sample or max(16000, 15000 * cores)       # ~15 s of CPU work on `cores` threads
