@@ -480,7 +480,8 @@ int dispatch_sw(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks, c
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int sub_score(uint32_t a, uint32_t b) { return (a > 3 || b > 3) ? -1 : (a == b ? 1 : -2); }
 
-__global__ void select_kernel(RefDev ref, ReadsDev reads, const uint32_t* __restrict__ candbits, const SwTask* __restrict__ tasks,
+__global__ void select_kernel(RefDev ref, ReadsDev reads, const uint32_t* __restrict__ candbits, const uint32_t* __restrict__ canonbits,
+                              const SwTask* __restrict__ tasks,
                               const uint32_t* __restrict__ task_off, const uint32_t* __restrict__ task_score, int64_t cap_tasks,
                               int64_t first_ordinal, int min_score, catt_aln* __restrict__ recs, SwTask* __restrict__ wtasks,
                               unsigned long long* __restrict__ counters) {
@@ -505,16 +506,26 @@ __global__ void select_kernel(RefDev ref, ReadsDev reads, const uint32_t* __rest
     const uint64_t ord = (uint64_t)(first_ordinal + r);
     int ncand = 0, ntied = 0, win_c = -1;
     uint64_t win_h = ~0ull;
+    // expand_kernel emitted the tasks in bit order of the canonical bitmap, forward strand first, two candidates per task: the
+    // score of canonical candidate cc sits in task t0 (+ forward tasks) + rank/2, half rank%2, rank = its position among the
+    // canonical candidates of its strand - a popcount, not a search
+    uint16_t pre[2][MAX_CW];
+    uint32_t nfw = 0, nrv = 0;
+    for (int w = 0; w < ref.CW; w++) {
+      const uint32_t b = canonbits[r * ref.CW + w];
+      pre[0][w] = (uint16_t)nfw; pre[1][w] = (uint16_t)nrv;
+      nfw += __popc(b & 0x55555555u); nrv += __popc(b & 0xAAAAAAAAu);
+    }
+    const uint32_t rv_base = t0 + (nfw + 1) / 2;
     auto consider = [&](int c) {
       ncand++;
       my_cells += (unsigned long long)m * ref.rec_len[c >> 1];
       const int cc = ref.canon[c];
-      int sc = -1;
-      for (uint32_t t = t0; t < t1; t++) {
-        const SwTask tk = tasks[t];
-        if (tk.a == cc) { sc = (int)(task_score[t] & 0xffff); break; }
-        if (tk.b == cc) { sc = (int)(task_score[t] >> 16); break; }
-      }
+      const int st = cc & 1, w = cc >> 5;
+      const uint32_t below = canonbits[r * ref.CW + w] & (st ? 0xAAAAAAAAu : 0x55555555u) & ((1u << (cc & 31)) - 1u);
+      const uint32_t rank = pre[st][w] + __popc(below);
+      const uint32_t ts = task_score[(st ? rv_base : t0) + (rank >> 1)];
+      const int sc = (int)((rank & 1) ? ts >> 16 : ts & 0xffff);
       if (sc == mx) {
         const uint64_t h = hash_64(ord + (uint64_t)ntied);
         ntied++;
@@ -752,7 +763,7 @@ int launch_sw(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int sm
 int launch_select(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, catt_aln* recs, int64_t first_ordinal, int min_score,
                   int sm_count, cudaStream_t st, int* launches) {
   if (reads.n == 0) return CATT_OK;
-  select_kernel<<<(unsigned)((reads.n + 127) / 128), 128, 0, st>>>(ref, reads, ab.candbits, ab.tasks, ab.task_off, ab.task_score,
+  select_kernel<<<(unsigned)((reads.n + 127) / 128), 128, 0, st>>>(ref, reads, ab.candbits, ab.canonbits, ab.tasks, ab.task_off, ab.task_score,
                                                                    ab.cap_tasks, first_ordinal, min_score, recs, ab.wtasks, ab.counters);
   CATT_CUDA(cudaGetLastError());
   int rc = dispatch_sw<true>(ref, reads, ab.wtasks, reinterpret_cast<const uint32_t*>(ab.counters + 7), reads.n, ab.wres, sm_count, st);
