@@ -467,6 +467,7 @@ int dispatch_sw(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks, c
   if (n <= 32) return launch_sw_t<4, 8, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
   if (n <= 48) return launch_sw_t<4, 12, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
   if (n <= 64) return launch_sw_t<8, 8, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
+  if (n <= 100 && TRACK && !getenv("CATT_SW_G8")) return launch_sw_t<4, 25, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
   if (n <= 104) return launch_sw_t<8, 13, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
   if (n <= 160) return launch_sw_t<16, 10, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
   if (n <= 320) return launch_sw_t<32, 10, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
