@@ -180,10 +180,11 @@ int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool
   // the quality strings follow their chunk to HBM on the copy stream (the result strings are written on the device)
   char* d_quals = nullptr;
   if (dq) *dq = DeviceQuals{};
+  if ((rc = c->rd_seqoff.ensure((size_t)(n + 1) * sizeof(int64_t)))) return rc;
+  const int64_t* d_seqoff = c->rd_seqoff.as<int64_t>();
+  CATT_CUDA(cudaMemcpyAsync(c->rd_seqoff.p, hr.seq_off, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
   if (want_quals && dq && n > 0) {
-    if ((rc = c->rd_seqoff.ensure((size_t)(n + 1) * sizeof(int64_t)))) return rc;
-    CATT_CUDA(cudaMemcpyAsync(c->rd_seqoff.p, hr.seq_off, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-    dq->seq_off = c->rd_seqoff.as<int64_t>();
+    dq->seq_off = d_seqoff;
     if (hr.quals) {
       if ((rc = c->rd_quals.ensure((size_t)hr.seq_off[n] + 16))) return rc;
       d_quals = c->rd_quals.as<char>();
@@ -192,7 +193,7 @@ int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool
   }
   CATT_CUDA(cudaMemcpyAsync(dr.off, h_off, (size_t)(n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   CATT_CUDA(cudaMemcpyAsync(dr.len, h_len, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  if (info) info->bytes_h2d += (int64_t)((n + 1) * 4 + n * 4 + (dq && dq->seq_off ? (n + 1) * 8 : 0));
+  if (info) info->bytes_h2d += (int64_t)((n + 1) * 4 + n * 4 + (n + 1) * 8);
   struct Chunk { int64_t i0, cnt, ordinal; int file; };
   std::vector<Chunk> chunks;
   const int nfiles = (int)fh->start.size() - 1;
@@ -206,22 +207,32 @@ int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool
       i0 += cnt;
     }
   const int64_t nchunks = (int64_t)chunks.size();
-  auto stage_chunk = [&](int64_t ci) -> int {           // pack chunk ci into its staging buffer and start its H2D
+  // the host only moves bytes: the raw bases (and quality strings) of chunk ci are copied by all host threads into pinned staging
+  // and follow on the copy stream; the 2-bit packing runs on the device in front of the chunk's kernels
+  auto par_copy = [](char* dst, const char* src, size_t bytes) {
+    const int64_t piece = 1 << 20, np = (int64_t)((bytes + piece - 1) / piece);
+    #pragma omp parallel for schedule(static)
+    for (int64_t p = 0; p < np; p++) memcpy(dst + p * piece, src + p * piece, (size_t)std::min<int64_t>(piece, (int64_t)bytes - p * piece));
+  };
+  auto stage_chunk = [&](int64_t ci) -> int {
     const int64_t i0 = chunks[ci].i0, i1 = i0 + chunks[ci].cnt;
-    const size_t words = (size_t)(h_off[i1] - h_off[i0]);
+    const size_t bytes = (size_t)(hr.seq_off[i1] - hr.seq_off[i0]);
+    if (ci >= 2) CATT_CUDA(cudaEventSynchronize(c->ev_q[ci & 1]));        // the copies that last read these staging buffers
     PinBuf& pb = c->pin[PIN_PACK0 + (ci & 1)];
-    if (ci >= 2) CATT_CUDA(cudaEventSynchronize(c->ev_h2d[ci & 1]));      // the copy that last read this buffer
-    int r = pb.ensure((words + 4) * sizeof(uint32_t));
-    if (r) return r;
-    pack_range(i0, i1, hr.seqs, hr.seq_off, h_off, pb.as<uint32_t>());
-    CATT_CUDA(cudaMemcpyAsync(dr.words + h_off[i0], pb.p, words * sizeof(uint32_t), cudaMemcpyHostToDevice, cs));
+    int r;
+    if ((r = pb.ensure(bytes + 16)) || (r = c->rd_raw[ci & 1].ensure(bytes + 16))) return r;
+    par_copy(pb.as<char>(), hr.seqs + hr.seq_off[i0], bytes);
+    CATT_CUDA(cudaMemcpyAsync(c->rd_raw[ci & 1].p, pb.p, bytes, cudaMemcpyHostToDevice, cs));
     CATT_CUDA(cudaEventRecord(c->ev_h2d[ci & 1], cs));
-    if (info) info->bytes_h2d += (int64_t)(words * sizeof(uint32_t));
-    if (d_quals && hr.seq_off[i1] > hr.seq_off[i0]) {     // pageable source: staged by the driver while the previous chunk computes
-      if (info) info->bytes_h2d += hr.seq_off[i1] - hr.seq_off[i0];
-      CATT_CUDA(cudaMemcpyAsync(d_quals + hr.seq_off[i0], hr.quals + hr.seq_off[i0], (size_t)(hr.seq_off[i1] - hr.seq_off[i0]),
-                                cudaMemcpyHostToDevice, cs));
+    if (info) info->bytes_h2d += (int64_t)bytes;
+    if (d_quals && bytes) {
+      PinBuf& qb = c->pin[PIN_QUAL0 + (ci & 1)];
+      if ((r = qb.ensure(bytes + 16))) return r;
+      par_copy(qb.as<char>(), hr.quals + hr.seq_off[i0], bytes);
+      CATT_CUDA(cudaMemcpyAsync(d_quals + hr.seq_off[i0], qb.p, bytes, cudaMemcpyHostToDevice, cs));
+      if (info) info->bytes_h2d += (int64_t)bytes;
     }
+    CATT_CUDA(cudaEventRecord(c->ev_q[ci & 1], cs));
     return CATT_OK;
   };
   if (nchunks > 0 && (rc = stage_chunk(0))) return rc;
@@ -231,6 +242,8 @@ int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool
     const Chunk ch = chunks[ci];
     const ReadsDev rv = dr.view(ch.i0, ch.cnt);
     CATT_CUDA(cudaStreamWaitEvent(st, c->ev_h2d[ci & 1], 0));
+    if ((rc = launch_pack_raw(c->rd_raw[ci & 1].as<char>() - hr.seq_off[ch.i0], d_seqoff + ch.i0, dr.len + ch.i0, dr.off + ch.i0, ch.cnt, dr.words,
+                              c->sm_count, st, launches))) return rc;
     if (align)
       for (int which = 0; which < 2; which++)
         if ((rc = align_queue(c, which, rv, c->recs_all[which].as<catt_aln>() + ch.i0, ch.ordinal, launches))) return rc;
@@ -507,6 +520,7 @@ int catt_ctx_create(catt_ctx** out, const catt_config* cfg) {
   for (auto& ev : c->ev) CATT_CUDA(cudaEventCreate(&ev));
   for (auto& row : c->ev_a) for (auto& ev : row) CATT_CUDA(cudaEventCreate(&ev));
   for (auto& ev : c->ev_h2d) CATT_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  for (auto& ev : c->ev_q) CATT_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   if ((rc = c->pin[PIN_CNT].ensure(1024))) return rc;
   *out = c.release();
   return CATT_OK;
@@ -527,6 +541,8 @@ void catt_ctx_destroy(catt_ctx* c) {
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   for (auto& row : c->ev_a) for (auto& ev : row) if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->ev_h2d) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : c->ev_q) if (ev) cudaEventDestroy(ev);
+  for (auto& b : c->rd_raw) b.release();
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   delete c;

@@ -73,7 +73,7 @@ enum {
   SB_EOUT, SB_KFLAG, SB_KFLAG1, SB_KPOS2, SB_KPOS3, SB_PFLAG, SB_XPOS, SB_TAB_KEYS, SB_TAB_VALS, SB_PITEMS, SB_PARTIAL, SB_XOUT, SB_DESC, SB_SSZ, SB_QSZ, SB_SOFF, SB_QOFF, SB_OUT_SEQ, SB_OUT_QUAL, SB_OUT_PART, SB_CNT, SB_CUB,
   SB_COUNT
 };
-enum { PIN_PACK0 = 0, PIN_PACK1, PIN_OFF, PIN_LEN, PIN_CNT, PIN_DESC, PIN_XOUT, PIN_TEXT, PIN_COUNT };
+enum { PIN_PACK0 = 0, PIN_PACK1, PIN_QUAL0, PIN_QUAL1, PIN_OFF, PIN_LEN, PIN_CNT, PIN_DESC, PIN_XOUT, PIN_TEXT, PIN_COUNT };
 constexpr int EV_A = 6;     // per reference set: seed start, seed end, expand end, sw end, select end
 
 struct catt_ctx {
@@ -96,7 +96,9 @@ struct catt_ctx {
   PinBuf pin[PIN_COUNT];
   cudaEvent_t ev[8]{};
   cudaEvent_t ev_a[2][EV_A]{};            // Stage A stage boundaries per reference set
-  cudaEvent_t ev_h2d[2]{};                // staging buffer c&1 has reached the device
+  cudaEvent_t ev_h2d[2]{};                // sequence staging buffer c&1 has reached the device
+  cudaEvent_t ev_q[2]{};                  // ... and the quality staging buffer
+  DevBuf rd_raw[2];                       // raw bases of the chunk in flight (packed on the device)
 };
 
 // QNAMEs in HBM: name i = s[beg[i], end[i]).  Host-supplied names are contiguous (beg = off, end = off + 1); names parsed on the
@@ -154,6 +156,8 @@ int stage_b(catt_ctx* c, int64_t n, const NamesDev& names, const ReadsDev& reads
 // FASTQ text of one input file, resident at d_text[t0, t1) -> spans + packed reads appended at read index `base` (ingest.cu)
 int ingest_fastq(catt_ctx* c, const char* d_text, int64_t t0, int64_t t1, int64_t base, uint64_t word_base, int64_t* n_out,
                  uint64_t* words_out, int* max_len, int* fallback, int* launches);
+int launch_pack_raw(const char* d_text, const int64_t* d_seq_beg, const int32_t* d_len, const uint32_t* d_off, int64_t n, uint32_t* d_words,
+                    int sm_count, cudaStream_t st, int* launches);
 // uploads host QNAMEs (contiguous, n+1 offsets) into the context's name buffers
 int upload_names(catt_ctx* c, int64_t n, const char* names, const int64_t* name_off, NamesDev* out, catt_info* info);
 }  // namespace catt

@@ -88,6 +88,17 @@ __global__ void __launch_bounds__(256) pack_kernel(const char* __restrict__ text
 
 }  // namespace
 
+// 2-bit packing of reads whose raw bases sit in HBM: read r = text[seq_beg[r], seq_beg[r] + len[r]) -> words + off[r]
+int launch_pack_raw(const char* d_text, const int64_t* d_seq_beg, const int32_t* d_len, const uint32_t* d_off, int64_t n, uint32_t* d_words,
+                    int sm_count, cudaStream_t st, int* launches) {
+  if (n == 0) return CATT_OK;
+  const int grid = (int)std::min<int64_t>((n + 7) / 8, (int64_t)sm_count * 32);
+  pack_kernel<<<grid, 256, 0, st>>>(d_text, reinterpret_cast<const long long*>(d_seq_beg), d_len, d_off, n, d_words);
+  CATT_CUDA(cudaGetLastError());
+  *launches += 1;
+  return CATT_OK;
+}
+
 // Parses the FASTQ text of one input file, resident at d_text[t0, t1) (ends with '\n'), appending its reads at index `base`.
 // On success *n_out = records found; the ctx read buffers (rd_off is filled per file relative to `word_base`) are extended.
 int ingest_fastq(catt_ctx* c, const char* d_text, int64_t t0, int64_t t1, int64_t base, uint64_t word_base, int64_t* n_out,
