@@ -753,6 +753,66 @@ int catt_assemble(catt_ctx* c, int64_t n, const char* names, const int64_t* name
   return CATT_OK;
 }
 
+int catt_records_device(catt_ctx* c, int which, int64_t capacity, uint64_t* device_ptr) {
+  if (!c || !device_ptr || which < 0 || which > 1 || capacity < 0) { set_error("catt_records_device: bad argument"); return CATT_E_ARG; }
+  CATT_CUDA(cudaSetDevice(c->device));
+  int rc = c->recs_all[which].ensure_keep((size_t)std::max<int64_t>(capacity, 1) * sizeof(catt_aln), c->stream);
+  if (rc) return rc;
+  *device_ptr = (uint64_t)(uintptr_t)c->recs_all[which].p;
+  return CATT_OK;
+}
+
+namespace {
+__global__ void count_mapped_kernel(const catt_aln* __restrict__ recs, int64_t n, unsigned long long* __restrict__ out) {
+  unsigned long long mine = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) mine += recs[i].mapped != 0;
+  #pragma unroll
+  for (int d = 16; d; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(out, mine);
+}
+}  // namespace
+
+int catt_assemble_device(catt_ctx* c, int64_t n, const char* names, const int64_t* name_off, const char* seqs, const int64_t* seq_off,
+                         const char* quals, catt_result** out) {
+  if (!c || !out || n < 0 || (n > 0 && (!names || !name_off || !seqs || !seq_off))) { set_error("catt_assemble_device: bad argument"); return CATT_E_ARG; }
+  CATT_CUDA(cudaSetDevice(c->device));
+  if (c->recs_all[0].cap < (size_t)n * sizeof(catt_aln) || c->recs_all[1].cap < (size_t)n * sizeof(catt_aln)) {
+    set_error("catt_assemble_device: the record arrays hold fewer than n records (call catt_records_device first)");
+    return CATT_E_ARG;
+  }
+  HostReads hr;
+  hr.n = n; hr.names = names; hr.name_off = name_off; hr.seqs = seqs; hr.seq_off = seq_off; hr.quals = quals;
+  std::unique_ptr<catt_result> R(new catt_result());
+  R->info.n_reads = n;
+  unsigned long long* cnt = c->pin[PIN_CNT].as<unsigned long long>();
+  int rc;
+  if ((rc = c->sb[SB_CNT].ensure(64 * sizeof(unsigned long long)))) return rc;
+  unsigned long long* d_cnt = c->sb[SB_CNT].as<unsigned long long>();
+  CATT_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), c->stream));
+  if (n) {
+    for (int which = 0; which < 2; which++) count_mapped_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(c->recs_all[which].as<catt_aln>(), n, d_cnt + which);
+    CATT_CUDA(cudaGetLastError());
+  }
+  CATT_CUDA(cudaMemcpyAsync(cnt, d_cnt, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  CATT_CUDA(cudaStreamSynchronize(c->stream));
+  R->info.v_hits = (int64_t)cnt[0]; R->info.j_hits = (int64_t)cnt[1];
+  DeviceReads dr;
+  DeviceQuals dq;
+  int launches = 2;
+  FileHits fh;
+  fh.start = {0, n};
+  // pack + upload only; the records stay where the caller put them (ensure_recs never shrinks or moves a large enough array)
+  if ((rc = stage_a_stream(c, hr, 0, false, true, &dr, &dq, &fh, &R->info, &launches))) return rc;
+  fh.single(n, R->info.v_hits, R->info.j_hits);
+  if (c->keep_records && (rc = download_records(c, n, R.get()))) return rc;
+  NamesDev nd;
+  if ((rc = upload_names(c, n, names, name_off, &nd, &R->info))) return rc;
+  if ((rc = stage_b(c, n, nd, dr.view(), dq, fh, R.get(), &launches))) return rc;
+  R->info.kernel_launches = launches;
+  *out = R.release();
+  return CATT_OK;
+}
+
 // Stage B on a batch that is already resident in HBM and aligned (catt_batch_align): used for the device-resident
 // throughput number.  The host buffers are still needed for the QNAMEs and to materialise the Myread strings.
 int catt_batch_assemble(catt_ctx* c, catt_batch* b, const char* names, const int64_t* name_off, const char* seqs,

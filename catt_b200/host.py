@@ -230,6 +230,23 @@ class Catt:
                                                 j.ctypes.data))
         return v, j
 
+    def align_shard_device(self, n, seq_buf, seq_off, first_ordinal=0):
+        """Stage A of a shard; the records stay in HBM (at the start of the context's record arrays)."""
+        _lib.check(_lib.load().catt_align_shard(self._h, n, _addr(seq_buf), seq_off.ctypes.data, first_ordinal, None, None))
+
+    def records_device(self, which, capacity) -> int:
+        """Device address of the context's record array for `which` (0 = V, 1 = J), grown to `capacity` records."""
+        p = C.c_uint64()
+        _lib.check(_lib.load().catt_records_device(self._h, which, capacity, C.byref(p)))
+        return p.value
+
+    def assemble_device(self, n, name_buf, name_off, seq_buf, seq_off, qual_buf) -> Result:
+        """Stage B on the n records already sitting in the context's record arrays (after an NCCL all-gather)."""
+        h = C.c_void_p()
+        _lib.check(_lib.load().catt_assemble_device(self._h, n, _addr(name_buf), name_off.ctypes.data, _addr(seq_buf), seq_off.ctypes.data,
+                                                    _addr(qual_buf) if qual_buf is not None else None, C.byref(h)))
+        return Result(self, h)
+
     def upload(self, n, seq_buf, seq_off, first_ordinal=0) -> Batch:
         h = C.c_void_p()
         _lib.check(_lib.load().catt_batch_upload(self._h, n, _addr(seq_buf), seq_off.ctypes.data, first_ordinal, C.byref(h)))

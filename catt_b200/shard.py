@@ -4,6 +4,9 @@ the GLOBAL `first_ordinal` (bwa's hash tie-break uses the global read ordinal), 
 all-gathered (NCCL over NVLink on GPUs, gloo in the CPU tests), and Stage B (`catt_assemble`: the SAM order / QNAME
 dedup / V-J join are global, the k-mer table is a global last-writer-wins map) runs once, on rank `root`.
 
+With `on_device=True` the records never leave HBM: the ranks all-gather them between the contexts' record arrays
+(`catt_records_device`, NCCL over NVLink) and the root runs `catt_assemble_device`.
+
 One process per GPU, launched with torchrun; `torch.distributed` is plumbing only - every computation is in
 libcatt_b200.so.  Independent samples (the weak-scaling mode of bench.py) need no exchange at all.
 """
@@ -47,6 +50,35 @@ def gather_records(local: np.ndarray, n: int, group=None, device=None) -> np.nda
     return full
 
 
+class _DevMem:
+    """A device allocation owned by libcatt_b200, exposed to torch through the CUDA array interface (no copy)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def gather_records_device(ctx, n_local: int, n: int, group=None, device=None):
+    """NCCL all-gather of the alignment records WITHOUT leaving HBM: every rank's block sits at the start of its context's
+    record arrays (catt_align_shard with NULL outputs); the gathered, padded blocks are copied device-to-device into the
+    arrays of this rank's context at their global positions (NVLink all-gather + one D2D pass, no PCIe)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rec = _lib.ALN_DTYPE.itemsize
+    cap = max(shard_bounds(n, world, 0)[1], 1)
+    for which in (0, 1):
+        ptr = ctx.records_device(which, max(n, cap))
+        whole = torch.as_tensor(_DevMem(ptr, max(n, cap) * rec), device=device)
+        send = torch.zeros(cap * rec, dtype=torch.uint8, device=device)
+        send[:n_local * rec].copy_(whole[:n_local * rec])
+        out = torch.empty(world * cap * rec, dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(out, send, group=group)
+        for r in range(world):
+            lo, hi = shard_bounds(n, world, r)
+            whole[lo * rec:hi * rec].copy_(out[r * cap * rec:r * cap * rec + (hi - lo) * rec])
+    torch.cuda.synchronize(device)
+
+
 class ShardedCatt:
     """`Catt.mainflow_buffers` for one sample spread over the ranks of a process group.
 
@@ -54,8 +86,8 @@ class ShardedCatt:
     `assemble_fn(n, names, name_off, seqs, seq_off, quals, v_recs, j_recs) -> result` default to the context's
     `catt_align_shard` / `catt_assemble`; the CPU tests inject stand-ins so the sharding logic runs under gloo."""
 
-    def __init__(self, ctx=None, group=None, device=None, align_fn=None, assemble_fn=None, root=0):
-        self.ctx, self.group, self.device, self.root = ctx, group, device, root
+    def __init__(self, ctx=None, group=None, device=None, align_fn=None, assemble_fn=None, root=0, on_device=False):
+        self.ctx, self.group, self.device, self.root, self.on_device = ctx, group, device, root, on_device
         self.align_fn = align_fn or self._align
         self.assemble_fn = assemble_fn or self._assemble
 
@@ -75,6 +107,12 @@ class ShardedCatt:
         sub_off = seq_off[lo:hi + 1] - base
         sub_seq = np.frombuffer(seq_buf, dtype=np.uint8)[base:int(seq_off[hi])] if not isinstance(seq_buf, np.ndarray) else \
             seq_buf[base:int(seq_off[hi])]
+        if self.on_device:                       # records never leave HBM: NCCL all-gather between the contexts' record arrays
+            self.ctx.align_shard_device(hi - lo, np.ascontiguousarray(sub_seq), np.ascontiguousarray(sub_off), lo)
+            gather_records_device(self.ctx, hi - lo, n, self.group, self.device)
+            if rank != self.root:
+                return None
+            return self.ctx.assemble_device(n, name_buf, name_off, seq_buf, seq_off, qual_buf)
         v, j = self.align_fn(hi - lo, np.ascontiguousarray(sub_seq), np.ascontiguousarray(sub_off), lo)
         v_all = gather_records(v, n, self.group, self.device)
         j_all = gather_records(j, n, self.group, self.device)

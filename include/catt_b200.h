@@ -165,6 +165,14 @@ int catt_best_d(catt_ctx* ctx, const char* const* cdr3, int64_t n, int32_t* d_in
 int catt_align_shard(catt_ctx* ctx, int64_t n, const char* seqs, const int64_t* seq_off, int64_t first_ordinal,
                      catt_aln* v_out, catt_aln* j_out);
 
+/* Device-side exchange for one sample over several GPUs (catt_b200/shard.py): after catt_align_shard(..., NULL, NULL) the shard's
+ * records sit at the start of the context's record arrays; catt_records_device returns their device address (arrays grown to hold
+ * `capacity` records, contents kept) so the ranks can all-gather them over NCCL / NVLink without a host round trip, and
+ * catt_assemble_device runs Stage B on the n records the caller left there. */
+int catt_records_device(catt_ctx* ctx, int which, int64_t capacity, uint64_t* device_ptr);
+int catt_assemble_device(catt_ctx* ctx, int64_t n, const char* names, const int64_t* name_off, const char* seqs,
+                         const int64_t* seq_off, const char* quals, catt_result** out);
+
 /* Device-resident variant used by bench.py: upload once, run Stage A repeatedly on the resident batch, read back. */
 typedef struct catt_batch catt_batch;
 int catt_batch_upload(catt_ctx* ctx, int64_t n, const char* seqs, const int64_t* seq_off, int64_t first_ordinal,
