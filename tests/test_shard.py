@@ -116,3 +116,34 @@ def test_sharded_class_on_gpu_world1(fx, trb):
         c.close()
     finally:
         dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_sharded_device_gather_world1(fx, trb):
+    """on_device=True: records stay in HBM (catt_records_device + NCCL all-gather + catt_assemble_device); NCCL group of one rank.
+    The N-rank run of the same code is profiles/shard_check.py under torchrun (profiles/r01e_shard_2gpu.txt)."""
+    import torch
+    import torch.distributed as dist
+    from catt_b200 import _lib
+    from catt_b200.host import Catt
+    from catt_b200.shard import ShardedCatt
+    from oracle import oracle as O
+    from util import myread_tuple
+    torch.cuda.set_device(0)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{_free_port()}", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        V, J = O.RefSet(trb["vregion"]), O.RefSet(trb["jregion"])
+        names, seqs, quals = synth_reads(5000, [V.record(i) for i in range(V.nrec)], [J.record(i) for i in range(J.nrec)], 150, seed=6)
+        nb, no = _lib.concat(names)
+        sb, so = _lib.concat(seqs)
+        qb, _ = _lib.concat(quals)
+        c = Catt(chain_cfg=trb)
+        whole = c.mainflow_buffers(len(seqs), nb, no, sb, so, qb)
+        want = ([myread_tuple(r) for r in whole.Vpart], [myread_tuple(r) for r in whole.Jpart])
+        res = ShardedCatt(c, device=torch.device("cuda", 0), on_device=True).mainflow_buffers(len(seqs), nb, no, sb, so, qb)
+        assert ([myread_tuple(r) for r in res.Vpart], [myread_tuple(r) for r in res.Jpart]) == want
+        ref = O.run_mem(V, J, O.make_config(trb), names, seqs, quals)
+        assert want == ([myread_tuple(r) for r in ref.Vpart], [myread_tuple(r) for r in ref.Jpart])
+        c.close()
+    finally:
+        dist.destroy_process_group()
