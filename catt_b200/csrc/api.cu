@@ -136,24 +136,33 @@ int ensure_recs(catt_ctx* c, int64_t n) {
 
 // Stage A over reads that are already resident: chunk by chunk (bounded scratch), records into ctx->recs_all.  `fh->start`
 // lists the input files: chunks never straddle a file and the read ordinal restarts at every file.
+int stage_a_range(catt_ctx* c, const DeviceReads& dr, int64_t lo, int64_t hi, int64_t ordinal0, int file, FileHits* fh, catt_info* info,
+                  int* launches) {
+  int rc;
+  for (int64_t i0 = lo; i0 < hi;) {
+    const int64_t left = hi - i0;
+    const int64_t cnt = left <= c->chunk_reads * 3 / 2 ? left : c->chunk_reads;      // no tiny tail chunk
+    const int64_t ord = ordinal0 + (i0 - lo);
+    const ReadsDev rv = dr.view(i0, cnt);
+    for (int which = 0; which < 2; which++)
+      if ((rc = align_queue(c, which, rv, c->recs_all[which].as<catt_aln>() + i0, ord, launches))) return rc;
+    CATT_CUDA(cudaStreamSynchronize(c->stream));
+    const int64_t v0 = info->v_hits, j0 = info->j_hits;
+    for (int which = 0; which < 2; which++)
+      if ((rc = align_finish(c, which, rv, c->recs_all[which].as<catt_aln>() + i0, ord, info, launches))) return rc;
+    fh->v[file] += info->v_hits - v0; fh->j[file] += info->j_hits - j0;
+    i0 += cnt;
+  }
+  return CATT_OK;
+}
+
 int stage_a_resident(catt_ctx* c, const DeviceReads& dr, int64_t first_ordinal, FileHits* fh, catt_info* info, int* launches) {
   int rc;
   if ((rc = ensure_recs(c, dr.n))) return rc;
   const int nfiles = (int)fh->start.size() - 1;
   fh->v.assign(nfiles, 0); fh->j.assign(nfiles, 0);
   for (int f = 0; f < nfiles; f++)
-    for (int64_t i0 = fh->start[f]; i0 < fh->start[f + 1]; i0 += c->chunk_reads) {
-      const int64_t cnt = std::min<int64_t>(c->chunk_reads, fh->start[f + 1] - i0);
-      const int64_t ord = first_ordinal + (i0 - fh->start[f]);
-      const ReadsDev rv = dr.view(i0, cnt);
-      for (int which = 0; which < 2; which++)
-        if ((rc = align_queue(c, which, rv, c->recs_all[which].as<catt_aln>() + i0, ord, launches))) return rc;
-      CATT_CUDA(cudaStreamSynchronize(c->stream));
-      const int64_t v0 = info->v_hits, j0 = info->j_hits;
-      for (int which = 0; which < 2; which++)
-        if ((rc = align_finish(c, which, rv, c->recs_all[which].as<catt_aln>() + i0, ord, info, launches))) return rc;
-      fh->v[f] += info->v_hits - v0; fh->j[f] += info->j_hits - j0;
-    }
+    if ((rc = stage_a_range(c, dr, fh->start[f], fh->start[f + 1], first_ordinal, f, fh, info, launches))) return rc;
   return CATT_OK;
 }
 
@@ -392,30 +401,72 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
     if (e == 0 || dst[0] != '@') return CATT_OK;                  // empty or not FASTQ: host path
     dst[e++] = '\n';
     tend[f] = tpos[f] + e;
-    CATT_CUDA(cudaMemcpyAsync(d_text + tpos[f], dst, (size_t)e, cudaMemcpyHostToDevice, c->stream));
   }
-  tr.lap("run_files: read + H2D text");
+  // every file goes to HBM in pieces that end on a record boundary (a line that starts with '@' whose second next line starts
+  // with '+'), queued on the copy stream up front: piece k+1 crosses PCIe while piece k is indexed, packed and aligned
+  struct Piece { int64_t t0, t1; int file; };
+  std::vector<Piece> pieces;
+  const int64_t piece_bytes = std::max<int64_t>(c->chunk_reads * 320, 1 << 20);
+  for (int f = 0; f < nfiles; f++) {
+    int64_t p = tpos[f];
+    while (p < tend[f]) {
+      int64_t q = std::min(tend[f], p + piece_bytes);
+      while (q < tend[f]) {                                        // advance q to the start of a header line
+        const char* nl = (const char*)memchr(h + q, '\n', (size_t)(tend[f] - q));
+        if (!nl) { q = tend[f]; break; }
+        q = (nl - h) + 1;
+        if (q >= tend[f]) break;
+        if (h[q] != '@') continue;
+        const char* n1 = (const char*)memchr(h + q, '\n', (size_t)(tend[f] - q));
+        const char* n2 = n1 ? (const char*)memchr(n1 + 1, '\n', (size_t)(h + tend[f] - (n1 + 1))) : nullptr;
+        if (n2 && n2 + 1 < h + tend[f] && n2[1] == '+') break;
+      }
+      pieces.push_back(Piece{p, q, f});
+      p = q;
+    }
+  }
+  if ((int)c->ev_piece.size() < (int)pieces.size()) {
+    const size_t old = c->ev_piece.size();
+    c->ev_piece.resize(pieces.size());
+    for (size_t k = old; k < pieces.size(); k++) CATT_CUDA(cudaEventCreateWithFlags(&c->ev_piece[k], cudaEventDisableTiming));
+  }
+  for (size_t k = 0; k < pieces.size(); k++) {
+    CATT_CUDA(cudaMemcpyAsync(d_text + pieces[k].t0, h + pieces[k].t0, (size_t)(pieces[k].t1 - pieces[k].t0), cudaMemcpyHostToDevice, c->copy_stream));
+    CATT_CUDA(cudaEventRecord(c->ev_piece[k], c->copy_stream));
+  }
+  tr.lap("run_files: read text + queue H2D");
   std::unique_ptr<catt_result> R(new catt_result());
   int launches = 0;
   FileHits fh;
   fh.start = {0};
+  fh.v.assign(nfiles, 0); fh.j.assign(nfiles, 0);
   int64_t n = 0;
   uint64_t words = 0;
   int max_len = 0;
-  for (int f = 0; f < nfiles; f++) {
-    int64_t nf = 0; uint64_t wf = 0; int fb = 0;
-    rc = ingest_fastq(c, d_text, tpos[f], tend[f], n, words, &nf, &wf, &max_len, &fb, &launches);
+  // the seeding kernel sizes its scratch by the longest read of the sample, which is only known at the end: use the limit of the
+  // first piece's reads for that piece, then the running maximum (a later, longer read only enlarges later launches)
+  for (size_t k = 0; k < pieces.size(); k++) {
+    const Piece& pc = pieces[k];
+    if (k > 0 && pieces[k - 1].file != pc.file) fh.start.push_back(n);
+    CATT_CUDA(cudaStreamWaitEvent(c->stream, c->ev_piece[k], 0));
+    int64_t np = 0; uint64_t wp = 0; int fb = 0;
+    rc = ingest_fastq(c, d_text, pc.t0, pc.t1, n, words, &np, &wp, &max_len, &fb, &launches);
     if (rc) { if (fb) return CATT_OK; return rc; }                 // fallback: *handled stays false
-    n += nf; words += wf;
-    fh.start.push_back(n);
-    R->info.bytes_h2d += tend[f] - tpos[f];
+    R->info.bytes_h2d += pc.t1 - pc.t0;
+    DeviceReads dr;
+    dr.words = c->rd_words.as<uint32_t>(); dr.off = c->rd_off.as<uint32_t>(); dr.len = c->rd_len.as<int32_t>(); dr.n = n + np; dr.max_len = max_len;
+    for (int which = 0; which < 2; which++)
+      if ((rc = c->recs_all[which].ensure_keep((size_t)std::max<int64_t>(n + np, 1) * sizeof(catt_aln), c->stream))) return rc;
+    const int64_t file_first = fh.start[pc.file];
+    if ((rc = stage_a_range(c, dr, n, n + np, n - file_first, pc.file, &fh, &R->info, &launches))) return rc;
+    n += np; words += wp;
   }
-  tr.lap("run_files: index + pack on the device");
+  fh.start.push_back(n);
+  if ((int)fh.start.size() != nfiles + 1) { set_error("run_files: piece bookkeeping"); return CATT_E_ARG; }
+  tr.lap("run_files: index + pack + align, piece by piece");
   R->info.n_reads = n;
   DeviceReads dr;
   dr.words = c->rd_words.as<uint32_t>(); dr.off = c->rd_off.as<uint32_t>(); dr.len = c->rd_len.as<int32_t>(); dr.n = n; dr.max_len = max_len;
-  if ((rc = stage_a_resident(c, dr, 0, &fh, &R->info, &launches))) return rc;
-  tr.lap("run_files: align");
   if (c->keep_records && (rc = download_records(c, n, R.get()))) return rc;
   NamesDev nd;
   nd.s = d_text; nd.beg = reinterpret_cast<const int64_t*>(c->rd_name_beg.p); nd.end = reinterpret_cast<const int64_t*>(c->rd_name_end.p);
@@ -542,6 +593,7 @@ void catt_ctx_destroy(catt_ctx* c) {
   for (auto& row : c->ev_a) for (auto& ev : row) if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->ev_h2d) if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->ev_q) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : c->ev_piece) if (ev) cudaEventDestroy(ev);
   for (auto& b : c->rd_raw) b.release();
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);

@@ -98,6 +98,7 @@ struct catt_ctx {
   cudaEvent_t ev_a[2][EV_A]{};            // Stage A stage boundaries per reference set
   cudaEvent_t ev_h2d[2]{};                // sequence staging buffer c&1 has reached the device
   cudaEvent_t ev_q[2]{};                  // ... and the quality staging buffer
+  std::vector<cudaEvent_t> ev_piece;      // file input: piece k of the FASTQ text has reached the device
   DevBuf rd_raw[2];                       // raw bases of the chunk in flight (packed on the device)
 };
 
