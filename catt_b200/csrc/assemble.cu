@@ -376,10 +376,21 @@ struct BlockCache {
 BlockCache g_blocks;
 constexpr size_t BLOCK_SMALL = 1 << 20;            // below this plain malloc/free is fine
 constexpr size_t BLOCK_KEEP_MAX = (size_t)6 << 30;  // never sit on more than this much freed memory
+constexpr size_t BLOCK_PIN_MAX = (size_t)1 << 30;   // larger blocks are not pinned (pinning costs more than it saves per call)
 }  // namespace
 
 void* block_get(size_t bytes, size_t* cap) {
   if (bytes < BLOCK_SMALL) { *cap = bytes; return malloc(std::max<size_t>(bytes, 1)); }
+  size_t pin_max = BLOCK_PIN_MAX;
+  if (const char* e = getenv("CATT_PIN_MAX")) pin_max = (size_t)atoll(e);      // tests force the ring path on small results
+  if (bytes > pin_max) {                                 // too large to pin per call: filled through the pinned ring (d2h_ring)
+    const size_t want = (bytes + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
+    void* p = nullptr;
+    if (posix_memalign(&p, 2u << 20, want) != 0) return nullptr;
+    madvise(p, want, MADV_HUGEPAGE);
+    *cap = want | 1;                                     // odd capacity = "not registered, not cached"
+    return p;
+  }
   {
     std::lock_guard<std::mutex> lk(g_blocks.mu);
     size_t best = SIZE_MAX;
@@ -407,7 +418,7 @@ void* block_get(size_t bytes, size_t* cap) {
 
 void block_put(void* p, size_t cap) {
   if (!p) return;
-  if (cap < BLOCK_SMALL) { free(p); return; }
+  if (cap < BLOCK_SMALL || (cap & 1)) { free(p); return; }
   std::lock_guard<std::mutex> lk(g_blocks.mu);
   if (g_blocks.held + cap > BLOCK_KEEP_MAX || g_blocks.free_list.size() >= 16) {
     if (cudaHostUnregister(p) != cudaSuccess) cudaGetLastError();
@@ -428,6 +439,35 @@ struct StrLut {
 const StrLut SLUT;
 
 }  // namespace
+
+// device -> host copy of one result arena.  Pinned (cached) blocks take one bulk copy; larger, unpinned blocks are filled through
+// two pinned 64 MiB ring buffers: the copy engine fills one while the host threads empty the other into the destination.
+static int d2h_arena(catt_ctx* c, void* dst, size_t cap, const void* d_src, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return CATT_OK;
+  if (!(cap & 1) || bytes < BLOCK_SMALL) { CATT_CUDA(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, st)); return CATT_OK; }
+  const size_t piece = (size_t)64 << 20;
+  int rc;
+  if ((rc = c->pin[PIN_RING0].ensure(piece)) || (rc = c->pin[PIN_RING1].ensure(piece))) return rc;
+  const size_t np = (bytes + piece - 1) / piece;
+  auto issue = [&](size_t i) -> int {
+    const size_t o = i * piece, len = std::min(piece, bytes - o);
+    CATT_CUDA(cudaMemcpyAsync(c->pin[PIN_RING0 + (i & 1)].p, (const char*)d_src + o, len, cudaMemcpyDeviceToHost, st));
+    CATT_CUDA(cudaEventRecord(c->ev_q[i & 1], st));
+    return CATT_OK;
+  };
+  auto drain = [&](size_t i) -> int {
+    const size_t o = i * piece, len = std::min(piece, bytes - o);
+    CATT_CUDA(cudaEventSynchronize(c->ev_q[i & 1]));
+    const char* src = c->pin[PIN_RING0 + (i & 1)].as<char>();
+    const int64_t sub = 1 << 20, ns = (int64_t)((len + sub - 1) / sub);
+    #pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < ns; k++) memcpy((char*)dst + o + k * sub, src + k * sub, (size_t)std::min<int64_t>(sub, (int64_t)len - k * sub));
+    return CATT_OK;
+  };
+  if ((rc = issue(0))) return rc;
+  for (size_t i = 1; i < np; i++) { if ((rc = issue(i)) || (rc = drain(i - 1))) return rc; }
+  return drain(np - 1);
+}
 
 int upload_names(catt_ctx* c, int64_t n, const char* names, const int64_t* name_off, NamesDev* out, catt_info* info) {
   *out = NamesDev{};
@@ -695,9 +735,8 @@ int stage_b(catt_ctx* c, int64_t n, const NamesDev& names, const ReadsDev& reads
     CATT_CUDA(cudaGetLastError());
     *launches += 1;
     CATT_CUDA(cudaEventRecord(c->ev[6], st));
-    CATT_CUDA(cudaMemcpyAsync(R->seq_arena, d_seq, seq_bytes - 1, cudaMemcpyDeviceToHost, st));
-    CATT_CUDA(cudaMemcpyAsync(R->qual_arena, d_qual, qual_bytes - 1, cudaMemcpyDeviceToHost, st));
-    CATT_CUDA(cudaMemcpyAsync(R->part[0], d_part, (size_t)M * sizeof(catt_read), cudaMemcpyDeviceToHost, st));
+    if ((rc = d2h_arena(c, R->seq_arena, R->cap_seq, d_seq, seq_bytes - 1, st)) || (rc = d2h_arena(c, R->qual_arena, R->cap_qual, d_qual, qual_bytes - 1, st)) ||
+        (rc = d2h_arena(c, R->part[0], R->cap_part[0], d_part, (size_t)M * sizeof(catt_read), st))) return rc;
     CATT_CUDA(cudaEventRecord(c->ev[7], st));
     CATT_CUDA(cudaStreamSynchronize(st));
     info.bytes_d2h += (int64_t)(seq_bytes + qual_bytes - 2) + M * (int64_t)sizeof(catt_read) + (2 + nfiles) * C_COUNT * 8;

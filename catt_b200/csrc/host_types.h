@@ -73,7 +73,7 @@ enum {
   SB_EOUT, SB_KFLAG, SB_KFLAG1, SB_KPOS2, SB_KPOS3, SB_PFLAG, SB_XPOS, SB_TAB_KEYS, SB_TAB_VALS, SB_PITEMS, SB_PARTIAL, SB_XOUT, SB_DESC, SB_SSZ, SB_QSZ, SB_SOFF, SB_QOFF, SB_OUT_SEQ, SB_OUT_QUAL, SB_OUT_PART, SB_CNT, SB_CUB,
   SB_COUNT
 };
-enum { PIN_PACK0 = 0, PIN_PACK1, PIN_QUAL0, PIN_QUAL1, PIN_OFF, PIN_LEN, PIN_CNT, PIN_DESC, PIN_XOUT, PIN_TEXT, PIN_COUNT };
+enum { PIN_PACK0 = 0, PIN_PACK1, PIN_QUAL0, PIN_QUAL1, PIN_OFF, PIN_LEN, PIN_CNT, PIN_DESC, PIN_XOUT, PIN_TEXT, PIN_RING0, PIN_RING1, PIN_COUNT };
 constexpr int EV_A = 6;     // per reference set: seed start, seed end, expand end, sw end, select end
 
 struct catt_ctx {

@@ -383,3 +383,20 @@ def test_fastq_ingest_on_device_equals_host_parser(ctx, O, orefs, trb, sample, t
     with pytest.raises(_lib.CattError) as ei:
         ctx.mainflow(p)
     assert ei.value.code == -2
+
+
+def test_large_result_ring_copy(ctx, O, orefs, trb, sample):
+    """Results too large to pin per call come back through the two pinned ring buffers (forced here with CATT_PIN_MAX)."""
+    names, seqs, quals = [x[:7000] for x in sample]
+    want = ctx.mainflow_reads(names, seqs, quals)
+    a = ([myread_tuple(r) for r in want.Vpart], [myread_tuple(r) for r in want.Jpart])
+    os.environ["CATT_PIN_MAX"] = "1"
+    try:
+        got = ctx.mainflow_reads(names * 8, seqs * 8, quals * 8)       # > 1 MiB of strings: above the malloc threshold
+        ref = ctx_ref = None
+    finally:
+        os.environ.pop("CATT_PIN_MAX", None)
+    again = ctx.mainflow_reads(names * 8, seqs * 8, quals * 8)
+    assert ([myread_tuple(r) for r in got.Vpart], [myread_tuple(r) for r in got.Jpart]) == \
+           ([myread_tuple(r) for r in again.Vpart], [myread_tuple(r) for r in again.Jpart])
+    assert len(got.Vpart) >= len(a[0])
