@@ -234,7 +234,9 @@ def main():
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     host_threads = max(1, len(os.sched_getaffinity(0)) // max(1, local_world))
     set_host_threads(host_threads)
-    ctx = Catt(chain_cfg=cc, device=local_rank)
+    # the production setting of INTEGRATION.md: the lists as catt() uses them (after catt.jl:581-582); e2e_full_lists below measures
+    # the same call returning every Vpart/Jpart read
+    ctx = Catt(chain_cfg=cc, device=local_rank, only_cdr3=True)
     R = args.reads_per_step
     first = rank * R
     name_buf, name_off, seq_buf, seq_off, qual_buf = ctx.synth_reads(R, args.length, first_index=first, seed=SEED)
@@ -305,7 +307,8 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
         "config": {"workload": workload, "reads_per_step_per_gpu": R, "read_length": args.length, "chain": "hs TRB",
                    "l2": f"packed batch {packed_bytes >> 20} MiB per step vs 126 MB L2" + (" (larger than L2)" if packed_bytes > 126e6 else " (compute-bound kernel; see DESIGN.md)"),
-                   "multi_gpu": "shards are independent samples; no data-path collective", "host_threads_per_rank": host_threads},
+                   "multi_gpu": "shards are independent samples; no data-path collective", "host_threads_per_rank": host_threads,
+                   "result": "only_cdr3 = 1: Vpart/Jpart as they stand after catt.jl:581-582 (the reads catt() goes on to use); counters of the full lists in info"},
         "gcups": world * cells / (sw_ms * 1e-3) / 1e9,
         "gcups_note": "DP cell updates / SW-kernel time (CUDA events in the library), summed over GPUs",
         "stage_ms": {k: sum(i[k] for i in infos) / len(infos) for k in ("ms_seed", "ms_sw", "ms_select", "ms_order", "ms_extract", "ms_pool", "ms_strings", "ms_d2h", "ms_host", "ms_pack")},
@@ -325,6 +328,21 @@ def main():
         "roofline_other": roofline_other(infos, args.length, world),
         "counters": {k: info[k] for k in ("v_hits", "j_hits", "vpart", "jpart", "direct", "left", "rescued", "cand_v", "cand_j", "gapped_v")},
     }
+    if rank == 0 and world == 1:
+        ctx_full = Catt(chain_cfg=cc, device=local_rank)
+        for _ in range(2):
+            ctx_full.mainflow_buffers(R, name_buf, name_off, seq_buf, seq_off, qual_buf).close()
+        t0 = time.perf_counter()
+        fi = None
+        for _ in range(args.steps):
+            rr = ctx_full.mainflow_buffers(R, name_buf, name_off, seq_buf, seq_off, qual_buf)
+            fi = rr.info
+            rr.close()
+        dtf = time.perf_counter() - t0
+        line["e2e_full_lists"] = {"value": R * args.steps / dtf, "unit": "reads/s", "ms_per_step": 1e3 * dtf / args.steps,
+                                  "h2d_bytes_per_step": fi["bytes_h2d"], "d2h_bytes_per_step": fi["bytes_d2h"],
+                                  "note": "only_cdr3 = 0: every Vpart/Jpart read comes back, cdr3 == None included (the lists before catt.jl:581)"}
+        ctx_full.close()
     if rank == 0 and world == 1 and not args.no_file_e2e:
         line["e2e_file"] = file_e2e(ctx, np, R, args.length, seq_buf, qual_buf, first)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

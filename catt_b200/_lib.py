@@ -22,7 +22,7 @@ class Config(C.Structure):
                 ("inner_c", C.c_char_p), ("inner_f", C.c_char_p), ("coffset", C.c_int32), ("foffset", C.c_int32),
                 ("min_score", C.c_int32), ("kmer", C.c_int32), ("julia_nthreads", C.c_int32), ("allow_v", C.c_int32),
                 ("allow_j", C.c_int32), ("device", C.c_int32), ("n_d", C.c_int32), ("d_names", C.POINTER(C.c_char_p)),
-                ("d_seqs", C.POINTER(C.c_char_p)), ("keep_records", C.c_int32), ("chunk_reads", C.c_int32)]
+                ("d_seqs", C.POINTER(C.c_char_p)), ("keep_records", C.c_int32), ("chunk_reads", C.c_int32), ("only_cdr3", C.c_int32), ("reserved_", C.c_int32)]
 
 
 ALN_DTYPE = np.dtype([("ordinal", "<i4"), ("rid", "<i4"), ("strand", "<i2"), ("mapped", "<i2"), ("as", "<i2"), ("qb", "<i2"),

@@ -564,6 +564,7 @@ int catt_ctx_create(catt_ctx** out, const catt_config* cfg) {
     CATT_CUDA(cudaMemcpy(c->d_doff, off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   }
   c->keep_records = cfg->keep_records != 0;
+  c->only_cdr3 = cfg->only_cdr3 != 0;
   if (cfg->chunk_reads > 0) c->chunk_reads = cfg->chunk_reads;
   if (const char* e = getenv("CATT_CHUNK_READS")) { const long long v = atoll(e); if (v > 0) c->chunk_reads = v; }
   CATT_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));

@@ -33,7 +33,7 @@ constexpr uint32_t INF = 0xFFFFFFFFu;
 constexpr unsigned FULL = 0xffffffffu;
 // device counters (SB_CNT, unsigned long long each)
 enum { C_NMAP_V = 0, C_NMAP_J, C_F_V, C_F_J, C_NV, C_NJ, C_NP, C_MAXNAME, C_SUM_LEN, C_SUM_NM, C_SUM_MI, C_MISMATCH, C_M, C_VPART,
-       C_FULL, C_NPARTIAL, C_RESCUED, C_COUNT = 24 };
+       C_FULL, C_NPARTIAL, C_RESCUED, C_E, C_EV, C_COUNT = 24 };
 
 
 __device__ __forceinline__ int trimmed_len(const char* s, int l) {            // bwa trim_readno
@@ -253,8 +253,25 @@ __global__ void partial_kernel(int64_t n_items, const uint32_t* __restrict__ pfl
 struct StrSrc {
   const OutDesc* desc; const ExtendOut* xout;     // xout == nullptr: no extension pass ran (every partial read keeps n_ext = 0)
   const char* quals; const int64_t* seq_off;      // quals == nullptr: FASTA input, 'I' everywhere
-  int64_t M, vpart;
+  int64_t M, vpart;                               // all Vpart/Jpart reads; the first vpart are Vpart
+  const uint32_t* map; int64_t E;                 // output entry e is read map[e] (map == nullptr: every read, E == M)
 };
+__device__ __forceinline__ int64_t str_read(const StrSrc& S, int64_t e) { return S.map ? (int64_t)S.map[e] : e; }
+
+// only_cdr3: which reads survive `filter!(x -> x.cdr3 != "None", ...)` (catt.jl:581-582)
+__global__ void cdr3_flag_kernel(const OutDesc* __restrict__ desc, const ExtendOut* __restrict__ xout, int64_t M, uint32_t* __restrict__ flag) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m > M) return;
+  if (m == M) { flag[m] = 0; return; }
+  const OutDesc p = desc[m];
+  flag[m] = p.xi >= 0 ? (xout != nullptr && xout[p.xi].cdr3_off >= 0) : (p.cdr3_off >= 0);
+}
+__global__ void cdr3_map_kernel(const uint32_t* __restrict__ flag, const uint32_t* __restrict__ pos, int64_t M, int64_t vpart,
+                                uint32_t* __restrict__ map, unsigned long long* __restrict__ cnt) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m == 0) { cnt[C_E] = pos[M]; cnt[C_EV] = pos[vpart]; }
+  if (m < M && flag[m]) map[pos[m]] = (uint32_t)m;
+}
 __device__ __forceinline__ void str_dims(const StrSrc& S, int64_t m, int* n_ext, int* c_off, int* c_len, int* slen, int* qlen, int* base_q) {
   const OutDesc p = S.desc[m];
   *n_ext = 0; *c_off = p.cdr3_off; *c_len = p.cdr3_len;
@@ -268,12 +285,12 @@ __device__ __forceinline__ void str_dims(const StrSrc& S, int64_t m, int* n_ext,
 }
 
 __global__ void strsize_kernel(StrSrc S, unsigned long long* __restrict__ ssz, unsigned long long* __restrict__ qsz) {
-  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m > S.M) return;
-  if (m == S.M) { ssz[m] = 0; qsz[m] = 0; return; }
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e > S.E) return;
+  if (e == S.E) { ssz[e] = 0; qsz[e] = 0; return; }
   int n_ext, c_off, c_len, slen, qlen, base_q;
-  str_dims(S, m, &n_ext, &c_off, &c_len, &slen, &qlen, &base_q);
-  ssz[m] = (unsigned long long)slen + 1; qsz[m] = (unsigned long long)qlen + 1;
+  str_dims(S, str_read(S, e), &n_ext, &c_off, &c_len, &slen, &qlen, &base_q);
+  ssz[e] = (unsigned long long)slen + 1; qsz[e] = (unsigned long long)qlen + 1;
 }
 
 constexpr int MW = 8;   // warps per CTA
@@ -283,7 +300,8 @@ __global__ void __launch_bounds__(MW * 32) materialise_kernel(StrSrc S, ReadsDev
                                                               const char* host_seq, const char* host_qual) {
   const int lane = threadIdx.x & 31;
   const char NT[5] = {'A', 'C', 'G', 'T', 'N'};
-  for (int64_t m = (int64_t)blockIdx.x * MW + (threadIdx.x >> 5); m < S.M; m += (int64_t)gridDim.x * MW) {
+  for (int64_t e_ = (int64_t)blockIdx.x * MW + (threadIdx.x >> 5); e_ < S.E; e_ += (int64_t)gridDim.x * MW) {
+    const int64_t m = str_read(S, e_);
     const OutDesc p = S.desc[m];
     int n_ext, c_off, c_len, slen, qlen, base_q;
     str_dims(S, m, &n_ext, &c_off, &c_len, &slen, &qlen, &base_q);
@@ -293,7 +311,7 @@ __global__ void __launch_bounds__(MW * 32) materialise_kernel(StrSrc S, ReadsDev
     const int len = reads.len[p.read];
     const uint32_t* __restrict__ w = reads.words + reads.off[p.read];
     const uint32_t* __restrict__ nm = w + read_base_words(len);
-    char* s = seq_arena + soff[m];
+    char* s = seq_arena + soff[e_];
     for (int i = lane; i <= slen; i += 32) {
       char ch = 0;
       if (i < slen) {
@@ -317,7 +335,7 @@ __global__ void __launch_bounds__(MW * 32) materialise_kernel(StrSrc S, ReadsDev
     const int src0 = p.kind == 1 ? 0 : p.seq_off;
     const int a0 = c_off >= 0 ? c_off : 0;
     const char* rq = S.quals ? S.quals + S.seq_off[p.read] : nullptr;
-    char* q = qual_arena + qoff[m];
+    char* q = qual_arena + qoff[e_];
     for (int i = lane; i <= qlen; i += 32) {
       char ch = 0;
       if (i < qlen) {
@@ -332,12 +350,12 @@ __global__ void __launch_bounds__(MW * 32) materialise_kernel(StrSrc S, ReadsDev
     }
     if (lane == 0) {
       catt_read rd;
-      rd.seq = host_seq + soff[m]; rd.qual = host_qual + qoff[m]; rd.seq_len = slen; rd.qual_len = qlen;
+      rd.seq = host_seq + soff[e_]; rd.qual = host_qual + qoff[e_]; rd.seq_len = slen; rd.qual_len = qlen;
       rd.v_id = p.v_id; rd.j_id = p.j_id; rd.cdr3_off = c_off; rd.cdr3_len = c_off >= 0 ? c_len : 0;
       rd.ordinal = (int32_t)p.read; rd.able = 1;
       rd.flags = (uint8_t)((p.kind == 0 ? 1 : p.kind == 1 ? 2 : 4) | ((c_off >= 0 && c_off + c_len > qfull) ? 8 : 0));   // 8: reference BoundsError
       rd.pad_[0] = 0; rd.pad_[1] = 0;
-      part[m] = rd;
+      part[e_] = rd;
     }
   }
 }
@@ -693,53 +711,69 @@ int stage_b(catt_ctx* c, int64_t n, const NamesDev& names, const ReadsDev& reads
   CATT_CUDA(cudaEventRecord(c->ev[6], st));
   // ---- the Myread strings: sizes -> offsets (scans) -> one warp per read writes both strings and the catt_read entry; the
   //      arenas go to the host as three bulk copies into pinned result blocks
-  StrSrc S{desc, xout, dq.quals, dq.seq_off, M, info.vpart};
+  StrSrc S{desc, xout, dq.quals, dq.seq_off, M, info.vpart, nullptr, M};
+  int64_t E = M, EV = info.vpart;
+  if (c->only_cdr3 && M > 0) {                      // the lists as they stand after catt.jl:581-582
+    uint32_t *cflag, *cpos, *cmap;
+    if ((rc = ensure(c, SB_CFLAG, M + 1, &cflag)) || (rc = ensure(c, SB_CPOS, M + 1, &cpos)) || (rc = ensure(c, SB_CMAP, M, &cmap))) return rc;
+    cdr3_flag_kernel<<<nblk(M + 1), 256, 0, st>>>(desc, xout, M, cflag);
+    CATT_CUDA(cudaGetLastError());
+    if ((rc = scan_u32(c, cflag, cpos, M + 1, st))) return rc;
+    cdr3_map_kernel<<<nblk(M), 256, 0, st>>>(cflag, cpos, M, info.vpart, cmap, cnt);
+    CATT_CUDA(cudaGetLastError());
+    *launches += 4;
+    unsigned long long ev2[2];
+    CATT_CUDA(cudaMemcpyAsync(ev2, cnt + C_E, sizeof ev2, cudaMemcpyDeviceToHost, st));
+    CATT_CUDA(cudaStreamSynchronize(st));
+    E = (int64_t)ev2[0]; EV = (int64_t)ev2[1];
+    S.map = cmap; S.E = E;
+  }
   unsigned long long *ssz, *qsz, *soff, *qoff;
-  if ((rc = ensure(c, SB_SSZ, M + 1, &ssz)) || (rc = ensure(c, SB_QSZ, M + 1, &qsz)) || (rc = ensure(c, SB_SOFF, M + 1, &soff)) ||
-      (rc = ensure(c, SB_QOFF, M + 1, &qoff))) return rc;
-  strsize_kernel<<<nblk(M + 1), 256, 0, st>>>(S, ssz, qsz);
+  if ((rc = ensure(c, SB_SSZ, E + 1, &ssz)) || (rc = ensure(c, SB_QSZ, E + 1, &qsz)) || (rc = ensure(c, SB_SOFF, E + 1, &soff)) ||
+      (rc = ensure(c, SB_QOFF, E + 1, &qoff))) return rc;
+  strsize_kernel<<<nblk(E + 1), 256, 0, st>>>(S, ssz, qsz);
   CATT_CUDA(cudaGetLastError());
   for (int which = 0; which < 2; which++) {
     size_t need = 0;
-    CATT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, which ? qsz : ssz, which ? qoff : soff, M + 1, st));
+    CATT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, which ? qsz : ssz, which ? qoff : soff, E + 1, st));
     if ((rc = ensure_cub(c, need))) return rc;
     need = c->sb[SB_CUB].cap;
-    CATT_CUDA(cub::DeviceScan::ExclusiveSum(c->sb[SB_CUB].p, need, which ? qsz : ssz, which ? qoff : soff, M + 1, st));
+    CATT_CUDA(cub::DeviceScan::ExclusiveSum(c->sb[SB_CUB].p, need, which ? qsz : ssz, which ? qoff : soff, E + 1, st));
   }
   *launches += 5;
   CATT_CUDA(cudaMemcpyAsync(hcnt, cnt, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-  CATT_CUDA(cudaMemcpyAsync(hcnt + C_COUNT, soff + M, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-  CATT_CUDA(cudaMemcpyAsync(hcnt + C_COUNT + 1, qoff + M, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CATT_CUDA(cudaMemcpyAsync(hcnt + C_COUNT, soff + E, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CATT_CUDA(cudaMemcpyAsync(hcnt + C_COUNT + 1, qoff + E, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   CATT_CUDA(cudaStreamSynchronize(st));
   { float a = 0; cudaEventElapsedTime(&a, c->ev[5], c->ev[6]); info.ms_pool += a; }
   if (run_pool) { float a = 0; cudaEventElapsedTime(&a, c->ev[0], c->ev[1]); info.ms_pool_kernel += a; }
   info.rescued += (int64_t)(uint32_t)hcnt[C_RESCUED];
   tr.lap("B: pool + extend + string sizes");
   const double t2 = now_ms();
-  const size_t seq_bytes = (size_t)hcnt[C_COUNT] + 1, qual_bytes = (size_t)hcnt[C_COUNT + 1] + 1, part_bytes = (size_t)std::max<int64_t>(M, 1) * sizeof(catt_read);
+  const size_t seq_bytes = (size_t)hcnt[C_COUNT] + 1, qual_bytes = (size_t)hcnt[C_COUNT + 1] + 1, part_bytes = (size_t)std::max<int64_t>(E, 1) * sizeof(catt_read);
   R->seq_arena = (char*)block_get(seq_bytes, &R->cap_seq);
   R->qual_arena = (char*)block_get(qual_bytes, &R->cap_qual);
   R->part[0] = (catt_read*)block_get(part_bytes, &R->cap_part[0]);
   if (!R->seq_arena || !R->qual_arena || !R->part[0]) { set_error("out of host memory for the result"); return CATT_E_LIMIT; }
-  R->npart[0] = info.vpart; R->npart[1] = info.jpart;
-  R->part[1] = R->part[0] + info.vpart;             // one block: Vpart entries, then Jpart entries
+  R->npart[0] = EV; R->npart[1] = E - EV;
+  R->part[1] = R->part[0] + EV;                     // one block: Vpart entries, then Jpart entries
   info.ms_host += now_ms() - t2;
   tr.lap("B: result blocks");
-  if (M > 0) {
+  if (E > 0) {
     char *d_seq, *d_qual; catt_read* d_part;
     if ((rc = ensure(c, SB_OUT_SEQ, (int64_t)seq_bytes, &d_seq)) || (rc = ensure(c, SB_OUT_QUAL, (int64_t)qual_bytes, &d_qual)) ||
-        (rc = ensure(c, SB_OUT_PART, M, &d_part))) return rc;
+        (rc = ensure(c, SB_OUT_PART, E, &d_part))) return rc;
     CATT_CUDA(cudaEventRecord(c->ev[5], st));
-    const int grid = (int)std::min<int64_t>((M + MW - 1) / MW, (int64_t)c->sm_count * 16);
+    const int grid = (int)std::min<int64_t>((E + MW - 1) / MW, (int64_t)c->sm_count * 16);
     materialise_kernel<<<grid, MW * 32, 0, st>>>(S, reads, soff, qoff, d_seq, d_qual, d_part, R->seq_arena, R->qual_arena);
     CATT_CUDA(cudaGetLastError());
     *launches += 1;
     CATT_CUDA(cudaEventRecord(c->ev[6], st));
     if ((rc = d2h_arena(c, R->seq_arena, R->cap_seq, d_seq, seq_bytes - 1, st)) || (rc = d2h_arena(c, R->qual_arena, R->cap_qual, d_qual, qual_bytes - 1, st)) ||
-        (rc = d2h_arena(c, R->part[0], R->cap_part[0], d_part, (size_t)M * sizeof(catt_read), st))) return rc;
+        (rc = d2h_arena(c, R->part[0], R->cap_part[0], d_part, (size_t)E * sizeof(catt_read), st))) return rc;
     CATT_CUDA(cudaEventRecord(c->ev[7], st));
     CATT_CUDA(cudaStreamSynchronize(st));
-    info.bytes_d2h += (int64_t)(seq_bytes + qual_bytes - 2) + M * (int64_t)sizeof(catt_read) + (2 + nfiles) * C_COUNT * 8;
+    info.bytes_d2h += (int64_t)(seq_bytes + qual_bytes - 2) + E * (int64_t)sizeof(catt_read) + (2 + nfiles) * C_COUNT * 8;
     { float a = 0, b2 = 0; cudaEventElapsedTime(&a, c->ev[5], c->ev[6]); cudaEventElapsedTime(&b2, c->ev[6], c->ev[7]); info.ms_strings += a; info.ms_d2h += b2; }
   }
   tr.lap("B: strings + D2H");

@@ -70,7 +70,7 @@ struct PinBuf {
 enum {
   SB_NAMES = 0, SB_NAME_OFF, SB_NAME_END, SB_SLOT_OF, SB_OWNER, SB_MINV, SB_MINJ, SB_KEYS_A, SB_SORT_V, SB_SORT_J, SB_FLAG, SB_KPOS_V,
   SB_KPOS_J, SB_ORD_IDX_V, SB_ORD_IDX_J, SB_ORD_FLAG_V, SB_ORD_FLAG_J, SB_OPOS_V, SB_OPOS_J, SB_PAIR_A, SB_PAIR_B, SB_PKEY_A, SB_PKEY_B, SB_ITEMS,
-  SB_EOUT, SB_KFLAG, SB_KFLAG1, SB_KPOS2, SB_KPOS3, SB_PFLAG, SB_XPOS, SB_TAB_KEYS, SB_TAB_VALS, SB_PITEMS, SB_PARTIAL, SB_XOUT, SB_DESC, SB_SSZ, SB_QSZ, SB_SOFF, SB_QOFF, SB_OUT_SEQ, SB_OUT_QUAL, SB_OUT_PART, SB_CNT, SB_CUB,
+  SB_EOUT, SB_KFLAG, SB_KFLAG1, SB_KPOS2, SB_KPOS3, SB_PFLAG, SB_XPOS, SB_TAB_KEYS, SB_TAB_VALS, SB_PITEMS, SB_PARTIAL, SB_XOUT, SB_DESC, SB_SSZ, SB_QSZ, SB_SOFF, SB_QOFF, SB_OUT_SEQ, SB_OUT_QUAL, SB_OUT_PART, SB_CFLAG, SB_CPOS, SB_CMAP, SB_CNT, SB_CUB,
   SB_COUNT
 };
 enum { PIN_PACK0 = 0, PIN_PACK1, PIN_QUAL0, PIN_QUAL1, PIN_OFF, PIN_LEN, PIN_CNT, PIN_DESC, PIN_XOUT, PIN_TEXT, PIN_RING0, PIN_RING1, PIN_COUNT };
@@ -82,6 +82,7 @@ struct catt_ctx {
   catt::FinderDev* d_finder = nullptr;
   int min_score = 12, kmer = CATT_KMER_AUTO, nthreads = 1, allow_v = 3, allow_j = 9, device = 0, sm_count = 148;
   int keep_records = 0;                   // download the per-read alignment records into every result (diagnostics)
+  int only_cdr3 = 0;                      // return the lists as they stand after filter!(x -> x.cdr3 != "None") (catt.jl:581-582)
   int64_t chunk_reads = 1 << 18;          // Stage A batch size of the pipelined path
   cudaStream_t stream = nullptr;          // kernels
   cudaStream_t copy_stream = nullptr;     // H2D of the packed chunks, under the kernels of the previous chunk

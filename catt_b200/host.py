@@ -138,7 +138,7 @@ class Catt:
     """One CATT configuration bound to one GPU (catt_ctx)."""
 
     def __init__(self, species="hs", chain="TRB", region="CDR3", resource_dir=None, bowsc=12, kmer=10000, thread=1,
-                 allow_v=3, allow_j=9, device=0, chain_cfg=None, keep_records=False, chunk_reads=0):
+                 allow_v=3, allow_j=9, device=0, chain_cfg=None, keep_records=False, chunk_reads=0, only_cdr3=False):
         L = _lib.load()
         cc = chain_cfg or chain_config(species, chain, region, resource_dir)
         self.chain_cfg = cc
@@ -147,7 +147,7 @@ class Catt:
                       (C.c_char_p * max(len(d), 1))(*[x[1].encode() for x in d])]
         cfg = _lib.Config(cc["vregion"].encode(), cc["jregion"].encode(), cc["cmotif"].encode(), cc["fmotif"].encode(),
                           cc["innerC"].encode(), cc["innerF"].encode(), cc["coffset"], cc["foffset"], bowsc, kmer, thread,
-                          allow_v, allow_j, device, len(d), self._keep[0], self._keep[1], int(keep_records), int(chunk_reads))
+                          allow_v, allow_j, device, len(d), self._keep[0], self._keep[1], int(keep_records), int(chunk_reads), int(only_cdr3), 0)
         h = C.c_void_p()
         _lib.check(L.catt_ctx_create(C.byref(h), C.byref(cfg)))
         self._h = h

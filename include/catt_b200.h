@@ -54,6 +54,11 @@ typedef struct catt_config {
                                64 B/read device->host copy, so it is off on the production path */
   int32_t chunk_reads;      /* Stage A batch size of the pipelined path (0 = default 262144): host packing + H2D of chunk
                                i+1 run under the kernels of chunk i */
+  int32_t only_cdr3;        /* 0: Vpart / Jpart exactly as catt() holds them before catt.jl:581 (every read, cdr3 "None" included);
+                               1: as they stand after catt.jl:581-582, `filter!(x -> x.cdr3 != "None", ...)` - the only reads the
+                               rest of catt() ever touches; catt_info still carries the counts of the full lists for the log
+                               lines.  Cuts the device->host traffic ~50x on typical samples. */
+  int32_t reserved_;
 } catt_config;
 
 /* One SAM-visible alignment record = the line `bwa mem | samtools ... | awk` would leave for one read against one

@@ -400,3 +400,23 @@ def test_large_result_ring_copy(ctx, O, orefs, trb, sample):
     assert ([myread_tuple(r) for r in got.Vpart], [myread_tuple(r) for r in got.Jpart]) == \
            ([myread_tuple(r) for r in again.Vpart], [myread_tuple(r) for r in again.Jpart])
     assert len(got.Vpart) >= len(a[0])
+
+
+def test_only_cdr3_lists(trb, O, orefs):
+    """only_cdr3 = 1 returns the lists as they stand after catt.jl:581-582 (filter cdr3 != "None"): same reads, same order, same
+    strings as the filtered full lists; the info counters still describe the full lists."""
+    from catt_b200.host import Catt
+    V, J = orefs
+    names, seqs, quals = synth_reads(6000, [V.record(i) for i in range(V.nrec)], [J.record(i) for i in range(J.nrec)], 100, seed=77)
+    full_ctx, cdr3_ctx = Catt(chain_cfg=trb), Catt(chain_cfg=trb, only_cdr3=True)
+    full, comp = full_ctx.mainflow_reads(names, seqs, quals), cdr3_ctx.mainflow_reads(names, seqs, quals)
+    fv = [myread_tuple(r) for r in full.Vpart if r.cdr3 != "None"]
+    fj = [myread_tuple(r) for r in full.Jpart if r.cdr3 != "None"]
+    assert len(fv) + len(fj) > 20
+    assert [myread_tuple(r) for r in comp.Vpart] == fv and [myread_tuple(r) for r in comp.Jpart] == fj
+    for k in ("vpart", "jpart", "direct", "left", "rescued", "kmer", "the_err"):
+        assert comp.info[k] == full.info[k]
+    assert comp.info["bytes_d2h"] < full.info["bytes_d2h"] / 5
+    ref = O.run_mem(V, J, O.make_config(trb), names, seqs, quals)
+    assert [myread_tuple(r) for r in ref.Vpart if r.cdr3 != "None"] == fv
+    full_ctx.close(); cdr3_ctx.close()
