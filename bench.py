@@ -276,7 +276,8 @@ def main():
         res.close()
         return info
 
-    step_e2e()
+    for _ in range(max(2, min(args.warmup, 3))):
+        step_e2e()
     barrier()
     t0 = time.perf_counter()
     e2e_infos = [step_e2e() for _ in range(args.steps)]
