@@ -207,10 +207,13 @@ int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool
   std::vector<Chunk> chunks;
   const int nfiles = (int)fh->start.size() - 1;
   fh->v.assign(nfiles, 0); fh->j.assign(nfiles, 0);
-  // the very first chunk is small: nothing hides its packing / upload, so the GPU should get work as early as possible
+  // the first chunk is small (nothing hides its copy, the GPU should get work early) and the sizes ramp up x4 per chunk: the
+  // copy of chunk i+1 always fits under the kernels of chunk i
+  int64_t ramp = std::max<int64_t>(c->chunk_reads / 64, 1024);
   for (int f = 0; f < nfiles; f++)
     for (int64_t i0 = fh->start[f]; i0 < fh->start[f + 1];) {
-      const int64_t want = chunks.empty() ? std::max<int64_t>(c->chunk_reads / 8, 1024) : c->chunk_reads;
+      const int64_t want = std::min<int64_t>(ramp, c->chunk_reads);
+      ramp = std::min<int64_t>(ramp * 4, c->chunk_reads);
       const int64_t cnt = std::min<int64_t>(want, fh->start[f + 1] - i0);
       chunks.push_back(Chunk{i0, cnt, first_ordinal + (i0 - fh->start[f]), f});
       i0 += cnt;
@@ -406,11 +409,13 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
   // with '+'), queued on the copy stream up front: piece k+1 crosses PCIe while piece k is indexed, packed and aligned
   struct Piece { int64_t t0, t1; int file; };
   std::vector<Piece> pieces;
-  const int64_t piece_bytes = std::max<int64_t>(c->chunk_reads * 320, 1 << 20);
+  const int64_t piece_max = std::max<int64_t>(c->chunk_reads * 320, 1 << 20);
+  int64_t piece_bytes = std::max<int64_t>(piece_max / 64, 1 << 20);          // small first piece, x4 ramp (see stage_a_stream)
   for (int f = 0; f < nfiles; f++) {
     int64_t p = tpos[f];
     while (p < tend[f]) {
       int64_t q = std::min(tend[f], p + piece_bytes);
+      piece_bytes = std::min(piece_bytes * 4, piece_max);
       while (q < tend[f]) {                                        // advance q to the start of a header line
         const char* nl = (const char*)memchr(h + q, '\n', (size_t)(tend[f] - q));
         if (!nl) { q = tend[f]; break; }

@@ -83,7 +83,7 @@ struct catt_ctx {
   int min_score = 12, kmer = CATT_KMER_AUTO, nthreads = 1, allow_v = 3, allow_j = 9, device = 0, sm_count = 148;
   int keep_records = 0;                   // download the per-read alignment records into every result (diagnostics)
   int only_cdr3 = 0;                      // return the lists as they stand after filter!(x -> x.cdr3 != "None") (catt.jl:581-582)
-  int64_t chunk_reads = 1 << 18;          // Stage A batch size of the pipelined path
+  int64_t chunk_reads = 1 << 20;          // Stage A batch size of the pipelined path
   cudaStream_t stream = nullptr;          // kernels
   cudaStream_t copy_stream = nullptr;     // H2D of the packed chunks, under the kernels of the previous chunk
   std::vector<std::string> d_names, d_seqs;

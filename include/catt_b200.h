@@ -52,7 +52,7 @@ typedef struct catt_config {
   const char* const* d_seqs;
   int32_t keep_records;     /* 1: every result also carries the per-read alignment records (catt_align_records); costs a
                                64 B/read device->host copy, so it is off on the production path */
-  int32_t chunk_reads;      /* Stage A batch size of the pipelined path (0 = default 262144): host packing + H2D of chunk
+  int32_t chunk_reads;      /* Stage A batch size of the pipelined path (0 = default 1048576): host packing + H2D of chunk
                                i+1 run under the kernels of chunk i */
   int32_t only_cdr3;        /* 0: Vpart / Jpart exactly as catt() holds them before catt.jl:581 (every read, cdr3 "None" included);
                                1: as they stand after catt.jl:581-582, `filter!(x -> x.cdr3 != "None", ...)` - the only reads the
