@@ -4,7 +4,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -375,70 +378,121 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
   if ((rc = c->pin[PIN_TEXT].ensure((size_t)tpos[nfiles] + 16)) || (rc = c->rd_text.ensure((size_t)tpos[nfiles] + 16))) return rc;
   char* h = c->pin[PIN_TEXT].as<char>();
   char* d_text = c->rd_text.as<char>();
-  std::vector<int64_t> tend((size_t)nfiles, 0);
-  for (int f = 0; f < nfiles; f++) {
-    char* dst = h + tpos[f];
-    if (isgz[f]) {
-      memcpy(dst, gz[f].data(), (size_t)size[f]);
-      std::string().swap(gz[f]);
-    } else {
-      const int fd = open(paths[f], O_RDONLY);
-      if (fd < 0) { set_error("cannot read %s", paths[f]); return CATT_E_IO; }
-      const int64_t piece = 8 << 20, np = (size[f] + piece - 1) / piece;
-      bool ok = true;
-      #pragma omp parallel for schedule(dynamic, 1) reduction(&& : ok)
-      for (int64_t p = 0; p < np; p++) {
-        int64_t o = p * piece;
-        const int64_t e = std::min(size[f], o + piece);
-        while (o < e) {
-          const ssize_t r = pread(fd, dst + o, (size_t)(e - o), (off_t)o);
-          if (r <= 0) { ok = false; break; }
-          o += r;
-        }
-      }
-      close(fd);
-      if (!ok) { set_error("short read on %s", paths[f]); return CATT_E_IO; }
-    }
-    int64_t e = size[f];
-    while (e > 0 && (dst[e - 1] == '\n' || dst[e - 1] == '\r' || dst[e - 1] == ' ' || dst[e - 1] == '\t')) e--;
-    if (e == 0 || dst[0] != '@') return CATT_OK;                  // empty or not FASTQ: host path
-    dst[e++] = '\n';
-    tend[f] = tpos[f] + e;
-  }
-  // every file goes to HBM in pieces that end on a record boundary (a line that starts with '@' whose second next line starts
-  // with '+'), queued on the copy stream up front: piece k+1 crosses PCIe while piece k is indexed, packed and aligned
+  // A reader thread brings the files into pinned memory block by block and, as soon as a record-aligned piece is complete (a line
+  // that starts with '@' whose second next line starts with '+'), queues its copy to HBM on the copy stream and publishes it:
+  // piece k+1 is read and crosses PCIe while piece k is indexed, packed and aligned.  Pieces ramp up x4 from a small first one.
   struct Piece { int64_t t0, t1; int file; };
-  std::vector<Piece> pieces;
+  struct Feed {
+    std::mutex mu; std::condition_variable cv;
+    std::vector<Piece> pieces; bool done = false; int status = CATT_OK; bool fallback = false; std::string err;
+  } feed;
   const int64_t piece_max = std::max<int64_t>(c->chunk_reads * 320, 1 << 20);
-  int64_t piece_bytes = std::max<int64_t>(piece_max / 64, 1 << 20);          // small first piece, x4 ramp (see stage_a_stream)
-  for (int f = 0; f < nfiles; f++) {
-    int64_t p = tpos[f];
-    while (p < tend[f]) {
-      int64_t q = std::min(tend[f], p + piece_bytes);
-      piece_bytes = std::min(piece_bytes * 4, piece_max);
-      while (q < tend[f]) {                                        // advance q to the start of a header line
-        const char* nl = (const char*)memchr(h + q, '\n', (size_t)(tend[f] - q));
-        if (!nl) { q = tend[f]; break; }
-        q = (nl - h) + 1;
-        if (q >= tend[f]) break;
-        if (h[q] != '@') continue;
-        const char* n1 = (const char*)memchr(h + q, '\n', (size_t)(tend[f] - q));
-        const char* n2 = n1 ? (const char*)memchr(n1 + 1, '\n', (size_t)(h + tend[f] - (n1 + 1))) : nullptr;
-        if (n2 && n2 + 1 < h + tend[f] && n2[1] == '+') break;
-      }
-      pieces.push_back(Piece{p, q, f});
-      p = q;
+  {
+    int64_t total = 0;
+    for (int f = 0; f < nfiles; f++) total += size[f];
+    const size_t want = (size_t)(16 + nfiles * 8 + total / piece_max * 2);
+    const size_t old = c->ev_piece.size();
+    if (old < want) {
+      c->ev_piece.resize(want);
+      for (size_t k = old; k < want; k++) CATT_CUDA(cudaEventCreateWithFlags(&c->ev_piece[k], cudaEventDisableTiming));
     }
   }
-  if ((int)c->ev_piece.size() < (int)pieces.size()) {
-    const size_t old = c->ev_piece.size();
-    c->ev_piece.resize(pieces.size());
-    for (size_t k = old; k < pieces.size(); k++) CATT_CUDA(cudaEventCreateWithFlags(&c->ev_piece[k], cudaEventDisableTiming));
-  }
-  for (size_t k = 0; k < pieces.size(); k++) {
-    CATT_CUDA(cudaMemcpyAsync(d_text + pieces[k].t0, h + pieces[k].t0, (size_t)(pieces[k].t1 - pieces[k].t0), cudaMemcpyHostToDevice, c->copy_stream));
-    CATT_CUDA(cudaEventRecord(c->ev_piece[k], c->copy_stream));
-  }
+  const int device = c->device;
+  std::thread reader([&, device]() {
+    cudaSetDevice(device);
+    auto fail = [&](int code, const std::string& msg, bool fb) {
+      std::lock_guard<std::mutex> lk(feed.mu);
+      feed.status = code; feed.err = msg; feed.fallback = fb; feed.done = true;
+      feed.cv.notify_all();
+    };
+    int64_t piece_bytes = std::max<int64_t>(piece_max / 64, 1 << 20);
+    size_t n_published = 0;
+    for (int f = 0; f < nfiles; f++) {
+      char* dst = h + tpos[f];
+      int fd = -1;
+      if (isgz[f]) { memcpy(dst, gz[f].data(), (size_t)size[f]); std::string().swap(gz[f]); }
+      else if ((fd = open(paths[f], O_RDONLY)) < 0) { fail(CATT_E_IO, std::string("cannot read ") + paths[f], false); return; }
+      int64_t have = isgz[f] ? size[f] : 0, end = -1, p = 0;      // bytes of the file in memory; trimmed end once known; next piece start
+      while (true) {
+        if (have < size[f]) {                                      // next block, all host threads
+          const int64_t blk = std::min<int64_t>(size[f] - have, 32 << 20), sub = 4 << 20, ns = (blk + sub - 1) / sub;
+          bool ok = true;
+          #pragma omp parallel for schedule(dynamic, 1) reduction(&& : ok)
+          for (int64_t k = 0; k < ns; k++) {
+            int64_t o = have + k * sub;
+            const int64_t e = std::min(have + blk, o + sub);
+            while (o < e) {
+              const ssize_t r = pread(fd, dst + o, (size_t)(e - o), (off_t)o);
+              if (r <= 0) { ok = false; break; }
+              o += r;
+            }
+          }
+          if (!ok) { close(fd); fail(CATT_E_IO, std::string("short read on ") + paths[f], false); return; }
+          have += blk;
+        }
+        if (have == size[f] && end < 0) {                          // whole file present: trim trailing blank space, terminate with '\n'
+          int64_t e = size[f];
+          while (e > 0 && (dst[e - 1] == '\n' || dst[e - 1] == '\r' || dst[e - 1] == ' ' || dst[e - 1] == '\t')) e--;
+          if (e == 0) { if (fd >= 0) close(fd); fail(CATT_OK, "", true); return; }
+          dst[e++] = '\n';
+          end = e;
+        }
+        if (p == 0 && have > 0 && dst[0] != '@') { if (fd >= 0) close(fd); fail(CATT_OK, "", true); return; }   // not FASTQ: host path
+        // cut as many pieces as the bytes at hand allow
+        while (true) {
+          const int64_t limit = end >= 0 ? end : have;
+          int64_t q = p + piece_bytes;
+          if (end >= 0 && q >= end) q = end;
+          else {
+            if (q + 65536 > limit && end < 0) break;               // the boundary search needs a little look-ahead
+            bool found = false;
+            while (q < limit) {                                    // advance q to the start of a header line
+              const char* nl = (const char*)memchr(dst + q, '\n', (size_t)(limit - q));
+              if (!nl) break;
+              q = (nl - dst) + 1;
+              if (q >= limit) break;
+              if (dst[q] != '@') continue;
+              const char* n1 = (const char*)memchr(dst + q, '\n', (size_t)(limit - q));
+              const char* n2 = n1 ? (const char*)memchr(n1 + 1, '\n', (size_t)(dst + limit - (n1 + 1))) : nullptr;
+              if (n2 && n2 + 1 < dst + limit && n2[1] == '+') { found = true; break; }
+            }
+            if (!found) { if (end >= 0) q = end; else break; }
+          }
+          if (q <= p) break;
+          const Piece pc{tpos[f] + p, tpos[f] + q, f};
+          if (cudaMemcpyAsync(d_text + pc.t0, h + pc.t0, (size_t)(pc.t1 - pc.t0), cudaMemcpyHostToDevice, c->copy_stream) != cudaSuccess ||
+              n_published >= c->ev_piece.size() || cudaEventRecord(c->ev_piece[n_published], c->copy_stream) != cudaSuccess) {
+            if (fd >= 0) close(fd);
+            fail(CATT_E_CUDA, "FASTQ text upload failed", false);
+            return;
+          }
+          {
+            std::lock_guard<std::mutex> lk(feed.mu);
+            feed.pieces.push_back(pc);
+          }
+          feed.cv.notify_all();
+          n_published++;
+          p = q;
+          piece_bytes = std::min(piece_bytes * 4, piece_max);
+          if (end >= 0 && p >= end) break;
+        }
+        if (end >= 0 && p >= end) break;
+      }
+      if (fd >= 0) close(fd);
+    }
+    std::lock_guard<std::mutex> lk(feed.mu);
+    feed.done = true;
+    feed.cv.notify_all();
+  });
+  struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{reader};
+  auto next_piece = [&](size_t k, Piece* out) -> int {          // 1 = piece k available, 0 = no more pieces, < 0 = error / fallback
+    std::unique_lock<std::mutex> lk(feed.mu);
+    feed.cv.wait(lk, [&] { return feed.pieces.size() > k || feed.done; });
+    if (feed.pieces.size() > k) { *out = feed.pieces[k]; return 1; }
+    if (feed.fallback) return -2;
+    if (feed.status != CATT_OK) { set_error("%s", feed.err.c_str()); return -1; }
+    return 0;
+  };
   tr.lap("run_files: read text + queue H2D");
   std::unique_ptr<catt_result> R(new catt_result());
   int launches = 0;
@@ -450,9 +504,15 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
   int max_len = 0;
   // the seeding kernel sizes its scratch by the longest read of the sample, which is only known at the end: use the limit of the
   // first piece's reads for that piece, then the running maximum (a later, longer read only enlarges later launches)
-  for (size_t k = 0; k < pieces.size(); k++) {
-    const Piece& pc = pieces[k];
-    if (k > 0 && pieces[k - 1].file != pc.file) fh.start.push_back(n);
+  int prev_file = -1;
+  for (size_t k = 0;; k++) {
+    Piece pc;
+    const int got = next_piece(k, &pc);
+    if (got == 0) break;
+    if (got == -2) return CATT_OK;                                 // not strict FASTQ: the host parser takes over
+    if (got < 0) return feed.status;
+    if (prev_file >= 0 && prev_file != pc.file) fh.start.push_back(n);
+    prev_file = pc.file;
     CATT_CUDA(cudaStreamWaitEvent(c->stream, c->ev_piece[k], 0));
     int64_t np = 0; uint64_t wp = 0; int fb = 0;
     rc = ingest_fastq(c, d_text, pc.t0, pc.t1, n, words, &np, &wp, &max_len, &fb, &launches);
