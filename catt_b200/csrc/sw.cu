@@ -423,14 +423,133 @@ __global__ void __launch_bounds__(SW_THREADS) sw_bulk_kernel(RefDev ref, ReadsDe
   }
 }
 
+// Two rows per wavefront step: lane g works on read rows 2(st-g) and 2(st-g)+1 for its C columns, column by column, the second
+// row one cell behind the first.  Same cells, same operations per cell - but two independent F chains per thread (the ALU pipe
+// was stalling on the 3-instruction dependency chain of a single row) and half as many shuffles / loop iterations per row.
+template <int G, int C>
+__global__ void __launch_bounds__(SW_THREADS) sw_bulk2_kernel(RefDev ref, ReadsDev reads, const SwTask* __restrict__ tasks,
+                                                              const uint32_t* __restrict__ ntasks_dev, int64_t ntasks_cap,
+                                                              uint32_t* __restrict__ out, int ml) {
+  constexpr int GPW = 32 / G;
+  constexpr int GPB = GPW * (SW_THREADS / 32);
+  constexpr int CH = (C + 3) / 4;
+  constexpr int ROWW = G * CH * 4;
+  constexpr int PROFW = 5 * ROWW;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int64_t ntasks = (int64_t)*ntasks_dev;
+  if (ntasks > ntasks_cap) return;
+  if ((int64_t)blockIdx.x * GPB >= ntasks) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane % G, grp = lane / G;
+  const int slot = warp * GPW + grp;
+  uint32_t* prof = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)slot * PROFW;
+  uint8_t* qarr = smem_raw + (size_t)GPB * PROFW * 4 + (size_t)slot * ml;       // ml is even and > max_len
+  const uint32_t prof_base = smem_u32(prof) + (uint32_t)g * 16u;
+  const uint8_t* __restrict__ Tb = ref.Tb;
+  const uint32_t neg7 = NEG7 ^ (uint32_t)((unsigned long long)ntasks_cap >> 62);   // == NEG7, opaque to constant propagation
+
+  for (int64_t base = ((int64_t)blockIdx.x * (SW_THREADS / 32) + warp) * GPW; base < ntasks;
+       base += (int64_t)gridDim.x * GPB) {
+    const int64_t t = base + grp;
+    const bool live = t < ntasks;
+    int m = 0;
+    if (live) {
+      const SwTask tk = tasks[t];
+      const int strand = tk.a & 1;
+      m = reads.len[tk.read];
+      const uint32_t* __restrict__ w = reads.words + reads.off[tk.read];
+      const uint32_t* __restrict__ nm = w + read_base_words(m);
+      for (int i = g; i < m; i += G) qarr[i] = (uint8_t)read_code(w, nm, m, i, strand);
+      if (g == 0 && (m & 1)) qarr[m] = 4;               // the phantom last row of an odd-length read scores -1 everywhere
+      const int ra = tk.a >> 1, oa = ref.rec_off[ra], la = ref.rec_len[ra];
+      int ob = 0, lb = 0;
+      if (tk.b != 0xFFFF) { const int rb = tk.b >> 1; ob = ref.rec_off[rb]; lb = ref.rec_len[rb]; }
+      #pragma unroll
+      for (int c = 0; c < C; c++) {
+        const int j = g * C + c;
+        const int ba = j < la ? (int)Tb[oa + j] : 7, bb = j < lb ? (int)Tb[ob + j] : 7;
+        uint32_t* dst = prof + ((c >> 2) * G + g) * 4 + (c & 3);
+        #pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int sa = q == ba ? 1 : -2, sb = (q == bb ? 1 : -2) - (sa < 0);
+          dst[q * ROWW] = ((uint32_t)sb << 16) | ((uint32_t)sa & 0xFFFFu);
+        }
+        dst[4 * ROWW] = 0xFFFEFFFFu;
+      }
+    }
+    __syncwarp();
+    const int rows2 = (m + 1) >> 1;
+    int steps = live ? rows2 + G - 1 : 0;
+    #pragma unroll
+    for (int d = 16; d; d >>= 1) steps = max(steps, __shfl_xor_sync(FULL, steps, d));
+
+    uint32_t Hp[C], E[C];
+    #pragma unroll
+    for (int c = 0; c < C; c++) { Hp[c] = TWO2; E[c] = TWO2; }
+    uint32_t lastH0 = TWO2, lastH1 = TWO2, lastF0 = TWO2, lastF1 = TWO2, diag_in = TWO2, best = TWO2;
+    const uint32_t q_base = smem_u32(qarr);
+    for (int st = 0; st < steps; st++) {
+      uint32_t inH0 = __shfl_up_sync(FULL, lastH0, 1, G);
+      uint32_t inH1 = __shfl_up_sync(FULL, lastH1, 1, G);
+      uint32_t inF0 = __shfl_up_sync(FULL, lastF0, 1, G);
+      uint32_t inF1 = __shfl_up_sync(FULL, lastF1, 1, G);
+      if (g == 0) { inH0 = TWO2; inH1 = TWO2; inF0 = TWO2; inF1 = TWO2; }
+      const int i2 = st - g;
+      if (i2 >= 0 && i2 < rows2) {
+        uint32_t qq;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(qq) : "r"(q_base + 2u * (uint32_t)i2));
+        const uint32_t row0 = prof_base + (qq & 0xffu) * (uint32_t)(ROWW * 4);
+        const uint32_t row1 = prof_base + (qq >> 8) * (uint32_t)(ROWW * 4);
+        uint32_t hd0 = diag_in, f0 = inF0;    // row 2*i2:   diagonal = H(row-1, left neighbour's last column)
+        uint32_t hd1 = inH0, f1 = inF1;       // row 2*i2+1: diagonal = H(row 2*i2, left neighbour's last column)
+        diag_in = inH1;
+        uint32_t h0 = TWO2;
+        #pragma unroll
+        for (int ch = 0; ch < CH; ch++) {
+          uint32_t s0[4], s1[4];
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(s0[0]), "=r"(s0[1]), "=r"(s0[2]), "=r"(s0[3]) : "r"(row0 + (uint32_t)(ch * G * 16)));
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(s1[0]), "=r"(s1[1]), "=r"(s1[2]), "=r"(s1[3]) : "r"(row1 + (uint32_t)(ch * G * 16)));
+          #pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int c = 4 * ch + k;
+            if (c < C) {
+              const uint32_t t0 = hd0 + s0[k];                       // packed adds as plain 32-bit adds (see sw_row)
+              h0 = __vimax3_s16x2(t0, E[c], f0);
+              hd0 = Hp[c];
+              const uint32_t hm0 = __viaddmax_s16x2(h0, neg7, TWO2);
+              const uint32_t e0 = __viaddmax_s16x2(E[c], NEG1, hm0);
+              f0 = __viaddmax_s16x2(f0, NEG1, hm0);
+              const uint32_t t1 = hd1 + s1[k];
+              const uint32_t h1 = __vimax3_s16x2(t1, e0, f1);
+              hd1 = h0;
+              const uint32_t hm1 = __viaddmax_s16x2(h1, neg7, TWO2);
+              E[c] = __viaddmax_s16x2(e0, NEG1, hm1);
+              f1 = __viaddmax_s16x2(f1, NEG1, hm1);
+              Hp[c] = h1;
+              best = __vimax3_s16x2(best, h0, h1);
+            }
+          }
+        }
+        lastH0 = h0; lastH1 = Hp[C - 1];
+        lastF0 = f0; lastF1 = f1;
+      }
+    }
+    #pragma unroll
+    for (int d = G / 2; d; d >>= 1) best = __vimax_s16x2_relu(best, __shfl_xor_sync(FULL, best, d, G));
+    if (live && g == 0) out[t] = best - TWO2;
+    __syncwarp();
+  }
+}
+
 template <int G, int C>
 int launch_sw_bulk(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks, const uint32_t* ntasks_dev, int64_t cap, uint32_t* res,
                    int sm_count, cudaStream_t st) {
   constexpr int GPB = (32 / G) * (SW_THREADS / 32);
   constexpr int PROFW = 5 * G * ((C + 3) / 4) * 4;
-  const int ml = (reads.max_len + 15) & ~15;
+  const int ml = (reads.max_len + 1 + 15) & ~15;                 // room for the phantom row of odd-length reads
   const size_t smem = (size_t)GPB * (PROFW * 4 + ml);
-  auto k = sw_bulk_kernel<G, C>;
+  static const bool one_row = getenv("CATT_SW_1ROW") != nullptr;
+  auto k = one_row ? sw_bulk_kernel<G, C> : sw_bulk2_kernel<G, C>;
   static bool attr = false;
   static int per_sm = 0;
   if (!attr) {
