@@ -84,7 +84,7 @@ def ncu_traffic():
     (profiles/traffic.json, written by profiles/summarize_ncu.py); None when no capture is committed."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            return json.load(fh)["sw_bulk_kernel"]
+            return json.load(fh)["sw_bulk2_kernel"]
     except Exception:
         return None
 
@@ -319,7 +319,7 @@ def main():
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(sum(i["kernel_launches"] for i in infos)),
         "clocks": sampler.summary(),
-        "roofline": {"bound": "alu", "kernel": "sw_bulk_kernel<4,25> (V) + <4,8> (J)", "achieved": achieved / 1e12, "peak": peak / 1e12,
+        "roofline": {"bound": "alu", "kernel": "sw_bulk2_kernel<4,25> (V) + <4,8> (J)", "achieved": achieved / 1e12, "peak": peak / 1e12,
                      "unit": "Tiop/s", "frac": achieved / peak, "traffic": ncu_traffic(),
                      "note": "achieved = 12 int ops x algorithmic DP cells (every scored (read, record, strand) pair, len x len) / SW kernel time; "
                              "byte-identical records are computed once and the kernel issues 4.5 ALU-pipe instructions per cell pair, so frac can "
