@@ -195,7 +195,10 @@ int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool
   if ((rc = c->rd_seqoff.ensure((size_t)(n + 1) * sizeof(int64_t)))) return rc;
   const int64_t* d_seqoff = c->rd_seqoff.as<int64_t>();
   CATT_CUDA(cudaMemcpyAsync(c->rd_seqoff.p, hr.seq_off, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-  if (want_quals && dq && n > 0) {
+  if (want_quals && dq && n > 0 && c->only_cdr3) {
+    dq->seq_off = d_seqoff;                       // the strings follow later, for the reads that keep a CDR3 only (assemble.cu)
+    dq->host_quals = hr.quals; dq->host_seq_off = hr.seq_off;
+  } else if (want_quals && dq && n > 0) {
     dq->seq_off = d_seqoff;
     if (hr.quals) {
       if ((rc = c->rd_quals.ensure((size_t)hr.seq_off[n] + 16))) return rc;

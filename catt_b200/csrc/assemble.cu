@@ -255,6 +255,7 @@ struct StrSrc {
   const char* quals; const int64_t* seq_off;      // quals == nullptr: FASTA input, 'I' everywhere
   int64_t M, vpart;                               // all Vpart/Jpart reads; the first vpart are Vpart
   const uint32_t* map; int64_t E;                 // output entry e is read map[e] (map == nullptr: every read, E == M)
+  const int64_t* q_entry_off;                     // != nullptr: quality strings were gathered per output entry (quals + q_entry_off[e])
 };
 __device__ __forceinline__ int64_t str_read(const StrSrc& S, int64_t e) { return S.map ? (int64_t)S.map[e] : e; }
 
@@ -265,6 +266,10 @@ __global__ void cdr3_flag_kernel(const OutDesc* __restrict__ desc, const ExtendO
   if (m == M) { flag[m] = 0; return; }
   const OutDesc p = desc[m];
   flag[m] = p.xi >= 0 ? (xout != nullptr && xout[p.xi].cdr3_off >= 0) : (p.cdr3_off >= 0);
+}
+__global__ void entry_read_kernel(const OutDesc* __restrict__ desc, const uint32_t* __restrict__ map, int64_t E, uint32_t* __restrict__ rid) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < E) rid[e] = desc[map[e]].read;
 }
 __global__ void cdr3_map_kernel(const uint32_t* __restrict__ flag, const uint32_t* __restrict__ pos, int64_t M, int64_t vpart,
                                 uint32_t* __restrict__ map, unsigned long long* __restrict__ cnt) {
@@ -334,7 +339,7 @@ __global__ void __launch_bounds__(MW * 32) materialise_kernel(StrSrc S, ReadsDev
     const int real_lo = lead, real_hi = lead + (p.kind == 1 ? min(base_q, p.q_start1 - 1) : base_q);
     const int src0 = p.kind == 1 ? 0 : p.seq_off;
     const int a0 = c_off >= 0 ? c_off : 0;
-    const char* rq = S.quals ? S.quals + S.seq_off[p.read] : nullptr;
+    const char* rq = S.quals ? (S.q_entry_off ? S.quals + S.q_entry_off[e_] : S.quals + S.seq_off[p.read]) : nullptr;
     char* q = qual_arena + qoff[e_];
     for (int i = lane; i <= qlen; i += 32) {
       char ch = 0;
@@ -711,7 +716,7 @@ int stage_b(catt_ctx* c, int64_t n, const NamesDev& names, const ReadsDev& reads
   CATT_CUDA(cudaEventRecord(c->ev[6], st));
   // ---- the Myread strings: sizes -> offsets (scans) -> one warp per read writes both strings and the catt_read entry; the
   //      arenas go to the host as three bulk copies into pinned result blocks
-  StrSrc S{desc, xout, dq.quals, dq.seq_off, M, info.vpart, nullptr, M};
+  StrSrc S{desc, xout, dq.quals, dq.seq_off, M, info.vpart, nullptr, M, nullptr};
   int64_t E = M, EV = info.vpart;
   if (c->only_cdr3 && M > 0) {                      // the lists as they stand after catt.jl:581-582
     uint32_t *cflag, *cpos, *cmap;
@@ -727,6 +732,30 @@ int stage_b(catt_ctx* c, int64_t n, const NamesDev& names, const ReadsDev& reads
     CATT_CUDA(cudaStreamSynchronize(st));
     E = (int64_t)ev2[0]; EV = (int64_t)ev2[1];
     S.map = cmap; S.E = E;
+    if (dq.host_quals && E > 0) {                   // gather the quality strings of the E surviving reads on the host, upload them
+      uint32_t* d_rid; char* d_gather; int64_t* d_entry;
+      if ((rc = ensure(c, SB_QRID, E, &d_rid)) || (rc = c->pin[PIN_QRID].ensure((size_t)E * 4)) || (rc = c->pin[PIN_QENTRY].ensure((size_t)(E + 1) * 8))) return rc;
+      entry_read_kernel<<<nblk(E), 256, 0, st>>>(desc, cmap, E, d_rid);
+      CATT_CUDA(cudaGetLastError());
+      *launches += 1;
+      uint32_t* h_rid = c->pin[PIN_QRID].as<uint32_t>();
+      int64_t* h_entry = c->pin[PIN_QENTRY].as<int64_t>();
+      CATT_CUDA(cudaMemcpyAsync(h_rid, d_rid, (size_t)E * 4, cudaMemcpyDeviceToHost, st));
+      CATT_CUDA(cudaStreamSynchronize(st));
+      h_entry[0] = 0;
+      for (int64_t e = 0; e < E; e++) h_entry[e + 1] = h_entry[e] + (dq.host_seq_off[h_rid[e] + 1] - dq.host_seq_off[h_rid[e]]);
+      const int64_t gbytes = h_entry[E];
+      if ((rc = c->pin[PIN_QGATHER].ensure((size_t)gbytes + 16)) || (rc = ensure(c, SB_QGATHER, gbytes + 16, &d_gather)) ||
+          (rc = ensure(c, SB_QENTRY, E + 1, &d_entry))) return rc;
+      char* h_gather = c->pin[PIN_QGATHER].as<char>();
+      #pragma omp parallel for schedule(static)
+      for (int64_t e = 0; e < E; e++)
+        memcpy(h_gather + h_entry[e], dq.host_quals + dq.host_seq_off[h_rid[e]], (size_t)(h_entry[e + 1] - h_entry[e]));
+      CATT_CUDA(cudaMemcpyAsync(d_gather, h_gather, (size_t)gbytes, cudaMemcpyHostToDevice, st));
+      CATT_CUDA(cudaMemcpyAsync(d_entry, h_entry, (size_t)(E + 1) * 8, cudaMemcpyHostToDevice, st));
+      info.bytes_h2d += gbytes + (E + 1) * 8; info.bytes_d2h += E * 4;
+      S.quals = d_gather; S.q_entry_off = d_entry;
+    }
   }
   unsigned long long *ssz, *qsz, *soff, *qoff;
   if ((rc = ensure(c, SB_SSZ, E + 1, &ssz)) || (rc = ensure(c, SB_QSZ, E + 1, &qsz)) || (rc = ensure(c, SB_SOFF, E + 1, &soff)) ||

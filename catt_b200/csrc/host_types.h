@@ -70,10 +70,10 @@ struct PinBuf {
 enum {
   SB_NAMES = 0, SB_NAME_OFF, SB_NAME_END, SB_SLOT_OF, SB_OWNER, SB_MINV, SB_MINJ, SB_KEYS_A, SB_SORT_V, SB_SORT_J, SB_FLAG, SB_KPOS_V,
   SB_KPOS_J, SB_ORD_IDX_V, SB_ORD_IDX_J, SB_ORD_FLAG_V, SB_ORD_FLAG_J, SB_OPOS_V, SB_OPOS_J, SB_PAIR_A, SB_PAIR_B, SB_PKEY_A, SB_PKEY_B, SB_ITEMS,
-  SB_EOUT, SB_KFLAG, SB_KFLAG1, SB_KPOS2, SB_KPOS3, SB_PFLAG, SB_XPOS, SB_TAB_KEYS, SB_TAB_VALS, SB_PITEMS, SB_PARTIAL, SB_XOUT, SB_DESC, SB_SSZ, SB_QSZ, SB_SOFF, SB_QOFF, SB_OUT_SEQ, SB_OUT_QUAL, SB_OUT_PART, SB_CFLAG, SB_CPOS, SB_CMAP, SB_CNT, SB_CUB,
+  SB_EOUT, SB_KFLAG, SB_KFLAG1, SB_KPOS2, SB_KPOS3, SB_PFLAG, SB_XPOS, SB_TAB_KEYS, SB_TAB_VALS, SB_PITEMS, SB_PARTIAL, SB_XOUT, SB_DESC, SB_SSZ, SB_QSZ, SB_SOFF, SB_QOFF, SB_OUT_SEQ, SB_OUT_QUAL, SB_OUT_PART, SB_CFLAG, SB_CPOS, SB_CMAP, SB_QRID, SB_QGATHER, SB_QENTRY, SB_CNT, SB_CUB,
   SB_COUNT
 };
-enum { PIN_PACK0 = 0, PIN_PACK1, PIN_QUAL0, PIN_QUAL1, PIN_OFF, PIN_LEN, PIN_CNT, PIN_DESC, PIN_XOUT, PIN_TEXT, PIN_RING0, PIN_RING1, PIN_COUNT };
+enum { PIN_PACK0 = 0, PIN_PACK1, PIN_QUAL0, PIN_QUAL1, PIN_OFF, PIN_LEN, PIN_CNT, PIN_DESC, PIN_XOUT, PIN_TEXT, PIN_RING0, PIN_RING1, PIN_QRID, PIN_QGATHER, PIN_QENTRY, PIN_COUNT };
 constexpr int EV_A = 6;     // per reference set: seed start, seed end, expand end, sw end, select end
 
 struct catt_ctx {
@@ -108,7 +108,12 @@ struct catt_ctx {
 struct NamesDev { const char* s = nullptr; const int64_t* beg = nullptr; const int64_t* end = nullptr; };
 
 // quality strings of the sample in HBM (uploaded under the Stage A kernels); quals == nullptr for FASTA input
-struct DeviceQuals { const char* quals = nullptr; const int64_t* seq_off = nullptr; };
+struct DeviceQuals {
+  const char* quals = nullptr; const int64_t* seq_off = nullptr;
+  // only_cdr3 with host buffers: the quality strings stay on the host until Stage B knows the few reads that keep a CDR3; their
+  // strings are then gathered and uploaded (host_quals + host_seq_off = the caller's buffers)
+  const char* host_quals = nullptr; const int64_t* host_seq_off = nullptr;
+};
 
 struct catt_batch {
   DevBuf quals, seqoff; bool have_quals = false;
