@@ -146,13 +146,28 @@ def file_e2e(ctx, np, R, length, seq_buf, qual_buf, first):
             "note": "catt_run_file on a FASTQ in the page cache, median of 3 calls after 1 warm-up; QNAMEs are zero-padded read numbers"}
 
 
-def cpu_reference_run(fx, length, n_sample, first_index=0):
+def dilute(np, seq_buf, qual_buf, n, length, tcr_fraction, seed):
+    """RNA-seq-like mix (BASELINE configs[1] substitute): keep a fraction of the TCR-derived reads, replace the
+    rest by uniform-random ACGT reads (deterministic in `seed`)."""
+    if tcr_fraction >= 1.0:
+        return
+    rng = np.random.default_rng(seed)
+    noise = rng.random(n) >= tcr_fraction
+    k = int(noise.sum())
+    seqs = seq_buf.reshape(n, length)
+    seqs[noise] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=(k, length), dtype=np.uint8)]
+    qual_buf.reshape(n, length)[noise] = ord("I")
+
+
+def cpu_reference_run(fx, length, n_sample, first_index=0, species="hs", chain="TRB", tcr_fraction=1.0):
     """The CPU restatement (oracle) on n_sample reads with all host threads; returns (reads/s, seconds, info)."""
+    import numpy as np
     from catt_b200.refg import chain_config
     from oracle import oracle as O
-    cc = chain_config("hs", "TRB", "CDR3", os.path.join(fx, "resource"))
+    cc = chain_config(species, chain, "CDR3", os.path.join(fx, "resource"))
     V, J = O.RefSet(cc["vregion"]), O.RefSet(cc["jregion"])
     seqs, quals = O.synth_reads(V, J, n_sample, length, first_index=first_index, seed=SEED)
+    dilute(np, seqs, quals, n_sample, length, tcr_fraction, SEED + first_index)
     cfg = O.make_config(cc)
     t0 = time.perf_counter()
     R = O.run_flat(V, J, cfg, seqs, quals, first_index=first_index, threads=len(os.sched_getaffinity(0)))   # explicit: torchrun exports OMP_NUM_THREADS=1
@@ -167,6 +182,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--reads-per-step", type=int, default=2_000_000)
     ap.add_argument("--length", type=int, default=150)
+    ap.add_argument("--species", default="hs", help="other BASELINE configs: ms / pig (configs[4])")
+    ap.add_argument("--chain", default="TRB", help="TRA / IGH / ... (configs[3] with --length 50)")
+    ap.add_argument("--tcr-fraction", type=float, default=1.0, help="< 1: RNA-seq-like mix, the rest are random reads (configs[1] substitute)")
     ap.add_argument("--impl", default="gpu", choices=["gpu", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU-baseline sample (0 = auto, ~15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -177,7 +195,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cores = len(os.sched_getaffinity(0)) or 1
-    workload = f"synthetic hs TRB {args.length}bp reads from IMGT V/J with random CDR3 insertions (BASELINE configs[2], SURVEY 8d config 3)"
+    workload = f"synthetic {args.species} {args.chain} {args.length}bp reads from IMGT V/J with random CDR3 insertions (BASELINE configs[2], SURVEY 8d config 3)"
+    if (args.species, args.chain, args.length, args.tcr_fraction) != ("hs", "TRB", 150, 1.0):
+        workload = (f"synthetic {args.species} {args.chain} {args.length}bp reads, TCR-derived fraction {args.tcr_fraction} "
+                    "(one of the other BASELINE configs; same generator, SURVEY 8d)")
 
     # ------------------------------------------------------------------------------------------------- reference arm
     if args.impl == "reference":
@@ -188,10 +209,10 @@ def main():
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
         n = args.cpu_sample or max(8000, 5000 * cores)         # ~5 s per step on `cores` threads
         for i in range(args.warmup):
-            cpu_reference_run(fx, args.length, max(1000, n // 8), first_index=i * n)
+            cpu_reference_run(fx, args.length, max(1000, n // 8), first_index=i * n, species=args.species, chain=args.chain, tcr_fraction=args.tcr_fraction)
         t_tot, cells = 0.0, 0
         for i in range(args.steps):
-            rps, dt, info = cpu_reference_run(fx, args.length, n, first_index=i * n)
+            rps, dt, info = cpu_reference_run(fx, args.length, n, first_index=i * n, species=args.species, chain=args.chain, tcr_fraction=args.tcr_fraction)
             t_tot += dt
             cells += info["cells_v"] + info["cells_j"]
         value = n * args.steps / t_tot
@@ -199,7 +220,7 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
                 "gcups": cells / t_tot / 1e9,
-                "config": {"workload": workload, "reads_per_step": n, "read_length": args.length, "chain": "hs TRB",
+                "config": {"workload": workload, "reads_per_step": n, "read_length": args.length, "chain": f"{args.species} {args.chain}",
                            "note": "CPU restatement of the reference path (oracle, OpenMP) - the Julia+bwa+samtools program cannot run here"},
                 "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": "port",
                                  "sample": f"{args.steps} x {n} reads of the same generator"},
@@ -229,7 +250,7 @@ def main():
     from catt_b200.host import Catt, set_host_threads
     from catt_b200.refg import chain_config
     fx = fixture_dir()
-    cc = chain_config("hs", "TRB", "CDR3", os.path.join(fx, "resource"))
+    cc = chain_config(args.species, args.chain, "CDR3", os.path.join(fx, "resource"))
     # one process per GPU: every rank gets its share of the host cores (torchrun exports OMP_NUM_THREADS=1)
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     host_threads = max(1, len(os.sched_getaffinity(0)) // max(1, local_world))
@@ -240,6 +261,7 @@ def main():
     R = args.reads_per_step
     first = rank * R
     name_buf, name_off, seq_buf, seq_off, qual_buf = ctx.synth_reads(R, args.length, first_index=first, seed=SEED)
+    dilute(np, seq_buf, qual_buf, R, args.length, args.tcr_fraction, SEED + first)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
 
     peak_ops, peak_ms = ctx.alu_peak()            # packed DPX add-max thread-instructions per second
@@ -306,7 +328,7 @@ def main():
         "metric": "reads_per_sec", "value": world * R * args.steps / (dev_ms * 1e-3), "unit": "reads/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-        "config": {"workload": workload, "reads_per_step_per_gpu": R, "read_length": args.length, "chain": "hs TRB",
+        "config": {"workload": workload, "reads_per_step_per_gpu": R, "read_length": args.length, "chain": f"{args.species} {args.chain}",
                    "l2": f"packed batch {packed_bytes >> 20} MiB per step vs 126 MB L2" + (" (larger than L2)" if packed_bytes > 126e6 else " (compute-bound kernel; see DESIGN.md)"),
                    "multi_gpu": "shards are independent samples; no data-path collective", "host_threads_per_rank": host_threads,
                    "result": "only_cdr3 = 1: Vpart/Jpart as they stand after catt.jl:581-582 (the reads catt() goes on to use); counters of the full lists in info"},
@@ -349,7 +371,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
         n = args.cpu_sample or max(16000, 15000 * cores)       # ~15 s of CPU work on `cores` threads
-        rps, dt, cinfo = cpu_reference_run(fx, args.length, n)
+        rps, dt, cinfo = cpu_reference_run(fx, args.length, n, species=args.species, chain=args.chain, tcr_fraction=args.tcr_fraction)
         line["cpu_baseline"] = {"value": rps, "unit": "reads/s", "cores": cores, "kind": "port",
                                 "sample": f"first {n} reads of the same generator, {dt:.1f} s; CPU restatement (oracle, OpenMP), not the Julia program",
                                 "gcups": (cinfo["cells_v"] + cinfo["cells_j"]) / dt / 1e9}

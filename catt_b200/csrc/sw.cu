@@ -573,8 +573,9 @@ int dispatch_sw_bulk(const RefDev& ref, const ReadsDev& reads, const SwTask* tas
   if (n <= 64) return launch_sw_bulk<8, 8>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
   if (n <= 100 && !getenv("CATT_SW_G8")) return launch_sw_bulk<4, 25>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
   if (n <= 104) return launch_sw_bulk<8, 13>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
-  if (n <= 160) return launch_sw_bulk<16, 10>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
-  if (n <= 320) return launch_sw_bulk<32, 10>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
+  // long records (IGHV, pig / mouse TRBV: 280-320 nt): few lanes with many columns keep the skew short (G - 1 idle steps per task)
+  if (n <= 160) return launch_sw_bulk<8, 20>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
+  if (n <= 320) return launch_sw_bulk<16, 20>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
   set_error("record length %d exceeds the SW kernel's tiling", n);
   return CATT_E_LIMIT;
 }
@@ -588,8 +589,8 @@ int dispatch_sw(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks, c
   if (n <= 64) return launch_sw_t<8, 8, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
   if (n <= 100 && TRACK && !getenv("CATT_SW_G8")) return launch_sw_t<4, 25, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
   if (n <= 104) return launch_sw_t<8, 13, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
-  if (n <= 160) return launch_sw_t<16, 10, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
-  if (n <= 320) return launch_sw_t<32, 10, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
+  if (n <= 160) return launch_sw_t<8, 20, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
+  if (n <= 320) return launch_sw_t<16, 20, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
   set_error("record length %d exceeds the SW kernel's tiling", n);
   return CATT_E_LIMIT;
 }
