@@ -8,13 +8,14 @@
 //   selection = best score over the candidates; ties broken by bwa's hash_64(read ordinal + rank in T order);
 //   facts     = soft clip (GetStartCigar), end of the first M block (GetEndCigar), POS, NM, sum(M+I).
 //
-// sw_score_kernel: G lanes cooperate on one (read, 2 candidates) task.  Each lane owns C record columns and keeps
-// H/E for them in registers as packed int16x2 — low half = candidate A, high half = candidate B, both on the same
-// strand of the same read, so one query row drives both.  Rows advance as a skewed wavefront (lane g works on row
-// t-g at step t); the last column's H and the running F cross to the next lane by warp shuffle.  The substitution
-// score of a cell-pair is one PRMT (byte permute with sign replication) from two per-column byte tables; the
-// recurrences use the DPX packed add-max instructions (VIADDMNMX/VIMNMX .S16x2).  No tensor cores: there is no
-// dense contraction in this recurrence.
+// Two DP kernels share one layout: G lanes cooperate on one task, each lane owns C record columns and keeps H/E for them in
+// registers as packed int16x2 (two alignments per register), rows advance as a skewed wavefront, the last column's H and the
+// running F cross to the next lane by warp shuffle, the recurrences are DPX packed add-max / 3-way max instructions
+// (VIADDMNMX / VIMNMX3 .S16x2) on +2-biased values (see sw_row).  No tensor cores: there is no dense contraction here.
+//   sw_bulk2_kernel  - scores of EVERY candidate: task = one read against two candidate records of the same strand; substitution
+//                      scores from a shared-memory query profile (LDS.128), two read rows per step.  The roofline kernel.
+//   sw_score_kernel  - TRACK pass, the winner of every mapped read only: task = two reads (one per half), scores by PRMT from
+//                      per-column byte tables, plus the first cell that reaches the maximum (end of the alignment).
 #include <stdlib.h>
 
 #include <cub/device/device_scan.cuh>
@@ -317,112 +318,12 @@ int launch_sw_t(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks, c
 
 // ---------------------------------------------------------------------------------------------------------------
 // the bulk score pass with a shared-memory query profile.
-// Same recurrence, layout and +2 bias as sw_score_kernel<G, C, false>, but the substitution scores of a row come from a
-// per-task profile in shared memory instead of one PRMT per cell: prof[q][column] = (s_B - [s_A < 0]) << 16 | s_A for
-// read base q = 0..3 and q = 4 (N: -1 against everything), laid out so that the G lanes of a task read one contiguous
-// 16-byte word each per LDS.128 (conflict free, also across the skewed rows, whose profile rows are 128-byte multiples
-// apart).  That moves 1 of the 5.5 ALU-pipe instructions per cell pair to the otherwise idle LSU pipe.
+// Same recurrence, layout and +2 bias as sw_score_kernel (the TRACK pass above), but the substitution scores of a row come from
+// a per-task profile in shared memory instead of one PRMT per cell: prof[q][column] = (s_B - [s_A < 0]) << 16 | s_A for read
+// base q = 0..3 and q = 4 (N: -1 against everything), laid out so that the G lanes of a task read one contiguous 16-byte word
+// each per LDS.128 (conflict free, also across the skewed rows, whose profile rows are 128-byte multiples apart).  That moves 1
+// of the 5.5 ALU-pipe instructions per cell pair to the otherwise idle LSU pipe.
 // ---------------------------------------------------------------------------------------------------------------
-template <int G, int C>
-__global__ void __launch_bounds__(SW_THREADS) sw_bulk_kernel(RefDev ref, ReadsDev reads, const SwTask* __restrict__ tasks,
-                                                             const uint32_t* __restrict__ ntasks_dev, int64_t ntasks_cap,
-                                                             uint32_t* __restrict__ out, int ml) {
-  constexpr int GPW = 32 / G;
-  constexpr int GPB = GPW * (SW_THREADS / 32);
-  constexpr int CH = (C + 3) / 4;                       // 16-byte chunks per lane and profile row
-  constexpr int ROWW = G * CH * 4;                      // words per profile row
-  constexpr int PROFW = 5 * ROWW;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int64_t ntasks = (int64_t)*ntasks_dev;
-  if (ntasks > ntasks_cap) return;                      // expand_kernel flagged the overflow; nothing valid to score
-  if ((int64_t)blockIdx.x * GPB >= ntasks) return;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = lane % G, grp = lane / G;
-  const int slot = warp * GPW + grp;
-  uint32_t* prof = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)slot * PROFW;
-  uint8_t* qarr = smem_raw + (size_t)GPB * PROFW * 4 + (size_t)slot * ml;
-  const uint32_t prof_base = smem_u32(prof) + (uint32_t)g * 16u;
-  const uint8_t* __restrict__ Tb = ref.Tb;
-  const uint32_t neg7 = NEG7 ^ (uint32_t)((unsigned long long)ntasks_cap >> 62);   // == NEG7, opaque to constant propagation
-
-  for (int64_t base = ((int64_t)blockIdx.x * (SW_THREADS / 32) + warp) * GPW; base < ntasks;
-       base += (int64_t)gridDim.x * GPB) {
-    const int64_t t = base + grp;
-    const bool live = t < ntasks;
-    int m = 0;
-    if (live) {
-      const SwTask tk = tasks[t];
-      const int strand = tk.a & 1;
-      m = reads.len[tk.read];
-      const uint32_t* __restrict__ w = reads.words + reads.off[tk.read];
-      const uint32_t* __restrict__ nm = w + read_base_words(m);
-      for (int i = g; i < m; i += G) qarr[i] = (uint8_t)read_code(w, nm, m, i, strand);
-      const int ra = tk.a >> 1, oa = ref.rec_off[ra], la = ref.rec_len[ra];
-      int ob = 0, lb = 0;
-      if (tk.b != 0xFFFF) { const int rb = tk.b >> 1; ob = ref.rec_off[rb]; lb = ref.rec_len[rb]; }
-      #pragma unroll
-      for (int c = 0; c < C; c++) {
-        const int j = g * C + c;
-        const int ba = j < la ? (int)Tb[oa + j] : 7, bb = j < lb ? (int)Tb[ob + j] : 7;
-        uint32_t* dst = prof + ((c >> 2) * G + g) * 4 + (c & 3);
-        #pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const int sa = q == ba ? 1 : -2, sb = (q == bb ? 1 : -2) - (sa < 0);
-          dst[q * ROWW] = ((uint32_t)sb << 16) | ((uint32_t)sa & 0xFFFFu);
-        }
-        dst[4 * ROWW] = 0xFFFEFFFFu;                    // N: (-1, -1) with the carry of the low half taken out of the high half
-      }
-    }
-    __syncwarp();
-    int steps = live ? m + G - 1 : 0;
-    #pragma unroll
-    for (int d = 16; d; d >>= 1) steps = max(steps, __shfl_xor_sync(FULL, steps, d));
-
-    uint32_t Hp[C], E[C];
-    #pragma unroll
-    for (int c = 0; c < C; c++) { Hp[c] = TWO2; E[c] = TWO2; }
-    uint32_t lastH = TWO2, lastF = TWO2, diag_in = TWO2, best = TWO2;
-    const uint32_t q_base = smem_u32(qarr);
-    for (int st = 0; st < steps; st++) {
-      uint32_t inH = __shfl_up_sync(FULL, lastH, 1, G);
-      uint32_t inF = __shfl_up_sync(FULL, lastF, 1, G);
-      if (g == 0) { inH = TWO2; inF = TWO2; }
-      const int i = st - g;
-      if (i >= 0 && i < m) {
-        uint32_t q;
-        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(q) : "r"(q_base + (uint32_t)i));
-        const uint32_t row = prof_base + q * (uint32_t)(ROWW * 4);
-        uint32_t sv[CH * 4];
-        #pragma unroll
-        for (int ch = 0; ch < CH; ch++)
-          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                       : "=r"(sv[4 * ch]), "=r"(sv[4 * ch + 1]), "=r"(sv[4 * ch + 2]), "=r"(sv[4 * ch + 3])
-                       : "r"(row + (uint32_t)(ch * G * 16)));
-        uint32_t hd = diag_in, f = inF;       // F(i, first column) arrives already advanced from the left neighbour
-        diag_in = inH;
-        #pragma unroll
-        for (int c = 0; c < C; c++) {
-          const uint32_t tt = hd + sv[c];                        // packed add as a plain 32-bit add (see sw_row)
-          const uint32_t h = __vimax3_s16x2(tt, E[c], f);
-          hd = Hp[c];
-          Hp[c] = h;
-          const uint32_t hm7 = __viaddmax_s16x2(h, neg7, TWO2);
-          E[c] = __viaddmax_s16x2(E[c], NEG1, hm7);
-          f = __viaddmax_s16x2(f, NEG1, hm7);
-          if (c & 1) best = __vimax3_s16x2(best, Hp[c - 1], h);
-          else if (c == C - 1) best = __vimax_s16x2_relu(best, h);
-        }
-        lastH = Hp[C - 1];
-        lastF = f;
-      }
-    }
-    #pragma unroll
-    for (int d = G / 2; d; d >>= 1) best = __vimax_s16x2_relu(best, __shfl_xor_sync(FULL, best, d, G));
-    if (live && g == 0) out[t] = best - TWO2;
-    __syncwarp();
-  }
-}
-
 // Two rows per wavefront step: lane g works on read rows 2(st-g) and 2(st-g)+1 for its C columns, column by column, the second
 // row one cell behind the first.  Same cells, same operations per cell - but two independent F chains per thread (the ALU pipe
 // was stalling on the 3-instruction dependency chain of a single row) and half as many shuffles / loop iterations per row.
@@ -548,8 +449,7 @@ int launch_sw_bulk(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks
   constexpr int PROFW = 5 * G * ((C + 3) / 4) * 4;
   const int ml = (reads.max_len + 1 + 15) & ~15;                 // room for the phantom row of odd-length reads
   const size_t smem = (size_t)GPB * (PROFW * 4 + ml);
-  static const bool one_row = getenv("CATT_SW_1ROW") != nullptr;
-  auto k = one_row ? sw_bulk_kernel<G, C> : sw_bulk2_kernel<G, C>;
+  auto k = sw_bulk2_kernel<G, C>;
   static bool attr = false;
   static int per_sm = 0;
   if (!attr) {
@@ -571,7 +471,7 @@ int dispatch_sw_bulk(const RefDev& ref, const ReadsDev& reads, const SwTask* tas
   if (n <= 32) return launch_sw_bulk<4, 8>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
   if (n <= 48) return launch_sw_bulk<4, 12>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
   if (n <= 64) return launch_sw_bulk<8, 8>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
-  if (n <= 100 && !getenv("CATT_SW_G8")) return launch_sw_bulk<4, 25>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
+  if (n <= 100) return launch_sw_bulk<4, 25>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
   if (n <= 104) return launch_sw_bulk<8, 13>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
   // long records (IGHV, pig / mouse TRBV: 280-320 nt): few lanes with many columns keep the skew short (G - 1 idle steps per task)
   if (n <= 160) return launch_sw_bulk<8, 20>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
@@ -587,7 +487,7 @@ int dispatch_sw(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks, c
   if (n <= 32) return launch_sw_t<4, 8, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
   if (n <= 48) return launch_sw_t<4, 12, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
   if (n <= 64) return launch_sw_t<8, 8, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
-  if (n <= 100 && TRACK && !getenv("CATT_SW_G8")) return launch_sw_t<4, 25, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
+  if (n <= 100) return launch_sw_t<4, 25, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
   if (n <= 104) return launch_sw_t<8, 13, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
   if (n <= 160) return launch_sw_t<8, 20, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
   if (n <= 320) return launch_sw_t<16, 20, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
@@ -876,7 +776,6 @@ int launch_expand(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, cu
 
 int launch_sw(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int sm_count, cudaStream_t st, int* launches) {
   *launches += 1;
-  if (getenv("CATT_SW_PRMT")) return dispatch_sw<false>(ref, reads, ab.tasks, ab.task_off + reads.n, ab.cap_tasks, ab.task_score, sm_count, st);
   return dispatch_sw_bulk(ref, reads, ab.tasks, ab.task_off + reads.n, ab.cap_tasks, ab.task_score, sm_count, st);
 }
 
