@@ -45,7 +45,7 @@ class Info(C.Structure):
                [(k, C.c_double) for k in ("ms_seed", "ms_sw", "ms_select", "ms_extract", "ms_pool", "ms_h2d", "ms_d2h", "ms_host")] + \
                [(k, C.c_int64) for k in ("cells_computed_v", "cells_computed_j")] + \
                [(k, C.c_double) for k in ("ms_order", "ms_pack", "ms_seed_kernel", "ms_pool_kernel", "ms_strings")] + \
-               [(k, C.c_int64) for k in ("bytes_h2d", "bytes_d2h")]
+               [(k, C.c_int64) for k in ("bytes_h2d", "bytes_d2h")] + [("ms_j_stream", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved_"}

@@ -86,6 +86,8 @@ struct catt_ctx {
   int64_t chunk_reads = 1 << 20;          // Stage A batch size of the pipelined path
   cudaStream_t stream = nullptr;          // kernels
   cudaStream_t copy_stream = nullptr;     // H2D of the packed chunks, under the kernels of the previous chunk
+  cudaStream_t stream_j = nullptr;        // Stage A of the J reference set, concurrent with the V set on `stream`
+  cudaEvent_t ev_inputs = nullptr;        // the chunk's packed reads are ready (fork point of the two Stage A streams)
   std::vector<std::string> d_names, d_seqs;
   char* d_dseq = nullptr; int32_t* d_doff = nullptr;
   catt::AlignBuffers ab[2];

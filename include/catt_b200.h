@@ -108,7 +108,8 @@ typedef struct catt_info {
   int64_t cells_v, cells_j;   /* DP cell updates: sum len(read) x len(record) */
   int64_t gapped_v, gapped_j; /* winners that needed the traceback kernel */
   int64_t kernel_launches;    /* CUDA kernels launched for this result */
-  double ms_seed, ms_sw, ms_select, ms_extract, ms_pool, ms_h2d, ms_d2h, ms_host;  /* device/host stage times */
+  double ms_seed, ms_sw, ms_select, ms_extract, ms_pool, ms_h2d, ms_d2h, ms_host;  /* device/host stage times; seed / sw /
+                                 select are those of the V reference set (the J set runs concurrently, see ms_j_stream) */
   int64_t cells_computed_v, cells_computed_j; /* DP cells actually computed: byte-identical records are scored once */
   double ms_order;            /* device time of the SAM ordering / QNAME dedup / pairing kernels (samtools sort | tac | awk) */
   double ms_pack;             /* host time packing reads that was NOT hidden under kernels */
@@ -116,6 +117,7 @@ typedef struct catt_info {
   double ms_pool_kernel;      /* pool_kernel alone (ms_pool also holds the extension kernel) */
   double ms_strings;          /* the kernel that writes the Myread strings into the result arenas */
   int64_t bytes_h2d, bytes_d2h; /* bytes the library copied host->device / device->host for this result */
+  double ms_j_stream;         /* Stage A of the J reference set (seed + sw + select), on its own stream under the V kernels */
 } catt_info;
 
 /* ---- lifecycle --------------------------------------------------------------------------------------------- */

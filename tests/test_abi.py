@@ -35,7 +35,7 @@ def test_struct_layouts_match_header():
     from catt_b200 import _lib
     assert _lib.ALN_DTYPE.itemsize == 32
     assert C.sizeof(_lib.Read) == 48
-    assert C.sizeof(_lib.Info) == 16 + 8 + 20 * 8 + 8 * 8 + 2 * 8 + 5 * 8 + 2 * 8
+    assert C.sizeof(_lib.Info) == 16 + 8 + 20 * 8 + 8 * 8 + 2 * 8 + 5 * 8 + 2 * 8 + 8
 
 
 def test_no_cpu_fallback(trb):
