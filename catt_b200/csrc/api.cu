@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <condition_variable>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -191,7 +192,7 @@ int stage_a_resident(catt_ctx* c, const DeviceReads& dr, int64_t first_ordinal, 
 // i+1 into pinned staging and the copy stream moves it to HBM.  `fh->start` lists the input files of the sample: chunks never
 // straddle a file and bwa's read ordinal restarts at every file (each file is one `bwa mem` run, catt.jl:143-147).
 int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool align, bool want_quals, DeviceReads* view, DeviceQuals* dq,
-                   FileHits* fh, catt_info* info, int* launches) {
+                   FileHits* fh, catt_info* info, int* launches, const std::function<int()>& under_kernels = nullptr) {
   const int64_t n = hr.n;
   int rc;
   const double t0 = now_ms();
@@ -212,7 +213,7 @@ int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool
   if (dq) *dq = DeviceQuals{};
   if ((rc = c->rd_seqoff.ensure((size_t)(n + 1) * sizeof(int64_t)))) return rc;
   const int64_t* d_seqoff = c->rd_seqoff.as<int64_t>();
-  CATT_CUDA(cudaMemcpyAsync(c->rd_seqoff.p, hr.seq_off, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  // the per-read offset / length tables travel with their chunk (stage_chunk) instead of in one unhidden copy up front
   if (want_quals && dq && n > 0 && c->only_cdr3) {
     dq->seq_off = d_seqoff;                       // the strings follow later, for the reads that keep a CDR3 only (assemble.cu)
     dq->host_quals = hr.quals; dq->host_seq_off = hr.seq_off;
@@ -224,8 +225,6 @@ int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool
       dq->quals = d_quals;
     }
   }
-  CATT_CUDA(cudaMemcpyAsync(dr.off, h_off, (size_t)(n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-  CATT_CUDA(cudaMemcpyAsync(dr.len, h_len, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   if (info) info->bytes_h2d += (int64_t)((n + 1) * 4 + n * 4 + (n + 1) * 8);
   struct Chunk { int64_t i0, cnt, ordinal; int file; };
   std::vector<Chunk> chunks;
@@ -258,6 +257,9 @@ int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool
     int r;
     if ((r = pb.ensure(bytes + 16)) || (r = c->rd_raw[ci & 1].ensure(bytes + 16))) return r;
     par_copy(pb.as<char>(), hr.seqs + hr.seq_off[i0], bytes);
+    CATT_CUDA(cudaMemcpyAsync(dr.off + i0, h_off + i0, (size_t)(i1 - i0 + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, cs));
+    CATT_CUDA(cudaMemcpyAsync(dr.len + i0, h_len + i0, (size_t)(i1 - i0) * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+    CATT_CUDA(cudaMemcpyAsync(c->rd_seqoff.as<int64_t>() + i0, hr.seq_off + i0, (size_t)(i1 - i0 + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, cs));
     CATT_CUDA(cudaMemcpyAsync(c->rd_raw[ci & 1].p, pb.p, bytes, cudaMemcpyHostToDevice, cs));
     CATT_CUDA(cudaEventRecord(c->ev_h2d[ci & 1], cs));
     if (info) info->bytes_h2d += (int64_t)bytes;
@@ -274,6 +276,8 @@ int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool
   if (nchunks > 0 && (rc = stage_chunk(0))) return rc;
   if (info) info->ms_pack += now_ms() - t0;
   catt_info local{};
+  int64_t queued_reads = 0;
+  bool hook_done = false;
   for (int64_t ci = 0; ci < nchunks; ci++) {
     const Chunk ch = chunks[ci];
     const ReadsDev rv = dr.view(ch.i0, ch.cnt);
@@ -286,6 +290,11 @@ int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool
         if ((rc = align_queue(c, which, rv, c->recs_all[which].as<catt_aln>() + ch.i0, ch.ordinal, launches))) return rc;
     }
     if (ci + 1 < nchunks && (rc = stage_chunk(ci + 1))) return rc;
+    queued_reads += ch.cnt;
+    if (under_kernels && !hook_done && (queued_reads >= 200000 || ci + 1 == nchunks)) {      // host work hidden under this chunk's kernels
+      hook_done = true;
+      if ((rc = under_kernels())) return rc;
+    }
     if ((rc = join_streams(c))) return rc;
     if (align) {
       const int64_t v0 = local.v_hits, j0 = local.j_hits;
@@ -296,6 +305,7 @@ int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool
   }
   CATT_CUDA(cudaStreamSynchronize(st));
   CATT_CUDA(cudaStreamSynchronize(cs));
+  if (under_kernels && !hook_done && (rc = under_kernels())) return rc;
   if (info && align) {
     info->ms_seed += local.ms_seed; info->ms_seed_kernel += local.ms_seed_kernel; info->ms_sw += local.ms_sw; info->ms_select += local.ms_select;
     info->ms_j_stream += local.ms_j_stream;
@@ -578,11 +588,13 @@ int run_all(catt_ctx* c, const HostReads& hr, const std::vector<int64_t>& file_s
   DeviceQuals dq;
   FileHits fh;
   fh.start = file_start;
-  int rc = stage_a_stream(c, hr, 0, true, true, &dr, &dq, &fh, &R->info, &launches);
+  NamesDev nd;
+  catt_result* Rp = R.get();
+  // the QNAMEs (pageable, ~20 B per read) cross PCIe while the kernels of a large chunk run
+  int rc = stage_a_stream(c, hr, 0, true, true, &dr, &dq, &fh, &R->info, &launches,
+                          [&]() { return upload_names(c, hr.n, hr.names, hr.name_off, &nd, &Rp->info, c->copy_stream); });
   tr.lap("run_all: pack + H2D + align (pipelined)");
   if (rc == CATT_OK && c->keep_records) rc = download_records(c, hr.n, R.get());
-  NamesDev nd;
-  if (rc == CATT_OK) rc = upload_names(c, hr.n, hr.names, hr.name_off, &nd, &R->info);
   if (rc == CATT_OK) rc = stage_b(c, hr.n, nd, dr.view(), dq, fh, R.get(), &launches);
   tr.lap("run_all: stage_b");
   if (rc) return rc;

@@ -492,15 +492,16 @@ static int d2h_arena(catt_ctx* c, void* dst, size_t cap, const void* d_src, size
   return drain(np - 1);
 }
 
-int upload_names(catt_ctx* c, int64_t n, const char* names, const int64_t* name_off, NamesDev* out, catt_info* info) {
+int upload_names(catt_ctx* c, int64_t n, const char* names, const int64_t* name_off, NamesDev* out, catt_info* info, cudaStream_t stream) {
+  cudaStream_t st = stream ? stream : c->stream;
   *out = NamesDev{};
   if (n == 0) return CATT_OK;
   char* d_names; int64_t* d_off;
   int rc;
   const int64_t name_bytes = name_off[n];
   if ((rc = ensure(c, SB_NAMES, name_bytes + 16, &d_names)) || (rc = ensure(c, SB_NAME_OFF, n + 1, &d_off))) return rc;
-  CATT_CUDA(cudaMemcpyAsync(d_names, names, (size_t)name_bytes, cudaMemcpyHostToDevice, c->stream));
-  CATT_CUDA(cudaMemcpyAsync(d_off, name_off, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+  CATT_CUDA(cudaMemcpyAsync(d_names, names, (size_t)name_bytes, cudaMemcpyHostToDevice, st));
+  CATT_CUDA(cudaMemcpyAsync(d_off, name_off, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
   if (info) info->bytes_h2d += name_bytes + (n + 1) * 8;
   out->s = d_names; out->beg = d_off; out->end = d_off + 1;
   return CATT_OK;

@@ -168,5 +168,5 @@ int ingest_fastq(catt_ctx* c, const char* d_text, int64_t t0, int64_t t1, int64_
 int launch_pack_raw(const char* d_text, const int64_t* d_seq_beg, const int32_t* d_len, const uint32_t* d_off, int64_t n, uint32_t* d_words,
                     int sm_count, cudaStream_t st, int* launches);
 // uploads host QNAMEs (contiguous, n+1 offsets) into the context's name buffers
-int upload_names(catt_ctx* c, int64_t n, const char* names, const int64_t* name_off, NamesDev* out, catt_info* info);
+int upload_names(catt_ctx* c, int64_t n, const char* names, const int64_t* name_off, NamesDev* out, catt_info* info, cudaStream_t st = nullptr);
 }  // namespace catt
