@@ -856,7 +856,7 @@ int catt_batch_download(catt_ctx* c, catt_batch* b, catt_aln* v_out, catt_aln* j
   return CATT_OK;
 }
 
-void catt_batch_free(catt_batch* b) { if (b) { b->dr.release(); b->quals.release(); b->seqoff.release(); delete b; } }
+void catt_batch_free(catt_batch* b) { if (b) { b->dr.release(); b->quals.release(); b->seqoff.release(); b->names.release(); b->name_off.release(); delete b; } }
 
 int catt_align_shard(catt_ctx* c, int64_t n, const char* seqs, const int64_t* seq_off, int64_t first_ordinal, catt_aln* v_out,
                      catt_aln* j_out) {
@@ -995,13 +995,16 @@ int catt_batch_assemble(catt_ctx* c, catt_batch* b, const char* names, const int
       if ((rc = b->quals.ensure((size_t)seq_off[n] + 16))) return rc;
       CATT_CUDA(cudaMemcpyAsync(b->quals.p, quals, (size_t)seq_off[n], cudaMemcpyHostToDevice, c->stream));
     }
+    if ((rc = b->names.ensure((size_t)name_off[n] + 16)) || (rc = b->name_off.ensure((size_t)(n + 1) * sizeof(int64_t)))) return rc;
+    CATT_CUDA(cudaMemcpyAsync(b->names.p, names, (size_t)name_off[n], cudaMemcpyHostToDevice, c->stream));
+    CATT_CUDA(cudaMemcpyAsync(b->name_off.p, name_off, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
     CATT_CUDA(cudaStreamSynchronize(c->stream));
     b->have_quals = true;
   }
   DeviceQuals dq;
   dq.seq_off = b->seqoff.as<int64_t>(); dq.quals = quals ? b->quals.as<char>() : nullptr;
   NamesDev nd;
-  if ((rc = upload_names(c, n, names, name_off, &nd, &R->info))) return rc;
+  if (n > 0) { nd.s = b->names.as<char>(); nd.beg = b->name_off.as<int64_t>(); nd.end = nd.beg + 1; }
   rc = stage_b(c, n, nd, b->dr.view(), dq, fh, R.get(), &launches);
   if (rc) return rc;
   R->info.kernel_launches = launches;

@@ -118,7 +118,7 @@ struct DeviceQuals {
 };
 
 struct catt_batch {
-  DevBuf quals, seqoff; bool have_quals = false;
+  DevBuf quals, seqoff, names, name_off; bool have_quals = false;      // inputs of Stage B, resident after the first assemble
   DeviceReads dr;
   int64_t first_ordinal = 0;
   catt_info info{};

@@ -197,7 +197,8 @@ int catt_assemble(catt_ctx* ctx, int64_t n, const char* names, const int64_t* na
                   const int64_t* seq_off, const char* quals, const catt_aln* v_recs, const catt_aln* j_recs,
                   catt_result** out);
 
-/* Stage B on a resident, aligned batch (inputs already in HBM); host buffers are used for QNAME dedup and strings. */
+/* Stage B on a resident, aligned batch.  The first call moves the QNAMEs and quality strings of the batch to HBM as well (they
+ * are inputs of Stage B); later calls on the same batch must pass the same buffers and run with every input resident. */
 int catt_batch_assemble(catt_ctx* ctx, catt_batch* b, const char* names, const int64_t* name_off, const char* seqs,
                         const int64_t* seq_off, const char* quals, catt_result** out);
 
