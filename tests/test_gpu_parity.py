@@ -420,3 +420,50 @@ def test_only_cdr3_lists(trb, O, orefs):
     ref = O.run_mem(V, J, O.make_config(trb), names, seqs, quals)
     assert [myread_tuple(r) for r in ref.Vpart if r.cdr3 != "None"] == fv
     full_ctx.close(); cdr3_ctx.close()
+
+
+def test_file_pipeline_many_pieces(trb, fx, O, orefs, tmp_path):
+    """File input with a tiny chunk size: the reader thread cuts the FASTQ into many record-aligned pieces (size ramp, several Stage A
+    chunks per piece, growing device buffers); result == oracle.  Also: a one-read file, an empty file, paired files with small pieces."""
+    from catt_b200 import _lib
+    from catt_b200.host import Catt
+    path = os.path.join(fx, "testSample.fq")
+    ref = O.run_file(orefs[0], orefs[1], O.make_config(trb), path)
+    want = ([myread_tuple(r) for r in ref.Vpart], [myread_tuple(r) for r in ref.Jpart])
+    for chunk in (1024, 3000):
+        c = Catt(chain_cfg=trb, chunk_reads=chunk)
+        res = c.mainflow(path)
+        assert ([myread_tuple(r) for r in res.Vpart], [myread_tuple(r) for r in res.Jpart]) == want, chunk
+        assert res.info["n_reads"] == 7922 and res.info["the_err"] == ref.info["the_err"]
+        # the in-memory path with the same tiny chunks (size ramp, many chunks)
+        lines = open(path).read().split("\n")
+        names = [lines[i][1:].split()[0] for i in range(0, len(lines) - 3, 4)]
+        seqs = [lines[i + 1] for i in range(0, len(lines) - 3, 4)]
+        quals = [lines[i + 3] for i in range(0, len(lines) - 3, 4)]
+        res2 = c.mainflow_reads(names, seqs, quals)
+        assert ([myread_tuple(r) for r in res2.Vpart], [myread_tuple(r) for r in res2.Jpart]) == want, chunk
+        c.close()
+    c = Catt(chain_cfg=trb, chunk_reads=1024)
+    one = str(tmp_path / "one.fq")
+    with open(one, "w") as fh:
+        fh.write("\n".join(open(path).read().split("\n")[:4]) + "\n")
+    r1 = c.mainflow(one)
+    assert r1.info["n_reads"] == 1
+    empty = str(tmp_path / "empty.fq")
+    open(empty, "w").close()
+    r0 = c.mainflow(empty)
+    assert r0.info["n_reads"] == 0 and r0.Vpart == [] and r0.Jpart == []
+    # paired files, small pieces: same as the oracle's per-file restatement
+    lines = open(path).read().split("\n")
+    recs = [(lines[i][1:].split()[0], lines[i + 1], lines[i + 3]) for i in range(0, len(lines) - 3, 4)]
+    f1 = [r for r in recs if r[0].endswith("/1")][:2500]
+    f2 = [r for r in recs if r[0].endswith("/2")][:2300]
+    p1, p2 = str(tmp_path / "a_1.fq"), str(tmp_path / "a_2.fq")
+    for p, f in ((p1, f1), (p2, f2)):
+        with open(p, "w") as fh:
+            fh.write("".join(f"@{n}\n{s}\n+\n{q}\n" for n, s, q in f))
+    refp = O.run_mem_files(orefs[0], orefs[1], O.make_config(trb), [tuple(map(list, zip(*f1))), tuple(map(list, zip(*f2)))])
+    rp = c.mainflow_paired(p1, p2)
+    assert [myread_tuple(r) for r in rp.Vpart] == [myread_tuple(r) for r in refp.Vpart]
+    assert [myread_tuple(r) for r in rp.Jpart] == [myread_tuple(r) for r in refp.Jpart]
+    c.close()
