@@ -473,9 +473,10 @@ int dispatch_sw_bulk(const RefDev& ref, const ReadsDev& reads, const SwTask* tas
   if (n <= 64) return launch_sw_bulk<8, 8>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
   if (n <= 100) return launch_sw_bulk<4, 25>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
   if (n <= 104) return launch_sw_bulk<8, 13>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
-  // long records (IGHV, pig / mouse TRBV: 280-320 nt): few lanes with many columns keep the skew short (G - 1 idle steps per task)
-  if (n <= 160) return launch_sw_bulk<8, 20>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
-  if (n <= 320) return launch_sw_bulk<16, 20>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
+  // long records (IGHV, pig TRBV: 280-320 nt): few lanes with many columns keep the skew short (G - 1 idle steps per task);
+  // 40 columns per lane cost 152 registers and 2 CTAs / SM, which the two-row kernel tolerates (IGH: 4485 -> 5077 GCUPS vs 16 x 20)
+  if (n <= 160) return launch_sw_bulk<4, 40>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
+  if (n <= 320) return launch_sw_bulk<8, 40>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
   set_error("record length %d exceeds the SW kernel's tiling", n);
   return CATT_E_LIMIT;
 }
