@@ -409,7 +409,8 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
     tpos[f + 1] = (tpos[f + 1] + 15) & ~(int64_t)15;
   }
   int rc;
-  if ((rc = c->pin[PIN_TEXT].ensure((size_t)tpos[nfiles] + 16)) || (rc = c->rd_text.ensure((size_t)tpos[nfiles] + 16))) return rc;
+  if (c->pin[PIN_TEXT].ensure((size_t)tpos[nfiles] + 16) != CATT_OK) { cudaGetLastError(); return CATT_OK; }   // cannot pin that much: host path
+  if ((rc = c->rd_text.ensure((size_t)tpos[nfiles] + 16))) return rc;
   char* h = c->pin[PIN_TEXT].as<char>();
   char* d_text = c->rd_text.as<char>();
   // A reader thread brings the files into pinned memory block by block and, as soon as a record-aligned piece is complete (a line
