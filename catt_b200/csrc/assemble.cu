@@ -12,7 +12,8 @@
 //   * share_name, the NR % nthreads chunk order (closed form), the name-sorted both-mapped pairing (LSD radix sort over
 //     8-byte name digits) (catt.jl:221-319)
 //   * assignV/J, real_score, finder!, k-mer table, extension: extract.cu / pool.cu
-// The host only formats two numbers and materialises the Myread strings (the quality strings never leave host memory).
+// The Myread strings are written on the device too (materialise_kernel) and come back as three bulk copies; the host only
+// formats two numbers (mean length, error rate) the way `samtools stats` prints them.
 #include <omp.h>
 #include <stdio.h>
 #include <string.h>
@@ -451,17 +452,6 @@ void block_put(void* p, size_t cap) {
   g_blocks.free_list.push_back({p, cap});
   g_blocks.held += cap;
 }
-
-namespace {
-const char FWD[6] = "ACGTN";
-const char RCV[6] = "TGCAN";
-struct StrLut {
-  char fwd[256], rc[256];
-  StrLut() { for (int i = 0; i < 256; i++) { const uint8_t c = nt_code((char)i); fwd[i] = FWD[c]; rc[i] = RCV[c]; } }
-};
-const StrLut SLUT;
-
-}  // namespace
 
 // device -> host copy of one result arena.  Pinned (cached) blocks take one bulk copy; larger, unpinned blocks are filled through
 // two pinned 64 MiB ring buffers: the copy engine fills one while the host threads empty the other into the destination.
