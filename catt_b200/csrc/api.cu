@@ -305,6 +305,7 @@ int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool
   }
   CATT_CUDA(cudaStreamSynchronize(st));
   CATT_CUDA(cudaStreamSynchronize(cs));
+  c->last_n = n; c->last_words = (int64_t)total_words; c->last_max_len = max_len;
   if (under_kernels && !hook_done && (rc = under_kernels())) return rc;
   if (info && align) {
     info->ms_seed += local.ms_seed; info->ms_seed_kernel += local.ms_seed_kernel; info->ms_sw += local.ms_sw; info->ms_select += local.ms_select;
@@ -912,6 +913,23 @@ int catt_assemble(catt_ctx* c, int64_t n, const char* names, const int64_t* name
   return CATT_OK;
 }
 
+int catt_shard_counts(const catt_ctx* c, int64_t* n_reads, int64_t* n_words, int32_t* max_len) {
+  if (!c || !n_reads || !n_words || !max_len) return CATT_E_ARG;
+  *n_reads = c->last_n; *n_words = c->last_words; *max_len = c->last_max_len;
+  return CATT_OK;
+}
+
+int catt_reads_device(catt_ctx* c, int64_t cap_reads, int64_t cap_words, uint64_t* words_ptr, uint64_t* off_ptr, uint64_t* len_ptr) {
+  if (!c || !words_ptr || !off_ptr || !len_ptr || cap_reads < 0 || cap_words < 0) { set_error("catt_reads_device: bad argument"); return CATT_E_ARG; }
+  if ((uint64_t)cap_words > 0xFFFFFFF0ull) { set_error("batch too large: packed reads exceed 2^32 words"); return CATT_E_LIMIT; }
+  CATT_CUDA(cudaSetDevice(c->device));
+  int rc;
+  if ((rc = c->rd_words.ensure_keep((size_t)(cap_words + 4) * 4, c->stream)) || (rc = c->rd_off.ensure_keep((size_t)(cap_reads + 2) * 4, c->stream)) ||
+      (rc = c->rd_len.ensure_keep((size_t)(cap_reads + 1) * 4, c->stream))) return rc;
+  *words_ptr = (uint64_t)(uintptr_t)c->rd_words.p; *off_ptr = (uint64_t)(uintptr_t)c->rd_off.p; *len_ptr = (uint64_t)(uintptr_t)c->rd_len.p;
+  return CATT_OK;
+}
+
 int catt_records_device(catt_ctx* c, int which, int64_t capacity, uint64_t* device_ptr) {
   if (!c || !device_ptr || which < 0 || which > 1 || capacity < 0) { set_error("catt_records_device: bad argument"); return CATT_E_ARG; }
   CATT_CUDA(cudaSetDevice(c->device));
@@ -962,6 +980,55 @@ int catt_assemble_device(catt_ctx* c, int64_t n, const char* names, const int64_
   fh.start = {0, n};
   // pack + upload only; the records stay where the caller put them (ensure_recs never shrinks or moves a large enough array)
   if ((rc = stage_a_stream(c, hr, 0, false, true, &dr, &dq, &fh, &R->info, &launches))) return rc;
+  fh.single(n, R->info.v_hits, R->info.j_hits);
+  if (c->keep_records && (rc = download_records(c, n, R.get()))) return rc;
+  NamesDev nd;
+  if ((rc = upload_names(c, n, names, name_off, &nd, &R->info))) return rc;
+  if ((rc = stage_b(c, n, nd, dr.view(), dq, fh, R.get(), &launches))) return rc;
+  R->info.kernel_launches = launches;
+  *out = R.release();
+  return CATT_OK;
+}
+
+int catt_assemble_resident(catt_ctx* c, int64_t n, int32_t max_len, const char* names, const int64_t* name_off, const int64_t* seq_off,
+                           const char* quals, catt_result** out) {
+  if (!c || !out || n < 0 || (n > 0 && (!names || !name_off || !seq_off))) { set_error("catt_assemble_resident: bad argument"); return CATT_E_ARG; }
+  CATT_CUDA(cudaSetDevice(c->device));
+  const size_t rb = (size_t)n * sizeof(catt_aln);
+  if (c->recs_all[0].cap < rb || c->recs_all[1].cap < rb || c->rd_len.cap < (size_t)n * 4 || c->rd_off.cap < (size_t)(n + 1) * 4) {
+    set_error("catt_assemble_resident: the context's buffers hold fewer than n reads / records");
+    return CATT_E_ARG;
+  }
+  std::unique_ptr<catt_result> R(new catt_result());
+  R->info.n_reads = n;
+  int rc;
+  if ((rc = c->sb[SB_CNT].ensure(64 * sizeof(unsigned long long)))) return rc;
+  unsigned long long* d_cnt = c->sb[SB_CNT].as<unsigned long long>();
+  unsigned long long* cnt = c->pin[PIN_CNT].as<unsigned long long>();
+  CATT_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), c->stream));
+  if (n) {
+    for (int which = 0; which < 2; which++) count_mapped_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(c->recs_all[which].as<catt_aln>(), n, d_cnt + which);
+    CATT_CUDA(cudaGetLastError());
+  }
+  CATT_CUDA(cudaMemcpyAsync(cnt, d_cnt, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  CATT_CUDA(cudaStreamSynchronize(c->stream));
+  R->info.v_hits = (int64_t)cnt[0]; R->info.j_hits = (int64_t)cnt[1];
+  DeviceReads dr;
+  dr.words = c->rd_words.as<uint32_t>(); dr.off = c->rd_off.as<uint32_t>(); dr.len = c->rd_len.as<int32_t>(); dr.n = n; dr.max_len = max_len;
+  DeviceQuals dq;
+  if (n > 0) {
+    if ((rc = c->rd_seqoff.ensure((size_t)(n + 1) * sizeof(int64_t)))) return rc;
+    CATT_CUDA(cudaMemcpyAsync(c->rd_seqoff.p, seq_off, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    dq.seq_off = c->rd_seqoff.as<int64_t>();
+    if (c->only_cdr3) { dq.host_quals = quals; dq.host_seq_off = seq_off; }
+    else if (quals) {
+      if ((rc = c->rd_quals.ensure((size_t)seq_off[n] + 16))) return rc;
+      CATT_CUDA(cudaMemcpyAsync(c->rd_quals.p, quals, (size_t)seq_off[n], cudaMemcpyHostToDevice, c->stream));
+      dq.quals = c->rd_quals.as<char>();
+    }
+  }
+  int launches = 2;
+  FileHits fh;
   fh.single(n, R->info.v_hits, R->info.j_hits);
   if (c->keep_records && (rc = download_records(c, n, R.get()))) return rc;
   NamesDev nd;

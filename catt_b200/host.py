@@ -247,6 +247,25 @@ class Catt:
                                                     _addr(qual_buf) if qual_buf is not None else None, C.byref(h)))
         return Result(self, h)
 
+    def shard_counts(self):
+        """(reads, packed words, longest read) of what the last align_shard* call left in the context's read buffers."""
+        n, w, m = C.c_int64(), C.c_int64(), C.c_int32()
+        _lib.check(_lib.load().catt_shard_counts(self._h, C.byref(n), C.byref(w), C.byref(m)))
+        return n.value, w.value, m.value
+
+    def reads_device(self, cap_reads, cap_words):
+        """Device addresses (words, offsets, lengths) of the context's packed-read buffers, grown to the given capacities."""
+        a, b, c_ = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _lib.check(_lib.load().catt_reads_device(self._h, cap_reads, cap_words, C.byref(a), C.byref(b), C.byref(c_)))
+        return a.value, b.value, c_.value
+
+    def assemble_resident(self, n, max_len, name_buf, name_off, seq_off, qual_buf) -> Result:
+        """Stage B on n reads + records that are all resident in the context's buffers (after the NCCL gathers)."""
+        h = C.c_void_p()
+        _lib.check(_lib.load().catt_assemble_resident(self._h, n, max_len, _addr(name_buf), name_off.ctypes.data, seq_off.ctypes.data,
+                                                      _addr(qual_buf) if qual_buf is not None else None, C.byref(h)))
+        return Result(self, h)
+
     def upload(self, n, seq_buf, seq_off, first_ordinal=0) -> Batch:
         h = C.c_void_p()
         _lib.check(_lib.load().catt_batch_upload(self._h, n, _addr(seq_buf), seq_off.ctypes.data, first_ordinal, C.byref(h)))

@@ -180,6 +180,16 @@ int catt_records_device(catt_ctx* ctx, int which, int64_t capacity, uint64_t* de
 int catt_assemble_device(catt_ctx* ctx, int64_t n, const char* names, const int64_t* name_off, const char* seqs,
                          const int64_t* seq_off, const char* quals, catt_result** out);
 
+/* ... and the packed reads: after catt_align_shard the shard's 2-bit packed reads sit in the context's read buffers
+ * (catt_shard_counts says how many reads / words / the longest read); catt_reads_device returns the device addresses of the word,
+ * offset and length arrays, grown (contents kept) to the given capacities, so the ranks can all-gather them as well; and
+ * catt_assemble_resident runs Stage B on n reads + records that are ALL already in the context's buffers - the root re-reads
+ * nothing from the host except the QNAMEs (and, with only_cdr3, the quality strings of the few surviving reads). */
+int catt_shard_counts(const catt_ctx* ctx, int64_t* n_reads, int64_t* n_words, int32_t* max_len);
+int catt_reads_device(catt_ctx* ctx, int64_t cap_reads, int64_t cap_words, uint64_t* words_ptr, uint64_t* off_ptr, uint64_t* len_ptr);
+int catt_assemble_resident(catt_ctx* ctx, int64_t n, int32_t max_len, const char* names, const int64_t* name_off,
+                           const int64_t* seq_off, const char* quals, catt_result** out);
+
 /* Device-resident variant used by bench.py: upload once, run Stage A repeatedly on the resident batch, read back. */
 typedef struct catt_batch catt_batch;
 int catt_batch_upload(catt_ctx* ctx, int64_t n, const char* seqs, const int64_t* seq_off, int64_t first_ordinal,

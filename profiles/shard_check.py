@@ -14,7 +14,7 @@ from catt_b200.host import Catt, set_host_threads
 from catt_b200.refg import chain_config
 from catt_b200.shard import ShardedCatt
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 2000000
+n = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 2000000
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
@@ -23,11 +23,14 @@ set_host_threads(max(1, len(os.sched_getaffinity(0)) // world))
 d = tempfile.mkdtemp(prefix="catt_shard_")
 with tarfile.open(os.path.join(ROOT, "tests", "golden", "catt_fixture.tar.gz")) as tar:
     tar.extractall(d)
-ctx = Catt(chain_cfg=chain_config("hs", "TRB", "CDR3", os.path.join(d, "resource")), device=local)
-bufs = ctx.synth_reads(n, 150)                       # every rank generates the same whole sample
-key = lambda r: (r.seq, r.qual, r.vs, r.js, r.cdr3)
-for mode in ("host", "device"):
-    sc = ShardedCatt(ctx, device=dev, on_device=(mode == "device"))
+cc = chain_config("hs", "TRB", "CDR3", os.path.join(d, "resource"))
+ctx_full = Catt(chain_cfg=cc, device=local)
+ctx_cdr3 = Catt(chain_cfg=cc, device=local, only_cdr3=True)      # what catt.jl's default output needs (no full read lists)
+bufs = ctx_full.synth_reads(n, 150)                  # every rank generates the same whole sample
+modes = ("host", "device", "device+only_cdr3") if "--all" in sys.argv else ("device", "device+only_cdr3")
+for mode in modes:
+    ctx = ctx_cdr3 if mode.endswith("only_cdr3") else ctx_full
+    sc = ShardedCatt(ctx, device=dev, on_device=mode.startswith("device"))
     for rep in range(3):
         dist.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -35,6 +38,12 @@ for mode in ("host", "device"):
         dist.barrier(); torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if rank == 0 and rep == 2:
+            if sc.laps_ms:
+                print(f"[{mode}] rank 0 laps: " + ", ".join(f"{k} {v:.1f} ms" for k, v in sc.laps_ms.items()), flush=True)
+            whole_t = []
+            for _ in range(2):
+                t1 = time.perf_counter(); w2 = ctx.mainflow_buffers(n, *bufs); whole_t.append(time.perf_counter() - t1); w2.close()
+            print(f"[1 GPU, {mode}] the same sample in one unsharded call: {min(whole_t) * 1e3:.1f} ms", flush=True)
             print(f"[{world} GPUs, records gathered through {mode}] one sample of {n} reads: {dt * 1e3:.1f} ms = {n / dt / 1e6:.2f} M reads/s", flush=True)
         if rank == 0 and rep == 0:
             whole = ctx.mainflow_buffers(n, *bufs)
