@@ -694,6 +694,7 @@ void catt_ctx_destroy(catt_ctx* c) {
   c->rd_words.release(); c->rd_off.release(); c->rd_len.release(); c->rd_quals.release(); c->rd_seqoff.release();
   c->rd_text.release(); c->rd_nl.release(); c->rd_name_beg.release(); c->rd_name_end.release(); c->rd_seq_beg.release();
   c->rd_qual_beg.release(); c->rd_nwords.release();
+  for (auto& b : c->nb) b.release();
   cudaFree(c->d_finder); cudaFree(c->d_dseq); cudaFree(c->d_doff);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   for (auto& row : c->ev_a) for (auto& ev : row) if (ev) cudaEventDestroy(ev);

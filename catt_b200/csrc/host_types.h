@@ -93,7 +93,8 @@ struct catt_ctx {
   catt::AlignBuffers ab[2];
   DevBuf rd_words, rd_off, rd_len;        // packed reads of the sample being run (catt_run_*, catt_assemble)
   int64_t last_n = 0, last_words = 0; int last_max_len = 0;   // what the last Stage A left in rd_* (catt_shard_counts)
-  DevBuf rd_quals, rd_seqoff;             // its quality strings (as given) and int64 offsets, for the string kernel
+  DevBuf rd_quals, rd_seqoff;
+  DevBuf nb[4];                           // nbsorb scans (nbsorb.cu): raw sequences, query planes, target planes, aux             // its quality strings (as given) and int64 offsets, for the string kernel
   DevBuf rd_text, rd_nl, rd_name_beg, rd_name_end, rd_seq_beg, rd_qual_beg, rd_nwords;   // FASTQ text ingested on the device (ingest.cu)
   DevBuf recs_all[2];                     // one catt_aln per read and reference set, for the whole sample
   DevBuf sb[SB_COUNT];

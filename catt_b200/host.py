@@ -266,6 +266,39 @@ class Catt:
                                                       _addr(qual_buf) if qual_buf is not None else None, C.byref(h)))
         return Result(self, h)
 
+    @staticmethod
+    def _flat(seqs, lgt):
+        """n x lgt bytes, back to back: a list of equal-length strings or an (n, lgt) uint8 array."""
+        if isinstance(seqs, np.ndarray):
+            a = np.ascontiguousarray(seqs, dtype=np.uint8)
+            if a.ndim != 2 or a.shape[1] != lgt:
+                raise ValueError("sequence array must be (n, lgt) uint8")
+            return a, a.shape[0]
+        if any(len(s) != lgt for s in seqs):
+            raise ValueError("all sequences of one nbsorb group have the same length")
+        return np.frombuffer("".join(seqs).encode(), dtype=np.uint8), len(seqs)
+
+    def link_leaves(self, lgt, roots, uplimit, leaves, leaf_count):
+        """linkRLG for every leaf (Jtool.jl:396-421, 524-531): (statu, root_index) int32 arrays."""
+        r, nr = self._flat(roots, lgt)
+        l, nl = self._flat(leaves, lgt)
+        up = np.ascontiguousarray(np.asarray(uplimit, dtype=np.float64).reshape(nr, 7))
+        cnt = np.ascontiguousarray(leaf_count, dtype=np.int64)
+        if cnt.shape != (nl,):
+            raise ValueError("one count per leaf")
+        statu, hold = np.zeros(nl, dtype=np.int32), np.zeros(nl, dtype=np.int32)
+        _lib.check(_lib.load().catt_link_leaves(self._h, lgt, r.ctypes.data, nr, up.ctypes.data, l.ctypes.data, cnt.ctypes.data, nl,
+                                                statu.ctypes.data, hold.ctypes.data))
+        return statu, hold
+
+    def near_any(self, lgt, queries, targets, upper=3, skip=3):
+        """Jtool.jl:553-558: per query, is any target within `upper` mismatches of it (first / last `skip` positions ignored)?"""
+        q, nq = self._flat(queries, lgt)
+        t, nt = self._flat(targets, lgt)
+        flag = np.zeros(nq, dtype=np.uint8)
+        _lib.check(_lib.load().catt_near_any(self._h, lgt, q.ctypes.data, nq, t.ctypes.data, nt, upper, skip, flag.ctypes.data))
+        return flag
+
     def upload(self, n, seq_buf, seq_off, first_ordinal=0) -> Batch:
         h = C.c_void_p()
         _lib.check(_lib.load().catt_batch_upload(self._h, n, _addr(seq_buf), seq_off.ctypes.data, first_ordinal, C.byref(h)))

@@ -166,6 +166,19 @@ void catt_result_free(catt_result* r);
  * segment of the context's D list, or -1 for "None". */
 int catt_best_d(catt_ctx* ctx, const char* const* cdr3, int64_t n, int32_t* d_index_out);
 
+/* ---- the two O(n x m) scans of `nbsorb`; grouping, thresholds and tree assignment stay in Julia --- */
+/* Replaces the Threads.@threads loop over linkRLG (Jtool.jl:524-531 calling Jtool.jl:396-421).  All sequences of one nbsorb call have
+ * the same length `lgt` (catt.jl:624-633) and are passed back to back, n x lgt bytes over ACGTN, no terminators.
+ * `uplimit` = root_up (Jtool.jl:515-519), n_roots x 7 doubles; leaf_count = the leaves' frequencies.  Per leaf: statu = number of roots r
+ * with HammingDistanceG3(leaf, root_r, argmin|uplimit_r - count|; skip = 3), capped at 2, and root_index = 1-based index of the first
+ * such root (1 if none), exactly what linkRLG returns. */
+int catt_link_leaves(catt_ctx* ctx, int32_t lgt, const char* roots, int64_t n_roots, const double* uplimit, const char* leaves,
+                     const int64_t* leaf_count, int64_t n_leaves, int32_t* statu, int32_t* root_index);
+/* Replaces the inner `for confm in highconf` scan of Jtool.jl:553-558: flag[q] = 1 iff some target t has
+ * HammingDistanceG3(query_q, target_t, upper; skip) (the reference uses upper = 3, skip = 3).  The err_cnt tests around it stay in Julia. */
+int catt_near_any(catt_ctx* ctx, int32_t lgt, const char* queries, int64_t n_queries, const char* targets, int64_t n_targets,
+                  int32_t upper, int32_t skip, uint8_t* flag);
+
 /* ---- stage-level entry points (sharding, benchmarks, parity tests) --------------------------------------------- */
 /* Stage A = map2align for a shard of reads: seeding + SW + hit selection.  `first_ordinal` is the global index of
  * seqs[0] (bwa's hash tie-break uses the global read ordinal).  Writes n records per reference set. */

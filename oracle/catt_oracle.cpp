@@ -1324,4 +1324,53 @@ int co_result_records(void* r, int which, int32_t* out) {
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// nbsorb inner scans.  Parity note: the reference's golden CSV runs nbsorb, but on testSample every
+// distinct CDR3 is a root (threshold 1), so linkRLG never executes there and the maybe x highconf scan only ever meets
+// an identical sequence: these two restatements follow Jtool.jl line by line and are otherwise "parity unpinned".
+// ---------------------------------------------------------------------------------------------------------------
+// Jtool.jl:65-74 HammingDistanceG3(s1, s2, upper; skip): true unless more than `upper` of positions skip+1..len-skip differ
+static bool hamming_g3(const char* s1, const char* s2, int len, int64_t upper, int skip) {
+  int64_t cnt = 0;
+  for (int i = skip; i < len - skip; i++)
+    if (s1[i] != s2[i] && ++cnt > upper) return false;
+  return true;
+}
+
+// Jtool.jl:396-421 linkRLG for every leaf (the Threads.@threads loop at Jtool.jl:524-531).  roots / leaves: n x lgt bytes;
+// uplimit: n_roots x 7 doubles (Jtool.jl:515-519); statu = number of roots within reach, capped at 2; holder = 1-based index of the
+// first such root (1 when there is none).
+void co_link_leaves(int lgt, const char* roots, int64_t n_roots, const double* uplimit, const char* leaves, const int64_t* leaf_count,
+                    int64_t n_leaves, int32_t* statu, int32_t* holder) {
+  #pragma omp parallel for schedule(dynamic, 64)
+  for (int64_t l = 0; l < n_leaves; l++) {
+    int cnt = 0, hold = 1;
+    for (int64_t r = 0; r < n_roots; r++) {
+      const double* u = uplimit + r * 7;
+      int upper = 1;                                            // argmin(@. abs(uplimit[idy] - leaf[2])): first minimum, 1-based
+      double best = std::fabs(u[0] - (double)leaf_count[l]);
+      for (int x = 1; x < 7; x++) {
+        double dlt = std::fabs(u[x] - (double)leaf_count[l]);
+        if (dlt < best) { best = dlt; upper = x + 1; }
+      }
+      if (hamming_g3(leaves + l * lgt, roots + r * lgt, lgt, upper, 3)) {
+        if (++cnt > 1) break;
+        hold = (int)(r + 1);
+      }
+    }
+    statu[l] = cnt; holder[l] = hold;
+  }
+}
+
+// Jtool.jl:553-558: is any target within `upper` mismatches (positions skip+1..len-skip) of the query?
+void co_near_any(int lgt, const char* queries, int64_t nq, const char* targets, int64_t nt, int upper, int skip, uint8_t* flag) {
+  #pragma omp parallel for schedule(dynamic, 64)
+  for (int64_t q = 0; q < nq; q++) {
+    uint8_t f = 0;
+    for (int64_t t = 0; t < nt && !f; t++) f = hamming_g3(queries + q * lgt, targets + t * lgt, lgt, upper, skip);
+    flag[q] = f;
+  }
+}
+
 }  // extern "C"
+

@@ -71,7 +71,9 @@ def link_rlg(leaf, roots, uplimit):                        # Jtool.jl:396-421
     return cnt, holder
 
 
-def nbsorb(lgt, val, err_rate, sc_mode=False):             # Jtool.jl:475-590; val = [(cdr3, qual), ...]
+def nbsorb(lgt, val, err_rate, sc_mode=False, link_fn=None, near_fn=None):   # Jtool.jl:475-590; val = [(cdr3, qual), ...]
+    # link_fn(lgt, root_seqs, root_up, leaf_seqs, leaf_counts) -> (statu[], holder[]) and near_fn(lgt, query_seqs, target_seqs) -> flag[]
+    # stand in for the two scan loops (Jtool.jl:524-531, 553-558) when a test wants another implementation of them checked
     if not val:
         return set(), {}
     val = sorted(val, key=lambda x: x[0])
@@ -104,18 +106,25 @@ def nbsorb(lgt, val, err_rate, sc_mode=False):             # Jtool.jl:475-590; v
         nt = math.floor(max_value(p, L, root[1]))
         root_up.append([junfen(error_number(p, L, nt, x, 3.291), L * 3 ** x, 3.291) for x in range(1, 8)])
     trees = {}
-    for leaf in leafs:
-        statu, ridx = link_rlg(leaf, roots, root_up)
+    if link_fn is not None and leafs:
+        st, hd = link_fn(lgt, [r[0][0] for r in roots], root_up, [x[0][0] for x in leafs], [x[1] for x in leafs])
+        linked = list(zip([int(a) for a in st], [int(b) for b in hd]))
+    else:
+        linked = [link_rlg(leaf, roots, root_up) for leaf in leafs]
+    for leaf, (statu, ridx) in zip(leafs, linked):
         if statu == 0:
             conf.add(leaf[0][0])
         elif statu == 1:
             trees.setdefault(ridx, []).append(leaf)
     highconf = leafs + roots
     jiuji = set()
-    for x in maybe:
+    near = near_fn(lgt, [x[0][0] for x in maybe], [c[0][0] for c in highconf]) if near_fn is not None and maybe else None
+    for im, x in enumerate(maybe):
         flag = False
         if err_cnt_seq(x[0][0]) > 1:
             flag = True
+        elif near is not None:
+            flag = bool(near[im])
         else:
             for confm in highconf:
                 if hamming_g3(x[0][0], confm[0][0], 3, skip=3):
@@ -166,7 +175,7 @@ def prob_of(aa, tab):                                      # catt.jl:656-669
     return round(v, 5)
 
 
-def clonotype_table(Vpart, Jpart, the_err, dlist=None, best_d=None, sc_mode=False, prob_tab=None):
+def clonotype_table(Vpart, Jpart, the_err, dlist=None, best_d=None, sc_mode=False, prob_tab=None, link_fn=None, near_fn=None):
     """catt.jl:583-686 from the filtered Vpart/Jpart to output rows.
     Returns Counter{(AAseq, NNseq, Vregion, Jregion, Dregion) -> Frequency} (row order is Julia Dict order in the
     reference, so rows are compared as a multiset)."""
@@ -177,7 +186,7 @@ def clonotype_table(Vpart, Jpart, the_err, dlist=None, best_d=None, sc_mode=Fals
         grp = [r for r in V if len(r.cdr3) == lgt] + [r for r in J if len(r.cdr3) == lgt]
         if not grp:
             continue
-        cf, c2c = nbsorb(lgt, [(r.cdr3, r.qual) for r in grp], the_err, sc_mode)
+        cf, c2c = nbsorb(lgt, [(r.cdr3, r.qual) for r in grp], the_err, sc_mode, link_fn, near_fn)
         conf |= cf
         seq2seq.update(c2c)
         res += grp

@@ -77,6 +77,10 @@ def lib():
         L.co_result_dump.restype = C.c_char_p
         L.co_result_dump.argtypes = [C.c_void_p, C.c_int]
         L.co_result_records.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.co_link_leaves.restype = None
+        L.co_link_leaves.argtypes = [C.c_int, C.c_char_p, C.c_int64, C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.co_near_any.restype = None
+        L.co_near_any.argtypes = [C.c_int, C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]
         _lib = L
     return _lib
 
@@ -273,3 +277,20 @@ def run_flat(vref: RefSet, jref: RefSet, cfg: CoConfig, seqs: np.ndarray, quals:
     L.co_run_flat.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(CoConfig), C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     n, length = seqs.shape
     return RunResult(L.co_run_flat(vref.h, jref.h, C.byref(cfg), n, first_index, length, seqs.ctypes.data, quals.ctypes.data, threads))
+
+
+def link_leaves(lgt: int, roots, uplimit, leaves, leaf_count):
+    """Jtool.jl:396-421 over every leaf: (statu, holder) int32 arrays.  roots / leaves: lists of equal-length strings."""
+    up = np.ascontiguousarray(np.asarray(uplimit, dtype=np.float64).reshape(len(roots), 7))
+    cnt = np.ascontiguousarray(leaf_count, dtype=np.int64)
+    statu, hold = np.zeros(len(leaves), dtype=np.int32), np.zeros(len(leaves), dtype=np.int32)
+    lib().co_link_leaves(lgt, "".join(roots).encode(), len(roots), up.ctypes.data, "".join(leaves).encode(), cnt.ctypes.data, len(leaves),
+                         statu.ctypes.data, hold.ctypes.data)
+    return statu, hold
+
+
+def near_any(lgt: int, queries, targets, upper=3, skip=3):
+    """Jtool.jl:553-558: per query, is any target within `upper` mismatches (ends skipped)?"""
+    flag = np.zeros(len(queries), dtype=np.uint8)
+    lib().co_near_any(lgt, "".join(queries).encode(), len(queries), "".join(targets).encode(), len(targets), upper, skip, flag.ctypes.data)
+    return flag
