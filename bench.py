@@ -115,6 +115,30 @@ def roofline_other(infos, length, world):
     return out
 
 
+def nbsorb_scans(ctx, np, peak_ops):
+    """the low-count neighbour scan of nbsorb (Jtool.jl:553-558) through catt_near_any, 10^6 x 10^4 random 45-nt
+    sequences from host buffers (no early exit: every pair is compared), and linkRLG (Jtool.jl:396-421) through catt_link_leaves."""
+    rng = np.random.default_rng(1)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    lgt, nq, nt = 45, 1_000_000, 10_000
+    q, t = lut[rng.integers(0, 4, size=(nq, lgt))], lut[rng.integers(0, 4, size=(nt, lgt))]
+    ctx.near_any(lgt, q, t)
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter(); ctx.near_any(lgt, q, t); ts.append(time.perf_counter() - t0)
+    dt = sorted(ts)[1]
+    nl, nr = 200_000, 2_000
+    up = np.tile(np.array([40.0, 12.0, 4.0, 1.5, 1.0, 1.0, 1.0]), (nr, 1))
+    cnt = rng.integers(1, 50, size=nl)
+    ctx.link_leaves(lgt, t[:nr], up, q[:nl], cnt)
+    t0 = time.perf_counter(); ctx.link_leaves(lgt, t[:nr], up, q[:nl], cnt); dl = time.perf_counter() - t0
+    return {"near_any": {"pairs": nq * nt, "ms_per_call": dt * 1e3, "pairs_per_s": nq * nt / dt, "base_compares_per_s": nq * nt * (lgt - 6) / dt},
+            "link_leaves": {"pairs": nl * nr, "ms_per_call": dl * 1e3, "pairs_per_s": nl * nr / dl},
+            "note": "wall clock of the C-ABI call, pageable host buffers in / flags out (upload + bit-plane packing + scan + download); "
+                    "kernel-only times in profiles/r01i_nbsorb_scans.txt; integer-ALU bound (2 LOP3 + 1 POPC per rejected pair), "
+                    f"measured ALU issue peak {peak_ops / 1e12:.2f} T thread-instr/s"}
+
+
 def file_e2e(ctx, np, R, length, seq_buf, qual_buf, first):
     """The same batch as a FASTQ file on local disk through catt_run_file - the call the patched Julia driver makes
     (INTEGRATION.md): parallel pread into pinned memory, text to HBM, indexing / validation / 2-bit packing on the device."""
@@ -368,6 +392,7 @@ def main():
         ctx_full.close()
     if rank == 0 and world == 1 and not args.no_file_e2e:
         line["e2e_file"] = file_e2e(ctx, np, R, args.length, seq_buf, qual_buf, first)
+        line["nbsorb_scans"] = nbsorb_scans(ctx, np, peak_ops)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
         n = args.cpu_sample or max(16000, 15000 * cores)       # ~15 s of CPU work on `cores` threads

@@ -75,13 +75,15 @@ __device__ __forceinline__ int reach_of(const double* __restrict__ u, double cnt
 }
 
 // LINK: count the targets within reach (stop at 2) and remember the first one; !LINK: flag the query if any target is within `upper`.
-template <int NW, bool LINK>
+// PARITY picks the reject test: one parity plane, eight targets per branch (bounds <= 4), or the lo and hi planes, four per branch.
+template <int NW, bool LINK, bool PARITY>
 __global__ void __launch_bounds__(NB_THREADS)
 nb_scan_kernel(const uint32_t* __restrict__ qp, int64_t nq, const uint32_t* __restrict__ tp, int64_t nt, int64_t per_split,
                const double* __restrict__ uplimit, const int64_t* __restrict__ qcount, int upper,
                unsigned int* __restrict__ cnt_out, unsigned int* __restrict__ first_out, uint8_t* __restrict__ flag_out) {
   __shared__ __align__(16) uint32_t tile[NB_TILE * 3 * NW];
-  __shared__ __align__(16) uint2 quick[NB_TILE];          // (lo, hi) plane of word 0: the 2-instruction-per-plane reject test
+  __shared__ __align__(16) uint2 quick2[NB_TILE];         // word 0 of the lo and hi planes, or (PARITY) lo ^ hi packed as uint32
+  uint32_t* quick = reinterpret_cast<uint32_t*>(quick2);
   const int64_t q = (int64_t)blockIdx.x * NB_THREADS + threadIdx.x;
   const bool live = q < nq;
   uint32_t my[3 * NW];
@@ -110,20 +112,36 @@ nb_scan_kernel(const uint32_t* __restrict__ qp, int64_t nq, const uint32_t* __re
     // every thread of the block has what it needs (or does not exist): the remaining tiles cannot change any output
     if (__syncthreads_and(!live || found >= (LINK ? 2 : 1))) break;
     for (int k = threadIdx.x; k < cntt * 3 * NW; k += NB_THREADS) tile[k] = tp[t0 * 3 * NW + k];
-    for (int k = threadIdx.x; k < NB_TILE; k += NB_THREADS)
-      quick[k] = k < cntt ? make_uint2(tp[(t0 + k) * 3 * NW], tp[(t0 + k) * 3 * NW + NW]) : make_uint2(0u, 0u);   // padding: the full test below never looks past cntt
+    for (int k = threadIdx.x; k < NB_TILE; k += NB_THREADS) {      // padding entries: the full test below never looks past cntt
+      const uint32_t lo = k < cntt ? tp[(t0 + k) * 3 * NW] : 0u, hi = k < cntt ? tp[(t0 + k) * 3 * NW + NW] : 0u;
+      if (PARITY) quick[k] = lo ^ hi; else quick2[k] = make_uint2(lo, hi);
+    }
     __syncthreads();
     if (live && found < (LINK ? 2 : 1)) {
-      // mismatches of word 0 in the lo/hi planes are a lower bound of the pair's mismatches: unrelated sequences (~3/4 of the
-      // positions differ) fail it, four targets per branch; only the rare survivors take the full three-plane test, in order
+      // The reject test is a lower bound of the pair's mismatches from word 0 alone; unrelated sequences fail it and only the rare
+      // survivors take the full three-plane test, in target order.  Two planes (popc((lo^lo')|(hi^hi')), 3/4 of unrelated positions
+      // count, 4 targets per branch) when the bound is large; for bounds <= 4 the parity plane lo^hi is enough (two bases whose
+      // parities differ differ; half of the unrelated positions count): 1 LOP3 + 1 POPC per pair, 8 targets per branch.
       bool done = false;
-      for (int i = 0; i < cntt && !done; i += 4) {
-        const uint4 a = *reinterpret_cast<const uint4*>(&quick[i]);
-        const uint4 b = *reinterpret_cast<const uint4*>(&quick[i + 2]);
-        const int m0 = __popc((my[0] ^ a.x) | (my[NW] ^ a.y)), m1 = __popc((my[0] ^ a.z) | (my[NW] ^ a.w));
-        const int m2 = __popc((my[0] ^ b.x) | (my[NW] ^ b.y)), m3 = __popc((my[0] ^ b.z) | (my[NW] ^ b.w));
-        if (min(min(m0, m1), min(m2, m3)) > bound) continue;
-        for (int k = 0; k < 4 && i + k < cntt && !done; k++) done = full(i + k, t0 + i + k);
+      if (PARITY) {
+        const uint32_t mine = my[0] ^ my[NW];
+        for (int i = 0; i < cntt && !done; i += 8) {
+          const uint4 a = *reinterpret_cast<const uint4*>(&quick[i]);
+          const uint4 b = *reinterpret_cast<const uint4*>(&quick[i + 4]);
+          const int m0 = __popc(mine ^ a.x), m1 = __popc(mine ^ a.y), m2 = __popc(mine ^ a.z), m3 = __popc(mine ^ a.w);
+          const int m4 = __popc(mine ^ b.x), m5 = __popc(mine ^ b.y), m6 = __popc(mine ^ b.z), m7 = __popc(mine ^ b.w);
+          if (min(min(min(m0, m1), min(m2, m3)), min(min(m4, m5), min(m6, m7))) > bound) continue;
+          for (int k = 0; k < 8 && i + k < cntt && !done; k++) done = full(i + k, t0 + i + k);
+        }
+      } else {
+        for (int i = 0; i < cntt && !done; i += 4) {
+          const uint4 a = *reinterpret_cast<const uint4*>(&quick2[i]);
+          const uint4 b = *reinterpret_cast<const uint4*>(&quick2[i + 2]);
+          const int m0 = __popc((my[0] ^ a.x) | (my[NW] ^ a.y)), m1 = __popc((my[0] ^ a.z) | (my[NW] ^ a.w));
+          const int m2 = __popc((my[0] ^ b.x) | (my[NW] ^ b.y)), m3 = __popc((my[0] ^ b.z) | (my[NW] ^ b.w));
+          if (min(min(m0, m1), min(m2, m3)) > bound) continue;
+          for (int k = 0; k < 4 && i + k < cntt && !done; k++) done = full(i + k, t0 + i + k);
+        }
       }
     }
   }
@@ -142,14 +160,14 @@ __global__ void nb_link_finish_kernel(const unsigned int* __restrict__ cnt, cons
   holder[i] = c ? (int32_t)first[i] + 1 : 1;
 }
 
-template <bool LINK>
+template <bool LINK, bool PARITY>
 int launch_scan(int nw, dim3 grid, cudaStream_t st, const uint32_t* qp, int64_t nq, const uint32_t* tp, int64_t nt, int64_t per_split,
                 const double* up, const int64_t* qc, int upper, unsigned int* cnt, unsigned int* first, uint8_t* flag) {
   switch (nw) {
-    case 1: nb_scan_kernel<1, LINK><<<grid, NB_THREADS, 0, st>>>(qp, nq, tp, nt, per_split, up, qc, upper, cnt, first, flag); break;
-    case 2: nb_scan_kernel<2, LINK><<<grid, NB_THREADS, 0, st>>>(qp, nq, tp, nt, per_split, up, qc, upper, cnt, first, flag); break;
-    case 3: nb_scan_kernel<3, LINK><<<grid, NB_THREADS, 0, st>>>(qp, nq, tp, nt, per_split, up, qc, upper, cnt, first, flag); break;
-    default: nb_scan_kernel<4, LINK><<<grid, NB_THREADS, 0, st>>>(qp, nq, tp, nt, per_split, up, qc, upper, cnt, first, flag); break;
+    case 1: nb_scan_kernel<1, LINK, PARITY><<<grid, NB_THREADS, 0, st>>>(qp, nq, tp, nt, per_split, up, qc, upper, cnt, first, flag); break;
+    case 2: nb_scan_kernel<2, LINK, PARITY><<<grid, NB_THREADS, 0, st>>>(qp, nq, tp, nt, per_split, up, qc, upper, cnt, first, flag); break;
+    case 3: nb_scan_kernel<3, LINK, PARITY><<<grid, NB_THREADS, 0, st>>>(qp, nq, tp, nt, per_split, up, qc, upper, cnt, first, flag); break;
+    default: nb_scan_kernel<4, LINK, PARITY><<<grid, NB_THREADS, 0, st>>>(qp, nq, tp, nt, per_split, up, qc, upper, cnt, first, flag); break;
   }
   CATT_CUDA(cudaGetLastError());
   return CATT_OK;
@@ -219,7 +237,7 @@ int catt_link_leaves(catt_ctx* c, int32_t lgt, const char* roots, int64_t n_root
   CATT_CUDA(cudaMemsetAsync(aux + o_f, 0xFF, (size_t)n_leaves * 4, c->stream));
   dim3 grid; int64_t per_split;
   split_targets(c, n_leaves, n_roots, &grid, &per_split);
-  if ((rc = launch_scan<true>(nw, grid, c->stream, c->nb[1].as<uint32_t>(), n_leaves, c->nb[2].as<uint32_t>(), n_roots, per_split,
+  if ((rc = launch_scan<true, false>(nw, grid, c->stream, c->nb[1].as<uint32_t>(), n_leaves, c->nb[2].as<uint32_t>(), n_roots, per_split,
                               (const double*)(aux + o_up), (const int64_t*)(aux + o_cnt), 0, (unsigned int*)(aux + o_c),
                               (unsigned int*)(aux + o_f), nullptr))) return rc;
   nb_link_finish_kernel<<<(unsigned)((n_leaves + 255) / 256), 256, 0, c->stream>>>((unsigned int*)(aux + o_c), (unsigned int*)(aux + o_f), n_leaves,
@@ -251,8 +269,11 @@ int catt_near_any(catt_ctx* c, int32_t lgt, const char* queries, int64_t nq, con
   CATT_CUDA(cudaMemsetAsync(aux + 256, 0, (size_t)nq, c->stream));
   dim3 grid; int64_t per_split;
   split_targets(c, nq, nt, &grid, &per_split);
-  if ((rc = launch_scan<false>(nw, grid, c->stream, c->nb[1].as<uint32_t>(), nq, c->nb[2].as<uint32_t>(), nt, per_split, nullptr, nullptr,
-                               upper, nullptr, nullptr, (uint8_t*)(aux + 256)))) return rc;
+  rc = upper <= 4 ? launch_scan<false, true>(nw, grid, c->stream, c->nb[1].as<uint32_t>(), nq, c->nb[2].as<uint32_t>(), nt, per_split, nullptr,
+                                             nullptr, upper, nullptr, nullptr, (uint8_t*)(aux + 256))
+                  : launch_scan<false, false>(nw, grid, c->stream, c->nb[1].as<uint32_t>(), nq, c->nb[2].as<uint32_t>(), nt, per_split, nullptr,
+                                              nullptr, upper, nullptr, nullptr, (uint8_t*)(aux + 256));
+  if (rc) return rc;
   int bad = 0;
   CATT_CUDA(cudaMemcpyAsync(flag, aux + 256, (size_t)nq, cudaMemcpyDeviceToHost, c->stream));
   CATT_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
