@@ -56,7 +56,7 @@ EXPORTS = ["catt_ctx_create", "catt_ctx_destroy", "catt_last_error", "catt_versi
            "catt_result_free", "catt_best_d", "catt_align_shard", "catt_batch_upload", "catt_batch_align", "catt_batch_sync",
            "catt_batch_download", "catt_batch_free", "catt_ctx_stream", "catt_assemble", "catt_seed_candidates", "catt_sw_pairs",
            "catt_finder", "catt_alu_peak", "catt_batch_assemble", "catt_synth_reads", "catt_run_files", "catt_run_reads_files", "catt_set_host_threads", "catt_records_device", "catt_assemble_device", "catt_shard_counts", "catt_reads_device",
-           "catt_assemble_resident", "catt_link_leaves", "catt_near_any"]
+           "catt_assemble_resident", "catt_link_leaves", "catt_near_any", "catt_run_bam", "catt_bam_to_fastq", "catt_inflate_file"]
 
 _lib = None
 
@@ -86,6 +86,9 @@ def load():
     L.catt_assemble_device.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, C.POINTER(vp)]
     L.catt_shard_counts.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
     L.catt_reads_device.argtypes = [vp, C.c_int64, C.c_int64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.catt_run_bam.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    L.catt_bam_to_fastq.argtypes = [C.c_char_p, C.c_char_p]
+    L.catt_inflate_file.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_int32)]
     L.catt_link_leaves.argtypes = [vp, C.c_int32, vp, C.c_int64, vp, vp, vp, C.c_int64, vp, vp]
     L.catt_near_any.argtypes = [vp, C.c_int32, vp, C.c_int64, vp, C.c_int64, C.c_int32, C.c_int32, vp]
     L.catt_assemble_resident.argtypes = [vp, C.c_int64, C.c_int32, vp, vp, vp, vp, C.POINTER(vp)]

@@ -16,11 +16,12 @@
 #include <omp.h>
 #include <unistd.h>
 
+#include "gz.h"
 #include "host_types.h"
 
 namespace catt {
 const char* last_error();
-bool slurp_file(const std::string& path, std::string& out);
+int parse_bam(const char* path, HostReads* hr);          // bam.cu
 }  // namespace catt
 
 using namespace catt;
@@ -779,6 +780,52 @@ int catt_run_files(catt_ctx* c, int32_t nfiles, const char* const* paths, catt_r
   }
   tr.lap("run_files: read + parse");
   return run_all(c, hr, fs, out);
+}
+
+int catt_run_bam(catt_ctx* c, const char* path, catt_result** out) {
+  if (!c || !path || !out) { set_error("catt_run_bam: null argument"); return CATT_E_ARG; }
+  CATT_CUDA(cudaSetDevice(c->device));
+  HostReads hr;
+  Trace tr;
+  int rc = parse_bam(path, &hr);
+  if (rc) return rc;
+  tr.lap("run_bam: inflate + decode");
+  return run_all(c, hr, {0, hr.n}, out);
+}
+
+int catt_inflate_file(const char* path, const char* out_path, int32_t* method) {
+  if (!path || !out_path) { set_error("catt_inflate_file: null argument"); return CATT_E_ARG; }
+  std::string txt;
+  int how = 0;
+  if (!slurp_file(path, txt, &how)) { set_error("cannot read %s", path); return CATT_E_IO; }
+  FILE* f = fopen(out_path, "wb");
+  if (!f) { set_error("cannot write %s", out_path); return CATT_E_IO; }
+  const bool ok = fwrite(txt.data(), 1, txt.size(), f) == txt.size();
+  if (fclose(f) != 0 || !ok) { set_error("short write to %s", out_path); return CATT_E_IO; }
+  if (method) *method = how;
+  return CATT_OK;
+}
+
+int catt_bam_to_fastq(const char* bam_path, const char* fastq_path) {
+  if (!bam_path || !fastq_path) { set_error("catt_bam_to_fastq: null argument"); return CATT_E_ARG; }
+  HostReads hr;
+  int rc = parse_bam(bam_path, &hr);
+  if (rc) return rc;
+  FILE* f = fopen(fastq_path, "wb");
+  if (!f) { set_error("cannot write %s", fastq_path); return CATT_E_IO; }
+  std::string buf;
+  for (int64_t i = 0; i < hr.n; i++) {
+    const int64_t s0 = hr.seq_off[i], s1 = hr.seq_off[i + 1];
+    buf += '@'; buf.append(hr.names + hr.name_off[i], (size_t)(hr.name_off[i + 1] - hr.name_off[i])); buf += '\n';
+    buf.append(hr.seqs + s0, (size_t)(s1 - s0)); buf += "\n+\n";
+    buf.append(hr.quals + s0, (size_t)(s1 - s0)); buf += '\n';
+    if (buf.size() > (1u << 24) || i + 1 == hr.n) {
+      if (fwrite(buf.data(), 1, buf.size(), f) != buf.size()) { fclose(f); set_error("short write to %s", fastq_path); return CATT_E_IO; }
+      buf.clear();
+    }
+  }
+  if (fclose(f) != 0) { set_error("cannot close %s", fastq_path); return CATT_E_IO; }
+  return CATT_OK;
 }
 
 int catt_result_info(const catt_result* r, catt_info* out) { if (!r || !out) return CATT_E_ARG; *out = r->info; return CATT_OK; }

@@ -1,0 +1,597 @@
+// pgz.cu — parallel inflate of an ordinary (single-member) gzip file on the host threads, for `.fastq.gz` / `.fa.gz` input
+// (the reference hands such files to bwa, which reads them through zlib on one thread; at 13 M reads/s on the GPU a
+// single zlib stream (~0.2-0.3 GB/s of text, < 1 M reads/s) would be the whole run time).
+//
+// A deflate stream can only be decoded from its start: blocks begin at arbitrary bit offsets and matches reach 32 KiB back.  So:
+//   1. the compressed bytes are cut into chunks; for every chunk a finder looks for the first bit offset at which a non-final
+//      dynamic-Huffman block starts (header fields in range, complete code-length / literal / distance codes, and the block plus
+//      the header after it decode cleanly);
+//   2. chunks are decoded in parallel from their start to the next chunk's start into 16-bit symbols: a byte, or - where a match
+//      reaches back past the chunk start - a marker holding the position in the unknown 32 KiB window;
+//   3. windows are propagated chunk by chunk (32 KiB each, sequential), then all markers are replaced in parallel while the bytes
+//      are written to the output and CRC-32'd.
+// Every assumption is checked: a decode error, a chunk that does not end exactly where the next one starts, a marker in the first
+// chunk, a second gzip member, or a CRC-32 / ISIZE mismatch against the gzip trailer makes pgz_inflate() return false, and the
+// caller reads the file through zlib as before.  BGZF files (bgzip, BAM) have independent members and take bam.cu's block path.
+// Checked against zlib's output in tests/test_gz_input.py.
+#include <omp.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "gz.h"
+#include "internal.cuh"
+
+namespace catt {
+namespace {
+
+constexpr int FAST_BITS = 11;
+constexpr uint16_t MARK = 0x8000;
+
+const uint16_t LEN_BASE[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+const uint8_t LEN_EXTRA[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+const uint16_t DIST_BASE[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+const uint8_t DIST_EXTRA[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+const uint8_t CL_ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+// LSB-first bit reader over a buffer with >= 8 readable bytes of padding behind `nbits`
+struct Bits {
+  const uint8_t* base; uint64_t pos, nbits;
+  inline uint64_t window() const { uint64_t w; memcpy(&w, base + (pos >> 3), 8); return w >> (pos & 7); }      // >= 57 valid bits
+  inline uint32_t peek(int n) const { return (uint32_t)(window() & ((1ull << n) - 1)); }
+  inline uint32_t take(int n) { const uint32_t v = peek(n); pos += n; return v; }
+  inline bool over() const { return pos > nbits; }
+};
+
+struct Huff {
+  uint16_t fast[1 << FAST_BITS];          // (symbol << 4) | length, 0 = longer than FAST_BITS (or unused)
+  uint16_t count[16], symbol[288];
+  int maxlen;
+};
+
+// zlib's rule (inftrees.c): over-subscribed sets are invalid; an incomplete set is invalid for the code-length code (kind 0) and,
+// for the literal/length and distance codes (kind 1), unless it is a single code of length 1 (or, distance only, no code at all)
+bool build_huff(Huff& h, const uint8_t* lens, int n, int kind) {
+  memset(h.count, 0, sizeof h.count);
+  for (int i = 0; i < n; i++) h.count[lens[i]]++;
+  h.count[0] = 0;
+  int left = 1, total = 0;
+  h.maxlen = 0;
+  for (int l = 1; l <= 15; l++) {
+    left = (left << 1) - h.count[l];
+    if (left < 0) return false;                       // over-subscribed
+    total += h.count[l];
+    if (h.count[l]) h.maxlen = l;
+  }
+  if (left > 0 && (kind == 0 || h.maxlen > 1)) return false;     // incomplete
+  uint16_t offs[16];
+  offs[1] = 0;
+  for (int l = 1; l < 15; l++) offs[l + 1] = offs[l] + h.count[l];
+  for (int i = 0; i < n; i++) if (lens[i]) h.symbol[offs[lens[i]]++] = (uint16_t)i;
+  memset(h.fast, 0, sizeof h.fast);
+  int code = 0, idx = 0;
+  for (int l = 1; l <= std::min(15, FAST_BITS); l++) {
+    for (int k = 0; k < h.count[l]; k++, code++, idx++) {
+      uint32_t rev = 0;
+      for (int b = 0; b < l; b++) rev |= ((code >> b) & 1u) << (l - 1 - b);
+      const uint16_t e = (uint16_t)((h.symbol[idx] << 4) | l);
+      for (uint32_t x = rev; x < (1u << FAST_BITS); x += 1u << l) h.fast[x] = e;
+    }
+    code <<= 1;
+  }
+  return true;
+}
+
+inline int decode_sym(const Huff& h, Bits& b) {
+  const uint64_t w = b.window();
+  const uint16_t e = h.fast[w & ((1u << FAST_BITS) - 1)];
+  if (e) { b.pos += e & 15; return e >> 4; }
+  int code = 0, first = 0, index = 0;                 // canonical walk (codes longer than FAST_BITS are rare)
+  for (int l = 1; l <= h.maxlen; l++) {
+    code |= (int)((w >> (l - 1)) & 1);
+    const int cnt = h.count[l];
+    if (code - cnt < first) { b.pos += l; return h.symbol[index + (code - first)]; }
+    index += cnt; first += cnt; first <<= 1; code <<= 1;
+  }
+  return -1;
+}
+
+// First-touch page faults are the cost that does not parallelise (and are slow in a VM): big buffers are 2 MiB aligned and ask for
+// transparent huge pages, and the symbol buffers are reused from wave to wave.
+void* big_alloc(size_t bytes) {
+  void* p = nullptr;
+  const size_t al = 2u << 20;
+  bytes = (bytes + al - 1) / al * al;
+  if (posix_memalign(&p, al, bytes) != 0) return nullptr;
+  madvise(p, bytes, MADV_HUGEPAGE);
+  return p;
+}
+void advise_huge(const void* p, size_t bytes) {
+  const uintptr_t al = 2u << 20, a = ((uintptr_t)p + al - 1) / al * al, e = ((uintptr_t)p + bytes) / al * al;
+  if (e > a) madvise((void*)a, e - a, MADV_HUGEPAGE);
+}
+
+struct SymBuf {
+  uint16_t* p = nullptr; size_t n = 0, cap = 0;
+  SymBuf() = default;
+  SymBuf(const SymBuf&) = delete;
+  SymBuf& operator=(const SymBuf&) = delete;
+  SymBuf(SymBuf&& o) noexcept : p(o.p), n(o.n), cap(o.cap) { o.p = nullptr; o.n = o.cap = 0; }
+  SymBuf& operator=(SymBuf&& o) noexcept { if (this != &o) { free(p); p = o.p; n = o.n; cap = o.cap; o.p = nullptr; o.n = o.cap = 0; } return *this; }
+  ~SymBuf() { free(p); }
+  bool room(size_t extra) {
+    if (n + extra <= cap) return true;
+    const size_t want = std::max(cap * 2, n + extra + (4u << 20));
+    uint16_t* q = (uint16_t*)big_alloc(want * sizeof(uint16_t));
+    if (!q) return false;
+    if (n) memcpy(q, p, n * sizeof(uint16_t));
+    free(p);
+    p = q; cap = want;
+    return true;
+  }
+};
+
+struct Tables { Huff lit, dist; };
+
+// Reads a dynamic block header at b (BFINAL / BTYPE already consumed) and builds both tables.
+bool read_dynamic_header(Bits& b, Tables& t) {
+  if (b.pos + 14 + 12 > b.nbits) return false;
+  const int hlit = (int)b.take(5) + 257, hdist = (int)b.take(5) + 1, hclen = (int)b.take(4) + 4;
+  if (hlit > 286 || hdist > 30) return false;
+  uint8_t cl[19] = {0};
+  for (int i = 0; i < hclen; i++) cl[CL_ORDER[i]] = (uint8_t)b.take(3);
+  Huff& clh = t.dist;                                  // scratch: rebuilt below
+  if (!build_huff(clh, cl, 19, 0)) return false;
+  uint8_t lens[286 + 30 + 138];
+  int i = 0;
+  while (i < hlit + hdist) {
+    if (b.over()) return false;
+    const int s = decode_sym(clh, b);
+    if (s < 0) return false;
+    if (s < 16) { lens[i++] = (uint8_t)s; continue; }
+    int rep, val = 0;
+    if (s == 16) { if (i == 0) return false; val = lens[i - 1]; rep = 3 + (int)b.take(2); }
+    else if (s == 17) rep = 3 + (int)b.take(3);
+    else rep = 11 + (int)b.take(7);
+    if (i + rep > hlit + hdist) return false;
+    while (rep--) lens[i++] = (uint8_t)val;
+  }
+  if (lens[256] == 0) return false;                    // no end-of-block code
+  if (!build_huff(t.lit, lens, hlit, 1)) return false;
+  return build_huff(t.dist, lens + hlit, hdist, 1);
+}
+
+// One deflate block at b, symbols appended to out (nullptr = validate only).  Returns 0 ok, 1 ok and it was the final block, < 0 error.
+int decode_block(Bits& b, SymBuf* out, size_t* produced, Tables& scratch) {
+  if (b.pos + 3 > b.nbits) return -1;
+  const int final = (int)b.take(1), type = (int)b.take(2);
+  if (type == 3) return -1;
+  if (type == 0) {
+    b.pos = (b.pos + 7) & ~7ull;
+    if (b.pos + 32 > b.nbits) return -1;
+    const uint32_t len = b.take(16), nlen = b.take(16);
+    if ((len ^ nlen) != 0xFFFF) return -1;
+    if (b.pos + 8ull * len > b.nbits) return -1;
+    if (out) {
+      if (!out->room(len)) return -2;
+      const uint8_t* s = b.base + (b.pos >> 3);
+      for (uint32_t i = 0; i < len; i++) out->p[out->n++] = s[i];
+    }
+    *produced += len;
+    b.pos += 8ull * len;
+    return final;
+  }
+  const Tables* t = &scratch;
+  if (type == 2) { if (!read_dynamic_header(b, scratch)) return -1; }
+  else {
+    // fixed code: the distance code has 30 of 32 codes; build once, permissively
+    static const Tables* fx = [] {
+      Tables* q = new Tables();
+      uint8_t l[288];
+      for (int i = 0; i < 144; i++) l[i] = 8;
+      for (int i = 144; i < 256; i++) l[i] = 9;
+      for (int i = 256; i < 280; i++) l[i] = 7;
+      for (int i = 280; i < 288; i++) l[i] = 8;
+      build_huff(q->lit, l, 288, 1);
+      uint8_t d[32];
+      for (int i = 0; i < 32; i++) d[i] = 5;
+      build_huff(q->dist, d, 32, 1);                    // codes 30, 31 decode but are rejected below
+      return q;
+    }();
+    t = fx;
+  }
+  while (true) {
+    if (b.over()) return -1;
+    if (out && !out->room(300)) return -2;
+    const int s = decode_sym(t->lit, b);
+    if (s < 0) return -1;
+    if (s < 256) { if (out) out->p[out->n++] = (uint16_t)s; ++*produced; continue; }
+    if (s == 256) return b.over() ? -1 : final;
+    if (s > 285) return -1;
+    const int len = LEN_BASE[s - 257] + (int)b.take(LEN_EXTRA[s - 257]);
+    const int ds = decode_sym(t->dist, b);
+    if (ds < 0 || ds > 29) return -1;
+    const int dist = DIST_BASE[ds] + (int)b.take(DIST_EXTRA[ds]);
+    if (out) {
+      uint16_t* p = out->p;
+      size_t n = out->n;
+      int i = 0;
+      for (; i < len && (int64_t)n - dist < 0; i++, n++) p[n] = (uint16_t)(MARK | (uint16_t)(32768 + ((int64_t)n - dist)));   // before the chunk: [-32768, -1]
+      if (i < len) {
+        const uint16_t* src = p + (n - (size_t)dist);
+        const int rest = len - i;
+        if (dist >= rest) memcpy(p + n, src, (size_t)rest * sizeof(uint16_t));
+        else for (int j = 0; j < rest; j++) p[n + j] = src[j];          // overlapping run
+        n += (size_t)rest;
+      }
+      out->n = n;
+    }
+    *produced += (size_t)len;
+  }
+}
+
+// First bit offset in [from, to) at which a non-final dynamic block starts whose header, body and following block header are valid.
+uint64_t find_block(const uint8_t* base, uint64_t nbits, uint64_t from, uint64_t to) {
+  Tables* t = new Tables();
+  uint64_t found = UINT64_MAX;
+  for (uint64_t p = from; p < to && p + 64 < nbits; p++) {
+    Bits b{base, p, nbits};
+    if (b.peek(3) != 4) continue;                      // BFINAL = 0, BTYPE = 2 (bits: 0, then 0 1)
+    const uint32_t hdr = b.peek(17);
+    if (((hdr >> 3) & 31) > 29 || ((hdr >> 8) & 31) > 29) continue;
+    b.pos += 3;
+    if (!read_dynamic_header(b, *t)) continue;
+    // the block must decode to its end, and another plausible block must follow
+    Bits body{base, p, nbits};
+    size_t produced = 0;
+    const int r = decode_block(body, nullptr, &produced, *t);
+    if (r != 0 || produced < 64) continue;
+    if (body.pos + 3 > nbits) continue;
+    Bits nxt = body;
+    size_t produced2 = 0;
+    const int r2 = decode_block(nxt, nullptr, &produced2, *t);
+    if (r2 < 0) continue;
+    found = p;
+    break;
+  }
+  delete t;
+  return found;
+}
+
+bool parse_gzip_header(const uint8_t* in, size_t n, size_t* data_off, bool* bgzf) {
+  if (n < 18 || in[0] != 0x1f || in[1] != 0x8b || in[2] != 8) return false;
+  const int flg = in[3];
+  size_t p = 10;
+  *bgzf = false;
+  if (flg & 4) {
+    if (p + 2 > n) return false;
+    const size_t xlen = in[p] | (in[p + 1] << 8);
+    for (size_t x = p + 2; x + 4 <= p + 2 + xlen && x + 4 <= n;) {
+      const size_t sl = in[x + 2] | (in[x + 3] << 8);
+      if (in[x] == 'B' && in[x + 1] == 'C' && sl == 2) *bgzf = true;
+      x += 4 + sl;
+    }
+    p += 2 + xlen;
+  }
+  if (flg & 8) { while (p < n && in[p]) p++; p++; }
+  if (flg & 16) { while (p < n && in[p]) p++; p++; }
+  if (flg & 2) p += 2;
+  if (p >= n) return false;
+  *data_off = p;
+  return true;
+}
+
+}  // namespace
+
+// ---- streaming interface: one wave of chunks per call ----------------------------------------------------------------
+struct PgzStream::Impl {
+  const uint8_t* base = nullptr; uint64_t nbits = 0;
+  uint32_t want_crc = 0, want_isize = 0;
+  size_t chunk_bytes = 0, nchunks = 0, next_chunk = 0;   // nominal chunks; next_chunk = first nominal chunk not yet searched
+  uint64_t cur_start = 0;                                // start (bits) of the first undecoded chunk
+  bool started = false, finished = false, failed = false;
+  std::vector<uint8_t> window = std::vector<uint8_t>(32768, 0);
+  size_t have_window = 0;
+  uint32_t crc = 0; uint64_t total = 0;
+  std::vector<SymBuf> sym;
+  double t_find = 0, t_dec = 0, t_res = 0; size_t chunks_done = 0;
+};
+
+namespace {
+// symbol buffers survive the stream: their pages are faulted in once per process, not once per file
+std::mutex g_pool_mu;
+std::vector<SymBuf> g_pool;
+}  // namespace
+
+PgzStream::PgzStream() : d(new Impl()) {}
+PgzStream::~PgzStream() {
+  if (!d->sym.empty()) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (auto& sb : d->sym) if (sb.p && g_pool.size() < 64) { g_pool.emplace_back(); std::swap(g_pool.back(), sb); }
+  }
+  delete d;
+}
+
+bool PgzStream::open(const unsigned char* in, size_t n, size_t chunk_bytes) {
+  size_t data_off = 0;
+  bool bgzf = false;
+  if (!parse_gzip_header(in, n, &data_off, &bgzf) || bgzf || n < data_off + 8 + 2) return false;
+  d->base = in + data_off;
+  d->nbits = 8ull * (n - 8 - data_off);
+  d->want_crc = in[n - 8] | (in[n - 7] << 8) | (in[n - 6] << 16) | ((uint32_t)in[n - 5] << 24);
+  d->want_isize = in[n - 4] | (in[n - 3] << 8) | (in[n - 2] << 16) | ((uint32_t)in[n - 1] << 24);
+  d->chunk_bytes = std::max<size_t>(chunk_bytes, 64u << 10);
+  d->nchunks = std::max<size_t>(1, (size_t)((d->nbits / 8 + d->chunk_bytes - 1) / d->chunk_bytes));
+  d->next_chunk = 1; d->cur_start = 0;
+  d->crc = (uint32_t)crc32(0L, Z_NULL, 0);
+  return true;
+}
+
+uint32_t PgzStream::isize_field() const { return d->want_isize; }
+uint64_t PgzStream::produced() const { return d->total; }
+
+// Decodes the next wave of chunks and appends its bytes at dst (room for `cap` bytes).  1 = more to come, 0 = stream finished and
+// verified against the trailer, -1 = failed (nothing written by this stream may be trusted), -2 = cap too small.
+int PgzStream::next(char* dst, size_t cap, size_t* wrote) {
+  Impl& S = *d;
+  *wrote = 0;
+  if (S.failed) return -1;
+  if (S.finished) return 0;
+  const int T = std::max(1, omp_get_max_threads());
+  const size_t want = S.started ? (size_t)T * 2 : (size_t)T;      // a short first wave: the consumer can start early
+  S.started = true;
+  const bool trace = getenv("CATT_TRACE") != nullptr;
+  double tt = omp_get_wtime();
+  // starts of this wave's chunks: cur_start, then the first block found in each following nominal chunk
+  std::vector<uint64_t> s{S.cur_start};
+  {
+    const size_t k0 = S.next_chunk, k1 = std::min(S.nchunks, k0 + want);
+    std::vector<uint64_t> f(k1 > k0 ? k1 - k0 : 0, UINT64_MAX);
+    #pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t k = (int64_t)k0; k < (int64_t)k1; k++)
+      f[k - k0] = find_block(S.base, S.nbits, std::max<uint64_t>(8ull * k * S.chunk_bytes, S.cur_start + 1), 8ull * (k + 1) * S.chunk_bytes);
+    for (uint64_t x : f) if (x != UINT64_MAX) s.push_back(x);
+    S.next_chunk = k1;
+    if (k1 == S.nchunks) s.push_back(S.nbits);           // the last wave runs to the end of the deflate data
+  }
+  const bool last_wave = S.next_chunk == S.nchunks;
+  // chunks of this wave: [s[i], s[i+1]); when it is not the last wave the final entry of s is the next wave's first start
+  const size_t m = s.size() - 1;
+  S.t_find += omp_get_wtime() - tt; tt = omp_get_wtime();
+  if (m == 0) return 1;                                  // no block start found in this stretch: the next wave continues from cur_start
+  if (S.sym.size() < m) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    while (S.sym.size() < m) {
+      S.sym.emplace_back();
+      if (!g_pool.empty()) { std::swap(S.sym.back(), g_pool.back()); g_pool.pop_back(); }
+    }
+  }
+  std::vector<char> good(m, 1), fin(m, 0);
+  #pragma omp parallel for schedule(dynamic, 1)
+  for (int64_t i = 0; i < (int64_t)m; i++) {
+    SymBuf& sb = S.sym[i];
+    sb.n = 0;
+    if (!sb.room(S.chunk_bytes * 5)) { good[i] = 0; continue; }
+    Tables* t = new Tables();
+    Bits b{S.base, s[i], S.nbits};
+    size_t produced = 0;
+    const uint64_t target = s[i + 1];
+    const bool last_chunk = last_wave && (size_t)i + 1 == m;
+    bool final_seen = false;
+    while (b.pos < target) {
+      const int r = decode_block(b, &sb, &produced, *t);
+      if (r < 0) { good[i] = 0; break; }
+      if (r == 1) { final_seen = true; break; }
+    }
+    delete t;
+    if (!good[i]) continue;
+    if (final_seen) {
+      // only the last chunk may end the stream, exactly at the trailer (after byte alignment)
+      if (!last_chunk || ((b.pos + 7) & ~7ull) != S.nbits) good[i] = 0;
+      fin[i] = 1;
+    } else if (b.pos != target || last_chunk) good[i] = 0;
+  }
+  bool ok = true, saw_final = false;
+  for (size_t i = 0; i < m; i++) { if (!good[i]) ok = false; if (fin[i]) saw_final = true; }
+  S.t_dec += omp_get_wtime() - tt; tt = omp_get_wtime();
+  if (!ok) { S.failed = true; return -1; }
+  // windows: sequential over the wave's chunks; win[i] = window BEFORE chunk i
+  std::vector<std::vector<uint8_t>> win(m);
+  std::vector<size_t> avail(m), off(m + 1, 0);
+  for (size_t i = 0; i < m; i++) {
+    win[i] = S.window; avail[i] = S.have_window;
+    const SymBuf& sb = S.sym[i];
+    off[i + 1] = off[i] + sb.n;
+    std::vector<uint8_t> nw(32768);                      // new window = last 32 KiB of (window + resolved chunk)
+    const size_t take = std::min<size_t>(sb.n, 32768);
+    for (size_t j = 0; j < take; j++) {
+      const uint16_t v = sb.p[sb.n - take + j];
+      if (v & MARK) { if ((size_t)(32768 - (v & 0x7FFF)) > S.have_window) ok = false; nw[32768 - take + j] = S.window[v & 0x7FFF]; }
+      else nw[32768 - take + j] = (uint8_t)v;
+    }
+    if (take < 32768) memcpy(nw.data(), S.window.data() + take, 32768 - take);
+    S.window.swap(nw);
+    S.have_window = std::min<size_t>(32768, S.have_window + sb.n);
+  }
+  if (!ok) { S.failed = true; return -1; }
+  if (off[m] > cap) { S.failed = true; return -2; }
+  std::vector<uint32_t> ccrc(m);
+  bool bad_marker = false;
+  #pragma omp parallel for schedule(dynamic, 1) reduction(|| : bad_marker)
+  for (int64_t i = 0; i < (int64_t)m; i++) {
+    const SymBuf& sb = S.sym[i];
+    const uint8_t* wv = win[i].data();
+    char* o = dst + off[i];
+    const size_t av = avail[i];
+    for (size_t j = 0; j < sb.n; j++) {
+      const uint16_t v = sb.p[j];
+      if (v & MARK) { if ((size_t)(32768 - (v & 0x7FFF)) > av) bad_marker = true; o[j] = (char)wv[v & 0x7FFF]; }
+      else o[j] = (char)v;
+    }
+    uint32_t c = (uint32_t)crc32(0L, Z_NULL, 0);          // zlib's crc32 takes uInt lengths: feed in slices
+    for (size_t q = 0; q < sb.n; q += (1u << 30)) c = (uint32_t)crc32(c, (const Bytef*)o + q, (uInt)std::min<size_t>(sb.n - q, 1u << 30));
+    ccrc[i] = c;
+  }
+  if (bad_marker) { S.failed = true; return -1; }
+  for (size_t i = 0; i < m; i++) { S.crc = (uint32_t)crc32_combine(S.crc, ccrc[i], (z_off_t)S.sym[i].n); S.total += S.sym[i].n; }
+  S.chunks_done += m;
+  S.cur_start = s[m];
+  *wrote = off[m];
+  S.t_res += omp_get_wtime() - tt;
+  if (!last_wave) return 1;
+  if (trace) fprintf(stderr, "[catt trace] pgz: %zu chunks, find %.1f ms, decode %.1f ms, resolve + crc %.1f ms\n", S.chunks_done, S.t_find * 1e3,
+                     S.t_dec * 1e3, S.t_res * 1e3);
+  if (!saw_final || S.crc != S.want_crc || (uint32_t)(S.total & 0xFFFFFFFFull) != S.want_isize) { S.failed = true; return -1; }
+  S.finished = true;
+  return 0;
+}
+
+// true: `out` holds the inflated bytes (appended); false: not handled (not gzip, BGZF, multi-member, or any check failed).
+// `in` must have 64 readable bytes behind in[n - 1] (the bit reader loads 8 bytes at a time and checks its position afterwards).
+bool pgz_inflate(const unsigned char* in, size_t n, std::string* out, size_t chunk_bytes) {
+  PgzStream st;
+  if (!st.open(in, n, chunk_bytes)) return false;
+  const size_t start_size = out->size();
+  if (st.isize_field() >= n) {                          // exact for members below 4 GiB; only a hint otherwise
+    out->reserve(start_size + st.isize_field());
+    advise_huge(out->data() + start_size, st.isize_field());
+  }
+  std::string wave_buf;
+  while (true) {
+    // a wave's output size is not known before it is decoded: give it generous room, then shrink to what it wrote
+    const size_t o0 = out->size();
+    size_t room = std::max<size_t>(64u << 20, (size_t)omp_get_max_threads() * 2 * chunk_bytes * 8);
+    int r; size_t wrote = 0;
+    while (true) {
+      out->resize(o0 + room);
+      r = st.next(&(*out)[o0], room, &wrote);
+      if (r != -2) break;
+      out->resize(start_size);
+      return false;                                      // (a wave larger than 8x its compressed size x2: leave it to zlib)
+    }
+    out->resize(o0 + wrote);
+    if (r < 0) { out->resize(start_size); return false; }
+    if (r == 0) return true;
+  }
+}
+
+}  // namespace catt
+
+namespace catt {
+
+bool read_raw_file(const char* path, std::vector<unsigned char>* buf, size_t* size) {
+  FILE* f = fopen(path, "rb");
+  if (!f) return false;
+  fseeko(f, 0, SEEK_END);
+  const int64_t sz = (int64_t)ftello(f);
+  fseeko(f, 0, SEEK_SET);
+  if (sz < 0) { fclose(f); return false; }
+  buf->assign((size_t)sz + 64, 0);                      // 64 bytes of slack for the bit readers
+  const size_t got = sz > 0 ? fread(buf->data(), 1, (size_t)sz, f) : 0;
+  fclose(f);
+  *size = (size_t)sz;
+  return (int64_t)got == sz;
+}
+
+namespace {
+inline uint32_t le32(const unsigned char* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+inline uint32_t le16(const unsigned char* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+struct Block { size_t cdata, clen, uoff; uint32_t ulen, crc; };
+}  // namespace
+
+// BGZF (SAMv1 4.1): a series of gzip members, each with a 'BC' extra subfield holding the member's total size - 1; the members
+// inflate independently, on all host threads.  Returns 1 = inflated (appended to out), 0 = not BGZF, < 0 = error (set_error called).
+int bgzf_inflate(const unsigned char* in, size_t n, std::string* out, const char* path) {
+  std::vector<Block> blocks;
+  size_t p = 0, total = 0;
+  while (p < n) {
+    if (n - p < 18 || in[p] != 0x1f || in[p + 1] != 0x8b || in[p + 2] != 8 || !(in[p + 3] & 4)) {
+      if (blocks.empty()) return 0;
+      set_error("%s: corrupt BGZF block header at byte %zu", path, p);
+      return CATT_E_IO;
+    }
+    const size_t xlen = le16(&in[p + 10]);
+    if (p + 12 + xlen > n) { set_error("%s: truncated BGZF block at byte %zu", path, p); return CATT_E_IO; }
+    size_t bsize = 0;
+    for (size_t x = p + 12; x + 4 <= p + 12 + xlen;) {
+      const size_t slen = le16(&in[x + 2]);
+      if (in[x] == 'B' && in[x + 1] == 'C' && slen == 2 && x + 6 <= p + 12 + xlen) bsize = le16(&in[x + 4]) + 1;
+      x += 4 + slen;
+    }
+    if (!bsize) {
+      if (blocks.empty()) return 0;
+      set_error("%s: gzip member without a BGZF size field at byte %zu", path, p);
+      return CATT_E_IO;
+    }
+    if (bsize < xlen + 20 || p + bsize > n) { set_error("%s: truncated BGZF block at byte %zu", path, p); return CATT_E_IO; }
+    Block b;
+    b.cdata = p + 12 + xlen; b.clen = bsize - xlen - 20;
+    b.crc = le32(&in[p + bsize - 8]); b.ulen = le32(&in[p + bsize - 4]);
+    b.uoff = total;
+    if (b.ulen > 65536) { set_error("%s: BGZF block larger than 64 KiB at byte %zu", path, p); return CATT_E_IO; }
+    total += b.ulen;
+    blocks.push_back(b);
+    p += bsize;
+  }
+  const size_t o0 = out->size();
+  out->resize(o0 + total);
+  unsigned char* dst = reinterpret_cast<unsigned char*>(&(*out)[0]) + o0;
+  int bad = -1;
+  #pragma omp parallel for schedule(dynamic, 16)
+  for (int64_t i = 0; i < (int64_t)blocks.size(); i++) {
+    const Block& b = blocks[i];
+    if (b.ulen == 0) continue;
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (inflateInit2(&zs, -15) != Z_OK) { bad = (int)i; continue; }
+    zs.next_in = const_cast<unsigned char*>(&in[b.cdata]); zs.avail_in = (uInt)b.clen;
+    zs.next_out = dst + b.uoff; zs.avail_out = b.ulen;
+    const int r = inflate(&zs, Z_FINISH);
+    inflateEnd(&zs);
+    if (r != Z_STREAM_END || zs.avail_out != 0 || crc32(crc32(0L, Z_NULL, 0), dst + b.uoff, b.ulen) != b.crc) bad = (int)i;
+  }
+  if (bad >= 0) { out->resize(o0); set_error("%s: BGZF block %d does not inflate / fails its CRC", path, bad); return CATT_E_IO; }
+  return 1;
+}
+
+// Whole file into memory: plain bytes, BGZF (parallel), single-member gzip (parallel, pgz_inflate) or anything else zlib reads.
+bool slurp_file(const std::string& path, std::string& out, int* method) {
+  int dummy;
+  if (!method) method = &dummy;
+  *method = 0;
+  out.clear();
+  std::vector<unsigned char> raw;
+  size_t n = 0;
+  if (!read_raw_file(path.c_str(), &raw, &n)) return false;
+  if (n < 2 || raw[0] != 0x1f || raw[1] != 0x8b) { out.assign(reinterpret_cast<const char*>(raw.data()), n); return true; }
+  if (!getenv("CATT_ZLIB_ONLY")) {
+    const int r = bgzf_inflate(raw.data(), n, &out, path.c_str());
+    if (r == 1) { *method = 1; return true; }
+    out.clear();
+    const char* cb = getenv("CATT_PGZ_CHUNK");                 // tests: small chunks on small files
+    const size_t chunk = cb ? (size_t)atol(cb) : (1u << 20);
+    if (r == 0 && (cb || n >= (1u << 20)) && pgz_inflate(raw.data(), n, &out, chunk)) { *method = 2; return true; }
+    out.clear();
+  }
+  std::vector<unsigned char>().swap(raw);
+  *method = 3;
+  gzFile f = gzopen(path.c_str(), "rb");                 // multi-member, tiny or unusual gzip files: one zlib stream
+  if (!f) return false;
+  gzbuffer(f, 1u << 20);
+  std::vector<char> buf(1u << 20);
+  int got;
+  while ((got = gzread(f, buf.data(), (unsigned)buf.size())) > 0) out.append(buf.data(), (size_t)got);
+  const bool ok = got == 0;
+  gzclose(f);
+  return ok;
+}
+
+}  // namespace catt

@@ -12,6 +12,7 @@
 
 #include <algorithm>
 
+#include "gz.h"
 #include "internal.cuh"
 
 namespace catt {
@@ -31,18 +32,6 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   return CATT_E_CUDA;
 }
 
-static bool slurp(const std::string& path, std::string& out) {
-  gzFile f = gzopen(path.c_str(), "rb");
-  if (!f) return false;
-  out.clear();
-  char buf[1 << 16];
-  int n;
-  while ((n = gzread(f, buf, sizeof buf)) > 0) out.append(buf, n);
-  gzclose(f);
-  return true;
-}
-bool slurp_file(const std::string& path, std::string& out) { return slurp(path, out); }
-
 // lrand48 as bwa's index builder calls it (srand48(11), one draw per reference N) when no .pac is at hand.
 struct Lrand48 {
   uint64_t x = ((uint64_t)11 << 16) | 0x330E;
@@ -51,7 +40,7 @@ struct Lrand48 {
 
 int RefSet::load(const std::string& fasta) {
   std::string txt;
-  if (!slurp(fasta, txt)) { set_error("cannot read reference FASTA %s", fasta.c_str()); return CATT_E_IO; }
+  if (!slurp_file(fasta, txt)) { set_error("cannot read reference FASTA %s", fasta.c_str()); return CATT_E_IO; }
   names.clear(); off.clear(); len.clear(); fa.clear(); T.clear(); L = 0; maxlen = 0;
   size_t p = 0;
   int cur = -1;
@@ -81,7 +70,7 @@ int RefSet::load(const std::string& fasta) {
   if (maxlen > MAX_REC_LEN) { set_error("%s: record of %d nt exceeds the limit of %d", fasta.c_str(), maxlen, MAX_REC_LEN); return CATT_E_LIMIT; }
   // alignment bases: N -> what the bwa index holds
   std::string pac;
-  bool have_pac = slurp(fasta + ".pac", pac) && (int)pac.size() >= (L + 3) / 4;
+  bool have_pac = slurp_file(fasta + ".pac", pac) && (int)pac.size() >= (L + 3) / 4;
   Lrand48 rng;
   T.resize(2 * (size_t)L);
   for (int i = 0; i < L; i++) {

@@ -129,6 +129,19 @@ class Batch:
             pass
 
 
+def bam_to_fastq(bam_path: str, fastq_path: str) -> None:
+    """The `samtools fastq -N in.bam > out.fastq` step of catt.jl:760 (BAM or SAM in, FASTQ out); needs no GPU."""
+    _lib.check(_lib.load().catt_bam_to_fastq(bam_path.encode(), fastq_path.encode()))
+
+
+def inflate_file(path: str, out_path: str) -> int:
+    """Write the bytes the library reads from a plain / BGZF / gzip input file; returns the method (0 plain, 1 BGZF in parallel,
+    2 parallel gzip, 3 one zlib stream).  Needs no GPU."""
+    m = C.c_int32(-1)
+    _lib.check(_lib.load().catt_inflate_file(path.encode(), out_path.encode(), C.byref(m)))
+    return m.value
+
+
 def set_host_threads(n: int = 0):
     """Host threads for read packing / result materialisation (0 = all hardware threads); one process per GPU -> cores // ranks."""
     _lib.check(_lib.load().catt_set_host_threads(n))
@@ -168,6 +181,12 @@ class Catt:
         """input_convert + read_alignrs + pool/extension for one single-end file (catt.jl:767-768 up to :577)."""
         h = C.c_void_p()
         _lib.check(_lib.load().catt_run_file(self._h, fastx_path.encode(), C.byref(h)))
+        return Result(self, h)
+
+    def mainflow_bam(self, bam_path: str) -> Result:
+        """--bam input (catt.jl:756-768): what `samtools fastq -N` would extract from a BAM / SAM file, through the single-end path."""
+        h = C.c_void_p()
+        _lib.check(_lib.load().catt_run_bam(self._h, bam_path.encode(), C.byref(h)))
         return Result(self, h)
 
     def mainflow_paired(self, *fastx_paths: str) -> Result:

@@ -154,6 +154,19 @@ int catt_run_files(catt_ctx* ctx, int32_t nfiles, const char* const* paths, catt
 int catt_run_reads_files(catt_ctx* ctx, int64_t n, const char* names, const int64_t* name_off, const char* seqs,
                          const int64_t* seq_off, const char* quals, int32_t nfiles, const int64_t* file_start, catt_result** out);
 
+/* `--bam` input (catt.jl:756-764: `samtools fastq -N in.bam > tmp.fastq`, then the single-end path): BAM (BGZF or uncompressed)
+ * or SAM text.  Secondary / supplementary records are dropped, reverse-strand records are restored to read orientation, "/1" "/2"
+ * are appended to READ1 / READ2 names, a missing quality string becomes 'B's - what `samtools fastq -N` writes - and the reads
+ * go through the same path as catt_run_reads without ever becoming FASTQ text. */
+int catt_run_bam(catt_ctx* ctx, const char* path, catt_result** out);
+/* The same conversion written out as FASTQ (needs no GPU and no context): a stand-in for the `samtools fastq -N` step itself. */
+int catt_bam_to_fastq(const char* bam_path, const char* fastq_path);
+/* How the library reads a (possibly compressed) input file, written back out: plain bytes (method 0), BGZF members inflated in
+ * parallel (1), a single-member gzip stream inflated in parallel by speculative block decoding, verified by its CRC-32 (2), or one
+ * zlib stream (3: multi-member or unusual files).  The reference reads .gz inputs through zlib inside bwa (kseq + gzread, one
+ * thread); this is the same bytes, faster.  Needs no GPU and no context; used by the tests and for timing. */
+int catt_inflate_file(const char* path, const char* out_path, int32_t* method);
+
 int catt_result_info(const catt_result* r, catt_info* out);
 /* Vpart (which=0) / Jpart (1) in the reference's list order, ready for catt.jl:579 onwards. */
 int catt_result_reads(const catt_result* r, int which, const catt_read** reads, int64_t* n);
