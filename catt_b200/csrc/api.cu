@@ -402,8 +402,34 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
   std::vector<std::string> gz((size_t)nfiles);
   std::vector<int64_t> size((size_t)nfiles, 0), tpos((size_t)nfiles + 1, 0);
   std::vector<char> isgz((size_t)nfiles, 0);
+  // single-member .gz files are inflated wave by wave straight into the pinned text (pgz.cu), so the first pieces cross PCIe and
+  // are aligned while the rest of the file is still being inflated; their size is the gzip trailer's ISIZE (verified at the end)
+  std::vector<std::vector<unsigned char>> raw((size_t)nfiles);
+  std::vector<std::unique_ptr<PgzStream>> pgz((size_t)nfiles);
   for (int f = 0; f < nfiles; f++) {
     bool g = false;
+    {
+      FILE* fp = fopen(paths[f], "rb");
+      unsigned char magic[2] = {0, 0};
+      if (!fp) { set_error("cannot read %s", paths[f]); return CATT_E_IO; }
+      g = fread(magic, 1, 2, fp) == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+      fclose(fp);
+    }
+    if (g && !getenv("CATT_ZLIB_ONLY")) {
+      size_t rn = 0;
+      if (!read_raw_file(paths[f], &raw[f], &rn)) { set_error("cannot read %s", paths[f]); return CATT_E_IO; }
+      const char* cb = getenv("CATT_PGZ_CHUNK");
+      std::unique_ptr<PgzStream> st(new PgzStream());
+      if ((cb || rn >= (1u << 20)) && st->open(raw[f].data(), rn, cb ? (size_t)atol(cb) : (1u << 20)) && st->isize_field() > 0 &&
+          (uint64_t)st->isize_field() * 2 >= rn) {
+        pgz[f] = std::move(st);
+        size[f] = (int64_t)pgz[f]->isize_field();
+        isgz[f] = 2;
+        tpos[f + 1] = (tpos[f] + size[f] + 16 + 15) & ~(int64_t)15;
+        continue;
+      }
+      std::vector<unsigned char>().swap(raw[f]);
+    }
     if (!read_whole(paths[f], &gz[f], &size[f], &g)) { set_error("cannot read %s", paths[f]); return CATT_E_IO; }
     isgz[f] = g;
     if (g) size[f] = (int64_t)gz[f].size();
@@ -447,11 +473,18 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
     for (int f = 0; f < nfiles; f++) {
       char* dst = h + tpos[f];
       int fd = -1;
-      if (isgz[f]) { memcpy(dst, gz[f].data(), (size_t)size[f]); std::string().swap(gz[f]); }
-      else if ((fd = open(paths[f], O_RDONLY)) < 0) { fail(CATT_E_IO, std::string("cannot read ") + paths[f], false); return; }
-      int64_t have = isgz[f] ? size[f] : 0, end = -1, p = 0;      // bytes of the file in memory; trimmed end once known; next piece start
+      if (isgz[f] == 1) { memcpy(dst, gz[f].data(), (size_t)size[f]); std::string().swap(gz[f]); }
+      else if (isgz[f] == 0 && (fd = open(paths[f], O_RDONLY)) < 0) { fail(CATT_E_IO, std::string("cannot read ") + paths[f], false); return; }
+      int64_t have = isgz[f] == 1 ? size[f] : 0, end = -1, p = 0;  // bytes of the file in memory; trimmed end once known; next piece start
       while (true) {
-        if (have < size[f]) {                                      // next block, all host threads
+        if (have < size[f] && isgz[f] == 2) {                      // next wave of the parallel inflate
+          size_t wrote = 0;
+          const int r = pgz[f]->next(dst + have, (size_t)(size[f] - have), &wrote);
+          have += (int64_t)wrote;
+          // a failed check anywhere in the stream: nothing it produced may be trusted - the host path (zlib) takes the whole sample
+          if (r < 0 || (r == 0 && have != size[f]) || (r == 1 && have == size[f])) { fail(CATT_OK, "", true); return; }
+          if (wrote == 0) continue;
+        } else if (have < size[f]) {                               // next block, all host threads
           const int64_t blk = std::min<int64_t>(size[f] - have, 32 << 20), sub = 4 << 20, ns = (blk + sub - 1) / sub;
           bool ok = true;
           #pragma omp parallel for schedule(dynamic, 1) reduction(&& : ok)

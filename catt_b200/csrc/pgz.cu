@@ -21,6 +21,9 @@
 #include <string.h>
 #include <sys/mman.h>
 #include <zlib.h>
+#ifdef __SSE2__
+#include <emmintrin.h>
+#endif
 
 #include <algorithm>
 #include <mutex>
@@ -208,21 +211,56 @@ int decode_block(Bits& b, SymBuf* out, size_t* produced, Tables& scratch) {
     }();
     t = fx;
   }
-  while (true) {
-    if (b.over()) return -1;
-    if (out && !out->room(300)) return -2;
-    const int s = decode_sym(t->lit, b);
-    if (s < 0) return -1;
-    if (s < 256) { if (out) out->p[out->n++] = (uint16_t)s; ++*produced; continue; }
-    if (s == 256) return b.over() ? -1 : final;
-    if (s > 285) return -1;
-    const int len = LEN_BASE[s - 257] + (int)b.take(LEN_EXTRA[s - 257]);
-    const int ds = decode_sym(t->dist, b);
-    if (ds < 0 || ds > 29) return -1;
-    const int dist = DIST_BASE[ds] + (int)b.take(DIST_EXTRA[ds]);
-    if (out) {
-      uint16_t* p = out->p;
+  if (out) {
+    // Hot loop with everything in locals: one 8-byte load serves a literal and, when the next code is a literal too, that one as well.
+    const uint8_t* const base = b.base;
+    const uint64_t nbits = b.nbits;
+    uint64_t pos = b.pos;
+    const uint16_t* const lfast = t->lit.fast;
+    constexpr uint64_t FM = (1u << FAST_BITS) - 1;
+    while (true) {
+      if (pos > nbits) return -1;
+      if (out->n + 600 > out->cap && !out->room(600)) return -2;
+      uint16_t* const p = out->p;
       size_t n = out->n;
+      const size_t stop = out->cap - 300;
+      int s;
+      while (true) {                                       // literal run
+        uint64_t w;
+        memcpy(&w, base + (pos >> 3), 8);
+        w >>= (pos & 7);
+        uint32_t e = lfast[w & FM];
+        if (e && e < (256u << 4)) {
+          p[n++] = (uint16_t)(e >> 4); pos += e & 15; w >>= (e & 15);
+          e = lfast[w & FM];
+          if (e && e < (256u << 4)) {
+            p[n++] = (uint16_t)(e >> 4); pos += e & 15; w >>= (e & 15);
+            e = lfast[w & FM];
+            if (e && e < (256u << 4)) { p[n++] = (uint16_t)(e >> 4); pos += e & 15; }
+          }
+          if (n < stop && pos <= nbits) continue;
+          s = -2;                                          // out of room or input: back to the outer checks
+          break;
+        }
+        if (e) { s = (int)(e >> 4); pos += e & 15; break; }
+        b.pos = pos;
+        s = decode_sym(t->lit, b);                         // long code
+        pos = b.pos;
+        break;
+      }
+      out->n = n;
+      if (s == -2) continue;
+      if (s < 0) return -1;
+      if (s < 256) { p[out->n++] = (uint16_t)s; continue; }
+      if (s == 256) { b.pos = pos; *produced = out->n; return pos > nbits ? -1 : final; }
+      if (s > 285) return -1;
+      b.pos = pos;
+      const int len = LEN_BASE[s - 257] + (int)b.take(LEN_EXTRA[s - 257]);
+      const int ds = decode_sym(t->dist, b);
+      if (ds < 0 || ds > 29) return -1;
+      const int dist = DIST_BASE[ds] + (int)b.take(DIST_EXTRA[ds]);
+      pos = b.pos;
+      n = out->n;
       int i = 0;
       for (; i < len && (int64_t)n - dist < 0; i++, n++) p[n] = (uint16_t)(MARK | (uint16_t)(32768 + ((int64_t)n - dist)));   // before the chunk: [-32768, -1]
       if (i < len) {
@@ -234,6 +272,18 @@ int decode_block(Bits& b, SymBuf* out, size_t* produced, Tables& scratch) {
       }
       out->n = n;
     }
+  }
+  while (true) {                                           // validation only (the finder): no output
+    if (b.over()) return -1;
+    const int s = decode_sym(t->lit, b);
+    if (s < 0) return -1;
+    if (s < 256) { ++*produced; continue; }
+    if (s == 256) return b.over() ? -1 : final;
+    if (s > 285) return -1;
+    const int len = LEN_BASE[s - 257] + (int)b.take(LEN_EXTRA[s - 257]);
+    const int ds = decode_sym(t->dist, b);
+    if (ds < 0 || ds > 29) return -1;
+    b.pos += DIST_EXTRA[ds];
     *produced += (size_t)len;
   }
 }
@@ -431,7 +481,22 @@ int PgzStream::next(char* dst, size_t cap, size_t* wrote) {
     const uint8_t* wv = win[i].data();
     char* o = dst + off[i];
     const size_t av = avail[i];
-    for (size_t j = 0; j < sb.n; j++) {
+    size_t j = 0;
+#ifdef __SSE2__
+    for (; j + 16 <= sb.n; j += 16) {                      // 16 symbols at a time; markers are rare after the first 32 KiB of a chunk
+      const __m128i a = _mm_loadu_si128((const __m128i*)(sb.p + j)), b2 = _mm_loadu_si128((const __m128i*)(sb.p + j + 8));
+      if (_mm_movemask_epi8(_mm_or_si128(a, b2)) & 0xAAAA) {
+        for (size_t q = j; q < j + 16; q++) {
+          const uint16_t v = sb.p[q];
+          if (v & MARK) { if ((size_t)(32768 - (v & 0x7FFF)) > av) bad_marker = true; o[q] = (char)wv[v & 0x7FFF]; }
+          else o[q] = (char)v;
+        }
+      } else {
+        _mm_storeu_si128((__m128i*)(o + j), _mm_packus_epi16(a, b2));
+      }
+    }
+#endif
+    for (; j < sb.n; j++) {
       const uint16_t v = sb.p[j];
       if (v & MARK) { if ((size_t)(32768 - (v & 0x7FFF)) > av) bad_marker = true; o[j] = (char)wv[v & 0x7FFF]; }
       else o[j] = (char)v;
