@@ -396,7 +396,7 @@ bool read_whole(const char* path, std::string* gz_out, int64_t* plain_size, bool
   return true;
 }
 
-int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_result** out, bool* handled) {
+int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_result** out, bool* handled, bool bam = false) {
   *handled = false;
   Trace tr;
   std::vector<std::string> gz((size_t)nfiles);
@@ -406,6 +406,9 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
   // are aligned while the rest of the file is still being inflated; their size is the gzip trailer's ISIZE (verified at the end)
   std::vector<std::vector<unsigned char>> raw((size_t)nfiles);
   std::vector<std::unique_ptr<PgzStream>> pgz((size_t)nfiles);
+  std::vector<std::unique_ptr<BgzfStream>> bgzf((size_t)nfiles);
+  std::vector<std::unique_ptr<BamTextStream>> bamtx((size_t)nfiles);
+  std::vector<std::function<int(char*, size_t, size_t*)>> src((size_t)nfiles);      // streamed sources: next(dst, cap, &wrote)
   for (int f = 0; f < nfiles; f++) {
     bool g = false;
     {
@@ -415,15 +418,37 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
       g = fread(magic, 1, 2, fp) == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
       fclose(fp);
     }
+    if (bam && !g) return CATT_OK;                                   // SAM text / uncompressed BAM: the host decoder (bam.cu)
     if (g && !getenv("CATT_ZLIB_ONLY")) {
       size_t rn = 0;
       if (!read_raw_file(paths[f], &raw[f], &rn)) { set_error("cannot read %s", paths[f]); return CATT_E_IO; }
-      const char* cb = getenv("CATT_PGZ_CHUNK");
-      std::unique_ptr<PgzStream> st(new PgzStream());
-      if ((cb || rn >= (1u << 20)) && st->open(raw[f].data(), rn, cb ? (size_t)atol(cb) : (1u << 20)) && st->isize_field() > 0 &&
-          (uint64_t)st->isize_field() * 2 >= rn) {
-        pgz[f] = std::move(st);
-        size[f] = (int64_t)pgz[f]->isize_field();
+      int64_t bound = -1;
+      if (bam) {                                                     // BGZF BAM -> FASTQ text, group by group (bam.cu)
+        std::unique_ptr<BamTextStream> bt(new BamTextStream());
+        if (!bt->open(raw[f].data(), rn)) return CATT_OK;            // gzipped SAM, damaged chain: the host decoder reports it
+        bound = (int64_t)bt->text_bound();
+        bamtx[f] = std::move(bt);
+        BamTextStream* q = bamtx[f].get();
+        src[f] = [q](char* d, size_t cap, size_t* w) { return q->next(d, cap, w); };
+      } else {
+        const char* cb = getenv("CATT_PGZ_CHUNK");
+        std::unique_ptr<PgzStream> st(new PgzStream());
+        std::unique_ptr<BgzfStream> bs(new BgzfStream());
+        if ((cb || rn >= (1u << 20)) && st->open(raw[f].data(), rn, cb ? (size_t)atol(cb) : (1u << 20)) && st->isize_field() > 0 &&
+            (uint64_t)st->isize_field() * 2 >= rn) {
+          bound = (int64_t)st->isize_field();                        // the trailer's ISIZE; the stream verifies it at the end
+          pgz[f] = std::move(st);
+          PgzStream* q = pgz[f].get();
+          src[f] = [q](char* d, size_t cap, size_t* w) { return q->next(d, cap, w); };
+        } else if (bs->open(raw[f].data(), rn) && bs->total() > 0) { // bgzip'd FASTQ: independent members, exact size known
+          bound = (int64_t)bs->total();
+          bgzf[f] = std::move(bs);
+          BgzfStream* q = bgzf[f].get();
+          src[f] = [q](char* d, size_t cap, size_t* w) { return q->next(d, cap, w); };
+        }
+      }
+      if (bound >= 0) {
+        size[f] = bound;
         isgz[f] = 2;
         tpos[f + 1] = (tpos[f] + size[f] + 16 + 15) & ~(int64_t)15;
         continue;
@@ -479,11 +504,13 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
       while (true) {
         if (have < size[f] && isgz[f] == 2) {                      // next wave of the parallel inflate
           size_t wrote = 0;
-          const int r = pgz[f]->next(dst + have, (size_t)(size[f] - have), &wrote);
+          const int r = src[f](dst + have, (size_t)(size[f] - have), &wrote);
           have += (int64_t)wrote;
-          // a failed check anywhere in the stream: nothing it produced may be trusted - the host path (zlib) takes the whole sample
-          if (r < 0 || (r == 0 && have != size[f]) || (r == 1 && have == size[f])) { fail(CATT_OK, "", true); return; }
-          if (wrote == 0) continue;
+          // a failed check anywhere in the stream (or a size bound that does not hold): nothing it produced may be trusted - the
+          // host path (zlib / the host BAM decoder) takes the whole sample
+          if (r < 0) { fail(CATT_OK, "", true); return; }
+          if (r == 0) size[f] = have;                                // the source is exhausted: now the size is exact
+          else if (wrote == 0) continue;
         } else if (have < size[f]) {                               // next block, all host threads
           const int64_t blk = std::min<int64_t>(size[f] - have, 32 << 20), sub = 4 << 20, ns = (blk + sub - 1) / sub;
           bool ok = true;
@@ -818,6 +845,12 @@ int catt_run_files(catt_ctx* c, int32_t nfiles, const char* const* paths, catt_r
 int catt_run_bam(catt_ctx* c, const char* path, catt_result** out) {
   if (!c || !path || !out) { set_error("catt_run_bam: null argument"); return CATT_E_ARG; }
   CATT_CUDA(cudaSetDevice(c->device));
+  if (!getenv("CATT_HOST_PARSE")) {                      // BGZF BAM: converted to FASTQ text group by group under the GPU pipeline
+    bool handled = false;
+    const char* paths[1] = {path};
+    int rc = run_files_device(c, 1, paths, out, &handled, true);
+    if (rc || handled) return rc;
+  }
   HostReads hr;
   Trace tr;
   int rc = parse_bam(path, &hr);

@@ -156,6 +156,98 @@ int parse_sam_bytes(const unsigned char* d, size_t N, const char* path, HostRead
 
 }  // namespace
 
+}  // namespace catt (reopened below)
+
+namespace catt {
+
+bool BamTextStream::open(const unsigned char* in, size_t n) {
+  buf_.clear(); pending_ = 0; header_done_ = false; eof_ = false;
+  return bz_.open(in, n) && bz_.total() >= 12;
+}
+
+int BamTextStream::next(char* dst, size_t cap, size_t* wrote) {
+  *wrote = 0;
+  if (eof_) return 0;
+  // inflate the next group of blocks behind the bytes left over from the previous call
+  const size_t group_bound = (size_t)std::max(1, omp_get_max_threads()) * 48 * 65536;
+  if (buf_.size() < pending_ + group_bound) buf_.resize(pending_ + group_bound);
+  size_t got = 0;
+  const int r = bz_.next(reinterpret_cast<char*>(buf_.data()) + pending_, buf_.size() - pending_, &got);
+  if (r < 0) return -1;
+  const bool last = r == 0;
+  const size_t N = pending_ + got;
+  const unsigned char* d = buf_.data();
+  size_t p = 0;
+  if (!header_done_) {
+    if (N < 12) { if (last) return -1; pending_ = N; return 1; }
+    if (memcmp(d, "BAM\1", 4) != 0) return -1;
+    size_t q = 8 + (size_t)le32(d + 4);
+    bool complete = q + 4 <= N;
+    if (complete) {
+      const uint32_t n_ref = le32(d + q);
+      q += 4;
+      for (uint32_t i = 0; i < n_ref && complete; i++) {
+        if (q + 4 > N) { complete = false; break; }
+        q += 4 + (size_t)le32(d + q) + 4;
+        if (q > N) complete = false;
+      }
+    }
+    if (!complete) { if (last) return -1; pending_ = N; return 1; }     // a header longer than one group: wait for more
+    header_done_ = true;
+    p = q;
+  }
+  // complete records of this stretch
+  std::vector<Rec> recs;
+  std::vector<size_t> off{0};
+  while (p + 4 <= N) {
+    const size_t bs = le32(d + p);
+    if (bs < 32) return -1;
+    if (p + 4 + bs > N) break;
+    const unsigned char* rr = d + p + 4;
+    const uint32_t l_read_name = rr[8], n_cigar = le16(rr + 12), flag = le16(rr + 14), l_seq = le32(rr + 16);
+    const size_t need = 32 + (size_t)l_read_name + 4 * (size_t)n_cigar + ((size_t)l_seq + 1) / 2 + l_seq;
+    if (need > bs || l_read_name == 0) return -1;
+    if (!(flag & 0x900)) {
+      Rec x;
+      x.name = p + 4 + 32; x.lname = l_read_name - 1;
+      x.seq = x.name + l_read_name + 4 * (size_t)n_cigar; x.qual = x.seq + ((size_t)l_seq + 1) / 2;
+      x.lseq = l_seq; x.flag = (uint16_t)flag;
+      recs.push_back(x);
+      off.push_back(off.back() + 1 + x.lname + (suffix_of(x.flag) ? 2 : 0) + 1 + 2 * (size_t)l_seq + 4);
+    }
+    p += 4 + bs;
+  }
+  if (last && p != N) return -1;                           // a truncated record at the end of the file
+  if (off.back() > cap) return -2;
+  #pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < (int64_t)recs.size(); i++) {
+    const Rec& x = recs[i];
+    char* o = dst + off[i];
+    *o++ = '@';
+    memcpy(o, d + x.name, x.lname); o += x.lname;
+    if (const int sfx = suffix_of(x.flag)) { *o++ = '/'; *o++ = (char)('0' + sfx); }
+    *o++ = '\n';
+    char* s = o;
+    char* q = o + x.lseq + 3;
+    const bool rev = x.flag & 0x10;
+    const bool noq = x.lseq && d[x.qual] == 0xff;
+    for (uint32_t k = 0; k < x.lseq; k++) {
+      const uint32_t src = rev ? x.lseq - 1 - k : k;
+      const unsigned char c = d[x.seq + (src >> 1)];
+      const unsigned code = (src & 1) ? (c & 15) : (c >> 4);
+      s[k] = NT16[rev ? COMP16[code] : code];
+      q[k] = noq ? 'B' : (char)(d[x.qual + src] + 33);
+    }
+    s[x.lseq] = '\n'; s[x.lseq + 1] = '+'; s[x.lseq + 2] = '\n';
+    q[x.lseq] = '\n';
+  }
+  *wrote = off.back();
+  pending_ = N - p;
+  if (pending_) memmove(buf_.data(), buf_.data() + p, pending_);
+  if (last) { eof_ = true; return 0; }
+  return 1;
+}
+
 // BAM (BGZF or uncompressed) or SAM text (plain or gzipped) -> the reads `samtools fastq -N` would write, appended to hr.
 int parse_bam(const char* path, HostReads* hr) {
   std::vector<unsigned char> raw;

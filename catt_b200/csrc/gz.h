@@ -31,6 +31,32 @@ class PgzStream {
  private:
   Impl* d;
 };
+// BGZF members (bgzip, BAM) group by group; the total size is known from the block trailers before anything is inflated.
+class BgzfStream {
+ public:
+  bool open(const unsigned char* in, size_t n);                            // false = not BGZF / damaged block chain
+  uint64_t total() const { return total_; }
+  int next(char* dst, size_t cap, size_t* wrote);                          // 1 more, 0 done, -1 a block fails to inflate / its CRC, -2 cap
+ private:
+  struct Block { size_t cdata, clen, uoff; uint32_t ulen, crc; };
+  const unsigned char* in_ = nullptr;
+  std::vector<Block> blocks_;
+  size_t next_ = 0;
+  uint64_t total_ = 0;
+};
+// A BGZF-compressed BAM as the FASTQ text `samtools fastq -N` would write (bam.cu), group by group: the file pipeline indexes and
+// packs that text on the GPU like any FASTQ, so the conversion overlaps the alignment.  text_bound() >= the bytes it will write.
+class BamTextStream {
+ public:
+  bool open(const unsigned char* in, size_t n);                            // false = not a BGZF file
+  uint64_t text_bound() const { return bz_.total() / 3 * 4 + 4096; }       // 2L+ln+8 FASTQ bytes <= 4/3 of (1.5L+ln+37) BAM bytes
+  int next(char* dst, size_t cap, size_t* wrote);                          // 1 more, 0 done, -1 malformed, -2 cap
+ private:
+  BgzfStream bz_;
+  std::vector<unsigned char> buf_;                                         // inflated bytes not consumed yet (a partial record)
+  size_t pending_ = 0;
+  bool header_done_ = false, eof_ = false;
+};
 // plain / BGZF / gzip file into memory; *method = 0 plain bytes, 1 BGZF members in parallel, 2 parallel gzip, 3 one zlib stream
 bool slurp_file(const std::string& path, std::string& out, int* method = nullptr);
 }  // namespace catt

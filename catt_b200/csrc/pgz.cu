@@ -36,7 +36,7 @@
 namespace catt {
 namespace {
 
-constexpr int FAST_BITS = 11;
+constexpr int FAST_BITS = 10;
 constexpr uint16_t MARK = 0x8000;
 
 const uint16_t LEN_BASE[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
@@ -55,14 +55,15 @@ struct Bits {
 };
 
 struct Huff {
-  uint16_t fast[1 << FAST_BITS];          // (symbol << 4) | length, 0 = longer than FAST_BITS (or unused)
+  uint16_t fast[1 << FAST_BITS];          // (symbol << 4) | length, 0 = longer than `fb` bits (or unused); the first 2^fb entries are used
   uint16_t count[16], symbol[288];
-  int maxlen;
+  int maxlen, fb;                         // fb: index width of `fast` for this table (small tables are cheaper to build per block)
 };
 
 // zlib's rule (inftrees.c): over-subscribed sets are invalid; an incomplete set is invalid for the code-length code (kind 0) and,
 // for the literal/length and distance codes (kind 1), unless it is a single code of length 1 (or, distance only, no code at all)
-bool build_huff(Huff& h, const uint8_t* lens, int n, int kind) {
+bool build_huff(Huff& h, const uint8_t* lens, int n, int kind, int fb = FAST_BITS) {
+  h.fb = fb;
   memset(h.count, 0, sizeof h.count);
   for (int i = 0; i < n; i++) h.count[lens[i]]++;
   h.count[0] = 0;
@@ -79,14 +80,14 @@ bool build_huff(Huff& h, const uint8_t* lens, int n, int kind) {
   offs[1] = 0;
   for (int l = 1; l < 15; l++) offs[l + 1] = offs[l] + h.count[l];
   for (int i = 0; i < n; i++) if (lens[i]) h.symbol[offs[lens[i]]++] = (uint16_t)i;
-  memset(h.fast, 0, sizeof h.fast);
+  memset(h.fast, 0, sizeof(uint16_t) << fb);
   int code = 0, idx = 0;
-  for (int l = 1; l <= std::min(15, FAST_BITS); l++) {
+  for (int l = 1; l <= std::min(15, fb); l++) {
     for (int k = 0; k < h.count[l]; k++, code++, idx++) {
       uint32_t rev = 0;
       for (int b = 0; b < l; b++) rev |= ((code >> b) & 1u) << (l - 1 - b);
       const uint16_t e = (uint16_t)((h.symbol[idx] << 4) | l);
-      for (uint32_t x = rev; x < (1u << FAST_BITS); x += 1u << l) h.fast[x] = e;
+      for (uint32_t x = rev; x < (1u << fb); x += 1u << l) h.fast[x] = e;
     }
     code <<= 1;
   }
@@ -95,7 +96,7 @@ bool build_huff(Huff& h, const uint8_t* lens, int n, int kind) {
 
 inline int decode_sym(const Huff& h, Bits& b) {
   const uint64_t w = b.window();
-  const uint16_t e = h.fast[w & ((1u << FAST_BITS) - 1)];
+  const uint16_t e = h.fast[w & ((1u << h.fb) - 1)];
   if (e) { b.pos += e & 15; return e >> 4; }
   int code = 0, first = 0, index = 0;                 // canonical walk (codes longer than FAST_BITS are rare)
   for (int l = 1; l <= h.maxlen; l++) {
@@ -152,7 +153,7 @@ bool read_dynamic_header(Bits& b, Tables& t) {
   uint8_t cl[19] = {0};
   for (int i = 0; i < hclen; i++) cl[CL_ORDER[i]] = (uint8_t)b.take(3);
   Huff& clh = t.dist;                                  // scratch: rebuilt below
-  if (!build_huff(clh, cl, 19, 0)) return false;
+  if (!build_huff(clh, cl, 19, 0, 7)) return false;
   uint8_t lens[286 + 30 + 138];
   int i = 0;
   while (i < hlit + hdist) {
@@ -168,8 +169,8 @@ bool read_dynamic_header(Bits& b, Tables& t) {
     while (rep--) lens[i++] = (uint8_t)val;
   }
   if (lens[256] == 0) return false;                    // no end-of-block code
-  if (!build_huff(t.lit, lens, hlit, 1)) return false;
-  return build_huff(t.dist, lens + hlit, hdist, 1);
+  if (!build_huff(t.lit, lens, hlit, 1, FAST_BITS)) return false;
+  return build_huff(t.dist, lens + hlit, hdist, 1, 8);
 }
 
 // One deflate block at b, symbols appended to out (nullptr = validate only).  Returns 0 ok, 1 ok and it was the final block, < 0 error.
@@ -569,61 +570,91 @@ bool read_raw_file(const char* path, std::vector<unsigned char>* buf, size_t* si
 namespace {
 inline uint32_t le32(const unsigned char* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 inline uint32_t le16(const unsigned char* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
-struct Block { size_t cdata, clen, uoff; uint32_t ulen, crc; };
 }  // namespace
 
 // BGZF (SAMv1 4.1): a series of gzip members, each with a 'BC' extra subfield holding the member's total size - 1; the members
-// inflate independently, on all host threads.  Returns 1 = inflated (appended to out), 0 = not BGZF, < 0 = error (set_error called).
-int bgzf_inflate(const unsigned char* in, size_t n, std::string* out, const char* path) {
-  std::vector<Block> blocks;
-  size_t p = 0, total = 0;
+// inflate independently, on all host threads.
+bool BgzfStream::open(const unsigned char* in, size_t n) {
+  in_ = in; blocks_.clear(); next_ = 0; total_ = 0;
+  size_t p = 0;
   while (p < n) {
-    if (n - p < 18 || in[p] != 0x1f || in[p + 1] != 0x8b || in[p + 2] != 8 || !(in[p + 3] & 4)) {
-      if (blocks.empty()) return 0;
-      set_error("%s: corrupt BGZF block header at byte %zu", path, p);
-      return CATT_E_IO;
-    }
+    if (n - p < 18 || in[p] != 0x1f || in[p + 1] != 0x8b || in[p + 2] != 8 || !(in[p + 3] & 4)) return false;
     const size_t xlen = le16(&in[p + 10]);
-    if (p + 12 + xlen > n) { set_error("%s: truncated BGZF block at byte %zu", path, p); return CATT_E_IO; }
+    if (p + 12 + xlen > n) return false;
     size_t bsize = 0;
     for (size_t x = p + 12; x + 4 <= p + 12 + xlen;) {
       const size_t slen = le16(&in[x + 2]);
       if (in[x] == 'B' && in[x + 1] == 'C' && slen == 2 && x + 6 <= p + 12 + xlen) bsize = le16(&in[x + 4]) + 1;
       x += 4 + slen;
     }
-    if (!bsize) {
-      if (blocks.empty()) return 0;
-      set_error("%s: gzip member without a BGZF size field at byte %zu", path, p);
-      return CATT_E_IO;
-    }
-    if (bsize < xlen + 20 || p + bsize > n) { set_error("%s: truncated BGZF block at byte %zu", path, p); return CATT_E_IO; }
+    if (!bsize || bsize < xlen + 20 || p + bsize > n) return false;
     Block b;
     b.cdata = p + 12 + xlen; b.clen = bsize - xlen - 20;
     b.crc = le32(&in[p + bsize - 8]); b.ulen = le32(&in[p + bsize - 4]);
-    b.uoff = total;
-    if (b.ulen > 65536) { set_error("%s: BGZF block larger than 64 KiB at byte %zu", path, p); return CATT_E_IO; }
-    total += b.ulen;
-    blocks.push_back(b);
+    b.uoff = total_;
+    if (b.ulen > 65536) return false;
+    total_ += b.ulen;
+    blocks_.push_back(b);
     p += bsize;
   }
-  const size_t o0 = out->size();
-  out->resize(o0 + total);
-  unsigned char* dst = reinterpret_cast<unsigned char*>(&(*out)[0]) + o0;
-  int bad = -1;
-  #pragma omp parallel for schedule(dynamic, 16)
-  for (int64_t i = 0; i < (int64_t)blocks.size(); i++) {
-    const Block& b = blocks[i];
+  return !blocks_.empty();
+}
+
+int BgzfStream::next(char* dst, size_t cap, size_t* wrote) {
+  *wrote = 0;
+  if (next_ >= blocks_.size()) return 0;
+  const size_t group = (size_t)std::max(1, omp_get_max_threads()) * 48;         // ~3 MiB of text per thread and call
+  const size_t b0 = next_, b1 = std::min(blocks_.size(), b0 + group);
+  const uint64_t o0 = blocks_[b0].uoff, o1 = b1 < blocks_.size() ? blocks_[b1].uoff : total_;
+  if (o1 - o0 > cap) return -2;
+  bool bad = false;
+  #pragma omp parallel for schedule(dynamic, 4) reduction(|| : bad)
+  for (int64_t i = (int64_t)b0; i < (int64_t)b1; i++) {
+    const Block& b = blocks_[i];
     if (b.ulen == 0) continue;
+    unsigned char* o = reinterpret_cast<unsigned char*>(dst) + (b.uoff - o0);
     z_stream zs;
     memset(&zs, 0, sizeof zs);
-    if (inflateInit2(&zs, -15) != Z_OK) { bad = (int)i; continue; }
-    zs.next_in = const_cast<unsigned char*>(&in[b.cdata]); zs.avail_in = (uInt)b.clen;
-    zs.next_out = dst + b.uoff; zs.avail_out = b.ulen;
+    if (inflateInit2(&zs, -15) != Z_OK) { bad = true; continue; }
+    zs.next_in = const_cast<unsigned char*>(&in_[b.cdata]); zs.avail_in = (uInt)b.clen;
+    zs.next_out = o; zs.avail_out = b.ulen;
     const int r = inflate(&zs, Z_FINISH);
     inflateEnd(&zs);
-    if (r != Z_STREAM_END || zs.avail_out != 0 || crc32(crc32(0L, Z_NULL, 0), dst + b.uoff, b.ulen) != b.crc) bad = (int)i;
+    if (r != Z_STREAM_END || zs.avail_out != 0 || crc32(crc32(0L, Z_NULL, 0), o, b.ulen) != b.crc) bad = true;
   }
-  if (bad >= 0) { out->resize(o0); set_error("%s: BGZF block %d does not inflate / fails its CRC", path, bad); return CATT_E_IO; }
+  if (bad) return -1;
+  next_ = b1;
+  *wrote = (size_t)(o1 - o0);
+  return b1 < blocks_.size() && o1 < total_ ? 1 : 0;       // trailing empty members (the EOF marker) hold nothing to check
+}
+
+// 1 = inflated and appended to out, 0 = not BGZF, < 0 = error (set_error called)
+int bgzf_inflate(const unsigned char* in, size_t n, std::string* out, const char* path) {
+  if (n < 18 || in[0] != 0x1f || in[1] != 0x8b || !(in[3] & 4)) return 0;
+  BgzfStream st;
+  if (!st.open(in, n)) {
+    // distinguish "an ordinary gzip file" from "BGZF with a damaged block chain": the first member decides
+    const size_t xlen = le16(&in[10]);
+    bool first_is_bgzf = false;
+    for (size_t x = 12; x + 4 <= 12 + xlen && x + 4 <= n;) {
+      const size_t slen = le16(&in[x + 2]);
+      if (in[x] == 'B' && in[x + 1] == 'C' && slen == 2) first_is_bgzf = true;
+      x += 4 + slen;
+    }
+    if (!first_is_bgzf) return 0;
+    set_error("%s: corrupt or truncated BGZF block chain", path);
+    return CATT_E_IO;
+  }
+  const size_t o0 = out->size();
+  out->resize(o0 + st.total());
+  size_t have = 0;
+  while (true) {
+    size_t wrote = 0;
+    const int r = st.next(&(*out)[o0 + have], (size_t)st.total() - have, &wrote);
+    have += wrote;
+    if (r < 0) { out->resize(o0); set_error("%s: a BGZF block does not inflate / fails its CRC", path); return CATT_E_IO; }
+    if (r == 0) break;
+  }
   return 1;
 }
 
