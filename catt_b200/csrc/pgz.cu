@@ -19,7 +19,10 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <fcntl.h>
 #include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 #ifdef __SSE2__
 #include <emmintrin.h>
@@ -123,25 +126,30 @@ void advise_huge(const void* p, size_t bytes) {
   if (e > a) madvise((void*)a, e - a, MADV_HUGEPAGE);
 }
 
-struct SymBuf {
-  uint16_t* p = nullptr; size_t n = 0, cap = 0;
-  SymBuf() = default;
-  SymBuf(const SymBuf&) = delete;
-  SymBuf& operator=(const SymBuf&) = delete;
-  SymBuf(SymBuf&& o) noexcept : p(o.p), n(o.n), cap(o.cap) { o.p = nullptr; o.n = o.cap = 0; }
-  SymBuf& operator=(SymBuf&& o) noexcept { if (this != &o) { free(p); p = o.p; n = o.n; cap = o.cap; o.p = nullptr; o.n = o.cap = 0; } return *this; }
-  ~SymBuf() { free(p); }
+// T = uint16_t: bytes and window markers (a chunk that starts in the middle of a stream); T = uint8_t: plain bytes (a stream decoded
+// from its start, e.g. a BGZF member - a match that reaches back past the start is then an error)
+template <class T>
+struct OutBuf {
+  T* p = nullptr; size_t n = 0, cap = 0;
+  OutBuf() = default;
+  OutBuf(const OutBuf&) = delete;
+  OutBuf& operator=(const OutBuf&) = delete;
+  OutBuf(OutBuf&& o) noexcept : p(o.p), n(o.n), cap(o.cap) { o.p = nullptr; o.n = o.cap = 0; }
+  OutBuf& operator=(OutBuf&& o) noexcept { if (this != &o) { free(p); p = o.p; n = o.n; cap = o.cap; o.p = nullptr; o.n = o.cap = 0; } return *this; }
+  ~OutBuf() { free(p); }
   bool room(size_t extra) {
     if (n + extra <= cap) return true;
     const size_t want = std::max(cap * 2, n + extra + (4u << 20));
-    uint16_t* q = (uint16_t*)big_alloc(want * sizeof(uint16_t));
+    T* q = (T*)big_alloc(want * sizeof(T));
     if (!q) return false;
-    if (n) memcpy(q, p, n * sizeof(uint16_t));
+    if (n) memcpy(q, p, n * sizeof(T));
     free(p);
     p = q; cap = want;
     return true;
   }
 };
+
+using SymBuf = OutBuf<uint16_t>;
 
 struct Tables { Huff lit, dist; };
 
@@ -174,7 +182,8 @@ bool read_dynamic_header(Bits& b, Tables& t) {
 }
 
 // One deflate block at b, symbols appended to out (nullptr = validate only).  Returns 0 ok, 1 ok and it was the final block, < 0 error.
-int decode_block(Bits& b, SymBuf* out, size_t* produced, Tables& scratch) {
+template <class T>
+int decode_block(Bits& b, OutBuf<T>* out, size_t* produced, Tables& scratch) {
   if (b.pos + 3 > b.nbits) return -1;
   const int final = (int)b.take(1), type = (int)b.take(2);
   if (type == 3) return -1;
@@ -187,7 +196,7 @@ int decode_block(Bits& b, SymBuf* out, size_t* produced, Tables& scratch) {
     if (out) {
       if (!out->room(len)) return -2;
       const uint8_t* s = b.base + (b.pos >> 3);
-      for (uint32_t i = 0; i < len; i++) out->p[out->n++] = s[i];
+      for (uint32_t i = 0; i < len; i++) out->p[out->n++] = (T)s[i];
     }
     *produced += len;
     b.pos += 8ull * len;
@@ -222,7 +231,7 @@ int decode_block(Bits& b, SymBuf* out, size_t* produced, Tables& scratch) {
     while (true) {
       if (pos > nbits) return -1;
       if (out->n + 600 > out->cap && !out->room(600)) return -2;
-      uint16_t* const p = out->p;
+      T* const p = out->p;
       size_t n = out->n;
       const size_t stop = out->cap - 300;
       int s;
@@ -232,12 +241,12 @@ int decode_block(Bits& b, SymBuf* out, size_t* produced, Tables& scratch) {
         w >>= (pos & 7);
         uint32_t e = lfast[w & FM];
         if (e && e < (256u << 4)) {
-          p[n++] = (uint16_t)(e >> 4); pos += e & 15; w >>= (e & 15);
+          p[n++] = (T)(e >> 4); pos += e & 15; w >>= (e & 15);
           e = lfast[w & FM];
           if (e && e < (256u << 4)) {
-            p[n++] = (uint16_t)(e >> 4); pos += e & 15; w >>= (e & 15);
+            p[n++] = (T)(e >> 4); pos += e & 15; w >>= (e & 15);
             e = lfast[w & FM];
-            if (e && e < (256u << 4)) { p[n++] = (uint16_t)(e >> 4); pos += e & 15; }
+            if (e && e < (256u << 4)) { p[n++] = (T)(e >> 4); pos += e & 15; }
           }
           if (n < stop && pos <= nbits) continue;
           s = -2;                                          // out of room or input: back to the outer checks
@@ -252,7 +261,7 @@ int decode_block(Bits& b, SymBuf* out, size_t* produced, Tables& scratch) {
       out->n = n;
       if (s == -2) continue;
       if (s < 0) return -1;
-      if (s < 256) { p[out->n++] = (uint16_t)s; continue; }
+      if (s < 256) { p[out->n++] = (T)s; continue; }
       if (s == 256) { b.pos = pos; *produced = out->n; return pos > nbits ? -1 : final; }
       if (s > 285) return -1;
       b.pos = pos;
@@ -263,11 +272,12 @@ int decode_block(Bits& b, SymBuf* out, size_t* produced, Tables& scratch) {
       pos = b.pos;
       n = out->n;
       int i = 0;
-      for (; i < len && (int64_t)n - dist < 0; i++, n++) p[n] = (uint16_t)(MARK | (uint16_t)(32768 + ((int64_t)n - dist)));   // before the chunk: [-32768, -1]
+      if (sizeof(T) == 1) { if ((size_t)dist > n) return -1; }        // byte mode: nothing exists before the start
+      else for (; i < len && (int64_t)n - dist < 0; i++, n++) p[n] = (T)(MARK | (uint16_t)(32768 + ((int64_t)n - dist)));   // before the chunk: [-32768, -1]
       if (i < len) {
-        const uint16_t* src = p + (n - (size_t)dist);
+        const T* src = p + (n - (size_t)dist);
         const int rest = len - i;
-        if (dist >= rest) memcpy(p + n, src, (size_t)rest * sizeof(uint16_t));
+        if (dist >= rest) memcpy(p + n, src, (size_t)rest * sizeof(T));
         else for (int j = 0; j < rest; j++) p[n + j] = src[j];          // overlapping run
         n += (size_t)rest;
       }
@@ -303,12 +313,12 @@ uint64_t find_block(const uint8_t* base, uint64_t nbits, uint64_t from, uint64_t
     // the block must decode to its end, and another plausible block must follow
     Bits body{base, p, nbits};
     size_t produced = 0;
-    const int r = decode_block(body, nullptr, &produced, *t);
+    const int r = decode_block<uint16_t>(body, nullptr, &produced, *t);
     if (r != 0 || produced < 64) continue;
     if (body.pos + 3 > nbits) continue;
     Bits nxt = body;
     size_t produced2 = 0;
-    const int r2 = decode_block(nxt, nullptr, &produced2, *t);
+    const int r2 = decode_block<uint16_t>(nxt, nullptr, &produced2, *t);
     if (r2 < 0) continue;
     found = p;
     break;
@@ -397,7 +407,12 @@ int PgzStream::next(char* dst, size_t cap, size_t* wrote) {
   if (S.failed) return -1;
   if (S.finished) return 0;
   const int T = std::max(1, omp_get_max_threads());
-  const size_t want = S.started ? (size_t)T * 2 : (size_t)T;      // a short first wave: the consumer can start early
+  // a short first wave so the consumer can start early, then two chunks per thread, then waves that shrink towards the end of the
+  // file so that little text is left for the consumer when the last one lands
+  const size_t left = S.nchunks - std::min(S.nchunks, S.next_chunk);
+  size_t want = S.started ? (size_t)T * 2 : (size_t)T;
+  if (left < want * 2) want = std::max<size_t>((size_t)(T + 1) / 2, left / 2);
+  if (left <= (size_t)(T + 1) / 2) want = left;
   S.started = true;
   const bool trace = getenv("CATT_TRACE") != nullptr;
   double tt = omp_get_wtime();
@@ -554,17 +569,31 @@ bool pgz_inflate(const unsigned char* in, size_t n, std::string* out, size_t chu
 namespace catt {
 
 bool read_raw_file(const char* path, std::vector<unsigned char>* buf, size_t* size) {
-  FILE* f = fopen(path, "rb");
-  if (!f) return false;
-  fseeko(f, 0, SEEK_END);
-  const int64_t sz = (int64_t)ftello(f);
-  fseeko(f, 0, SEEK_SET);
-  if (sz < 0) { fclose(f); return false; }
-  buf->assign((size_t)sz + 64, 0);                      // 64 bytes of slack for the bit readers
-  const size_t got = sz > 0 ? fread(buf->data(), 1, (size_t)sz, f) : 0;
-  fclose(f);
-  *size = (size_t)sz;
-  return (int64_t)got == sz;
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) return false;
+  struct stat stt;
+  if (fstat(fd, &stt) != 0 || stt.st_size < 0) { close(fd); return false; }
+  const size_t sz = (size_t)stt.st_size;
+  buf->clear();
+  buf->reserve(sz + 64);
+  buf->resize(sz + 64);                                 // 64 zero bytes of slack for the bit readers (the rest is overwritten below)
+  // parallel pread: the page-cache copy of a few hundred MB is worth spreading over the threads
+  const size_t sub = 8u << 20;
+  const int64_t ns = (int64_t)((sz + sub - 1) / sub);
+  bool ok = true;
+  #pragma omp parallel for schedule(dynamic, 1) reduction(&& : ok)
+  for (int64_t k = 0; k < ns; k++) {
+    size_t o = (size_t)k * sub;
+    const size_t e = std::min(sz, o + sub);
+    while (o < e) {
+      const ssize_t r = pread(fd, buf->data() + o, e - o, (off_t)o);
+      if (r <= 0) { ok = false; break; }
+      o += (size_t)r;
+    }
+  }
+  close(fd);
+  *size = sz;
+  return ok;
 }
 
 namespace {
@@ -613,6 +642,21 @@ int BgzfStream::next(char* dst, size_t cap, size_t* wrote) {
     const Block& b = blocks_[i];
     if (b.ulen == 0) continue;
     unsigned char* o = reinterpret_cast<unsigned char*>(dst) + (b.uoff - o0);
+    // the member's deflate data through the byte-mode decoder above (about twice zlib's inflate on the GPU boxes' hosts); the
+    // member's CRC-32 and size are the check, and zlib gets the member if anything is off
+    static thread_local OutBuf<uint8_t> scratch;
+    static thread_local Tables* tables = new Tables();
+    bool done = false;
+    scratch.n = 0;
+    if (!getenv("CATT_ZLIB_ONLY") && scratch.room(65536 + 1024)) {
+      // the decoder may read a few bytes past the member's deflate data: the member's 8-byte trailer and the next header are there
+      Bits bits{in_ + b.cdata, 0, 8ull * b.clen};
+      size_t produced = 0;
+      int r = 0;
+      while (r == 0 && scratch.n <= 65536) r = decode_block<uint8_t>(bits, &scratch, &produced, *tables);
+      if (r == 1 && scratch.n == b.ulen && crc32(crc32(0L, Z_NULL, 0), scratch.p, b.ulen) == b.crc) { memcpy(o, scratch.p, b.ulen); done = true; }
+    }
+    if (done) continue;
     z_stream zs;
     memset(&zs, 0, sizeof zs);
     if (inflateInit2(&zs, -15) != Z_OK) { bad = true; continue; }
