@@ -235,6 +235,8 @@ int decode_block(Bits& b, OutBuf<T>* out, size_t* produced, Tables& scratch) {
       size_t n = out->n;
       const size_t stop = out->cap - 300;
       int s;
+      bool wvalid = false;
+      uint64_t wsave = 0;
       while (true) {                                       // literal run
         uint64_t w;
         memcpy(&w, base + (pos >> 3), 8);
@@ -252,7 +254,7 @@ int decode_block(Bits& b, OutBuf<T>* out, size_t* produced, Tables& scratch) {
           s = -2;                                          // out of room or input: back to the outer checks
           break;
         }
-        if (e) { s = (int)(e >> 4); pos += e & 15; break; }
+        if (e) { s = (int)(e >> 4); pos += e & 15; w >>= (e & 15); wvalid = true; wsave = w; break; }
         b.pos = pos;
         s = decode_sym(t->lit, b);                         // long code
         pos = b.pos;
@@ -264,21 +266,42 @@ int decode_block(Bits& b, OutBuf<T>* out, size_t* produced, Tables& scratch) {
       if (s < 256) { p[out->n++] = (T)s; continue; }
       if (s == 256) { b.pos = pos; *produced = out->n; return pos > nbits ? -1 : final; }
       if (s > 285) return -1;
-      b.pos = pos;
-      const int len = LEN_BASE[s - 257] + (int)b.take(LEN_EXTRA[s - 257]);
-      const int ds = decode_sym(t->dist, b);
-      if (ds < 0 || ds > 29) return -1;
-      const int dist = DIST_BASE[ds] + (int)b.take(DIST_EXTRA[ds]);
-      pos = b.pos;
+      int len, dist;
+      {
+        // length extra bits, distance code and distance extra bits: at most 5 + 15 + 13 bits, all still in the window that held the
+        // length code (>= 46 valid bits left) unless that came through the long-code path
+        uint64_t w = wsave;
+        if (!wvalid) { memcpy(&w, base + (pos >> 3), 8); w >>= (pos & 7); }
+        const int le = LEN_EXTRA[s - 257];
+        len = LEN_BASE[s - 257] + (int)(w & ((1u << le) - 1));
+        w >>= le; pos += le;
+        int ds;
+        const uint16_t de = t->dist.fast[w & ((1u << t->dist.fb) - 1)];
+        if (de) { ds = de >> 4; w >>= (de & 15); pos += de & 15; }
+        else {
+          b.pos = pos;
+          ds = decode_sym(t->dist, b);
+          pos = b.pos;
+          memcpy(&w, base + (pos >> 3), 8); w >>= (pos & 7);
+        }
+        if (ds < 0 || ds > 29) return -1;
+        const int dx = DIST_EXTRA[ds];
+        dist = DIST_BASE[ds] + (int)(w & ((1u << dx) - 1));
+        pos += dx;
+      }
       n = out->n;
       int i = 0;
       if (sizeof(T) == 1) { if ((size_t)dist > n) return -1; }        // byte mode: nothing exists before the start
       else for (; i < len && (int64_t)n - dist < 0; i++, n++) p[n] = (T)(MARK | (uint16_t)(32768 + ((int64_t)n - dist)));   // before the chunk: [-32768, -1]
       if (i < len) {
         const T* src = p + (n - (size_t)dist);
+        T* dstp = p + n;
         const int rest = len - i;
-        if (dist >= rest) memcpy(p + n, src, (size_t)rest * sizeof(T));
-        else for (int j = 0; j < rest; j++) p[n + j] = src[j];          // overlapping run
+        constexpr int W = 8 / (int)sizeof(T);              // symbols per 8-byte word
+        if (dist >= W) {                                   // word copies; may write up to W - 1 symbols past the match (slack above)
+          T* const end = dstp + rest;
+          do { memcpy(dstp, src, 8); dstp += W; src += W; } while (dstp < end);
+        } else for (int j = 0; j < rest; j++) dstp[j] = src[j];          // short-distance overlapping run
         n += (size_t)rest;
       }
       out->n = n;
@@ -495,24 +518,29 @@ int PgzStream::next(char* dst, size_t cap, size_t* wrote) {
     char* o = dst + off[i];
     const size_t av = avail[i];
     size_t j = 0;
-#ifdef __SSE2__
-    for (; j + 16 <= sb.n; j += 16) {                      // 16 symbols at a time; markers are rare after the first 32 KiB of a chunk
-      const __m128i a = _mm_loadu_si128((const __m128i*)(sb.p + j)), b2 = _mm_loadu_si128((const __m128i*)(sb.p + j + 8));
-      if (_mm_movemask_epi8(_mm_or_si128(a, b2)) & 0xAAAA) {
-        for (size_t q = j; q < j + 16; q++) {
-          const uint16_t v = sb.p[q];
-          if (v & MARK) { if ((size_t)(32768 - (v & 0x7FFF)) > av) bad_marker = true; o[q] = (char)wv[v & 0x7FFF]; }
-          else o[q] = (char)v;
-        }
-      } else {
-        _mm_storeu_si128((__m128i*)(o + j), _mm_packus_epi16(a, b2));
+    if (av < 32768) {                                      // the first 32 KiB of the stream: markers must stay inside what exists
+      for (; j < sb.n; j++) {
+        const uint16_t v = sb.p[j];
+        if (v & MARK) { if ((size_t)(32768 - (v & 0x7FFF)) > av) bad_marker = true; o[j] = (char)wv[v & 0x7FFF]; }
+        else o[j] = (char)v;
       }
-    }
+    } else {
+      // one table for both kinds of symbol (bytes map to themselves, markers to the window): no branch per symbol; groups of 16
+      // symbols without a marker are packed with SSE2
+      std::vector<uint8_t> lut(65536);
+      for (int q = 0; q < 256; q++) lut[q] = (uint8_t)q;
+      memcpy(lut.data() + MARK, wv, 32768);
+#ifdef __SSE2__
+      for (; j + 16 <= sb.n; j += 16) {
+        const __m128i a = _mm_loadu_si128((const __m128i*)(sb.p + j)), b2 = _mm_loadu_si128((const __m128i*)(sb.p + j + 8));
+        if (_mm_movemask_epi8(_mm_or_si128(a, b2)) & 0xAAAA) {
+          for (size_t q = j; q < j + 16; q++) o[q] = (char)lut[sb.p[q]];
+        } else {
+          _mm_storeu_si128((__m128i*)(o + j), _mm_packus_epi16(a, b2));
+        }
+      }
 #endif
-    for (; j < sb.n; j++) {
-      const uint16_t v = sb.p[j];
-      if (v & MARK) { if ((size_t)(32768 - (v & 0x7FFF)) > av) bad_marker = true; o[j] = (char)wv[v & 0x7FFF]; }
-      else o[j] = (char)v;
+      for (; j < sb.n; j++) o[j] = (char)lut[sb.p[j]];
     }
     uint32_t c = (uint32_t)crc32(0L, Z_NULL, 0);          // zlib's crc32 takes uInt lengths: feed in slices
     for (size_t q = 0; q < sb.n; q += (1u << 30)) c = (uint32_t)crc32(c, (const Bytef*)o + q, (uInt)std::min<size_t>(sb.n - q, 1u << 30));
