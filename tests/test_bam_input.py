@@ -162,3 +162,51 @@ def test_run_bam_equals_the_fastq_path(trb, fx, sample, tmp_path, kind):
     for k in ("kmer", "v_hits", "j_hits", "vpart", "jpart", "direct", "left", "rescued", "the_err"):
         assert a.info[k] == b.info[k] == ref.info[k], k
     a.close(); b.close(); c.close()
+
+
+def test_mutated_inputs_never_crash(tmp_path):
+    """Random byte flips, truncations and insertions in BAM / raw BAM / SAM / .gz inputs: either a clean result or a CattError."""
+    import zlib
+    from catt_b200 import _lib
+    from catt_b200.host import bam_to_fastq, inflate_file
+    rng = random.Random(99)
+    recs = make_records(5, 300)
+    srcs = {}
+    for kind, kw in (("bam", {"block_bytes": 3000}), ("rawbam", {"compressed": False})):
+        p = str(tmp_path / f"{kind}.bin")
+        bamio.write_bam(p, recs, **kw)
+        srcs[kind] = open(p, "rb").read()
+    p = str(tmp_path / "s.sam")
+    bamio.write_sam(p, recs)
+    srcs["sam"] = open(p, "rb").read()
+    text = bamio.fastq_text(bamio.samtools_fastq_N(recs)) * 8
+    co = zlib.compressobj(6, zlib.DEFLATED, 31)
+    srcs["gz"] = co.compress(text) + co.flush()
+    os.environ["CATT_PGZ_CHUNK"] = "65536"
+    outcomes = {"ok": 0, "err": 0}
+    try:
+        for it in range(240):
+            kind = ("bam", "rawbam", "sam", "gz")[it % 4]
+            data = bytearray(srcs[kind])
+            for _ in range(rng.choice([1, 1, 2, 5, 20])):
+                op = rng.random()
+                if op < 0.6:
+                    data[rng.randrange(len(data))] = rng.randrange(256)
+                elif op < 0.8:
+                    del data[rng.randrange(1, len(data)):]
+                else:
+                    q = rng.randrange(len(data) + 1)
+                    data[q:q] = bytes(rng.randrange(256) for _ in range(rng.randrange(1, 9)))
+            f = str(tmp_path / "x.bin")
+            open(f, "wb").write(bytes(data))
+            try:
+                if kind == "gz":
+                    inflate_file(f, str(tmp_path / "o"))
+                else:
+                    bam_to_fastq(f, str(tmp_path / "o"))
+                outcomes["ok"] += 1
+            except _lib.CattError:
+                outcomes["err"] += 1
+    finally:
+        os.environ.pop("CATT_PGZ_CHUNK", None)
+    assert outcomes["err"] > 50 and outcomes["ok"] + outcomes["err"] == 240
