@@ -462,7 +462,14 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
     tpos[f + 1] = (tpos[f + 1] + 15) & ~(int64_t)15;
   }
   int rc;
-  if (c->pin[PIN_TEXT].ensure((size_t)tpos[nfiles] + 16) != CATT_OK) { cudaGetLastError(); return CATT_OK; }   // cannot pin that much: host path
+  const int64_t piece_max = std::max<int64_t>(c->chunk_reads * 320, 1 << 20);
+  // The text stays in HBM for Stage B, but on the host a piece is dead as soon as its copy has completed: inputs larger than the
+  // window (2 GiB; CATT_PIN_WINDOW for tests) pass through a sliding pinned window instead of being pinned whole
+  int64_t wcap = 2ll << 30;
+  if (const char* e = getenv("CATT_PIN_WINDOW")) wcap = std::max<int64_t>(atoll(e), 1 << 20);
+  const bool windowed = tpos[nfiles] + 16 > wcap;
+  if (windowed) wcap = std::max<int64_t>(wcap, 3 * piece_max);            // tail of an unfinished piece + the next block / wave
+  if (c->pin[PIN_TEXT].ensure((size_t)(windowed ? wcap : tpos[nfiles]) + 16) != CATT_OK) { cudaGetLastError(); return CATT_OK; }   // cannot pin that much: host path
   if ((rc = c->rd_text.ensure((size_t)tpos[nfiles] + 16))) return rc;
   char* h = c->pin[PIN_TEXT].as<char>();
   char* d_text = c->rd_text.as<char>();
@@ -474,7 +481,6 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
     std::mutex mu; std::condition_variable cv;
     std::vector<Piece> pieces; bool done = false; int status = CATT_OK; bool fallback = false; std::string err;
   } feed;
-  const int64_t piece_max = std::max<int64_t>(c->chunk_reads * 320, 1 << 20);
   {
     int64_t total = 0;
     for (int f = 0; f < nfiles; f++) total += size[f];
@@ -496,15 +502,37 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
     int64_t piece_bytes = std::max<int64_t>(piece_max / 64, 1 << 20);
     size_t n_published = 0;
     for (int f = 0; f < nfiles; f++) {
-      char* dst = h + tpos[f];
+      // dst + x is where byte x of file f lives on the host.  Whole-input mode: h + tpos[f] + x.  Windowed: h + (x - wbase), where
+      // wbase = the first byte still held (everything before the next piece start p has been published; the window slides once
+      // those copies have completed)
+      int64_t wbase = 0;
+      char* dst = windowed ? h : h + tpos[f];
+      int64_t have = 0, end = -1, p = 0;                           // bytes of the file produced so far; trimmed end once known; next piece start
+      if (windowed && n_published && cudaEventSynchronize(c->ev_piece[n_published - 1]) != cudaSuccess) { fail(CATT_E_CUDA, "FASTQ text upload failed", false); return; }
+      auto make_room = [&](int64_t need) -> bool {                 // room for bytes [have, have + need) of this file
+        if (!windowed || (have - wbase) + need + 16 <= wcap) return true;
+        if (n_published && cudaEventSynchronize(c->ev_piece[n_published - 1]) != cudaSuccess) return false;
+        memmove(h, dst + p, (size_t)(have - p));
+        if (getenv("CATT_TRACE_WINDOW")) fprintf(stderr, "[catt trace] pinned window slides: file %d, origin %lld -> %lld, %lld bytes kept\n", f, (long long)wbase, (long long)p, (long long)(have - p));
+        wbase = p;
+        dst = h - wbase;
+        return (have - wbase) + need + 16 <= wcap;
+      };
       int fd = -1;
-      if (isgz[f] == 1) { memcpy(dst, gz[f].data(), (size_t)size[f]); std::string().swap(gz[f]); }
-      else if (isgz[f] == 0 && (fd = open(paths[f], O_RDONLY)) < 0) { fail(CATT_E_IO, std::string("cannot read ") + paths[f], false); return; }
-      int64_t have = isgz[f] == 1 ? size[f] : 0, end = -1, p = 0;  // bytes of the file in memory; trimmed end once known; next piece start
+      int64_t gz_copied = 0;                                       // isgz == 1: bytes of the inflated string copied into the window
+      if (isgz[f] == 0 && (fd = open(paths[f], O_RDONLY)) < 0) { fail(CATT_E_IO, std::string("cannot read ") + paths[f], false); return; }
       while (true) {
-        if (have < size[f] && isgz[f] == 2) {                      // next wave of the parallel inflate
+        if (have < size[f] && isgz[f] == 1) {                      // inflated beforehand (zlib path): copy it in, block by block
+          const int64_t blk = std::min<int64_t>(size[f] - have, windowed ? std::min<int64_t>(256 << 20, wcap / 4) : size[f]);
+          if (!make_room(blk)) { fail(CATT_OK, "", true); return; }
+          memcpy(dst + have, gz[f].data() + gz_copied, (size_t)blk);
+          gz_copied += blk; have += blk;
+          if (have == size[f]) std::string().swap(gz[f]);
+        } else if (have < size[f] && isgz[f] == 2) {               // next wave of the parallel inflate
           size_t wrote = 0;
-          const int r = src[f](dst + have, (size_t)(size[f] - have), &wrote);
+          if (!make_room(std::min<int64_t>(size[f] - have, wcap / 3))) { fail(CATT_OK, "", true); return; }
+          const int64_t cap = windowed ? std::min<int64_t>(size[f] - have, wcap - 16 - (have - wbase)) : size[f] - have;
+          const int r = src[f](dst + have, (size_t)cap, &wrote);
           have += (int64_t)wrote;
           // a failed check anywhere in the stream (or a size bound that does not hold): nothing it produced may be trusted - the
           // host path (zlib / the host BAM decoder) takes the whole sample
@@ -512,7 +540,8 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
           if (r == 0) size[f] = have;                                // the source is exhausted: now the size is exact
           else if (wrote == 0) continue;
         } else if (have < size[f]) {                               // next block, all host threads
-          const int64_t blk = std::min<int64_t>(size[f] - have, 32 << 20), sub = 4 << 20, ns = (blk + sub - 1) / sub;
+          const int64_t blk = std::min<int64_t>(size[f] - have, std::min<int64_t>(32 << 20, std::max<int64_t>(wcap / 8, 1 << 16))), sub = 4 << 20, ns = (blk + sub - 1) / sub;
+          if (!make_room(blk)) { if (fd >= 0) close(fd); fail(CATT_OK, "", true); return; }
           bool ok = true;
           #pragma omp parallel for schedule(dynamic, 1) reduction(&& : ok)
           for (int64_t k = 0; k < ns; k++) {
@@ -529,7 +558,7 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
         }
         if (have == size[f] && end < 0) {                          // whole file present: trim trailing blank space, terminate with '\n'
           int64_t e = size[f];
-          while (e > 0 && (dst[e - 1] == '\n' || dst[e - 1] == '\r' || dst[e - 1] == ' ' || dst[e - 1] == '\t')) e--;
+          while (e > wbase && (dst[e - 1] == '\n' || dst[e - 1] == '\r' || dst[e - 1] == ' ' || dst[e - 1] == '\t')) e--;
           if (e == 0) { if (fd >= 0) close(fd); fail(CATT_OK, "", true); return; }
           dst[e++] = '\n';
           end = e;
@@ -557,7 +586,7 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
           }
           if (q <= p) break;
           const Piece pc{tpos[f] + p, tpos[f] + q, f};
-          if (cudaMemcpyAsync(d_text + pc.t0, h + pc.t0, (size_t)(pc.t1 - pc.t0), cudaMemcpyHostToDevice, c->copy_stream) != cudaSuccess ||
+          if (cudaMemcpyAsync(d_text + pc.t0, dst + p, (size_t)(pc.t1 - pc.t0), cudaMemcpyHostToDevice, c->copy_stream) != cudaSuccess ||
               n_published >= c->ev_piece.size() || cudaEventRecord(c->ev_piece[n_published], c->copy_stream) != cudaSuccess) {
             if (fd >= 0) close(fd);
             fail(CATT_E_CUDA, "FASTQ text upload failed", false);
