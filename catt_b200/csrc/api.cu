@@ -434,9 +434,12 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
         const char* cb = getenv("CATT_PGZ_CHUNK");
         std::unique_ptr<PgzStream> st(new PgzStream());
         std::unique_ptr<BgzfStream> bs(new BgzfStream());
-        if ((cb || rn >= (1u << 20)) && st->open(raw[f].data(), rn, cb ? (size_t)atol(cb) : (1u << 20)) && st->isize_field() > 0 &&
-            (uint64_t)st->isize_field() * 2 >= rn) {
-          bound = (int64_t)st->isize_field();                        // the trailer's ISIZE; the stream verifies it at the end
+        const bool opened = (cb || rn >= (1u << 20)) && st->open(raw[f].data(), rn, cb ? (size_t)atol(cb) : (1u << 20));
+        // the trailer's ISIZE is the text length mod 2^32: plausible (at least half the compressed size) -> exact bound; a large file
+        // with an implausible one has wrapped -> generous bound (8x; FASTQ compresses 3-6x), HBM only - the host side is a window
+        const bool wrapped = opened && (uint64_t)st->isize_field() * 2 < rn && rn >= (1u << 29);
+        if (opened && ((st->isize_field() > 0 && (uint64_t)st->isize_field() * 2 >= rn) || wrapped)) {
+          bound = wrapped ? (int64_t)rn * 8 : (int64_t)st->isize_field();   // the stream verifies ISIZE (mod 2^32) and the CRC-32 at the end
           pgz[f] = std::move(st);
           PgzStream* q = pgz[f].get();
           src[f] = [q](char* d, size_t cap, size_t* w) { return q->next(d, cap, w); };
