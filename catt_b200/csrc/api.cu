@@ -404,7 +404,7 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
   std::vector<char> isgz((size_t)nfiles, 0);
   // single-member .gz files are inflated wave by wave straight into the pinned text (pgz.cu), so the first pieces cross PCIe and
   // are aligned while the rest of the file is still being inflated; their size is the gzip trailer's ISIZE (verified at the end)
-  std::vector<std::vector<unsigned char>> raw((size_t)nfiles);
+  std::vector<RawFile> raw((size_t)nfiles);
   std::vector<std::unique_ptr<PgzStream>> pgz((size_t)nfiles);
   std::vector<std::unique_ptr<BgzfStream>> bgzf((size_t)nfiles);
   std::vector<std::unique_ptr<BamTextStream>> bamtx((size_t)nfiles);
@@ -420,8 +420,8 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
     }
     if (bam && !g) return CATT_OK;                                   // SAM text / uncompressed BAM: the host decoder (bam.cu)
     if (g && !getenv("CATT_ZLIB_ONLY")) {
-      size_t rn = 0;
-      if (!read_raw_file(paths[f], &raw[f], &rn)) { set_error("cannot read %s", paths[f]); return CATT_E_IO; }
+      if (!raw[f].open(paths[f])) { set_error("cannot read %s", paths[f]); return CATT_E_IO; }
+      const size_t rn = raw[f].size();
       int64_t bound = -1;
       if (bam) {                                                     // BGZF BAM -> FASTQ text, group by group (bam.cu)
         std::unique_ptr<BamTextStream> bt(new BamTextStream());
@@ -456,7 +456,7 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
         tpos[f + 1] = (tpos[f] + size[f] + 16 + 15) & ~(int64_t)15;
         continue;
       }
-      std::vector<unsigned char>().swap(raw[f]);
+      raw[f].close();
     }
     if (!read_whole(paths[f], &gz[f], &size[f], &g)) { set_error("cannot read %s", paths[f]); return CATT_E_IO; }
     isgz[f] = g;

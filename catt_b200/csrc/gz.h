@@ -9,6 +9,23 @@
 namespace catt {
 // the file's bytes plus 64 zero bytes of slack; *size = the file's size
 bool read_raw_file(const char* path, std::vector<unsigned char>* buf, size_t* size);
+// The same without the copy: the file mapped from the page cache (read-only); falls back to read_raw_file when the 64 bytes behind
+// the last byte would not be mapped.  data()[0 .. size() + 64) is readable.
+class RawFile {
+ public:
+  RawFile() = default;
+  RawFile(const RawFile&) = delete;
+  RawFile& operator=(const RawFile&) = delete;
+  ~RawFile() { close(); }
+  bool open(const char* path);
+  void close();
+  const unsigned char* data() const { return p_; }
+  size_t size() const { return n_; }
+ private:
+  const unsigned char* p_ = nullptr;
+  size_t n_ = 0, mapped_ = 0;
+  std::vector<unsigned char> buf_;
+};
 // 1 = inflated and appended to out, 0 = not BGZF, < 0 = error (set_error called)
 int bgzf_inflate(const unsigned char* in, size_t n, std::string* out, const char* path);
 // single-member gzip, speculative parallel decode verified by the trailer's CRC-32; false = not handled (caller uses zlib).

@@ -621,6 +621,34 @@ bool read_raw_file(const char* path, std::vector<unsigned char>* buf, size_t* si
   return ok;
 }
 
+bool RawFile::open(const char* path) {
+  close();
+  const int fd = ::open(path, O_RDONLY);
+  if (fd < 0) return false;
+  struct stat stt;
+  if (fstat(fd, &stt) != 0 || stt.st_size < 0) { ::close(fd); return false; }
+  const size_t sz = (size_t)stt.st_size, page = 4096, tail = sz % page;
+  if (sz > 0 && tail != 0 && tail + 64 <= page) {           // the slack behind the last byte lies inside the last mapped page (zeros)
+    void* m = mmap(nullptr, sz, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+    if (m != MAP_FAILED) {
+      ::close(fd);
+      madvise(m, sz, MADV_SEQUENTIAL);
+      p_ = (const unsigned char*)m; n_ = sz; mapped_ = sz;
+      return true;
+    }
+  }
+  ::close(fd);
+  if (!read_raw_file(path, &buf_, &n_)) return false;
+  p_ = buf_.data();
+  return true;
+}
+
+void RawFile::close() {
+  if (mapped_) munmap(const_cast<unsigned char*>(p_), mapped_);
+  p_ = nullptr; n_ = 0; mapped_ = 0;
+  std::vector<unsigned char>().swap(buf_);
+}
+
 namespace {
 inline uint32_t le32(const unsigned char* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 inline uint32_t le16(const unsigned char* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
