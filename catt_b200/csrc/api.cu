@@ -906,6 +906,28 @@ int catt_inflate_file(const char* path, const char* out_path, int32_t* method) {
 
 int catt_bam_to_fastq(const char* bam_path, const char* fastq_path) {
   if (!bam_path || !fastq_path) { set_error("catt_bam_to_fastq: null argument"); return CATT_E_ARG; }
+  if (!getenv("CATT_HOST_PARSE")) {                      // BGZF BAM: the streamed converter the file pipeline uses
+    RawFile raw;
+    BamTextStream bt;
+    if (raw.open(bam_path) && raw.size() >= 2 && raw.data()[0] == 0x1f && raw.data()[1] == 0x8b && bt.open(raw.data(), raw.size())) {
+      FILE* f = fopen(fastq_path, "wb");
+      if (!f) { set_error("cannot write %s", fastq_path); return CATT_E_IO; }
+      std::vector<char> text((size_t)std::max(1, omp_get_max_threads()) * 48 * 65536 / 3 * 4 + (1u << 20));
+      int r = 1;
+      bool wrote_ok = true;
+      while (r == 1) {
+        size_t wrote = 0;
+        r = bt.next(text.data(), text.size(), &wrote);
+        if (r >= 0 && wrote && fwrite(text.data(), 1, wrote, f) != wrote) wrote_ok = false;
+      }
+      const bool closed = fclose(f) == 0;
+      if (r == 0) {
+        if (!wrote_ok || !closed) { set_error("short write to %s", fastq_path); return CATT_E_IO; }
+        return CATT_OK;
+      }
+      // malformed for the streamed converter: the host decoder below names the problem
+    }
+  }
   HostReads hr;
   int rc = parse_bam(bam_path, &hr);
   if (rc) return rc;

@@ -172,7 +172,10 @@ int BamTextStream::next(char* dst, size_t cap, size_t* wrote) {
   const size_t group_bound = (size_t)std::max(1, omp_get_max_threads()) * 48 * 65536;
   if (buf_.size() < pending_ + group_bound) buf_.resize(pending_ + group_bound);
   size_t got = 0;
+  static double t_inf = 0, t_scan = 0, t_conv = 0;
+  double tt = omp_get_wtime();
   const int r = bz_.next(reinterpret_cast<char*>(buf_.data()) + pending_, buf_.size() - pending_, &got);
+  t_inf += omp_get_wtime() - tt; tt = omp_get_wtime();
   if (r < 0) return -1;
   const bool last = r == 0;
   const size_t N = pending_ + got;
@@ -199,10 +202,15 @@ int BamTextStream::next(char* dst, size_t cap, size_t* wrote) {
   // complete records of this stretch
   std::vector<Rec> recs;
   std::vector<size_t> off{0};
+  recs.reserve(N / 200 + 16); off.reserve(N / 200 + 17);
   while (p + 4 <= N) {
     const size_t bs = le32(d + p);
     if (bs < 32) return -1;
     if (p + 4 + bs > N) break;
+    // the chain of block_size fields is serial and every header is a cache miss (the bytes were just written by other cores):
+    // records of one run have similar sizes, so the headers a few records ahead can be fetched early
+    __builtin_prefetch(d + std::min(N - 1, p + 8 * (bs + 4)));
+    __builtin_prefetch(d + std::min(N - 1, p + 8 * (bs + 4) + 64));
     const unsigned char* rr = d + p + 4;
     const uint32_t l_read_name = rr[8], n_cigar = le16(rr + 12), flag = le16(rr + 14), l_seq = le32(rr + 16);
     const size_t need = 32 + (size_t)l_read_name + 4 * (size_t)n_cigar + ((size_t)l_seq + 1) / 2 + l_seq;
@@ -219,6 +227,7 @@ int BamTextStream::next(char* dst, size_t cap, size_t* wrote) {
   }
   if (last && p != N) return -1;                           // a truncated record at the end of the file
   if (off.back() > cap) return -2;
+  t_scan += omp_get_wtime() - tt; tt = omp_get_wtime();
   #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < (int64_t)recs.size(); i++) {
     const Rec& x = recs[i];
@@ -241,6 +250,8 @@ int BamTextStream::next(char* dst, size_t cap, size_t* wrote) {
     s[x.lseq] = '\n'; s[x.lseq + 1] = '+'; s[x.lseq + 2] = '\n';
     q[x.lseq] = '\n';
   }
+  t_conv += omp_get_wtime() - tt;
+  if (last && getenv("CATT_TRACE")) { fprintf(stderr, "[catt trace] bam stream: inflate %.1f ms, record scan %.1f ms, text %.1f ms\n", t_inf * 1e3, t_scan * 1e3, t_conv * 1e3); t_inf = t_scan = t_conv = 0; }
   *wrote = off.back();
   pending_ = N - p;
   if (pending_) memmove(buf_.data(), buf_.data() + p, pending_);
