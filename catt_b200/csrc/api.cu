@@ -602,7 +602,9 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
           feed.cv.notify_all();
           n_published++;
           p = q;
-          piece_bytes = std::min(piece_bytes * 4, piece_max);
+          // a source that is slower than the GPU (inflate, BAM conversion) should not end on a huge piece: whatever is published
+          // last is processed after the reader has finished
+          piece_bytes = std::min(piece_bytes * 4, isgz[f] == 2 ? std::max<int64_t>(piece_max / 4, 1 << 20) : piece_max);
           if (end >= 0 && p >= end) break;
         }
         if (end >= 0 && p >= end) break;
