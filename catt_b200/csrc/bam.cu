@@ -161,7 +161,7 @@ int parse_sam_bytes(const unsigned char* d, size_t N, const char* path, HostRead
 namespace catt {
 
 bool BamTextStream::open(const unsigned char* in, size_t n) {
-  buf_.clear(); pending_ = 0; header_done_ = false; eof_ = false;
+  buf_.clear(); pending_ = 0; header_done_ = false; eof_ = false; t_inf_ = t_scan_ = t_conv_ = 0;
   return bz_.open(in, n) && bz_.total() >= 12;
 }
 
@@ -172,10 +172,9 @@ int BamTextStream::next(char* dst, size_t cap, size_t* wrote) {
   const size_t group_bound = (size_t)std::max(1, omp_get_max_threads()) * 48 * 65536;
   if (buf_.size() < pending_ + group_bound) buf_.resize(pending_ + group_bound);
   size_t got = 0;
-  static double t_inf = 0, t_scan = 0, t_conv = 0;
   double tt = omp_get_wtime();
   const int r = bz_.next(reinterpret_cast<char*>(buf_.data()) + pending_, buf_.size() - pending_, &got);
-  t_inf += omp_get_wtime() - tt; tt = omp_get_wtime();
+  t_inf_ += omp_get_wtime() - tt; tt = omp_get_wtime();
   if (r < 0) return -1;
   const bool last = r == 0;
   const size_t N = pending_ + got;
@@ -227,7 +226,7 @@ int BamTextStream::next(char* dst, size_t cap, size_t* wrote) {
   }
   if (last && p != N) return -1;                           // a truncated record at the end of the file
   if (off.back() > cap) return -2;
-  t_scan += omp_get_wtime() - tt; tt = omp_get_wtime();
+  t_scan_ += omp_get_wtime() - tt; tt = omp_get_wtime();
   #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < (int64_t)recs.size(); i++) {
     const Rec& x = recs[i];
@@ -250,8 +249,8 @@ int BamTextStream::next(char* dst, size_t cap, size_t* wrote) {
     s[x.lseq] = '\n'; s[x.lseq + 1] = '+'; s[x.lseq + 2] = '\n';
     q[x.lseq] = '\n';
   }
-  t_conv += omp_get_wtime() - tt;
-  if (last && getenv("CATT_TRACE")) { fprintf(stderr, "[catt trace] bam stream: inflate %.1f ms, record scan %.1f ms, text %.1f ms\n", t_inf * 1e3, t_scan * 1e3, t_conv * 1e3); t_inf = t_scan = t_conv = 0; }
+  t_conv_ += omp_get_wtime() - tt;
+  if (last && getenv("CATT_TRACE")) fprintf(stderr, "[catt trace] bam stream: inflate %.1f ms, record scan %.1f ms, text %.1f ms\n", t_inf_ * 1e3, t_scan_ * 1e3, t_conv_ * 1e3);
   *wrote = off.back();
   pending_ = N - p;
   if (pending_) memmove(buf_.data(), buf_.data() + p, pending_);

@@ -73,6 +73,7 @@ class BamTextStream {
   std::vector<unsigned char> buf_;                                         // inflated bytes not consumed yet (a partial record)
   size_t pending_ = 0;
   bool header_done_ = false, eof_ = false;
+  double t_inf_ = 0, t_scan_ = 0, t_conv_ = 0;                             // CATT_TRACE laps
 };
 // plain / BGZF / gzip file into memory; *method = 0 plain bytes, 1 BGZF members in parallel, 2 parallel gzip, 3 one zlib stream
 bool slurp_file(const std::string& path, std::string& out, int* method = nullptr);
