@@ -11,7 +11,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 2000000
 d = tempfile.mkdtemp(prefix="catt_file_")
 with tarfile.open(os.path.join(ROOT, "tests", "golden", "catt_fixture.tar.gz")) as tar:
     tar.extractall(d)
-ctx = Catt(chain_cfg=chain_config("hs", "TRB", "CDR3", os.path.join(d, "resource")))
+ctx = Catt(chain_cfg=chain_config("hs", "TRB", "CDR3", os.path.join(d, "resource")), only_cdr3="cdr3" in sys.argv)   # "cdr3": the production result mode
 names, name_off, seqs, seq_off, quals = ctx.synth_reads(n, 150)
 path = os.path.join(d, "synth.fq")
 L = 150
@@ -31,5 +31,5 @@ for rep in range(3):
     t0 = time.perf_counter()
     res = ctx.mainflow(path)
     dt = time.perf_counter() - t0
-    print(f"catt_run_file: {dt * 1e3:.1f} ms  ({n / dt / 1e6:.2f} M reads/s)", {k: res.info[k] for k in ("vpart", "jpart")})
+    print(f"catt_run_file: {dt * 1e3:.1f} ms  ({n / dt / 1e6:.2f} M reads/s)", {k: res.info[k] for k in ("vpart", "jpart")}, flush=True)
     res.close()
