@@ -467,8 +467,9 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
   int rc;
   const int64_t piece_max = std::max<int64_t>(c->chunk_reads * 320, 1 << 20);
   // The text stays in HBM for Stage B, but on the host a piece is dead as soon as its copy has completed: inputs larger than the
-  // window (2 GiB; CATT_PIN_WINDOW for tests) pass through a sliding pinned window instead of being pinned whole
-  int64_t wcap = 2ll << 30;
+  // window (1 GiB - pinning costs ~0.4 s per GiB on the first call; CATT_PIN_WINDOW for tests) pass through a sliding pinned window
+  // instead of being pinned whole
+  int64_t wcap = 1ll << 30;
   if (const char* e = getenv("CATT_PIN_WINDOW")) wcap = std::max<int64_t>(atoll(e), 1 << 20);
   const bool windowed = tpos[nfiles] + 16 > wcap;
   if (windowed) wcap = std::max<int64_t>(wcap, 3 * piece_max);            // tail of an unfinished piece + the next block / wave
@@ -656,6 +657,21 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
     const int64_t file_first = fh.start[pc.file];
     if ((rc = stage_a_range(c, dr, n, n + np, n - file_first, pc.file, &fh, &R->info, &launches))) return rc;
     n += np; words += wp;
+    if (k == 0 && np > 0 && tpos[nfiles] > 4 * (pc.t1 - pc.t0)) {
+      // The first piece tells bytes and packed words per read: size the per-read buffers for the whole input once instead of growing
+      // them piece by piece (each growth is a cudaMalloc + copy + cudaFree: ~2 s of the first call on a 9.5 GB file)
+      const double per_read = (double)(pc.t1 - pc.t0) / (double)np;
+      const int64_t est = (int64_t)((double)tpos[nfiles] / per_read * 1.03) + 4096;
+      const uint64_t est_words = (uint64_t)((double)wp / (double)np * (double)est) + 4096;
+      cudaStream_t st = c->stream;
+      if (est_words < 0xFFFFFFF0ull &&
+          ((rc = c->rd_name_beg.ensure_keep((size_t)(est + 1) * 8, st)) || (rc = c->rd_name_end.ensure_keep((size_t)(est + 1) * 8, st)) ||
+           (rc = c->rd_seq_beg.ensure_keep((size_t)(est + 1) * 8, st)) || (rc = c->rd_qual_beg.ensure_keep((size_t)(est + 1) * 8, st)) ||
+           (rc = c->rd_len.ensure_keep((size_t)(est + 1) * 4, st)) || (rc = c->rd_off.ensure_keep((size_t)(est + 2) * 4, st)) ||
+           (rc = c->rd_words.ensure_keep((size_t)(est_words + 4) * 4, st)) ||
+           (rc = c->recs_all[0].ensure_keep((size_t)est * sizeof(catt_aln), st)) || (rc = c->recs_all[1].ensure_keep((size_t)est * sizeof(catt_aln), st))))
+        return rc;
+    }
   }
   fh.start.push_back(n);
   if ((int)fh.start.size() != nfiles + 1) { set_error("run_files: piece bookkeeping"); return CATT_E_ARG; }
