@@ -149,6 +149,19 @@ int align_finish(catt_ctx* c, int which, const ReadsDev& reads, catt_aln* recs, 
   return CATT_OK;
 }
 
+// Size the per-chunk Stage A scratch of both reference sets for the largest chunk that will come, before the pipeline is busy:
+// growing it chunk by chunk along the size ramp costs a cudaFree (device-wide sync) + cudaMalloc per step on the first call.
+int presize_align(catt_ctx* c, int64_t total_reads) {
+  const int64_t maxchunk = std::min<int64_t>(total_reads, c->chunk_reads * 3 / 2);
+  if (maxchunk <= 0) return CATT_OK;
+  int rc;
+  for (int which = 0; which < 2; which++) {
+    RefSet& rs = which ? c->J : c->V;
+    if ((rc = ensure_align_buffers(c->ab[which], rs.dev, maxchunk)) || (rc = ensure_task_buffers(c->ab[which], maxchunk * 10 + 4096))) return rc;
+  }
+  return CATT_OK;
+}
+
 int ensure_recs(catt_ctx* c, int64_t n) {
   int rc;
   for (int which = 0; which < 2; which++)
@@ -181,7 +194,7 @@ int stage_a_range(catt_ctx* c, const DeviceReads& dr, int64_t lo, int64_t hi, in
 
 int stage_a_resident(catt_ctx* c, const DeviceReads& dr, int64_t first_ordinal, FileHits* fh, catt_info* info, int* launches) {
   int rc;
-  if ((rc = ensure_recs(c, dr.n))) return rc;
+  if ((rc = ensure_recs(c, dr.n)) || (rc = presize_align(c, dr.n))) return rc;
   const int nfiles = (int)fh->start.size() - 1;
   fh->v.assign(nfiles, 0); fh->j.assign(nfiles, 0);
   for (int f = 0; f < nfiles; f++)
@@ -204,7 +217,7 @@ int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool
   if ((rc = pack_layout(n, hr.seq_off, h_off, h_len, &max_len))) return rc;
   const uint64_t total_words = h_off[n];
   if ((rc = c->rd_words.ensure((total_words + 4) * sizeof(uint32_t))) || (rc = c->rd_off.ensure((size_t)(n + 1) * sizeof(uint32_t))) ||
-      (rc = c->rd_len.ensure((size_t)std::max<int64_t>(n, 1) * sizeof(int32_t))) || (rc = ensure_recs(c, n))) return rc;
+      (rc = c->rd_len.ensure((size_t)std::max<int64_t>(n, 1) * sizeof(int32_t))) || (rc = ensure_recs(c, n)) || (align && (rc = presize_align(c, n)))) return rc;
   DeviceReads dr;
   dr.words = c->rd_words.as<uint32_t>(); dr.off = c->rd_off.as<uint32_t>(); dr.len = c->rd_len.as<int32_t>(); dr.n = n; dr.max_len = max_len;
   *view = dr;
@@ -465,11 +478,19 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
     tpos[f + 1] = (tpos[f + 1] + 15) & ~(int64_t)15;
   }
   int rc;
-  const int64_t piece_max = std::max<int64_t>(c->chunk_reads * 320, 1 << 20);
+  const int64_t piece_max_full = std::max<int64_t>(c->chunk_reads * 320, 1 << 20);
   // The text stays in HBM for Stage B, but on the host a piece is dead as soon as its copy has completed: inputs larger than the
   // window (1 GiB - pinning costs ~0.4 s per GiB on the first call; CATT_PIN_WINDOW for tests) pass through a sliding pinned window
   // instead of being pinned whole
   int64_t wcap = 1ll << 30;
+  // Pinning host memory costs ~0.4 ms per MB, and a process that handles one sample (the Julia driver) pays it inside its only call:
+  // the first call of a context works with a 320 MB window and pieces of at most 80 MB; a context that is used again is a server or a
+  // benchmark loop and gets the full window (and the full-size pieces) from its second call on
+  const bool first_call = c->file_calls++ == 0 && c->pin[PIN_TEXT].cap == 0;
+  int64_t piece_max = piece_max_full;
+  bool any_pgz = false;                                  // a wave of the parallel gzip decoder can be ~250 MB: it keeps the full window
+  for (int f = 0; f < nfiles; f++) any_pgz = any_pgz || (bool)pgz[f];
+  if (first_call && !any_pgz) { wcap = 320ll << 20; piece_max = std::min<int64_t>(piece_max_full, 80ll << 20); }
   if (const char* e = getenv("CATT_PIN_WINDOW")) wcap = std::max<int64_t>(atoll(e), 1 << 20);
   const bool windowed = tpos[nfiles] + 16 > wcap;
   if (windowed) wcap = std::max<int64_t>(wcap, 3 * piece_max);            // tail of an unfinished piece + the next block / wave
@@ -647,7 +668,9 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
     prev_file = pc.file;
     CATT_CUDA(cudaStreamWaitEvent(c->stream, c->ev_piece[k], 0));
     int64_t np = 0; uint64_t wp = 0; int fb = 0;
+    const double tp0 = now_ms();
     rc = ingest_fastq(c, d_text, pc.t0, pc.t1, n, words, &np, &wp, &max_len, &fb, &launches);
+    const double tp1 = now_ms();
     if (rc) { if (fb) return CATT_OK; return rc; }                 // fallback: *handled stays false
     R->info.bytes_h2d += pc.t1 - pc.t0;
     DeviceReads dr;
@@ -656,6 +679,8 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
       if ((rc = c->recs_all[which].ensure_keep((size_t)std::max<int64_t>(n + np, 1) * sizeof(catt_aln), c->stream))) return rc;
     const int64_t file_first = fh.start[pc.file];
     if ((rc = stage_a_range(c, dr, n, n + np, n - file_first, pc.file, &fh, &R->info, &launches))) return rc;
+    if (tr.on) fprintf(stderr, "[catt trace]   piece %zu: %lld bytes, %lld reads, waited+ingest %.1f ms, stage A %.1f ms\n", k, (long long)(pc.t1 - pc.t0),
+                       (long long)np, tp1 - tp0, now_ms() - tp1);
     n += np; words += wp;
     if (k == 0 && np > 0 && tpos[nfiles] > 4 * (pc.t1 - pc.t0)) {
       // The first piece tells bytes and packed words per read: size the per-read buffers for the whole input once instead of growing
@@ -671,6 +696,7 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
            (rc = c->rd_words.ensure_keep((size_t)(est_words + 4) * 4, st)) ||
            (rc = c->recs_all[0].ensure_keep((size_t)est * sizeof(catt_aln), st)) || (rc = c->recs_all[1].ensure_keep((size_t)est * sizeof(catt_aln), st))))
         return rc;
+      if ((rc = presize_align(c, est))) return rc;
     }
   }
   fh.start.push_back(n);

@@ -92,6 +92,7 @@ struct catt_ctx {
   char* d_dseq = nullptr; int32_t* d_doff = nullptr;
   catt::AlignBuffers ab[2];
   DevBuf rd_words, rd_off, rd_len;        // packed reads of the sample being run (catt_run_*, catt_assemble)
+  int64_t file_calls = 0;                 // catt_run_file(s) / catt_run_bam calls served by the device file pipeline so far
   int64_t last_n = 0, last_words = 0; int last_max_len = 0;   // what the last Stage A left in rd_* (catt_shard_counts)
   DevBuf rd_quals, rd_seqoff;
   DevBuf nb[4];                           // nbsorb scans (nbsorb.cu): raw sequences, query planes, target planes, aux             // its quality strings (as given) and int64 offsets, for the string kernel
