@@ -480,21 +480,19 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
   int rc;
   const int64_t piece_max_full = std::max<int64_t>(c->chunk_reads * 320, 1 << 20);
   // The text stays in HBM for Stage B, but on the host a piece is dead as soon as its copy has completed: inputs larger than the
-  // window (1 GiB - pinning costs ~0.4 s per GiB on the first call; CATT_PIN_WINDOW for tests) pass through a sliding pinned window
-  // instead of being pinned whole
-  int64_t wcap = 1ll << 30;
-  // Pinning host memory costs ~0.4 ms per MB, and a process that handles one sample (the Julia driver) pays it inside its only call:
-  // the first call of a context works with a 320 MB window and pieces of at most 80 MB; a context that is used again is a server or a
-  // benchmark loop and gets the full window (and the full-size pieces) from its second call on
-  const bool first_call = c->file_calls++ == 0 && c->pin[PIN_TEXT].cap == 0;
-  int64_t piece_max = piece_max_full;
-  bool any_pgz = false;                                  // a wave of the parallel gzip decoder can be ~250 MB: it keeps the full window
+  // window pass through a sliding pinned window instead of being pinned whole.  Pinned memory costs ~1 ms per MB (allocation + first
+  // touch) and a process that handles one sample - the Julia driver - pays it inside its only call, so the window is small: 320 MB
+  // with pieces of at most 80 MB (Stage A is as efficient on 265 k-read pieces as on 1 M-read ones; measured steady state 149.6 ms
+  // per 2 M reads against 144.6 ms with 768 MB, first call 375 against 856 ms).  The parallel gzip decoder produces up to a third of
+  // the window per wave and gets 640 MB.  CATT_PIN_WINDOW overrides (tests).
+  bool any_pgz = false;
   for (int f = 0; f < nfiles; f++) any_pgz = any_pgz || (bool)pgz[f];
-  if (first_call && !any_pgz) { wcap = 320ll << 20; piece_max = std::min<int64_t>(piece_max_full, 80ll << 20); }
+  int64_t wcap = any_pgz ? (640ll << 20) : (320ll << 20);
   if (const char* e = getenv("CATT_PIN_WINDOW")) wcap = std::max<int64_t>(atoll(e), 1 << 20);
+  const int64_t piece_max = std::min<int64_t>(piece_max_full, std::max<int64_t>(wcap / 4, 1 << 20));
   const bool windowed = tpos[nfiles] + 16 > wcap;
   if (windowed) wcap = std::max<int64_t>(wcap, 3 * piece_max);            // tail of an unfinished piece + the next block / wave
-  if (c->pin[PIN_TEXT].ensure((size_t)(windowed ? wcap : tpos[nfiles]) + 16) != CATT_OK) { cudaGetLastError(); return CATT_OK; }   // cannot pin that much: host path
+  if (c->pin[PIN_TEXT].ensure((size_t)(windowed ? wcap : tpos[nfiles]) + 16, true) != CATT_OK) { cudaGetLastError(); return CATT_OK; }   // cannot pin that much: host path
   if ((rc = c->rd_text.ensure((size_t)tpos[nfiles] + 16))) return rc;
   char* h = c->pin[PIN_TEXT].as<char>();
   char* d_text = c->rd_text.as<char>();
@@ -624,9 +622,7 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
           feed.cv.notify_all();
           n_published++;
           p = q;
-          // a source that is slower than the GPU (inflate, BAM conversion) should not end on a huge piece: whatever is published
-          // last is processed after the reader has finished
-          piece_bytes = std::min(piece_bytes * 4, isgz[f] == 2 ? std::max<int64_t>(piece_max / 4, 1 << 20) : piece_max);
+          piece_bytes = std::min(piece_bytes * 4, piece_max);
           if (end >= 0 && p >= end) break;
         }
         if (end >= 0 && p >= end) break;
@@ -658,36 +654,44 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
   // the seeding kernel sizes its scratch by the longest read of the sample, which is only known at the end: use the limit of the
   // first piece's reads for that piece, then the running maximum (a later, longer read only enlarges later launches)
   int prev_file = -1;
-  for (size_t k = 0;; k++) {
-    Piece pc;
-    const int got = next_piece(k, &pc);
-    if (got == 0) break;
-    if (got == -2) return CATT_OK;                                 // not strict FASTQ: the host parser takes over
-    if (got < 0) return feed.status;
+  // Indexing + packing of piece k+1 (three small host round trips on the ingest stream) runs while Stage A of piece k occupies the
+  // alignment streams: queue Stage A of k, ingest k+1, then wait for Stage A of k.
+  struct Ingested { Piece pc{0, 0, 0}; int64_t np = 0; uint64_t wp = 0; double ms = 0; };
+  int64_t n_ing = 0; uint64_t words_ing = 0;              // reads / words ingested so far (n, words: through Stage A)
+  bool want_fallback = false; int ing_rc = CATT_OK;
+  auto fetch_and_ingest = [&](size_t k, Ingested* g) -> int {       // 1 = piece k ingested, 0 = no more pieces, -1 = want_fallback / ing_rc
+    const int got = next_piece(k, &g->pc);
+    if (got == 0) return 0;
+    if (got == -2) { want_fallback = true; return -1; }            // not strict FASTQ: the host parser takes over
+    if (got < 0) { ing_rc = feed.status; return -1; }
+    const double t0 = now_ms();
+    if (cudaStreamWaitEvent(c->stream_ingest, c->ev_piece[k], 0) != cudaSuccess) { ing_rc = CATT_E_CUDA; set_error("ingest stream wait failed"); return -1; }
+    int fb = 0;
+    g->np = 0; g->wp = 0;
+    const int r = ingest_fastq(c, d_text, g->pc.t0, g->pc.t1, n_ing, words_ing, &g->np, &g->wp, &max_len, &fb, &launches, c->stream_ingest);
+    if (r) { if (fb) want_fallback = true; else ing_rc = r; return -1; }
+    if (cudaEventRecord(c->ev_ingest, c->stream_ingest) != cudaSuccess) { ing_rc = CATT_E_CUDA; set_error("ingest event failed"); return -1; }
+    n_ing += g->np; words_ing += g->wp;
+    g->ms = now_ms() - t0;
+    return 1;
+  };
+  Ingested cur, nxt;
+  int more = fetch_and_ingest(0, &cur);
+  if (more < 0) return want_fallback ? CATT_OK : ing_rc;
+  for (size_t k = 0; more == 1; k++) {
+    const Piece& pc = cur.pc;
+    const int64_t np = cur.np;
     if (prev_file >= 0 && prev_file != pc.file) fh.start.push_back(n);
     prev_file = pc.file;
-    CATT_CUDA(cudaStreamWaitEvent(c->stream, c->ev_piece[k], 0));
-    int64_t np = 0; uint64_t wp = 0; int fb = 0;
-    const double tp0 = now_ms();
-    rc = ingest_fastq(c, d_text, pc.t0, pc.t1, n, words, &np, &wp, &max_len, &fb, &launches);
-    const double tp1 = now_ms();
-    if (rc) { if (fb) return CATT_OK; return rc; }                 // fallback: *handled stays false
     R->info.bytes_h2d += pc.t1 - pc.t0;
-    DeviceReads dr;
-    dr.words = c->rd_words.as<uint32_t>(); dr.off = c->rd_off.as<uint32_t>(); dr.len = c->rd_len.as<int32_t>(); dr.n = n + np; dr.max_len = max_len;
-    for (int which = 0; which < 2; which++)
-      if ((rc = c->recs_all[which].ensure_keep((size_t)std::max<int64_t>(n + np, 1) * sizeof(catt_aln), c->stream))) return rc;
-    const int64_t file_first = fh.start[pc.file];
-    if ((rc = stage_a_range(c, dr, n, n + np, n - file_first, pc.file, &fh, &R->info, &launches))) return rc;
-    if (tr.on) fprintf(stderr, "[catt trace]   piece %zu: %lld bytes, %lld reads, waited+ingest %.1f ms, stage A %.1f ms\n", k, (long long)(pc.t1 - pc.t0),
-                       (long long)np, tp1 - tp0, now_ms() - tp1);
-    n += np; words += wp;
+    // nothing is in flight on the alignment streams here; the ingest stream may still be packing piece k
     if (k == 0 && np > 0 && tpos[nfiles] > 4 * (pc.t1 - pc.t0)) {
       // The first piece tells bytes and packed words per read: size the per-read buffers for the whole input once instead of growing
       // them piece by piece (each growth is a cudaMalloc + copy + cudaFree: ~2 s of the first call on a 9.5 GB file)
+      CATT_CUDA(cudaStreamSynchronize(c->stream_ingest));
       const double per_read = (double)(pc.t1 - pc.t0) / (double)np;
       const int64_t est = (int64_t)((double)tpos[nfiles] / per_read * 1.03) + 4096;
-      const uint64_t est_words = (uint64_t)((double)wp / (double)np * (double)est) + 4096;
+      const uint64_t est_words = (uint64_t)((double)cur.wp / (double)np * (double)est) + 4096;
       cudaStream_t st = c->stream;
       if (est_words < 0xFFFFFFF0ull &&
           ((rc = c->rd_name_beg.ensure_keep((size_t)(est + 1) * 8, st)) || (rc = c->rd_name_end.ensure_keep((size_t)(est + 1) * 8, st)) ||
@@ -698,6 +702,40 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
         return rc;
       if ((rc = presize_align(c, est))) return rc;
     }
+    for (int which = 0; which < 2; which++)
+      if ((rc = c->recs_all[which].ensure_keep((size_t)std::max<int64_t>(n + np, 1) * sizeof(catt_aln), c->stream))) return rc;
+    CATT_CUDA(cudaStreamWaitEvent(c->stream, c->ev_ingest, 0));   // the packed reads of piece k are complete
+    const int64_t file_first = fh.start[pc.file];
+    const int64_t ord = n - file_first;
+    const int piece_max_len = max_len;                             // as of piece k (the next ingest may raise it)
+    auto reads_now = [&]() {                                       // current addresses of the read buffers (a growth moves them)
+      DeviceReads dr;
+      dr.words = c->rd_words.as<uint32_t>(); dr.off = c->rd_off.as<uint32_t>(); dr.len = c->rd_len.as<int32_t>(); dr.n = n + np; dr.max_len = piece_max_len;
+      return dr;
+    };
+    const double ta = now_ms();
+    if (np > 0 && np <= c->chunk_reads * 3 / 2) {                  // one Stage A chunk: queue it, ingest the next piece under it, then finish
+      const ReadsDev rv = reads_now().view(n, np);
+      if ((rc = fork_j(c))) return rc;
+      for (int which = 0; which < 2; which++)
+        if ((rc = align_queue(c, which, rv, c->recs_all[which].as<catt_aln>() + n, ord, &launches))) { join_streams(c); return rc; }
+      more = fetch_and_ingest(k + 1, &nxt);
+      if ((rc = join_streams(c))) return rc;
+      if (more < 0) return want_fallback ? CATT_OK : ing_rc;
+      const ReadsDev rv2 = reads_now().view(n, np);
+      const int64_t v0 = R->info.v_hits, j0 = R->info.j_hits;
+      for (int which = 0; which < 2; which++)
+        if ((rc = align_finish(c, which, rv2, c->recs_all[which].as<catt_aln>() + n, ord, &R->info, &launches))) return rc;
+      fh.v[pc.file] += R->info.v_hits - v0; fh.j[pc.file] += R->info.j_hits - j0;
+    } else {                                                       // several chunks (short reads): the plain loop, then the next piece
+      if (np > 0 && (rc = stage_a_range(c, reads_now(), n, n + np, ord, pc.file, &fh, &R->info, &launches))) return rc;
+      more = fetch_and_ingest(k + 1, &nxt);
+      if (more < 0) return want_fallback ? CATT_OK : ing_rc;
+    }
+    if (tr.on) fprintf(stderr, "[catt trace]   piece %zu: %lld bytes, %lld reads, ingest %.1f ms (under the previous piece's Stage A), stage A %.1f ms\n", k,
+                       (long long)(pc.t1 - pc.t0), (long long)np, cur.ms, now_ms() - ta);
+    n += np; words += cur.wp;
+    cur = nxt;
   }
   fh.start.push_back(n);
   if ((int)fh.start.size() != nfiles + 1) { set_error("run_files: piece bookkeeping"); return CATT_E_ARG; }
@@ -810,6 +848,8 @@ int catt_ctx_create(catt_ctx** out, const catt_config* cfg) {
   CATT_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CATT_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   CATT_CUDA(cudaStreamCreateWithFlags(&c->stream_j, cudaStreamNonBlocking));
+  CATT_CUDA(cudaStreamCreateWithFlags(&c->stream_ingest, cudaStreamNonBlocking));
+  CATT_CUDA(cudaEventCreateWithFlags(&c->ev_ingest, cudaEventDisableTiming));
   CATT_CUDA(cudaEventCreateWithFlags(&c->ev_inputs, cudaEventDisableTiming));
   for (auto& ev : c->ev) CATT_CUDA(cudaEventCreate(&ev));
   for (auto& row : c->ev_a) for (auto& ev : row) CATT_CUDA(cudaEventCreate(&ev));
@@ -842,6 +882,8 @@ void catt_ctx_destroy(catt_ctx* c) {
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->stream_j) cudaStreamDestroy(c->stream_j);
+  if (c->stream_ingest) cudaStreamDestroy(c->stream_ingest);
+  if (c->ev_ingest) cudaEventDestroy(c->ev_ingest);
   if (c->ev_inputs) cudaEventDestroy(c->ev_inputs);
   delete c;
 }

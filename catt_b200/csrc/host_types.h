@@ -52,11 +52,11 @@ struct DevBuf {
 // grow-only pinned host staging
 struct PinBuf {
   void* p = nullptr; size_t cap = 0;
-  int ensure(size_t bytes) {
+  int ensure(size_t bytes, bool exact = false) {          // exact: no growth slack (pinning costs ~1 ms per MB, allocation + first touch)
     if (bytes <= cap) return CATT_OK;
     if (p) cudaFreeHost(p);
     p = nullptr; cap = 0;
-    const size_t want = bytes + bytes / 4 + 256;
+    const size_t want = exact ? bytes + 256 : bytes + bytes / 4 + 256;
     cudaError_t e = cudaMallocHost(&p, want);
     if (e != cudaSuccess) return catt::cuda_fail(e, "pinned cudaMallocHost", __FILE__, __LINE__);
     cap = want;
@@ -87,12 +87,13 @@ struct catt_ctx {
   cudaStream_t stream = nullptr;          // kernels
   cudaStream_t copy_stream = nullptr;     // H2D of the packed chunks, under the kernels of the previous chunk
   cudaStream_t stream_j = nullptr;        // Stage A of the J reference set, concurrent with the V set on `stream`
+  cudaStream_t stream_ingest = nullptr;   // FASTQ indexing + packing of the next piece, under Stage A of the current one (file pipeline)
+  cudaEvent_t ev_ingest = nullptr;        // the piece's packed reads are complete
   cudaEvent_t ev_inputs = nullptr;        // the chunk's packed reads are ready (fork point of the two Stage A streams)
   std::vector<std::string> d_names, d_seqs;
   char* d_dseq = nullptr; int32_t* d_doff = nullptr;
   catt::AlignBuffers ab[2];
   DevBuf rd_words, rd_off, rd_len;        // packed reads of the sample being run (catt_run_*, catt_assemble)
-  int64_t file_calls = 0;                 // catt_run_file(s) / catt_run_bam calls served by the device file pipeline so far
   int64_t last_n = 0, last_words = 0; int last_max_len = 0;   // what the last Stage A left in rd_* (catt_shard_counts)
   DevBuf rd_quals, rd_seqoff;
   DevBuf nb[4];                           // nbsorb scans (nbsorb.cu): raw sequences, query planes, target planes, aux             // its quality strings (as given) and int64 offsets, for the string kernel
@@ -167,7 +168,7 @@ int stage_b(catt_ctx* c, int64_t n, const NamesDev& names, const ReadsDev& reads
             int* launches);
 // FASTQ text of one input file, resident at d_text[t0, t1) -> spans + packed reads appended at read index `base` (ingest.cu)
 int ingest_fastq(catt_ctx* c, const char* d_text, int64_t t0, int64_t t1, int64_t base, uint64_t word_base, int64_t* n_out,
-                 uint64_t* words_out, int* max_len, int* fallback, int* launches);
+                 uint64_t* words_out, int* max_len, int* fallback, int* launches, cudaStream_t st);
 int launch_pack_raw(const char* d_text, const int64_t* d_seq_beg, const int32_t* d_len, const uint32_t* d_off, int64_t n, uint32_t* d_words,
                     int sm_count, cudaStream_t st, int* launches);
 // uploads host QNAMEs (contiguous, n+1 offsets) into the context's name buffers

@@ -101,10 +101,20 @@ int launch_pack_raw(const char* d_text, const int64_t* d_seq_beg, const int32_t*
 
 // Parses the FASTQ text of one input file, resident at d_text[t0, t1) (ends with '\n'), appending its reads at index `base`.
 // On success *n_out = records found; the ctx read buffers (rd_off is filled per file relative to `word_base`) are extended.
+// Runs on `st`.  The per-read buffers it appends to may be in use by Stage A of the previous piece on the alignment streams: before
+// any of them has to GROW (free + reallocate), those streams are drained.
 int ingest_fastq(catt_ctx* c, const char* d_text, int64_t t0, int64_t t1, int64_t base, uint64_t word_base, int64_t* n_out,
-                 uint64_t* words_out, int* max_len, int* fallback, int* launches) {
+                 uint64_t* words_out, int* max_len, int* fallback, int* launches, cudaStream_t st) {
   *fallback = 0; *n_out = 0; *words_out = 0;
-  cudaStream_t st = c->stream;
+  auto drain_if_growing = [&](std::initializer_list<std::pair<const DevBuf*, size_t>> need) -> int {
+    for (const auto& x : need)
+      if (x.second > x.first->cap) {
+        CATT_CUDA(cudaStreamSynchronize(c->stream));
+        CATT_CUDA(cudaStreamSynchronize(c->stream_j));
+        break;
+      }
+    return CATT_OK;
+  };
   const int64_t bytes = t1 - t0;
   if (bytes <= 0) return CATT_OK;
   int rc;
@@ -136,6 +146,8 @@ int ingest_fastq(catt_ctx* c, const char* d_text, int64_t t0, int64_t t1, int64_
   const int64_t n = n_lines / 4;
   // ---- per-record spans
   const int64_t tot = base + n;
+  if ((rc = drain_if_growing({{&c->rd_name_beg, (size_t)(tot + 1) * 8}, {&c->rd_name_end, (size_t)(tot + 1) * 8}, {&c->rd_seq_beg, (size_t)(tot + 1) * 8},
+                              {&c->rd_qual_beg, (size_t)(tot + 1) * 8}, {&c->rd_len, (size_t)(tot + 1) * 4}, {&c->rd_off, (size_t)(tot + 2) * 4}}))) return rc;
   if ((rc = c->rd_name_beg.ensure_keep((size_t)(tot + 1) * 8, st)) || (rc = c->rd_name_end.ensure_keep((size_t)(tot + 1) * 8, st)) ||
       (rc = c->rd_seq_beg.ensure_keep((size_t)(tot + 1) * 8, st)) || (rc = c->rd_qual_beg.ensure_keep((size_t)(tot + 1) * 8, st)) ||
       (rc = c->rd_len.ensure_keep((size_t)(tot + 1) * 4, st)) || (rc = c->rd_off.ensure_keep((size_t)(tot + 2) * 4, st)) ||
@@ -168,6 +180,7 @@ int ingest_fastq(catt_ctx* c, const char* d_text, int64_t t0, int64_t t1, int64_
     return CATT_E_LIMIT;
   }
   // ---- pack
+  if ((rc = drain_if_growing({{&c->rd_words, (size_t)(word_base + total_words + 4) * 4}}))) return rc;
   if ((rc = c->rd_words.ensure_keep((size_t)(word_base + total_words + 4) * 4, st))) return rc;
   const int grid = (int)std::min<int64_t>((n + 7) / 8, (int64_t)c->sm_count * 32);
   pack_kernel<<<grid, 256, 0, st>>>(d_text, seq_beg, len, off, n, c->rd_words.as<uint32_t>());

@@ -432,7 +432,9 @@ int PgzStream::next(char* dst, size_t cap, size_t* wrote) {
   const int T = std::max(1, omp_get_max_threads());
   // a short first wave so the consumer can start early, then two chunks per thread (fewer, larger waves decode faster than a tail
   // of shrinking ones: tried, 379 -> 426 ms per 2 M reads)
-  const size_t want = S.started ? (size_t)T * 2 : (size_t)T;
+  size_t want = S.started ? (size_t)T * 2 : (size_t)T;
+  // the caller's room bounds the wave: text rarely exceeds 8x its compressed size (FASTQ: 3-6x); a wave that does anyway is reported (-2)
+  want = std::max<size_t>(1, std::min(want, cap / (S.chunk_bytes * 8)));
   S.started = true;
   const bool trace = getenv("CATT_TRACE") != nullptr;
   double tt = omp_get_wtime();

@@ -27,7 +27,7 @@ rec[:, 15 + L:15 + 2 * L] = quals.reshape(n, L)
 rec[:, 15 + 2 * L] = 10
 rec.tofile(path)
 print("file bytes", os.path.getsize(path))
-for rep in range(3):
+for rep in range(int(os.environ.get('FILE_RUN_REPS', '3'))):
     t0 = time.perf_counter()
     res = ctx.mainflow(path)
     dt = time.perf_counter() - t0
