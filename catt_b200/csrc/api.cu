@@ -528,8 +528,15 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
       // dst + x is where byte x of file f lives on the host.  Whole-input mode: h + tpos[f] + x.  Windowed: h + (x - wbase), where
       // wbase = the first byte still held (everything before the next piece start p has been published; the window slides once
       // those copies have completed)
+      // (a view, not a pointer: in windowed mode byte 0 of the file may lie before the buffer)
+      struct FileView {
+        char* base; int64_t origin;                              // base[0] holds byte `origin` of the file
+        char* operator+(int64_t x) const { return base + (x - origin); }
+        char& operator[](int64_t x) const { return base[x - origin]; }
+      };
+      auto offset_of = [](const char* p, const FileView& v) -> int64_t { return (int64_t)(p - v.base) + v.origin; };
       int64_t wbase = 0;
-      char* dst = windowed ? h : h + tpos[f];
+      FileView dst{windowed ? h : h + tpos[f], 0};
       int64_t have = 0, end = -1, p = 0;                           // bytes of the file produced so far; trimmed end once known; next piece start
       if (windowed && n_published && cudaEventSynchronize(c->ev_piece[n_published - 1]) != cudaSuccess) { fail(CATT_E_CUDA, "FASTQ text upload failed", false); return; }
       auto make_room = [&](int64_t need) -> bool {                 // room for bytes [have, have + need) of this file
@@ -538,7 +545,7 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
         memmove(h, dst + p, (size_t)(have - p));
         if (getenv("CATT_TRACE_WINDOW")) fprintf(stderr, "[catt trace] pinned window slides: file %d, origin %lld -> %lld, %lld bytes kept\n", f, (long long)wbase, (long long)p, (long long)(have - p));
         wbase = p;
-        dst = h - wbase;
+        dst.origin = wbase;
         return (have - wbase) + need + 16 <= wcap;
       };
       int fd = -1;
@@ -598,11 +605,11 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
             while (q < limit) {                                    // advance q to the start of a header line
               const char* nl = (const char*)memchr(dst + q, '\n', (size_t)(limit - q));
               if (!nl) break;
-              q = (nl - dst) + 1;
+              q = offset_of(nl, dst) + 1;
               if (q >= limit) break;
               if (dst[q] != '@') continue;
               const char* n1 = (const char*)memchr(dst + q, '\n', (size_t)(limit - q));
-              const char* n2 = n1 ? (const char*)memchr(n1 + 1, '\n', (size_t)(dst + limit - (n1 + 1))) : nullptr;
+              const char* n2 = n1 ? (const char*)memchr(n1 + 1, '\n', (size_t)((dst + limit) - (n1 + 1))) : nullptr;
               if (n2 && n2 + 1 < dst + limit && n2[1] == '+') { found = true; break; }
             }
             if (!found) { if (end >= 0) q = end; else break; }
