@@ -692,6 +692,7 @@ int BgzfStream::next(char* dst, size_t cap, size_t* wrote) {
   const uint64_t o0 = blocks_[b0].uoff, o1 = b1 < blocks_.size() ? blocks_[b1].uoff : total_;
   if (o1 - o0 > cap) return -2;
   bool bad = false;
+  const bool zlib_only = getenv("CATT_ZLIB_ONLY") != nullptr;
   #pragma omp parallel for schedule(dynamic, 4) reduction(|| : bad)
   for (int64_t i = (int64_t)b0; i < (int64_t)b1; i++) {
     const Block& b = blocks_[i];
@@ -703,7 +704,7 @@ int BgzfStream::next(char* dst, size_t cap, size_t* wrote) {
     static thread_local Tables* tables = new Tables();
     bool done = false;
     scratch.n = 0;
-    if (!getenv("CATT_ZLIB_ONLY") && scratch.room(65536 + 1024)) {
+    if (!zlib_only && scratch.room(65536 + 1024)) {
       // the decoder may read a few bytes past the member's deflate data: the member's 8-byte trailer and the next header are there
       Bits bits{in_ + b.cdata, 0, 8ull * b.clen};
       size_t produced = 0;
