@@ -184,4 +184,19 @@ def test_fastq_gz_through_the_library(trb, fx, tmp_path):
             res.close()
     finally:
         os.environ.pop("CATT_PGZ_CHUNK", None)
+    # an empty .gz, and a .gz of a FASTA (not FASTQ: the host parser takes over)
+    p3 = str(tmp_path / "empty.fq.gz")
+    open(p3, "wb").write(gz_bytes(b""))
+    r0 = c.mainflow(p3)
+    assert r0.info["n_reads"] == 0 and r0.Vpart == [] and r0.Jpart == []
+    r0.close()
+    lines = src.decode().split("\n")
+    fa = "".join(f">{lines[i][1:]}\n{lines[i + 1]}\n" for i in range(0, 4 * 500, 4)).encode()
+    p4, p5 = str(tmp_path / "s.fa.gz"), str(tmp_path / "s.fa")
+    open(p4, "wb").write(gz_bytes(fa))
+    open(p5, "wb").write(fa)
+    ra, rb = c.mainflow(p4), c.mainflow(p5)
+    assert ra.info["n_reads"] == rb.info["n_reads"] == 500
+    assert [(r.seq, r.vs, r.js, r.cdr3) for r in ra.Vpart] == [(r.seq, r.vs, r.js, r.cdr3) for r in rb.Vpart]
+    ra.close(); rb.close()
     ref.close(); c.close()
