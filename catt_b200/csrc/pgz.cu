@@ -151,7 +151,28 @@ struct OutBuf {
 
 using SymBuf = OutBuf<uint16_t>;
 
-struct Tables { Huff lit, dist; };
+// lit32 / dist32: the fast tables with everything a symbol needs folded in, so the hot loop does one lookup per code:
+//   bits 0-3 code length, bits 4-7 number of extra bits, bits 8-9 kind (1 literal, 2 match length, 3 end of block; distance: 1),
+//   bits 16-31 the literal, the length base or the distance base.  0 = code longer than the table index (or invalid): slow path.
+constexpr int DIST_FAST_BITS = 10;
+struct Tables { Huff lit, dist; uint32_t lit32[1 << FAST_BITS], dist32[1 << DIST_FAST_BITS]; };
+
+void fold_tables(Tables& t) {
+  for (uint32_t i = 0; i < (1u << FAST_BITS); i++) {
+    const uint32_t e = t.lit.fast[i], sym = e >> 4, l = e & 15;
+    uint32_t v = 0;
+    if (e) {
+      if (sym < 256) v = (sym << 16) | (1u << 8) | l;
+      else if (sym == 256) v = (3u << 8) | l;
+      else if (sym <= 285) v = ((uint32_t)LEN_BASE[sym - 257] << 16) | (2u << 8) | ((uint32_t)LEN_EXTRA[sym - 257] << 4) | l;
+    }
+    t.lit32[i] = v;
+  }
+  for (uint32_t i = 0; i < (1u << DIST_FAST_BITS); i++) {
+    const uint32_t e = t.dist.fb == DIST_FAST_BITS ? t.dist.fast[i] : 0, sym = e >> 4, l = e & 15;
+    t.dist32[i] = (e && sym <= 29) ? ((uint32_t)DIST_BASE[sym] << 16) | (1u << 8) | ((uint32_t)DIST_EXTRA[sym] << 4) | l : 0;
+  }
+}
 
 // Reads a dynamic block header at b (BFINAL / BTYPE already consumed) and builds both tables.
 bool read_dynamic_header(Bits& b, Tables& t) {
@@ -178,7 +199,9 @@ bool read_dynamic_header(Bits& b, Tables& t) {
   }
   if (lens[256] == 0) return false;                    // no end-of-block code
   if (!build_huff(t.lit, lens, hlit, 1, FAST_BITS)) return false;
-  return build_huff(t.dist, lens + hlit, hdist, 1, 10);
+  if (!build_huff(t.dist, lens + hlit, hdist, 1, DIST_FAST_BITS)) return false;
+  fold_tables(t);
+  return true;
 }
 
 // One deflate block at b, symbols appended to out (nullptr = validate only).  Returns 0 ok, 1 ok and it was the final block, < 0 error.
@@ -216,80 +239,86 @@ int decode_block(Bits& b, OutBuf<T>* out, size_t* produced, Tables& scratch) {
       build_huff(q->lit, l, 288, 1);
       uint8_t d[32];
       for (int i = 0; i < 32; i++) d[i] = 5;
-      build_huff(q->dist, d, 32, 1);                    // codes 30, 31 decode but are rejected below
+      build_huff(q->dist, d, 32, 1, DIST_FAST_BITS);    // codes 30, 31 decode but are rejected below
+      fold_tables(*q);
       return q;
     }();
     t = fx;
   }
   if (out) {
-    // Hot loop with everything in locals: one 8-byte load serves a literal and, when the next code is a literal too, that one as well.
+    // Hot loop with everything in locals.  One 8-byte load gives >= 57 valid bits: enough for three literals, or for a whole match
+    // (length code <= 11 + 5 extra + distance code <= 10 + 13 extra = 39 bits) when its codes are in the fast tables.
     const uint8_t* const base = b.base;
     const uint64_t nbits = b.nbits;
     uint64_t pos = b.pos;
-    const uint16_t* const lfast = t->lit.fast;
-    constexpr uint64_t FM = (1u << FAST_BITS) - 1;
+    const uint32_t* const lit32 = t->lit32;
+    const uint32_t* const dist32 = t->dist32;
+    constexpr uint64_t FM = (1u << FAST_BITS) - 1, DM = (1u << DIST_FAST_BITS) - 1;
+    constexpr int W = 8 / (int)sizeof(T);                  // symbols per 8-byte word
     while (true) {
       if (pos > nbits) return -1;
       if (out->n + 600 > out->cap && !out->room(600)) return -2;
       T* const p = out->p;
       size_t n = out->n;
       const size_t stop = out->cap - 300;
-      int s;
-      bool wvalid = false;
-      uint64_t wsave = 0;
-      while (true) {                                       // literal run
+      int len = 0, dist = 0, s = -3;                       // s: -3 = a match decoded in the fast path, -2 = re-check room / input, >= 0 = slow-path symbol
+      while (true) {
         uint64_t w;
         memcpy(&w, base + (pos >> 3), 8);
         w >>= (pos & 7);
-        uint32_t e = lfast[w & FM];
-        if (e && e < (256u << 4)) {
-          p[n++] = (T)(e >> 4); pos += e & 15; w >>= (e & 15);
-          e = lfast[w & FM];
-          if (e && e < (256u << 4)) {
-            p[n++] = (T)(e >> 4); pos += e & 15; w >>= (e & 15);
-            e = lfast[w & FM];
-            if (e && e < (256u << 4)) { p[n++] = (T)(e >> 4); pos += e & 15; }
+        uint32_t e = lit32[w & FM];
+        if ((e & 0x300) == 0x100) {                        // literal run
+          p[n++] = (T)(e >> 16); pos += e & 15; w >>= (e & 15);
+          e = lit32[w & FM];
+          if ((e & 0x300) == 0x100) {
+            p[n++] = (T)(e >> 16); pos += e & 15; w >>= (e & 15);
+            e = lit32[w & FM];
+            if ((e & 0x300) == 0x100) { p[n++] = (T)(e >> 16); pos += e & 15; }
           }
           if (n < stop && pos <= nbits) continue;
-          s = -2;                                          // out of room or input: back to the outer checks
+          s = -2;
           break;
         }
-        if (e) { s = (int)(e >> 4); pos += e & 15; w >>= (e & 15); wvalid = true; wsave = w; break; }
-        b.pos = pos;
-        s = decode_sym(t->lit, b);                         // long code
+        if ((e & 0x300) == 0x200) {                        // match: length, then distance, from the same window
+          uint32_t l = e & 15, x = (e >> 4) & 15;
+          w >>= l;
+          len = (int)(e >> 16) + (int)(w & ((1u << x) - 1));
+          w >>= x; pos += l + x;
+          const uint32_t de = dist32[w & DM];
+          if (de) {
+            l = de & 15; x = (de >> 4) & 15;
+            w >>= l;
+            dist = (int)(de >> 16) + (int)(w & ((1u << x) - 1));
+            pos += l + x;
+          } else {                                         // long or invalid distance code
+            b.pos = pos;
+            const int ds = decode_sym(t->dist, b);
+            if (ds < 0 || ds > 29) return -1;
+            dist = DIST_BASE[ds] + (int)b.take(DIST_EXTRA[ds]);
+            pos = b.pos;
+          }
+          break;
+        }
+        if ((e & 0x300) == 0x300) { pos += e & 15; s = 256; break; }
+        b.pos = pos;                                       // long (or invalid) literal / length code
+        s = decode_sym(t->lit, b);
         pos = b.pos;
         break;
       }
       out->n = n;
       if (s == -2) continue;
-      if (s < 0) return -1;
-      if (s < 256) { p[out->n++] = (T)s; continue; }
-      if (s == 256) { b.pos = pos; *produced = out->n; return pos > nbits ? -1 : final; }
-      if (s > 285) return -1;
-      int len, dist;
-      {
-        // length extra bits, distance code and distance extra bits: at most 5 + 15 + 13 bits, all still in the window that held the
-        // length code (>= 46 valid bits left) unless that came through the long-code path
-        uint64_t w = wsave;
-        if (!wvalid) { memcpy(&w, base + (pos >> 3), 8); w >>= (pos & 7); }
-        const int le = LEN_EXTRA[s - 257];
-        len = LEN_BASE[s - 257] + (int)(w & ((1u << le) - 1));
-        w >>= le; pos += le;
-        int ds;
-        const uint16_t de = t->dist.fast[w & ((1u << t->dist.fb) - 1)];
-        if (de) { ds = de >> 4; w >>= (de & 15); pos += de & 15; }
-        else {
-          b.pos = pos;
-          ds = decode_sym(t->dist, b);
-          pos = b.pos;
-          memcpy(&w, base + (pos >> 3), 8); w >>= (pos & 7);
-        }
+      if (s != -3) {
+        if (s < 0) return -1;
+        if (s < 256) { p[out->n++] = (T)s; continue; }
+        if (s == 256) { b.pos = pos; *produced = out->n; return pos > nbits ? -1 : final; }
+        if (s > 285) return -1;
+        b.pos = pos;
+        len = LEN_BASE[s - 257] + (int)b.take(LEN_EXTRA[s - 257]);
+        const int ds = decode_sym(t->dist, b);
         if (ds < 0 || ds > 29) return -1;
-        const int dx = DIST_EXTRA[ds];
-        dist = DIST_BASE[ds] + (int)(w & ((1u << dx) - 1));
-        pos += dx;
+        dist = DIST_BASE[ds] + (int)b.take(DIST_EXTRA[ds]);
+        pos = b.pos;
       }
-      n = out->n;
       int i = 0;
       if (sizeof(T) == 1) { if ((size_t)dist > n) return -1; }        // byte mode: nothing exists before the start
       else for (; i < len && (int64_t)n - dist < 0; i++, n++) p[n] = (T)(MARK | (uint16_t)(32768 + ((int64_t)n - dist)));   // before the chunk: [-32768, -1]
@@ -297,9 +326,10 @@ int decode_block(Bits& b, OutBuf<T>* out, size_t* produced, Tables& scratch) {
         const T* src = p + (n - (size_t)dist);
         T* dstp = p + n;
         const int rest = len - i;
-        constexpr int W = 8 / (int)sizeof(T);              // symbols per 8-byte word
-        if (dist >= W) {                                   // word copies; may write up to W - 1 symbols past the match (slack above)
-          T* const end = dstp + rest;
+        T* const end = dstp + rest;
+        if (dist >= 4 * W) {                               // 32 bytes per step: most matches are one step; may write up to 4W - 1 symbols past the match
+          do { memcpy(dstp, src, 16); memcpy(dstp + 2 * W, src + 2 * W, 16); dstp += 4 * W; src += 4 * W; } while (dstp < end);
+        } else if (dist >= W) {
           do { memcpy(dstp, src, 8); dstp += W; src += W; } while (dstp < end);
         } else for (int j = 0; j < rest; j++) dstp[j] = src[j];          // short-distance overlapping run
         n += (size_t)rest;
