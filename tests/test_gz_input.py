@@ -200,3 +200,46 @@ def test_fastq_gz_through_the_library(trb, fx, tmp_path):
     assert [(r.seq, r.vs, r.js, r.cdr3) for r in ra.Vpart] == [(r.seq, r.vs, r.js, r.cdr3) for r in rb.Vpart]
     ra.close(); rb.close()
     ref.close(); c.close()
+
+
+def test_random_streams_property(tmp_path):
+    """Randomly structured data (runs, repeats at random distances up to the 32 KiB window and beyond, noise, text) under random zlib
+    settings: the parallel decoder's bytes are zlib's, whatever blocks and matches the compressor chose."""
+    rng = random.Random(2024)
+    for case in range(25):
+        parts, total = [], 0
+        target = rng.choice([200_000, 700_000, 1_500_000])
+        while total < target:
+            kind = rng.random()
+            if kind < 0.25:
+                blk = rng.randbytes(rng.randint(1, 40000))
+            elif kind < 0.5:
+                blk = bytes([rng.randrange(256)]) * rng.randint(1, 70000)
+            elif kind < 0.8 and parts:
+                src = b"".join(parts[-3:])
+                back = rng.randint(1, min(len(src), 40000))
+                seg = src[len(src) - back:len(src) - back + rng.randint(1, 300)]
+                blk = seg * rng.randint(1, 50)
+            else:
+                blk = "".join(rng.choice("ACGTN\n@+IF#") for _ in range(rng.randint(1, 30000))).encode()
+            parts.append(blk)
+            total += len(blk)
+        data = b"".join(parts)
+        level = rng.choice([1, 2, 4, 6, 9])
+        strategy = rng.choice([zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_RLE, zlib.Z_HUFFMAN_ONLY, zlib.Z_FIXED])
+        mem = rng.choice([1, 4, 8, 9])
+        co = zlib.compressobj(level, zlib.DEFLATED, 31, mem, strategy)
+        blob = b""
+        pos = 0
+        while pos < len(data):                               # occasional sync / full flushes: empty stored blocks, window resets
+            step = rng.randint(1, 400_000)
+            blob += co.compress(data[pos:pos + step])
+            pos += step
+            if rng.random() < 0.3:
+                blob += co.flush(rng.choice([zlib.Z_SYNC_FLUSH, zlib.Z_FULL_FLUSH]))
+        blob += co.flush()
+        p = str(tmp_path / f"r{case}.gz")
+        open(p, "wb").write(blob)
+        m, got = inflate(p, tmp_path, chunk=65536)
+        assert got == data, (case, level, strategy, mem)
+        assert m in (2, 3), case                             # the parallel path or (if a check failed) zlib - never a wrong answer
