@@ -22,7 +22,8 @@ class Config(C.Structure):
                 ("inner_c", C.c_char_p), ("inner_f", C.c_char_p), ("coffset", C.c_int32), ("foffset", C.c_int32),
                 ("min_score", C.c_int32), ("kmer", C.c_int32), ("julia_nthreads", C.c_int32), ("allow_v", C.c_int32),
                 ("allow_j", C.c_int32), ("device", C.c_int32), ("n_d", C.c_int32), ("d_names", C.POINTER(C.c_char_p)),
-                ("d_seqs", C.POINTER(C.c_char_p)), ("keep_records", C.c_int32), ("chunk_reads", C.c_int32), ("only_cdr3", C.c_int32), ("reserved_", C.c_int32)]
+                ("d_seqs", C.POINTER(C.c_char_p)), ("keep_records", C.c_int32), ("chunk_reads", C.c_int32), ("only_cdr3", C.c_int32), ("ngpu", C.c_int32),
+                ("devices", C.POINTER(C.c_int32))]
 
 
 ALN_DTYPE = np.dtype([("ordinal", "<i4"), ("rid", "<i4"), ("strand", "<i2"), ("mapped", "<i2"), ("as", "<i2"), ("qb", "<i2"),
@@ -45,10 +46,19 @@ class Info(C.Structure):
                [(k, C.c_double) for k in ("ms_seed", "ms_sw", "ms_select", "ms_extract", "ms_pool", "ms_h2d", "ms_d2h", "ms_host")] + \
                [(k, C.c_int64) for k in ("cells_computed_v", "cells_computed_j")] + \
                [(k, C.c_double) for k in ("ms_order", "ms_pack", "ms_seed_kernel", "ms_pool_kernel", "ms_strings")] + \
-               [(k, C.c_int64) for k in ("bytes_h2d", "bytes_d2h")] + [("ms_j_stream", C.c_double)]
+               [(k, C.c_int64) for k in ("bytes_h2d", "bytes_d2h")] + [("ms_j_stream", C.c_double)] + \
+               [("n_ranks", C.c_int32), ("reserved2_", C.c_int32), ("ms_comm", C.c_double), ("bytes_comm", C.c_int64),
+                ("ms_coll", C.c_double * 8), ("bytes_coll", C.c_int64 * 8), ("ms_stage_a_max", C.c_double), ("ms_stage_a_min", C.c_double)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved_"}
+        d = {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("reserved")}
+        d["ms_coll"] = list(self.ms_coll)
+        d["bytes_coll"] = list(self.bytes_coll)
+        return d
+
+
+COLL_NAMES = ("records_allgather", "mate_reads_allreduce", "item_flags_allreduce", "kmer_alltoall", "kmer_table_allgather",
+              "string_sizes_allreduce", "result_reduce")      # CATT_COLL_* of include/catt_b200.h
 
 
 EXPORTS = ["catt_ctx_create", "catt_ctx_destroy", "catt_last_error", "catt_version", "catt_ref_count", "catt_ref_name",
@@ -56,7 +66,8 @@ EXPORTS = ["catt_ctx_create", "catt_ctx_destroy", "catt_last_error", "catt_versi
            "catt_result_free", "catt_best_d", "catt_align_shard", "catt_batch_upload", "catt_batch_align", "catt_batch_sync",
            "catt_batch_download", "catt_batch_free", "catt_ctx_stream", "catt_assemble", "catt_seed_candidates", "catt_sw_pairs",
            "catt_finder", "catt_alu_peak", "catt_batch_assemble", "catt_synth_reads", "catt_run_files", "catt_run_reads_files", "catt_set_host_threads", "catt_records_device", "catt_assemble_device", "catt_shard_counts", "catt_reads_device",
-           "catt_assemble_resident", "catt_link_leaves", "catt_near_any", "catt_run_bam", "catt_bam_to_fastq", "catt_inflate_file"]
+           "catt_assemble_resident", "catt_link_leaves", "catt_near_any", "catt_run_bam", "catt_bam_to_fastq", "catt_inflate_file",
+           "catt_comm_id", "catt_ctx_join", "catt_run_reads_shard"]
 
 _lib = None
 
@@ -116,6 +127,9 @@ def load():
     L.catt_batch_assemble.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]
     L.catt_synth_reads.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, C.c_uint64, C.c_double, C.c_int32, vp, vp, vp, vp]
     L.catt_alu_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.catt_comm_id.argtypes = [vp]
+    L.catt_ctx_join.argtypes = [vp, C.c_int32, C.c_int32, vp]
+    L.catt_run_reads_shard.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, vp, vp, vp, vp, vp, C.c_int32, vp, C.POINTER(vp)]
     _lib = L
     return L
 

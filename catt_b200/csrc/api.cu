@@ -206,7 +206,8 @@ int stage_a_resident(catt_ctx* c, const DeviceReads& dr, int64_t first_ordinal, 
 // i+1 into pinned staging and the copy stream moves it to HBM.  `fh->start` lists the input files of the sample: chunks never
 // straddle a file and bwa's read ordinal restarts at every file (each file is one `bwa mem` run, catt.jl:143-147).
 int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool align, bool want_quals, DeviceReads* view, DeviceQuals* dq,
-                   FileHits* fh, catt_info* info, int* launches, const std::function<int()>& under_kernels = nullptr) {
+                   FileHits* fh, catt_info* info, int* launches, const std::function<int()>& under_kernels = nullptr,
+                   const std::vector<int64_t>* file_ordinal0 = nullptr) {
   const int64_t n = hr.n;
   int rc;
   const double t0 = now_ms();
@@ -234,8 +235,10 @@ int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool
   } else if (want_quals && dq && n > 0) {
     dq->seq_off = d_seqoff;
     if (hr.quals) {
-      if ((rc = c->rd_quals.ensure((size_t)hr.seq_off[n] + 16))) return rc;
-      d_quals = c->rd_quals.as<char>();
+      // seq_off may be a view into a larger sample (one rank's block of a GPU group): the device copy holds this block only and is
+      // addressed with the caller's absolute offsets
+      if ((rc = c->rd_quals.ensure((size_t)(hr.seq_off[n] - hr.seq_off[0]) + 16))) return rc;
+      d_quals = c->rd_quals.as<char>() - hr.seq_off[0];
       dq->quals = d_quals;
     }
   }
@@ -252,7 +255,7 @@ int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool
       const int64_t want = std::min<int64_t>(ramp, c->chunk_reads);
       ramp = std::min<int64_t>(ramp * 4, c->chunk_reads);
       const int64_t cnt = std::min<int64_t>(want, fh->start[f + 1] - i0);
-      chunks.push_back(Chunk{i0, cnt, first_ordinal + (i0 - fh->start[f]), f});
+      chunks.push_back(Chunk{i0, cnt, (file_ordinal0 ? (*file_ordinal0)[f] : first_ordinal) + (i0 - fh->start[f]), f});
       i0 += cnt;
     }
   const int64_t nchunks = (int64_t)chunks.size();
@@ -787,6 +790,162 @@ int run_all(catt_ctx* c, const HostReads& hr, const std::vector<int64_t>& file_s
   return CATT_OK;
 }
 
+// ---- one sample over several GPUs -------------------------------------------------------------------------------------
+// Contiguous block [lo, hi) of rank r: sizes differ by at most one read, earlier ranks take the extra ones.
+void block_bounds(int64_t n, int nranks, int r, int64_t* lo, int64_t* hi) {
+  const int64_t base = n / nranks, extra = n % nranks;
+  *lo = r * base + std::min<int64_t>(r, extra);
+  *hi = *lo + base + (r < extra ? 1 : 0);
+}
+
+// One rank: Stage A on this rank's block `hr` (reads [lo, lo + hr.n) of the sample), then its part of the global Stage B.
+// `gstart` are the global file boundaries.  Every rank returns a result; the lists are on `root`.
+int run_rank(catt_ctx* c, Comm* comm, int root, int64_t n_total, int64_t lo, const HostReads& hr, const std::vector<int64_t>& gstart, catt_result** out) {
+  std::unique_ptr<catt_result> R(new catt_result());
+  int launches = 0, rc;
+  Trace tr;
+  const int N = comm->nranks;
+  const int64_t n_loc = hr.n;
+  const int nfiles = (int)gstart.size() - 1;
+  if (nfiles < 1 || gstart.front() != 0 || gstart.back() != n_total || lo < 0 || lo + n_loc > n_total) { set_error("GPU group: block [%lld, %lld) outside the sample of %lld reads", (long long)lo, (long long)(lo + n_loc), (long long)n_total); return CATT_E_ARG; }
+  // this block's share of every input file; bwa's read ordinal restarts with every file (catt.jl:143-147)
+  FileHits fh;
+  std::vector<int64_t> ord0;
+  fh.start = {0};
+  for (int f = 0; f < nfiles; f++) {
+    const int64_t a = std::min(std::max(gstart[f], lo), lo + n_loc), b = std::min(std::max(gstart[f + 1], lo), lo + n_loc);
+    fh.start.push_back(b - lo);
+    ord0.push_back(a - gstart[f]);
+  }
+  DeviceReads dr;
+  DeviceQuals dq;
+  NamesDev nd;
+  catt_result* Rp = R.get();
+  const double t0 = now_ms();
+  rc = stage_a_stream(c, hr, 0, true, true, &dr, &dq, &fh, &R->info, &launches,
+                      [&]() { return upload_names(c, hr.n, hr.names, hr.name_off, &nd, &Rp->info, c->copy_stream); }, &ord0);
+  const double ms_a = now_ms() - t0;
+  tr.lap("run_rank: pack + H2D + align (pipelined)");
+  // a rank that failed must still answer the first exchange, or its peers would wait for it forever: the status travels with the bounds
+  long long mine[4] = {lo, n_loc, rc ? -1 : (long long)dr.max_len, rc};
+  std::vector<long long> all((size_t)4 * N);
+  int rc2 = comm->host_allgather(mine, all.data(), sizeof mine, c->stream);
+  if (rc) return rc;
+  if (rc2) return rc2;
+  ShardIn in;
+  in.comm = comm; in.lo = lo; in.n_loc = n_loc; in.n_words = c->last_words; in.gstart = gstart; in.root = root;
+  in.bounds.assign((size_t)N + 1, 0);
+  int64_t expect = 0;
+  for (int r = 0; r < N; r++) {
+    if (all[4 * r + 3] != 0) { set_error("GPU group: rank %d failed in Stage A (code %lld)", r, all[4 * r + 3]); return (int)all[4 * r + 3]; }
+    if (all[4 * r] != expect) { set_error("GPU group: the blocks of the ranks are not contiguous (rank %d starts at %lld, expected %lld)", r, all[4 * r], (long long)expect); return CATT_E_ARG; }
+    in.bounds[r] = expect; expect += all[4 * r + 1];
+    in.max_len = std::max(in.max_len, (int)all[4 * r + 2]);
+  }
+  in.bounds[N] = expect;
+  if (expect != n_total) { set_error("GPU group: the blocks cover %lld reads, the sample has %lld", (long long)expect, (long long)n_total); return CATT_E_ARG; }
+  if (c->keep_records) {                            // diagnostics: every rank's records, in input order, on the root
+    std::vector<size_t> cn(N), dp(N);
+    for (int r = 0; r < N; r++) { cn[r] = (size_t)(in.bounds[r + 1] - in.bounds[r]) * sizeof(catt_aln); dp[r] = (size_t)in.bounds[r] * sizeof(catt_aln); }
+    for (int which = 0; which < 2; which++) {
+      if ((rc = c->sh[SH_SLOTS - 1].ensure((size_t)std::max<int64_t>(n_total, 1) * sizeof(catt_aln)))) return rc;
+      if ((rc = comm->allgatherv(c->recs_all[which].p, c->sh[SH_SLOTS - 1].p, cn.data(), dp.data(), c->stream))) return rc;
+      CATT_CUDA(cudaStreamSynchronize(c->stream));
+      if (comm->rank == root) {
+        R->rec[which].resize((size_t)n_total);
+        if (n_total) CATT_CUDA(cudaMemcpy(R->rec[which].data(), c->sh[SH_SLOTS - 1].p, (size_t)n_total * sizeof(catt_aln), cudaMemcpyDeviceToHost));
+      }
+    }
+  }
+  if ((rc = stage_b_sharded(c, in, nd, dq, R.get(), &launches))) return rc;
+  tr.lap("run_rank: stage_b_sharded");
+  // counters: sums over the ranks; stage times: the slowest rank
+  catt_info& I = R->info;
+  I.kernel_launches = launches;
+  I.ms_stage_a_max = I.ms_stage_a_min = ms_a;
+  std::vector<catt_info> infos((size_t)N);
+  if ((rc = comm->host_allgather(&I, infos.data(), sizeof(catt_info), c->stream))) return rc;
+  catt_info T = infos[(size_t)root];                 // the globally derived values (lists, k, the_ERR, ...) are identical on every rank
+  auto sum = [&](int64_t catt_info::*m) { int64_t v = 0; for (auto& x : infos) v += x.*m; T.*m = v; };
+  auto mx = [&](double catt_info::*m) { double v = 0; for (auto& x : infos) v = std::max(v, x.*m); T.*m = v; };
+  sum(&catt_info::v_hits); sum(&catt_info::j_hits); sum(&catt_info::cand_v); sum(&catt_info::cand_j); sum(&catt_info::cells_v); sum(&catt_info::cells_j);
+  sum(&catt_info::gapped_v); sum(&catt_info::gapped_j); sum(&catt_info::cells_computed_v); sum(&catt_info::cells_computed_j);
+  sum(&catt_info::kernel_launches); sum(&catt_info::bytes_h2d); sum(&catt_info::bytes_d2h); sum(&catt_info::rescued); sum(&catt_info::bytes_comm);
+  mx(&catt_info::ms_seed); mx(&catt_info::ms_sw); mx(&catt_info::ms_select); mx(&catt_info::ms_extract); mx(&catt_info::ms_pool); mx(&catt_info::ms_h2d);
+  mx(&catt_info::ms_d2h); mx(&catt_info::ms_host); mx(&catt_info::ms_order); mx(&catt_info::ms_pack); mx(&catt_info::ms_seed_kernel);
+  mx(&catt_info::ms_pool_kernel); mx(&catt_info::ms_strings); mx(&catt_info::ms_j_stream); mx(&catt_info::ms_comm); mx(&catt_info::ms_stage_a_max);
+  for (int k = 0; k < 8; k++) {
+    double m = 0; int64_t b = 0;
+    for (auto& x : infos) { m = std::max(m, x.ms_coll[k]); b += x.bytes_coll[k]; }
+    T.ms_coll[k] = m; T.bytes_coll[k] = b;
+  }
+  T.ms_stage_a_min = infos[0].ms_stage_a_min;
+  for (auto& x : infos) T.ms_stage_a_min = std::min(T.ms_stage_a_min, x.ms_stage_a_min);
+  T.n_reads = n_total; T.n_ranks = N;
+  I = T;
+  *out = R.release();
+  return CATT_OK;
+}
+
+// The in-process group: rank r runs on its own host thread and its own context / device; rank 0 on the calling thread.
+int run_group(catt_ctx* c, const HostReads& hr, const std::vector<int64_t>& fs, catt_result** out) {
+  const int N = 1 + (int)c->peers.size();
+  std::vector<int> rcs((size_t)N, CATT_OK);
+  std::vector<std::string> errs((size_t)N);
+  std::vector<catt_result*> res((size_t)N, nullptr);
+  const int host_threads = std::max(1, omp_get_max_threads()), per_rank = std::max(1, host_threads / N);
+  if (c->lgroup) catt::local_group_reset(c->lgroup);
+  auto body = [&](int r) {
+    catt_ctx* cr = r ? c->peers[(size_t)r - 1] : c;
+    if (cudaSetDevice(cr->device) != cudaSuccess) { rcs[r] = CATT_E_CUDA; errs[r] = "cudaSetDevice failed"; return; }
+    omp_set_num_threads(per_rank);                   // a per-thread setting: every rank packs / copies with its share of the cores
+    int64_t lo, hi;
+    block_bounds(hr.n, N, r, &lo, &hi);
+    HostReads sub;
+    sub.n = hi - lo; sub.names = hr.names; sub.name_off = hr.name_off ? hr.name_off + lo : nullptr; sub.seqs = hr.seqs;
+    sub.seq_off = hr.seq_off ? hr.seq_off + lo : nullptr; sub.quals = hr.quals;
+    rcs[r] = run_rank(cr, c->comms[(size_t)r], 0, hr.n, lo, sub, fs, &res[r]);
+    if (rcs[r]) { errs[r] = catt::last_error(); if (c->lgroup) catt::local_group_fail(c->lgroup); }
+  };
+  std::vector<std::thread> th;
+  for (int r = 1; r < N; r++) th.emplace_back(body, r);
+  body(0);
+  for (auto& t : th) t.join();
+  omp_set_num_threads(host_threads);
+  cudaSetDevice(c->device);
+  int bad = -1;
+  for (int r = 0; r < N; r++) if (rcs[r] && (bad < 0 || errs[bad].find("peer rank") != std::string::npos)) bad = r;     // prefer the root cause
+  if (bad >= 0) {
+    for (auto* p : res) delete p;
+    set_error("GPU group rank %d (device %d): %s", bad, bad ? c->peers[(size_t)bad - 1]->device : c->device, errs[bad].c_str());
+    return rcs[bad];
+  }
+  for (int r = 1; r < N; r++) delete res[r];
+  *out = res[0];
+  return CATT_OK;
+}
+
+int run_reads_dispatch(catt_ctx* c, const HostReads& hr, const std::vector<int64_t>& fs, catt_result** out);
+// File input on a GPU group: the files are read and parsed on the host (all threads), then the reads are split over the ranks.
+int run_files_group(catt_ctx* c, int nfiles, const char* const* paths, bool bam, catt_result** out) {
+  HostReads hr;
+  std::vector<int64_t> fs{0};
+  Trace tr;
+  for (int f = 0; f < nfiles; f++) {
+    if (!paths[f]) { set_error("catt_run_files: null path"); return CATT_E_ARG; }
+    int rc = bam ? parse_bam(paths[f], &hr) : parse_fastx(paths[f], &hr);
+    if (rc) return rc;
+    fs.push_back(hr.n);
+  }
+  tr.lap("run_files_group: read + parse");
+  return run_reads_dispatch(c, hr, fs, out);
+}
+
+int run_reads_dispatch(catt_ctx* c, const HostReads& hr, const std::vector<int64_t>& fs, catt_result** out) {
+  if (!c->peers.empty()) return run_group(c, hr, fs, out);
+  return run_all(c, hr, fs, out);
+}
+
 std::string dup(const char* s) { return s ? std::string(s) : std::string(); }
 
 inline uint64_t sm64(uint64_t& s) {
@@ -818,12 +977,24 @@ int catt_ctx_create(catt_ctx** out, const catt_config* cfg) {
     set_error("no usable CUDA device (%s); libcatt_b200 has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
     return CATT_E_CUDA;
   }
-  if (cfg->device < 0 || cfg->device >= ndev) { set_error("device %d out of range (have %d)", cfg->device, ndev); return CATT_E_ARG; }
-  CATT_CUDA(cudaSetDevice(cfg->device));
+  // a group of GPUs for one sample: this context is rank 0 (devices[0]); the other ranks get contexts of their own below
+  const int ngpu = cfg->ngpu > 1 ? cfg->ngpu : 1;
+  if (ngpu > 16) { set_error("ngpu = %d exceeds the limit of 16 ranks", ngpu); return CATT_E_ARG; }
+  std::vector<int> devs((size_t)ngpu);
+  for (int r = 0; r < ngpu; r++) devs[r] = ngpu > 1 ? (cfg->devices ? cfg->devices[r] : r) : cfg->device;
+  for (int r = 0; r < ngpu; r++)
+    if (devs[r] < 0 || devs[r] >= ndev) { set_error("device %d out of range (have %d)", devs[r], ndev); return CATT_E_ARG; }
+  if (cfg->kmer != CATT_KMER_AUTO && (cfg->kmer < 1 || cfg->kmer > KMER_MAX)) {
+    // args["kmer"] is free in the reference's CLI (catt:18); the k-mer table here holds one 2-bit packed 64-bit word per k-mer
+    set_error("kmer = %d is outside the supported range 1..%d (or CATT_KMER_AUTO)", cfg->kmer, KMER_MAX);
+    return CATT_E_LIMIT;
+  }
+  const int device = devs[0];
+  CATT_CUDA(cudaSetDevice(device));
   std::unique_ptr<catt_ctx> c(new catt_ctx());
-  c->device = cfg->device;
+  c->device = device;
   cudaDeviceProp prop;
-  CATT_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  CATT_CUDA(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
   c->min_score = cfg->min_score; c->kmer = cfg->kmer; c->nthreads = cfg->julia_nthreads < 1 ? 1 : cfg->julia_nthreads;
   c->allow_v = cfg->allow_v; c->allow_j = cfg->allow_j;
@@ -863,13 +1034,46 @@ int catt_ctx_create(catt_ctx** out, const catt_config* cfg) {
   for (auto& ev : c->ev_h2d) CATT_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto& ev : c->ev_q) CATT_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   if ((rc = c->pin[PIN_CNT].ensure(1024))) return rc;
+  if (ngpu > 1) {
+    struct Guard { catt_ctx* c; bool armed = true; ~Guard() { if (armed) { for (auto* p : c->peers) catt_ctx_destroy(p); c->peers.clear(); for (auto* m : c->comms) delete m; c->comms.clear(); } } } guard{c.get()};
+    for (int r = 1; r < ngpu; r++) {
+      catt_config sub = *cfg;
+      sub.ngpu = 1; sub.devices = nullptr; sub.device = devs[r];
+      catt_ctx* p = nullptr;
+      if ((rc = catt_ctx_create(&p, &sub))) return rc;
+      c->peers.push_back(p);
+    }
+    CATT_CUDA(cudaSetDevice(device));
+    bool distinct = true;
+    for (int a = 0; a < ngpu; a++) for (int b = a + 1; b < ngpu; b++) distinct = distinct && devs[a] != devs[b];
+    const char* force = getenv("CATT_COMM");
+    const bool want_local = !distinct || (force && !strcmp(force, "local"));
+    if (!want_local) {
+      if ((rc = nccl_comms_create_all(ngpu, devs.data(), &c->comms))) return rc;
+      CATT_CUDA(cudaSetDevice(device));
+    } else {
+      c->lgroup = local_group_create(ngpu, devs.data());
+      if (!c->lgroup) { set_error("cannot create the in-process GPU group"); return CATT_E_ARG; }
+      for (int r = 0; r < ngpu; r++) c->comms.push_back(local_comm_create(c->lgroup, r));
+    }
+    guard.armed = false;
+  }
   *out = c.release();
   return CATT_OK;
 }
 
 void catt_ctx_destroy(catt_ctx* c) {
   if (!c) return;
+  for (size_t r = 0; r < c->comms.size(); r++) {       // communicators first (each on its own device), then the other ranks' contexts
+    cudaSetDevice(r ? c->peers[r - 1]->device : c->device);
+    delete c->comms[r];
+  }
+  c->comms.clear();
+  for (auto* p : c->peers) catt_ctx_destroy(p);
+  c->peers.clear();
   cudaSetDevice(c->device);
+  delete c->comm;
+  for (auto& b : c->sh) b.release();
   c->V.release(); c->J.release();
   free_align_buffers(c->ab[0]); free_align_buffers(c->ab[1]);
   for (auto& b : c->sb) b.release();
@@ -923,7 +1127,7 @@ int catt_run_reads(catt_ctx* c, int64_t n, const char* names, const int64_t* nam
   CATT_CUDA(cudaSetDevice(c->device));
   HostReads hr;
   hr.n = n; hr.names = names; hr.name_off = name_off; hr.seqs = seqs; hr.seq_off = seq_off; hr.quals = quals;
-  return run_all(c, hr, {0, n}, out);
+  return run_reads_dispatch(c, hr, {0, n}, out);
 }
 
 int catt_run_reads_files(catt_ctx* c, int64_t n, const char* names, const int64_t* name_off, const char* seqs, const int64_t* seq_off,
@@ -937,7 +1141,7 @@ int catt_run_reads_files(catt_ctx* c, int64_t n, const char* names, const int64_
   CATT_CUDA(cudaSetDevice(c->device));
   HostReads hr;
   hr.n = n; hr.names = names; hr.name_off = name_off; hr.seqs = seqs; hr.seq_off = seq_off; hr.quals = quals;
-  return run_all(c, hr, fs, out);
+  return run_reads_dispatch(c, hr, fs, out);
 }
 
 int catt_run_file(catt_ctx* c, const char* path, catt_result** out) {
@@ -949,6 +1153,7 @@ int catt_run_file(catt_ctx* c, const char* path, catt_result** out) {
 int catt_run_files(catt_ctx* c, int32_t nfiles, const char* const* paths, catt_result** out) {
   if (!c || !paths || !out || nfiles < 1) { set_error("catt_run_files: bad argument"); return CATT_E_ARG; }
   CATT_CUDA(cudaSetDevice(c->device));
+  if (!c->peers.empty()) return run_files_group(c, nfiles, paths, false, out);
   if (!getenv("CATT_HOST_PARSE")) {
     bool handled = false;
     int rc = run_files_device(c, nfiles, paths, out, &handled);
@@ -964,12 +1169,13 @@ int catt_run_files(catt_ctx* c, int32_t nfiles, const char* const* paths, catt_r
     fs.push_back(hr.n);
   }
   tr.lap("run_files: read + parse");
-  return run_all(c, hr, fs, out);
+  return run_reads_dispatch(c, hr, fs, out);
 }
 
 int catt_run_bam(catt_ctx* c, const char* path, catt_result** out) {
   if (!c || !path || !out) { set_error("catt_run_bam: null argument"); return CATT_E_ARG; }
   CATT_CUDA(cudaSetDevice(c->device));
+  if (!c->peers.empty()) { const char* one[1] = {path}; return run_files_group(c, 1, one, true, out); }
   if (!getenv("CATT_HOST_PARSE")) {                      // BGZF BAM: converted to FASTQ text group by group under the GPU pipeline
     bool handled = false;
     const char* paths[1] = {path};
@@ -981,7 +1187,7 @@ int catt_run_bam(catt_ctx* c, const char* path, catt_result** out) {
   int rc = parse_bam(path, &hr);
   if (rc) return rc;
   tr.lap("run_bam: inflate + decode");
-  return run_all(c, hr, {0, hr.n}, out);
+  return run_reads_dispatch(c, hr, {0, hr.n}, out);
 }
 
 int catt_inflate_file(const char* path, const char* out_path, int32_t* method) {
@@ -1039,6 +1245,34 @@ int catt_bam_to_fastq(const char* bam_path, const char* fastq_path) {
   }
   if (fclose(f) != 0) { set_error("cannot close %s", fastq_path); return CATT_E_IO; }
   return CATT_OK;
+}
+
+int catt_comm_id(uint8_t id[128]) {
+  if (!id) { set_error("catt_comm_id: null argument"); return CATT_E_ARG; }
+  return nccl_unique_id(id);
+}
+
+int catt_ctx_join(catt_ctx* c, int32_t nranks, int32_t rank, const uint8_t id[128]) {
+  if (!c || !id) { set_error("catt_ctx_join: null argument"); return CATT_E_ARG; }
+  if (!c->peers.empty() || c->comm) { set_error("catt_ctx_join: the context already belongs to a GPU group"); return CATT_E_ARG; }
+  CATT_CUDA(cudaSetDevice(c->device));
+  return nccl_comm_create_rank(nranks, rank, id, &c->comm);
+}
+
+int catt_run_reads_shard(catt_ctx* c, int64_t n_total, int64_t lo, int64_t n_local, const char* names, const int64_t* name_off, const char* seqs,
+                         const int64_t* seq_off, const char* quals, int32_t nfiles, const int64_t* file_start, catt_result** out) {
+  if (!c || !out || n_total < 0 || lo < 0 || n_local < 0 || nfiles < 1 || !file_start || (n_local > 0 && (!names || !name_off || !seqs || !seq_off))) {
+    set_error("catt_run_reads_shard: bad argument");
+    return CATT_E_ARG;
+  }
+  if (!c->comm) { set_error("catt_run_reads_shard: call catt_ctx_join first"); return CATT_E_ARG; }
+  std::vector<int64_t> fs(file_start, file_start + nfiles + 1);
+  if (fs.front() != 0 || fs.back() != n_total || !std::is_sorted(fs.begin(), fs.end())) { set_error("catt_run_reads_shard: file_start must run from 0 to n_total"); return CATT_E_ARG; }
+  CATT_CUDA(cudaSetDevice(c->device));
+  static const int64_t zero_off[1] = {0};
+  HostReads hr;
+  hr.n = n_local; hr.names = names; hr.name_off = n_local ? name_off : zero_off; hr.seqs = seqs; hr.seq_off = n_local ? seq_off : zero_off; hr.quals = quals;
+  return run_rank(c, c->comm, 0, n_total, lo, hr, fs, out);
 }
 
 int catt_result_info(const catt_result* r, catt_info* out) { if (!r || !out) return CATT_E_ARG; *out = r->info; return CATT_OK; }
@@ -1466,7 +1700,7 @@ int catt_finder(catt_ctx* c, int array_version, int64_t n, const char* seqs, con
   if ((rc = upload_reads(pr, n, &dr, c->stream))) return rc;
   int32_t* d_out = nullptr;
   CATT_CUDA(cudaMalloc(&d_out, std::max<int64_t>(n, 1) * 12));
-  rc = launch_finder_raw(dr.view(), c->d_finder, array_version, d_out, c->stream);
+  rc = launch_finder_raw(dr.view(), c->d_finder, array_version, d_out, c->sm_count, c->stream);
   if (!rc) {
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (e == cudaSuccess) e = cudaMemcpy(out3, d_out, n * 12, cudaMemcpyDeviceToHost);

@@ -134,20 +134,33 @@ __global__ void order_kernel(int64_t nm, const unsigned long long* __restrict__ 
                              uint32_t* __restrict__ ord_idx, uint32_t* __restrict__ ord_flag, uint32_t* __restrict__ pair_j,
                              unsigned long long* __restrict__ cnt) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= nm || !flag[r]) return;
-  const uint32_t F = kpos[nm];
-  const uint32_t idx = (uint32_t)sorted[r];
-  const uint32_t y = chunk_pos(kpos[r] + 1, F, (uint32_t)T);
-  const uint32_t slot = slot_of[idx];
-  const bool shared = minv[slot] != INF && minj[slot] != INF;
-  ord_idx[y] = idx;
-  ord_flag[y] = !shared;
-  if (which == 1 && shared) {
-    const unsigned long long p = atomicAdd(&cnt[C_NP], 1ull);
-    pair_j[p] = idx;
-    const char* s = nd.s + nd.beg[idx];
-    atomicMax(&cnt[C_MAXNAME], (unsigned long long)trimmed_len(s, (int)(nd.end[idx] - nd.beg[idx])));
+  const bool live = r < nm && flag[r];
+  bool pair = false;
+  uint32_t idx = 0;
+  if (live) {
+    const uint32_t F = kpos[nm];
+    idx = (uint32_t)sorted[r];
+    const uint32_t y = chunk_pos(kpos[r] + 1, F, (uint32_t)T);
+    const uint32_t slot = slot_of[idx];
+    const bool shared = minv[slot] != INF && minj[slot] != INF;
+    ord_idx[y] = idx;
+    ord_flag[y] = !shared;
+    pair = which == 1 && shared;
   }
+  // the J records of shared QNAMEs seed the both-mapped pairs: one atomic per warp (a counter every thread hits serialises)
+  const unsigned bal = __ballot_sync(FULL, pair);
+  if (!bal) return;
+  const int lane = threadIdx.x & 31, leader = __ffs(bal) - 1;
+  unsigned long long base = 0;
+  unsigned nl = 0;
+  if (pair) {
+    const char* s = nd.s + nd.beg[idx];
+    nl = (unsigned)trimmed_len(s, (int)(nd.end[idx] - nd.beg[idx]));
+  }
+  nl = __reduce_max_sync(FULL, nl);
+  if (lane == leader) { base = atomicAdd(&cnt[C_NP], (unsigned long long)__popc(bal)); atomicMax(&cnt[C_MAXNAME], (unsigned long long)nl); }
+  base = __shfl_sync(FULL, base, leader);
+  if (pair) pair_j[base + __popc(bal & ((1u << lane) - 1))] = idx;
 }
 
 __global__ void collect_kernel(const uint32_t* kpos_v, int64_t nm_v, const uint32_t* kpos_j, int64_t nm_j, const uint32_t* opos_v,
@@ -257,6 +270,10 @@ struct StrSrc {
   int64_t M, vpart;                               // all Vpart/Jpart reads; the first vpart are Vpart
   const uint32_t* map; int64_t E;                 // output entry e is read map[e] (map == nullptr: every read, E == M)
   const int64_t* q_entry_off;                     // != nullptr: quality strings were gathered per output entry (quals + q_entry_off[e])
+  // one sample over several GPUs: this GPU materialises ITS reads at their positions in the global lists - read m of `desc` is
+  // read gm[m] of [Vpart; Jpart], its output entry is epos[gm[m]] and the string offsets are indexed by gm[m] (nullptr: one GPU)
+  const uint32_t* gm = nullptr; const uint32_t* epos = nullptr;
+  int64_t ordinal_base = 0;                       // global input index of this GPU's first read
 };
 __device__ __forceinline__ int64_t str_read(const StrSrc& S, int64_t e) { return S.map ? (int64_t)S.map[e] : e; }
 
@@ -312,12 +329,14 @@ __global__ void __launch_bounds__(MW * 32) materialise_kernel(StrSrc S, ReadsDev
     int n_ext, c_off, c_len, slen, qlen, base_q;
     str_dims(S, m, &n_ext, &c_off, &c_len, &slen, &qlen, &base_q);
     const ExtendOut* x = (p.xi >= 0 && S.xout) ? &S.xout[p.xi] : nullptr;
-    const int side = m < S.vpart ? 0 : 1;
+    int64_t oe = e_, oi = e_;                                      // output entry, index of its string offsets
+    if (S.gm) { oi = (int64_t)S.gm[m]; oe = (int64_t)S.epos[oi]; }
+    const int side = p.kind == 1;                                  // J-side reads form Jpart, everything else Vpart
     const int lead = side == 1 ? n_ext : 0;                       // a left extension is prepended
     const int len = reads.len[p.read];
     const uint32_t* __restrict__ w = reads.words + reads.off[p.read];
     const uint32_t* __restrict__ nm = w + read_base_words(len);
-    char* s = seq_arena + soff[e_];
+    char* s = seq_arena + soff[oi];
     for (int i = lane; i <= slen; i += 32) {
       char ch = 0;
       if (i < slen) {
@@ -341,7 +360,7 @@ __global__ void __launch_bounds__(MW * 32) materialise_kernel(StrSrc S, ReadsDev
     const int src0 = p.kind == 1 ? 0 : p.seq_off;
     const int a0 = c_off >= 0 ? c_off : 0;
     const char* rq = S.quals ? (S.q_entry_off ? S.quals + S.q_entry_off[e_] : S.quals + S.seq_off[p.read]) : nullptr;
-    char* q = qual_arena + qoff[e_];
+    char* q = qual_arena + qoff[oi];
     for (int i = lane; i <= qlen; i += 32) {
       char ch = 0;
       if (i < qlen) {
@@ -356,12 +375,12 @@ __global__ void __launch_bounds__(MW * 32) materialise_kernel(StrSrc S, ReadsDev
     }
     if (lane == 0) {
       catt_read rd;
-      rd.seq = host_seq + soff[e_]; rd.qual = host_qual + qoff[e_]; rd.seq_len = slen; rd.qual_len = qlen;
+      rd.seq = host_seq + soff[oi]; rd.qual = host_qual + qoff[oi]; rd.seq_len = slen; rd.qual_len = qlen;
       rd.v_id = p.v_id; rd.j_id = p.j_id; rd.cdr3_off = c_off; rd.cdr3_len = c_off >= 0 ? c_len : 0;
-      rd.ordinal = (int32_t)p.read; rd.able = 1;
+      rd.ordinal = (int32_t)(S.ordinal_base + p.read); rd.able = 1;
       rd.flags = (uint8_t)((p.kind == 0 ? 1 : p.kind == 1 ? 2 : 4) | ((c_off >= 0 && c_off + c_len > qfull) ? 8 : 0));   // 8: reference BoundsError
       rd.pad_[0] = 0; rd.pad_[1] = 0;
-      part[e_] = rd;
+      part[oe] = rd;
     }
   }
 }
@@ -377,6 +396,16 @@ template <class T> int ensure(catt_ctx* c, int slot, int64_t count, T** out) {
 int ensure_cub(catt_ctx* c, size_t need) { return c->sb[SB_CUB].ensure(std::max<size_t>(need, 256)); }
 
 int scan_u32(catt_ctx* c, const uint32_t* in, uint32_t* out, int64_t count, cudaStream_t st) {
+  size_t need = 0;
+  CATT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, in, out, count, st));
+  int rc = ensure_cub(c, need);
+  if (rc) return rc;
+  need = c->sb[SB_CUB].cap;
+  CATT_CUDA(cub::DeviceScan::ExclusiveSum(c->sb[SB_CUB].p, need, in, out, count, st));
+  return CATT_OK;
+}
+
+int scan_u64(catt_ctx* c, const unsigned long long* in, unsigned long long* out, int64_t count, cudaStream_t st) {
   size_t need = 0;
   CATT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, in, out, count, st));
   int rc = ensure_cub(c, need);
@@ -488,12 +517,184 @@ int upload_names(catt_ctx* c, int64_t n, const char* names, const int64_t* name_
   if (n == 0) return CATT_OK;
   char* d_names; int64_t* d_off;
   int rc;
-  const int64_t name_bytes = name_off[n];
+  // name_off may be a view into a larger sample (one rank's block of a GPU group): only this block's bytes are uploaded, the
+  // device copy is addressed with the caller's absolute offsets
+  const int64_t base = name_off[0], name_bytes = name_off[n] - base;
   if ((rc = ensure(c, SB_NAMES, name_bytes + 16, &d_names)) || (rc = ensure(c, SB_NAME_OFF, n + 1, &d_off))) return rc;
-  CATT_CUDA(cudaMemcpyAsync(d_names, names, (size_t)name_bytes, cudaMemcpyHostToDevice, st));
+  CATT_CUDA(cudaMemcpyAsync(d_names, names + base, (size_t)name_bytes, cudaMemcpyHostToDevice, st));
   CATT_CUDA(cudaMemcpyAsync(d_off, name_off, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
   if (info) info->bytes_h2d += name_bytes + (n + 1) * 8;
-  out->s = d_names; out->beg = d_off; out->end = d_off + 1;
+  out->s = d_names - base; out->beg = d_off; out->end = d_off + 1;
+  return CATT_OK;
+}
+
+// ---- per-file ordering: names -> SAM order -> QNAME dedup -> share_name -> work items --------------------------------------
+// (read_alignrs, catt.jl:210-326, up to the point where records become Myreads)
+struct OrderScratch {
+  uint32_t* slot_of; int32_t* owner; uint32_t* minr[2]; uint64_t cap;
+  unsigned long long *keys_a, *sorted[2];
+  uint32_t *flag, *kpos[2], *ord_idx[2], *ord_flag[2], *opos[2], *pair_a, *pair_b;
+};
+struct OrderOut { int64_t F[2], n_v, n_p, n_j; };
+
+static int order_alloc(catt_ctx* c, int64_t max_reads, int64_t max_v, int64_t max_j, OrderScratch* S) {
+  int rc;
+  uint64_t cap = 1024;
+  while (cap < (uint64_t)(max_v + max_j) * 2 + 2) cap <<= 1;
+  if (cap > 0x80000000ull) { set_error("too many mapped reads for the QNAME table"); return CATT_E_LIMIT; }
+  S->cap = cap;
+  if ((rc = ensure(c, SB_SLOT_OF, max_reads, &S->slot_of)) || (rc = ensure(c, SB_OWNER, (int64_t)cap, &S->owner)) ||
+      (rc = ensure(c, SB_MINV, (int64_t)cap, &S->minr[0])) || (rc = ensure(c, SB_MINJ, (int64_t)cap, &S->minr[1]))) return rc;
+  const int64_t nmax = std::max(max_v, max_j);
+  if ((rc = ensure(c, SB_KEYS_A, nmax, &S->keys_a)) || (rc = ensure(c, SB_SORT_V, max_v, &S->sorted[0])) ||
+      (rc = ensure(c, SB_SORT_J, max_j, &S->sorted[1])) || (rc = ensure(c, SB_FLAG, nmax + 1, &S->flag)) || (rc = ensure(c, SB_KPOS_V, max_v + 1, &S->kpos[0])) ||
+      (rc = ensure(c, SB_KPOS_J, max_j + 1, &S->kpos[1])) || (rc = ensure(c, SB_ORD_IDX_V, max_v + 1, &S->ord_idx[0])) ||
+      (rc = ensure(c, SB_ORD_IDX_J, max_j + 1, &S->ord_idx[1])) || (rc = ensure(c, SB_ORD_FLAG_V, max_v + 1, &S->ord_flag[0])) ||
+      (rc = ensure(c, SB_ORD_FLAG_J, max_j + 1, &S->ord_flag[1])) ||
+      (rc = ensure(c, SB_OPOS_V, max_v + 1, &S->opos[0])) || (rc = ensure(c, SB_OPOS_J, max_j + 1, &S->opos[1])) ||
+      (rc = ensure(c, SB_PAIR_A, max_j + 1, &S->pair_a)) || (rc = ensure(c, SB_PAIR_B, max_j + 1, &S->pair_b))) return rc;
+  return CATT_OK;
+}
+
+// One input file: nf reads (records rec[0/1], names nd, lengths len, all indexed 0..nf), nm[] of them mapped per reference set.
+// Writes the file's work items [V part | both-mapped | J part] in the reference's processing order to `seg` (read indices
+// = read_base + index), updates k (args["kmer"], catt.jl:156-172) and the_ERR / the log counters in `info`.
+static int order_file(catt_ctx* c, const OrderScratch& S, int64_t nf, const NamesDev& nd, const catt_aln* const rec[2], const int32_t* len,
+                      const int64_t nm[2], uint32_t read_base, int* kmer, catt_info& info, unsigned long long* cnt, unsigned long long* hcnt,
+                      ExtractItem* seg, int64_t seg_cap, OrderOut* out, int* launches) {
+  cudaStream_t st = c->stream;
+  int rc;
+  int& k = *kmer;
+  CATT_CUDA(cudaMemsetAsync(cnt, 0, C_COUNT * sizeof(unsigned long long), st));
+  if (nm[0] + nm[1] > 0) {
+    CATT_CUDA(cudaMemsetAsync(S.owner, 0xff, S.cap * sizeof(int32_t), st));
+    CATT_CUDA(cudaMemsetAsync(S.minr[0], 0xff, S.cap * sizeof(uint32_t), st));
+    CATT_CUDA(cudaMemsetAsync(S.minr[1], 0xff, S.cap * sizeof(uint32_t), st));
+    name_kernel<<<nblk(nf), 256, 0, st>>>(nf, nd, rec[0], rec[1], S.owner, (uint32_t)(S.cap - 1), S.slot_of);
+    CATT_CUDA(cudaGetLastError());
+    *launches += 1;
+  }
+  // per reference set: sorted final SAM order, QNAME dedup
+  for (int which = 0; which < 2; which++) {
+    if (nm[which] == 0) continue;
+    key_kernel<<<nblk(nf), 256, 0, st>>>(nf, rec[which], S.keys_a, cnt + C_NMAP_V + which);
+    CATT_CUDA(cudaGetLastError());
+    size_t need = 0;
+    CATT_CUDA(cub::DeviceRadixSort::SortKeysDescending(nullptr, need, S.keys_a, S.sorted[which], nm[which], 0, 61, st));
+    if ((rc = ensure_cub(c, need))) return rc;
+    need = c->sb[SB_CUB].cap;
+    CATT_CUDA(cub::DeviceRadixSort::SortKeysDescending(c->sb[SB_CUB].p, need, S.keys_a, S.sorted[which], nm[which], 0, 61, st));
+    minrank_kernel<<<nblk(nm[which]), 256, 0, st>>>(nm[which], S.sorted[which], S.slot_of, S.minr[which]);
+    CATT_CUDA(cudaGetLastError());
+    *launches += 10;     // key, radix sort (histogram + 7 onesweep passes), minrank
+  }
+  for (int which = 0; which < 2; which++) {
+    if (nm[which] == 0) continue;
+    flag_kernel<<<nblk(nm[which] + 1), 256, 0, st>>>(nm[which], S.sorted[which], S.slot_of, S.minr[which], rec[which], len, which == 0, S.flag, cnt);
+    CATT_CUDA(cudaGetLastError());
+    if ((rc = scan_u32(c, S.flag, S.kpos[which], nm[which] + 1, st))) return rc;
+    CATT_CUDA(cudaMemsetAsync(S.ord_flag[which], 0, (size_t)(nm[which] + 1) * sizeof(uint32_t), st));
+    order_kernel<<<nblk(nm[which]), 256, 0, st>>>(nm[which], S.sorted[which], S.flag, S.kpos[which], c->nthreads, S.slot_of, S.minr[0], S.minr[1], which, nd,
+                                                  S.ord_idx[which], S.ord_flag[which], S.pair_a, cnt);
+    CATT_CUDA(cudaGetLastError());
+    if ((rc = scan_u32(c, S.ord_flag[which], S.opos[which], nm[which] + 1, st))) return rc;
+    *launches += 6;
+  }
+  collect_kernel<<<1, 1, 0, st>>>(S.kpos[0], nm[0], S.kpos[1], nm[1], S.opos[0], S.opos[1], cnt);
+  CATT_CUDA(cudaGetLastError());
+  *launches += 1;
+  CATT_CUDA(cudaMemcpyAsync(hcnt, cnt, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CATT_CUDA(cudaStreamSynchronize(st));
+  if ((int64_t)hcnt[C_NMAP_V] != nm[0] || (int64_t)hcnt[C_NMAP_J] != nm[1]) {
+    set_error("stage B: mapped-record count mismatch (V %llu vs %lld, J %llu vs %lld)", hcnt[C_NMAP_V], (long long)nm[0], hcnt[C_NMAP_J], (long long)nm[1]);
+    return CATT_E_ARG;
+  }
+  const int64_t F[2] = {(int64_t)hcnt[C_F_V], (int64_t)hcnt[C_F_J]};
+  const int64_t n_v = (int64_t)hcnt[C_NV], n_j = (int64_t)hcnt[C_NJ], n_p = (int64_t)hcnt[C_NP];
+  info.v_final += F[0]; info.j_final += F[1]; info.share += n_p;
+  // get_kmer_fromsam / get_err_fromsam on this file's final V list, as samtools stats prints them
+  {
+    const uint64_t tot = hcnt[C_SUM_LEN], snm = hcnt[C_SUM_NM], smi = hcnt[C_SUM_MI];
+    const float avg = F[0] == 0 ? 0.f : (float)(tot / (uint64_t)F[0]);       // samtools: integer division, printed %.0f
+    char buf[64];
+    snprintf(buf, sizeof buf, "%.0f", avg);
+    const double avg_r = atof(buf);
+    info.avg_len = avg_r;
+    if (k == CATT_KMER_AUTO) {
+      if (avg_r >= 50) k = 15;
+      if (avg_r >= 75) k = 19;
+      if (avg_r >= 100) k = 23;
+      if (avg_r >= 150) k = 25;
+    }
+    const float er = smi ? (float)snm / (float)smi : 0.f;
+    snprintf(buf, sizeof buf, "%e", (double)er);
+    info.the_err = atof(buf);
+    if (!(info.the_err == info.the_err)) info.the_err = 0.0;
+  }
+  // both-mapped pairs in QNAME order: LSD radix over 8-byte digits of the trimmed name
+  uint32_t* pairs = S.pair_a;
+  if (n_p > 1) {
+    unsigned long long *pk_a, *pk_b;
+    if ((rc = ensure(c, SB_PKEY_A, n_p, &pk_a)) || (rc = ensure(c, SB_PKEY_B, n_p, &pk_b))) return rc;
+    const int digits = std::max(1, (int)((hcnt[C_MAXNAME] + 7) / 8));
+    uint32_t* other = S.pair_b;
+    for (int d = digits - 1; d >= 0; d--) {
+      pair_key_kernel<<<nblk(n_p), 256, 0, st>>>(n_p, pairs, nd, d, pk_a);
+      CATT_CUDA(cudaGetLastError());
+      size_t need = 0;
+      CATT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, pk_a, pk_b, pairs, other, n_p, 0, 64, st));
+      if ((rc = ensure_cub(c, need))) return rc;
+      need = c->sb[SB_CUB].cap;
+      CATT_CUDA(cub::DeviceRadixSort::SortPairs(c->sb[SB_CUB].p, need, pk_a, pk_b, pairs, other, n_p, 0, 64, st));
+      std::swap(pairs, other);
+      *launches += 10;
+    }
+  }
+  // work items in the reference's processing order: [V part | both-mapped | J part] of this file
+  const int64_t nseg = n_v + n_p + n_j;
+  if (nseg > seg_cap) { set_error("stage B: item count exceeds the mapped-record bound"); return CATT_E_ARG; }
+  if (F[0] > 0) {
+    part_item_kernel<<<nblk(F[0]), 256, 0, st>>>(F[0], S.ord_idx[0], S.ord_flag[0], S.opos[0], rec[0], 0, read_base, seg);
+    CATT_CUDA(cudaGetLastError());
+    *launches += 1;
+  }
+  if (n_p > 0) {
+    pair_item_kernel<<<nblk(n_p), 256, 0, st>>>(n_p, pairs, S.slot_of, S.minr[0], S.sorted[0], rec[0], rec[1], read_base, seg + n_v);
+    CATT_CUDA(cudaGetLastError());
+    *launches += 1;
+  }
+  if (F[1] > 0) {
+    part_item_kernel<<<nblk(F[1]), 256, 0, st>>>(F[1], S.ord_idx[1], S.ord_flag[1], S.opos[1], rec[1], 1, read_base, seg + n_v + n_p);
+    CATT_CUDA(cudaGetLastError());
+    *launches += 1;
+  }
+  out->F[0] = F[0]; out->F[1] = F[1]; out->n_v = n_v; out->n_p = n_p; out->n_j = n_j;
+  return CATT_OK;
+}
+
+// only_cdr3 with host buffers: gather the quality strings of the E surviving reads (read indices d_rid, local to h_quals) on the
+// host and upload them; S.quals / S.q_entry_off then index them per output entry
+static int gather_host_quals(catt_ctx* c, const DeviceQuals& dq, const uint32_t* d_rid, int64_t E, StrSrc* S, catt_info& info, cudaStream_t st) {
+  int rc;
+  char* d_gather; int64_t* d_entry;
+  if ((rc = c->pin[PIN_QRID].ensure((size_t)E * 4)) || (rc = c->pin[PIN_QENTRY].ensure((size_t)(E + 1) * 8))) return rc;
+  uint32_t* h_rid = c->pin[PIN_QRID].as<uint32_t>();
+  int64_t* h_entry = c->pin[PIN_QENTRY].as<int64_t>();
+  CATT_CUDA(cudaMemcpyAsync(h_rid, d_rid, (size_t)E * 4, cudaMemcpyDeviceToHost, st));
+  CATT_CUDA(cudaStreamSynchronize(st));
+  h_entry[0] = 0;
+  for (int64_t e = 0; e < E; e++) h_entry[e + 1] = h_entry[e] + (dq.host_seq_off[h_rid[e] + 1] - dq.host_seq_off[h_rid[e]]);
+  const int64_t gbytes = h_entry[E];
+  if ((rc = c->pin[PIN_QGATHER].ensure((size_t)gbytes + 16)) || (rc = ensure(c, SB_QGATHER, gbytes + 16, &d_gather)) ||
+      (rc = ensure(c, SB_QENTRY, E + 1, &d_entry))) return rc;
+  char* h_gather = c->pin[PIN_QGATHER].as<char>();
+  #pragma omp parallel for schedule(static)
+  for (int64_t e = 0; e < E; e++)
+    memcpy(h_gather + h_entry[e], dq.host_quals + dq.host_seq_off[h_rid[e]], (size_t)(h_entry[e + 1] - h_entry[e]));
+  CATT_CUDA(cudaMemcpyAsync(d_gather, h_gather, (size_t)gbytes, cudaMemcpyHostToDevice, st));
+  CATT_CUDA(cudaMemcpyAsync(d_entry, h_entry, (size_t)(E + 1) * 8, cudaMemcpyHostToDevice, st));
+  info.bytes_h2d += gbytes + (E + 1) * 8; info.bytes_d2h += E * 4;
+  S->quals = d_gather; S->q_entry_off = d_entry;
   return CATT_OK;
 }
 
@@ -515,22 +716,8 @@ int stage_b(catt_ctx* c, int64_t n, const NamesDev& names, const ReadsDev& reads
     max_v = std::max(max_v, fh.v[f]); max_j = std::max(max_j, fh.j[f]); max_reads = std::max(max_reads, fh.start[f + 1] - fh.start[f]);
   }
   // ---- per-file QNAME classes; work items of all files accumulate in `items` (n_items <= mapped records)
-  uint32_t* slot_of; int32_t* owner; uint32_t* minr[2];
-  uint64_t cap = 1024;
-  while (cap < (uint64_t)(max_v + max_j) * 2 + 2) cap <<= 1;
-  if (cap > 0x80000000ull) { set_error("too many mapped reads for the QNAME table"); return CATT_E_LIMIT; }
-  if ((rc = ensure(c, SB_SLOT_OF, max_reads, &slot_of)) || (rc = ensure(c, SB_OWNER, (int64_t)cap, &owner)) ||
-      (rc = ensure(c, SB_MINV, (int64_t)cap, &minr[0])) || (rc = ensure(c, SB_MINJ, (int64_t)cap, &minr[1]))) return rc;
-  unsigned long long *keys_a, *sorted[2];
-  uint32_t *flag, *kpos[2], *ord_idx[2], *ord_flag[2], *opos[2], *pair_a, *pair_b;
-  const int64_t nmax = std::max(max_v, max_j);
-  if ((rc = ensure(c, SB_KEYS_A, nmax, &keys_a)) || (rc = ensure(c, SB_SORT_V, max_v, &sorted[0])) ||
-      (rc = ensure(c, SB_SORT_J, max_j, &sorted[1])) || (rc = ensure(c, SB_FLAG, nmax + 1, &flag)) || (rc = ensure(c, SB_KPOS_V, max_v + 1, &kpos[0])) ||
-      (rc = ensure(c, SB_KPOS_J, max_j + 1, &kpos[1])) || (rc = ensure(c, SB_ORD_IDX_V, max_v + 1, &ord_idx[0])) ||
-      (rc = ensure(c, SB_ORD_IDX_J, max_j + 1, &ord_idx[1])) || (rc = ensure(c, SB_ORD_FLAG_V, max_v + 1, &ord_flag[0])) ||
-      (rc = ensure(c, SB_ORD_FLAG_J, max_j + 1, &ord_flag[1])) ||
-      (rc = ensure(c, SB_OPOS_V, max_v + 1, &opos[0])) || (rc = ensure(c, SB_OPOS_J, max_j + 1, &opos[1])) ||
-      (rc = ensure(c, SB_PAIR_A, max_j + 1, &pair_a)) || (rc = ensure(c, SB_PAIR_B, max_j + 1, &pair_b))) return rc;
+  OrderScratch OS;
+  if ((rc = order_alloc(c, max_reads, max_v, max_j, &OS))) return rc;
   ExtractItem* items; ExtractOut* eout; uint32_t *kflag0, *kflag1, *kpos0, *kpos1, *pflag, *xpos;
   if ((rc = ensure(c, SB_ITEMS, tot_hits, &items)) || (rc = ensure(c, SB_EOUT, tot_hits, &eout)) || (rc = ensure(c, SB_KFLAG, tot_hits + 1, &kflag0)) ||
       (rc = ensure(c, SB_KFLAG1, tot_hits + 1, &kflag1)) || (rc = ensure(c, SB_KPOS2, tot_hits + 1, &kpos0)) || (rc = ensure(c, SB_KPOS3, tot_hits + 1, &kpos1)) ||
@@ -546,114 +733,13 @@ int stage_b(catt_ctx* c, int64_t n, const NamesDev& names, const ReadsDev& reads
     const int64_t nm[2] = {fh.v[f], fh.j[f]};
     const catt_aln* rec[2] = {c->recs_all[0].as<catt_aln>() + lo, c->recs_all[1].as<catt_aln>() + lo};
     const NamesDev nd{names.s, names.beg + lo, names.end + lo};
-    CATT_CUDA(cudaMemsetAsync(cnt, 0, C_COUNT * sizeof(unsigned long long), st));
     CATT_CUDA(cudaEventRecord(c->ev[5], st));
-    if (nm[0] + nm[1] > 0) {
-      CATT_CUDA(cudaMemsetAsync(owner, 0xff, cap * sizeof(int32_t), st));
-      CATT_CUDA(cudaMemsetAsync(minr[0], 0xff, cap * sizeof(uint32_t), st));
-      CATT_CUDA(cudaMemsetAsync(minr[1], 0xff, cap * sizeof(uint32_t), st));
-      name_kernel<<<nblk(nf), 256, 0, st>>>(nf, nd, rec[0], rec[1], owner, (uint32_t)(cap - 1), slot_of);
-      CATT_CUDA(cudaGetLastError());
-      *launches += 1;
-    }
-    // per reference set: sorted final SAM order, QNAME dedup
-    for (int which = 0; which < 2; which++) {
-      if (nm[which] == 0) continue;
-      key_kernel<<<nblk(nf), 256, 0, st>>>(nf, rec[which], keys_a, cnt + C_NMAP_V + which);
-      CATT_CUDA(cudaGetLastError());
-      size_t need = 0;
-      CATT_CUDA(cub::DeviceRadixSort::SortKeysDescending(nullptr, need, keys_a, sorted[which], nm[which], 0, 61, st));
-      if ((rc = ensure_cub(c, need))) return rc;
-      need = c->sb[SB_CUB].cap;
-      CATT_CUDA(cub::DeviceRadixSort::SortKeysDescending(c->sb[SB_CUB].p, need, keys_a, sorted[which], nm[which], 0, 61, st));
-      minrank_kernel<<<nblk(nm[which]), 256, 0, st>>>(nm[which], sorted[which], slot_of, minr[which]);
-      CATT_CUDA(cudaGetLastError());
-      *launches += 10;     // key, radix sort (histogram + 7 onesweep passes), minrank
-    }
-    for (int which = 0; which < 2; which++) {
-      if (nm[which] == 0) continue;
-      flag_kernel<<<nblk(nm[which] + 1), 256, 0, st>>>(nm[which], sorted[which], slot_of, minr[which], rec[which], reads.len + lo, which == 0, flag, cnt);
-      CATT_CUDA(cudaGetLastError());
-      if ((rc = scan_u32(c, flag, kpos[which], nm[which] + 1, st))) return rc;
-      CATT_CUDA(cudaMemsetAsync(ord_flag[which], 0, (size_t)(nm[which] + 1) * sizeof(uint32_t), st));
-      order_kernel<<<nblk(nm[which]), 256, 0, st>>>(nm[which], sorted[which], flag, kpos[which], c->nthreads, slot_of, minr[0], minr[1], which, nd,
-                                                    ord_idx[which], ord_flag[which], pair_a, cnt);
-      CATT_CUDA(cudaGetLastError());
-      if ((rc = scan_u32(c, ord_flag[which], opos[which], nm[which] + 1, st))) return rc;
-      *launches += 6;
-    }
-    collect_kernel<<<1, 1, 0, st>>>(kpos[0], nm[0], kpos[1], nm[1], opos[0], opos[1], cnt);
-    CATT_CUDA(cudaGetLastError());
-    *launches += 1;
-    CATT_CUDA(cudaMemcpyAsync(hcnt, cnt, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CATT_CUDA(cudaStreamSynchronize(st));
-    if ((int64_t)hcnt[C_NMAP_V] != nm[0] || (int64_t)hcnt[C_NMAP_J] != nm[1]) {
-      set_error("stage B: mapped-record count mismatch (V %llu vs %lld, J %llu vs %lld)", hcnt[C_NMAP_V], (long long)nm[0], hcnt[C_NMAP_J], (long long)nm[1]);
-      return CATT_E_ARG;
-    }
-    const int64_t F[2] = {(int64_t)hcnt[C_F_V], (int64_t)hcnt[C_F_J]};
-    const int64_t n_v = (int64_t)hcnt[C_NV], n_j = (int64_t)hcnt[C_NJ], n_p = (int64_t)hcnt[C_NP];
-    info.v_final += F[0]; info.j_final += F[1]; info.share += n_p;
-    // get_kmer_fromsam / get_err_fromsam on this file's final V list, as samtools stats prints them
-    {
-      const uint64_t tot = hcnt[C_SUM_LEN], snm = hcnt[C_SUM_NM], smi = hcnt[C_SUM_MI];
-      const float avg = F[0] == 0 ? 0.f : (float)(tot / (uint64_t)F[0]);       // samtools: integer division, printed %.0f
-      char buf[64];
-      snprintf(buf, sizeof buf, "%.0f", avg);
-      const double avg_r = atof(buf);
-      info.avg_len = avg_r;
-      if (k == CATT_KMER_AUTO) {
-        if (avg_r >= 50) k = 15;
-        if (avg_r >= 75) k = 19;
-        if (avg_r >= 100) k = 23;
-        if (avg_r >= 150) k = 25;
-      }
-      const float er = smi ? (float)snm / (float)smi : 0.f;
-      snprintf(buf, sizeof buf, "%e", (double)er);
-      info.the_err = atof(buf);
-      if (!(info.the_err == info.the_err)) info.the_err = 0.0;
-    }
-    // both-mapped pairs in QNAME order: LSD radix over 8-byte digits of the trimmed name
-    uint32_t* pairs = pair_a;
-    if (n_p > 1) {
-      unsigned long long *pk_a, *pk_b;
-      if ((rc = ensure(c, SB_PKEY_A, n_p, &pk_a)) || (rc = ensure(c, SB_PKEY_B, n_p, &pk_b))) return rc;
-      const int digits = std::max(1, (int)((hcnt[C_MAXNAME] + 7) / 8));
-      uint32_t* other = pair_b;
-      for (int d = digits - 1; d >= 0; d--) {
-        pair_key_kernel<<<nblk(n_p), 256, 0, st>>>(n_p, pairs, nd, d, pk_a);
-        CATT_CUDA(cudaGetLastError());
-        size_t need = 0;
-        CATT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, pk_a, pk_b, pairs, other, n_p, 0, 64, st));
-        if ((rc = ensure_cub(c, need))) return rc;
-        need = c->sb[SB_CUB].cap;
-        CATT_CUDA(cub::DeviceRadixSort::SortPairs(c->sb[SB_CUB].p, need, pk_a, pk_b, pairs, other, n_p, 0, 64, st));
-        std::swap(pairs, other);
-        *launches += 10;
-      }
-    }
-    // work items in the reference's processing order: [V part | both-mapped | J part] of this file
-    const int64_t nseg = n_v + n_p + n_j;
-    if (n_items + nseg > tot_hits) { set_error("stage B: item count exceeds the mapped-record bound"); return CATT_E_ARG; }
-    ExtractItem* seg = items + n_items;
-    if (F[0] > 0) {
-      part_item_kernel<<<nblk(F[0]), 256, 0, st>>>(F[0], ord_idx[0], ord_flag[0], opos[0], rec[0], 0, (uint32_t)lo, seg);
-      CATT_CUDA(cudaGetLastError());
-      *launches += 1;
-    }
-    if (n_p > 0) {
-      pair_item_kernel<<<nblk(n_p), 256, 0, st>>>(n_p, pairs, slot_of, minr[0], sorted[0], rec[0], rec[1], (uint32_t)lo, seg + n_v);
-      CATT_CUDA(cudaGetLastError());
-      *launches += 1;
-    }
-    if (F[1] > 0) {
-      part_item_kernel<<<nblk(F[1]), 256, 0, st>>>(F[1], ord_idx[1], ord_flag[1], opos[1], rec[1], 1, (uint32_t)lo, seg + n_v + n_p);
-      CATT_CUDA(cudaGetLastError());
-      *launches += 1;
-    }
+    OrderOut oo;
+    if ((rc = order_file(c, OS, nf, nd, rec, reads.len + lo, nm, (uint32_t)lo, &k, info, cnt, hcnt, items + n_items, tot_hits - n_items, &oo, launches))) return rc;
+    const int64_t nseg = oo.n_v + oo.n_p + oo.n_j;
     CATT_CUDA(cudaEventRecord(c->ev[6], st));
     // K5: assignV/J, real_score, clipping, finder! with the k that is current for this file (catt.jl:279,301)
-    if ((rc = launch_extract(c->V.dev, c->J.dev, reads, c->d_finder, seg, eout + n_items, nseg, k, c->allow_v, c->allow_j, st, launches))) return rc;
+    if ((rc = launch_extract(c->V.dev, c->J.dev, reads, c->d_finder, items + n_items, eout + n_items, nseg, k, c->allow_v, c->allow_j, c->sm_count, st, launches))) return rc;
     CATT_CUDA(cudaEventRecord(c->ev[7], st));
     CATT_CUDA(cudaStreamSynchronize(st));
     { float a = 0, b = 0; cudaEventElapsedTime(&a, c->ev[5], c->ev[6]); cudaEventElapsedTime(&b, c->ev[6], c->ev[7]); ms_order += a; ms_extract += b; }
@@ -688,21 +774,20 @@ int stage_b(catt_ctx* c, int64_t n, const NamesDev& names, const ReadsDev& reads
 
   // ---- K6/K7: k-mer table + extension of the partial reads
   ExtendOut* xout = nullptr;
-  const bool run_pool = M > 0 && k <= 31 && n_partial > 0;
+  const bool run_pool = M > 0 && k <= KMER_MAX && n_partial > 0;
   CATT_CUDA(cudaEventRecord(c->ev[5], st));
   if (run_pool) {
-    uint64_t slots = 1024;
-    while (slots < (uint64_t)M * 11ull * 2ull) slots <<= 1;
+    const uint64_t slots = std::max<uint64_t>(1024, (uint64_t)M * 11ull * 2ull);
     KmerTable tab{};
     if ((rc = ensure(c, SB_TAB_KEYS, (int64_t)slots, &tab.keys)) || (rc = ensure(c, SB_TAB_VALS, (int64_t)slots, &tab.vals)) ||
         (rc = ensure(c, SB_XOUT, n_partial, &xout))) return rc;
-    tab.mask = slots - 1;
+    tab.sub_slots = slots; tab.nsub = 1;
     CATT_CUDA(cudaMemsetAsync(tab.keys, 0xff, slots * sizeof(unsigned long long), st));
     CATT_CUDA(cudaMemsetAsync(tab.vals, 0, slots * sizeof(unsigned long long), st));
     CATT_CUDA(cudaEventRecord(c->ev[0], st));
-    if ((rc = launch_pool(reads, pitems, M, k, tab, st, launches))) return rc;
+    if ((rc = launch_pool(reads, pitems, M, k, tab, c->sm_count, st, launches))) return rc;
     CATT_CUDA(cudaEventRecord(c->ev[1], st));
-    if ((rc = launch_extend(reads, c->d_finder, pitems, partial_idx, n_partial, k, tab, xout, reinterpret_cast<uint32_t*>(cnt + C_RESCUED), st, launches))) return rc;
+    if ((rc = launch_extend(reads, c->d_finder, pitems, partial_idx, n_partial, k, tab, xout, reinterpret_cast<uint32_t*>(cnt + C_RESCUED), c->sm_count, st, launches))) return rc;
   }
   CATT_CUDA(cudaEventRecord(c->ev[6], st));
   // ---- the Myread strings: sizes -> offsets (scans) -> one warp per read writes both strings and the catt_read entry; the
@@ -724,28 +809,12 @@ int stage_b(catt_ctx* c, int64_t n, const NamesDev& names, const ReadsDev& reads
     E = (int64_t)ev2[0]; EV = (int64_t)ev2[1];
     S.map = cmap; S.E = E;
     if (dq.host_quals && E > 0) {                   // gather the quality strings of the E surviving reads on the host, upload them
-      uint32_t* d_rid; char* d_gather; int64_t* d_entry;
-      if ((rc = ensure(c, SB_QRID, E, &d_rid)) || (rc = c->pin[PIN_QRID].ensure((size_t)E * 4)) || (rc = c->pin[PIN_QENTRY].ensure((size_t)(E + 1) * 8))) return rc;
+      uint32_t* d_rid;
+      if ((rc = ensure(c, SB_QRID, E, &d_rid))) return rc;
       entry_read_kernel<<<nblk(E), 256, 0, st>>>(desc, cmap, E, d_rid);
       CATT_CUDA(cudaGetLastError());
       *launches += 1;
-      uint32_t* h_rid = c->pin[PIN_QRID].as<uint32_t>();
-      int64_t* h_entry = c->pin[PIN_QENTRY].as<int64_t>();
-      CATT_CUDA(cudaMemcpyAsync(h_rid, d_rid, (size_t)E * 4, cudaMemcpyDeviceToHost, st));
-      CATT_CUDA(cudaStreamSynchronize(st));
-      h_entry[0] = 0;
-      for (int64_t e = 0; e < E; e++) h_entry[e + 1] = h_entry[e] + (dq.host_seq_off[h_rid[e] + 1] - dq.host_seq_off[h_rid[e]]);
-      const int64_t gbytes = h_entry[E];
-      if ((rc = c->pin[PIN_QGATHER].ensure((size_t)gbytes + 16)) || (rc = ensure(c, SB_QGATHER, gbytes + 16, &d_gather)) ||
-          (rc = ensure(c, SB_QENTRY, E + 1, &d_entry))) return rc;
-      char* h_gather = c->pin[PIN_QGATHER].as<char>();
-      #pragma omp parallel for schedule(static)
-      for (int64_t e = 0; e < E; e++)
-        memcpy(h_gather + h_entry[e], dq.host_quals + dq.host_seq_off[h_rid[e]], (size_t)(h_entry[e + 1] - h_entry[e]));
-      CATT_CUDA(cudaMemcpyAsync(d_gather, h_gather, (size_t)gbytes, cudaMemcpyHostToDevice, st));
-      CATT_CUDA(cudaMemcpyAsync(d_entry, h_entry, (size_t)(E + 1) * 8, cudaMemcpyHostToDevice, st));
-      info.bytes_h2d += gbytes + (E + 1) * 8; info.bytes_d2h += E * 4;
-      S.quals = d_gather; S.q_entry_off = d_entry;
+      if ((rc = gather_host_quals(c, dq, d_rid, E, &S, info, st))) return rc;
     }
   }
   unsigned long long *ssz, *qsz, *soff, *qoff;
@@ -753,13 +822,7 @@ int stage_b(catt_ctx* c, int64_t n, const NamesDev& names, const ReadsDev& reads
       (rc = ensure(c, SB_QOFF, E + 1, &qoff))) return rc;
   strsize_kernel<<<nblk(E + 1), 256, 0, st>>>(S, ssz, qsz);
   CATT_CUDA(cudaGetLastError());
-  for (int which = 0; which < 2; which++) {
-    size_t need = 0;
-    CATT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, which ? qsz : ssz, which ? qoff : soff, E + 1, st));
-    if ((rc = ensure_cub(c, need))) return rc;
-    need = c->sb[SB_CUB].cap;
-    CATT_CUDA(cub::DeviceScan::ExclusiveSum(c->sb[SB_CUB].p, need, which ? qsz : ssz, which ? qoff : soff, E + 1, st));
-  }
+  if ((rc = scan_u64(c, ssz, soff, E + 1, st)) || (rc = scan_u64(c, qsz, qoff, E + 1, st))) return rc;
   *launches += 5;
   CATT_CUDA(cudaMemcpyAsync(hcnt, cnt, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   CATT_CUDA(cudaMemcpyAsync(hcnt + C_COUNT, soff + E, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -797,6 +860,585 @@ int stage_b(catt_ctx* c, int64_t n, const NamesDev& names, const ReadsDev& reads
     { float a = 0, b2 = 0; cudaEventElapsedTime(&a, c->ev[5], c->ev[6]); cudaEventElapsedTime(&b2, c->ev[6], c->ev[7]); info.ms_strings += a; info.ms_d2h += b2; }
   }
   tr.lap("B: strings + D2H");
+  return CATT_OK;
+}
+
+
+// =================================================================================================================================
+// One sample over N GPUs.  Every rank owns a contiguous block of the reads, has run Stage A on it (records in
+// c->recs_all, packed reads in c->rd_*) and now takes part in ONE global Stage B:
+//   1. the records + QNAMEs of the MAPPED reads are all-gathered (64 B + name per mapped read) and every rank derives the same
+//      global SAM order / QNAME dedup / share_name / pairing with the single-GPU code above (catt.jl:45-48, 221-237, 288-297):
+//      ~0.7 ms per million reads, cheaper than any exchange that would shard it;
+//   2. each work item is processed by the rank that owns its read: assignV/J, real_score, finder! (extract_kernel) run sharded;
+//      a both-mapped pair whose two records sit on different ranks (mates far apart in the file) gets the other read's packed
+//      words through one sparse all-reduce;
+//   3. one byte per item (kept / list / partial) is all-reduced, so every rank knows every read's position in [Vpart; Jpart];
+//   4. the k-mer table is global and last-writer-wins (catt.jl:426-446, 481-497): every rank buckets its (k-mer, order << 8 | pos)
+//      pairs by the owner of the key (hash % N), one all-to-all moves them, the owners insert with atomicMax, the sub-tables are
+//      all-gathered, and the extension (catt.jl:341-424, 552-577) runs sharded against the replicated table;
+//   5. every rank writes the strings of ITS reads at their global offsets into zeroed arenas; one sum-reduce to the root merges
+//      them (each byte has exactly one writer).
+// =================================================================================================================================
+namespace {
+
+struct GRec { catt_aln v, j; uint32_t gidx; int32_t len; int32_t name_len; int32_t pad_; };    // one mapped read on the wire (80 B)
+struct RankBounds { long long b[17]; int n; };
+__device__ __forceinline__ int owner_of(const RankBounds& rb, long long g) {
+  int r = 0;
+  while (r + 1 < rb.n && g >= rb.b[r + 1]) r++;
+  return r;
+}
+enum { SH_FLAG = 0, SH_POS, SH_NLEN, SH_NPOS, SH_GREC_LOC, SH_NAMES_LOC, SH_GREC, SH_NAMES, SH_RECV, SH_RECJ, SH_GIDX, SH_LEN, SH_NLEN64, SH_NBEG,
+       SH_SEG, SH_OWN, SH_CROSS, SH_OWNPOS, SH_CROSSPOS, SH_ITEMS_LOC, SH_EOUT_LOC, SH_GIT, SH_XBUF, SH_GFL, SH_LKEEP, SH_LKPOS, SH_LPFLAG, SH_LXPOS,
+       SH_GM, SH_CURSOR, SH_SEND, SH_RECVBUF, SH_SZW, SH_EFLAG, SH_EPOS, SH_LMAP, SH_LEFLAG, SH_LEPOS, SH_ALLREC, SH_COUNT_ };
+
+template <class T> int ensure_sh(catt_ctx* c, int slot, int64_t count, T** out) {
+  static_assert(SH_COUNT_ <= SH_SLOTS, "raise SH_SLOTS in host_types.h");
+  int rc = c->sh[slot].ensure((size_t)std::max<int64_t>(count, 1) * sizeof(T));
+  *out = c->sh[slot].as<T>();
+  return rc;
+}
+
+// local reads [a, b) of the current file: which are mapped, and how long are their QNAMEs
+__global__ void mapped_flag_kernel(int64_t a, int64_t cnt_, const catt_aln* __restrict__ rv, const catt_aln* __restrict__ rj, NamesDev nd,
+                                   uint32_t* __restrict__ flag, uint32_t* __restrict__ nlen) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > cnt_) return;
+  if (t == cnt_) { flag[t] = 0; nlen[t] = 0; return; }
+  const int64_t i = a + t;
+  const bool m = rv[i].mapped || rj[i].mapped;
+  flag[t] = m;
+  nlen[t] = m ? (uint32_t)(nd.end[i] - nd.beg[i]) : 0u;
+}
+__global__ void grec_pack_kernel(int64_t a, int64_t cnt_, const catt_aln* __restrict__ rv, const catt_aln* __restrict__ rj, NamesDev nd,
+                                 const int32_t* __restrict__ len, uint32_t gidx0, const uint32_t* __restrict__ flag, const uint32_t* __restrict__ pos,
+                                 const uint32_t* __restrict__ npos, GRec* __restrict__ out, char* __restrict__ names_out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= cnt_ || !flag[t]) return;
+  const int64_t i = a + t;
+  GRec g;
+  g.v = rv[i]; g.j = rj[i]; g.gidx = gidx0 + (uint32_t)t; g.len = len[i]; g.name_len = (int32_t)(nd.end[i] - nd.beg[i]); g.pad_ = 0;
+  out[pos[t]] = g;
+  const char* s = nd.s + nd.beg[i];
+  char* d = names_out + npos[t];
+  for (int k = 0; k < g.name_len; k++) d[k] = s[k];
+}
+__global__ void grec_unpack_kernel(int64_t n, const GRec* __restrict__ in, catt_aln* __restrict__ rv, catt_aln* __restrict__ rj, uint32_t* __restrict__ gidx,
+                                   int32_t* __restrict__ len, unsigned long long* __restrict__ nlen, unsigned long long* __restrict__ cnt2) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool mv = false, mj = false;
+  if (t < n) {
+    const GRec g = in[t];
+    rv[t] = g.v; rj[t] = g.j; gidx[t] = g.gidx; len[t] = g.len; nlen[t] = (unsigned long long)g.name_len;
+    mv = g.v.mapped != 0; mj = g.j.mapped != 0;
+  } else if (t == n) {
+    nlen[t] = 0;
+  }
+  const unsigned bv = __ballot_sync(FULL, mv), bj = __ballot_sync(FULL, mj);
+  if ((threadIdx.x & 31) == 0) { if (bv) atomicAdd(&cnt2[0], (unsigned long long)__popc(bv)); if (bj) atomicAdd(&cnt2[1], (unsigned long long)__popc(bj)); }
+}
+
+// which items of the (globally identical) item list does this rank process, and which both-mapped pairs straddle two ranks
+__global__ void own_kernel(int64_t n_seg, const ExtractItem* __restrict__ seg, const uint32_t* __restrict__ gidx, long long gstart, RankBounds rb, int me,
+                           uint32_t* __restrict__ own, uint32_t* __restrict__ cross) {
+  const int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (it > n_seg) return;
+  if (it == n_seg) { own[it] = 0; cross[it] = 0; return; }
+  const ExtractItem x = seg[it];
+  const int o1 = owner_of(rb, gstart + gidx[x.read]);
+  const int o2 = x.kind == 2 ? owner_of(rb, gstart + gidx[x.read2]) : o1;
+  own[it] = o1 == me;
+  cross[it] = o1 != o2;
+}
+// this rank's items, in list order, with LOCAL read indices; the other read of a straddling pair is extra read `cross position`
+__global__ void own_compact_kernel(int64_t n_seg, const ExtractItem* __restrict__ seg, const uint32_t* __restrict__ gidx, long long gstart, long long lo,
+                                   const uint32_t* __restrict__ own, const uint32_t* __restrict__ cross, const uint32_t* __restrict__ ownpos,
+                                   const uint32_t* __restrict__ crosspos, uint32_t extra_base, uint32_t item_base, ExtractItem* __restrict__ out,
+                                   uint32_t* __restrict__ git) {
+  const int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (it >= n_seg || !own[it]) return;
+  ExtractItem x = seg[it];
+  const uint32_t r2 = x.read2;
+  x.read = (uint32_t)(gstart + gidx[x.read] - lo);
+  x.read2 = x.kind != 2 ? x.read : (cross[it] ? extra_base + crosspos[it] : (uint32_t)(gstart + gidx[r2] - lo));
+  out[ownpos[it]] = x;
+  git[ownpos[it]] = item_base + (uint32_t)it;
+}
+// the J-side read of every straddling pair, written by the rank that owns it into slot `cross position`: [len, packed words]
+__global__ void xfill_kernel(int64_t n_seg, const ExtractItem* __restrict__ seg, const uint32_t* __restrict__ gidx, long long gstart, long long lo,
+                             RankBounds rb, int me, const uint32_t* __restrict__ cross, const uint32_t* __restrict__ crosspos, ReadsDev reads, int W,
+                             uint32_t* __restrict__ xbuf) {
+  const int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (it >= n_seg || !cross[it]) return;
+  const long long g2 = gstart + gidx[seg[it].read2];
+  if (owner_of(rb, g2) != me) return;
+  const int64_t r = g2 - lo;
+  const int len = reads.len[r], nw = read_words(len);
+  uint32_t* d = xbuf + (size_t)crosspos[it] * (size_t)(W + 1);
+  d[0] = (uint32_t)len;
+  const uint32_t* w = reads.words + reads.off[r];
+  for (int k = 0; k < nw; k++) d[1 + k] = w[k];
+}
+// ... appended behind the local reads as extra reads (fixed stride W words)
+__global__ void xappend_kernel(int64_t nx, const uint32_t* __restrict__ xbuf, int W, int64_t read0, uint32_t word0, uint32_t* __restrict__ words,
+                               uint32_t* __restrict__ off, int32_t* __restrict__ len) {
+  const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= nx) return;
+  const uint32_t* s = xbuf + (size_t)x * (size_t)(W + 1);
+  const uint32_t o = word0 + (uint32_t)x * (uint32_t)W;
+  off[read0 + x] = o; len[read0 + x] = (int32_t)s[0];
+  for (int k = 0; k < W; k++) words[o + k] = s[1 + k];
+}
+
+// one byte per global item, written by the item's rank: 1 kept Vpart read, 2 kept Jpart read, 4 partial (cdr3 == "None"),
+// 8 dropped for SEQ mismatch (catt.jl:298), 16 kept both-mapped read
+__global__ void gflag_fill_kernel(int64_t nl, const ExtractItem* __restrict__ items, const ExtractOut* __restrict__ eout, const uint32_t* __restrict__ git,
+                                  uint8_t* __restrict__ gfl) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nl) return;
+  const int st = eout[k].status, kind = items[k].kind;
+  const bool kept = st == 1;
+  gfl[git[k]] = (uint8_t)((kept && kind != 1 ? 1 : 0) | (kept && kind == 1 ? 2 : 0) | (kept && eout[k].cdr3_off < 0 ? 4 : 0) | (st == 2 ? 8 : 0) |
+                          (kept && kind == 2 ? 16 : 0));
+}
+__global__ void gflag_expand_kernel(int64_t n, const uint8_t* __restrict__ gfl, uint32_t* __restrict__ kflag0, uint32_t* __restrict__ kflag1,
+                                    unsigned long long* __restrict__ cnt) {
+  const int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint8_t b = 0;
+  if (it < n) b = gfl[it];
+  if (it <= n) { kflag0[it] = b & 1; kflag1[it] = (b >> 1) & 1; }
+  const unsigned bp = __ballot_sync(FULL, b & 4), bm = __ballot_sync(FULL, b & 8), bf = __ballot_sync(FULL, b & 16);
+  if ((threadIdx.x & 31) == 0) {
+    if (bp) atomicAdd(&cnt[C_NPARTIAL], (unsigned long long)__popc(bp));
+    if (bm) atomicAdd(&cnt[C_MISMATCH], (unsigned long long)__popc(bm));
+    if (bf) atomicAdd(&cnt[C_FULL], (unsigned long long)__popc(bf));
+  }
+}
+__global__ void lkeep_kernel(int64_t nl, const ExtractOut* __restrict__ eout, uint32_t* __restrict__ lkeep) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k <= nl) lkeep[k] = k < nl && eout[k].status == 1;
+}
+// this rank's kept items -> PoolItem / OutDesc at their LOCAL rank j, carrying their GLOBAL position m in [Vpart; Jpart]
+__global__ void pitem_shard_kernel(int64_t nl, const ExtractItem* __restrict__ items, const ExtractOut* __restrict__ eout, const uint32_t* __restrict__ git,
+                                   const uint32_t* __restrict__ lkeep, const uint32_t* __restrict__ lkpos, const uint32_t* __restrict__ kpos0,
+                                   const uint32_t* __restrict__ kpos1, uint32_t vpart, const int32_t* __restrict__ jlen, PoolItem* __restrict__ pitems,
+                                   OutDesc* __restrict__ desc, uint32_t* __restrict__ gm, uint32_t* __restrict__ lpflag) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k == nl) lpflag[lkpos[nl]] = 0;                           // sentinel behind the last kept item
+  if (k >= nl || !lkeep[k]) return;
+  const ExtractItem x = items[k];
+  const ExtractOut e = eout[k];
+  const int side = x.kind == 1;
+  const uint32_t g = git[k];
+  const uint32_t m = side ? vpart + kpos1[g] : kpos0[g];
+  const uint32_t j = lkpos[k];
+  PoolItem pi;
+  pi.read = x.read; pi.strand = x.strand; pi.seq_off = e.seq_off; pi.seq_len = e.seq_len; pi.side = (int16_t)side;
+  pi.order = m; pi.partial = e.cdr3_off < 0;
+  pitems[j] = pi;
+  lpflag[j] = pi.partial;
+  gm[j] = m;
+  OutDesc d;
+  d.read = x.read; d.xi = -1; d.strand = x.strand; d.kind = x.kind; d.seq_off = e.seq_off; d.seq_len = e.seq_len;
+  d.cdr3_off = e.cdr3_off; d.cdr3_len = e.cdr3_len;
+  d.v_id = x.kind == 1 ? -1 : x.rid; d.j_id = x.kind == 0 ? -1 : (x.kind == 1 ? x.rid : x.j_rid);
+  d.q_start1 = (int16_t)(x.qb + 1); d.j_pad = x.kind == 1 ? (int16_t)(jlen[x.rid] - (x.rb + 1)) : 0; d.pad_ = 0;
+  desc[j] = d;
+}
+__global__ void lpartial_kernel(int64_t ml, const uint32_t* __restrict__ lpflag, const uint32_t* __restrict__ lxpos, uint32_t* __restrict__ partial_idx,
+                                OutDesc* __restrict__ desc) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ml || !lpflag[j]) return;
+  partial_idx[lxpos[j]] = (uint32_t)j;
+  desc[j].xi = (int32_t)lxpos[j];
+}
+// one word per global list position, written by the read's rank: bit 31 = the read is returned, bits 12.. = qual bytes, 0..11 = seq bytes
+__global__ void szw_fill_kernel(StrSrc S, int only_cdr3, uint32_t* __restrict__ szw, uint32_t* __restrict__ leflag) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > S.M) return;
+  if (j == S.M) { leflag[j] = 0; return; }
+  int n_ext, c_off, c_len, slen, qlen, base_q;
+  str_dims(S, j, &n_ext, &c_off, &c_len, &slen, &qlen, &base_q);
+  const bool present = !only_cdr3 || c_off >= 0;
+  leflag[j] = present;
+  if (present) szw[S.gm[j]] = 0x80000000u | ((uint32_t)(qlen + 1) << 12) | (uint32_t)(slen + 1);
+}
+__global__ void szw_expand_kernel(int64_t M, const uint32_t* __restrict__ szw, uint32_t* __restrict__ eflag, unsigned long long* __restrict__ ssz,
+                                  unsigned long long* __restrict__ qsz) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m > M) return;
+  const uint32_t w = m < M ? szw[m] : 0u;
+  const bool p = (w >> 31) != 0;
+  eflag[m] = p; ssz[m] = p ? (w & 0xfffu) : 0u; qsz[m] = p ? ((w >> 12) & 0xfffu) : 0u;
+}
+__global__ void lmap_kernel(int64_t ml, const uint32_t* __restrict__ leflag, const uint32_t* __restrict__ lepos, const OutDesc* __restrict__ desc,
+                            uint32_t* __restrict__ lmap, uint32_t* __restrict__ rid) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ml || !leflag[j]) return;
+  lmap[lepos[j]] = (uint32_t)j;
+  rid[lepos[j]] = desc[j].read;
+}
+
+}  // namespace
+
+int stage_b_sharded(catt_ctx* c, const ShardIn& in, const NamesDev& names, const DeviceQuals& dq, catt_result* R, int* launches) {
+  Comm* comm = in.comm;
+  const int N = comm->nranks, me = comm->rank;
+  catt_info& info = R->info;
+  info.kmer = c->kmer;
+  cudaStream_t st = c->stream;
+  Trace tr;
+  int rc;
+  if (N > 16) { set_error("GPU group of %d ranks (limit 16)", N); return CATT_E_ARG; }
+  if (in.bounds.back() == 0) return CATT_OK;                      // an empty sample (every rank sees that)
+  unsigned long long* cnt; unsigned long long* hcnt;
+  if ((rc = ensure(c, SB_CNT, C_COUNT, &cnt))) return rc;
+  hcnt = c->pin[PIN_CNT].as<unsigned long long>() + 2 * N_COUNTERS;
+  const int nfiles = (int)in.gstart.size() - 1;
+  const int64_t lo = in.lo, n_loc = in.n_loc;
+  RankBounds rb{};
+  rb.n = N;
+  for (int r = 0; r <= N; r++) rb.b[r] = in.bounds[r];
+  const catt_aln* lrv = c->recs_all[0].as<catt_aln>();
+  const catt_aln* lrj = c->recs_all[1].as<catt_aln>();
+  const int W = read_words(in.max_len);
+  float ms_order = 0, ms_extract = 0;
+  // per collective: device time between two events on the stream (read after the next sync) and the bytes this rank moved
+  int64_t bytes_mark = comm->bytes_moved;
+  auto comm_lap = [&](int which, cudaEvent_t a, cudaEvent_t b) {
+    float x = 0;
+    cudaEventElapsedTime(&x, a, b);
+    info.ms_coll[which] += x; info.ms_comm += x;
+  };
+  auto comm_bytes = [&](int which) { info.bytes_coll[which] += comm->bytes_moved - bytes_mark; info.bytes_comm += comm->bytes_moved - bytes_mark; bytes_mark = comm->bytes_moved; };
+
+  // local items of all files, in list order
+  ExtractItem* items_loc = nullptr; ExtractOut* eout_loc = nullptr; uint32_t* git = nullptr;
+  int64_t nl = 0, nl_cap = 0;                     // local items so far / capacity
+  int64_t n_items_g = 0;                          // global items so far
+  int64_t n_extra = 0;                            // extra reads appended behind the local ones
+  uint64_t extra_words = 0;
+  int k = c->kmer;
+
+  for (int f = 0; f < nfiles; f++) {
+    const int64_t gs = in.gstart[f], ge = in.gstart[f + 1];
+    const int64_t a = std::min(std::max(lo, gs), lo + n_loc) - lo, b = std::max(std::min(lo + n_loc, ge), lo) - lo;     // local reads [a, b) of this file
+    const int64_t cn = std::max<int64_t>(b - a, 0);
+    // ---- 1. mapped reads of this block -> wire format
+    uint32_t *flag, *pos, *nlen, *npos;
+    if ((rc = ensure_sh(c, SH_FLAG, cn + 1, &flag)) || (rc = ensure_sh(c, SH_POS, cn + 1, &pos)) || (rc = ensure_sh(c, SH_NLEN, cn + 1, &nlen)) ||
+        (rc = ensure_sh(c, SH_NPOS, cn + 1, &npos))) return rc;
+    CATT_CUDA(cudaEventRecord(c->ev[5], st));
+    mapped_flag_kernel<<<nblk(cn + 1), 256, 0, st>>>(a, cn, lrv, lrj, names, flag, nlen);
+    CATT_CUDA(cudaGetLastError());
+    if ((rc = scan_u32(c, flag, pos, cn + 1, st)) || (rc = scan_u32(c, nlen, npos, cn + 1, st))) return rc;
+    uint32_t h2[2];
+    CATT_CUDA(cudaMemcpyAsync(&h2[0], pos + cn, 4, cudaMemcpyDeviceToHost, st));
+    CATT_CUDA(cudaMemcpyAsync(&h2[1], npos + cn, 4, cudaMemcpyDeviceToHost, st));
+    CATT_CUDA(cudaStreamSynchronize(st));
+    const int64_t nmap_loc = h2[0], nb_loc = h2[1];
+    GRec* grec_loc; char* names_loc;
+    if ((rc = ensure_sh(c, SH_GREC_LOC, nmap_loc, &grec_loc)) || (rc = ensure_sh(c, SH_NAMES_LOC, nb_loc + 16, &names_loc))) return rc;
+    if (cn > 0) {
+      grec_pack_kernel<<<nblk(cn), 256, 0, st>>>(a, cn, lrv, lrj, names, c->rd_len.as<int32_t>(), (uint32_t)(lo + a - gs), flag, pos, npos, grec_loc, names_loc);
+      CATT_CUDA(cudaGetLastError());
+    }
+    *launches += 6;
+    // ---- 2. all-gather them
+    std::vector<long long> mine{(long long)nmap_loc, (long long)nb_loc}, all((size_t)2 * N);
+    if ((rc = comm->host_allgather(mine.data(), all.data(), 2 * sizeof(long long), st))) return rc;
+    std::vector<size_t> cnt_r(N), dsp_r(N), cnt_n(N), dsp_n(N);
+    int64_t nmap = 0, nbytes = 0;
+    for (int r = 0; r < N; r++) {
+      cnt_r[r] = (size_t)all[2 * r] * sizeof(GRec); dsp_r[r] = (size_t)nmap * sizeof(GRec); nmap += all[2 * r];
+      cnt_n[r] = (size_t)all[2 * r + 1]; dsp_n[r] = (size_t)nbytes; nbytes += all[2 * r + 1];
+    }
+    if (nmap >= 0xFFFFFFF0ll) { set_error("too many mapped reads in one file for the sharded path"); return CATT_E_LIMIT; }
+    GRec* grec; char* gnames;
+    if ((rc = ensure_sh(c, SH_GREC, nmap, &grec)) || (rc = ensure_sh(c, SH_NAMES, nbytes + 16, &gnames))) return rc;
+    CATT_CUDA(cudaEventRecord(c->ev[2], st));
+    if ((rc = comm->allgatherv(grec_loc, grec, cnt_r.data(), dsp_r.data(), st)) || (rc = comm->allgatherv(names_loc, gnames, cnt_n.data(), dsp_n.data(), st))) return rc;
+    CATT_CUDA(cudaEventRecord(c->ev[3], st));
+    comm_bytes(CATT_COLL_RECORDS);
+    catt_aln *grv, *grj; uint32_t* gidx; int32_t* glen; unsigned long long *gnlen, *gnbeg;
+    if ((rc = ensure_sh(c, SH_RECV, nmap, &grv)) || (rc = ensure_sh(c, SH_RECJ, nmap, &grj)) || (rc = ensure_sh(c, SH_GIDX, nmap, &gidx)) ||
+        (rc = ensure_sh(c, SH_LEN, nmap, &glen)) || (rc = ensure_sh(c, SH_NLEN64, nmap + 1, &gnlen)) || (rc = ensure_sh(c, SH_NBEG, nmap + 1, &gnbeg))) return rc;
+    CATT_CUDA(cudaMemsetAsync(cnt, 0, 2 * sizeof(unsigned long long), st));
+    grec_unpack_kernel<<<nblk(nmap + 1), 256, 0, st>>>(nmap, grec, grv, grj, gidx, glen, gnlen, cnt);
+    CATT_CUDA(cudaGetLastError());
+    if ((rc = scan_u64(c, gnlen, gnbeg, nmap + 1, st))) return rc;
+    unsigned long long hm[2];
+    CATT_CUDA(cudaMemcpyAsync(hm, cnt, sizeof hm, cudaMemcpyDeviceToHost, st));
+    CATT_CUDA(cudaStreamSynchronize(st));
+    comm_lap(CATT_COLL_RECORDS, c->ev[2], c->ev[3]);
+    *launches += 3;
+    const int64_t nm[2] = {(int64_t)hm[0], (int64_t)hm[1]};
+    // ---- 3. the global order, identically on every rank (indices = positions in the gathered arrays: input order is kept)
+    OrderScratch OS;
+    if ((rc = order_alloc(c, nmap, nm[0], nm[1], &OS))) return rc;
+    ExtractItem* seg;
+    if ((rc = ensure_sh(c, SH_SEG, nm[0] + nm[1], &seg))) return rc;
+    const NamesDev gnd{gnames, reinterpret_cast<const int64_t*>(gnbeg), reinterpret_cast<const int64_t*>(gnbeg) + 1};
+    const catt_aln* rec[2] = {grv, grj};
+    OrderOut oo;
+    if ((rc = order_file(c, OS, nmap, gnd, rec, glen, nm, 0u, &k, info, cnt, hcnt, seg, nm[0] + nm[1], &oo, launches))) return rc;
+    const int64_t nseg = oo.n_v + oo.n_p + oo.n_j;
+    if (n_items_g + nseg >= 0xFFFFFFF0ll) { set_error("too many work items for the sharded path"); return CATT_E_LIMIT; }
+    // ---- 4. this rank's items; pairs that straddle two ranks
+    uint32_t *own, *cross, *ownpos, *crosspos;
+    if ((rc = ensure_sh(c, SH_OWN, nseg + 1, &own)) || (rc = ensure_sh(c, SH_CROSS, nseg + 1, &cross)) || (rc = ensure_sh(c, SH_OWNPOS, nseg + 1, &ownpos)) ||
+        (rc = ensure_sh(c, SH_CROSSPOS, nseg + 1, &crosspos))) return rc;
+    own_kernel<<<nblk(nseg + 1), 256, 0, st>>>(nseg, seg, gidx, gs, rb, me, own, cross);
+    CATT_CUDA(cudaGetLastError());
+    if ((rc = scan_u32(c, own, ownpos, nseg + 1, st)) || (rc = scan_u32(c, cross, crosspos, nseg + 1, st))) return rc;
+    CATT_CUDA(cudaMemcpyAsync(&h2[0], ownpos + nseg, 4, cudaMemcpyDeviceToHost, st));
+    CATT_CUDA(cudaMemcpyAsync(&h2[1], crosspos + nseg, 4, cudaMemcpyDeviceToHost, st));
+    CATT_CUDA(cudaStreamSynchronize(st));
+    const int64_t n_own = h2[0], n_cross = h2[1];
+    *launches += 5;
+    if (nl + n_own > nl_cap) {
+      nl_cap = (nl + n_own) + (nl + n_own) / 4 + 1024;
+      if ((rc = c->sh[SH_ITEMS_LOC].ensure_keep((size_t)nl_cap * sizeof(ExtractItem), st)) || (rc = c->sh[SH_EOUT_LOC].ensure_keep((size_t)nl_cap * sizeof(ExtractOut), st)) ||
+          (rc = c->sh[SH_GIT].ensure_keep((size_t)nl_cap * sizeof(uint32_t), st))) return rc;
+    }
+    items_loc = c->sh[SH_ITEMS_LOC].as<ExtractItem>(); eout_loc = c->sh[SH_EOUT_LOC].as<ExtractOut>(); git = c->sh[SH_GIT].as<uint32_t>();
+    if (nseg > 0) {
+      own_compact_kernel<<<nblk(nseg), 256, 0, st>>>(nseg, seg, gidx, gs, lo, own, cross, ownpos, crosspos, (uint32_t)(n_loc + n_extra), (uint32_t)n_items_g,
+                                                     items_loc + nl, git + nl);
+      CATT_CUDA(cudaGetLastError());
+      *launches += 1;
+    }
+    if (n_cross > 0) {                             // the other read of every straddling pair: sparse fill + all-reduce, then appended locally
+      uint32_t* xbuf;
+      const size_t xw = (size_t)n_cross * (size_t)(W + 1);
+      if ((rc = ensure_sh(c, SH_XBUF, (int64_t)xw, &xbuf))) return rc;
+      CATT_CUDA(cudaMemsetAsync(xbuf, 0, xw * 4, st));
+      ReadsDev lr{c->rd_words.as<uint32_t>(), c->rd_off.as<uint32_t>(), c->rd_len.as<int32_t>(), n_loc, in.max_len};
+      xfill_kernel<<<nblk(nseg), 256, 0, st>>>(nseg, seg, gidx, gs, lo, rb, me, cross, crosspos, lr, W, xbuf);
+      CATT_CUDA(cudaGetLastError());
+      CATT_CUDA(cudaEventRecord(c->ev[2], st));
+      if ((rc = comm->allreduce_sum_u32(xbuf, xw, st))) return rc;
+      CATT_CUDA(cudaEventRecord(c->ev[3], st));
+      comm_bytes(CATT_COLL_MATES);
+      const uint64_t word0 = (uint64_t)in.n_words + extra_words;
+      if (word0 + (uint64_t)n_cross * W >= 0xFFFFFFF0ull) { set_error("packed reads exceed 2^32 words"); return CATT_E_LIMIT; }
+      if ((rc = c->rd_words.ensure_keep((size_t)(word0 + (uint64_t)n_cross * W + 4) * 4, st)) ||
+          (rc = c->rd_off.ensure_keep((size_t)(n_loc + n_extra + n_cross + 2) * 4, st)) || (rc = c->rd_len.ensure_keep((size_t)(n_loc + n_extra + n_cross + 1) * 4, st))) return rc;
+      xappend_kernel<<<nblk(n_cross), 256, 0, st>>>(n_cross, xbuf, W, n_loc + n_extra, (uint32_t)word0, c->rd_words.as<uint32_t>(), c->rd_off.as<uint32_t>(),
+                                                    c->rd_len.as<int32_t>());
+      CATT_CUDA(cudaGetLastError());
+      CATT_CUDA(cudaStreamSynchronize(st));
+      comm_lap(CATT_COLL_MATES, c->ev[2], c->ev[3]);
+      n_extra += n_cross; extra_words += (uint64_t)n_cross * W;
+      *launches += 2;
+    }
+    CATT_CUDA(cudaEventRecord(c->ev[6], st));
+    // ---- 5. assignV/J, real_score, finder! on this rank's items
+    const ReadsDev reads{c->rd_words.as<uint32_t>(), c->rd_off.as<uint32_t>(), c->rd_len.as<int32_t>(), n_loc + n_extra, in.max_len};
+    if ((rc = launch_extract(c->V.dev, c->J.dev, reads, c->d_finder, items_loc + nl, eout_loc + nl, n_own, k, c->allow_v, c->allow_j, c->sm_count, st, launches))) return rc;
+    CATT_CUDA(cudaEventRecord(c->ev[7], st));
+    CATT_CUDA(cudaStreamSynchronize(st));
+    { float x = 0, y = 0; cudaEventElapsedTime(&x, c->ev[5], c->ev[6]); cudaEventElapsedTime(&y, c->ev[6], c->ev[7]); ms_order += x; ms_extract += y; }
+    nl += n_own; n_items_g += nseg;
+  }
+  info.kmer = k;
+  tr.lap("B/N: gather + order + extract");
+  const ReadsDev reads{c->rd_words.as<uint32_t>(), c->rd_off.as<uint32_t>(), c->rd_len.as<int32_t>(), n_loc + n_extra, in.max_len};
+
+  // ---- 6. every read's position in [Vpart; Jpart]: one byte per item, all-reduced
+  uint8_t* gfl; uint32_t *kflag0, *kflag1, *kpos0, *kpos1;
+  const size_t gfl_words = ((size_t)n_items_g + 4) / 4 + 1;
+  if ((rc = ensure_sh(c, SH_GFL, (int64_t)gfl_words * 4, &gfl)) || (rc = ensure(c, SB_KFLAG, n_items_g + 1, &kflag0)) || (rc = ensure(c, SB_KFLAG1, n_items_g + 1, &kflag1)) ||
+      (rc = ensure(c, SB_KPOS2, n_items_g + 1, &kpos0)) || (rc = ensure(c, SB_KPOS3, n_items_g + 1, &kpos1))) return rc;
+  CATT_CUDA(cudaEventRecord(c->ev[5], st));
+  CATT_CUDA(cudaMemsetAsync(gfl, 0, gfl_words * 4, st));
+  CATT_CUDA(cudaMemsetAsync(cnt, 0, C_COUNT * sizeof(unsigned long long), st));
+  if (nl > 0) { gflag_fill_kernel<<<nblk(nl), 256, 0, st>>>(nl, items_loc, eout_loc, git, gfl); CATT_CUDA(cudaGetLastError()); }
+  CATT_CUDA(cudaEventRecord(c->ev[2], st));
+  if ((rc = comm->allreduce_sum_u32(reinterpret_cast<uint32_t*>(gfl), gfl_words, st))) return rc;
+  CATT_CUDA(cudaEventRecord(c->ev[3], st));
+  comm_bytes(CATT_COLL_FLAGS);
+  gflag_expand_kernel<<<nblk(n_items_g + 1), 256, 0, st>>>(n_items_g, gfl, kflag0, kflag1, cnt);
+  CATT_CUDA(cudaGetLastError());
+  if ((rc = scan_u32(c, kflag0, kpos0, n_items_g + 1, st)) || (rc = scan_u32(c, kflag1, kpos1, n_items_g + 1, st))) return rc;
+  uint32_t hv[2];
+  CATT_CUDA(cudaMemcpyAsync(&hv[0], kpos0 + n_items_g, 4, cudaMemcpyDeviceToHost, st));
+  CATT_CUDA(cudaMemcpyAsync(&hv[1], kpos1 + n_items_g, 4, cudaMemcpyDeviceToHost, st));
+  CATT_CUDA(cudaMemcpyAsync(hcnt, cnt, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CATT_CUDA(cudaStreamSynchronize(st));
+  comm_lap(CATT_COLL_FLAGS, c->ev[2], c->ev[3]);
+  const int64_t vpart = hv[0], M = (int64_t)hv[0] + hv[1], n_partial_g = (int64_t)hcnt[C_NPARTIAL];
+  info.vpart = vpart; info.jpart = M - vpart; info.full_pushed = (int64_t)hcnt[C_FULL]; info.pair_seq_mismatch = (int64_t)hcnt[C_MISMATCH];
+  info.left = n_partial_g; info.direct = M - n_partial_g;
+  // this rank's kept reads
+  uint32_t *lkeep, *lkpos, *lpflag, *lxpos, *gm, *partial_idx;
+  PoolItem* pitems; OutDesc* desc;
+  if ((rc = ensure_sh(c, SH_LKEEP, nl + 1, &lkeep)) || (rc = ensure_sh(c, SH_LKPOS, nl + 1, &lkpos)) || (rc = ensure_sh(c, SH_LPFLAG, nl + 1, &lpflag)) ||
+      (rc = ensure_sh(c, SH_LXPOS, nl + 1, &lxpos)) || (rc = ensure_sh(c, SH_GM, nl + 1, &gm)) || (rc = ensure(c, SB_PITEMS, nl, &pitems)) ||
+      (rc = ensure(c, SB_DESC, nl, &desc)) || (rc = ensure(c, SB_PARTIAL, nl, &partial_idx))) return rc;
+  lkeep_kernel<<<nblk(nl + 1), 256, 0, st>>>(nl, eout_loc, lkeep);
+  CATT_CUDA(cudaGetLastError());
+  if ((rc = scan_u32(c, lkeep, lkpos, nl + 1, st))) return rc;
+  pitem_shard_kernel<<<nblk(nl + 1), 256, 0, st>>>(nl, items_loc, eout_loc, git, lkeep, lkpos, kpos0, kpos1, (uint32_t)vpart, c->J.dev.rec_len, pitems, desc, gm, lpflag);
+  CATT_CUDA(cudaGetLastError());
+  uint32_t hml = 0;
+  CATT_CUDA(cudaMemcpyAsync(&hml, lkpos + nl, 4, cudaMemcpyDeviceToHost, st));
+  CATT_CUDA(cudaStreamSynchronize(st));
+  const int64_t ml = hml;                          // this rank's share of [Vpart; Jpart]
+  if ((rc = scan_u32(c, lpflag, lxpos, ml + 1, st))) return rc;
+  if (ml > 0) { lpartial_kernel<<<nblk(ml), 256, 0, st>>>(ml, lpflag, lxpos, partial_idx, desc); CATT_CUDA(cudaGetLastError()); }
+  uint32_t hpl = 0;
+  CATT_CUDA(cudaMemcpyAsync(&hpl, lxpos + ml, 4, cudaMemcpyDeviceToHost, st));
+  CATT_CUDA(cudaEventRecord(c->ev[6], st));
+  CATT_CUDA(cudaStreamSynchronize(st));
+  const int64_t n_partial = hpl;                   // ... and of the partial reads
+  { float x = 0; cudaEventElapsedTime(&x, c->ev[5], c->ev[6]); info.ms_order += ms_order + x; info.ms_extract += ms_extract; }
+  *launches += 12;
+  tr.lap("B/N: lists");
+
+  // ---- 7. the global k-mer table, then the extension of this rank's partial reads
+  ExtendOut* xout = nullptr;
+  const bool run_pool = M > 0 && k <= KMER_MAX && n_partial_g > 0;
+  CATT_CUDA(cudaEventRecord(c->ev[5], st));
+  if (run_pool) {
+    KmerTable tab{};
+    tab.nsub = (uint32_t)N;
+    tab.sub_slots = std::max<uint64_t>(1024, ((uint64_t)M * 11ull * 2ull + N - 1) / N);
+    const uint64_t slots = tab.sub_slots * (uint64_t)N;
+    unsigned long long* cursor; PoolEntry *sendb, *recvb;
+    if ((rc = ensure(c, SB_TAB_KEYS, (int64_t)slots, &tab.keys)) || (rc = ensure(c, SB_TAB_VALS, (int64_t)slots, &tab.vals)) ||
+        (rc = ensure(c, SB_XOUT, n_partial, &xout)) || (rc = ensure_sh(c, SH_CURSOR, 2 * N, &cursor)) || (rc = ensure_sh(c, SH_SEND, ml * 11, &sendb))) return rc;
+    CATT_CUDA(cudaMemsetAsync(tab.keys + (uint64_t)me * tab.sub_slots, 0xff, tab.sub_slots * sizeof(unsigned long long), st));
+    CATT_CUDA(cudaMemsetAsync(tab.vals + (uint64_t)me * tab.sub_slots, 0, tab.sub_slots * sizeof(unsigned long long), st));
+    CATT_CUDA(cudaMemsetAsync(cursor, 0, (size_t)2 * N * sizeof(unsigned long long), st));
+    CATT_CUDA(cudaEventRecord(c->ev[0], st));
+    if ((rc = launch_pool_emit(reads, pitems, ml, k, tab, 0, cursor, nullptr, c->sm_count, st, launches))) return rc;
+    std::vector<unsigned long long> hc((size_t)N), allc((size_t)N * N), off((size_t)N);
+    CATT_CUDA(cudaMemcpyAsync(hc.data(), cursor, (size_t)N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CATT_CUDA(cudaStreamSynchronize(st));
+    unsigned long long run = 0;
+    for (int r = 0; r < N; r++) { off[r] = run; run += hc[r]; }
+    CATT_CUDA(cudaMemcpyAsync(cursor + N, off.data(), (size_t)N * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+    if ((rc = launch_pool_emit(reads, pitems, ml, k, tab, 1, cursor + N, sendb, c->sm_count, st, launches))) return rc;
+    if ((rc = comm->host_allgather(hc.data(), allc.data(), (size_t)N * sizeof(unsigned long long), st))) return rc;
+    std::vector<size_t> sc(N), sd(N), rcn(N), rd(N);
+    size_t rtot = 0;
+    for (int r = 0; r < N; r++) {
+      sc[r] = (size_t)hc[r] * sizeof(PoolEntry); sd[r] = (size_t)off[r] * sizeof(PoolEntry);
+      rcn[r] = (size_t)allc[(size_t)r * N + me] * sizeof(PoolEntry); rd[r] = rtot; rtot += rcn[r];
+    }
+    if ((rc = ensure_sh(c, SH_RECVBUF, (int64_t)(rtot / sizeof(PoolEntry)), &recvb))) return rc;
+    CATT_CUDA(cudaEventRecord(c->ev[2], st));
+    if ((rc = comm->alltoallv(sendb, sc.data(), sd.data(), recvb, rcn.data(), rd.data(), st))) return rc;
+    CATT_CUDA(cudaEventRecord(c->ev[3], st));
+    comm_bytes(CATT_COLL_KMER_A2A);
+    if ((rc = launch_pool_insert(recvb, (int64_t)(rtot / sizeof(PoolEntry)), tab, c->sm_count, st, launches))) return rc;
+    std::vector<size_t> gc(N, (size_t)tab.sub_slots * 8), gd(N);
+    for (int r = 0; r < N; r++) gd[r] = (size_t)r * tab.sub_slots * 8;
+    CATT_CUDA(cudaEventRecord(c->ev[4], st));
+    if ((rc = comm->allgatherv(tab.keys + (uint64_t)me * tab.sub_slots, tab.keys, gc.data(), gd.data(), st)) ||
+        (rc = comm->allgatherv(tab.vals + (uint64_t)me * tab.sub_slots, tab.vals, gc.data(), gd.data(), st))) return rc;
+    CATT_CUDA(cudaEventRecord(c->ev[1], st));
+    comm_bytes(CATT_COLL_KMER_TABLE);
+    if ((rc = launch_extend(reads, c->d_finder, pitems, partial_idx, n_partial, k, tab, xout, reinterpret_cast<uint32_t*>(cnt + C_RESCUED), c->sm_count, st, launches))) return rc;
+  }
+  CATT_CUDA(cudaEventRecord(c->ev[6], st));
+
+  // ---- 8. string sizes at global positions -> global offsets
+  StrSrc S{desc, xout, dq.quals, dq.seq_off, ml, vpart, nullptr, ml, nullptr};
+  S.gm = gm; S.ordinal_base = lo;
+  uint32_t *szw, *eflag, *epos, *leflag, *lepos, *lmap, *lrid;
+  unsigned long long *ssz, *qsz, *soff, *qoff;
+  if ((rc = ensure_sh(c, SH_SZW, M + 1, &szw)) || (rc = ensure_sh(c, SH_EFLAG, M + 1, &eflag)) || (rc = ensure_sh(c, SH_EPOS, M + 1, &epos)) ||
+      (rc = ensure_sh(c, SH_LEFLAG, ml + 1, &leflag)) || (rc = ensure_sh(c, SH_LEPOS, ml + 1, &lepos)) || (rc = ensure_sh(c, SH_LMAP, ml + 1, &lmap)) ||
+      (rc = ensure(c, SB_QRID, ml + 1, &lrid)) ||
+      (rc = ensure(c, SB_SSZ, M + 1, &ssz)) || (rc = ensure(c, SB_QSZ, M + 1, &qsz)) || (rc = ensure(c, SB_SOFF, M + 1, &soff)) || (rc = ensure(c, SB_QOFF, M + 1, &qoff))) return rc;
+  CATT_CUDA(cudaMemsetAsync(szw, 0, (size_t)(M + 1) * 4, st));
+  szw_fill_kernel<<<nblk(ml + 1), 256, 0, st>>>(S, c->only_cdr3, szw, leflag);
+  CATT_CUDA(cudaGetLastError());
+  CATT_CUDA(cudaEventRecord(c->ev[7], st));
+  if ((rc = comm->allreduce_sum_u32(szw, (size_t)M + 1, st))) return rc;
+  CATT_CUDA(cudaEventRecord(c->ev_a[0][0], st));
+  comm_bytes(CATT_COLL_SIZES);
+  szw_expand_kernel<<<nblk(M + 1), 256, 0, st>>>(M, szw, eflag, ssz, qsz);
+  CATT_CUDA(cudaGetLastError());
+  if ((rc = scan_u32(c, eflag, epos, M + 1, st)) || (rc = scan_u64(c, ssz, soff, M + 1, st)) || (rc = scan_u64(c, qsz, qoff, M + 1, st)) ||
+      (rc = scan_u32(c, leflag, lepos, ml + 1, st))) return rc;
+  if (ml > 0) { lmap_kernel<<<nblk(ml), 256, 0, st>>>(ml, leflag, lepos, desc, lmap, lrid); CATT_CUDA(cudaGetLastError()); }
+  uint32_t he[3]; unsigned long long hs[2];
+  CATT_CUDA(cudaMemcpyAsync(&he[0], epos + M, 4, cudaMemcpyDeviceToHost, st));
+  CATT_CUDA(cudaMemcpyAsync(&he[1], epos + vpart, 4, cudaMemcpyDeviceToHost, st));
+  CATT_CUDA(cudaMemcpyAsync(&he[2], lepos + ml, 4, cudaMemcpyDeviceToHost, st));
+  CATT_CUDA(cudaMemcpyAsync(&hs[0], soff + M, 8, cudaMemcpyDeviceToHost, st));
+  CATT_CUDA(cudaMemcpyAsync(&hs[1], qoff + M, 8, cudaMemcpyDeviceToHost, st));
+  CATT_CUDA(cudaMemcpyAsync(hcnt, cnt, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CATT_CUDA(cudaStreamSynchronize(st));
+  *launches += 10;
+  { float x = 0; cudaEventElapsedTime(&x, c->ev[5], c->ev[6]); info.ms_pool += x; }
+  if (run_pool) {
+    float x = 0; cudaEventElapsedTime(&x, c->ev[0], c->ev[1]); info.ms_pool_kernel += x;
+    comm_lap(CATT_COLL_KMER_A2A, c->ev[2], c->ev[3]); comm_lap(CATT_COLL_KMER_TABLE, c->ev[4], c->ev[1]);
+  }
+  comm_lap(CATT_COLL_SIZES, c->ev[7], c->ev_a[0][0]);
+  info.rescued += (int64_t)(uint32_t)hcnt[C_RESCUED];     // this rank's partial reads; summed over the ranks by the caller
+  const int64_t E = he[0], EV = he[1], el = he[2];
+  tr.lap("B/N: k-mer table + extension + sizes");
+  S.map = lmap; S.E = el; S.epos = epos;
+  if (dq.host_quals && el > 0 && (rc = gather_host_quals(c, dq, lrid, el, &S, info, st))) return rc;
+
+  // ---- 9. strings of this rank's reads at their global offsets; sum-reduce to the root (one writer per byte)
+  const size_t seq_bytes = (size_t)hs[0] + 1, qual_bytes = (size_t)hs[1] + 1;
+  const size_t seq_w = (seq_bytes + 3) / 4, qual_w = (qual_bytes + 3) / 4, part_w = (size_t)E * sizeof(catt_read) / 4;
+  char *d_seq, *d_qual; catt_read* d_part;
+  if ((rc = ensure(c, SB_OUT_SEQ, (int64_t)seq_w * 4, &d_seq)) || (rc = ensure(c, SB_OUT_QUAL, (int64_t)qual_w * 4, &d_qual)) ||
+      (rc = ensure(c, SB_OUT_PART, E, &d_part))) return rc;
+  CATT_CUDA(cudaEventRecord(c->ev[5], st));
+  CATT_CUDA(cudaMemsetAsync(d_seq, 0, seq_w * 4, st));
+  CATT_CUDA(cudaMemsetAsync(d_qual, 0, qual_w * 4, st));
+  CATT_CUDA(cudaMemsetAsync(d_part, 0, std::max<size_t>(part_w * 4, 4), st));
+  const bool root = me == in.root;
+  if (root) {
+    const double t2 = now_ms();
+    const size_t part_bytes = (size_t)std::max<int64_t>(E, 1) * sizeof(catt_read);
+    R->seq_arena = (char*)block_get(seq_bytes, &R->cap_seq);
+    R->qual_arena = (char*)block_get(qual_bytes, &R->cap_qual);
+    R->part[0] = (catt_read*)block_get(part_bytes, &R->cap_part[0]);
+    if (!R->seq_arena || !R->qual_arena || !R->part[0]) { set_error("out of host memory for the result"); return CATT_E_LIMIT; }
+    R->npart[0] = EV; R->npart[1] = E - EV;
+    R->part[1] = R->part[0] + EV;
+    info.ms_host += now_ms() - t2;
+  }
+  // every rank writes the ROOT's host addresses into its catt_read entries: the root publishes its two arena bases
+  unsigned long long bases[2] = {root ? (unsigned long long)(uintptr_t)R->seq_arena : 0ull, root ? (unsigned long long)(uintptr_t)R->qual_arena : 0ull};
+  std::vector<unsigned long long> allb((size_t)2 * N);
+  if ((rc = comm->host_allgather(bases, allb.data(), sizeof bases, st))) return rc;
+  const char* host_seq = reinterpret_cast<const char*>((uintptr_t)allb[(size_t)2 * in.root]);
+  const char* host_qual = reinterpret_cast<const char*>((uintptr_t)allb[(size_t)2 * in.root + 1]);
+  if (el > 0) {
+    const int grid = (int)std::min<int64_t>((el + MW - 1) / MW, (int64_t)c->sm_count * 16);
+    materialise_kernel<<<grid, MW * 32, 0, st>>>(S, reads, soff, qoff, d_seq, d_qual, d_part, host_seq, host_qual);
+    CATT_CUDA(cudaGetLastError());
+    *launches += 1;
+  }
+  CATT_CUDA(cudaEventRecord(c->ev[6], st));
+  if (E > 0) {
+    if ((rc = comm->reduce_sum_u32(reinterpret_cast<uint32_t*>(d_seq), seq_w, in.root, st)) ||
+        (rc = comm->reduce_sum_u32(reinterpret_cast<uint32_t*>(d_qual), qual_w, in.root, st)) ||
+        (rc = comm->reduce_sum_u32(reinterpret_cast<uint32_t*>(d_part), part_w, in.root, st))) return rc;
+  }
+  CATT_CUDA(cudaEventRecord(c->ev[7], st));
+  comm_bytes(CATT_COLL_RESULT);
+  if (root && E > 0) {
+    if ((rc = d2h_arena(c, R->seq_arena, R->cap_seq, d_seq, seq_bytes - 1, st)) || (rc = d2h_arena(c, R->qual_arena, R->cap_qual, d_qual, qual_bytes - 1, st)) ||
+        (rc = d2h_arena(c, R->part[0], R->cap_part[0], d_part, (size_t)E * sizeof(catt_read), st))) return rc;
+    info.bytes_d2h += (int64_t)(seq_bytes + qual_bytes - 2) + E * (int64_t)sizeof(catt_read);
+  }
+  CATT_CUDA(cudaEventRecord(c->ev[0], st));
+  CATT_CUDA(cudaStreamSynchronize(st));
+  { float x = 0, y = 0; cudaEventElapsedTime(&x, c->ev[5], c->ev[6]); cudaEventElapsedTime(&y, c->ev[7], c->ev[0]); info.ms_strings += x; info.ms_d2h += y; }
+  comm_lap(CATT_COLL_RESULT, c->ev[6], c->ev[7]);
+  tr.lap("B/N: strings + reduce + D2H");
   return CATT_OK;
 }
 

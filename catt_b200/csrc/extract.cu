@@ -151,25 +151,27 @@ __global__ void __launch_bounds__(EX_WARPS * 32) finder_raw_kernel(ReadsDev read
 }  // namespace
 
 int launch_extract(const RefDev& vref, const RefDev& jref, const ReadsDev& reads, const FinderDev* d_finder,
-                   const ExtractItem* d_items, ExtractOut* d_out, int64_t n, int kmer, int allow_v, int allow_j,
+                   const ExtractItem* d_items, ExtractOut* d_out, int64_t n, int kmer, int allow_v, int allow_j, int sm_count,
                    cudaStream_t st, int* launches) {
   if (n == 0) return CATT_OK;
   const size_t smem = sizeof(FinderDev) + sizeof(ExWarp) * EX_WARPS;
-  static bool attr = false;
-  if (!attr) { CATT_CUDA(cudaFuncSetAttribute(extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-  const int grid = (int)std::min<int64_t>((n + EX_WARPS - 1) / EX_WARPS, 148 * 8);
+  static std::atomic<unsigned long long> optin{0};
+  int rc = smem_optin(extract_kernel, (int)smem, optin);
+  if (rc) return rc;
+  const int grid = (int)std::min<int64_t>((n + EX_WARPS - 1) / EX_WARPS, (int64_t)sm_count * 8);
   extract_kernel<<<grid, EX_WARPS * 32, smem, st>>>(vref, jref, reads, d_finder, d_items, d_out, n, kmer, allow_v, allow_j);
   CATT_CUDA(cudaGetLastError());
   *launches += 1;
   return CATT_OK;
 }
 
-int launch_finder_raw(const ReadsDev& reads, const FinderDev* d_finder, int array_version, int32_t* d_out3, cudaStream_t st) {
+int launch_finder_raw(const ReadsDev& reads, const FinderDev* d_finder, int array_version, int32_t* d_out3, int sm_count, cudaStream_t st) {
   if (reads.n == 0) return CATT_OK;
   const size_t smem = sizeof(FinderDev) + sizeof(ExWarp) * EX_WARPS;
-  static bool attr = false;
-  if (!attr) { CATT_CUDA(cudaFuncSetAttribute(finder_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-  const int grid = (int)std::min<int64_t>((reads.n + EX_WARPS - 1) / EX_WARPS, 148 * 8);
+  static std::atomic<unsigned long long> optin{0};
+  int rc = smem_optin(finder_raw_kernel, (int)smem, optin);
+  if (rc) return rc;
+  const int grid = (int)std::min<int64_t>((reads.n + EX_WARPS - 1) / EX_WARPS, (int64_t)sm_count * 8);
   finder_raw_kernel<<<grid, EX_WARPS * 32, smem, st>>>(reads, d_finder, array_version, d_out3);
   CATT_CUDA(cudaGetLastError());
   return CATT_OK;

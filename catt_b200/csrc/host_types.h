@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 
+#include "comm.h"
 #include "internal.cuh"
 
 struct DeviceReads {
@@ -74,6 +75,7 @@ enum {
   SB_COUNT
 };
 enum { PIN_PACK0 = 0, PIN_PACK1, PIN_QUAL0, PIN_QUAL1, PIN_OFF, PIN_LEN, PIN_CNT, PIN_TEXT, PIN_RING0, PIN_RING1, PIN_QRID, PIN_QGATHER, PIN_QENTRY, PIN_COUNT };
+constexpr int SH_SLOTS = 48;  // scratch of the multi-GPU Stage B (assemble.cu: stage_b_sharded)
 constexpr int EV_A = 6;     // per reference set: seed start, seed end, expand end, sw end, select end
 
 struct catt_ctx {
@@ -100,6 +102,13 @@ struct catt_ctx {
   DevBuf rd_text, rd_nl, rd_name_beg, rd_name_end, rd_seq_beg, rd_qual_beg, rd_nwords;   // FASTQ text ingested on the device (ingest.cu)
   DevBuf recs_all[2];                     // one catt_aln per read and reference set, for the whole sample
   DevBuf sb[SB_COUNT];
+  DevBuf sh[SH_SLOTS];
+  // ---- one sample over several GPUs.  Either this context is rank 0 of an in-process group (catt_config.ngpu > 1: `peers` are the
+  //      contexts of ranks 1.., `comms[r]` the communicator of rank r) or it is one rank of a multi-process group (catt_ctx_join).
+  std::vector<catt_ctx*> peers;
+  std::vector<catt::Comm*> comms;
+  std::shared_ptr<catt::LocalGroup> lgroup;
+  catt::Comm* comm = nullptr;             // multi-process: this process' communicator
   PinBuf pin[PIN_COUNT];
   cudaEvent_t ev[8]{};
   cudaEvent_t ev_a[2][EV_A]{};            // Stage A stage boundaries per reference set
@@ -166,6 +175,17 @@ struct FileHits {
 };
 int stage_b(catt_ctx* c, int64_t n, const NamesDev& names, const ReadsDev& reads, const DeviceQuals& dq, const FileHits& fh, catt_result* R,
             int* launches);
+// Stage B of one sample spread over the ranks of `comm` (assemble.cu).  This rank holds reads [lo, lo + n_loc) of the concatenated
+// input files (records in c->recs_all, packed reads in c->rd_* with n_words words); the lists come out on rank `root`.
+struct ShardIn {
+  Comm* comm = nullptr;
+  int64_t lo = 0, n_loc = 0, n_words = 0;
+  std::vector<int64_t> gstart;            // global file boundaries (nfiles + 1)
+  std::vector<int64_t> bounds;            // global block boundaries of the ranks (nranks + 1)
+  int max_len = 0;                        // longest read of the whole sample
+  int root = 0;
+};
+int stage_b_sharded(catt_ctx* c, const ShardIn& in, const NamesDev& names, const DeviceQuals& dq, catt_result* R, int* launches);
 // FASTQ text of one input file, resident at d_text[t0, t1) -> spans + packed reads appended at read index `base` (ingest.cu)
 int ingest_fastq(catt_ctx* c, const char* d_text, int64_t t0, int64_t t1, int64_t base, uint64_t word_base, int64_t* n_out,
                  uint64_t* words_out, int* max_len, int* fallback, int* launches, cudaStream_t st);

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -21,6 +22,19 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     cudaError_t e__ = (call);                                                   \
     if (e__ != cudaSuccess) return ::catt::cuda_fail(e__, #call, __FILE__, __LINE__); \
   } while (0)
+
+// The opt-in to more than 48 KB of dynamic shared memory is a per-DEVICE attribute of a kernel: a process that drives several
+// GPUs (catt_config.ngpu, or one context per device) must set it on each of them.  One word per call site remembers the devices
+// of this process that already have it.
+template <class K> inline int smem_optin(K kernel, int bytes, std::atomic<unsigned long long>& done) {
+  int dev = 0;
+  CATT_CUDA(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return CATT_OK;
+  CATT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done.fetch_or(bit, std::memory_order_release);
+  return CATT_OK;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // limits and packing
@@ -184,9 +198,9 @@ struct ExtractOut {
   int32_t pad_;
 };
 int launch_extract(const RefDev& vref, const RefDev& jref, const ReadsDev& reads, const FinderDev* d_finder,
-                   const ExtractItem* d_items, ExtractOut* d_out, int64_t n, int kmer, int allow_v, int allow_j,
+                   const ExtractItem* d_items, ExtractOut* d_out, int64_t n, int kmer, int allow_v, int allow_j, int sm_count,
                    cudaStream_t st, int* launches);
-int launch_finder_raw(const ReadsDev& reads, const FinderDev* d_finder, int array_version, int32_t* d_out3, cudaStream_t st);
+int launch_finder_raw(const ReadsDev& reads, const FinderDev* d_finder, int array_version, int32_t* d_out3, int sm_count, cudaStream_t st);
 
 struct PoolItem {          // a Vpart/Jpart read as the k-mer table sees it
   uint32_t read;
@@ -209,10 +223,16 @@ struct OutDesc {           // everything the host needs to materialise one Myrea
   int16_t strand, kind, seq_off, seq_len, cdr3_off, cdr3_len, v_id, j_id, q_start1, j_pad;
   int32_t pad_;
 };
-struct KmerTable { unsigned long long* keys; unsigned long long* vals; uint64_t mask; };
-int launch_pool(const ReadsDev& reads, const PoolItem* d_items, int64_t n, int kmer, KmerTable tab, cudaStream_t st, int* launches);
+// open addressing, `nsub` sub-tables of `sub_slots` slots back to back (one GPU: nsub == 1); see pool.cu for the addressing
+struct KmerTable { unsigned long long* keys; unsigned long long* vals; uint64_t sub_slots; uint32_t nsub; };
+struct PoolEntry { unsigned long long key, val; };    // one (k-mer, order << 8 | position) pair on its way to the GPU that owns the key
+constexpr int KMER_MAX = 31;                            // one 2-bit packed u64 per k-mer, ~0 = empty slot
+int launch_pool(const ReadsDev& reads, const PoolItem* d_items, int64_t n, int kmer, KmerTable tab, int sm_count, cudaStream_t st, int* launches);
+int launch_pool_emit(const ReadsDev& reads, const PoolItem* d_items, int64_t n, int kmer, KmerTable tab, int pass, unsigned long long* d_cursor,
+                     PoolEntry* d_out, int sm_count, cudaStream_t st, int* launches);
+int launch_pool_insert(const PoolEntry* d_in, int64_t n, KmerTable tab, int sm_count, cudaStream_t st, int* launches);
 int launch_extend(const ReadsDev& reads, const FinderDev* d_finder, const PoolItem* d_items, const uint32_t* d_partial_idx,
-                  int64_t n_partial, int kmer, KmerTable tab, ExtendOut* d_out, uint32_t* d_rescued, cudaStream_t st, int* launches);
+                  int64_t n_partial, int kmer, KmerTable tab, ExtendOut* d_out, uint32_t* d_rescued, int sm_count, cudaStream_t st, int* launches);
 int launch_best_d(const char* d_cdr3, const int32_t* d_off, int64_t n, const char* d_dseq, const int32_t* d_doff, int nd,
                   int32_t* d_out, cudaStream_t st);
 

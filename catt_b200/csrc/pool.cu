@@ -31,42 +31,115 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {      // table slot hash 
   return x;
 }
 
-__device__ __forceinline__ void table_put(const KmerTable& t, uint64_t key, unsigned long long val) {
-  uint64_t slot = mix64(key) & t.mask;
+// Table addressing.  The table is `nsub` equal sub-tables laid back to back; a key lives in sub-table hash % nsub (the GPU that
+// owns the key when one sample is spread over several GPUs, shard.cu) at slot umulhi(hash, sub_slots) (no power-of-two rounding:
+// the load factor stays at 1/2 whatever the sample size), linear probing inside the sub-table.  One GPU: nsub == 1.
+__device__ __forceinline__ uint32_t table_sub(const KmerTable& t, uint64_t h) { return t.nsub == 1 ? 0u : (uint32_t)(h & 0xffffffffu) % t.nsub; }
+__device__ __forceinline__ void table_put_h(const KmerTable& t, uint64_t key, uint64_t h, unsigned long long val) {
+  const uint64_t base = (uint64_t)table_sub(t, h) * t.sub_slots;
+  uint64_t slot = __umul64hi(h, t.sub_slots);
   while (true) {
-    const unsigned long long prev = atomicCAS(&t.keys[slot], EMPTY, (unsigned long long)key);
-    if (prev == EMPTY || prev == key) { atomicMax(&t.vals[slot], val); return; }
-    slot = (slot + 1) & t.mask;
+    const unsigned long long prev = atomicCAS(&t.keys[base + slot], EMPTY, (unsigned long long)key);
+    if (prev == EMPTY || prev == key) { atomicMax(&t.vals[base + slot], val); return; }
+    if (++slot == t.sub_slots) slot = 0;
   }
+}
+// Warp-aggregated insert: lanes of the warp that hold the same key (reads of one clonotype share their k-mers) elect one lane,
+// which writes the largest (order, position) of the group - one atomic pair per distinct key instead of one per lane.
+__device__ __forceinline__ void table_put_warp(const KmerTable& t, bool active, uint64_t key, unsigned long long val) {
+  const unsigned live = __ballot_sync(FULL, active);
+  if (!active) return;
+  const unsigned peers = __match_any_sync(live, (unsigned long long)key);
+  unsigned long long best = val;
+  if (peers & (peers - 1)) {                                   // the group has more than one lane (rare): its maximum, by halves
+    const unsigned hi = __reduce_max_sync(peers, (unsigned)(val >> 32));
+    const unsigned lo = __reduce_max_sync(peers, (unsigned)(val >> 32) == hi ? (unsigned)val : 0u);
+    best = ((unsigned long long)hi << 32) | lo;
+  }
+  if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) table_put_h(t, key, mix64(key), best);
 }
 
 __device__ __forceinline__ int table_get(const KmerTable& t, uint64_t key, uint64_t gkey) {
   if (key == gkey) return 0;
-  uint64_t slot = mix64(key) & t.mask;
+  const uint64_t h = mix64(key);
+  const uint64_t base = (uint64_t)table_sub(t, h) * t.sub_slots;
+  uint64_t slot = __umul64hi(h, t.sub_slots);
   while (true) {
-    const unsigned long long k = t.keys[slot];
+    const unsigned long long k = t.keys[base + slot];
     if (k == EMPTY) return 0;
-    if (k == key) return (int)(t.vals[slot] & 0xff);
-    slot = (slot + 1) & t.mask;
+    if (k == key) return (int)(t.vals[base + slot] & 0xff);
+    if (++slot == t.sub_slots) slot = 0;
   }
 }
 
-// one warp per Vpart/Jpart read: lanes 0..10 insert the k-mers of the k+10 nt fragment
+// The k-mer at SAM position `pos` of a read WITHOUT N (reads with N never reach Vpart/Jpart, catt.jl:103,124,299), first base in
+// the most significant 2-bit group, straight from the packed words: one 2k-bit window, O(1) per k-mer instead of k base reads.
+// Forward strand: the window holds base pos in its lowest group -> reverse the groups.  Reverse strand: SAM base i is the
+// complement of read base len-1-i, so the window [len-pos-k, len-pos) already has the first SAM base on top -> complement only.
+__device__ __forceinline__ uint64_t kmer_at(const uint32_t* __restrict__ w, int len, int pos, int k, int strand) {
+  const int start = strand ? len - pos - k : pos;
+  const int o = 2 * start, wi = o >> 5, s = o & 31;
+  const uint64_t lo = (uint64_t)w[wi] | ((uint64_t)w[wi + 1] << 32);
+  uint64_t win = lo >> s;
+  if (s) win |= (uint64_t)w[wi + 2] << (64 - s);              // (the N-mask words and the buffer's padding follow: in bounds)
+  const uint64_t kmask = (1ull << (2 * k)) - 1;               // k <= 31
+  if (strand) return ~win & kmask;
+  uint64_t r = __brevll(win & kmask);                          // bit reversal, then swap the two bits of every group back
+  r = ((r & 0x5555555555555555ull) << 1) | ((r >> 1) & 0x5555555555555555ull);
+  return r >> (64 - 2 * k);
+}
+
+// (read, position) pair `t` of the pool: item t / 11, position t % 11 of its k+10 nt fragment; every lane of the warp owns one
+__device__ __forceinline__ bool pool_entry(const ReadsDev& reads, const PoolItem* __restrict__ items, int64_t t, int64_t n_entries, int k,
+                                           uint64_t* key, unsigned long long* val) {
+  if (t >= n_entries) return false;
+  const PoolItem pi = items[t / 11];
+  const int lane = (int)(t % 11);
+  const int f = min((int)pi.seq_len, k + 10);
+  if (lane >= f - k + 1) return false;
+  const int foff = pi.seq_off + (pi.side == 0 ? pi.seq_len - f : 0);     // last_serveral / first_serveral
+  *key = kmer_at(reads.words + reads.off[pi.read], reads.len[pi.read], foff + lane, k, pi.strand);
+  *val = ((unsigned long long)pi.order << 8) | (unsigned)(lane + 1);
+  return true;
+}
+
+// every (read, position): one lane, one window, one warp-aggregated insert
 __global__ void __launch_bounds__(PW * 32) pool_kernel(ReadsDev reads, const PoolItem* __restrict__ items, int64_t n, int k, KmerTable tab) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int64_t it = (int64_t)blockIdx.x * PW + warp; it < n; it += (int64_t)gridDim.x * PW) {
-    const PoolItem pi = items[it];
-    const int m = reads.len[pi.read];
-    const uint32_t* __restrict__ w = reads.words + reads.off[pi.read];
-    const uint32_t* __restrict__ nm = w + read_base_words(m);
-    const int f = min((int)pi.seq_len, k + 10);
-    const int foff = pi.seq_off + (pi.side == 0 ? pi.seq_len - f : 0);     // last_serveral / first_serveral
-    const int npos = f - k + 1;
-    if (lane < npos) {
-      uint64_t key = 0;
-      for (int i = 0; i < k; i++) key = (key << 2) | sam_code(w, nm, m, foff + lane + i, pi.strand);
-      table_put(tab, key, ((unsigned long long)pi.order << 8) | (unsigned)(lane + 1));
-    }
+  const int64_t n_entries = n * 11;
+  for (int64_t t0 = ((int64_t)blockIdx.x * PW + (threadIdx.x >> 5)) * 32; t0 < n_entries; t0 += (int64_t)gridDim.x * PW * 32) {
+    uint64_t key = 0; unsigned long long val = 0;
+    const bool ok = pool_entry(reads, items, t0 + (threadIdx.x & 31), n_entries, k, &key, &val);
+    table_put_warp(tab, ok, key, val);
+  }
+}
+
+// ---- one sample over several GPUs (shard.cu): the (k-mer, value) pairs of this GPU's reads, bucketed by the GPU that owns the
+//      key; the owners insert what they receive (pool_insert_kernel) and the sub-tables are all-gathered.
+//      pass 0 counts per owner, pass 1 scatters (cursor = exclusive offsets of the buckets, advanced by warp-aggregated atomics)
+template <int PASS>
+__global__ void __launch_bounds__(PW * 32) pool_emit_kernel(ReadsDev reads, const PoolItem* __restrict__ items, int64_t n, int k, KmerTable tab,
+                                                            unsigned long long* __restrict__ cursor, PoolEntry* __restrict__ out) {
+  const int64_t n_entries = n * 11;
+  for (int64_t t0 = ((int64_t)blockIdx.x * PW + (threadIdx.x >> 5)) * 32; t0 < n_entries; t0 += (int64_t)gridDim.x * PW * 32) {
+    uint64_t key = 0; unsigned long long val = 0;
+    const bool ok = pool_entry(reads, items, t0 + (threadIdx.x & 31), n_entries, k, &key, &val);
+    const unsigned live = __ballot_sync(FULL, ok);
+    if (!ok) continue;
+    const uint32_t dest = table_sub(tab, mix64(key));
+    const unsigned peers = __match_any_sync(live, dest);
+    const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(&cursor[dest], (unsigned long long)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    if (PASS == 1) out[base + __popc(peers & ((1u << lane) - 1))] = PoolEntry{key, val};
+  }
+}
+__global__ void __launch_bounds__(256) pool_insert_kernel(const PoolEntry* __restrict__ in, int64_t n, KmerTable tab) {
+  for (int64_t t0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ll; t0 < n; t0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = t0 + (threadIdx.x & 31);
+    PoolEntry e{0, 0};
+    if (t < n) e = in[t];
+    table_put_warp(tab, t < n, e.key, e.val);
   }
 }
 
@@ -197,22 +270,43 @@ __global__ void best_d_kernel(const char* __restrict__ cdr3, const int32_t* __re
 
 }  // namespace
 
-int launch_pool(const ReadsDev& reads, const PoolItem* d_items, int64_t n, int kmer, KmerTable tab, cudaStream_t st, int* launches) {
+int launch_pool(const ReadsDev& reads, const PoolItem* d_items, int64_t n, int kmer, KmerTable tab, int sm_count, cudaStream_t st, int* launches) {
   if (n == 0) return CATT_OK;
-  const int grid = (int)std::min<int64_t>((n + PW - 1) / PW, 148 * 16);
+  const int grid = (int)std::min<int64_t>((n * 11 + PW * 32 - 1) / (PW * 32), (int64_t)sm_count * 16);
   pool_kernel<<<grid, PW * 32, 0, st>>>(reads, d_items, n, kmer, tab);
   CATT_CUDA(cudaGetLastError());
   *launches += 1;
   return CATT_OK;
 }
 
+int launch_pool_emit(const ReadsDev& reads, const PoolItem* d_items, int64_t n, int kmer, KmerTable tab, int pass, unsigned long long* d_cursor,
+                     PoolEntry* d_out, int sm_count, cudaStream_t st, int* launches) {
+  if (n == 0) return CATT_OK;
+  const int grid = (int)std::min<int64_t>((n * 11 + PW * 32 - 1) / (PW * 32), (int64_t)sm_count * 16);
+  if (pass == 0) pool_emit_kernel<0><<<grid, PW * 32, 0, st>>>(reads, d_items, n, kmer, tab, d_cursor, d_out);
+  else pool_emit_kernel<1><<<grid, PW * 32, 0, st>>>(reads, d_items, n, kmer, tab, d_cursor, d_out);
+  CATT_CUDA(cudaGetLastError());
+  *launches += 1;
+  return CATT_OK;
+}
+
+int launch_pool_insert(const PoolEntry* d_in, int64_t n, KmerTable tab, int sm_count, cudaStream_t st, int* launches) {
+  if (n == 0) return CATT_OK;
+  const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count * 16);
+  pool_insert_kernel<<<grid, 256, 0, st>>>(d_in, n, tab);
+  CATT_CUDA(cudaGetLastError());
+  *launches += 1;
+  return CATT_OK;
+}
+
 int launch_extend(const ReadsDev& reads, const FinderDev* d_finder, const PoolItem* d_items, const uint32_t* d_partial_idx,
-                  int64_t n_partial, int kmer, KmerTable tab, ExtendOut* d_out, uint32_t* d_rescued, cudaStream_t st, int* launches) {
+                  int64_t n_partial, int kmer, KmerTable tab, ExtendOut* d_out, uint32_t* d_rescued, int sm_count, cudaStream_t st, int* launches) {
   if (n_partial == 0) return CATT_OK;
   const size_t smem = sizeof(FinderDev) + sizeof(ExtWarp) * PW;
-  static bool attr = false;
-  if (!attr) { CATT_CUDA(cudaFuncSetAttribute(extend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-  const int grid = (int)std::min<int64_t>((n_partial + PW - 1) / PW, 148 * 8);
+  static std::atomic<unsigned long long> optin{0};
+  int rc = smem_optin(extend_kernel, (int)smem, optin);
+  if (rc) return rc;
+  const int grid = (int)std::min<int64_t>((n_partial + PW - 1) / PW, (int64_t)sm_count * 8);
   extend_kernel<<<grid, PW * 32, smem, st>>>(reads, d_finder, d_items, d_partial_idx, n_partial, kmer, tab, d_out, d_rescued);
   CATT_CUDA(cudaGetLastError());
   *launches += 1;

@@ -399,12 +399,9 @@ int launch_seed(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int 
   const int t2_smem = t2_bytes <= T2_SMEM_MAX_BYTES ? t2_bytes : 0;
   const int ml = (reads.max_len + 31) & ~31;
   const size_t smem = ((warp_scratch_bytes(ml) + 15) & ~(size_t)15) * SEED_WARPS + t2_smem;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CATT_CUDA(cudaFuncSetAttribute(seed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CATT_CUDA(cudaFuncSetAttribute(seed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> optin0{0}, optin1{0};
+  int rc;
+  if ((rc = smem_optin(seed_kernel<false>, 200 * 1024, optin0)) || (rc = smem_optin(seed_kernel<true>, 200 * 1024, optin1))) return rc;
   int per_sm = 0;
   CATT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seed_kernel<false>, SEED_WARPS * 32, smem));
   if (per_sm < 1) per_sm = 1;

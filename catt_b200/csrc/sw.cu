@@ -300,12 +300,9 @@ int launch_sw_t(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks, c
   const int tb_smem = (sel_bytes + tb_bytes <= 100 * 1024) ? tb_bytes : 0;
   const size_t smem = sel_bytes + tb_smem;
   auto k = sw_score_kernel<G, C, TRACK>;
-  static bool attr = false;
-  static int per_sm = 0;
-  if (!attr) {
-    CATT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
-  }
+  static std::atomic<unsigned long long> optin{0};
+  int per_sm = 0;
+  { const int rc = smem_optin(k, 200 * 1024, optin); if (rc) return rc; }
   CATT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, SW_THREADS, smem));
   if (per_sm < 1) per_sm = 1;
   const int64_t ntasks_max = TRACK ? (cap + 1) / 2 : cap;
@@ -450,12 +447,9 @@ int launch_sw_bulk(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks
   const int ml = (reads.max_len + 1 + 15) & ~15;                 // room for the phantom row of odd-length reads
   const size_t smem = (size_t)GPB * (PROFW * 4 + ml);
   auto k = sw_bulk2_kernel<G, C>;
-  static bool attr = false;
-  static int per_sm = 0;
-  if (!attr) {
-    CATT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
-  }
+  static std::atomic<unsigned long long> optin{0};
+  int per_sm = 0;
+  { const int rc = smem_optin(k, 200 * 1024, optin); if (rc) return rc; }
   CATT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, SW_THREADS, smem));
   if (per_sm < 1) per_sm = 1;
   const int64_t want = (cap + GPB - 1) / GPB;
@@ -796,8 +790,8 @@ int launch_select(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, ca
     set_error("traceback tile (%zu bytes) exceeds shared memory", smem);
     return CATT_E_LIMIT;
   }
-  static size_t attr = 0;
-  if (smem > attr) { CATT_CUDA(cudaFuncSetAttribute(traceback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+  static std::atomic<unsigned long long> optin{0};
+  if ((rc = smem_optin(traceback_kernel, 220 * 1024, optin))) return rc;
   traceback_kernel<<<sm_count * 4, 32, smem, st>>>(ref, reads, ab.gapped_list, ab.counters, recs);
   CATT_CUDA(cudaGetLastError());
   *launches += 4;

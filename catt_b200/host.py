@@ -147,11 +147,19 @@ def set_host_threads(n: int = 0):
     _lib.check(_lib.load().catt_set_host_threads(n))
 
 
+def comm_id() -> bytes:
+    """128-byte id of a new multi-process GPU group (rank 0 creates it, the launcher's channel carries it to the other ranks)."""
+    buf = (C.c_uint8 * 128)()
+    _lib.check(_lib.load().catt_comm_id(buf))
+    return bytes(buf)
+
+
 class Catt:
-    """One CATT configuration bound to one GPU (catt_ctx)."""
+    """One CATT configuration bound to one GPU (catt_ctx) - or, with `ngpu` > 1, to a group of GPUs of this process that
+    share every sample (catt_config.ngpu / devices; same calls, same results)."""
 
     def __init__(self, species="hs", chain="TRB", region="CDR3", resource_dir=None, bowsc=12, kmer=10000, thread=1,
-                 allow_v=3, allow_j=9, device=0, chain_cfg=None, keep_records=False, chunk_reads=0, only_cdr3=False):
+                 allow_v=3, allow_j=9, device=0, chain_cfg=None, keep_records=False, chunk_reads=0, only_cdr3=False, ngpu=1, devices=None):
         L = _lib.load()
         cc = chain_cfg or chain_config(species, chain, region, resource_dir)
         self.chain_cfg = cc
@@ -160,7 +168,10 @@ class Catt:
                       (C.c_char_p * max(len(d), 1))(*[x[1].encode() for x in d])]
         cfg = _lib.Config(cc["vregion"].encode(), cc["jregion"].encode(), cc["cmotif"].encode(), cc["fmotif"].encode(),
                           cc["innerC"].encode(), cc["innerF"].encode(), cc["coffset"], cc["foffset"], bowsc, kmer, thread,
-                          allow_v, allow_j, device, len(d), self._keep[0], self._keep[1], int(keep_records), int(chunk_reads), int(only_cdr3), 0)
+                          allow_v, allow_j, device, len(d), self._keep[0], self._keep[1], int(keep_records), int(chunk_reads), int(only_cdr3),
+                          int(ngpu), (C.c_int32 * len(devices))(*devices) if devices else None)
+        if devices and len(devices) != ngpu:
+            raise ValueError("one device ordinal per rank")
         h = C.c_void_p()
         _lib.check(L.catt_ctx_create(C.byref(h), C.byref(cfg)))
         self._h = h
@@ -222,6 +233,22 @@ class Catt:
         h = C.c_void_p()
         _lib.check(_lib.load().catt_run_reads(self._h, n, _addr(name_buf), name_off.ctypes.data, _addr(seq_buf), seq_off.ctypes.data,
                                               _addr(qual_buf) if qual_buf is not None else None, C.byref(h)))
+        return Result(self, h)
+
+    # -- one sample over several GPUs, one process per GPU ------------------------------------------------------
+    def join(self, nranks: int, rank: int, id128: bytes):
+        """Collective: this context becomes rank `rank` of a multi-process GPU group (catt_ctx_join, ncclCommInitRank)."""
+        buf = (C.c_uint8 * 128)(*id128)
+        _lib.check(_lib.load().catt_ctx_join(self._h, nranks, rank, buf))
+
+    def mainflow_shard(self, n_total, lo, n_local, name_buf, name_off, seq_buf, seq_off, qual_buf, file_start=None) -> Result:
+        """Collective: every rank passes ITS block [lo, lo + n_local) of the sample (offsets local to its buffers); the lists
+        come back on rank 0, the counters on every rank."""
+        fs = np.ascontiguousarray(file_start if file_start is not None else [0, n_total], dtype=np.int64)
+        h = C.c_void_p()
+        _lib.check(_lib.load().catt_run_reads_shard(self._h, n_total, lo, n_local, _addr(name_buf), name_off.ctypes.data, _addr(seq_buf),
+                                                    seq_off.ctypes.data, _addr(qual_buf) if qual_buf is not None else None, len(fs) - 1,
+                                                    fs.ctypes.data, C.byref(h)))
         return Result(self, h)
 
     def selBestMatchD(self, seqs):

@@ -7,7 +7,8 @@
  *
  * Conventions: every function returns 0 on success or a negative CATT_E_* code; catt_last_error() returns a
  * thread-local message.  No exception crosses the ABI.  The library owns every buffer it returns until
- * catt_result_free().  One context per (process, GPU); calls on a context are blocking and must not overlap.
+ * catt_result_free().  One context per (process, GPU) - or one context for a group of GPUs (catt_config.ngpu); calls on a
+ * context are blocking and must not overlap.
  * There is NO CPU fallback: without a usable CUDA device catt_ctx_create fails with CATT_E_CUDA.
  */
 #ifndef CATT_B200_H
@@ -58,7 +59,15 @@ typedef struct catt_config {
                                1: as they stand after catt.jl:581-582, `filter!(x -> x.cdr3 != "None", ...)` - the only reads the
                                rest of catt() ever touches; catt_info still carries the counts of the full lists for the log
                                lines.  Cuts the device->host traffic ~50x on typical samples. */
-  int32_t reserved_;
+  int32_t ngpu;             /* <= 1: one GPU (`device`).  N > 1: ONE sample is spread over N GPUs of this process: the reads are
+                               split into N contiguous blocks, seeding / SW / assignV,J / finder! / extension run on every block's GPU,
+                               and the global steps of the reference - the SAM order and QNAME dedup (catt.jl:45-48), share_name and
+                               the both-mapped pairing (catt.jl:237, 288-319), the last-writer-wins k-mer table (catt.jl:426-497,
+                               544-548) and the final lists - are merged over NCCL / NVLink.  The calls and the results are the same
+                               as with one GPU (bit-identical lists); catt_info.ms_coll / bytes_coll report the exchange. */
+  const int32_t* devices;   /* ngpu CUDA device ordinals; NULL = 0 .. ngpu-1.  Repeated ordinals are allowed (several ranks on one
+                               GPU, exchanging through peer copies instead of NCCL): that is how the multi-rank path is tested on
+                               a single-GPU box. */
 } catt_config;
 
 /* One SAM-visible alignment record = the line `bwa mem | samtools ... | awk` would leave for one read against one
@@ -118,7 +127,25 @@ typedef struct catt_info {
   double ms_strings;          /* the kernel that writes the Myread strings into the result arenas */
   int64_t bytes_h2d, bytes_d2h; /* bytes the library copied host->device / device->host for this result */
   double ms_j_stream;         /* Stage A of the J reference set (seed + sw + select), on its own stream under the V kernels */
+  /* ---- one sample over several GPUs (catt_config.ngpu > 1 or catt_ctx_join); all zero on one GPU.  Counters above are sums over
+   *      the ranks, stage times the maximum over the ranks. */
+  int32_t n_ranks;            /* GPUs that shared this sample */
+  int32_t reserved2_;
+  double ms_comm;             /* device time inside collectives (maximum over the ranks) = sum of ms_coll */
+  int64_t bytes_comm;         /* bytes received over NVLink, summed over the ranks = sum of bytes_coll */
+  double ms_coll[8];          /* per collective, CATT_COLL_* below */
+  int64_t bytes_coll[8];
+  double ms_stage_a_max, ms_stage_a_min;   /* wall time of the slowest / fastest rank's Stage A (host clock around its pipeline) */
 } catt_info;
+
+/* indices of catt_info.ms_coll / bytes_coll */
+#define CATT_COLL_RECORDS 0     /* all-gather of the mapped reads' alignment records + QNAMEs (global SAM order / dedup / pairing) */
+#define CATT_COLL_MATES 1       /* all-reduce of the packed reads of both-mapped pairs whose records sit on two GPUs */
+#define CATT_COLL_FLAGS 2       /* all-reduce of one byte per work item: kept / list / partial -> positions in [Vpart; Jpart] */
+#define CATT_COLL_KMER_A2A 3    /* all-to-all of (k-mer, order << 8 | position) pairs to the GPU that owns the key */
+#define CATT_COLL_KMER_TABLE 4  /* all-gather of the merged k-mer sub-tables (the table is replicated for the extension) */
+#define CATT_COLL_SIZES 5       /* all-reduce of the string sizes of the returned reads -> global arena offsets */
+#define CATT_COLL_RESULT 6      /* sum-reduce of the result arenas to the root */
 
 /* ---- lifecycle --------------------------------------------------------------------------------------------- */
 /* Loads the V/J references (what `bwa index` + FASTA.Reader do, catt.jl:198-205) and builds the device tables. */
@@ -134,6 +161,19 @@ int catt_set_host_threads(int32_t n);
 int catt_ref_count(const catt_ctx* ctx, int which /*0=V,1=J*/);
 const char* catt_ref_name(const catt_ctx* ctx, int which, int32_t id);      /* FASTA.identifier, catt.jl:202 */
 int catt_ref_seq(const catt_ctx* ctx, int which, int32_t id, char* out, int32_t cap); /* alignment bases; returns length */
+
+/* ---- one sample over several GPUs, one PROCESS per GPU (torchrun / MPI style launchers) ------------------------------------------
+ * The in-process form needs nothing but catt_config.ngpu.  With one process per GPU, rank 0 calls catt_comm_id and hands the
+ * 128 bytes to the other ranks through the launcher's own channel; every rank then creates its context (ngpu <= 1, its own
+ * device) and calls catt_ctx_join (collective: ncclCommInitRank).  catt_run_reads_shard is then called by EVERY rank with its
+ * contiguous block [lo, lo + n_local) of the sample's reads (blocks in rank order, together covering 0 .. n_total);
+ * file_start are the GLOBAL file boundaries (nfiles + 1 entries, 0 .. n_total) as in catt_run_reads_files.  Rank 0 receives
+ * the lists; every rank receives the (identical) counters. */
+int catt_comm_id(uint8_t id[128]);
+int catt_ctx_join(catt_ctx* ctx, int32_t nranks, int32_t rank, const uint8_t id[128]);
+int catt_run_reads_shard(catt_ctx* ctx, int64_t n_total, int64_t lo, int64_t n_local, const char* names, const int64_t* name_off,
+                         const char* seqs, const int64_t* seq_off, const char* quals, int32_t nfiles, const int64_t* file_start,
+                         catt_result** out);
 
 /* ---- the hot path ------------------------------------------------------------------------------------------- */
 /* Replaces input_convert (catt.jl:134-151) + read_alignrs (catt.jl:186-339) + the k-mer pool / extension /
