@@ -1,16 +1,21 @@
 #!/usr/bin/env python3
-"""bench.py — reads/s and DP GCUPS of the CDR3 extraction hot path on synthetic hs-TRB reads (BASELINE.json configs[2]).
+"""bench.py — reads/s and DP GCUPS of the CDR3 extraction hot path on ONE sample of synthetic hs-TRB reads (BASELINE.json configs[2]:
+100 M x 150 bp), on 1 GPU or split over the N GPUs of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--reads-per-step R] [--length 150] [--impl gpu|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--reads 100000000] [--length 150] [--impl gpu|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-A step = one pass of the whole hot path (seeding, SW, selection, ordering/dedup, assign/finder, k-mer table, extension)
-over one batch of R synthetic 150-bp reads per GPU (SURVEY §8d config-3 generator, read i drawn from splitmix64(seed+i)).
-  value : reads/s with the packed batch already resident in HBM (catt_batch_align + catt_batch_assemble)
-  e2e   : reads/s through the public call catt_run_reads with HOST buffers (packing, H2D, all kernels, D2H, host glue)
-  roofline : the SW kernel against the measured integer-ALU (packed DPX add-max) issue peak of this GPU
+A step = one pass of the whole hot path (seeding, SW, selection, ordering/dedup, assign/finder, k-mer table, extension) over THE
+sample (SURVEY 8d config-3 generator, read i drawn from splitmix64(seed+i)).  With N > 1 the same sample is split into N contiguous
+blocks, one per rank (strong scaling): the per-read stages run on each block's GPU, the global steps of the reference (SAM order /
+QNAME dedup / V-J join, last-writer-wins k-mer table, result lists) are merged over NCCL by the library's own communicator
+(catt_ctx_join; torch.distributed only carries the 128-byte id, the barrier and the timing max).
+  value : reads/s with the sample already resident in HBM (catt_shard_upload once, catt_shard_run per step)
+  e2e   : reads/s through the public call with HOST buffers (catt_run_reads / catt_run_reads_shard: staging, H2D, kernels, collectives, D2H)
+  one_sample : result digest (identical on every N), Stage A spread over the ranks, per-collective time and bytes, limiting collective
+  roofline : the SW kernel against the measured integer-ALU (packed DPX add-max) issue peak of the GPU(s)
+  replicas : round 1's weak-scaling number (every GPU its own 2 M-read sample, no exchange)
   cpu_baseline : the CPU oracle (OpenMP restatement of the reference path, not the Julia program) on a bounded sample
-With N > 1 every rank runs its own shard of R reads (weak scaling, shards are independent samples, no data-path collective).
 `--impl reference` times the CPU restatement on all host cores on the same workload (rank 0 only).
 """
 from __future__ import annotations
@@ -89,7 +94,16 @@ def ncu_traffic():
         return None
 
 
-def roofline_other(infos, length, world):
+def ncu_pipe_alu():
+    """sm__inst_executed_pipe_alu (% of peak) of the dominant kernel from the committed ncu capture, None when absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            return json.load(fh).get("sw_bulk2_kernel_pipe_alu_pct")
+    except Exception:
+        return None
+
+
+def roofline_other(infos, length, world, n_total):
     """The two HBM-side kernels of SURVEY 8d against the measured copy bandwidth (MEASURED_PEAKS.json, else the recipe's fallback).
     Algorithmic bytes: seeding = packed read in (ceil(L/4) + ceil(L/8) B) + the two candidate bitmaps and the task count out per
     read and reference set; k-mer table = 16 B per insert, 11 inserts per Vpart/Jpart read.  Both kernels are latency / random-
@@ -100,11 +114,11 @@ def roofline_other(infos, length, world):
     except Exception:
         peak, src = 6650.0, "fallback (B200_PROFILING.md)"
     i = infos[-1]
-    n = i["n_reads"]
+    n = n_total / world                          # per GPU (the stage times are the slowest GPU's)
     ms_seed = sum(x["ms_seed_kernel"] for x in infos) / len(infos)
     ms_pool = sum(x["ms_pool_kernel"] for x in infos) / len(infos)
     seed_bytes = n * ((-(-length // 4) + -(-length // 8)) * 2 + 2 * 4 * (11 + 1) + 2 * 4)      # CW = 11 words (V) + 1 (J)
-    pool_bytes = 16 * 11 * (i["vpart"] + i["jpart"])
+    pool_bytes = 16 * 11 * (i["vpart"] + i["jpart"]) / world
     out = {}
     if ms_seed > 0:
         a = world * seed_bytes / (ms_seed * 1e-3) / 1e9
@@ -170,17 +184,23 @@ def file_e2e(ctx, np, R, length, seq_buf, qual_buf, first):
             "note": "catt_run_file on a FASTQ in the page cache, median of 3 calls after 1 warm-up; QNAMEs are zero-padded read numbers"}
 
 
-def dilute(np, seq_buf, qual_buf, n, length, tcr_fraction, seed):
+def dilute(np, seq_buf, qual_buf, lo, hi, length, tcr_fraction, seed):
     """RNA-seq-like mix (BASELINE configs[1] substitute): keep a fraction of the TCR-derived reads, replace the
-    rest by uniform-random ACGT reads (deterministic in `seed`)."""
-    if tcr_fraction >= 1.0:
+    rest by uniform-random ACGT reads.  Decided per GLOBAL read index (1 Mi-read tiles, each with its own generator), so the sample
+    is the same however it is split over GPUs.  seq_buf / qual_buf hold reads [lo, hi)."""
+    if tcr_fraction >= 1.0 or hi <= lo:
         return
-    rng = np.random.default_rng(seed)
-    noise = rng.random(n) >= tcr_fraction
-    k = int(noise.sum())
-    seqs = seq_buf.reshape(n, length)
-    seqs[noise] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=(k, length), dtype=np.uint8)]
-    qual_buf.reshape(n, length)[noise] = ord("I")
+    tile = 1 << 20
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    seqs, quals = seq_buf.reshape(hi - lo, length), qual_buf.reshape(hi - lo, length)
+    for t0 in range(lo - lo % tile, hi, tile):
+        rng = np.random.default_rng(seed + t0)
+        noise = rng.random(tile) >= tcr_fraction
+        bases = rng.integers(0, 4, size=(tile, length), dtype=np.uint8)
+        a, b = max(t0, lo), min(t0 + tile, hi)
+        sel = np.nonzero(noise[a - t0:b - t0])[0]
+        seqs[(a - lo) + sel] = lut[bases[(a - t0) + sel]]
+        quals[(a - lo) + sel] = ord("I")
 
 
 def cpu_reference_run(fx, length, n_sample, first_index=0, species="hs", chain="TRB", tcr_fraction=1.0):
@@ -191,7 +211,7 @@ def cpu_reference_run(fx, length, n_sample, first_index=0, species="hs", chain="
     cc = chain_config(species, chain, "CDR3", os.path.join(fx, "resource"))
     V, J = O.RefSet(cc["vregion"]), O.RefSet(cc["jregion"])
     seqs, quals = O.synth_reads(V, J, n_sample, length, first_index=first_index, seed=SEED)
-    dilute(np, seqs, quals, n_sample, length, tcr_fraction, SEED + first_index)
+    dilute(np, seqs, quals, first_index, first_index + n_sample, length, tcr_fraction, SEED)
     cfg = O.make_config(cc)
     t0 = time.perf_counter()
     R = O.run_flat(V, J, cfg, seqs, quals, first_index=first_index, threads=len(os.sched_getaffinity(0)))   # explicit: torchrun exports OMP_NUM_THREADS=1
@@ -204,7 +224,10 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--reads-per-step", type=int, default=2_000_000)
+    ap.add_argument("--reads", "--reads-per-step", dest="reads", type=int, default=100_000_000,
+                    help="reads of THE sample (BASELINE configs[2]: 100 M); every step runs the whole sample, split over the GPUs")
+    ap.add_argument("--replica-reads", type=int, default=2_000_000, help="reads per GPU of the small side measurements (0 = skip)")
+    ap.add_argument("--e2e-steps", type=int, default=5, help="timed host-buffer calls (at most --steps)")
     ap.add_argument("--length", type=int, default=150)
     ap.add_argument("--species", default="hs", help="other BASELINE configs: ms / pig (configs[4])")
     ap.add_argument("--chain", default="TRB", help="TRA / IGH / ... (configs[3] with --length 50)")
@@ -219,9 +242,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cores = len(os.sched_getaffinity(0)) or 1
-    workload = f"synthetic {args.species} {args.chain} {args.length}bp reads from IMGT V/J with random CDR3 insertions (BASELINE configs[2], SURVEY 8d config 3)"
+    workload = (f"one sample of {args.reads} synthetic {args.species} {args.chain} {args.length}bp reads from IMGT V/J with random CDR3 insertions "
+                "(BASELINE configs[2], SURVEY 8d config 3)")
     if (args.species, args.chain, args.length, args.tcr_fraction) != ("hs", "TRB", 150, 1.0):
-        workload = (f"synthetic {args.species} {args.chain} {args.length}bp reads, TCR-derived fraction {args.tcr_fraction} "
+        workload = (f"one sample of {args.reads} synthetic {args.species} {args.chain} {args.length}bp reads, TCR-derived fraction {args.tcr_fraction} "
                     "(one of the other BASELINE configs; same generator, SURVEY 8d)")
 
     # ------------------------------------------------------------------------------------------------- reference arm
@@ -242,9 +266,10 @@ def main():
         value = n * args.steps / t_tot
         line = {"impl": "reference", "metric": "reads_per_sec", "value": value, "unit": "reads/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+                "scaling": "strong", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
                 "gcups": cells / t_tot / 1e9,
-                "config": {"workload": workload, "reads_per_step": n, "read_length": args.length, "chain": f"{args.species} {args.chain}",
+                "config": {"workload": workload, "sample_reads": args.reads, "reads_per_step": n, "read_length": args.length, "chain": f"{args.species} {args.chain}",
+                           "step": f"a bounded sample of the workload: {n} reads of the same generator per step (the CPU path at full size would take hours)",
                            "note": "CPU restatement of the reference path (oracle, OpenMP) - the Julia+bwa+samtools program cannot run here"},
                 "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": "port",
                                  "sample": f"{args.steps} x {n} reads of the same generator"},
@@ -271,8 +296,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    from catt_b200.host import Catt, set_host_threads
+    from catt_b200 import _lib
+    from catt_b200.host import Catt, comm_id, set_host_threads
     from catt_b200.refg import chain_config
+    from catt_b200.shard import shard_bounds
     fx = fixture_dir()
     cc = chain_config(args.species, args.chain, "CDR3", os.path.join(fx, "resource"))
     # one process per GPU: every rank gets its share of the host cores (torchrun exports OMP_NUM_THREADS=1)
@@ -282,23 +309,38 @@ def main():
     # the production setting of INTEGRATION.md: the lists as catt() uses them (after catt.jl:581-582); e2e_full_lists below measures
     # the same call returning every Vpart/Jpart read
     ctx = Catt(chain_cfg=cc, device=local_rank, only_cdr3=True)
-    R = args.reads_per_step
-    first = rank * R
-    name_buf, name_off, seq_buf, seq_off, qual_buf = ctx.synth_reads(R, args.length, first_index=first, seed=SEED)
-    dilute(np, seq_buf, qual_buf, R, args.length, args.tcr_fraction, SEED + first)
+    if world > 1:                                  # ONE sample over the ranks: the library's own NCCL communicator (catt_ctx_join)
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(comm_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        ctx.join(world, rank, bytes(idt.cpu().numpy().tobytes()))
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
-
     peak_ops, peak_ms = ctx.alu_peak()            # packed DPX add-max thread-instructions per second
 
-    # ---- value: batch resident in HBM
-    batch = ctx.upload(R, seq_buf, seq_off, first_ordinal=first)
+    # ---- the sample: args.reads synthetic reads, read i drawn from splitmix64(seed + i); this rank generates ITS block
+    n_total = args.reads
+    lo, hi = shard_bounds(n_total, world, rank)
+    n_loc = hi - lo
+    t_gen = time.perf_counter()
+    name_buf, name_off, seq_buf, seq_off, qual_buf = ctx.synth_reads(n_loc, args.length, first_index=lo, seed=SEED)
+    dilute(np, seq_buf, qual_buf, lo, hi, args.length, args.tcr_fraction, SEED)
+    t_gen = time.perf_counter() - t_gen
 
-    def step_resident():
-        batch.align()
-        res = batch.assemble(name_buf, name_off, seq_buf, seq_off, qual_buf)
+    def run_e2e():
+        if world > 1:
+            return ctx.mainflow_shard(n_total, lo, n_loc, name_buf, name_off, seq_buf, seq_off, qual_buf)
+        return ctx.mainflow_buffers(n_total, name_buf, name_off, seq_buf, seq_off, qual_buf)
+
+    # ---- value: the sample resident in HBM (packed reads, QNAMEs, quality strings); a step = the whole hot path over the whole sample
+    ctx.shard_upload(n_total, lo, n_loc, name_buf, name_off, seq_buf, seq_off, qual_buf)
+
+    def step_resident(keep=False):
+        res = ctx.shard_run()
         info = res.info
+        dig = res.digest() if keep else None
         res.close()
-        return info
+        return info, dig
 
     for _ in range(args.warmup):
         step_resident()
@@ -308,25 +350,31 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     ev0.record(stream)
-    infos = [step_resident() for _ in range(args.steps)]
+    infos, digest = [], None
+    for k in range(args.steps):
+        inf, dg = step_resident(keep=(k == args.steps - 1))
+        infos.append(inf)
+        digest = dg or digest
     ev1.record(stream)
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     ev_ms = ev0.elapsed_time(ev1)
     dev_ms = max(wall_ms, ev_ms)
 
-    # ---- e2e: host buffers through the public call
-    def step_e2e():
-        res = ctx.mainflow_buffers(R, name_buf, name_off, seq_buf, seq_off, qual_buf)
-        info = res.info
-        res.close()
-        return info
-
-    for _ in range(max(2, min(args.warmup, 3))):
-        step_e2e()
+    # ---- e2e: the same sample from HOST buffers through the public call (catt_run_reads / catt_run_reads_shard): staging copies,
+    #      H2D, every kernel, the collectives, D2H of the lists - all inside the timed region
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    for _ in range(2):
+        run_e2e().close()
     barrier()
     t0 = time.perf_counter()
-    e2e_infos = [step_e2e() for _ in range(args.steps)]
+    e2e_infos, e2e_digest = [], None
+    for k in range(e2e_steps):
+        res = run_e2e()
+        e2e_infos.append(res.info)
+        if k == e2e_steps - 1:
+            e2e_digest = res.digest()
+        res.close()
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     sampler.stop_flag = True
@@ -337,72 +385,112 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(t[0]), float(t[1])
 
-    info = infos[-1]
+    info = infos[-1]                                            # counters are sums over the ranks, stage times the slowest rank's
+    ei = e2e_infos[-1]
     cells = info["cells_v"]                                     # the V reference set: its DP kernel is the one the roofline is about
     sw_ms = sum(i["ms_sw"] for i in infos) / len(infos)         # (the J set, ~3 % of the cells, runs concurrently on its own stream)
-    achieved = 12.0 * cells / (sw_ms * 1e-3)                    # algorithmic int ops/s (12 per cell)
-    peak = peak_ops * 4.0                                       # a packed add-max retires 2 adds + 2 max per thread-instruction
-    ei = e2e_infos[-1]
-    packed_bytes = R * (4 * ((args.length + 15) // 16 + (args.length + 31) // 32) + 8)
-    # counted by the library from the buffers it copies: H2D = packed reads + offsets/lengths, quality strings, QNAMEs + offsets;
-    # D2H = the two string arenas + one 48-byte catt_read per Vpart/Jpart read + the counters
+    achieved = 12.0 * cells / (sw_ms * 1e-3)                    # algorithmic int ops/s (12 per cell), all GPUs
+    peak = peak_ops * 4.0 * world                               # a packed add-max retires 2 adds + 2 max per thread-instruction
+    executed = 12.0 * info["cells_computed_v"] / (sw_ms * 1e-3)
+    packed_bytes = n_loc * (4 * ((args.length + 15) // 16 + (args.length + 31) // 32) + 8)
     h2d, d2h = ei["bytes_h2d"], ei["bytes_d2h"]
+    stage_keys = ("ms_seed", "ms_sw", "ms_select", "ms_order", "ms_extract", "ms_pool", "ms_strings", "ms_d2h", "ms_host", "ms_pack", "ms_j_stream",
+                  "ms_comm", "ms_stage_a_max", "ms_stage_a_min")
+
+    def coll_block(inf_list):
+        ms = [sum(i["ms_coll"][k] for i in inf_list) / len(inf_list) for k in range(len(_lib.COLL_NAMES))]
+        by = [inf_list[-1]["bytes_coll"][k] for k in range(len(_lib.COLL_NAMES))]
+        rows = {nm: {"ms": ms[k], "bytes_received_all_ranks": by[k]} for k, nm in enumerate(_lib.COLL_NAMES)}
+        top = max(range(len(ms)), key=lambda k: ms[k])
+        return {"per_collective": rows, "limiting": _lib.COLL_NAMES[top] if world > 1 else None,
+                "ms_total": sum(ms), "bytes_total": sum(by)}
 
     line = {
-        "metric": "reads_per_sec", "value": world * R * args.steps / (dev_ms * 1e-3), "unit": "reads/s", "n_gpus": world,
+        "metric": "reads_per_sec", "value": n_total * args.steps / (dev_ms * 1e-3), "unit": "reads/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-        "config": {"workload": workload, "reads_per_step_per_gpu": R, "read_length": args.length, "chain": f"{args.species} {args.chain}",
-                   "l2": f"packed batch {packed_bytes >> 20} MiB per step vs 126 MB L2" + (" (larger than L2)" if packed_bytes > 126e6 else " (compute-bound kernel; see DESIGN.md)"),
-                   "multi_gpu": "shards are independent samples; no data-path collective", "host_threads_per_rank": host_threads,
+        "scaling": "strong", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+        "config": {"workload": workload, "sample_reads": n_total, "reads_per_gpu": n_loc, "read_length": args.length, "chain": f"{args.species} {args.chain}",
+                   "step": "ONE sample of sample_reads reads through the whole hot path; with N GPUs the SAME sample is split into N contiguous blocks "
+                           "(strong scaling) and the global steps - SAM order / QNAME dedup / V-J join, the last-writer-wins k-mer table, the result lists - "
+                           "are merged over NCCL (catt_ctx_join + catt_shard_run / catt_run_reads_shard)",
+                   "l2": f"packed block {packed_bytes >> 20} MiB per GPU and step vs 126 MB L2" + (" (larger than L2)" if packed_bytes > 126e6 else " (compute-bound kernels; see DESIGN.md)"),
+                   "host_threads_per_rank": host_threads, "generate_s": t_gen,
                    "result": "only_cdr3 = 1: Vpart/Jpart as they stand after catt.jl:581-582 (the reads catt() goes on to use); counters of the full lists in info"},
-        "gcups": world * cells / (sw_ms * 1e-3) / 1e9,
-        "gcups_note": "DP cell updates of the V reference set / its SW-kernel time (CUDA events on its stream, in the library), summed over GPUs",
-        "stage_ms": {k: sum(i[k] for i in infos) / len(infos) for k in ("ms_seed", "ms_sw", "ms_select", "ms_order", "ms_extract", "ms_pool", "ms_strings", "ms_d2h", "ms_host", "ms_pack", "ms_j_stream")},
+        "gcups": cells / (sw_ms * 1e-3) / 1e9,
+        "gcups_note": "DP cell updates of the V reference set, all GPUs / the slowest GPU's SW-kernel time (CUDA events on its stream, in the library)",
+        "stage_ms": {k: sum(i[k] for i in infos) / len(infos) for k in stage_keys},
         "timing": {"wall_ms_per_step": wall_ms / args.steps, "cuda_event_ms_per_step": ev_ms / args.steps},
-        "e2e_stage_ms": {k: sum(i[k] for i in e2e_infos) / len(e2e_infos) for k in ("ms_seed", "ms_sw", "ms_select", "ms_order", "ms_extract", "ms_pool", "ms_strings", "ms_d2h", "ms_host", "ms_pack", "ms_j_stream")},
-        "e2e": {"value": world * R * args.steps / (e2e_ms * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": e2e_ms / args.steps},
+        "e2e_stage_ms": {k: sum(i[k] for i in e2e_infos) / len(e2e_infos) for k in stage_keys},
+        "e2e": {"value": n_total * e2e_steps / (e2e_ms * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps, "warmup": 2,
+                "note": "catt_run_reads (1 GPU) / catt_run_reads_shard (N GPUs) on pageable host buffers; bytes summed over the GPUs"},
         "gpu_launches": int(sum(i["kernel_launches"] for i in infos)),
         "clocks": sampler.summary(),
+        "one_sample": {"reads": n_total, "n_ranks": max(1, info["n_ranks"]), "ms_resident": dev_ms / args.steps, "ms_e2e": e2e_ms / e2e_steps,
+                       "result_digest": {"vpart": f"{digest[0]:016x}", "jpart": f"{digest[1]:016x}", "e2e_vpart": f"{e2e_digest[0]:016x}", "e2e_jpart": f"{e2e_digest[1]:016x}",
+                                         "note": "order-sensitive digest of every returned read (catt_result_digest): the same on 1, 2, 4 and 8 GPUs"},
+                       "stage_a_ms_slowest_rank": info["ms_stage_a_max"], "stage_a_ms_fastest_rank": info["ms_stage_a_min"],
+                       "collectives": coll_block(infos), "collectives_e2e": coll_block(e2e_infos),
+                       "transport": "NCCL (library-owned communicator, ncclCommInitRank) over NVLink" if world > 1 else "none (one GPU)"},
         "roofline": {"bound": "alu", "kernel": "sw_bulk2_kernel<4,25> (V) + <4,8> (J)", "achieved": achieved / 1e12, "peak": peak / 1e12,
-                     "unit": "Tiop/s", "frac": achieved / peak, "traffic": ncu_traffic(),
-                     "note": "achieved = 12 int ops x algorithmic DP cells of the V reference set (every scored (read, record, strand) pair, len x len) / its SW kernel time; "
-                             "byte-identical records are computed once and the kernel issues 4.5 ALU-pipe instructions per cell pair, so frac can "
-                             "approach or pass 1; peak = measured packed-DPX (VIADDMNMX.S16x2) issue rate x 4 "
-                             f"int16 ops per thread-instruction ({peak_ops / 1e12:.2f} T thread-instr/s, this GPU, in-repo microbenchmark); "
+                     "unit": "Tiop/s", "frac": achieved / peak, "frac_executed": executed / peak, "traffic": ncu_traffic(),
+                     "cells_algorithmic_v": int(cells), "cells_computed_v": int(info["cells_computed_v"]),
+                     "alu_instr_per_cell_pair": 4.5, "ncu_pipe_alu_pct": ncu_pipe_alu(),
+                     "note": "achieved = 12 int ops x ALGORITHMIC DP cells of the V reference set (every scored (read, record, strand) pair, len x len) / its SW kernel time; "
+                             "frac_executed counts only the cells the kernel computes (byte-identical records are scored once); the kernel issues 4.5 ALU-pipe "
+                             "instructions per cell pair where the 12-op model implies 6, so neither is pipe utilisation - ncu_pipe_alu_pct is (profiles/); "
+                             "peak = measured packed-DPX (VIADDMNMX.S16x2) issue rate x 4 "
+                             f"int16 ops per thread-instruction ({peak_ops / 1e12:.2f} T thread-instr/s per GPU, in-repo microbenchmark) x GPUs; "
                              "MEASURED_PEAKS.json has no integer entry"},
-        "roofline_other": roofline_other(infos, args.length, world),
-        "counters": {k: info[k] for k in ("v_hits", "j_hits", "vpart", "jpart", "direct", "left", "rescued", "cand_v", "cand_j", "gapped_v")},
+        "roofline_other": roofline_other(infos, args.length, world, n_total),
+        "counters": {k: info[k] for k in ("v_hits", "j_hits", "v_final", "j_final", "share", "vpart", "jpart", "direct", "left", "rescued", "cand_v", "cand_j", "gapped_v")},
     }
-    if rank == 0 and world == 1:
+
+    # ---- side measurements on a small batch (2 M reads per GPU): independent samples per GPU (the round-1 weak-scaling number),
+    #      full lists, file input, the nbsorb scans, the CPU baseline
+    R = min(args.replica_reads, n_loc)
+    if R > 0:
+        rb = ctx.synth_reads(R, args.length, first_index=rank * R, seed=SEED + 7)
+        for _ in range(2):
+            ctx.mainflow_buffers(R, *rb).close()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            ctx.mainflow_buffers(R, *rb).close()
+        barrier()
+        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        line["replicas"] = {"value": world * R * 3 / float(tt[0]), "unit": "reads/s", "reads_per_gpu_per_step": R, "steps": 3,
+                            "note": "weak scaling: every GPU runs its OWN sample of reads_per_gpu_per_step reads (catt_run_reads from host buffers), no exchange"}
+    if rank == 0 and world == 1 and R > 0:
         ctx_full = Catt(chain_cfg=cc, device=local_rank)
         for _ in range(2):
-            ctx_full.mainflow_buffers(R, name_buf, name_off, seq_buf, seq_off, qual_buf).close()
+            ctx_full.mainflow_buffers(R, *rb).close()
         t0 = time.perf_counter()
         fi = None
-        for _ in range(args.steps):
-            rr = ctx_full.mainflow_buffers(R, name_buf, name_off, seq_buf, seq_off, qual_buf)
+        for _ in range(3):
+            rr = ctx_full.mainflow_buffers(R, *rb)
             fi = rr.info
             rr.close()
         dtf = time.perf_counter() - t0
-        line["e2e_full_lists"] = {"value": R * args.steps / dtf, "unit": "reads/s", "ms_per_step": 1e3 * dtf / args.steps,
+        line["e2e_full_lists"] = {"value": R * 3 / dtf, "unit": "reads/s", "ms_per_step": 1e3 * dtf / 3, "reads_per_step": R,
                                   "h2d_bytes_per_step": fi["bytes_h2d"], "d2h_bytes_per_step": fi["bytes_d2h"],
                                   "note": "only_cdr3 = 0: every Vpart/Jpart read comes back, cdr3 == None included (the lists before catt.jl:581)"}
         ctx_full.close()
-    if rank == 0 and world == 1 and not args.no_file_e2e:
-        line["e2e_file"] = file_e2e(ctx, np, R, args.length, seq_buf, qual_buf, first)
+    if rank == 0 and world == 1 and not args.no_file_e2e and R > 0:
+        line["e2e_file"] = file_e2e(ctx, np, R, args.length, rb[2], rb[4], rank * R)
         line["nbsorb_scans"] = nbsorb_scans(ctx, np, peak_ops)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
         n = args.cpu_sample or max(16000, 15000 * cores)       # ~15 s of CPU work on `cores` threads
         rps, dt, cinfo = cpu_reference_run(fx, args.length, n, species=args.species, chain=args.chain, tcr_fraction=args.tcr_fraction)
         line["cpu_baseline"] = {"value": rps, "unit": "reads/s", "cores": cores, "kind": "port",
-                                "sample": f"first {n} reads of the same generator, {dt:.1f} s; CPU restatement (oracle, OpenMP), not the Julia program",
+                                "sample": f"first {n} reads of the same generator, {dt:.1f} s; CPU restatement (oracle, OpenMP, scalar full-matrix SW at -O2, "
+                                          "~0.27 GCUPS per core), not the Julia + bwa + samtools program",
                                 "gcups": (cinfo["cells_v"] + cinfo["cells_j"]) / dt / 1e9}
     if rank == 0:
         print(json.dumps(line))
-    batch.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

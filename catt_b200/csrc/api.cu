@@ -192,13 +192,14 @@ int stage_a_range(catt_ctx* c, const DeviceReads& dr, int64_t lo, int64_t hi, in
   return CATT_OK;
 }
 
-int stage_a_resident(catt_ctx* c, const DeviceReads& dr, int64_t first_ordinal, FileHits* fh, catt_info* info, int* launches) {
+int stage_a_resident(catt_ctx* c, const DeviceReads& dr, int64_t first_ordinal, FileHits* fh, catt_info* info, int* launches,
+                     const std::vector<int64_t>* file_ordinal0 = nullptr) {
   int rc;
   if ((rc = ensure_recs(c, dr.n)) || (rc = presize_align(c, dr.n))) return rc;
   const int nfiles = (int)fh->start.size() - 1;
   fh->v.assign(nfiles, 0); fh->j.assign(nfiles, 0);
   for (int f = 0; f < nfiles; f++)
-    if ((rc = stage_a_range(c, dr, fh->start[f], fh->start[f + 1], first_ordinal, f, fh, info, launches))) return rc;
+    if ((rc = stage_a_range(c, dr, fh->start[f], fh->start[f + 1], file_ordinal0 ? (*file_ordinal0)[f] : first_ordinal, f, fh, info, launches))) return rc;
   return CATT_OK;
 }
 
@@ -211,6 +212,7 @@ int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool
   const int64_t n = hr.n;
   int rc;
   const double t0 = now_ms();
+  c->shard.valid = false;                          // the read buffers are about to be overwritten (catt_shard_upload re-validates)
   if ((rc = c->pin[PIN_OFF].ensure((size_t)(n + 1) * sizeof(uint32_t))) || (rc = c->pin[PIN_LEN].ensure((size_t)std::max<int64_t>(n, 1) * sizeof(int32_t)))) return rc;
   uint32_t* h_off = c->pin[PIN_OFF].as<uint32_t>();
   int32_t* h_len = c->pin[PIN_LEN].as<int32_t>();
@@ -229,7 +231,7 @@ int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool
   if ((rc = c->rd_seqoff.ensure((size_t)(n + 1) * sizeof(int64_t)))) return rc;
   const int64_t* d_seqoff = c->rd_seqoff.as<int64_t>();
   // the per-read offset / length tables travel with their chunk (stage_chunk) instead of in one unhidden copy up front
-  if (want_quals && dq && n > 0 && c->only_cdr3) {
+  if (want_quals && dq && n > 0 && c->only_cdr3 && !c->resident_quals) {
     dq->seq_off = d_seqoff;                       // the strings follow later, for the reads that keep a CDR3 only (assemble.cu)
     dq->host_quals = hr.quals; dq->host_seq_off = hr.seq_off;
   } else if (want_quals && dq && n > 0) {
@@ -798,25 +800,35 @@ void block_bounds(int64_t n, int nranks, int r, int64_t* lo, int64_t* hi) {
   *hi = *lo + base + (r < extra ? 1 : 0);
 }
 
+// This block's share of every input file; bwa's read ordinal restarts with every file (catt.jl:143-147).
+int rank_files(int64_t n_total, int64_t lo, int64_t n_loc, const std::vector<int64_t>& gstart, FileHits* fh, std::vector<int64_t>* ord0) {
+  const int nfiles = (int)gstart.size() - 1;
+  if (nfiles < 1 || gstart.front() != 0 || gstart.back() != n_total || lo < 0 || lo + n_loc > n_total) {
+    set_error("GPU group: block [%lld, %lld) outside the sample of %lld reads", (long long)lo, (long long)(lo + n_loc), (long long)n_total);
+    return CATT_E_ARG;
+  }
+  fh->start = {0};
+  ord0->clear();
+  for (int f = 0; f < nfiles; f++) {
+    const int64_t a = std::min(std::max(gstart[f], lo), lo + n_loc), b = std::min(std::max(gstart[f + 1], lo), lo + n_loc);
+    fh->start.push_back(b - lo);
+    ord0->push_back(a - gstart[f]);
+  }
+  return CATT_OK;
+}
+
+int rank_finish(catt_ctx* c, Comm* comm, int root, int64_t n_total, int64_t lo, int64_t n_loc, const std::vector<int64_t>& gstart, const NamesDev& nd,
+                const DeviceQuals& dq, int max_len, double ms_a, int rc, std::unique_ptr<catt_result>& R, int launches, catt_result** out);
+
 // One rank: Stage A on this rank's block `hr` (reads [lo, lo + hr.n) of the sample), then its part of the global Stage B.
 // `gstart` are the global file boundaries.  Every rank returns a result; the lists are on `root`.
 int run_rank(catt_ctx* c, Comm* comm, int root, int64_t n_total, int64_t lo, const HostReads& hr, const std::vector<int64_t>& gstart, catt_result** out) {
   std::unique_ptr<catt_result> R(new catt_result());
   int launches = 0, rc;
   Trace tr;
-  const int N = comm->nranks;
-  const int64_t n_loc = hr.n;
-  const int nfiles = (int)gstart.size() - 1;
-  if (nfiles < 1 || gstart.front() != 0 || gstart.back() != n_total || lo < 0 || lo + n_loc > n_total) { set_error("GPU group: block [%lld, %lld) outside the sample of %lld reads", (long long)lo, (long long)(lo + n_loc), (long long)n_total); return CATT_E_ARG; }
-  // this block's share of every input file; bwa's read ordinal restarts with every file (catt.jl:143-147)
   FileHits fh;
   std::vector<int64_t> ord0;
-  fh.start = {0};
-  for (int f = 0; f < nfiles; f++) {
-    const int64_t a = std::min(std::max(gstart[f], lo), lo + n_loc), b = std::min(std::max(gstart[f + 1], lo), lo + n_loc);
-    fh.start.push_back(b - lo);
-    ord0.push_back(a - gstart[f]);
-  }
+  if ((rc = rank_files(n_total, lo, hr.n, gstart, &fh, &ord0))) return rc;
   DeviceReads dr;
   DeviceQuals dq;
   NamesDev nd;
@@ -826,8 +838,16 @@ int run_rank(catt_ctx* c, Comm* comm, int root, int64_t n_total, int64_t lo, con
                       [&]() { return upload_names(c, hr.n, hr.names, hr.name_off, &nd, &Rp->info, c->copy_stream); }, &ord0);
   const double ms_a = now_ms() - t0;
   tr.lap("run_rank: pack + H2D + align (pipelined)");
+  return rank_finish(c, comm, root, n_total, lo, hr.n, gstart, nd, dq, dr.max_len, ms_a, rc, R, launches, out);
+}
+
+// Everything after this rank's Stage A: the first exchange (block bounds + status), the global Stage B, the merged counters.
+int rank_finish(catt_ctx* c, Comm* comm, int root, int64_t n_total, int64_t lo, int64_t n_loc, const std::vector<int64_t>& gstart, const NamesDev& nd,
+                const DeviceQuals& dq, int max_len, double ms_a, int rc, std::unique_ptr<catt_result>& R, int launches, catt_result** out) {
+  Trace tr;
+  const int N = comm->nranks;
   // a rank that failed must still answer the first exchange, or its peers would wait for it forever: the status travels with the bounds
-  long long mine[4] = {lo, n_loc, rc ? -1 : (long long)dr.max_len, rc};
+  long long mine[4] = {lo, n_loc, rc ? -1 : (long long)max_len, rc};
   std::vector<long long> all((size_t)4 * N);
   int rc2 = comm->host_allgather(mine, all.data(), sizeof mine, c->stream);
   if (rc) return rc;
@@ -858,7 +878,7 @@ int run_rank(catt_ctx* c, Comm* comm, int root, int64_t n_total, int64_t lo, con
     }
   }
   if ((rc = stage_b_sharded(c, in, nd, dq, R.get(), &launches))) return rc;
-  tr.lap("run_rank: stage_b_sharded");
+  tr.lap("rank_finish: stage_b_sharded");
   // counters: sums over the ranks; stage times: the slowest rank
   catt_info& I = R->info;
   I.kernel_launches = launches;
@@ -1273,6 +1293,87 @@ int catt_run_reads_shard(catt_ctx* c, int64_t n_total, int64_t lo, int64_t n_loc
   HostReads hr;
   hr.n = n_local; hr.names = names; hr.name_off = n_local ? name_off : zero_off; hr.seqs = seqs; hr.seq_off = n_local ? seq_off : zero_off; hr.quals = quals;
   return run_rank(c, c->comm, 0, n_total, lo, hr, fs, out);
+}
+
+// Resident form of catt_run_reads_shard (bench.py's `value`): catt_shard_upload moves this rank's block to HBM - packed reads,
+// QNAMEs, quality strings - and catt_shard_run, which may be called repeatedly, runs Stage A on the resident block and the global
+// Stage B with every input already on the device.
+int catt_shard_upload(catt_ctx* c, int64_t n_total, int64_t lo, int64_t n_local, const char* names, const int64_t* name_off, const char* seqs,
+                      const int64_t* seq_off, const char* quals, int32_t nfiles, const int64_t* file_start) {
+  if (!c || n_total < 0 || lo < 0 || n_local < 0 || nfiles < 1 || !file_start || (n_local > 0 && (!names || !name_off || !seqs || !seq_off))) {
+    set_error("catt_shard_upload: bad argument");
+    return CATT_E_ARG;
+  }
+  if (!c->peers.empty()) { set_error("catt_shard_upload: not available on an in-process GPU group (use one process per GPU)"); return CATT_E_ARG; }
+  CATT_CUDA(cudaSetDevice(c->device));
+  static const int64_t zero_off[1] = {0};
+  HostReads hr;
+  hr.n = n_local; hr.names = names; hr.name_off = n_local ? name_off : zero_off; hr.seqs = seqs; hr.seq_off = n_local ? seq_off : zero_off; hr.quals = quals;
+  catt_ctx::Shard& S = c->shard;
+  S = catt_ctx::Shard{};
+  S.gstart.assign(file_start, file_start + nfiles + 1);
+  int rc;
+  if ((rc = rank_files(n_total, lo, n_local, S.gstart, &S.fh, &S.ord0))) return rc;
+  catt_info info{};
+  int launches = 0;
+  FileHits fh = S.fh;
+  c->resident_quals = true;
+  rc = stage_a_stream(c, hr, 0, false, true, &S.dr, &S.dq, &fh, &info, &launches);      // pack + upload only
+  c->resident_quals = false;
+  if (rc) return rc;
+  if ((rc = upload_names(c, n_local, hr.names, hr.name_off, &S.nd, &info))) return rc;
+  CATT_CUDA(cudaStreamSynchronize(c->stream));
+  S.n_total = n_total; S.lo = lo; S.valid = true;
+  return CATT_OK;
+}
+
+int catt_shard_run(catt_ctx* c, catt_result** out) {
+  if (!c || !out) { set_error("catt_shard_run: null argument"); return CATT_E_ARG; }
+  catt_ctx::Shard& S = c->shard;
+  if (!S.valid) { set_error("catt_shard_run: call catt_shard_upload first"); return CATT_E_ARG; }
+  CATT_CUDA(cudaSetDevice(c->device));
+  std::unique_ptr<catt_result> R(new catt_result());
+  int launches = 0;
+  FileHits fh = S.fh;
+  // (a previous run may have grown - moved - the read buffers to append the mates of straddling pairs)
+  S.dr.words = c->rd_words.as<uint32_t>(); S.dr.off = c->rd_off.as<uint32_t>(); S.dr.len = c->rd_len.as<int32_t>();
+  const double t0 = now_ms();
+  int rc = stage_a_resident(c, S.dr, 0, &fh, &R->info, &launches, &S.ord0);
+  const double ms_a = now_ms() - t0;
+  if (!c->comm) {                                     // one GPU: the block is the sample
+    if (rc) return rc;
+    if (S.lo != 0 || S.dr.n != S.n_total) { set_error("catt_shard_run: the context is not part of a GPU group (catt_ctx_join) but holds a partial block"); return CATT_E_ARG; }
+    R->info.n_reads = S.n_total;
+    fh.start = S.gstart;
+    if ((rc = stage_b(c, S.dr.n, S.nd, S.dr.view(), S.dq, fh, R.get(), &launches))) return rc;
+    R->info.kernel_launches = launches;
+    R->info.ms_stage_a_max = R->info.ms_stage_a_min = ms_a;
+    *out = R.release();
+    return CATT_OK;
+  }
+  c->last_n = S.dr.n; c->last_max_len = S.dr.max_len;   // (last_words is what the upload left)
+  return rank_finish(c, c->comm, 0, S.n_total, S.lo, S.dr.n, S.gstart, S.nd, S.dq, S.dr.max_len, ms_a, rc, R, launches, out);
+}
+
+// Order-sensitive digest of both result lists (every field of every catt_read and both strings): equal digests = identical lists.
+int catt_result_digest(const catt_result* r, uint64_t out[2]) {
+  if (!r || !out) return CATT_E_ARG;
+  for (int which = 0; which < 2; which++) {
+    const catt_read* rd = r->part[which];
+    const int64_t n = r->npart[which];
+    uint64_t acc = 0;
+    #pragma omp parallel for reduction(+ : acc) schedule(static)
+    for (int64_t i = 0; i < n; i++) {
+      uint64_t h = 0xcbf29ce484222325ull ^ (uint64_t)i * 0x9E3779B97F4A7C15ull;
+      auto mix = [&](const void* p, size_t len) { const unsigned char* b = (const unsigned char*)p; for (size_t k = 0; k < len; k++) { h ^= b[k]; h *= 0x100000001b3ull; } };
+      mix(rd[i].seq, (size_t)rd[i].seq_len); mix(rd[i].qual, (size_t)rd[i].qual_len);
+      mix(&rd[i].seq_len, 4 * 7); mix(&rd[i].able, 2);
+      h ^= h >> 29; h *= 0xbf58476d1ce4e5b9ull; h ^= h >> 32;
+      acc += h;
+    }
+    out[which] = acc ^ ((uint64_t)n * 0x94d049bb133111ebull);
+  }
+  return CATT_OK;
 }
 
 int catt_result_info(const catt_result* r, catt_info* out) { if (!r || !out) return CATT_E_ARG; *out = r->info; return CATT_OK; }

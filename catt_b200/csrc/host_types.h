@@ -78,6 +78,26 @@ enum { PIN_PACK0 = 0, PIN_PACK1, PIN_QUAL0, PIN_QUAL1, PIN_OFF, PIN_LEN, PIN_CNT
 constexpr int SH_SLOTS = 48;  // scratch of the multi-GPU Stage B (assemble.cu: stage_b_sharded)
 constexpr int EV_A = 6;     // per reference set: seed start, seed end, expand end, sw end, select end
 
+// QNAMEs in HBM: name i = s[beg[i], end[i]).  Host-supplied names are contiguous (beg = off, end = off + 1); names parsed on the
+// device point into the FASTQ text.
+struct NamesDev { const char* s = nullptr; const int64_t* beg = nullptr; const int64_t* end = nullptr; };
+
+// quality strings of the sample in HBM (uploaded under the Stage A kernels); quals == nullptr for FASTA input
+struct DeviceQuals {
+  const char* quals = nullptr; const int64_t* seq_off = nullptr;
+  // only_cdr3 with host buffers: the quality strings stay on the host until Stage B knows the few reads that keep a CDR3; their
+  // strings are then gathered and uploaded (host_quals + host_seq_off = the caller's buffers)
+  const char* host_quals = nullptr; const int64_t* host_seq_off = nullptr;
+};
+
+namespace catt {
+// per input file of the sample (paired-end = two files, catt.jl:738-745): first read, mapped V / J records
+struct FileHits {
+  std::vector<int64_t> start, v, j;
+  void single(int64_t n, int64_t vh, int64_t jh) { start = {0, n}; v = {vh}; j = {jh}; }
+};
+}  // namespace catt
+
 struct catt_ctx {
   catt::RefSet V, J;
   catt::FinderDev finder{};
@@ -109,6 +129,14 @@ struct catt_ctx {
   std::vector<catt::Comm*> comms;
   std::shared_ptr<catt::LocalGroup> lgroup;
   catt::Comm* comm = nullptr;             // multi-process: this process' communicator
+  bool resident_quals = false;            // stage_a_stream: keep the quality strings on the device even with only_cdr3
+  struct Shard {                          // catt_shard_upload / catt_shard_run: this rank's block, resident in the rd_* / name buffers
+    bool valid = false;
+    int64_t n_total = 0, lo = 0;
+    std::vector<int64_t> gstart, ord0;
+    catt::FileHits fh;
+    DeviceReads dr; DeviceQuals dq; NamesDev nd;
+  } shard;
   PinBuf pin[PIN_COUNT];
   cudaEvent_t ev[8]{};
   cudaEvent_t ev_a[2][EV_A]{};            // Stage A stage boundaries per reference set
@@ -116,18 +144,6 @@ struct catt_ctx {
   cudaEvent_t ev_q[2]{};                  // ... and the quality staging buffer
   std::vector<cudaEvent_t> ev_piece;      // file input: piece k of the FASTQ text has reached the device
   DevBuf rd_raw[2];                       // raw bases of the chunk in flight (packed on the device)
-};
-
-// QNAMEs in HBM: name i = s[beg[i], end[i]).  Host-supplied names are contiguous (beg = off, end = off + 1); names parsed on the
-// device point into the FASTQ text.
-struct NamesDev { const char* s = nullptr; const int64_t* beg = nullptr; const int64_t* end = nullptr; };
-
-// quality strings of the sample in HBM (uploaded under the Stage A kernels); quals == nullptr for FASTA input
-struct DeviceQuals {
-  const char* quals = nullptr; const int64_t* seq_off = nullptr;
-  // only_cdr3 with host buffers: the quality strings stay on the host until Stage B knows the few reads that keep a CDR3; their
-  // strings are then gathered and uploaded (host_quals + host_seq_off = the caller's buffers)
-  const char* host_quals = nullptr; const int64_t* host_seq_off = nullptr;
 };
 
 struct catt_batch {
@@ -168,11 +184,6 @@ struct Trace {
 };
 // Stage B (assemble.cu): everything after the per-read alignment records exist.  The records are read from
 // c->recs_all[0/1] on the device; names/seqs/quals are host buffers (names are uploaded, strings are materialised on the host).
-// per input file of the sample (paired-end = two files, catt.jl:738-745): first read, mapped V / J records
-struct FileHits {
-  std::vector<int64_t> start, v, j;
-  void single(int64_t n, int64_t vh, int64_t jh) { start = {0, n}; v = {vh}; j = {jh}; }
-};
 int stage_b(catt_ctx* c, int64_t n, const NamesDev& names, const ReadsDev& reads, const DeviceQuals& dq, const FileHits& fh, catt_result* R,
             int* launches);
 // Stage B of one sample spread over the ranks of `comm` (assemble.cu).  This rank holds reads [lo, lo + n_loc) of the concatenated

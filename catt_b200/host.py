@@ -79,6 +79,12 @@ class Result:
         buf = (C.c_char * (n.value * _lib.ALN_DTYPE.itemsize)).from_address(p.value)
         return np.frombuffer(buf, dtype=_lib.ALN_DTYPE).copy()
 
+    def digest(self):
+        """(Vpart digest, Jpart digest): order-sensitive 64-bit digests of every field and string of the two lists."""
+        out = (C.c_uint64 * 2)()
+        _lib.check(_lib.load().catt_result_digest(self._h, out))
+        return int(out[0]), int(out[1])
+
     def close(self):
         if self._h:
             _lib.load().catt_result_free(self._h)
@@ -249,6 +255,18 @@ class Catt:
         _lib.check(_lib.load().catt_run_reads_shard(self._h, n_total, lo, n_local, _addr(name_buf), name_off.ctypes.data, _addr(seq_buf),
                                                     seq_off.ctypes.data, _addr(qual_buf) if qual_buf is not None else None, len(fs) - 1,
                                                     fs.ctypes.data, C.byref(h)))
+        return Result(self, h)
+
+    def shard_upload(self, n_total, lo, n_local, name_buf, name_off, seq_buf, seq_off, qual_buf, file_start=None):
+        """This rank's block to HBM (packed reads, QNAMEs, quality strings), for repeated `shard_run` calls."""
+        fs = np.ascontiguousarray(file_start if file_start is not None else [0, n_total], dtype=np.int64)
+        _lib.check(_lib.load().catt_shard_upload(self._h, n_total, lo, n_local, _addr(name_buf), name_off.ctypes.data, _addr(seq_buf),
+                                                 seq_off.ctypes.data, _addr(qual_buf) if qual_buf is not None else None, len(fs) - 1, fs.ctypes.data))
+
+    def shard_run(self) -> Result:
+        """Collective: Stage A on the resident block + the global Stage B (lists on rank 0)."""
+        h = C.c_void_p()
+        _lib.check(_lib.load().catt_shard_run(self._h, C.byref(h)))
         return Result(self, h)
 
     def selBestMatchD(self, seqs):

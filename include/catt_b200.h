@@ -175,6 +175,14 @@ int catt_run_reads_shard(catt_ctx* ctx, int64_t n_total, int64_t lo, int64_t n_l
                          const char* seqs, const int64_t* seq_off, const char* quals, int32_t nfiles, const int64_t* file_start,
                          catt_result** out);
 
+/* Resident form of catt_run_reads_shard, for throughput measurements with the inputs already in HBM (bench.py `value`):
+ * catt_shard_upload copies this rank's block to the device once (packed reads, QNAMEs, quality strings); catt_shard_run - collective,
+ * repeatable - runs seeding / SW / selection on the resident block and then the global Stage B.  Without catt_ctx_join the block
+ * must be the whole sample (lo = 0, n_local = n_total) and the call is the one-GPU path. */
+int catt_shard_upload(catt_ctx* ctx, int64_t n_total, int64_t lo, int64_t n_local, const char* names, const int64_t* name_off,
+                      const char* seqs, const int64_t* seq_off, const char* quals, int32_t nfiles, const int64_t* file_start);
+int catt_shard_run(catt_ctx* ctx, catt_result** out);
+
 /* ---- the hot path ------------------------------------------------------------------------------------------- */
 /* Replaces input_convert (catt.jl:134-151) + read_alignrs (catt.jl:186-339) + the k-mer pool / extension /
  * finder!(array) part of catt() (catt.jl:544-577) for one single-end FASTQ/FASTA(.gz) file. */
@@ -208,6 +216,9 @@ int catt_bam_to_fastq(const char* bam_path, const char* fastq_path);
 int catt_inflate_file(const char* path, const char* out_path, int32_t* method);
 
 int catt_result_info(const catt_result* r, catt_info* out);
+/* Order-sensitive 64-bit digests of Vpart (out[0]) and Jpart (out[1]) - every catt_read field and both strings of every entry:
+ * equal digests = identical lists (used to show that a sample gives the same result on 1, 2, 4 and 8 GPUs). */
+int catt_result_digest(const catt_result* r, uint64_t out[2]);
 /* Vpart (which=0) / Jpart (1) in the reference's list order, ready for catt.jl:579 onwards. */
 int catt_result_reads(const catt_result* r, int which, const catt_read** reads, int64_t* n);
 /* Per-read alignment records (input order, one per read; unmapped reads have mapped=0): parity/diagnostics.
