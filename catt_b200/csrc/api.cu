@@ -1376,6 +1376,35 @@ int catt_result_digest(const catt_result* r, uint64_t out[2]) {
   return CATT_OK;
 }
 
+// Canonical digest of a list as TEXT (what Julia would see): per entry FNV-1a over seq 0x1f qual 0x1f V name 0x1f J name 0x1f cdr3
+// 0x1f able, mixed with the entry's position, summed.  Independent of ids and offsets, so any implementation of the path can
+// compute it (the test oracle does) and two runs can be compared without moving the lists.
+int catt_result_text_digest(const catt_ctx* c, const catt_result* r, uint64_t out[2]) {
+  if (!c || !r || !out) return CATT_E_ARG;
+  for (int which = 0; which < 2; which++) {
+    const catt_read* rd = r->part[which];
+    const int64_t n = r->npart[which];
+    uint64_t acc = 0;
+    #pragma omp parallel for reduction(+ : acc) schedule(static)
+    for (int64_t i = 0; i < n; i++) {
+      uint64_t h = 0xcbf29ce484222325ull ^ ((uint64_t)i * 0x9E3779B97F4A7C15ull);
+      auto mix = [&](const char* p, size_t len) { for (size_t k = 0; k < len; k++) { h ^= (unsigned char)p[k]; h *= 0x100000001b3ull; } h ^= 0x1f; h *= 0x100000001b3ull; };
+      const catt_read& e = rd[i];
+      mix(e.seq, (size_t)e.seq_len); mix(e.qual, (size_t)e.qual_len);
+      const std::string* vn = e.v_id >= 0 && e.v_id < (int)c->V.names.size() ? &c->V.names[e.v_id] : nullptr;
+      const std::string* jn = e.j_id >= 0 && e.j_id < (int)c->J.names.size() ? &c->J.names[e.j_id] : nullptr;
+      if (vn) mix(vn->data(), vn->size()); else mix("None", 4);
+      if (jn) mix(jn->data(), jn->size()); else mix("None", 4);
+      if (e.cdr3_off >= 0) mix(e.seq + e.cdr3_off, (size_t)e.cdr3_len); else mix("None", 4);
+      h ^= (uint64_t)(e.able ? 1 : 0); h *= 0x100000001b3ull;
+      h ^= h >> 29; h *= 0xbf58476d1ce4e5b9ull; h ^= h >> 32;
+      acc += h;
+    }
+    out[which] = acc ^ ((uint64_t)n * 0x94d049bb133111ebull);
+  }
+  return CATT_OK;
+}
+
 int catt_result_info(const catt_result* r, catt_info* out) { if (!r || !out) return CATT_E_ARG; *out = r->info; return CATT_OK; }
 int catt_result_reads(const catt_result* r, int which, const catt_read** reads, int64_t* n) {
   if (!r || !reads || !n || which < 0 || which > 1) return CATT_E_ARG;

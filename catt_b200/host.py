@@ -85,6 +85,12 @@ class Result:
         _lib.check(_lib.load().catt_result_digest(self._h, out))
         return int(out[0]), int(out[1])
 
+    def text_digest(self):
+        """(Vpart, Jpart) digests over the lists as text (seq, qual, V name, J name, cdr3, able): comparable across implementations."""
+        out = (C.c_uint64 * 2)()
+        _lib.check(_lib.load().catt_result_text_digest(self._owner._h, self._h, out))
+        return int(out[0]), int(out[1])
+
     def close(self):
         if self._h:
             _lib.load().catt_result_free(self._h)

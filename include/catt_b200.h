@@ -219,6 +219,9 @@ int catt_result_info(const catt_result* r, catt_info* out);
 /* Order-sensitive 64-bit digests of Vpart (out[0]) and Jpart (out[1]) - every catt_read field and both strings of every entry:
  * equal digests = identical lists (used to show that a sample gives the same result on 1, 2, 4 and 8 GPUs). */
 int catt_result_digest(const catt_result* r, uint64_t out[2]);
+/* The same idea over the lists as TEXT - seq, qual, V name, J name, cdr3 ("None" when absent), able - i.e. over what the Julia side
+ * sees; independent of ids / offsets, so another implementation of the path can compute the same number (the test oracle does). */
+int catt_result_text_digest(const catt_ctx* ctx, const catt_result* r, uint64_t out[2]);
 /* Vpart (which=0) / Jpart (1) in the reference's list order, ready for catt.jl:579 onwards. */
 int catt_result_reads(const catt_result* r, int which, const catt_read** reads, int64_t* n);
 /* Per-read alignment records (input order, one per read; unmapped reads have mapped=0): parity/diagnostics.

@@ -1310,6 +1310,24 @@ const char* co_result_dump(void* r, int which) {
   return d.c_str();
 }
 
+// Canonical, order-sensitive digest of a list (the twin of catt_result_text_digest in libcatt_b200): per entry FNV-1a over
+// seq 0x1f qual 0x1f vs 0x1f js 0x1f cdr3 0x1f able, mixed with the entry's position, summed.  `only_cdr3` skips the reads whose
+// cdr3 is "None" (the lists as they stand after catt.jl:581-582); positions then count the kept reads.
+uint64_t co_result_digest(void* r, int which, int only_cdr3) {
+  RunResult* R = (RunResult*)r;
+  uint64_t acc = 0, pos = 0;
+  for (const Myread& m : (which ? R->Jpart : R->Vpart)) {
+    if (only_cdr3 && m.cdr3 == "None") continue;
+    uint64_t h = 0xcbf29ce484222325ull ^ (pos * 0x9E3779B97F4A7C15ull);
+    auto mix = [&](const std::string& t) { for (unsigned char b : t) { h ^= b; h *= 0x100000001b3ull; } h ^= 0x1f; h *= 0x100000001b3ull; };
+    mix(m.seq); mix(m.qual); mix(m.vs); mix(m.js); mix(m.cdr3);
+    h ^= (uint64_t)(m.able ? 1 : 0); h *= 0x100000001b3ull;
+    h ^= h >> 29; h *= 0xbf58476d1ce4e5b9ull; h ^= h >> 32;
+    acc += h; pos++;
+  }
+  return acc ^ (pos * 0x94d049bb133111ebull);
+}
+
 // per-read alignment records of the run: which=0 V, 1 J; out = n*16 int32 (layout as co_align)
 int co_result_records(void* r, int which, int32_t* out) {
   RunResult* R = (RunResult*)r;

@@ -185,6 +185,13 @@ class RunResult:
     def Jpart(self):
         return self.part(1)
 
+    def digest(self, only_cdr3=False):
+        """(Vpart, Jpart) canonical digests - the twin of catt_b200's Result.text_digest()."""
+        L = lib()
+        L.co_result_digest.restype = C.c_uint64
+        L.co_result_digest.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        return int(L.co_result_digest(self.h, 0, int(only_cdr3))), int(L.co_result_digest(self.h, 1, int(only_cdr3)))
+
     def records(self, which: int) -> np.ndarray:
         n = self.info["n_reads"]
         out = np.zeros((n, 16), dtype=np.int32)
