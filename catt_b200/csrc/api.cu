@@ -907,47 +907,185 @@ int rank_finish(catt_ctx* c, Comm* comm, int root, int64_t n_total, int64_t lo, 
   return CATT_OK;
 }
 
-// The in-process group: rank r runs on its own host thread and its own context / device; rank 0 on the calling thread.
-int run_group(catt_ctx* c, const HostReads& hr, const std::vector<int64_t>& fs, catt_result** out) {
+// ---- a FASTQ file on a GPU group: every rank reads ITS byte range of the file (cut at record starts), moves the text to its GPU,
+// indexes / validates / packs it there (ingest.cu) and learns how many reads it holds; one exchange of those counts gives every
+// rank the global ordinal of its first read (bwa's tie-break hashes it), then Stage A runs on the resident block and Stage B is the
+// global one.  N PCIe links and N shares of the host cores work in parallel; nothing is parsed on the host.
+// Returns RANK_FALLBACK (on every rank) when the file is not strict 4-line FASTQ: the caller takes the host parser.
+constexpr int RANK_FALLBACK = 1;
+
+// first record start at or after byte x: a line that starts with '@' whose second next line starts with '+'
+int64_t record_boundary(int fd, int64_t fsize, int64_t x) {
+  if (x <= 0) return 0;
+  if (x >= fsize) return fsize;
+  std::vector<char> buf;
+  for (size_t span = 1 << 18; span <= ((size_t)1 << 28); span <<= 2) {
+    const int64_t from = x - 1;                                  // one byte back: is x itself a line start?
+    const size_t want = (size_t)std::min<int64_t>((int64_t)span, fsize - from);
+    buf.resize(want);
+    size_t got = 0;
+    while (got < want) { const ssize_t r = pread(fd, buf.data() + got, want - got, (off_t)(from + (int64_t)got)); if (r <= 0) break; got += (size_t)r; }
+    if (got < want) return -1;
+    const char* b = buf.data();
+    const char* end = b + got;
+    const char* p = b;
+    while (p < end) {
+      const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+      if (!nl || nl + 1 >= end) break;
+      const char* q = nl + 1;                                    // a line start
+      if (*q == '@') {
+        const char* n1 = (const char*)memchr(q, '\n', (size_t)(end - q));
+        const char* n2 = n1 ? (const char*)memchr(n1 + 1, '\n', (size_t)(end - (n1 + 1))) : nullptr;
+        if (n2 && n2 + 1 < end) { if (n2[1] == '+') return from + (q - b); }
+        else if (from + (int64_t)got < fsize) break;             // need more look-ahead
+      }
+      p = q;
+    }
+    if (from + (int64_t)got >= fsize) return fsize;              // no further record start: the tail belongs to the previous block
+  }
+  return -1;
+}
+
+int run_file_rank(catt_ctx* c, Comm* comm, int root, const char* path, catt_result** out) {
+  std::unique_ptr<catt_result> R(new catt_result());
+  Trace tr;
+  const int N = comm->nranks, me = comm->rank;
+  int launches = 0, rc = CATT_OK, status = 0;                    // status: 0 ok, 1 fallback, < 0 error
+  int64_t n_loc = 0; uint64_t words = 0; int max_len = 0;
+  c->shard.valid = false;
+  const int fd = open(path, O_RDONLY);
+  int64_t fsize = 0, b0 = 0, b1 = 0;
+  if (fd < 0) { set_error("cannot read %s", path); status = CATT_E_IO; }
+  if (!status) {
+    fsize = (int64_t)lseek(fd, 0, SEEK_END);
+    unsigned char magic[2] = {0, 0};
+    if (fsize < 2 || pread(fd, magic, 2, 0) != 2 || magic[0] != '@') status = RANK_FALLBACK;         // gzip / BGZF / FASTA / empty: host path
+  }
+  if (!status) {
+    b0 = record_boundary(fd, fsize, fsize / N * me);
+    b1 = me + 1 == N ? fsize : record_boundary(fd, fsize, fsize / N * (me + 1));
+    if (b0 < 0 || b1 < 0) status = RANK_FALLBACK;
+  }
+  const double t0 = now_ms();
+  if (!status && b1 > b0) {
+    const int64_t bytes = b1 - b0;
+    const size_t piece = (size_t)64 << 20;
+    if ((rc = c->rd_text.ensure((size_t)bytes + 32)) || (rc = c->pin[PIN_PACK0].ensure(piece + 16)) || (rc = c->pin[PIN_PACK1].ensure(piece + 16))) status = rc;
+    char* d_text = c->rd_text.as<char>();
+    int64_t text_end = bytes;                                    // after trimming trailing blank space; then one '\n'
+    for (int64_t o = 0, k = 0; !status && o < bytes; o += (int64_t)piece, k++) {
+      const int64_t len = std::min<int64_t>((int64_t)piece, bytes - o);
+      char* h = c->pin[PIN_PACK0 + (k & 1)].as<char>();
+      if (k >= 2 && cudaEventSynchronize(c->ev_h2d[k & 1]) != cudaSuccess) { set_error("FASTQ text upload failed"); status = CATT_E_CUDA; break; }
+      const int64_t sub = 4 << 20, ns = (len + sub - 1) / sub;
+      bool ok = true;
+      #pragma omp parallel for schedule(dynamic, 1) reduction(&& : ok)
+      for (int64_t q = 0; q < ns; q++) {
+        int64_t a = q * sub;
+        const int64_t e = std::min(len, a + sub);
+        while (a < e) { const ssize_t r = pread(fd, h + a, (size_t)(e - a), (off_t)(b0 + o + a)); if (r <= 0) { ok = false; break; } a += r; }
+      }
+      if (!ok) { set_error("short read on %s", path); status = CATT_E_IO; break; }
+      int64_t put = len;
+      if (o + len == bytes) {                                    // last piece of the block: trailing blank space off, exactly one '\n'
+        while (put > 0 && (h[put - 1] == '\n' || h[put - 1] == '\r' || h[put - 1] == ' ' || h[put - 1] == '\t')) put--;
+        if (put == 0 && o > 0) { status = RANK_FALLBACK; break; }   // (a piece of nothing but blank lines: let the host parser decide)
+        h[put++] = '\n';
+        text_end = o + put;
+      }
+      if (cudaMemcpyAsync(d_text + o, h, (size_t)put, cudaMemcpyHostToDevice, c->copy_stream) != cudaSuccess ||
+          cudaEventRecord(c->ev_h2d[k & 1], c->copy_stream) != cudaSuccess) { set_error("FASTQ text upload failed"); status = CATT_E_CUDA; break; }
+      R->info.bytes_h2d += put;
+    }
+    if (!status && cudaStreamSynchronize(c->copy_stream) != cudaSuccess) { set_error("FASTQ text upload failed"); status = CATT_E_CUDA; }
+    tr.lap("run_file_rank: read + H2D");
+    if (!status && text_end > 1) {
+      int fb = 0;
+      rc = ingest_fastq(c, d_text, 0, text_end, 0, 0, &n_loc, &words, &max_len, &fb, &launches, c->stream);
+      if (rc) status = fb ? RANK_FALLBACK : rc;
+    }
+    tr.lap("run_file_rank: index + pack");
+  }
+  if (fd >= 0) close(fd);
+  const double ms_ingest = now_ms() - t0;
+  // first exchange: read counts and status.  Every rank answers it, whatever happened.
+  std::string err = status < 0 ? catt::last_error() : "";
+  long long mine[2] = {n_loc, status};
+  std::vector<long long> all((size_t)2 * N);
+  if ((rc = comm->host_allgather(mine, all.data(), sizeof mine, c->stream))) return rc;
+  int64_t lo = 0, n_total = 0;
+  bool fallback = false;
+  for (int r = 0; r < N; r++) {
+    if (all[2 * r + 1] < 0) { if (r == me) set_error("%s", err.c_str()); else set_error("GPU group: rank %d could not ingest %s (code %lld)", r, path, all[2 * r + 1]); return (int)all[2 * r + 1]; }
+    fallback = fallback || all[2 * r + 1] == RANK_FALLBACK;
+    if (r < me) lo += all[2 * r];
+    n_total += all[2 * r];
+  }
+  if (fallback) return RANK_FALLBACK;
+  c->last_n = n_loc; c->last_words = (int64_t)words; c->last_max_len = max_len;
+  R->info.ms_pack = ms_ingest;
+  DeviceReads dr;
+  dr.words = c->rd_words.as<uint32_t>(); dr.off = c->rd_off.as<uint32_t>(); dr.len = c->rd_len.as<int32_t>(); dr.n = n_loc; dr.max_len = max_len;
+  FileHits fh;
+  fh.start = {0, n_loc};
+  std::vector<int64_t> ord0{lo};
+  const double ta = now_ms();
+  rc = n_loc > 0 ? stage_a_resident(c, dr, 0, &fh, &R->info, &launches, &ord0) : CATT_OK;
+  const double ms_a = now_ms() - ta + ms_ingest;
+  tr.lap("run_file_rank: align");
+  NamesDev nd;
+  nd.s = c->rd_text.as<char>(); nd.beg = reinterpret_cast<const int64_t*>(c->rd_name_beg.p); nd.end = reinterpret_cast<const int64_t*>(c->rd_name_end.p);
+  DeviceQuals dq;
+  dq.quals = c->rd_text.as<char>(); dq.seq_off = reinterpret_cast<const int64_t*>(c->rd_qual_beg.p);
+  return rank_finish(c, comm, root, n_total, lo, n_loc, {0, n_total}, nd, dq, max_len, ms_a, rc, R, launches, out);
+}
+
+int run_reads_dispatch(catt_ctx* c, const HostReads& hr, const std::vector<int64_t>& fs, catt_result** out);
+// Runs `body(r, rank context, communicator)` on every rank of the in-process group: rank r on its own host thread and device, rank 0
+// on the calling thread.  Returns the first real error (a peer's "rank failed" echo is not one), or `same` when every rank returned
+// the same non-error code.
+int group_run(catt_ctx* c, const std::function<int(int, catt_ctx*, Comm*, catt_result**)>& body, catt_result** out) {
   const int N = 1 + (int)c->peers.size();
   std::vector<int> rcs((size_t)N, CATT_OK);
   std::vector<std::string> errs((size_t)N);
   std::vector<catt_result*> res((size_t)N, nullptr);
   const int host_threads = std::max(1, omp_get_max_threads()), per_rank = std::max(1, host_threads / N);
   if (c->lgroup) catt::local_group_reset(c->lgroup);
-  auto body = [&](int r) {
+  auto run = [&](int r) {
     catt_ctx* cr = r ? c->peers[(size_t)r - 1] : c;
     if (cudaSetDevice(cr->device) != cudaSuccess) { rcs[r] = CATT_E_CUDA; errs[r] = "cudaSetDevice failed"; return; }
     omp_set_num_threads(per_rank);                   // a per-thread setting: every rank packs / copies with its share of the cores
-    int64_t lo, hi;
-    block_bounds(hr.n, N, r, &lo, &hi);
-    HostReads sub;
-    sub.n = hi - lo; sub.names = hr.names; sub.name_off = hr.name_off ? hr.name_off + lo : nullptr; sub.seqs = hr.seqs;
-    sub.seq_off = hr.seq_off ? hr.seq_off + lo : nullptr; sub.quals = hr.quals;
-    rcs[r] = run_rank(cr, c->comms[(size_t)r], 0, hr.n, lo, sub, fs, &res[r]);
-    if (rcs[r]) { errs[r] = catt::last_error(); if (c->lgroup) catt::local_group_fail(c->lgroup); }
+    rcs[r] = body(r, cr, c->comms[(size_t)r], &res[r]);
+    if (rcs[r] < 0) { errs[r] = catt::last_error(); if (c->lgroup) catt::local_group_fail(c->lgroup); }
   };
   std::vector<std::thread> th;
-  for (int r = 1; r < N; r++) th.emplace_back(body, r);
-  body(0);
+  for (int r = 1; r < N; r++) th.emplace_back(run, r);
+  run(0);
   for (auto& t : th) t.join();
   omp_set_num_threads(host_threads);
   cudaSetDevice(c->device);
   int bad = -1;
-  for (int r = 0; r < N; r++) if (rcs[r] && (bad < 0 || errs[bad].find("peer rank") != std::string::npos)) bad = r;     // prefer the root cause
+  for (int r = 0; r < N; r++) if (rcs[r] < 0 && (bad < 0 || errs[bad].find("peer rank") != std::string::npos)) bad = r;     // prefer the root cause
   if (bad >= 0) {
     for (auto* p : res) delete p;
     set_error("GPU group rank %d (device %d): %s", bad, bad ? c->peers[(size_t)bad - 1]->device : c->device, errs[bad].c_str());
     return rcs[bad];
   }
   for (int r = 1; r < N; r++) delete res[r];
+  if (rcs[0] != CATT_OK) { delete res[0]; return rcs[0]; }
   *out = res[0];
   return CATT_OK;
 }
 
 int run_reads_dispatch(catt_ctx* c, const HostReads& hr, const std::vector<int64_t>& fs, catt_result** out);
-// File input on a GPU group: the files are read and parsed on the host (all threads), then the reads are split over the ranks.
+// File input on a GPU group.  One plain FASTQ file: every rank ingests its byte range on its own GPU (run_file_rank).  Anything
+// else (several files, .gz / BGZF, BAM / SAM, FASTA, wrapped lines): read and parsed on the host, then split over the ranks.
 int run_files_group(catt_ctx* c, int nfiles, const char* const* paths, bool bam, catt_result** out) {
+  if (nfiles == 1 && !bam && paths[0] && !getenv("CATT_HOST_PARSE")) {
+    const char* path = paths[0];
+    int rc = group_run(c, [&](int, catt_ctx* cr, Comm* comm, catt_result** o) { return run_file_rank(cr, comm, 0, path, o); }, out);
+    if (rc != RANK_FALLBACK) return rc;
+  }
   HostReads hr;
   std::vector<int64_t> fs{0};
   Trace tr;
@@ -962,8 +1100,16 @@ int run_files_group(catt_ctx* c, int nfiles, const char* const* paths, bool bam,
 }
 
 int run_reads_dispatch(catt_ctx* c, const HostReads& hr, const std::vector<int64_t>& fs, catt_result** out) {
-  if (!c->peers.empty()) return run_group(c, hr, fs, out);
-  return run_all(c, hr, fs, out);
+  if (c->peers.empty()) return run_all(c, hr, fs, out);
+  const int N = 1 + (int)c->peers.size();
+  return group_run(c, [&](int r, catt_ctx* cr, Comm* comm, catt_result** o) {
+    int64_t lo, hi;
+    block_bounds(hr.n, N, r, &lo, &hi);
+    HostReads sub;
+    sub.n = hi - lo; sub.names = hr.names; sub.name_off = hr.name_off ? hr.name_off + lo : nullptr; sub.seqs = hr.seqs;
+    sub.seq_off = hr.seq_off ? hr.seq_off + lo : nullptr; sub.quals = hr.quals;
+    return run_rank(cr, comm, 0, hr.n, lo, sub, fs, o);
+  }, out);
 }
 
 std::string dup(const char* s) { return s ? std::string(s) : std::string(); }
@@ -1293,6 +1439,15 @@ int catt_run_reads_shard(catt_ctx* c, int64_t n_total, int64_t lo, int64_t n_loc
   HostReads hr;
   hr.n = n_local; hr.names = names; hr.name_off = n_local ? name_off : zero_off; hr.seqs = seqs; hr.seq_off = n_local ? seq_off : zero_off; hr.quals = quals;
   return run_rank(c, c->comm, 0, n_total, lo, hr, fs, out);
+}
+
+int catt_run_file_shard(catt_ctx* c, const char* path, catt_result** out) {
+  if (!c || !path || !out) { set_error("catt_run_file_shard: null argument"); return CATT_E_ARG; }
+  if (!c->comm) { set_error("catt_run_file_shard: call catt_ctx_join first"); return CATT_E_ARG; }
+  CATT_CUDA(cudaSetDevice(c->device));
+  const int rc = run_file_rank(c, c->comm, 0, path, out);
+  if (rc == RANK_FALLBACK) { set_error("%s is not a plain 4-line FASTQ file: catt_run_file_shard reads nothing else (inflate / convert it first, or use catt_run_reads_shard)", path); return CATT_E_ARG; }
+  return rc;
 }
 
 // Resident form of catt_run_reads_shard (bench.py's `value`): catt_shard_upload moves this rank's block to HBM - packed reads,

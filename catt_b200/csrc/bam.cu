@@ -169,11 +169,16 @@ int BamTextStream::next(char* dst, size_t cap, size_t* wrote) {
   *wrote = 0;
   if (eof_) return 0;
   // inflate the next group of blocks behind the bytes left over from the previous call
+  // ... but never more BAM bytes than the caller has room for as text: a record's FASTQ text is < 4/3 of its BAM bytes (2 x l_seq
+  // + name + 8 against 1.5 x l_seq + name + 36), so 3/4 of `cap` is safe, and it is checked BEFORE any block is consumed
   const size_t group_bound = (size_t)std::max(1, omp_get_max_threads()) * 48 * 65536;
-  if (buf_.size() < pending_ + group_bound) buf_.resize(pending_ + group_bound);
+  const size_t room = cap / 4 * 3;
+  if (room < pending_ + 65536 + 1024) return -2;
+  const size_t want = std::min(group_bound, room - pending_);
+  if (buf_.size() < pending_ + want) buf_.resize(pending_ + want);
   size_t got = 0;
   double tt = omp_get_wtime();
-  const int r = bz_.next(reinterpret_cast<char*>(buf_.data()) + pending_, buf_.size() - pending_, &got);
+  const int r = bz_.next(reinterpret_cast<char*>(buf_.data()) + pending_, want, &got);
   t_inf_ += omp_get_wtime() - tt; tt = omp_get_wtime();
   if (r < 0) return -1;
   const bool last = r == 0;

@@ -24,6 +24,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
+#include <memory>
 #ifdef __SSE2__
 #include <emmintrin.h>
 #endif
@@ -718,9 +719,14 @@ int BgzfStream::next(char* dst, size_t cap, size_t* wrote) {
   *wrote = 0;
   if (next_ >= blocks_.size()) return 0;
   const size_t group = (size_t)std::max(1, omp_get_max_threads()) * 48;         // ~3 MiB of text per thread and call
-  const size_t b0 = next_, b1 = std::min(blocks_.size(), b0 + group);
-  const uint64_t o0 = blocks_[b0].uoff, o1 = b1 < blocks_.size() ? blocks_[b1].uoff : total_;
-  if (o1 - o0 > cap) return -2;
+  const size_t b0 = next_;
+  size_t b1 = std::min(blocks_.size(), b0 + group);
+  const uint64_t o0 = blocks_[b0].uoff;
+  auto end_of = [&](size_t b) { return b < blocks_.size() ? blocks_[b].uoff : total_; };
+  // the group follows the room the caller has (a small pinned window on a host with many threads): as many whole members as fit
+  while (b1 > b0 + 1 && end_of(b1) - o0 > cap) b1 = b0 + (b1 - b0) / 2;
+  const uint64_t o1 = end_of(b1);
+  if (o1 - o0 > cap) return -2;                                                 // not even one 64 KiB member fits
   bool bad = false;
   const bool zlib_only = getenv("CATT_ZLIB_ONLY") != nullptr;
   #pragma omp parallel for schedule(dynamic, 4) reduction(|| : bad)
@@ -731,7 +737,7 @@ int BgzfStream::next(char* dst, size_t cap, size_t* wrote) {
     // the member's deflate data through the byte-mode decoder above (about twice zlib's inflate on the GPU boxes' hosts); the
     // member's CRC-32 and size are the check, and zlib gets the member if anything is off
     static thread_local OutBuf<uint8_t> scratch;
-    static thread_local Tables* tables = new Tables();
+    static thread_local std::unique_ptr<Tables> tables(new Tables());
     bool done = false;
     scratch.n = 0;
     if (!zlib_only && scratch.room(65536 + 1024)) {

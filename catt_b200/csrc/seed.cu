@@ -39,9 +39,10 @@ struct WarpScratch {
   uint32_t* runs_q;     // [RUNS_SMEM] qs | qe << 16
   uint32_t* runs_t;     // [RUNS_SMEM] start in T
   uint16_t* cov;        // [RUNS_SMEM]
+  uint16_t* ord;        // [RUNS_SMEM] run indices by descending query end
 };
 __host__ __device__ inline size_t warp_scratch_bytes(int ml) {
-  return (size_t)ml * (4 * 3 + 2 + 1) + (MAX_READ / 32) * 4 + MAX_CW * 8 + 16 + (size_t)RUNS_SMEM * 10;
+  return (size_t)ml * (4 * 3 + 2 + 1) + (MAX_READ / 32) * 4 + MAX_CW * 8 + 16 + (size_t)RUNS_SMEM * 12;
 }
 __device__ inline WarpScratch carve(unsigned char* base, int ml) {
   WarpScratch ws;
@@ -55,13 +56,14 @@ __device__ inline WarpScratch carve(unsigned char* base, int ml) {
   ws.runs_q = reinterpret_cast<uint32_t*>(base); base += RUNS_SMEM * 4;
   ws.runs_t = reinterpret_cast<uint32_t*>(base); base += RUNS_SMEM * 4;
   ws.cov = reinterpret_cast<uint16_t*>(base); base += RUNS_SMEM * 2;
+  ws.ord = reinterpret_cast<uint16_t*>(base); base += RUNS_SMEM * 2;
   ws.starts = reinterpret_cast<uint16_t*>(base); base += 2 * ml;
   ws.codes = base;
   return ws;
 }
 
 struct Scratch {
-  uint32_t* runs_q; uint32_t* runs_t; uint16_t* cov; int cap;
+  uint32_t* runs_q; uint32_t* runs_t; uint16_t* cov; uint16_t* ord; int cap;
 };
 
 __device__ __forceinline__ uint32_t tbase(const uint32_t* T2, int p) { return (T2[p >> 4] >> ((p & 15) * 2)) & 3u; }
@@ -83,23 +85,29 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
   return v;
 }
 
-// pass 2 for one SMEM: maximal intervals containing `mid` with >= m covering runs
+// pass 2 for one SMEM: maximal intervals containing `mid` with >= m covering runs.  The runs are visited by descending query end
+// (sc.ord), so the covering list comes out in that order and "the m-th largest end among the covering runs that start at or
+// before sp" is a short counting scan per start instead of a top-m selection over the whole list.
 __device__ void reseed(const RefDev& ref, const WarpScratch& ws, const Scratch& sc, int n, int mid, int m, int lane) {
-  if (lane == 0) { ws.ctr[1] = 0; ws.ctr[2] = 0; }
+  if (lane == 0) ws.ctr[2] = 0;
   if (lane < MAX_READ / 32) ws.startbits[lane] = 0;
   __syncwarp();
+  int nc = 0;
   #pragma unroll 1
-  for (int r = lane; r < n; r += 32) {
-    const uint32_t q = sc.runs_q[r];
+  for (int j = 0; j < n; j += 32) {
+    const int k = j + lane < n ? (int)sc.ord[j + lane] : -1;
+    const uint32_t q = k >= 0 ? sc.runs_q[k] : 0u;
     const int qs = q & 0xffff, qe = q >> 16;
-    if (qs <= mid && qe > mid) {
-      const int idx = atomicAdd(&ws.ctr[1], 1);
-      sc.cov[idx] = (uint16_t)r;                      // cov capacity == run capacity
+    if (__shfl_sync(FULL, qe, 0) <= mid) break;           // every later run ends at or before mid as well
+    const bool cv = k >= 0 && qs <= mid && qe > mid;
+    const unsigned bal = __ballot_sync(FULL, cv);
+    if (cv) {
+      sc.cov[nc + __popc(bal & ((1u << lane) - 1))] = (uint16_t)k;      // cov capacity == run capacity
       atomicOr(&ws.startbits[qs >> 5], 1u << (qs & 31));
     }
+    nc += __popc(bal);
   }
   __syncwarp();
-  const int nc = ws.ctr[1];
   if (nc < m) return;
   int ns = 0;
   #pragma unroll 1
@@ -116,25 +124,14 @@ __device__ void reseed(const RefDev& ref, const WarpScratch& ws, const Scratch& 
     const int si = sb + lane;
     const bool valid = si < ns;
     const int sp = valid ? ws.starts[si] : -1;
-    uint32_t top[11];
-    #pragma unroll
-    for (int t = 0; t < 11; t++) top[t] = 0;
+    // e = m-th largest end among the covering runs with qs <= sp (0 when there are fewer than m)
+    uint32_t e = 0;
     int c = 0;
     #pragma unroll 1
     for (int k = 0; k < nc; k++) {
       const uint32_t q = sc.runs_q[sc.cov[k]];
-      const int qs = q & 0xffff;
-      uint32_t v = q >> 16;
-      if (qs <= sp) {
-        c++;
-        #pragma unroll
-        for (int t = 0; t < 11; t++) { const uint32_t a = max(top[t], v), b = min(top[t], v); top[t] = a; v = b; }
-      }
-    }
-    uint32_t e = 0;
-    if (c >= m) {
-      #pragma unroll
-      for (int t = 0; t < 11; t++) if (t == m - 1) e = top[t];
+      if ((int)(q & 0xffff) <= sp && ++c == m) e = q >> 16;
+      if (__all_sync(FULL, c >= m || !valid)) break;
     }
     uint32_t incl = e;
     #pragma unroll
@@ -263,6 +260,30 @@ __device__ bool seed_one_read(const RefDev& ref, const uint32_t* __restrict__ T2
     if (qe == ws.M1[qs] && ws.Pm[qs] < qe) { mark_seed(ref, ws.cand, (int)sc.runs_t[k], (int)(qe - qs)); atomicAdd(&ws.cnt[qs], 1u); }
   }
   __syncwarp();
+  // ---- run indices by descending query end (counting sort over the ends; Pm is free between pass 1 and pass 2's interval list)
+  #pragma unroll 1
+  for (int i = lane; i < len; i += 32) ws.Pm[i] = 0;
+  __syncwarp();
+  #pragma unroll 1
+  for (int k = lane; k < n; k += 32) atomicAdd(&ws.Pm[len - (int)(sc.runs_q[k] >> 16)], 1u);      // bin 0 = runs that end at the read's end
+  __syncwarp();
+  {
+    uint32_t carry = 0;
+    #pragma unroll 1
+    for (int base = 0; base < len; base += 32) {
+      const int i = base + lane;
+      const uint32_t v = i < len ? ws.Pm[i] : 0;
+      uint32_t incl = v;
+      #pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += t; }
+      if (i < len) ws.Pm[i] = carry + incl - v;
+      carry += __shfl_sync(FULL, incl, 31);
+    }
+  }
+  __syncwarp();
+  #pragma unroll 1
+  for (int k = lane; k < n; k += 32) sc.ord[atomicAdd(&ws.Pm[len - (int)(sc.runs_q[k] >> 16)], 1u)] = (uint16_t)k;
+  __syncwarp();
   // ---- pass 2: re-seeding inside long, rare SMEMs
   #pragma unroll 1
   for (int base = 0; base < len; base += 32) {
@@ -276,7 +297,9 @@ __device__ bool seed_one_read(const RefDev& ref, const uint32_t* __restrict__ T2
       reseed(ref, ws, sc, n, (a + b) >> 1, m, lane);
     }
   }
-  // ---- pass 3: tiles
+  // ---- pass 3: tiles.  Tile [x, e): the shortest e >= x + 11 with fewer than 20 runs covering it.  The number of covering runs
+  // is non-increasing in e, so e - 1 is the 20th largest end among the runs that start at or before x (when there are 20 with
+  // end >= x + 11): one counting scan over the runs by descending end, no bisection.
   int x = 0;
   #pragma unroll 1
   while (x < len) {
@@ -287,36 +310,31 @@ __device__ bool seed_one_read(const RefDev& ref, const uint32_t* __restrict__ T2
       const uint32_t bal = __ballot_sync(FULL, isn);
       if (bal) { x = x + 1 + (__ffs(bal) - 1) + 1; continue; }
     }
-    // shortest e >= x+11 with fewer than 20 runs covering [x, e): the count is non-increasing in e, so the end E of the
-    // last prefix that still has >= 20 covering runs is found by bisection instead of one warp-wide count per base
-    auto covering = [&](int e) {
-      uint32_t mine = 0;
-      #pragma unroll 1
-      for (int k = lane; k < n; k += 32) { const uint32_t q = sc.runs_q[k]; mine += ((int)(q & 0xffff) <= x && (int)(q >> 16) >= e); }
-      return warp_sum(mine);
-    };
-    int e = x + 11;
-    uint32_t c = covering(e);
-    if (c >= 20) {
-      int lo = e, hi = len;                                  // covering(lo) >= 20
-      uint32_t chi = lo < hi ? covering(hi) : c;
-      if (chi >= 20) break;                                  // the tile would run to the end of the read: stop
-      #pragma unroll 1
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        const uint32_t cm = covering(mid);
-        if (cm >= 20) lo = mid; else { hi = mid; chi = cm; }
-      }
-      if (ws.codes[lo] > 3) { x = lo + 1; continue; }       // the base that would extend the tile is an N
-      e = hi; c = chi;
+    int c = 0, e20 = -1;
+    #pragma unroll 1
+    for (int j = 0; j < n; j += 32) {
+      const int k = j + lane < n ? (int)sc.ord[j + lane] : -1;
+      const uint32_t q = k >= 0 ? sc.runs_q[k] : 0u;
+      const int qs = q & 0xffff, qe = q >> 16;
+      if (__shfl_sync(FULL, qe, 0) < x + 11) break;
+      const unsigned bal = __ballot_sync(FULL, k >= 0 && qs <= x && qe >= x + 11);
+      const int cc = __popc(bal);
+      if (c + cc >= 20) { e20 = __shfl_sync(FULL, qe, (int)__fns(bal, 0, 20 - c)); break; }
+      c += cc;
     }
-    if (c > 0) {
-      #pragma unroll 1
-      for (int k = lane; k < n; k += 32) {
-        const uint32_t q = sc.runs_q[k];
-        const int qs = q & 0xffff, qe = q >> 16;
-        if (qs <= x && qe >= e) mark_seed(ref, ws.cand, (int)sc.runs_t[k] + (x - qs), e - x);
-      }
+    int e = x + 11;
+    if (e20 >= 0) {
+      if (e20 >= len) break;                                 // the tile would run to the end of the read: stop
+      if (ws.codes[e20] > 3) { x = e20 + 1; continue; }     // the base that would extend the tile is an N
+      e = e20 + 1;
+    }
+    #pragma unroll 1
+    for (int j = 0; j < n; j += 32) {                        // every run that covers the tile (fewer than 20)
+      const int k = j + lane < n ? (int)sc.ord[j + lane] : -1;
+      const uint32_t q = k >= 0 ? sc.runs_q[k] : 0u;
+      const int qs = q & 0xffff, qe = q >> 16;
+      if (__shfl_sync(FULL, qe, 0) < e) break;
+      if (k >= 0 && qs <= x && qe >= e) mark_seed(ref, ws.cand, (int)sc.runs_t[k] + (x - qs), e - x);
     }
     x = e;
   }
@@ -371,10 +389,11 @@ __global__ void __launch_bounds__(SEED_WARPS * 32) seed_kernel(RefDev ref, Reads
   const int64_t gw = (int64_t)blockIdx.x * SEED_WARPS + warp, nw = (int64_t)gridDim.x * SEED_WARPS;
   Scratch sc;
   if (GS) {
-    uint32_t* base = gscratch + (size_t)gw * (RUNS_GLOBAL * 2 + RUNS_GLOBAL / 2);
-    sc.runs_q = base; sc.runs_t = base + RUNS_GLOBAL; sc.cov = reinterpret_cast<uint16_t*>(base + 2 * RUNS_GLOBAL); sc.cap = RUNS_GLOBAL;
+    uint32_t* base = gscratch + (size_t)gw * (RUNS_GLOBAL * 3);
+    sc.runs_q = base; sc.runs_t = base + RUNS_GLOBAL; sc.cov = reinterpret_cast<uint16_t*>(base + 2 * RUNS_GLOBAL);
+    sc.ord = reinterpret_cast<uint16_t*>(base + 2 * RUNS_GLOBAL + RUNS_GLOBAL / 2); sc.cap = RUNS_GLOBAL;
   } else {
-    sc.runs_q = ws.runs_q; sc.runs_t = ws.runs_t; sc.cov = ws.cov; sc.cap = RUNS_SMEM;
+    sc.runs_q = ws.runs_q; sc.runs_t = ws.runs_t; sc.cov = ws.cov; sc.ord = ws.ord; sc.cap = RUNS_SMEM;
   }
   const int64_t total = GS ? (int64_t)counters[4] : reads.n;
   for (int64_t it = gw; it < total; it += nw) {
@@ -411,7 +430,7 @@ int launch_seed(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int 
   CATT_CUDA(cudaGetLastError());
   // overflow pass (usually an empty list): global scratch sized for sm_count*2 CTAs
   const int grid2 = sm_count * 2;
-  const size_t need = (size_t)grid2 * SEED_WARPS * (RUNS_GLOBAL * 2 + RUNS_GLOBAL / 2);
+  const size_t need = (size_t)grid2 * SEED_WARPS * (RUNS_GLOBAL * 3);
   if (ab.seed_scratch_runs < need) {
     if (ab.seed_scratch) cudaFree(ab.seed_scratch);
     CATT_CUDA(cudaMalloc(&ab.seed_scratch, need * sizeof(uint32_t)));

@@ -263,6 +263,12 @@ class Catt:
                                                     fs.ctypes.data, C.byref(h)))
         return Result(self, h)
 
+    def mainflow_file_shard(self, fastq_path: str) -> Result:
+        """Collective: every rank ingests its byte range of the same plain FASTQ file on its own GPU (catt_run_file_shard)."""
+        h = C.c_void_p()
+        _lib.check(_lib.load().catt_run_file_shard(self._h, fastq_path.encode(), C.byref(h)))
+        return Result(self, h)
+
     def shard_upload(self, n_total, lo, n_local, name_buf, name_off, seq_buf, seq_off, qual_buf, file_start=None):
         """This rank's block to HBM (packed reads, QNAMEs, quality strings), for repeated `shard_run` calls."""
         fs = np.ascontiguousarray(file_start if file_start is not None else [0, n_total], dtype=np.int64)

@@ -175,6 +175,12 @@ int catt_run_reads_shard(catt_ctx* ctx, int64_t n_total, int64_t lo, int64_t n_l
                          const char* seqs, const int64_t* seq_off, const char* quals, int32_t nfiles, const int64_t* file_start,
                          catt_result** out);
 
+/* File form: every rank opens the same plain 4-line FASTQ file and ingests ITS byte range (cut at record starts) on its own GPU - N PCIe
+ * links and N shares of the host cores in parallel, nothing parsed on the host; the read counts are exchanged before Stage A because
+ * bwa's tie-break hashes the global read ordinal.  (catt_run_file on an in-process group does the same; other formats go through
+ * the host parser there, and are refused here.) */
+int catt_run_file_shard(catt_ctx* ctx, const char* fastq_path, catt_result** out);
+
 /* Resident form of catt_run_reads_shard, for throughput measurements with the inputs already in HBM (bench.py `value`):
  * catt_shard_upload copies this rank's block to the device once (packed reads, QNAMEs, quality strings); catt_shard_run - collective,
  * repeatable - runs seeding / SW / selection on the resident block and then the global Stage B.  Without catt_ctx_join the block

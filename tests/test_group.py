@@ -121,14 +121,35 @@ def test_group_paired_files_and_tiny_inputs(trb, sample):
         one.close(); grp.close()
 
 
-def test_group_file_input(trb, fx):
+def test_group_file_input(trb, fx, tmp_path):
+    """catt_run_file on a group: every rank ingests its byte range of the FASTQ on the device (record-aligned cuts, global read
+    ordinals exchanged before Stage A); other formats take the host parser.  Same lists either way."""
+    import gzip
     from catt_b200.host import Catt
     one = Catt(chain_cfg=trb, device=0)
-    grp = Catt(chain_cfg=trb, device=0, ngpu=2, devices=[0, 0])
+    fq = os.path.join(fx, "testSample.fq")
+    txt = open(fq, "rb").read()
+    variants = {"plain": txt, "no_final_newline": txt.rstrip(b"\n"), "trailing_blank_lines": txt + b"\n\n \n", "crlf": txt.replace(b"\n", b"\r\n")}
     try:
-        same(one.mainflow(os.path.join(fx, "testSample.fq")), grp.mainflow(os.path.join(fx, "testSample.fq")))
+        want = one.mainflow(fq)
+        for ngpu in (2, 3, 5):
+            grp = Catt(chain_cfg=trb, device=0, ngpu=ngpu, devices=[0] * ngpu)
+            try:
+                for name, data in variants.items():
+                    p = tmp_path / f"{name}.fq"
+                    p.write_bytes(data)
+                    same(want, grp.mainflow(str(p)))
+                gz = tmp_path / "s.fq.gz"
+                with gzip.open(gz, "wb") as fh:
+                    fh.write(txt)
+                same(want, grp.mainflow(str(gz)))                      # host path (inflate + parse), then split
+                tiny = tmp_path / "tiny.fq"
+                tiny.write_bytes(b"\n".join(txt.split(b"\n")[:8]) + b"\n")   # 2 reads on up to 5 ranks: empty byte ranges
+                same(one.mainflow(str(tiny)), grp.mainflow(str(tiny)))
+            finally:
+                grp.close()
     finally:
-        one.close(); grp.close()
+        one.close()
 
 
 def test_group_nccl_when_two_gpus(trb, sample):
