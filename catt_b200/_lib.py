@@ -23,7 +23,7 @@ class Config(C.Structure):
                 ("min_score", C.c_int32), ("kmer", C.c_int32), ("julia_nthreads", C.c_int32), ("allow_v", C.c_int32),
                 ("allow_j", C.c_int32), ("device", C.c_int32), ("n_d", C.c_int32), ("d_names", C.POINTER(C.c_char_p)),
                 ("d_seqs", C.POINTER(C.c_char_p)), ("keep_records", C.c_int32), ("chunk_reads", C.c_int32), ("only_cdr3", C.c_int32), ("ngpu", C.c_int32),
-                ("devices", C.POINTER(C.c_int32))]
+                ("devices", C.POINTER(C.c_int32)), ("clonotypes", C.c_int32), ("reserved_", C.c_int32)]
 
 
 ALN_DTYPE = np.dtype([("ordinal", "<i4"), ("rid", "<i4"), ("strand", "<i2"), ("mapped", "<i2"), ("as", "<i2"), ("qb", "<i2"),
@@ -36,6 +36,11 @@ class Read(C.Structure):
     _fields_ = [("seq", C.c_char_p), ("qual", C.c_char_p), ("seq_len", C.c_int32), ("qual_len", C.c_int32), ("v_id", C.c_int32),
                 ("j_id", C.c_int32), ("cdr3_off", C.c_int32), ("cdr3_len", C.c_int32), ("ordinal", C.c_int32),
                 ("able", C.c_uint8), ("flags", C.c_uint8), ("pad_", C.c_uint8 * 2)]
+
+
+class Clonotype(C.Structure):
+    _fields_ = [("cdr3", C.c_char_p), ("qual", C.c_char_p), ("cdr3_len", C.c_int32), ("v_id", C.c_int32), ("j_id", C.c_int32),
+                ("reserved_", C.c_int32), ("count", C.c_int64)]
 
 
 class Info(C.Structure):
@@ -67,7 +72,7 @@ EXPORTS = ["catt_ctx_create", "catt_ctx_destroy", "catt_last_error", "catt_versi
            "catt_batch_download", "catt_batch_free", "catt_ctx_stream", "catt_assemble", "catt_seed_candidates", "catt_sw_pairs",
            "catt_finder", "catt_alu_peak", "catt_batch_assemble", "catt_synth_reads", "catt_run_files", "catt_run_reads_files", "catt_set_host_threads", "catt_records_device", "catt_assemble_device", "catt_shard_counts", "catt_reads_device",
            "catt_assemble_resident", "catt_link_leaves", "catt_near_any", "catt_run_bam", "catt_bam_to_fastq", "catt_inflate_file",
-           "catt_comm_id", "catt_ctx_join", "catt_run_reads_shard", "catt_shard_upload", "catt_shard_run", "catt_result_digest", "catt_result_text_digest", "catt_run_file_shard"]
+           "catt_comm_id", "catt_ctx_join", "catt_run_reads_shard", "catt_shard_upload", "catt_shard_run", "catt_result_digest", "catt_result_text_digest", "catt_run_file_shard", "catt_result_clonotypes"]
 
 _lib = None
 
@@ -132,6 +137,7 @@ def load():
     L.catt_run_file_shard.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     L.catt_result_digest.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.catt_result_text_digest.argtypes = [vp, vp, C.POINTER(C.c_uint64)]
+    L.catt_result_clonotypes.argtypes = [vp, C.POINTER(C.POINTER(Clonotype)), i64p]
     L.catt_comm_id.argtypes = [vp]
     L.catt_ctx_join.argtypes = [vp, C.c_int32, C.c_int32, vp]
     L.catt_run_reads_shard.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, vp, vp, vp, vp, vp, C.c_int32, vp, C.POINTER(vp)]

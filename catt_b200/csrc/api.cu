@@ -1187,6 +1187,7 @@ int catt_ctx_create(catt_ctx** out, const catt_config* cfg) {
   }
   c->keep_records = cfg->keep_records != 0;
   c->only_cdr3 = cfg->only_cdr3 != 0;
+  c->want_clonotypes = cfg->clonotypes != 0;
   if (cfg->chunk_reads > 0) c->chunk_reads = cfg->chunk_reads;
   if (const char* e = getenv("CATT_CHUNK_READS")) { const long long v = atoll(e); if (v > 0) c->chunk_reads = v; }
   CATT_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -1240,6 +1241,7 @@ void catt_ctx_destroy(catt_ctx* c) {
   cudaSetDevice(c->device);
   delete c->comm;
   for (auto& b : c->sh) b.release();
+  for (auto& b : c->cl) b.release();
   c->V.release(); c->J.release();
   free_align_buffers(c->ab[0]); free_align_buffers(c->ab[1]);
   for (auto& b : c->sb) b.release();
@@ -1533,7 +1535,7 @@ int catt_result_digest(const catt_result* r, uint64_t out[2]) {
 
 // Canonical digest of a list as TEXT (what Julia would see): per entry FNV-1a over seq 0x1f qual 0x1f V name 0x1f J name 0x1f cdr3
 // 0x1f able, mixed with the entry's position, summed.  Independent of ids and offsets, so any implementation of the path can
-// compute it (the test oracle does) and two runs can be compared without moving the lists.
+// compute it (the CPU checker under tests does) and two runs can be compared without moving the lists.
 int catt_result_text_digest(const catt_ctx* c, const catt_result* r, uint64_t out[2]) {
   if (!c || !r || !out) return CATT_E_ARG;
   for (int which = 0; which < 2; which++) {
@@ -1569,6 +1571,11 @@ int catt_result_reads(const catt_result* r, int which, const catt_read** reads, 
 int catt_align_records(const catt_result* r, int which, const catt_aln** recs, int64_t* n) {
   if (!r || !recs || !n || which < 0 || which > 1) return CATT_E_ARG;
   *recs = r->rec[which].data(); *n = (int64_t)r->rec[which].size();
+  return CATT_OK;
+}
+int catt_result_clonotypes(const catt_result* r, const catt_clonotype** rows, int64_t* n) {
+  if (!r || !rows || !n) return CATT_E_ARG;
+  *rows = r->clono.data(); *n = r->n_clono;
   return CATT_OK;
 }
 void catt_result_free(catt_result* r) { Trace tr; delete r; tr.lap("result_free"); }

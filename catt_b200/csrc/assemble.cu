@@ -858,6 +858,7 @@ int stage_b(catt_ctx* c, int64_t n, const NamesDev& names, const ReadsDev& reads
     CATT_CUDA(cudaStreamSynchronize(st));
     info.bytes_d2h += (int64_t)(seq_bytes + qual_bytes - 2) + E * (int64_t)sizeof(catt_read) + (2 + nfiles) * C_COUNT * 8;
     { float a = 0, b2 = 0; cudaEventElapsedTime(&a, c->ev[5], c->ev[6]); cudaEventElapsedTime(&b2, c->ev[6], c->ev[7]); info.ms_strings += a; info.ms_d2h += b2; }
+    if (c->want_clonotypes && (rc = build_clonotypes(c, E, d_part, d_seq, d_qual, R->seq_arena, R->qual_arena, R, launches))) return rc;
   }
   tr.lap("B: strings + D2H");
   return CATT_OK;
@@ -1436,6 +1437,7 @@ int stage_b_sharded(catt_ctx* c, const ShardIn& in, const NamesDev& names, const
   }
   CATT_CUDA(cudaEventRecord(c->ev[0], st));
   CATT_CUDA(cudaStreamSynchronize(st));
+  if (root && E > 0 && c->want_clonotypes && (rc = build_clonotypes(c, E, d_part, d_seq, d_qual, R->seq_arena, R->qual_arena, R, launches))) return rc;
   { float x = 0, y = 0; cudaEventElapsedTime(&x, c->ev[5], c->ev[6]); cudaEventElapsedTime(&y, c->ev[7], c->ev[0]); info.ms_strings += x; info.ms_d2h += y; }
   comm_lap(CATT_COLL_RESULT, c->ev[6], c->ev[7]);
   tr.lap("B/N: strings + reduce + D2H");

@@ -123,6 +123,8 @@ struct catt_ctx {
   DevBuf recs_all[2];                     // one catt_aln per read and reference set, for the whole sample
   DevBuf sb[SB_COUNT];
   DevBuf sh[SH_SLOTS];
+  DevBuf cl[16];                          // clonotype table scratch (clonotype.cu)
+  int want_clonotypes = 0;
   // ---- one sample over several GPUs.  Either this context is rank 0 of an in-process group (catt_config.ngpu > 1: `peers` are the
   //      contexts of ranks 1.., `comms[r]` the communicator of rank r) or it is one rank of a multi-process group (catt_ctx_join).
   std::vector<catt_ctx*> peers;
@@ -166,6 +168,7 @@ struct catt_result {
   catt_read* part[2] = {nullptr, nullptr};
   int64_t npart[2] = {0, 0};
   std::vector<catt_aln> rec[2];
+  std::vector<catt_clonotype> clono; std::vector<char> clono_seq, clono_qual; int64_t n_clono = 0;     // clonotype.cu
   char* seq_arena = nullptr; char* qual_arena = nullptr;     // every Myread string, NUL-terminated, back to back
   size_t cap_part[2] = {0, 0}, cap_seq = 0, cap_qual = 0;
   ~catt_result() {
@@ -196,6 +199,8 @@ struct ShardIn {
   int max_len = 0;                        // longest read of the whole sample
   int root = 0;
 };
+int build_clonotypes(catt_ctx* c, int64_t E, const catt_read* d_part, const char* d_seq, const char* d_qual, const char* host_seq,
+                     const char* host_qual, catt_result* R, int* launches);
 int stage_b_sharded(catt_ctx* c, const ShardIn& in, const NamesDev& names, const DeviceQuals& dq, catt_result* R, int* launches);
 // FASTQ text of one input file, resident at d_text[t0, t1) -> spans + packed reads appended at read index `base` (ingest.cu)
 int ingest_fastq(catt_ctx* c, const char* d_text, int64_t t0, int64_t t1, int64_t base, uint64_t word_base, int64_t* n_out,

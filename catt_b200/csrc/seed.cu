@@ -178,32 +178,57 @@ __device__ bool seed_one_read(const RefDev& ref, const uint32_t* __restrict__ T2
   if (lane == 0) ws.ctr[0] = 0;
   __syncwarp();
   // ---- maximal runs >= 10 (each found once, from its left-maximal 10-mer window)
-  // step 1: every lane scans its window positions and queues the left-maximal (s, p) pairs
+  // step 1: 32 windows at a time.  Every lane looks its window up (bitmap, CSR range, the group to skip); the occurrences of all
+  // 32 windows are then expanded by ALL lanes (entry t of the concatenated lists belongs to the lane found by a 5-step search over
+  // the warp's prefix sums), so a window with dozens of occurrences - a 10-mer shared by many V alleles - does not serialise
+  // on one lane while the others idle, and the position loads of a step are all in flight together.
+  int nq_total = 0;
   #pragma unroll 1
-  for (int s = lane; s + SEED_K <= len; s += 32) {
-    const uint64_t bw = ((uint64_t)w[(s >> 4) + 1] << 32) | w[s >> 4];
-    const uint32_t key = (uint32_t)(bw >> ((s & 15) * 2)) & 0xFFFFFu;
-    const uint64_t mw = ((uint64_t)nm[(s >> 5) + 1] << 32) | nm[s >> 5];
-    if ((uint32_t)(mw >> (s & 31)) & 0x3FFu) continue;                 // window holds an N
-    if (!((__ldg(&ref.bitmap[key >> 5]) >> (key & 31)) & 1u)) continue;
-    const uint32_t h0 = __ldg(&ref.kstart[key]), h1 = __ldg(&ref.kstart[key + 1]);
-    // occurrences whose preceding text base equals the preceding read base continue a run found earlier: that whole
-    // group of the (grouped) occurrence list is skipped
-    const uint32_t prev = s > 0 ? ws.codes[s - 1] : 4u;
-    uint32_t ex0 = h1, ex1 = h1;
-    if (prev < 4) {
-      const unsigned long long sub = __ldg(&ref.ksub[key]);
-      ex0 = h0 + (prev ? (uint32_t)(sub >> (16 * (prev - 1))) & 0xFFFFu : 0u);
-      ex1 = h0 + ((uint32_t)(sub >> (16 * prev)) & 0xFFFFu);
+  for (int s0 = 0; s0 + SEED_K <= len; s0 += 32) {
+    const int s = s0 + lane;
+    uint32_t h0 = 0, ex0 = 0, ex1 = 0, cnt = 0;
+    if (s + SEED_K <= len) {
+      const uint64_t bw = ((uint64_t)w[(s >> 4) + 1] << 32) | w[s >> 4];
+      const uint32_t key = (uint32_t)(bw >> ((s & 15) * 2)) & 0xFFFFFu;
+      const uint64_t mw = ((uint64_t)nm[(s >> 5) + 1] << 32) | nm[s >> 5];
+      if (!((uint32_t)(mw >> (s & 31)) & 0x3FFu) &&                      // no N in the window
+          ((__ldg(&ref.bitmap[key >> 5]) >> (key & 31)) & 1u)) {
+        h0 = __ldg(&ref.kstart[key]);
+        const uint32_t h1 = __ldg(&ref.kstart[key + 1]);
+        // occurrences whose preceding text base equals the preceding read base continue a run found earlier: that whole
+        // group of the (grouped) occurrence list is skipped
+        const uint32_t prev = s > 0 ? ws.codes[s - 1] : 4u;
+        ex0 = h1; ex1 = h1;
+        if (prev < 4) {
+          const unsigned long long sub = __ldg(&ref.ksub[key]);
+          ex0 = h0 + (prev ? (uint32_t)(sub >> (16 * (prev - 1))) & 0xFFFFu : 0u);
+          ex1 = h0 + ((uint32_t)(sub >> (16 * prev)) & 0xFFFFu);
+        }
+        cnt = (h1 - h0) - (ex1 - ex0);
+      }
     }
+    uint32_t incl = cnt;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += t; }
+    const uint32_t excl = incl - cnt, total = __shfl_sync(FULL, incl, 31);
     #pragma unroll 1
-    for (uint32_t h = h0; h < h1; h++) {
-      if (h == ex0) { h = ex1; if (h >= h1) break; }
-      const int p = (int)__ldg(&ref.kpos[h]);
-      const int idx = atomicAdd(&ws.ctr[0], 1);
-      if (idx < sc.cap) { sc.runs_q[idx] = (uint32_t)s; sc.runs_t[idx] = (uint32_t)p; }
+    for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+      const uint32_t t = t0 + lane;
+      int owner = 0;                                         // the last lane whose exclusive prefix is <= t
+      #pragma unroll
+      for (int d = 16; d; d >>= 1) { const uint32_t v = __shfl_sync(FULL, excl, owner + d); if (v <= t) owner += d; }
+      const uint32_t oh0 = __shfl_sync(FULL, h0, owner), oex0 = __shfl_sync(FULL, ex0, owner), oex1 = __shfl_sync(FULL, ex1, owner);
+      const uint32_t oexcl = __shfl_sync(FULL, excl, owner);
+      if (t < total) {
+        uint32_t h = oh0 + (t - oexcl);
+        if (h >= oex0) h += oex1 - oex0;
+        const int idx = nq_total + (int)t;
+        if (idx < sc.cap) { sc.runs_q[idx] = (uint32_t)(s0 + owner); sc.runs_t[idx] = __ldg(&ref.kpos[h]); }
+      }
     }
+    nq_total += (int)total;
   }
+  if (lane == 0) ws.ctr[0] = nq_total;
   __syncwarp();
   // step 2: the queued runs are extended by all lanes, 16 bases per step on the packed words
   {
@@ -300,6 +325,32 @@ __device__ bool seed_one_read(const RefDev& ref, const uint32_t* __restrict__ T2
   // ---- pass 3: tiles.  Tile [x, e): the shortest e >= x + 11 with fewer than 20 runs covering it.  The number of covering runs
   // is non-increasing in e, so e - 1 is the 20th largest end among the runs that start at or before x (when there are 20 with
   // end >= x + 11): one counting scan over the runs by descending end, no bisection.
+  // c11[x] = runs covering [x, x + 11), for every x at once (difference array + prefix sum, in Pm): most tiles of a read lie in
+  // its non-V/J part and are covered by nothing - they advance without looking at the run list at all.
+  #pragma unroll 1
+  for (int i = lane; i < len; i += 32) ws.Pm[i] = 0;
+  __syncwarp();
+  #pragma unroll 1
+  for (int k = lane; k < n; k += 32) {
+    const uint32_t q = sc.runs_q[k];
+    const int qs = q & 0xffff, qe = q >> 16;
+    if (qe - qs >= 11) { atomicAdd(&ws.Pm[qs], 1u); if (qe - 10 < len) atomicSub(&ws.Pm[qe - 10], 1u); }
+  }
+  __syncwarp();
+  {
+    uint32_t carry = 0;
+    #pragma unroll 1
+    for (int base = 0; base < len; base += 32) {
+      const int i = base + lane;
+      uint32_t incl = i < len ? ws.Pm[i] : 0;
+      #pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += t; }
+      incl += carry;
+      if (i < len) ws.Pm[i] = incl;
+      carry = __shfl_sync(FULL, incl, 31);
+    }
+  }
+  __syncwarp();
   int x = 0;
   #pragma unroll 1
   while (x < len) {
@@ -310,20 +361,21 @@ __device__ bool seed_one_read(const RefDev& ref, const uint32_t* __restrict__ T2
       const uint32_t bal = __ballot_sync(FULL, isn);
       if (bal) { x = x + 1 + (__ffs(bal) - 1) + 1; continue; }
     }
-    int c = 0, e20 = -1;
-    #pragma unroll 1
-    for (int j = 0; j < n; j += 32) {
-      const int k = j + lane < n ? (int)sc.ord[j + lane] : -1;
-      const uint32_t q = k >= 0 ? sc.runs_q[k] : 0u;
-      const int qs = q & 0xffff, qe = q >> 16;
-      if (__shfl_sync(FULL, qe, 0) < x + 11) break;
-      const unsigned bal = __ballot_sync(FULL, k >= 0 && qs <= x && qe >= x + 11);
-      const int cc = __popc(bal);
-      if (c + cc >= 20) { e20 = __shfl_sync(FULL, qe, (int)__fns(bal, 0, 20 - c)); break; }
-      c += cc;
-    }
+    const int c11 = (int)ws.Pm[x];
+    if (c11 == 0) { x += 11; continue; }                     // an empty tile
     int e = x + 11;
-    if (e20 >= 0) {
+    if (c11 >= 20) {
+      int c = 0, e20 = -1;
+      #pragma unroll 1
+      for (int j = 0; j < n; j += 32) {
+        const int k = j + lane < n ? (int)sc.ord[j + lane] : -1;
+        const uint32_t q = k >= 0 ? sc.runs_q[k] : 0u;
+        const int qs = q & 0xffff, qe = q >> 16;
+        const unsigned bal = __ballot_sync(FULL, k >= 0 && qs <= x && qe >= x + 11);
+        const int cc = __popc(bal);
+        if (c + cc >= 20) { e20 = __shfl_sync(FULL, qe, (int)__fns(bal, 0, 20 - c)); break; }
+        c += cc;
+      }
       if (e20 >= len) break;                                 // the tile would run to the end of the read: stop
       if (ws.codes[e20] > 3) { x = e20 + 1; continue; }     // the base that would extend the tile is an N
       e = e20 + 1;

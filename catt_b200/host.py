@@ -79,6 +79,15 @@ class Result:
         buf = (C.c_char * (n.value * _lib.ALN_DTYPE.itemsize)).from_address(p.value)
         return np.frombuffer(buf, dtype=_lib.ALN_DTYPE).copy()
 
+    def clonotypes(self):
+        """The clonotype table (Catt(clonotypes=True)): [(cdr3, merged qual, V name, J name, count)], ordered by (len, cdr3, V id, J id)."""
+        L = _lib.load()
+        p, n = C.POINTER(_lib.Clonotype)(), C.c_int64()
+        _lib.check(L.catt_result_clonotypes(self._h, C.byref(p), C.byref(n)))
+        vn, jn = self._owner.v_names, self._owner.j_names
+        return [(p[i].cdr3.decode(), p[i].qual.decode(), vn[p[i].v_id] if p[i].v_id >= 0 else "None", jn[p[i].j_id] if p[i].j_id >= 0 else "None",
+                 p[i].count) for i in range(n.value)]
+
     def digest(self):
         """(Vpart digest, Jpart digest): order-sensitive 64-bit digests of every field and string of the two lists."""
         out = (C.c_uint64 * 2)()
@@ -171,7 +180,8 @@ class Catt:
     share every sample (catt_config.ngpu / devices; same calls, same results)."""
 
     def __init__(self, species="hs", chain="TRB", region="CDR3", resource_dir=None, bowsc=12, kmer=10000, thread=1,
-                 allow_v=3, allow_j=9, device=0, chain_cfg=None, keep_records=False, chunk_reads=0, only_cdr3=False, ngpu=1, devices=None):
+                 allow_v=3, allow_j=9, device=0, chain_cfg=None, keep_records=False, chunk_reads=0, only_cdr3=False, ngpu=1, devices=None,
+                 clonotypes=False):
         L = _lib.load()
         cc = chain_cfg or chain_config(species, chain, region, resource_dir)
         self.chain_cfg = cc
@@ -181,7 +191,7 @@ class Catt:
         cfg = _lib.Config(cc["vregion"].encode(), cc["jregion"].encode(), cc["cmotif"].encode(), cc["fmotif"].encode(),
                           cc["innerC"].encode(), cc["innerF"].encode(), cc["coffset"], cc["foffset"], bowsc, kmer, thread,
                           allow_v, allow_j, device, len(d), self._keep[0], self._keep[1], int(keep_records), int(chunk_reads), int(only_cdr3),
-                          int(ngpu), (C.c_int32 * len(devices))(*devices) if devices else None)
+                          int(ngpu), (C.c_int32 * len(devices))(*devices) if devices else None, int(clonotypes), 0)
         if devices and len(devices) != ngpu:
             raise ValueError("one device ordinal per rank")
         h = C.c_void_p()

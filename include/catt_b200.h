@@ -68,6 +68,10 @@ typedef struct catt_config {
   const int32_t* devices;   /* ngpu CUDA device ordinals; NULL = 0 .. ngpu-1.  Repeated ordinals are allowed (several ranks on one
                                GPU, exchanging through peer copies instead of NCCL): that is how the multi-rank path is tested on
                                a single-GPU box. */
+  int32_t clonotypes;       /* 1: every result also carries its clonotype table (catt_result_clonotypes): distinct (CDR3, V, J) with
+                               read count and merged quality string, built on the device from the lists - what nbsorb's grouping
+                               (Jtool.jl:475-490) and the output counter (catt.jl:644) compute from the reads */
+  int32_t reserved_;
 } catt_config;
 
 /* One SAM-visible alignment record = the line `bwa mem | samtools ... | awk` would leave for one read against one
@@ -104,6 +108,21 @@ typedef struct catt_read {
   uint8_t flags;        /* 1 V part read, 2 J part read, 4 both-mapped, 8 qual slice clipped (reference would throw) */
   uint8_t pad_[2];
 } catt_read;
+
+/* One row of the clonotype table: all returned reads with the same CDR3 nucleotides, V call and J call.  Rows are ordered by
+ * (cdr3_len, cdr3, v_id, j_id) - within a length that is the order of nbsorb's `sort!(val, by = x -> x.cdr3)` (Jtool.jl:481) -
+ * so the rows of one nbsorb call (one CDR3 length, catt.jl:624-633) are contiguous and the rows of one cdr3 adjacent:
+ *   nbsorb's (SeqIns(cdr3, reduce(MQ, quals)), count)  =  per cdr3: per-position max of `qual`, sum of `count` over its rows;
+ *   catt.jl:644's counter((vs, translate(cdr3), js, cdr3)) = the rows themselves. */
+typedef struct catt_clonotype {
+  const char* cdr3;       /* NUL-terminated nucleotides */
+  const char* qual;       /* NUL-terminated; per-position maximum of the members' quality characters = reduce(MQ, ...) (Jtool.jl:466-468,487) */
+  int32_t cdr3_len;
+  int32_t v_id;           /* index into the V reference names, -1 = "None" */
+  int32_t j_id;
+  int32_t reserved_;
+  int64_t count;          /* reads */
+} catt_clonotype;
 
 /* The numbers the reference logs (catt.jl:331,503-524,580) plus work counters. */
 typedef struct catt_info {
@@ -233,6 +252,8 @@ int catt_result_reads(const catt_result* r, int which, const catt_read** reads, 
 /* Per-read alignment records (input order, one per read; unmapped reads have mapped=0): parity/diagnostics.
  * Only present when the context was created with keep_records = 1 (otherwise *n = 0). */
 int catt_align_records(const catt_result* r, int which, const catt_aln** recs, int64_t* n);
+/* The clonotype table of the result (catt_config.clonotypes = 1; otherwise *n = 0). */
+int catt_result_clonotypes(const catt_result* r, const catt_clonotype** rows, int64_t* n);
 void catt_result_free(catt_result* r);
 
 /* Replaces the selBestMatchD loop (catt.jl:676-683, Jtool.jl:40-52): for each CDR3 string the index of the best D

@@ -71,22 +71,27 @@ def link_rlg(leaf, roots, uplimit):                        # Jtool.jl:396-421
     return cnt, holder
 
 
-def nbsorb(lgt, val, err_rate, sc_mode=False, link_fn=None, near_fn=None):   # Jtool.jl:475-590; val = [(cdr3, qual), ...]
+def nbsorb(lgt, val, err_rate, sc_mode=False, link_fn=None, near_fn=None, groups=None):   # Jtool.jl:475-590; val = [(cdr3, qual), ...]
     # link_fn(lgt, root_seqs, root_up, leaf_seqs, leaf_counts) -> (statu[], holder[]) and near_fn(lgt, query_seqs, target_seqs) -> flag[]
-    # stand in for the two scan loops (Jtool.jl:524-531, 553-558) when a test wants another implementation of them checked
-    if not val:
+    # stand in for the two scan loops (Jtool.jl:524-531, 553-558) when a test wants another implementation of them checked.
+    # groups = [((cdr3, merged qual), count), ...] in cdr3 order replaces the sort / run-length / MQ step (Jtool.jl:481-489) when
+    # a test wants the library's clonotype table checked as the source of those groups.
+    if not val and not groups:
         return set(), {}
-    val = sorted(val, key=lambda x: x[0])
-    ss = []
-    i = 0
-    while i < len(val):
-        j = i
-        q = val[i][1]
-        while j + 1 < len(val) and val[j + 1][0] == val[i][0]:
-            j += 1
-            q = MQ(q, val[j][1])
-        ss.append(((val[i][0], q), j - i + 1))
-        i = j + 1
+    if groups is not None:
+        ss = list(groups)
+    else:
+        val = sorted(val, key=lambda x: x[0])
+        ss = []
+        i = 0
+        while i < len(val):
+            j = i
+            q = val[i][1]
+            while j + 1 < len(val) and val[j + 1][0] == val[i][0]:
+                j += 1
+                q = MQ(q, val[j][1])
+            ss.append(((val[i][0], q), j - i + 1))
+            i = j + 1
     ss.sort(key=lambda x: -x[1])
     p, L = err_rate, lgt - 6
     nt = math.floor(max_value(p, L, ss[0][1]))
@@ -199,6 +204,37 @@ def clonotype_table(Vpart, Jpart, the_err, dlist=None, best_d=None, sc_mode=Fals
     for (vs, aa, js, nn), n in rows.items():
         d = best_d(nn, dlist) if dlist else ""
         out[(aa, nn, vs, js, d)] += n
+    return out
+
+
+def clonotype_table_from_rows(rows, the_err, dlist=None, best_d=None, sc_mode=False, link_fn=None, near_fn=None):
+    """The same output rows from a clonotype table [(cdr3, merged qual, vs, js, count), ...] ordered by (len, cdr3, ...) - the
+    library's catt_result_clonotypes - instead of from the reads: nbsorb's groups are the per-cdr3 sums / MQ maxima of the rows
+    (Jtool.jl:481-489), the output counter (catt.jl:644) the rows themselves."""
+    conf, seq2seq = set(), {}
+    by_len = {}
+    for r in rows:
+        by_len.setdefault(len(r[0]), []).append(r)
+    for lgt in range(21, 106):
+        grp = by_len.get(lgt)
+        if not grp:
+            continue
+        groups = []
+        for cdr3, qual, _, _, count in grp:                  # rows of one cdr3 are adjacent
+            if groups and groups[-1][0][0] == cdr3:
+                (c, q), n = groups[-1]
+                groups[-1] = ((c, MQ(q, qual)), n + count)
+            else:
+                groups.append(((cdr3, qual), count))
+        cf, c2c = nbsorb(lgt, None, the_err, sc_mode, link_fn, near_fn, groups=groups)
+        conf |= cf
+        seq2seq.update(c2c)
+    out = Counter()
+    for cdr3, _, vs, js, count in rows:
+        if 21 <= len(cdr3) <= 105 and (cdr3 in conf or cdr3 in seq2seq):
+            aa = translate(seq2seq.get(cdr3, cdr3))
+            d = best_d(cdr3, dlist) if dlist else ""
+            out[(aa, cdr3, vs, js, d)] += count
     return out
 
 

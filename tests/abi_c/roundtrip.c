@@ -29,7 +29,9 @@ static int layout(void) {
   P(catt_config, v_fasta); P(catt_config, j_fasta); P(catt_config, cmotif); P(catt_config, fmotif); P(catt_config, inner_c); P(catt_config, inner_f);
   P(catt_config, coffset); P(catt_config, foffset); P(catt_config, min_score); P(catt_config, kmer); P(catt_config, julia_nthreads);
   P(catt_config, allow_v); P(catt_config, allow_j); P(catt_config, device); P(catt_config, n_d); P(catt_config, d_names); P(catt_config, d_seqs);
-  P(catt_config, keep_records); P(catt_config, chunk_reads); P(catt_config, only_cdr3); P(catt_config, ngpu); P(catt_config, devices);
+  P(catt_config, keep_records); P(catt_config, chunk_reads); P(catt_config, only_cdr3); P(catt_config, ngpu); P(catt_config, devices); P(catt_config, clonotypes);
+  printf("sizeof.catt_clonotype %zu\n", sizeof(catt_clonotype));
+  P(catt_clonotype, cdr3); P(catt_clonotype, qual); P(catt_clonotype, cdr3_len); P(catt_clonotype, v_id); P(catt_clonotype, j_id); P(catt_clonotype, count);
   printf("sizeof.catt_aln %zu\n", sizeof(catt_aln));
   P(catt_aln, ordinal); P(catt_aln, rid); P(catt_aln, strand); P(catt_aln, mapped); P(catt_aln, as); P(catt_aln, qb); P(catt_aln, m_end);
   P(catt_aln, rb); P(catt_aln, qe); P(catt_aln, re); P(catt_aln, nm); P(catt_aln, mi); P(catt_aln, ncand); P(catt_aln, ntied);
@@ -65,7 +67,7 @@ static int run(const char* res, const char* fastq, int ngpu) {
   cfg.inner_c = "(CAS|CSA|CAW|CAT|CSV|CAI|CAR)"; cfg.inner_f = "place_holder";
   cfg.coffset = 2; cfg.foffset = 1; cfg.min_score = 12; cfg.kmer = CATT_KMER_AUTO; cfg.julia_nthreads = 2;
   cfg.allow_v = 3; cfg.allow_j = 9; cfg.device = 0; cfg.n_d = 3; cfg.d_names = d_names; cfg.d_seqs = d_seqs;
-  cfg.only_cdr3 = 1; cfg.ngpu = ngpu; cfg.devices = ngpu > 1 ? devices : NULL;
+  cfg.only_cdr3 = 1; cfg.clonotypes = 1; cfg.ngpu = ngpu; cfg.devices = ngpu > 1 ? devices : NULL;
   catt_ctx* ctx = NULL;
   catt_result* r = NULL;
   if (catt_ctx_create(&ctx, &cfg) != CATT_OK) { fprintf(stderr, "catt_ctx_create: %s\n", catt_last_error()); return 1; }
@@ -100,6 +102,16 @@ static int run(const char* res, const char* fastq, int ngpu) {
       if (catt_best_d(ctx, one, 1, &d) != CATT_OK) return 1;
     }
   }
+  /* the clonotype table: what nbsorb's grouping and the output counter need, without touching a read */
+  const catt_clonotype* rows = NULL;
+  int64_t n_rows = 0, row_reads = 0;
+  if (catt_result_clonotypes(r, &rows, &n_rows) != CATT_OK) return 1;
+  for (int64_t i = 0; i < n_rows; i++) {
+    if (strlen(rows[i].cdr3) != (size_t)rows[i].cdr3_len || strlen(rows[i].qual) != (size_t)rows[i].cdr3_len) { fprintf(stderr, "clonotype row %lld malformed\n", (long long)i); return 1; }
+    row_reads += rows[i].count;
+  }
+  if (row_reads != with_cdr3) { fprintf(stderr, "clonotype counts %lld != reads with a CDR3 %lld\n", (long long)row_reads, (long long)with_cdr3); return 1; }
+  printf("clonotypes %lld ", (long long)n_rows);
   printf("reads %lld kmer %d the_err %.6e vpart %lld jpart %lld returned_v %lld returned_j %lld with_cdr3 %lld rescued %lld n_ranks %d best_d %d checksum %016llx\n",
          (long long)info.n_reads, info.kmer, info.the_err, (long long)info.vpart, (long long)info.jpart, (long long)n_reads[0], (long long)n_reads[1],
          (long long)with_cdr3, (long long)info.rescued, info.n_ranks, d, h);

@@ -39,7 +39,7 @@ def test_struct_layouts_match_header():
     from catt_b200 import _lib
     out = subprocess.check_output([os.path.join(ROOT, "tests", "abi_c", "roundtrip"), "layout"], text=True)
     c_view = {k: int(v) for k, v in (ln.split() for ln in out.strip().split("\n"))}
-    py = {"catt_config": _lib.Config, "catt_read": _lib.Read, "catt_info": _lib.Info}
+    py = {"catt_config": _lib.Config, "catt_read": _lib.Read, "catt_info": _lib.Info, "catt_clonotype": _lib.Clonotype}
     seen = 0
     for name, val in c_view.items():
         kind, field = name.split(".")

@@ -513,3 +513,31 @@ def test_file_pipeline_sliding_pinned_window(trb, tmp_path):
         for k in ("CATT_PIN_WINDOW", "CATT_ZLIB_ONLY", "CATT_TRACE_WINDOW"):
             os.environ.pop(k, None)
     c.close()
+
+
+def test_one_million_reads_digest_parity(trb, O, orefs):
+    """1 M synthetic 150-bp reads (several Stage A chunks, ~650 k Vpart reads, the k-mer table and extension at size): both full
+    lists, the lists after filter!(cdr3 != "None"), every counter and a 4-rank GPU group against the oracle, compared through the
+    canonical text digest (seq, qual, V name, J name, cdr3, able of every read, order sensitive).  profiles/parity_at_scale.py
+    repeats this at 10 M reads and on five other chain / length configurations."""
+    from catt_b200.host import Catt
+    V, J = orefs
+    n, length = 1_000_000, 150
+    full = Catt(chain_cfg=trb, device=0)
+    only = Catt(chain_cfg=trb, device=0, only_cdr3=True)
+    grp = Catt(chain_cfg=trb, device=0, only_cdr3=True, ngpu=4, devices=[0, 0, 0, 0])
+    try:
+        bufs = full.synth_reads(n, length)
+        seqs, quals = O.synth_reads(V, J, n, length)
+        assert np.array_equal(seqs.reshape(-1), bufs[2]) and np.array_equal(quals.reshape(-1), bufs[4]), "the two generators disagree"
+        ref = O.run_flat(V, J, O.make_config(trb), seqs, quals, threads=len(os.sched_getaffinity(0)))
+        rf, ro, rg = full.mainflow_buffers(n, *bufs), only.mainflow_buffers(n, *bufs), grp.mainflow_buffers(n, *bufs)
+        assert rf.text_digest() == ref.digest(False), "full lists differ from the oracle"
+        assert ro.text_digest() == ref.digest(True), "lists after filter! differ from the oracle"
+        assert rg.text_digest() == ref.digest(True) and rg.digest() == ro.digest(), "the 4-rank group differs"
+        for k in ("kmer", "the_err", "v_hits", "j_hits", "v_final", "j_final", "share", "pair_seq_mismatch", "full_pushed", "vpart", "jpart",
+                  "direct", "left", "rescued", "cand_v", "cand_j", "cells_v", "cells_j"):
+            assert rf.info[k] == ref.info[k] == ro.info[k] == rg.info[k], (k, rf.info[k], ref.info[k], ro.info[k], rg.info[k])
+        assert rf.info["vpart"] > 500_000 and rf.info["rescued"] > 50
+    finally:
+        full.close(); only.close(); grp.close()
