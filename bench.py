@@ -146,8 +146,33 @@ def nbsorb_scans(ctx, np, peak_ops):
     cnt = rng.integers(1, 50, size=nl)
     ctx.link_leaves(lgt, t[:nr], up, q[:nl], cnt)
     t0 = time.perf_counter(); ctx.link_leaves(lgt, t[:nr], up, q[:nl], cnt); dl = time.perf_counter() - t0
+    # a CLUSTERED repertoire, as real ones are (uniform-random pairs all die in the word-0 reject test): 4,000 roots, every query a
+    # root with 1-5 substitutions, so every query has near targets and the full three-plane test and the early exit both matter
+    nroot = 4000
+    roots = rng.integers(0, 4, size=(nroot, lgt), dtype=np.uint8)
+    parent = rng.integers(0, nroot, size=nq)
+    cq = roots[parent].copy()
+    for _ in range(5):
+        hit = rng.random(nq) < 0.6
+        pos = rng.integers(0, lgt, size=nq)
+        cq[hit, pos[hit]] = (cq[hit, pos[hit]] + rng.integers(1, 4, size=int(hit.sum()))) % 4
+    ct = np.concatenate([roots, cq[:nt - nroot]])            # targets: the roots plus 6,000 of the mutated sequences
+    cqa, cta = lut[cq], lut[ct]
+    flags = ctx.near_any(lgt, cqa, cta)
+    tc = []
+    for _ in range(3):
+        t0 = time.perf_counter(); ctx.near_any(lgt, cqa, cta); tc.append(time.perf_counter() - t0)
+    dc = sorted(tc)[1]
+    cl_cnt = rng.integers(1, 50, size=nl)
+    ctx.link_leaves(lgt, lut[roots[:nr]], up, cqa[:nl], cl_cnt)
+    t0 = time.perf_counter(); st, _ = ctx.link_leaves(lgt, lut[roots[:nr]], up, cqa[:nl], cl_cnt); dlc = time.perf_counter() - t0
     return {"near_any": {"pairs": nq * nt, "ms_per_call": dt * 1e3, "pairs_per_s": nq * nt / dt, "base_compares_per_s": nq * nt * (lgt - 6) / dt},
             "link_leaves": {"pairs": nl * nr, "ms_per_call": dl * 1e3, "pairs_per_s": nl * nr / dl},
+            "near_any_clustered": {"pairs": nq * nt, "ms_per_call": dc * 1e3, "pairs_per_s": nq * nt / dc, "flagged": int(flags.sum()),
+                                   "note": "4,000 roots; queries = roots with up to 5 substitutions; targets = roots + 6,000 mutated sequences: every query "
+                                           "has a target within 3 mismatches unless its own mutations exceed that, so blocks leave early"},
+            "link_leaves_clustered": {"pairs": nl * nr, "ms_per_call": dlc * 1e3, "pairs_per_s": nl * nr / dlc, "linked_once": int((st == 1).sum()),
+                                      "linked_twice_or_more": int((st >= 2).sum())},
             "note": "wall clock of the C-ABI call, pageable host buffers in / flags out (upload + bit-plane packing + scan + download); "
                     "kernel-only times in profiles/r01i_nbsorb_scans.txt; integer-ALU bound (2 LOP3 + 1 POPC per rejected pair), "
                     f"measured ALU issue peak {peak_ops / 1e12:.2f} T thread-instr/s"}
@@ -235,6 +260,7 @@ def main():
     ap.add_argument("--impl", default="gpu", choices=["gpu", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU-baseline sample (0 = auto, ~15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the 1 M-read runs of the other BASELINE configs")
     ap.add_argument("--no-file-e2e", action="store_true", help="skip the catt_run_file measurement (FASTQ written to a temp file)")
     args = ap.parse_args()
 
@@ -481,6 +507,31 @@ def main():
     if rank == 0 and world == 1 and not args.no_file_e2e and R > 0:
         line["e2e_file"] = file_e2e(ctx, np, R, args.length, rb[2], rb[4], rank * R)
         line["nbsorb_scans"] = nbsorb_scans(ctx, np, peak_ops)
+    if rank == 0 and world == 1 and not args.no_other_configs:
+        # the other BASELINE configs (configs[3]: 50-bp reads of three chains; configs[4]: mouse / pig TRB) at 1 M reads each, one GPU,
+        # host buffers in / lists out; parity of each against the CPU checker at this size: profiles/r02_parity_10M.txt
+        oc = {}
+        for sp, ch, ln in (("hs", "TRA", 50), ("hs", "TRB", 50), ("hs", "IGH", 50), ("hs", "IGH", 150), ("ms", "TRB", 150), ("pig", "TRB", 150)):
+            cx = Catt(chain_cfg=chain_config(sp, ch, "CDR3", os.path.join(fx, "resource")), device=local_rank, only_cdr3=True)
+            nn = 1_000_000
+            b = cx.synth_reads(nn, ln, seed=SEED)
+            for _ in range(2):
+                cx.mainflow_buffers(nn, *b).close()
+            t0 = time.perf_counter()
+            ii = []
+            for _ in range(3):
+                r_ = cx.mainflow_buffers(nn, *b)
+                ii.append(r_.info)
+                r_.close()
+            dt = (time.perf_counter() - t0) / 3
+            msw = sum(i["ms_sw"] for i in ii) / 3
+            oc[f"{sp} {ch} {ln}bp"] = {"reads_per_s_e2e": nn / dt, "ms_per_call": dt * 1e3, "gcups": ii[-1]["cells_v"] / (msw * 1e-3) / 1e9,
+                                      "dp_frac_algorithmic": 12.0 * ii[-1]["cells_v"] / (msw * 1e-3) / (peak_ops * 4.0),
+                                      "dp_frac_executed": 12.0 * ii[-1]["cells_computed_v"] / (msw * 1e-3) / (peak_ops * 4.0),
+                                      "stage_ms": {k: sum(i[k] for i in ii) / 3 for k in ("ms_seed", "ms_sw", "ms_select", "ms_order", "ms_extract", "ms_pool")},
+                                      "cand_per_read": ii[-1]["cand_v"] / nn, "kmer": ii[-1]["kmer"], "left": ii[-1]["left"], "rescued": ii[-1]["rescued"]}
+            cx.close()
+        line["other_configs"] = {"reads_per_call": 1_000_000, "what": "catt_run_reads from host buffers, 3 calls after 2 warm-ups, one GPU", "configs": oc}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
         n = args.cpu_sample or max(16000, 15000 * cores)       # ~15 s of CPU work on `cores` threads

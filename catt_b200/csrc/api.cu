@@ -455,8 +455,12 @@ int run_files_device(catt_ctx* c, int nfiles, const char* const* paths, catt_res
         const bool opened = (cb || rn >= (1u << 20)) && st->open(raw[f].data(), rn, cb ? (size_t)atol(cb) : (1u << 20));
         // the trailer's ISIZE is the text length mod 2^32: plausible (at least half the compressed size) -> exact bound; a large file
         // with an implausible one has wrapped -> generous bound (8x; FASTQ compresses 3-6x), HBM only - the host side is a window
-        const bool wrapped = opened && (uint64_t)st->isize_field() * 2 < rn && rn >= (1u << 29);
-        if (opened && ((st->isize_field() > 0 && (uint64_t)st->isize_field() * 2 >= rn) || wrapped)) {
+        // ... and so has a large file whose ISIZE passes that test but gives a ratio no FASTQ reaches (text of 4 GiB and more: 9.6 GB of
+        // reads leave ISIZE ~ 1 GB beside a 1.9 GB .gz).  Plain FASTQ deflates 3-6x; below 2.5x on a file of 512 MB and more the field
+        // is taken as wrapped
+        const uint64_t isz = opened ? (uint64_t)st->isize_field() : 0;
+        const bool wrapped = opened && rn >= (1u << 29) && (isz * 2 < rn || isz * 2 < rn * 5);
+        if (opened && ((isz > 0 && isz * 2 >= rn) || wrapped)) {
           bound = wrapped ? (int64_t)rn * 8 : (int64_t)st->isize_field();   // the stream verifies ISIZE (mod 2^32) and the CRC-32 at the end
           pgz[f] = std::move(st);
           PgzStream* q = pgz[f].get();
@@ -1157,7 +1161,8 @@ int catt_ctx_create(catt_ctx** out, const catt_config* cfg) {
   }
   const int device = devs[0];
   CATT_CUDA(cudaSetDevice(device));
-  std::unique_ptr<catt_ctx> c(new catt_ctx());
+  // (every early return below releases what was allocated so far: device tables, streams, events, the other ranks' contexts)
+  std::unique_ptr<catt_ctx, void (*)(catt_ctx*)> c(new catt_ctx(), catt_ctx_destroy);
   c->device = device;
   cudaDeviceProp prop;
   CATT_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -1584,22 +1589,27 @@ int catt_best_d(catt_ctx* c, const char* const* cdr3, int64_t n, int32_t* out) {
   if (!c || !out || (n > 0 && !cdr3)) return CATT_E_ARG;
   if (c->d_seqs.empty()) { for (int64_t i = 0; i < n; i++) out[i] = -1; return CATT_OK; }
   CATT_CUDA(cudaSetDevice(c->device));
-  std::string cat; std::vector<int32_t> off{0};
-  for (int64_t i = 0; i < n; i++) { cat += cdr3[i]; off.push_back((int32_t)cat.size()); }
-  char* d_c = nullptr; int32_t* d_o = nullptr; int32_t* d_r = nullptr;
-  CATT_CUDA(cudaMalloc(&d_c, cat.size() + 16));
-  CATT_CUDA(cudaMalloc(&d_o, off.size() * sizeof(int32_t)));
-  CATT_CUDA(cudaMalloc(&d_r, std::max<int64_t>(n, 1) * sizeof(int32_t)));
-  CATT_CUDA(cudaMemcpyAsync(d_c, cat.data(), cat.size(), cudaMemcpyHostToDevice, c->stream));
-  CATT_CUDA(cudaMemcpyAsync(d_o, off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-  int rc = launch_best_d(d_c, d_o, n, c->d_dseq, c->d_doff, (int)c->d_seqs.size(), d_r, c->stream);
-  if (!rc) {
-    cudaError_t e = cudaMemcpyAsync(out, d_r, n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    if (e != cudaSuccess) rc = cuda_fail(e, "best_d", __FILE__, __LINE__);
+  // in chunks whose concatenated text stays far below 2^31 bytes (the offsets are int32); the context's scratch is reused
+  const int64_t CH = 1 << 22;
+  std::string cat; std::vector<int32_t> off;
+  for (int64_t i0 = 0; i0 < n; i0 += CH) {
+    const int64_t m = std::min(CH, n - i0);
+    cat.clear(); off.assign(1, 0);
+    for (int64_t i = 0; i < m; i++) {
+      if (!cdr3[i0 + i]) { set_error("catt_best_d: null string"); return CATT_E_ARG; }
+      cat += cdr3[i0 + i];
+      if (cat.size() > 0x7FFF0000ull) { set_error("catt_best_d: CDR3 strings too long"); return CATT_E_LIMIT; }
+      off.push_back((int32_t)cat.size());
+    }
+    int rc;
+    if ((rc = c->cl[13].ensure(cat.size() + 16)) || (rc = c->cl[14].ensure(off.size() * sizeof(int32_t))) || (rc = c->cl[15].ensure((size_t)m * sizeof(int32_t)))) return rc;
+    CATT_CUDA(cudaMemcpyAsync(c->cl[13].p, cat.data(), cat.size(), cudaMemcpyHostToDevice, c->stream));
+    CATT_CUDA(cudaMemcpyAsync(c->cl[14].p, off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    if ((rc = launch_best_d(c->cl[13].as<char>(), c->cl[14].as<int32_t>(), m, c->d_dseq, c->d_doff, (int)c->d_seqs.size(), c->cl[15].as<int32_t>(), c->stream))) return rc;
+    CATT_CUDA(cudaMemcpyAsync(out + i0, c->cl[15].p, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CATT_CUDA(cudaStreamSynchronize(c->stream));
   }
-  cudaFree(d_c); cudaFree(d_o); cudaFree(d_r);
-  return rc;
+  return CATT_OK;
 }
 
 // ---- stage-level ---------------------------------------------------------------------------------------------------
