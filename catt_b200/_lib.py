@@ -72,7 +72,7 @@ EXPORTS = ["catt_ctx_create", "catt_ctx_destroy", "catt_last_error", "catt_versi
            "catt_batch_download", "catt_batch_free", "catt_ctx_stream", "catt_assemble", "catt_seed_candidates", "catt_sw_pairs",
            "catt_finder", "catt_alu_peak", "catt_batch_assemble", "catt_synth_reads", "catt_run_files", "catt_run_reads_files", "catt_set_host_threads", "catt_records_device", "catt_assemble_device", "catt_shard_counts", "catt_reads_device",
            "catt_assemble_resident", "catt_link_leaves", "catt_near_any", "catt_run_bam", "catt_bam_to_fastq", "catt_inflate_file",
-           "catt_comm_id", "catt_ctx_join", "catt_run_reads_shard", "catt_shard_upload", "catt_shard_run", "catt_result_digest", "catt_result_text_digest", "catt_run_file_shard", "catt_result_clonotypes"]
+           "catt_comm_id", "catt_ctx_join", "catt_run_reads_shard", "catt_shard_upload", "catt_shard_run", "catt_result_digest", "catt_result_text_digest", "catt_run_file_shard", "catt_result_clonotypes", "catt_real_score", "catt_order_records"]
 
 _lib = None
 
@@ -138,6 +138,8 @@ def load():
     L.catt_result_digest.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.catt_result_text_digest.argtypes = [vp, vp, C.POINTER(C.c_uint64)]
     L.catt_result_clonotypes.argtypes = [vp, C.POINTER(C.POINTER(Clonotype)), i64p]
+    L.catt_real_score.argtypes = [vp, C.c_int, C.c_int64, vp, vp, vp, vp, vp, vp, vp, C.c_int32, vp]
+    L.catt_order_records.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, vp, i64p, vp]
     L.catt_comm_id.argtypes = [vp]
     L.catt_ctx_join.argtypes = [vp, C.c_int32, C.c_int32, vp]
     L.catt_run_reads_shard.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, vp, vp, vp, vp, vp, C.c_int32, vp, C.POINTER(vp)]

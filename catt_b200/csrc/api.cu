@@ -2012,6 +2012,58 @@ int catt_finder(catt_ctx* c, int array_version, int64_t n, const char* seqs, con
   return rc;
 }
 
+int catt_real_score(catt_ctx* c, int which, int64_t n, const char* seqs, const int64_t* seq_off, const int32_t* rid, const int32_t* strand,
+                    const int32_t* qb, const int32_t* m_end, const int32_t* rb, int32_t allowance, uint8_t* out) {
+  if (!c || !out || !rid || !strand || !qb || !m_end || !rb || which < 0 || which > 1 || n < 0) return CATT_E_ARG;
+  if (n == 0) return CATT_OK;
+  CATT_CUDA(cudaSetDevice(c->device));
+  RefSet& rs = which ? c->J : c->V;
+  for (int64_t i = 0; i < n; i++) {
+    const int64_t l = seq_off[i + 1] - seq_off[i];
+    if (rid[i] < 0 || rid[i] >= (int)rs.names.size() || qb[i] < 0 || m_end[i] < qb[i] + 1 || m_end[i] > l || rb[i] < 0 || rb[i] + (m_end[i] - qb[i] - 1) >= rs.len[rid[i]]) {
+      set_error("catt_real_score: record %lld is not a valid alignment record", (long long)i);
+      return CATT_E_ARG;
+    }
+  }
+  PackedReads pr;
+  int rc = pack_reads(n, seqs, seq_off, &pr);
+  if (rc) return rc;
+  DeviceReads dr;
+  if ((rc = upload_reads(pr, n, &dr, c->stream))) return rc;
+  const size_t b = (size_t)n * sizeof(int32_t);
+  if ((rc = c->cl[0].ensure(5 * b + (size_t)n + 64))) { dr.release(); return rc; }
+  int32_t* d = c->cl[0].as<int32_t>();
+  const int32_t* src[5] = {rid, strand, qb, m_end, rb};
+  cudaError_t e = cudaSuccess;
+  for (int k = 0; k < 5 && e == cudaSuccess; k++) e = cudaMemcpyAsync(d + (size_t)k * n, src[k], b, cudaMemcpyHostToDevice, c->stream);
+  uint8_t* d_out = reinterpret_cast<uint8_t*>(d + 5 * (size_t)n);
+  if (e == cudaSuccess) rc = launch_real_score(rs.dev, dr.view(), d, d + n, d + 2 * n, d + 3 * n, d + 4 * n, allowance, d_out, c->sm_count, c->stream);
+  if (e == cudaSuccess && !rc) e = cudaMemcpyAsync(out, d_out, (size_t)n, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  dr.release();
+  if (e != cudaSuccess) return cuda_fail(e, "catt_real_score", __FILE__, __LINE__);
+  return rc;
+}
+
+int catt_order_records(catt_ctx* c, int64_t n, const char* names, const int64_t* name_off, const int32_t* read_len, const catt_aln* v_recs,
+                       const catt_aln* j_recs, int32_t* items3, int64_t* n_items, int64_t* counts5) {
+  if (!c || n < 0 || !n_items || !counts5 || (n > 0 && (!names || !name_off || !read_len || !v_recs || !j_recs || !items3))) { set_error("catt_order_records: bad argument"); return CATT_E_ARG; }
+  *n_items = 0;
+  for (int k = 0; k < 5; k++) counts5[k] = 0;
+  if (n == 0) return CATT_OK;
+  CATT_CUDA(cudaSetDevice(c->device));
+  int rc;
+  if ((rc = ensure_recs(c, n)) || (rc = c->rd_len.ensure((size_t)n * sizeof(int32_t)))) return rc;
+  int64_t vh = 0, jh = 0;
+  for (int64_t i = 0; i < n; i++) { vh += v_recs[i].mapped != 0; jh += j_recs[i].mapped != 0; }
+  CATT_CUDA(cudaMemcpyAsync(c->recs_all[0].p, v_recs, (size_t)n * sizeof(catt_aln), cudaMemcpyHostToDevice, c->stream));
+  CATT_CUDA(cudaMemcpyAsync(c->recs_all[1].p, j_recs, (size_t)n * sizeof(catt_aln), cudaMemcpyHostToDevice, c->stream));
+  CATT_CUDA(cudaMemcpyAsync(c->rd_len.p, read_len, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  NamesDev nd;
+  if ((rc = upload_names(c, n, names, name_off, &nd, nullptr))) return rc;
+  return order_only(c, n, nd, c->rd_len.as<int32_t>(), vh, jh, items3, n_items, counts5);
+}
+
 int catt_alu_peak(catt_ctx* c, double* ops, double* ms) {
   if (!c || !ops || !ms) return CATT_E_ARG;
   CATT_CUDA(cudaSetDevice(c->device));

@@ -672,6 +672,33 @@ static int order_file(catt_ctx* c, const OrderScratch& S, int64_t nf, const Name
   return CATT_OK;
 }
 
+// The ordering stage alone (parity hook): n reads of ONE file with their records already in c->recs_all and QNAMEs `nd`; the work
+// items come back as (kind, read, read2) triples in processing order, counts = {final V, final J, V-only, pairs, J-only}.
+int order_only(catt_ctx* c, int64_t n, const NamesDev& nd, const int32_t* d_len, int64_t nm_v, int64_t nm_j, int32_t* h_items, int64_t* n_items, int64_t* counts) {
+  int rc, launches = 0;
+  unsigned long long* cnt;
+  if ((rc = ensure(c, SB_CNT, C_COUNT, &cnt))) return rc;
+  unsigned long long* hcnt = c->pin[PIN_CNT].as<unsigned long long>() + 2 * N_COUNTERS;
+  OrderScratch OS;
+  if ((rc = order_alloc(c, n, nm_v, nm_j, &OS))) return rc;
+  ExtractItem* items;
+  if ((rc = ensure(c, SB_ITEMS, nm_v + nm_j, &items))) return rc;
+  const catt_aln* rec[2] = {c->recs_all[0].as<catt_aln>(), c->recs_all[1].as<catt_aln>()};
+  const int64_t nm[2] = {nm_v, nm_j};
+  catt_info info{};
+  int k = c->kmer;
+  OrderOut oo;
+  if ((rc = order_file(c, OS, n, nd, rec, d_len, nm, 0u, &k, info, cnt, hcnt, items, nm_v + nm_j, &oo, &launches))) return rc;
+  const int64_t t = oo.n_v + oo.n_p + oo.n_j;
+  std::vector<ExtractItem> h((size_t)std::max<int64_t>(t, 1));
+  if (t) CATT_CUDA(cudaMemcpyAsync(h.data(), items, (size_t)t * sizeof(ExtractItem), cudaMemcpyDeviceToHost, c->stream));
+  CATT_CUDA(cudaStreamSynchronize(c->stream));
+  for (int64_t i = 0; i < t; i++) { h_items[3 * i] = h[i].kind; h_items[3 * i + 1] = (int32_t)h[i].read; h_items[3 * i + 2] = (int32_t)h[i].read2; }
+  *n_items = t;
+  counts[0] = oo.F[0]; counts[1] = oo.F[1]; counts[2] = oo.n_v; counts[3] = oo.n_p; counts[4] = oo.n_j;
+  return CATT_OK;
+}
+
 // only_cdr3 with host buffers: gather the quality strings of the E surviving reads (read indices d_rid, local to h_quals) on the
 // host and upload them; S.quals / S.q_entry_off then index them per output entry
 static int gather_host_quals(catt_ctx* c, const DeviceQuals& dq, const uint32_t* d_rid, int64_t E, StrSrc* S, catt_info& info, cudaStream_t st) {

@@ -148,7 +148,41 @@ __global__ void __launch_bounds__(EX_WARPS * 32) finder_raw_kernel(ReadsDev read
   }
 }
 
+// real_score alone (parity hook): one warp per SAM record
+__global__ void __launch_bounds__(EX_WARPS * 32) real_score_kernel(RefDev ref, ReadsDev reads, const int32_t* __restrict__ rid,
+                                                                   const int32_t* __restrict__ strand, const int32_t* __restrict__ qb,
+                                                                   const int32_t* __restrict__ m_end, const int32_t* __restrict__ rb, int allowance,
+                                                                   uint8_t* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ExWarp* wsall = reinterpret_cast<ExWarp*>(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  ExWarp& ws = wsall[warp];
+  for (int64_t it = (int64_t)blockIdx.x * EX_WARPS + warp; it < reads.n; it += (int64_t)gridDim.x * EX_WARPS) {
+    const int m = reads.len[it];
+    const uint32_t* __restrict__ w = reads.words + reads.off[it];
+    const uint32_t* __restrict__ nm = w + read_base_words(m);
+    for (int i = lane; i < m; i += 32) ws.seq[i] = (uint8_t)sam_code(w, nm, m, i, strand[it]);
+    __syncwarp();
+    const bool ok = real_score_warp(ws.seq, m, ref.fa + ref.rec_off[rid[it]], ref.rec_len[rid[it]], qb[it] + 1, m_end[it], rb[it] + 1, allowance, lane);
+    if (lane == 0) out[it] = ok;
+    __syncwarp();
+  }
+}
+
 }  // namespace
+
+int launch_real_score(const RefDev& ref, const ReadsDev& reads, const int32_t* d_rid, const int32_t* d_strand, const int32_t* d_qb, const int32_t* d_m_end,
+                      const int32_t* d_rb, int allowance, uint8_t* d_out, int sm_count, cudaStream_t st) {
+  if (reads.n == 0) return CATT_OK;
+  const size_t smem = sizeof(ExWarp) * EX_WARPS;
+  static std::atomic<unsigned long long> optin{0};
+  int rc = smem_optin(real_score_kernel, (int)smem, optin);
+  if (rc) return rc;
+  const int grid = (int)std::min<int64_t>((reads.n + EX_WARPS - 1) / EX_WARPS, (int64_t)sm_count * 8);
+  real_score_kernel<<<grid, EX_WARPS * 32, smem, st>>>(ref, reads, d_rid, d_strand, d_qb, d_m_end, d_rb, allowance, d_out);
+  CATT_CUDA(cudaGetLastError());
+  return CATT_OK;
+}
 
 int launch_extract(const RefDev& vref, const RefDev& jref, const ReadsDev& reads, const FinderDev* d_finder,
                    const ExtractItem* d_items, ExtractOut* d_out, int64_t n, int kmer, int allow_v, int allow_j, int sm_count,

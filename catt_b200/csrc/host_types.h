@@ -199,6 +199,7 @@ struct ShardIn {
   int max_len = 0;                        // longest read of the whole sample
   int root = 0;
 };
+int order_only(catt_ctx* c, int64_t n, const NamesDev& nd, const int32_t* d_len, int64_t nm_v, int64_t nm_j, int32_t* h_items, int64_t* n_items, int64_t* counts);
 int build_clonotypes(catt_ctx* c, int64_t E, const catt_read* d_part, const char* d_seq, const char* d_qual, const char* host_seq,
                      const char* host_qual, catt_result* R, int* launches);
 int stage_b_sharded(catt_ctx* c, const ShardIn& in, const NamesDev& names, const DeviceQuals& dq, catt_result* R, int* launches);

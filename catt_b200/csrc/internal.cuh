@@ -200,6 +200,8 @@ struct ExtractOut {
 int launch_extract(const RefDev& vref, const RefDev& jref, const ReadsDev& reads, const FinderDev* d_finder,
                    const ExtractItem* d_items, ExtractOut* d_out, int64_t n, int kmer, int allow_v, int allow_j, int sm_count,
                    cudaStream_t st, int* launches);
+int launch_real_score(const RefDev& ref, const ReadsDev& reads, const int32_t* d_rid, const int32_t* d_strand, const int32_t* d_qb, const int32_t* d_m_end,
+                      const int32_t* d_rb, int allowance, uint8_t* d_out, int sm_count, cudaStream_t st);
 int launch_finder_raw(const ReadsDev& reads, const FinderDev* d_finder, int array_version, int32_t* d_out3, int sm_count, cudaStream_t st);
 
 struct PoolItem {          // a Vpart/Jpart read as the k-mer table sees it

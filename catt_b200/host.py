@@ -448,6 +448,27 @@ class Catt:
         _lib.check(_lib.load().catt_finder(self._h, int(array_version), len(seqs), sb, so.ctypes.data, out.ctypes.data))
         return out
 
+    def real_score(self, which, seqs, rid, strand, qb, m_end, rb, allowance) -> np.ndarray:
+        """real_score (catt.jl:58-84) alone, one SAM record per read."""
+        sb, so = _lib.concat(seqs)
+        a = [np.ascontiguousarray(x, dtype=np.int32) for x in (rid, strand, qb, m_end, rb)]
+        out = np.zeros(len(seqs), dtype=np.uint8)
+        _lib.check(_lib.load().catt_real_score(self._h, which, len(seqs), sb, so.ctypes.data, *[x.ctypes.data for x in a], allowance, out.ctypes.data))
+        return out
+
+    def order_records(self, names, seq_lens, vrec, jrec):
+        """The ordering stage alone: (items [t, 3] = kind, read, read2; counts = final V, final J, V-only, pairs, J-only)."""
+        nb, no = _lib.concat(names)
+        n = len(names)
+        vrec, jrec = np.ascontiguousarray(vrec), np.ascontiguousarray(jrec)
+        lens = np.ascontiguousarray(seq_lens, dtype=np.int32)
+        items = np.zeros((2 * n + 1, 3), dtype=np.int32)
+        cnt = np.zeros(5, dtype=np.int64)
+        t = C.c_int64()
+        _lib.check(_lib.load().catt_order_records(self._h, n, nb, no.ctypes.data, lens.ctypes.data, vrec.ctypes.data, jrec.ctypes.data,
+                                                  items.ctypes.data, C.byref(t), cnt.ctypes.data))
+        return items[:t.value].copy(), cnt
+
     def alu_peak(self):
         ops, ms = C.c_double(), C.c_double()
         _lib.check(_lib.load().catt_alu_peak(self._h, C.byref(ops), C.byref(ms)))

@@ -332,6 +332,17 @@ int catt_sw_pairs(catt_ctx* ctx, int which, int64_t n, const char* seqs, const i
                   const int32_t* strand, int32_t* out3);
 /* finder! on raw nucleotide strings: out[i] = {able, cdr3_off (0-based, -1 none), cdr3_len}. */
 int catt_finder(catt_ctx* ctx, int array_version, int64_t n, const char* seqs, const int64_t* seq_off, int32_t* out3);
+/* real_score (catt.jl:58-84) alone, one SAM record per read: record id / strand / soft clip qb / GetEndCigar m_end / POS-1 rb and the
+ * allowance (3 in assignV, 9 in assignJ); out[i] = 1 when the record passes. */
+int catt_real_score(catt_ctx* ctx, int which, int64_t n, const char* seqs, const int64_t* seq_off, const int32_t* rid, const int32_t* strand,
+                    const int32_t* qb, const int32_t* m_end, const int32_t* rb, int32_t allowance, uint8_t* out);
+/* The ordering stage alone (`samtools sort -t AS | view -F 2308 | tac | awk '!a[$1]++'`, share_name, the NR % nthreads chunk order, the
+ * name-sorted pairing: catt.jl:45-48, 221-237, 256-276, 288-297) for the reads of ONE file: from QNAMEs, read lengths and per-read
+ * records to the work items in processing order - items3[3t] = kind (0 V-only, 1 J-only, 2 both-mapped), read, second read (the J
+ * record's read of a pair); room for 3 * (mapped V + mapped J) ints.  counts5 = final V records, final J records, V-only items,
+ * pairs, J-only items. */
+int catt_order_records(catt_ctx* ctx, int64_t n, const char* names, const int64_t* name_off, const int32_t* read_len, const catt_aln* v_recs,
+                       const catt_aln* j_recs, int32_t* items3, int64_t* n_items, int64_t* counts5);
 /* Integer-ALU peak microbenchmark used as the DP roofline denominator: returns packed-s16x2 DPX op/s. */
 int catt_alu_peak(catt_ctx* ctx, double* dpx_ops_per_s, double* ms);
 

@@ -1310,6 +1310,70 @@ const char* co_result_dump(void* r, int which) {
   return d.c_str();
 }
 
+static std::string trim_readno(const char* nm) {          // bwa trim_readno, as in load_fastq
+  std::string r(nm);
+  const size_t l = r.size();
+  if (l > 2 && r[l - 2] == '/' && isdigit((unsigned char)r[l - 1])) r.resize(l - 2);
+  return r;
+}
+
+// ---- single-stage hooks for the parity tests -------------------------------------------------------------------------------------
+// real_score (catt.jl:58-84) alone: raw reads, record id / strand / qb / m_end / rb of a SAM record each; out[i] = 1 when it passes
+int co_real_score(void* refset, int64_t n, const char* const* seqs, const int32_t* rid, const int32_t* strand, const int32_t* qb,
+                  const int32_t* m_end, const int32_t* rb, int allowance, uint8_t* out) {
+  const RefSet& rs = *(RefSet*)refset;
+  for (int64_t i = 0; i < n; i++) {
+    AlnRec a{};
+    a.rid = rid[i]; a.strand = strand[i]; a.qb = qb[i]; a.m_end = m_end[i]; a.rb = rb[i];
+    const std::string tseq = sam_seq(seqs[i], a.strand);
+    out[i] = real_score(a, tseq, &rs.fa[rs.off[a.rid]], rs.len[a.rid], allowance) ? 1 : 0;
+  }
+  return 0;
+}
+
+// The ordering stage alone (catt.jl:45-48, 221-237, 256-276, 288-297): from per-read records (mapped, AS, rid, rb, strand) and
+// QNAMEs to the work items in processing order - [V-only records in chunk order | both-mapped pairs in name order | J-only records
+// in chunk order].  items[3 * t] = kind (0 V, 1 J, 2 pair), read index, second read index (the J record's read for a pair).
+// counts = {final V records, final J records, V-only items, pairs, J-only items}.  Returns the number of items.
+int64_t co_order(int64_t n, const char* const* names, const int32_t* vrec16, const int32_t* jrec16, int nthreads, int32_t* items, int64_t* counts) {
+  std::vector<Read> reads((size_t)n);
+  std::vector<AlnRec> vr((size_t)n), jr((size_t)n);
+  auto fill = [&](const int32_t* src, std::vector<AlnRec>& dst) {
+    for (int64_t i = 0; i < n; i++) {
+      const int32_t* r = src + i * 16;
+      AlnRec a{};
+      a.rid = r[1]; a.strand = r[2]; a.mapped = r[3]; a.AS = r[4]; a.qb = r[5]; a.m_end = r[6]; a.rb = r[7];
+      dst[i] = a;
+    }
+  };
+  for (int64_t i = 0; i < n; i++) reads[i].name = trim_readno(names[i]);
+  fill(vrec16, vr); fill(jrec16, jr);
+  const std::vector<int> vfin = final_sam_order(vr, reads, 0, (size_t)n), jfin = final_sam_order(jr, reads, 0, (size_t)n);
+  std::unordered_set<std::string> vnames, share;
+  for (int i : vfin) vnames.insert(reads[i].name);
+  for (int i : jfin) if (vnames.count(reads[i].name)) share.insert(reads[i].name);
+  struct Full { std::string name; int idx; int which; };
+  std::vector<Full> full;
+  std::vector<int> part[2];
+  for (int which = 0; which < 2; which++)
+    for (int i : chunk_order(which ? jfin : vfin, nthreads)) {
+      if (share.count(reads[i].name)) full.push_back({reads[i].name, i, which});
+      else part[which].push_back(i);
+    }
+  std::stable_sort(full.begin(), full.end(), [](const Full& a, const Full& b) { return a.name < b.name; });
+  int64_t t = 0, np = 0;
+  for (int i : part[0]) { items[3 * t] = 0; items[3 * t + 1] = i; items[3 * t + 2] = i; t++; }
+  for (size_t g = 0; g < full.size();) {
+    size_t h = g;
+    while (h < full.size() && full[h].name == full[g].name) h++;
+    if (h - g == 2) { items[3 * t] = 2; items[3 * t + 1] = full[g].idx; items[3 * t + 2] = full[g + 1].idx; t++; np++; }
+    g = h;
+  }
+  for (int i : part[1]) { items[3 * t] = 1; items[3 * t + 1] = i; items[3 * t + 2] = i; t++; }
+  counts[0] = (int64_t)vfin.size(); counts[1] = (int64_t)jfin.size(); counts[2] = (int64_t)part[0].size(); counts[3] = np; counts[4] = (int64_t)part[1].size();
+  return t;
+}
+
 // Canonical, order-sensitive digest of a list (the twin of catt_result_text_digest in libcatt_b200): per entry FNV-1a over
 // seq 0x1f qual 0x1f vs 0x1f js 0x1f cdr3 0x1f able, mixed with the entry's position, summed.  `only_cdr3` skips the reads whose
 // cdr3 is "None" (the lists as they stand after catt.jl:581-582); positions then count the kept reads.

@@ -230,6 +230,30 @@ def run_mem_files(vref: RefSet, jref: RefSet, cfg: CoConfig, files, threads=0) -
                                         len(files), fs.ctypes.data, threads))
 
 
+def real_score(refset: RefSet, seqs, rid, strand, qb, m_end, rb, allowance) -> np.ndarray:
+    """real_score (catt.jl:58-84) per SAM record; seqs are the raw reads."""
+    L = lib()
+    L.co_real_score.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_char_p)] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
+    a = [np.ascontiguousarray(x, dtype=np.int32) for x in (rid, strand, qb, m_end, rb)]
+    out = np.zeros(len(seqs), dtype=np.uint8)
+    L.co_real_score(refset.h, len(seqs), _strarr(seqs), *[x.ctypes.data for x in a], allowance, out.ctypes.data)
+    return out
+
+
+def order_items(names, vrec16: np.ndarray, jrec16: np.ndarray, nthreads=1):
+    """The ordering stage alone: (items [t, 3] = kind, read, read2; counts = final V, final J, V-only, pairs, J-only)."""
+    L = lib()
+    L.co_order.restype = C.c_int64
+    L.co_order.argtypes = [C.c_int64, C.POINTER(C.c_char_p), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    n = len(names)
+    v = np.ascontiguousarray(vrec16, dtype=np.int32)
+    j = np.ascontiguousarray(jrec16, dtype=np.int32)
+    items = np.zeros((2 * n + 1, 3), dtype=np.int32)
+    counts = np.zeros(5, dtype=np.int64)
+    t = L.co_order(n, _strarr(names), v.ctypes.data, j.ctypes.data, nthreads, items.ctypes.data, counts.ctypes.data)
+    return items[:t].copy(), counts
+
+
 def sw(q: str, t: str):
     a, b = C.c_int(), C.c_int()
     s = lib().co_sw(q.encode(), t.encode(), C.byref(a), C.byref(b))

@@ -386,20 +386,73 @@ def test_fastq_ingest_on_device_equals_host_parser(ctx, O, orefs, trb, sample, t
 
 
 def test_large_result_ring_copy(ctx, O, orefs, trb, sample):
-    """Results too large to pin per call come back through the two pinned ring buffers (forced here with CATT_PIN_MAX)."""
-    names, seqs, quals = [x[:7000] for x in sample]
-    want = ctx.mainflow_reads(names, seqs, quals)
-    a = ([myread_tuple(r) for r in want.Vpart], [myread_tuple(r) for r in want.Jpart])
+    """Results too large to pin per call come back through the two pinned ring buffers (forced here with CATT_PIN_MAX): the lists
+    must still be the oracle's."""
+    names, seqs, quals = [x[:7000] * 8 for x in sample]       # > 1 MiB of strings: above the malloc threshold
+    ref = O.run_mem(orefs[0], orefs[1], O.make_config(trb), names, seqs, quals)
+    want = ([myread_tuple(r) for r in ref.Vpart], [myread_tuple(r) for r in ref.Jpart])
     os.environ["CATT_PIN_MAX"] = "1"
     try:
-        got = ctx.mainflow_reads(names * 8, seqs * 8, quals * 8)       # > 1 MiB of strings: above the malloc threshold
-        ref = ctx_ref = None
+        got = ctx.mainflow_reads(names, seqs, quals)
     finally:
         os.environ.pop("CATT_PIN_MAX", None)
-    again = ctx.mainflow_reads(names * 8, seqs * 8, quals * 8)
-    assert ([myread_tuple(r) for r in got.Vpart], [myread_tuple(r) for r in got.Jpart]) == \
-           ([myread_tuple(r) for r in again.Vpart], [myread_tuple(r) for r in again.Jpart])
-    assert len(got.Vpart) >= len(a[0])
+    assert ([myread_tuple(r) for r in got.Vpart], [myread_tuple(r) for r in got.Jpart]) == want
+    assert got.text_digest() == ref.digest(False)
+    again = ctx.mainflow_reads(names, seqs, quals)            # ... and the pinned-block path gives the same
+    assert again.digest() == got.digest()
+    assert len(want[0]) > 2000
+
+
+def test_real_score_hook(ctx, O, orefs, sample):
+    """real_score + HammingDistanceG4 (catt.jl:58-84) alone: every mapped record of the sample at the allowances assignV / assignJ
+    use (3, 9), the golden-file setting (0) and a generous one, plus records shifted so that the paddings hit both ends."""
+    seqs = sample[1]
+    for which in (0, 1):
+        recs = ctx.align_shard(seqs)[which]
+        idx = np.nonzero(recs["mapped"] == 1)[0]
+        rs = [seqs[i] for i in idx]
+        f = {k: recs[k][idx].astype(np.int32) for k in ("rid", "strand", "qb", "m_end", "rb")}
+        n_pass = {}
+        for allow in (0, 3, 9, 40):
+            g = ctx.real_score(which, rs, f["rid"], f["strand"], f["qb"], f["m_end"], f["rb"], allow)
+            o = O.real_score(orefs[which], rs, f["rid"], f["strand"], f["qb"], f["m_end"], f["rb"], allow)
+            assert np.array_equal(g, o), (which, allow, int((g != o).sum()))
+            n_pass[allow] = int(g.sum())
+        assert 0 < n_pass[0] <= n_pass[3] <= n_pass[9] <= n_pass[40] <= len(idx)
+        if which == 0:
+            assert n_pass[0] < n_pass[40], "the V records of the sample do discriminate the allowance (SURVEY 0.5)"
+
+
+@pytest.mark.parametrize("threads", [1, 2, 5])
+def test_order_records_hook(trb, O, orefs, sample, threads):
+    """The ordering stage alone (samtools sort -t AS | view -F 2308 | tac | awk dedup, share_name, the NR % nthreads chunk order, the
+    name-sorted pairing): the work items and their order from the sample's records, and from records with forced ties - equal AS /
+    record / position on several reads of one QNAME - where only the input order decides."""
+    from catt_b200.host import Catt
+    c = Catt(chain_cfg=trb, thread=threads)
+    try:
+        names, seqs, _ = sample
+        v, j = c.align_shard(seqs)
+        lens = [len(s) for s in seqs]
+
+        def to16(r):
+            out = np.zeros((len(r), 16), dtype=np.int32)
+            for col, k in enumerate(("ordinal", "rid", "strand", "mapped", "as", "qb", "m_end", "rb", "qe", "re", "nm", "mi", "ncand", "ntied")):
+                out[:, col] = r[k]
+            return out
+        for variant in range(2):
+            if variant == 1:                              # collapse QNAMEs 4 to 1 and flatten the scores: ties everywhere
+                names = [f"q{i // 4}/{1 + i % 2}" for i in range(len(names))]
+                v, j = v.copy(), j.copy()
+                v["as"] = np.where(v["mapped"] == 1, 40 + (np.arange(len(v)) % 3), v["as"])
+                j["as"] = np.where(j["mapped"] == 1, 25, j["as"])
+            items, cnt = c.order_records(names, lens, v, j)
+            oitems, ocnt = O.order_items(names, to16(v), to16(j), threads)
+            assert np.array_equal(cnt, ocnt), (variant, cnt, ocnt)
+            assert np.array_equal(items, oitems), (variant, int((items != oitems).any(axis=1).sum()))
+            assert cnt[3] > 100 and cnt[2] > 500
+    finally:
+        c.close()
 
 
 def test_only_cdr3_lists(trb, O, orefs):
