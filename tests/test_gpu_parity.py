@@ -388,7 +388,8 @@ def test_fastq_ingest_on_device_equals_host_parser(ctx, O, orefs, trb, sample, t
 def test_large_result_ring_copy(ctx, O, orefs, trb, sample):
     """Results too large to pin per call come back through the two pinned ring buffers (forced here with CATT_PIN_MAX): the lists
     must still be the oracle's."""
-    names, seqs, quals = [x[:7000] * 8 for x in sample]       # > 1 MiB of strings: above the malloc threshold
+    seqs, quals = sample[1][:7000] * 8, sample[2][:7000] * 8  # > 1 MiB of strings: above the malloc threshold
+    names = [f"c{k}_{nm}" for k in range(8) for nm in sample[0][:7000]]       # eight copies with QNAMEs of their own (mate suffixes kept)
     ref = O.run_mem(orefs[0], orefs[1], O.make_config(trb), names, seqs, quals)
     want = ([myread_tuple(r) for r in ref.Vpart], [myread_tuple(r) for r in ref.Jpart])
     os.environ["CATT_PIN_MAX"] = "1"
