@@ -5,7 +5,7 @@
  *   roundtrip layout
  *       prints sizeof / offsetof of every struct of the header, one "name value" per line: tests/test_abi.py compares them with
  *       the ctypes mirror (catt_b200/_lib.py), so the two cannot drift apart silently.  Needs no GPU.
- *   roundtrip run <resource_dir> <fastq> [ngpu]
+ *   roundtrip run <resource_dir> <fastq> [ngpu [distinct]]     (distinct: one GPU per rank, NCCL from a process without torch)
  *       fills catt_config BY VALUE for hs TRB (the fields of reference.jl:24-37), runs catt_run_file, walks the catt_read arrays
  *       the way catt.jl:579 would and prints the counters and an order-sensitive checksum of (seq, qual, V name, J name, cdr3)
  *       over both lists.  The GPU test compares this line with the same numbers obtained through ctypes.
@@ -52,7 +52,7 @@ static int layout(void) {
   return 0;
 }
 
-static int run(const char* res, const char* fastq, int ngpu) {
+static int run(const char* res, const char* fastq, int ngpu, int distinct) {
   char v[4096], j[4096];
   snprintf(v, sizeof v, "%s/TR/hs/TRB/TRBV-gai6-DNA.fa", res);
   snprintf(j, sizeof j, "%s/TR/hs/TRB/TRBJ-gai3-DNA.fa", res);
@@ -67,7 +67,8 @@ static int run(const char* res, const char* fastq, int ngpu) {
   cfg.inner_c = "(CAS|CSA|CAW|CAT|CSV|CAI|CAR)"; cfg.inner_f = "place_holder";
   cfg.coffset = 2; cfg.foffset = 1; cfg.min_score = 12; cfg.kmer = CATT_KMER_AUTO; cfg.julia_nthreads = 2;
   cfg.allow_v = 3; cfg.allow_j = 9; cfg.device = 0; cfg.n_d = 3; cfg.d_names = d_names; cfg.d_seqs = d_seqs;
-  cfg.only_cdr3 = 1; cfg.clonotypes = 1; cfg.ngpu = ngpu; cfg.devices = ngpu > 1 ? devices : NULL;
+  cfg.only_cdr3 = 1; cfg.clonotypes = 1; cfg.ngpu = ngpu;
+  cfg.devices = (ngpu > 1 && !distinct) ? devices : NULL;     /* all ranks on device 0 (peer copies), or devices 0..ngpu-1 (NCCL) */
   catt_ctx* ctx = NULL;
   catt_result* r = NULL;
   if (catt_ctx_create(&ctx, &cfg) != CATT_OK) { fprintf(stderr, "catt_ctx_create: %s\n", catt_last_error()); return 1; }
@@ -122,7 +123,7 @@ static int run(const char* res, const char* fastq, int ngpu) {
 
 int main(int argc, char** argv) {
   if (argc >= 2 && !strcmp(argv[1], "layout")) return layout();
-  if (argc >= 4 && !strcmp(argv[1], "run")) return run(argv[2], argv[3], argc >= 5 ? atoi(argv[4]) : 1);
-  fprintf(stderr, "usage: roundtrip layout | roundtrip run <resource_dir> <fastq> [ngpu]\n");
+  if (argc >= 4 && !strcmp(argv[1], "run")) return run(argv[2], argv[3], argc >= 5 ? atoi(argv[4]) : 1, argc >= 6 && !strcmp(argv[5], "distinct"));
+  fprintf(stderr, "usage: roundtrip layout | roundtrip run <resource_dir> <fastq> [ngpu [distinct]]\n");
   return 2;
 }

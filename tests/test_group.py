@@ -152,6 +152,34 @@ def test_group_file_input(trb, fx, tmp_path):
         one.close()
 
 
+def test_group_records_fixed_kmer_and_unmapped_samples(trb, sample):
+    """keep_records on a group (every rank's records, in input order, on the root), a fixed args["kmer"], and samples in which
+    nothing maps (random reads, reads of N): the exchanges must cope with empty gathers."""
+    from catt_b200.host import Catt
+    from util import random_reads
+    names, seqs, quals = [x[:3000] for x in sample]
+    one = Catt(chain_cfg=trb, device=0, keep_records=True, kmer=19)
+    grp = Catt(chain_cfg=trb, device=0, keep_records=True, kmer=19, ngpu=3, devices=[0, 0, 0])
+    try:
+        a, b = one.mainflow_reads(names, seqs, quals), grp.mainflow_reads(names, seqs, quals)
+        same(a, b)
+        assert a.info["kmer"] == 19
+        for which in (0, 1):
+            ra, rb = a.records(which), b.records(which)
+            assert len(ra) == len(rb) == 3000 and ra.tobytes() == rb.tobytes()
+        rnd = random_reads(4000, 60, 11)
+        rn = [f"x{i}" for i in range(len(rnd))]
+        rq = ["I" * 60] * len(rnd)
+        a, b = one.mainflow_reads(rn, rnd, rq), grp.mainflow_reads(rn, rnd, rq)
+        same(a, b)
+        alln = ["N" * 80] * 500
+        a, b = one.mainflow_reads(rn[:500], alln, ["#" * 80] * 500), grp.mainflow_reads(rn[:500], alln, ["#" * 80] * 500)
+        same(a, b)
+        assert b.info["v_hits"] == 0 and b.info["vpart"] == 0
+    finally:
+        one.close(); grp.close()
+
+
 def test_group_nccl_when_two_gpus(trb, sample):
     import torch
     if torch.cuda.device_count() < 2:
