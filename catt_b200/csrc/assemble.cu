@@ -1332,7 +1332,9 @@ int stage_b_sharded(catt_ctx* c, const ShardIn& in, const NamesDev& names, const
   if (run_pool) {
     KmerTable tab{};
     tab.nsub = (uint32_t)N;
-    tab.sub_slots = std::max<uint64_t>(1024, ((uint64_t)M * 11ull * 2ull + N - 1) / N);
+    // 1.5 slots per insert (the one-GPU table uses 2): the sub-tables cross NVLink once, and reads of one clonotype share most
+    // of their k-mers, so the real load factor is below 2/3
+    tab.sub_slots = std::max<uint64_t>(1024, ((uint64_t)M * 11ull * 3ull / 2ull + N - 1) / N);
     const uint64_t slots = tab.sub_slots * (uint64_t)N;
     unsigned long long* cursor; PoolEntry *sendb, *recvb;
     if ((rc = ensure(c, SB_TAB_KEYS, (int64_t)slots, &tab.keys)) || (rc = ensure(c, SB_TAB_VALS, (int64_t)slots, &tab.vals)) ||
