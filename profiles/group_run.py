@@ -55,6 +55,10 @@ print("  Stage A slowest / fastest rank %.0f / %.0f ms; order %.0f, extract %.0f
     ", ".join(f"{nm} {i['ms_coll'][k]:.1f} ms / {i['bytes_coll'][k] / 1e9:.2f} GB" for k, nm in enumerate(_lib.COLL_NAMES))), flush=True)
 r1.close(); rg.close()
 ok = same
+# fresh contexts for the file part: the 100 M-read calls left ~100 GB of scratch on device 0 (both contexts live there)
+one.close(); grp.close()
+one = Catt(chain_cfg=cc, device=0, only_cdr3=True, clonotypes=True)
+grp = Catt(chain_cfg=cc, device=0, only_cdr3=True, clonotypes=True, ngpu=ngpu, devices=[r % ndev for r in range(ngpu)] if ngpu > ndev else None)
 
 if nf > 0:
     nf = min(nf, n)
