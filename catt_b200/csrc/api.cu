@@ -950,6 +950,118 @@ int64_t record_boundary(int fd, int64_t fsize, int64_t x) {
   return -1;
 }
 
+// ---- Stage A in two halves, for inputs whose global read ordinals are not known yet (run_file_rank) ------------------------------
+// front: seeding, task expansion, SW scores, selection up to the tie-break (best score, candidate count, bitmap of the candidates
+// that reach it - per read, kept for the whole block in c->df_*); back: the tie-break with the ordinal, TRACK pass, CIGAR facts.
+int deferred_reserve(catt_ctx* c, int64_t n, cudaStream_t st) {
+  int rc;
+  for (int which = 0; which < 2; which++) {
+    const int CW = (which ? c->J : c->V).dev.CW;
+    if ((rc = c->df_tied[which].ensure_keep((size_t)std::max<int64_t>(n, 1) * CW * sizeof(uint32_t), st)) ||
+        (rc = c->df_mx[which].ensure_keep((size_t)std::max<int64_t>(n, 1) * sizeof(int16_t), st)) ||
+        (rc = c->df_nc[which].ensure_keep((size_t)std::max<int64_t>(n, 1) * sizeof(int16_t), st))) return rc;
+  }
+  return CATT_OK;
+}
+
+int front_launch(catt_ctx* c, int which, const ReadsDev& rv, int64_t r0, bool with_seed, int* launches) {
+  RefSet& rs = which ? c->J : c->V;
+  AlignBuffers& ab = c->ab[which];
+  cudaStream_t st = aln_stream(c, which);
+  cudaEvent_t* ev = c->ev_a[which];
+  int rc;
+  if (with_seed) {
+    CATT_CUDA(cudaMemsetAsync(ab.counters, 0, N_COUNTERS * sizeof(unsigned long long), st));
+    CATT_CUDA(cudaMemsetAsync(ab.ntask, 0, (rv.n + 1) * sizeof(uint32_t), st));
+    CATT_CUDA(cudaEventRecord(ev[0], st));
+    if ((rc = launch_seed(rs.dev, rv, ab, c->sm_count, st, launches))) return rc;
+    CATT_CUDA(cudaEventRecord(ev[1], st));
+  }
+  CATT_CUDA(cudaEventRecord(ev[2], st));
+  if ((rc = launch_expand(rs.dev, rv, ab, st, launches))) return rc;
+  CATT_CUDA(cudaEventRecord(ev[3], st));
+  if ((rc = launch_sw(rs.dev, rv, ab, c->sm_count, st, launches))) return rc;
+  CATT_CUDA(cudaEventRecord(ev[4], st));
+  if ((rc = launch_select_pre(rs.dev, rv, ab, c->df_tied[which].as<uint32_t>() + r0 * rs.dev.CW, c->df_mx[which].as<int16_t>() + r0,
+                              c->df_nc[which].as<int16_t>() + r0, st, launches))) return rc;
+  CATT_CUDA(cudaEventRecord(ev[5], st));
+  CATT_CUDA(cudaMemcpyAsync(c->pin[PIN_CNT].as<unsigned long long>() + which * N_COUNTERS, ab.counters, N_COUNTERS * sizeof(unsigned long long),
+                            cudaMemcpyDeviceToHost, st));
+  return CATT_OK;
+}
+
+int front_queue(catt_ctx* c, const ReadsDev& rv, int64_t r0, int* launches) {
+  int rc;
+  if ((rc = fork_j(c))) return rc;
+  for (int which = 0; which < 2; which++) {
+    RefSet& rs = which ? c->J : c->V;
+    if ((rc = ensure_align_buffers(c->ab[which], rs.dev, rv.n)) || (!c->ab[which].tasks && (rc = ensure_task_buffers(c->ab[which], rv.n * 10 + 4096)))) return rc;
+    if ((rc = front_launch(c, which, rv, r0, true, launches))) return rc;
+  }
+  return CATT_OK;
+}
+
+// after join_streams: the task buffer may have been too small (the piece's expansion + SW + pre-selection is re-run once), counters
+int front_finish(catt_ctx* c, const ReadsDev& rv, int64_t r0, catt_info* info, int* launches) {
+  int rc;
+  for (int which = 0; which < 2; which++) {
+    AlignBuffers& ab = c->ab[which];
+    cudaStream_t st = aln_stream(c, which);
+    cudaEvent_t* ev = c->ev_a[which];
+    unsigned long long* cnt = c->pin[PIN_CNT].as<unsigned long long>() + which * N_COUNTERS;
+    float ms_seed = 0, ms_exp = 0, ms_sw = 0, ms_sel = 0;
+    cudaEventElapsedTime(&ms_seed, ev[0], ev[1]);
+    for (int attempt = 0;; attempt++) {
+      if (cnt[6] > 0) { set_error("%llu reads exceed the seeding run-list capacity", cnt[6]); return CATT_E_LIMIT; }
+      float a = 0, b = 0, d = 0;
+      cudaEventElapsedTime(&a, ev[2], ev[3]); cudaEventElapsedTime(&b, ev[3], ev[4]); cudaEventElapsedTime(&d, ev[4], ev[5]);
+      ms_exp += a; ms_sw += b; ms_sel += d;
+      if (cnt[9] == 0) break;
+      if (attempt == 1) { set_error("SW task buffer overflow persists (%llu tasks)", cnt[9]); return CATT_E_LIMIT; }
+      if ((rc = ensure_task_buffers(ab, (int64_t)cnt[9] + (int64_t)cnt[9] / 8 + 1024))) return rc;
+      unsigned long long z[N_COUNTERS] = {0};
+      z[4] = cnt[4]; z[6] = cnt[6];
+      CATT_CUDA(cudaMemcpyAsync(ab.counters, z, sizeof z, cudaMemcpyHostToDevice, st));
+      CATT_CUDA(cudaStreamSynchronize(st));
+      if ((rc = front_launch(c, which, rv, r0, false, launches))) return rc;
+      CATT_CUDA(cudaStreamSynchronize(st));
+    }
+    if (which == 0) { info->ms_seed += ms_seed + ms_exp; info->ms_seed_kernel += ms_seed; info->ms_sw += ms_sw; info->ms_select += ms_sel; }
+    else info->ms_j_stream += ms_seed + ms_exp + ms_sw + ms_sel;
+    if (which) { info->cand_j += (int64_t)cnt[0]; info->cells_j += (int64_t)cnt[1]; info->cells_computed_j += (int64_t)cnt[8]; }
+    else { info->cand_v += (int64_t)cnt[0]; info->cells_v += (int64_t)cnt[1]; info->cells_computed_v += (int64_t)cnt[8]; }
+  }
+  return CATT_OK;
+}
+
+// the back half of one piece: tie-break with the reads' global ordinals, TRACK pass on the winners, CIGAR facts, traceback
+int back_chunk(catt_ctx* c, const ReadsDev& rv, int64_t r0, int64_t ordinal, catt_info* info, int* launches) {
+  int rc;
+  if ((rc = fork_j(c))) return rc;
+  for (int which = 0; which < 2; which++) {
+    RefSet& rs = which ? c->J : c->V;
+    AlignBuffers& ab = c->ab[which];
+    cudaStream_t st = aln_stream(c, which);
+    if ((rc = ensure_align_buffers(ab, rs.dev, rv.n))) return rc;
+    CATT_CUDA(cudaMemsetAsync(ab.counters, 0, N_COUNTERS * sizeof(unsigned long long), st));
+    CATT_CUDA(cudaEventRecord(c->ev_a[which][4], st));
+    if ((rc = launch_select_post(rs.dev, rv, ab, c->df_tied[which].as<uint32_t>() + r0 * rs.dev.CW, c->df_mx[which].as<int16_t>() + r0,
+                                 c->df_nc[which].as<int16_t>() + r0, c->recs_all[which].as<catt_aln>() + r0, ordinal, c->min_score, c->sm_count, st, launches))) return rc;
+    CATT_CUDA(cudaEventRecord(c->ev_a[which][5], st));
+    CATT_CUDA(cudaMemcpyAsync(c->pin[PIN_CNT].as<unsigned long long>() + which * N_COUNTERS, ab.counters, N_COUNTERS * sizeof(unsigned long long),
+                              cudaMemcpyDeviceToHost, st));
+  }
+  if ((rc = join_streams(c))) return rc;
+  for (int which = 0; which < 2; which++) {
+    const unsigned long long* cnt = c->pin[PIN_CNT].as<unsigned long long>() + which * N_COUNTERS;
+    float d = 0;
+    cudaEventElapsedTime(&d, c->ev_a[which][4], c->ev_a[which][5]);
+    if (which) { info->gapped_j += (int64_t)cnt[2]; info->j_hits += (int64_t)cnt[3]; info->ms_j_stream += d; }
+    else { info->gapped_v += (int64_t)cnt[2]; info->v_hits += (int64_t)cnt[3]; info->ms_select += d; }
+  }
+  return CATT_OK;
+}
+
 int run_file_rank(catt_ctx* c, Comm* comm, int root, const char* path, catt_result** out) {
   std::unique_ptr<catt_result> R(new catt_result());
   Trace tr;
@@ -970,45 +1082,108 @@ int run_file_rank(catt_ctx* c, Comm* comm, int root, const char* path, catt_resu
     b1 = me + 1 == N ? fsize : record_boundary(fd, fsize, fsize / N * (me + 1));
     if (b0 < 0 || b1 < 0) status = RANK_FALLBACK;
   }
+  // The block goes through in record-aligned pieces: piece k is read (all host threads of this rank) into one of two pinned buffers
+  // and copied to HBM; the GPU indexes + packs it and runs the FRONT half of Stage A on its reads - seeding, SW, and the selection up
+  // to the tie-break (select_kernel MODE 1) - while the host reads piece k+1.  The BACK half (tie-break with the global ordinal,
+  // TRACK pass, CIGAR facts) follows once every rank has counted its reads.
   const double t0 = now_ms();
+  struct Piece { int64_t r0, n; };
+  std::vector<Piece> pieces;
+  catt_info& I = R->info;
   if (!status && b1 > b0) {
     const int64_t bytes = b1 - b0;
-    const size_t piece = (size_t)64 << 20;
-    if ((rc = c->rd_text.ensure((size_t)bytes + 32)) || (rc = c->pin[PIN_PACK0].ensure(piece + 16)) || (rc = c->pin[PIN_PACK1].ensure(piece + 16))) status = rc;
+    int64_t piece = (int64_t)64 << 20;
+    if (const char* e = getenv("CATT_GROUP_PIECE")) piece = std::max<int64_t>(atoll(e), 4096);      // tests: many pieces on a small file
+    if ((rc = c->rd_text.ensure((size_t)bytes + 32)) || (rc = c->pin[PIN_PACK0].ensure((size_t)piece + 16)) || (rc = c->pin[PIN_PACK1].ensure((size_t)piece + 16))) status = rc;
     char* d_text = c->rd_text.as<char>();
-    int64_t text_end = bytes;                                    // after trimming trailing blank space; then one '\n'
-    for (int64_t o = 0, k = 0; !status && o < bytes; o += (int64_t)piece, k++) {
-      const int64_t len = std::min<int64_t>((int64_t)piece, bytes - o);
+    int64_t file_pos = b0, text_pos = 0, tail = 0;                // next byte to read; device offset of the next piece; bytes carried over
+    int64_t pending_r0 = -1, pending_n = 0;                       // the piece whose front half is in flight
+    auto finish_pending = [&]() -> int {
+      if (pending_r0 < 0) return CATT_OK;
+      int r = join_streams(c);
+      if (r) return r;
+      DeviceReads dr;
+      dr.words = c->rd_words.as<uint32_t>(); dr.off = c->rd_off.as<uint32_t>(); dr.len = c->rd_len.as<int32_t>(); dr.n = pending_r0 + pending_n; dr.max_len = max_len;
+      r = front_finish(c, dr.view(pending_r0, pending_n), pending_r0, &I, &launches);
+      pending_r0 = -1;
+      return r;
+    };
+    for (int64_t k = 0; !status && (file_pos < b1 || tail > 0); k++) {
       char* h = c->pin[PIN_PACK0 + (k & 1)].as<char>();
-      if (k >= 2 && cudaEventSynchronize(c->ev_h2d[k & 1]) != cudaSuccess) { set_error("FASTQ text upload failed"); status = CATT_E_CUDA; break; }
-      const int64_t sub = 4 << 20, ns = (len + sub - 1) / sub;
+      // (the carried tail was written into this buffer after its previous copy had completed, see below)
+      const int64_t want = std::min<int64_t>(piece - tail, b1 - file_pos);
+      const int64_t sub = 4 << 20, ns = (want + sub - 1) / sub;
       bool ok = true;
       #pragma omp parallel for schedule(dynamic, 1) reduction(&& : ok)
       for (int64_t q = 0; q < ns; q++) {
         int64_t a = q * sub;
-        const int64_t e = std::min(len, a + sub);
-        while (a < e) { const ssize_t r = pread(fd, h + a, (size_t)(e - a), (off_t)(b0 + o + a)); if (r <= 0) { ok = false; break; } a += r; }
+        const int64_t e = std::min(want, a + sub);
+        while (a < e) { const ssize_t r = pread(fd, h + tail + a, (size_t)(e - a), (off_t)(file_pos + a)); if (r <= 0) { ok = false; break; } a += r; }
       }
       if (!ok) { set_error("short read on %s", path); status = CATT_E_IO; break; }
-      int64_t put = len;
-      if (o + len == bytes) {                                    // last piece of the block: trailing blank space off, exactly one '\n'
-        while (put > 0 && (h[put - 1] == '\n' || h[put - 1] == '\r' || h[put - 1] == ' ' || h[put - 1] == '\t')) put--;
-        if (put == 0 && o > 0) { status = RANK_FALLBACK; break; }   // (a piece of nothing but blank lines: let the host parser decide)
-        h[put++] = '\n';
-        text_end = o + put;
+      int64_t have = tail + want;
+      file_pos += want;
+      int64_t cut = have;
+      if (file_pos >= b1) {                                      // last piece of the block: trailing blank space off, exactly one '\n'
+        while (cut > 0 && (h[cut - 1] == '\n' || h[cut - 1] == '\r' || h[cut - 1] == ' ' || h[cut - 1] == '\t')) cut--;
+        if (cut == 0) { if (text_pos == 0) break; status = RANK_FALLBACK; break; }     // (only blank lines left: let the host parser decide)
+        h[cut++] = '\n';
+        have = cut;
+      } else {                                                   // the last record start in the buffer: a line '@...' whose second next line is '+...'
+        int64_t q = have;
+        cut = -1;
+        for (int tries = 0; tries < 64 && q > 0; tries++) {
+          const char* nl = (const char*)memrchr(h, '\n', (size_t)(q - 1));      // the newline before the line that ends at or before q
+          const int64_t ls = nl ? (nl - h) + 1 : 0;
+          if (h[ls] == '@' && ls > 0) {
+            const char* n1 = (const char*)memchr(h + ls, '\n', (size_t)(have - ls));
+            const char* n2 = n1 ? (const char*)memchr(n1 + 1, '\n', (size_t)(h + have - (n1 + 1))) : nullptr;
+            if (n2 && n2 + 1 < h + have && n2[1] == '+') { cut = ls; break; }
+          }
+          q = ls;
+        }
+        if (cut <= 0) { status = RANK_FALLBACK; break; }          // no record boundary in a whole piece: not the FASTQ this path handles
       }
-      if (cudaMemcpyAsync(d_text + o, h, (size_t)put, cudaMemcpyHostToDevice, c->copy_stream) != cudaSuccess ||
+      if (cudaMemcpyAsync(d_text + text_pos, h, (size_t)cut, cudaMemcpyHostToDevice, c->copy_stream) != cudaSuccess ||
           cudaEventRecord(c->ev_h2d[k & 1], c->copy_stream) != cudaSuccess) { set_error("FASTQ text upload failed"); status = CATT_E_CUDA; break; }
-      R->info.bytes_h2d += put;
-    }
-    if (!status && cudaStreamSynchronize(c->copy_stream) != cudaSuccess) { set_error("FASTQ text upload failed"); status = CATT_E_CUDA; }
-    tr.lap("run_file_rank: read + H2D");
-    if (!status && text_end > 1) {
+      I.bytes_h2d += cut;
+      // the unfinished record(s) behind the cut go to the front of the other buffer, once the copy that last read it is done
+      tail = have - cut;
+      if (tail > 0) {
+        if (k >= 1 && cudaEventSynchronize(c->ev_h2d[(k + 1) & 1]) != cudaSuccess) { set_error("FASTQ text upload failed"); status = CATT_E_CUDA; break; }
+        memcpy(c->pin[PIN_PACK0 + ((k + 1) & 1)].as<char>(), h + cut, (size_t)tail);
+      } else if (k >= 1 && cudaEventSynchronize(c->ev_h2d[(k + 1) & 1]) != cudaSuccess) { set_error("FASTQ text upload failed"); status = CATT_E_CUDA; break; }
+      // the previous piece's kernels must be done before its per-piece scratch is reused (they ran while this piece was read)
+      if ((rc = finish_pending())) { status = rc; break; }
+      // index + pack this piece, then queue the front half of Stage A on its reads
+      if (cudaStreamWaitEvent(c->stream, c->ev_h2d[k & 1], 0) != cudaSuccess) { set_error("FASTQ text upload failed"); status = CATT_E_CUDA; break; }
       int fb = 0;
-      rc = ingest_fastq(c, d_text, 0, text_end, 0, 0, &n_loc, &words, &max_len, &fb, &launches, c->stream);
-      if (rc) status = fb ? RANK_FALLBACK : rc;
+      int64_t np = 0; uint64_t wp = 0;
+      rc = ingest_fastq(c, d_text, text_pos, text_pos + cut, n_loc, words, &np, &wp, &max_len, &fb, &launches, c->stream);
+      if (rc) { status = fb ? RANK_FALLBACK : rc; break; }
+      if (k == 0 && np > 0 && bytes > 2 * cut) {                  // size the per-read arrays for the whole block once (each growth is a copy)
+        const int64_t est = (int64_t)((double)bytes / ((double)cut / (double)np) * 1.03) + 4096;
+        const uint64_t est_words = (uint64_t)((double)wp / (double)np * (double)est) + 4096;
+        cudaStream_t st = c->stream;
+        if (est_words < 0xFFFFFFF0ull &&
+            ((rc = c->rd_name_beg.ensure_keep((size_t)(est + 1) * 8, st)) || (rc = c->rd_name_end.ensure_keep((size_t)(est + 1) * 8, st)) ||
+             (rc = c->rd_seq_beg.ensure_keep((size_t)(est + 1) * 8, st)) || (rc = c->rd_qual_beg.ensure_keep((size_t)(est + 1) * 8, st)) ||
+             (rc = c->rd_len.ensure_keep((size_t)(est + 1) * 4, st)) || (rc = c->rd_off.ensure_keep((size_t)(est + 2) * 4, st)) ||
+             (rc = c->rd_words.ensure_keep((size_t)(est_words + 4) * 4, st)) || (rc = deferred_reserve(c, est, st)))) { status = rc; break; }
+      }
+      if ((rc = deferred_reserve(c, n_loc + np, c->stream))) { status = rc; break; }
+      if (np > 0) {
+        DeviceReads dr;
+        dr.words = c->rd_words.as<uint32_t>(); dr.off = c->rd_off.as<uint32_t>(); dr.len = c->rd_len.as<int32_t>(); dr.n = n_loc + np; dr.max_len = max_len;
+        if ((rc = front_queue(c, dr.view(n_loc, np), n_loc, &launches))) { status = rc; break; }
+        pending_r0 = n_loc; pending_n = np;
+        pieces.push_back(Piece{n_loc, np});
+      }
+      n_loc += np; words += wp; text_pos += cut;
     }
-    tr.lap("run_file_rank: index + pack");
+    if (!status && (rc = finish_pending())) status = rc;
+    if (status) { join_streams(c); cudaStreamSynchronize(c->copy_stream); }
+    tr.lap("run_file_rank: read + H2D + index + pack + seeding / SW, piece by piece");
   }
   if (fd >= 0) close(fd);
   const double ms_ingest = now_ms() - t0;
@@ -1027,16 +1202,20 @@ int run_file_rank(catt_ctx* c, Comm* comm, int root, const char* path, catt_resu
   }
   if (fallback) return RANK_FALLBACK;
   c->last_n = n_loc; c->last_words = (int64_t)words; c->last_max_len = max_len;
-  R->info.ms_pack = ms_ingest;
-  DeviceReads dr;
-  dr.words = c->rd_words.as<uint32_t>(); dr.off = c->rd_off.as<uint32_t>(); dr.len = c->rd_len.as<int32_t>(); dr.n = n_loc; dr.max_len = max_len;
+  I.ms_pack = ms_ingest;
+  // the back half, now that this block's first read has its global ordinal
+  const double ta = now_ms();
+  rc = ensure_recs(c, n_loc);
   FileHits fh;
   fh.start = {0, n_loc};
-  std::vector<int64_t> ord0{lo};
-  const double ta = now_ms();
-  rc = n_loc > 0 ? stage_a_resident(c, dr, 0, &fh, &R->info, &launches, &ord0) : CATT_OK;
+  fh.v.assign(1, 0); fh.j.assign(1, 0);
+  for (size_t k = 0; !rc && k < pieces.size(); k++) {
+    DeviceReads dr;
+    dr.words = c->rd_words.as<uint32_t>(); dr.off = c->rd_off.as<uint32_t>(); dr.len = c->rd_len.as<int32_t>(); dr.n = n_loc; dr.max_len = max_len;
+    rc = back_chunk(c, dr.view(pieces[k].r0, pieces[k].n), pieces[k].r0, lo + pieces[k].r0, &I, &launches);
+  }
   const double ms_a = now_ms() - ta + ms_ingest;
-  tr.lap("run_file_rank: align");
+  tr.lap("run_file_rank: tie-break + TRACK pass");
   NamesDev nd;
   nd.s = c->rd_text.as<char>(); nd.beg = reinterpret_cast<const int64_t*>(c->rd_name_beg.p); nd.end = reinterpret_cast<const int64_t*>(c->rd_name_end.p);
   DeviceQuals dq;
@@ -1247,6 +1426,7 @@ void catt_ctx_destroy(catt_ctx* c) {
   delete c->comm;
   for (auto& b : c->sh) b.release();
   for (auto& b : c->cl) b.release();
+  for (int w = 0; w < 2; w++) { c->df_tied[w].release(); c->df_mx[w].release(); c->df_nc[w].release(); }
   c->V.release(); c->J.release();
   free_align_buffers(c->ab[0]); free_align_buffers(c->ab[1]);
   for (auto& b : c->sb) b.release();

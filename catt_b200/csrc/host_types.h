@@ -124,6 +124,7 @@ struct catt_ctx {
   DevBuf sb[SB_COUNT];
   DevBuf sh[SH_SLOTS];
   DevBuf cl[16];                          // clonotype table scratch (clonotype.cu)
+  DevBuf df_tied[2], df_mx[2], df_nc[2];  // Stage A split at the tie-break (run_file_rank): per read tied-candidate bitmap, best score, candidates
   int want_clonotypes = 0;
   // ---- one sample over several GPUs.  Either this context is rank 0 of an in-process group (catt_config.ngpu > 1: `peers` are the
   //      contexts of ranks 1.., `comms[r]` the communicator of rank r) or it is one rank of a multi-process group (catt_ctx_join).

@@ -175,6 +175,9 @@ int launch_expand(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, cu
 int launch_sw(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int sm_count, cudaStream_t st, int* launches);
 int launch_select(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, catt_aln* recs, int64_t first_ordinal, int min_score,
                   int sm_count, cudaStream_t st, int* launches);
+int launch_select_pre(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, uint32_t* tied, int16_t* mxs, int16_t* ncands, cudaStream_t st, int* launches);
+int launch_select_post(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, uint32_t* tied, int16_t* mxs, int16_t* ncands, catt_aln* recs,
+                       int64_t first_ordinal, int min_score, int sm_count, cudaStream_t st, int* launches);
 int launch_sw_pairs(const RefDev& ref, const ReadsDev& reads, const int32_t* d_rid, const int32_t* d_strand, int32_t* d_out3,
                     int sm_count, cudaStream_t st);
 int alu_peak(int sm_count, cudaStream_t st, double* ops_per_s, double* ms);

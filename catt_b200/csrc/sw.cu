@@ -496,14 +496,51 @@ int dispatch_sw(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks, c
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int sub_score(uint32_t a, uint32_t b) { return (a > 3 || b > 3) ? -1 : (a == b ? 1 : -2); }
 
+// MODE 0: the whole selection.  MODE 1 / 2 split it where bwa's tie-break enters (hash_64(read ordinal + rank among the tied)):
+// MODE 1 scores the candidates and leaves, per read, the best score, the candidate count and the bitmap of the candidates that
+// reach it; MODE 2 picks the winner from those once the read's global ordinal is known.  A GPU group that ingests a file learns
+// the ordinals only when every rank has counted its reads, and runs seeding + SW + MODE 1 while the file is still being read.
+template <int MODE>
 __global__ void select_kernel(RefDev ref, ReadsDev reads, const uint32_t* __restrict__ candbits, const uint32_t* __restrict__ canonbits,
                               const SwTask* __restrict__ tasks,
                               const uint32_t* __restrict__ task_off, const uint32_t* __restrict__ task_score, int64_t cap_tasks,
                               int64_t first_ordinal, int min_score, catt_aln* __restrict__ recs, SwTask* __restrict__ wtasks,
-                              unsigned long long* __restrict__ counters) {
+                              unsigned long long* __restrict__ counters, uint32_t* __restrict__ tied, int16_t* __restrict__ mxs,
+                              int16_t* __restrict__ ncands) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long my_cand = 0, my_cells = 0, my_hit = 0, my_comp = 0;
-  if (r < reads.n && (int64_t)task_off[reads.n] <= cap_tasks) {
+  if (MODE == 2) {
+    if (r < reads.n) {
+      catt_aln a;
+      a.ordinal = (int32_t)(first_ordinal + r);
+      a.rid = -1; a.strand = 0; a.mapped = 0; a.qb = 0; a.m_end = 0; a.rb = 0; a.qe = 0; a.re = 0; a.nm = 0; a.mi = 0; a.ntied = 0;
+      const int mx = mxs[r], ncand = ncands[r];
+      a.as = (int16_t)mx; a.ncand = (int16_t)ncand;
+      if (ncand > 0 && mx >= min_score) {
+        const uint64_t ord = (uint64_t)(first_ordinal + r);
+        int ntied = 0, win_c = -1;
+        uint64_t win_h = ~0ull;
+        auto consider = [&](int c) {
+          const uint64_t h = hash_64(ord + (uint64_t)ntied);
+          ntied++;
+          if (h < win_h) { win_h = h; win_c = c; }
+        };
+        for (int w = 0; w < ref.CW; w++) {                    // T order: forward records ascending, then reverse-strand records descending
+          uint32_t b = tied[r * ref.CW + w] & 0x55555555u;
+          while (b) { const int bit = __ffs(b) - 1; b &= b - 1; consider(w * 32 + bit); }
+        }
+        for (int w = ref.CW - 1; w >= 0; w--) {
+          uint32_t b = tied[r * ref.CW + w] & 0xAAAAAAAAu;
+          while (b) { const int bit = 31 - __clz(b); b &= ~(1u << bit); consider(w * 32 + bit); }
+        }
+        a.rid = win_c >> 1; a.strand = (int16_t)(win_c & 1); a.mapped = 1; a.ntied = (int16_t)ntied;
+        my_hit = 1;
+        const unsigned long long k = atomicAdd(&counters[7], 1ull);
+        wtasks[k] = SwTask{(uint32_t)r, (uint16_t)win_c, (uint16_t)0xFFFF};
+      }
+      recs[r] = a;
+    }
+  } else if (r < reads.n && (int64_t)task_off[reads.n] <= cap_tasks) {
     const uint32_t t0 = task_off[r], t1 = task_off[r + 1];
     const int m = reads.len[r];
     catt_aln a;
@@ -531,6 +568,7 @@ __global__ void select_kernel(RefDev ref, ReadsDev reads, const uint32_t* __rest
       const uint32_t b = canonbits[r * ref.CW + w];
       pre[0][w] = (uint16_t)nfw; pre[1][w] = (uint16_t)nrv;
       nfw += __popc(b & 0x55555555u); nrv += __popc(b & 0xAAAAAAAAu);
+      if (MODE == 1) tied[r * ref.CW + w] = 0;
     }
     const uint32_t rv_base = t0 + (nfw + 1) / 2;
     auto consider = [&](int c) {
@@ -543,9 +581,13 @@ __global__ void select_kernel(RefDev ref, ReadsDev reads, const uint32_t* __rest
       const uint32_t ts = task_score[(st ? rv_base : t0) + (rank >> 1)];
       const int sc = (int)((rank & 1) ? ts >> 16 : ts & 0xffff);
       if (sc == mx) {
-        const uint64_t h = hash_64(ord + (uint64_t)ntied);
-        ntied++;
-        if (h < win_h) { win_h = h; win_c = c; }
+        if (MODE == 1) {
+          tied[r * ref.CW + (c >> 5)] |= 1u << (c & 31);
+        } else {
+          const uint64_t h = hash_64(ord + (uint64_t)ntied);
+          ntied++;
+          if (h < win_h) { win_h = h; win_c = c; }
+        }
       }
     };
     if (t1 > t0) {
@@ -559,15 +601,19 @@ __global__ void select_kernel(RefDev ref, ReadsDev reads, const uint32_t* __rest
       }
     }
     my_cand = ncand;
-    a.ncand = (int16_t)ncand;
-    a.as = (int16_t)mx;
-    if (ncand > 0 && mx >= min_score) {
-      a.rid = win_c >> 1; a.strand = (int16_t)(win_c & 1); a.mapped = 1; a.ntied = (int16_t)ntied;
-      my_hit = 1;
-      const unsigned long long k = atomicAdd(&counters[7], 1ull);
-      wtasks[k] = SwTask{(uint32_t)r, (uint16_t)win_c, (uint16_t)0xFFFF};
+    if (MODE == 1) {
+      mxs[r] = (int16_t)mx; ncands[r] = (int16_t)ncand;
+    } else {
+      a.ncand = (int16_t)ncand;
+      a.as = (int16_t)mx;
+      if (ncand > 0 && mx >= min_score) {
+        a.rid = win_c >> 1; a.strand = (int16_t)(win_c & 1); a.mapped = 1; a.ntied = (int16_t)ntied;
+        my_hit = 1;
+        const unsigned long long k = atomicAdd(&counters[7], 1ull);
+        wtasks[k] = SwTask{(uint32_t)r, (uint16_t)win_c, (uint16_t)0xFFFF};
+      }
+      recs[r] = a;
     }
-    recs[r] = a;
   }
   // block-level reduction of the work counters
   __shared__ unsigned long long sh[4];
@@ -775,12 +821,8 @@ int launch_sw(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int sm
 }
 
 // selection, the TRACK pass over the winners, CIGAR facts, traceback of the rare gapped winners
-int launch_select(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, catt_aln* recs, int64_t first_ordinal, int min_score,
-                  int sm_count, cudaStream_t st, int* launches) {
-  if (reads.n == 0) return CATT_OK;
-  select_kernel<<<(unsigned)((reads.n + 127) / 128), 128, 0, st>>>(ref, reads, ab.candbits, ab.canonbits, ab.tasks, ab.task_off, ab.task_score,
-                                                                   ab.cap_tasks, first_ordinal, min_score, recs, ab.wtasks, ab.counters);
-  CATT_CUDA(cudaGetLastError());
+// TRACK pass on the winners, CIGAR facts, traceback of the gapped ones: everything after the winner of every read is known
+static int launch_after_select(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, catt_aln* recs, int sm_count, cudaStream_t st, int* launches) {
   int rc = dispatch_sw<true>(ref, reads, ab.wtasks, reinterpret_cast<const uint32_t*>(ab.counters + 7), reads.n, ab.wres, sm_count, st);
   if (rc) return rc;
   finish_kernel<<<(unsigned)((reads.n + 127) / 128), 128, 0, st>>>(ref, reads, ab.wtasks, ab.wres, recs, ab.gapped_list, ab.counters);
@@ -794,8 +836,37 @@ int launch_select(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, ca
   if ((rc = smem_optin(traceback_kernel, 220 * 1024, optin))) return rc;
   traceback_kernel<<<sm_count * 4, 32, smem, st>>>(ref, reads, ab.gapped_list, ab.counters, recs);
   CATT_CUDA(cudaGetLastError());
-  *launches += 4;
+  *launches += 3;
   return CATT_OK;
+}
+
+int launch_select(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, catt_aln* recs, int64_t first_ordinal, int min_score,
+                  int sm_count, cudaStream_t st, int* launches) {
+  if (reads.n == 0) return CATT_OK;
+  select_kernel<0><<<(unsigned)((reads.n + 127) / 128), 128, 0, st>>>(ref, reads, ab.candbits, ab.canonbits, ab.tasks, ab.task_off, ab.task_score,
+                                                                      ab.cap_tasks, first_ordinal, min_score, recs, ab.wtasks, ab.counters, nullptr, nullptr, nullptr);
+  CATT_CUDA(cudaGetLastError());
+  *launches += 1;
+  return launch_after_select(ref, reads, ab, recs, sm_count, st, launches);
+}
+
+// the selection split at the tie-break (select_kernel MODE 1 / 2): `tied` = reads.n x CW words, `mxs` / `ncands` = reads.n each
+int launch_select_pre(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, uint32_t* tied, int16_t* mxs, int16_t* ncands, cudaStream_t st, int* launches) {
+  if (reads.n == 0) return CATT_OK;
+  select_kernel<1><<<(unsigned)((reads.n + 127) / 128), 128, 0, st>>>(ref, reads, ab.candbits, ab.canonbits, ab.tasks, ab.task_off, ab.task_score,
+                                                                      ab.cap_tasks, 0, 0, nullptr, nullptr, ab.counters, tied, mxs, ncands);
+  CATT_CUDA(cudaGetLastError());
+  *launches += 1;
+  return CATT_OK;
+}
+int launch_select_post(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, uint32_t* tied, int16_t* mxs, int16_t* ncands, catt_aln* recs,
+                       int64_t first_ordinal, int min_score, int sm_count, cudaStream_t st, int* launches) {
+  if (reads.n == 0) return CATT_OK;
+  select_kernel<2><<<(unsigned)((reads.n + 127) / 128), 128, 0, st>>>(ref, reads, nullptr, nullptr, nullptr, nullptr, nullptr, 0, first_ordinal, min_score,
+                                                                      recs, ab.wtasks, ab.counters, tied, mxs, ncands);
+  CATT_CUDA(cudaGetLastError());
+  *launches += 1;
+  return launch_after_select(ref, reads, ab, recs, sm_count, st, launches);
 }
 
 int launch_sw_pairs(const RefDev& ref, const ReadsDev& reads, const int32_t* d_rid, const int32_t* d_strand, int32_t* d_out3,

@@ -152,6 +152,35 @@ def test_group_file_input(trb, fx, tmp_path):
         one.close()
 
 
+@pytest.mark.parametrize("piece", [4096, 70000, 1 << 20])
+def test_group_file_input_many_pieces(trb, fx, tmp_path, monkeypatch, piece):
+    """The ranks of a group take their byte range in record-aligned pieces: seeding, SW and the selection up to bwa's tie-break run
+    on piece k while piece k+1 is read; the tie-break (which hashes the GLOBAL read ordinal) and the TRACK pass follow when every
+    rank has counted its reads.  Small pieces (CATT_GROUP_PIECE) put dozens of them through a 2.7 MB file: same lists as one GPU,
+    also for CRLF text and a file whose records carry long '+' lines."""
+    from catt_b200.host import Catt
+    fq = os.path.join(fx, "testSample.fq")
+    txt = open(fq, "rb").read()
+    lines = txt.split(b"\n")
+    plus = b"\n".join(b"+" + lines[i - 2][1:] if i % 4 == 2 and i + 1 < len(lines) else l for i, l in enumerate(lines))
+    variants = {"plain": txt, "crlf": txt.replace(b"\n", b"\r\n"), "plus_names": plus, "no_final_newline": txt.rstrip(b"\n")}
+    one = Catt(chain_cfg=trb, device=0)
+    try:
+        want = one.mainflow(fq)
+        monkeypatch.setenv("CATT_GROUP_PIECE", str(piece))
+        for ngpu in (2, 3):
+            grp = Catt(chain_cfg=trb, device=0, ngpu=ngpu, devices=[0] * ngpu)
+            try:
+                for name, data in variants.items():
+                    p = tmp_path / f"{name}_{ngpu}.fq"
+                    p.write_bytes(data)
+                    same(want, grp.mainflow(str(p)))
+            finally:
+                grp.close()
+    finally:
+        one.close()
+
+
 def test_group_records_fixed_kmer_and_unmapped_samples(trb, sample):
     """keep_records on a group (every rank's records, in input order, on the root), a fixed args["kmer"], and samples in which
     nothing maps (random reads, reads of N): the exchanges must cope with empty gathers."""
