@@ -170,6 +170,8 @@ struct AlignBuffers {       // per reference set, sized for one batch
 int launch_seed(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int sm_count, cudaStream_t st, int* launches);
 // task expansion + SW scoring + selection + traceback (sw.cu)
 constexpr int N_COUNTERS = 16;
+// counters 10..13: work cursors of the persistent kernels (seeding, its overflow pass, bulk DP, TRACK pass), zeroed with the rest
+constexpr int CTR_WORK_SEED = 10, CTR_WORK_REDO = 11, CTR_WORK_SW = 12, CTR_WORK_TRACK = 13;
 int ensure_task_buffers(AlignBuffers& ab, int64_t want);
 int launch_expand(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, cudaStream_t st, int* launches);
 int launch_sw(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int sm_count, cudaStream_t st, int* launches);

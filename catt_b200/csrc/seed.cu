@@ -20,6 +20,7 @@ namespace catt {
 namespace {
 
 constexpr int SEED_WARPS = 8;
+constexpr int SEED_GRAB = 4;
 constexpr int RUNS_SMEM = 256;
 constexpr int RUNS_GLOBAL = 16384;
 constexpr unsigned FULL = 0xffffffffu;
@@ -438,7 +439,7 @@ __global__ void __launch_bounds__(SEED_WARPS * 32) seed_kernel(RefDev ref, Reads
     stage_to_smem(t2s, ref.T2, (uint32_t)t2_bytes_smem, &bar);
     T2 = t2s;
   }
-  const int64_t gw = (int64_t)blockIdx.x * SEED_WARPS + warp, nw = (int64_t)gridDim.x * SEED_WARPS;
+  const int64_t gw = (int64_t)blockIdx.x * SEED_WARPS + warp;
   Scratch sc;
   if (GS) {
     uint32_t* base = gscratch + (size_t)gw * (RUNS_GLOBAL * 3);
@@ -447,9 +448,21 @@ __global__ void __launch_bounds__(SEED_WARPS * 32) seed_kernel(RefDev ref, Reads
   } else {
     sc.runs_q = ws.runs_q; sc.runs_t = ws.runs_t; sc.cov = ws.cov; sc.ord = ws.ord; sc.cap = RUNS_SMEM;
   }
+  // reads are handed out SEED_GRAB at a time from a device-wide cursor: the work per read varies several-fold and a CTA may start
+  // late (the other reference set's kernels share the SMs), so a static split would end on its unluckiest warp
   const int64_t total = GS ? (int64_t)counters[4] : reads.n;
-  for (int64_t it = gw; it < total; it += nw) {
+  unsigned long long* cursor = counters + (GS ? CTR_WORK_REDO : CTR_WORK_SEED);
+  int64_t it = 0, it_end = 0;
+  for (;;) {
+    if (it == it_end) {
+      unsigned long long b = 0;
+      if (lane == 0) b = atomicAdd(cursor, (unsigned long long)SEED_GRAB);
+      it = (int64_t)__shfl_sync(FULL, b, 0);
+      if (it >= total) break;
+      it_end = min(it + SEED_GRAB, total);
+    }
     const int64_t r = GS ? (int64_t)redo[it] : it;
+    it++;
     const bool ok = seed_one_read(ref, T2, reads, r, ws, sc, lane);
     if (ok) {
       write_out(ref, ws, r, candbits, canonbits, ntask, lane);

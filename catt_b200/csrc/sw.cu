@@ -53,6 +53,15 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   return d;
 }
 
+// Work distribution of the persistent DP kernels: a warp takes its next `count` tasks from a device-wide cursor.  (A static
+// partition made every launch as slow as its last-started CTA: the V and J reference sets run on two streams, and a CTA that has
+// to wait for a slot held by the other stream's kernel would still own a full 1/grid share of the tasks.)
+__device__ __forceinline__ int64_t next_tasks(unsigned long long* work, int count, int lane) {
+  unsigned long long b = 0;
+  if (lane == 0) b = atomicAdd(work, (unsigned long long)count);
+  return (int64_t)__shfl_sync(FULL, b, 0);
+}
+
 // SAM-oriented base of a packed read: strand 1 = reverse complement
 __device__ __forceinline__ uint32_t read_code(const uint32_t* __restrict__ w, const uint32_t* __restrict__ nm, int len, int i, int strand) {
   const int p = strand ? len - 1 - i : i;
@@ -141,7 +150,8 @@ __device__ __forceinline__ uint32_t pack_key(int score, int i, int j) {
 template <int G, int C, bool TRACK>
 __global__ void __launch_bounds__(SW_THREADS) sw_score_kernel(RefDev ref, ReadsDev reads, const SwTask* __restrict__ tasks,
                                                               const uint32_t* __restrict__ ntasks_dev, int64_t ntasks_cap,
-                                                              uint32_t* __restrict__ out, int tb_bytes_smem, int ml) {
+                                                              uint32_t* __restrict__ out, int tb_bytes_smem, int ml,
+                                                              unsigned long long* __restrict__ work) {
   constexpr int GPW = 32 / G;                         // tasks per warp
   constexpr int GPB = GPW * (SW_THREADS / 32);        // tasks per block
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -161,8 +171,9 @@ __global__ void __launch_bounds__(SW_THREADS) sw_score_kernel(RefDev ref, ReadsD
   const int g = lane % G, grp = lane / G;
   uint32_t* sel_arr = sel_all + (size_t)(warp * GPW + grp) * ml;
 
-  for (int64_t base = ((int64_t)blockIdx.x * (SW_THREADS / 32) + warp) * GPW; base < ntasks;
-       base += (int64_t)gridDim.x * GPB) {
+  for (;;) {
+    const int64_t base = next_tasks(work, GPW, lane);
+    if (base >= ntasks) break;
     const int64_t t = base + grp;
     const bool live = t < ntasks;
     int m = 0;
@@ -292,7 +303,7 @@ __global__ void __launch_bounds__(SW_THREADS) sw_score_kernel(RefDev ref, ReadsD
 
 template <int G, int C, bool TRACK>
 int launch_sw_t(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks, const uint32_t* ntasks_dev, int64_t cap, uint32_t* res,
-                int sm_count, cudaStream_t st) {
+                unsigned long long* work, int sm_count, cudaStream_t st) {
   constexpr int GPB = (32 / G) * (SW_THREADS / 32);
   const int ml = (reads.max_len + 3) & ~3;
   const int tb_bytes = (ref.L + 64) & ~15;
@@ -308,7 +319,7 @@ int launch_sw_t(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks, c
   const int64_t ntasks_max = TRACK ? (cap + 1) / 2 : cap;
   const int64_t want = (ntasks_max + GPB - 1) / GPB;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)sm_count * per_sm, want));
-  k<<<grid, SW_THREADS, smem, st>>>(ref, reads, tasks, ntasks_dev, cap, res, tb_smem, ml);
+  k<<<grid, SW_THREADS, smem, st>>>(ref, reads, tasks, ntasks_dev, cap, res, tb_smem, ml, work);
   CATT_CUDA(cudaGetLastError());
   return CATT_OK;
 }
@@ -327,7 +338,7 @@ int launch_sw_t(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks, c
 template <int G, int C>
 __global__ void __launch_bounds__(SW_THREADS) sw_bulk2_kernel(RefDev ref, ReadsDev reads, const SwTask* __restrict__ tasks,
                                                               const uint32_t* __restrict__ ntasks_dev, int64_t ntasks_cap,
-                                                              uint32_t* __restrict__ out, int ml) {
+                                                              uint32_t* __restrict__ out, int ml, unsigned long long* __restrict__ work) {
   constexpr int GPW = 32 / G;
   constexpr int GPB = GPW * (SW_THREADS / 32);
   constexpr int CH = (C + 3) / 4;
@@ -346,8 +357,9 @@ __global__ void __launch_bounds__(SW_THREADS) sw_bulk2_kernel(RefDev ref, ReadsD
   const uint8_t* __restrict__ Tb = ref.Tb;
   const uint32_t neg7 = NEG7 ^ (uint32_t)((unsigned long long)ntasks_cap >> 62);   // == NEG7, opaque to constant propagation
 
-  for (int64_t base = ((int64_t)blockIdx.x * (SW_THREADS / 32) + warp) * GPW; base < ntasks;
-       base += (int64_t)gridDim.x * GPB) {
+  for (;;) {
+    const int64_t base = next_tasks(work, GPW, lane);
+    if (base >= ntasks) break;
     const int64_t t = base + grp;
     const bool live = t < ntasks;
     int m = 0;
@@ -441,7 +453,7 @@ __global__ void __launch_bounds__(SW_THREADS) sw_bulk2_kernel(RefDev ref, ReadsD
 
 template <int G, int C>
 int launch_sw_bulk(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks, const uint32_t* ntasks_dev, int64_t cap, uint32_t* res,
-                   int sm_count, cudaStream_t st) {
+                   unsigned long long* work, int sm_count, cudaStream_t st) {
   constexpr int GPB = (32 / G) * (SW_THREADS / 32);
   constexpr int PROFW = 5 * G * ((C + 3) / 4) * 4;
   const int ml = (reads.max_len + 1 + 15) & ~15;                 // room for the phantom row of odd-length reads
@@ -454,38 +466,38 @@ int launch_sw_bulk(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks
   if (per_sm < 1) per_sm = 1;
   const int64_t want = (cap + GPB - 1) / GPB;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)sm_count * per_sm, want));
-  k<<<grid, SW_THREADS, smem, st>>>(ref, reads, tasks, ntasks_dev, cap, res, ml);
+  k<<<grid, SW_THREADS, smem, st>>>(ref, reads, tasks, ntasks_dev, cap, res, ml, work);
   CATT_CUDA(cudaGetLastError());
   return CATT_OK;
 }
 
 int dispatch_sw_bulk(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks, const uint32_t* ntasks_dev, int64_t cap, uint32_t* res,
-                     int sm_count, cudaStream_t st) {
+                     unsigned long long* work, int sm_count, cudaStream_t st) {
   const int n = ref.maxlen;
-  if (n <= 32) return launch_sw_bulk<4, 8>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
-  if (n <= 48) return launch_sw_bulk<4, 12>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
-  if (n <= 64) return launch_sw_bulk<8, 8>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
-  if (n <= 100) return launch_sw_bulk<4, 25>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
-  if (n <= 104) return launch_sw_bulk<8, 13>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
+  if (n <= 32) return launch_sw_bulk<4, 8>(ref, reads, tasks, ntasks_dev, cap, res, work, sm_count, st);
+  if (n <= 48) return launch_sw_bulk<4, 12>(ref, reads, tasks, ntasks_dev, cap, res, work, sm_count, st);
+  if (n <= 64) return launch_sw_bulk<8, 8>(ref, reads, tasks, ntasks_dev, cap, res, work, sm_count, st);
+  if (n <= 100) return launch_sw_bulk<4, 25>(ref, reads, tasks, ntasks_dev, cap, res, work, sm_count, st);
+  if (n <= 104) return launch_sw_bulk<8, 13>(ref, reads, tasks, ntasks_dev, cap, res, work, sm_count, st);
   // long records (IGHV, pig TRBV: 280-320 nt): few lanes with many columns keep the skew short (G - 1 idle steps per task);
   // 40 columns per lane cost 152 registers and 2 CTAs / SM, which the two-row kernel tolerates (IGH: 4485 -> 5077 GCUPS vs 16 x 20)
-  if (n <= 160) return launch_sw_bulk<4, 40>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
-  if (n <= 320) return launch_sw_bulk<8, 40>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
+  if (n <= 160) return launch_sw_bulk<4, 40>(ref, reads, tasks, ntasks_dev, cap, res, work, sm_count, st);
+  if (n <= 320) return launch_sw_bulk<8, 40>(ref, reads, tasks, ntasks_dev, cap, res, work, sm_count, st);
   set_error("record length %d exceeds the SW kernel's tiling", n);
   return CATT_E_LIMIT;
 }
 
 template <bool TRACK>
 int dispatch_sw(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks, const uint32_t* ntasks_dev, int64_t cap, uint32_t* res,
-                int sm_count, cudaStream_t st) {
+                unsigned long long* work, int sm_count, cudaStream_t st) {
   const int n = ref.maxlen;
-  if (n <= 32) return launch_sw_t<4, 8, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
-  if (n <= 48) return launch_sw_t<4, 12, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
-  if (n <= 64) return launch_sw_t<8, 8, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
-  if (n <= 100) return launch_sw_t<4, 25, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
-  if (n <= 104) return launch_sw_t<8, 13, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
-  if (n <= 160) return launch_sw_t<8, 20, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
-  if (n <= 320) return launch_sw_t<16, 20, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, sm_count, st);
+  if (n <= 32) return launch_sw_t<4, 8, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, work, sm_count, st);
+  if (n <= 48) return launch_sw_t<4, 12, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, work, sm_count, st);
+  if (n <= 64) return launch_sw_t<8, 8, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, work, sm_count, st);
+  if (n <= 100) return launch_sw_t<4, 25, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, work, sm_count, st);
+  if (n <= 104) return launch_sw_t<8, 13, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, work, sm_count, st);
+  if (n <= 160) return launch_sw_t<8, 20, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, work, sm_count, st);
+  if (n <= 320) return launch_sw_t<16, 20, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, work, sm_count, st);
   set_error("record length %d exceeds the SW kernel's tiling", n);
   return CATT_E_LIMIT;
 }
@@ -817,13 +829,13 @@ int launch_expand(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, cu
 
 int launch_sw(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int sm_count, cudaStream_t st, int* launches) {
   *launches += 1;
-  return dispatch_sw_bulk(ref, reads, ab.tasks, ab.task_off + reads.n, ab.cap_tasks, ab.task_score, sm_count, st);
+  return dispatch_sw_bulk(ref, reads, ab.tasks, ab.task_off + reads.n, ab.cap_tasks, ab.task_score, ab.counters + CTR_WORK_SW, sm_count, st);
 }
 
 // selection, the TRACK pass over the winners, CIGAR facts, traceback of the rare gapped winners
 // TRACK pass on the winners, CIGAR facts, traceback of the gapped ones: everything after the winner of every read is known
 static int launch_after_select(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, catt_aln* recs, int sm_count, cudaStream_t st, int* launches) {
-  int rc = dispatch_sw<true>(ref, reads, ab.wtasks, reinterpret_cast<const uint32_t*>(ab.counters + 7), reads.n, ab.wres, sm_count, st);
+  int rc = dispatch_sw<true>(ref, reads, ab.wtasks, reinterpret_cast<const uint32_t*>(ab.counters + 7), reads.n, ab.wres, ab.counters + CTR_WORK_TRACK, sm_count, st);
   if (rc) return rc;
   finish_kernel<<<(unsigned)((reads.n + 127) / 128), 128, 0, st>>>(ref, reads, ab.wtasks, ab.wres, recs, ab.gapped_list, ab.counters);
   CATT_CUDA(cudaGetLastError());
@@ -875,14 +887,14 @@ int launch_sw_pairs(const RefDev& ref, const ReadsDev& reads, const int32_t* d_r
   if (n == 0) return CATT_OK;
   SwTask* tasks = nullptr;
   uint32_t* res = nullptr;
-  uint32_t* d_n = nullptr;
+  uint32_t* d_n = nullptr;                       // [0] task count, [2..3] the kernel's work cursor
   CATT_CUDA(cudaMalloc(&tasks, n * sizeof(SwTask)));
   CATT_CUDA(cudaMalloc(&res, n * 2 * sizeof(uint32_t)));
-  CATT_CUDA(cudaMalloc(&d_n, sizeof(uint32_t)));
-  const uint32_t n32 = (uint32_t)n;
-  CATT_CUDA(cudaMemcpyAsync(d_n, &n32, sizeof n32, cudaMemcpyHostToDevice, st));
+  CATT_CUDA(cudaMalloc(&d_n, 4 * sizeof(uint32_t)));
+  const uint32_t n32[4] = {(uint32_t)n, 0, 0, 0};
+  CATT_CUDA(cudaMemcpyAsync(d_n, n32, sizeof n32, cudaMemcpyHostToDevice, st));
   make_pair_tasks<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, d_rid, d_strand, tasks);
-  int rc = dispatch_sw<true>(ref, reads, tasks, d_n, n, res, sm_count, st);
+  int rc = dispatch_sw<true>(ref, reads, tasks, d_n, n, res, reinterpret_cast<unsigned long long*>(d_n + 2), sm_count, st);
   if (rc == CATT_OK) {
     unpack_pair_res<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, res, d_out3);
     cudaError_t e = cudaStreamSynchronize(st);
