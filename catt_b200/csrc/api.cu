@@ -1351,6 +1351,8 @@ int catt_ctx_create(catt_ctx** out, const catt_config* cfg) {
   int rc;
   if ((rc = c->V.load(cfg->v_fasta)) || (rc = c->J.load(cfg->j_fasta))) return rc;
   if ((rc = c->V.upload()) || (rc = c->J.upload())) return rc;
+  // J sets (9-62 short records): a read has one or two J candidates, so each is scored once by the TRACK kernel (sw.cu: launch_sw)
+  c->J.dev.direct = getenv("CATT_NO_DIRECT") ? 0 : 1;
   const char* res[M_COUNT] = {cfg->cmotif, cfg->fmotif, cfg->inner_c, cfg->inner_f, "(CAS|CSA|CAW|CAT|CSV|CAI|CAR|CAG|CSG)",
                               "(QYF|QFF|AFF|LFF|YTF|QHF|LHF|IYF|LTF)"};     // Jtool.jl:288,294
   for (int i = 0; i < M_COUNT; i++) if ((rc = compile_motif(res[i], &c->finder.m[i]))) return rc;

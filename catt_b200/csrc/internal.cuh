@@ -82,6 +82,7 @@ struct RefDev {            // POD view handed to kernels
   const int32_t* rec_len;
   const uint16_t* canon;   // candidate (rid*2+strand) -> candidate of the first byte-identical record (same strand)
   int32_t L, nrec, maxlen, CW;
+  int32_t direct;          // 1: every candidate goes through the TRACK kernel once (score + end cell), no bulk pass (sw.cu: launch_sw)
 };
 
 struct RefSet {

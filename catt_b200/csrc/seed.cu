@@ -417,7 +417,7 @@ __device__ __forceinline__ void write_out(const RefDev& ref, const WarpScratch& 
     nf = __popc(b & 0x55555555u); nr = __popc(b & 0xAAAAAAAAu);
   }
   nf = warp_sum(nf); nr = warp_sum(nr);
-  if (lane == 0) ntask[r] = (nf + 1) / 2 + (nr + 1) / 2;
+  if (lane == 0) ntask[r] = ref.direct ? nf + nr : (nf + 1) / 2 + (nr + 1) / 2;
 }
 
 // GS = false: scratch in shared memory, all reads; overflowing reads are appended to `redo`.
@@ -429,6 +429,7 @@ __global__ void __launch_bounds__(SEED_WARPS * 32) seed_kernel(RefDev ref, Reads
                                                                uint32_t* __restrict__ gscratch, int t2_bytes_smem) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint64_t bar;
+  if (GS && counters[4] == 0) return;                     // no read overflowed the shared run list (the usual case): skip the text staging too
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ml = (reads.max_len + 31) & ~31;
   const size_t wbytes = (warp_scratch_bytes(ml) + 15) & ~(size_t)15;

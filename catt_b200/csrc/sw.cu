@@ -92,7 +92,8 @@ __global__ void expand_kernel(RefDev ref, int64_t n, const uint32_t* __restrict_
         const int bit = __ffs(b) - 1;
         b &= b - 1;
         const int c = w * 32 + bit;
-        if (pend < 0) pend = c;
+        if (ref.direct) tasks[o++] = SwTask{(uint32_t)r, (uint16_t)c, (uint16_t)0xFFFF};
+        else if (pend < 0) pend = c;
         else { tasks[o++] = SwTask{(uint32_t)r, (uint16_t)pend, (uint16_t)c}; pend = -1; }
       }
     }
@@ -491,6 +492,9 @@ template <bool TRACK>
 int dispatch_sw(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks, const uint32_t* ntasks_dev, int64_t cap, uint32_t* res,
                 unsigned long long* work, int sm_count, cudaStream_t st) {
   const int n = ref.maxlen;
+  static const int tile32 = getenv("CATT_TILE32") ? atoi(getenv("CATT_TILE32")) : 4;
+  if (n <= 32 && tile32 == 2) return launch_sw_t<2, 16, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, work, sm_count, st);
+  if (n <= 32 && tile32 == 1) return launch_sw_t<1, 32, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, work, sm_count, st);
   if (n <= 32) return launch_sw_t<4, 8, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, work, sm_count, st);
   if (n <= 48) return launch_sw_t<4, 12, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, work, sm_count, st);
   if (n <= 64) return launch_sw_t<8, 8, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, work, sm_count, st);
@@ -518,7 +522,7 @@ __global__ void select_kernel(RefDev ref, ReadsDev reads, const uint32_t* __rest
                               const uint32_t* __restrict__ task_off, const uint32_t* __restrict__ task_score, int64_t cap_tasks,
                               int64_t first_ordinal, int min_score, catt_aln* __restrict__ recs, SwTask* __restrict__ wtasks,
                               unsigned long long* __restrict__ counters, uint32_t* __restrict__ tied, int16_t* __restrict__ mxs,
-                              int16_t* __restrict__ ncands) {
+                              int16_t* __restrict__ ncands, uint32_t* __restrict__ wres) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long my_cand = 0, my_cells = 0, my_hit = 0, my_comp = 0;
   if (MODE == 2) {
@@ -563,14 +567,16 @@ __global__ void select_kernel(RefDev ref, ReadsDev reads, const uint32_t* __rest
     for (uint32_t t = t0; t < t1; t++) {
       const SwTask tk = tasks[t];
       const uint32_t sc = task_score[t];
-      mx = max(mx, (int)(sc & 0xffff));
       my_comp += (unsigned long long)m * ref.rec_len[tk.a >> 1];
+      if (ref.direct) { mx = max(mx, (int)(sc >> 20)); continue; }          // one candidate per task: its TRACK key (pack_key)
+      mx = max(mx, (int)(sc & 0xffff));
       if (tk.b != 0xFFFF) { mx = max(mx, (int)(sc >> 16)); my_comp += (unsigned long long)m * ref.rec_len[tk.b >> 1]; }
     }
     // candidates in T order (forward records ascending, then reverse-strand records descending): rank among the tied
     const uint64_t ord = (uint64_t)(first_ordinal + r);
     int ncand = 0, ntied = 0, win_c = -1;
     uint64_t win_h = ~0ull;
+    uint32_t win_key = 0;
     // expand_kernel emitted the tasks in bit order of the canonical bitmap, forward strand first, two candidates per task: the
     // score of canonical candidate cc sits in task t0 (+ forward tasks) + rank/2, half rank%2, rank = its position among the
     // canonical candidates of its strand - a popcount, not a search
@@ -582,7 +588,7 @@ __global__ void select_kernel(RefDev ref, ReadsDev reads, const uint32_t* __rest
       nfw += __popc(b & 0x55555555u); nrv += __popc(b & 0xAAAAAAAAu);
       if (MODE == 1) tied[r * ref.CW + w] = 0;
     }
-    const uint32_t rv_base = t0 + (nfw + 1) / 2;
+    const uint32_t rv_base = ref.direct ? t0 + nfw : t0 + (nfw + 1) / 2;
     auto consider = [&](int c) {
       ncand++;
       my_cells += (unsigned long long)m * ref.rec_len[c >> 1];
@@ -590,15 +596,15 @@ __global__ void select_kernel(RefDev ref, ReadsDev reads, const uint32_t* __rest
       const int st = cc & 1, w = cc >> 5;
       const uint32_t below = canonbits[r * ref.CW + w] & (st ? 0xAAAAAAAAu : 0x55555555u) & ((1u << (cc & 31)) - 1u);
       const uint32_t rank = pre[st][w] + __popc(below);
-      const uint32_t ts = task_score[(st ? rv_base : t0) + (rank >> 1)];
-      const int sc = (int)((rank & 1) ? ts >> 16 : ts & 0xffff);
+      const uint32_t ts = task_score[(st ? rv_base : t0) + (ref.direct ? rank : rank >> 1)];
+      const int sc = ref.direct ? (int)(ts >> 20) : (int)((rank & 1) ? ts >> 16 : ts & 0xffff);
       if (sc == mx) {
         if (MODE == 1) {
           tied[r * ref.CW + (c >> 5)] |= 1u << (c & 31);
         } else {
           const uint64_t h = hash_64(ord + (uint64_t)ntied);
           ntied++;
-          if (h < win_h) { win_h = h; win_c = c; }
+          if (h < win_h) { win_h = h; win_c = c; win_key = ts; }
         }
       }
     };
@@ -623,6 +629,7 @@ __global__ void select_kernel(RefDev ref, ReadsDev reads, const uint32_t* __rest
         my_hit = 1;
         const unsigned long long k = atomicAdd(&counters[7], 1ull);
         wtasks[k] = SwTask{(uint32_t)r, (uint16_t)win_c, (uint16_t)0xFFFF};
+        if (ref.direct) wres[k] = win_key;           // the winner's end cell is already known: no TRACK pass (launch_select)
       }
       recs[r] = a;
     }
@@ -829,13 +836,18 @@ int launch_expand(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, cu
 
 int launch_sw(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int sm_count, cudaStream_t st, int* launches) {
   *launches += 1;
+  // a reference set whose reads have one or two candidates each (the J sets) skips the bulk pass: its packed halves would be half
+  // empty and the winner would be scored a second time; every candidate goes through the TRACK kernel once, two reads per task
+  if (ref.direct) return dispatch_sw<true>(ref, reads, ab.tasks, ab.task_off + reads.n, ab.cap_tasks, ab.task_score, ab.counters + CTR_WORK_SW, sm_count, st);
   return dispatch_sw_bulk(ref, reads, ab.tasks, ab.task_off + reads.n, ab.cap_tasks, ab.task_score, ab.counters + CTR_WORK_SW, sm_count, st);
 }
 
 // selection, the TRACK pass over the winners, CIGAR facts, traceback of the rare gapped winners
 // TRACK pass on the winners, CIGAR facts, traceback of the gapped ones: everything after the winner of every read is known
-static int launch_after_select(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, catt_aln* recs, int sm_count, cudaStream_t st, int* launches) {
-  int rc = dispatch_sw<true>(ref, reads, ab.wtasks, reinterpret_cast<const uint32_t*>(ab.counters + 7), reads.n, ab.wres, ab.counters + CTR_WORK_TRACK, sm_count, st);
+static int launch_after_select(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, catt_aln* recs, bool track, int sm_count, cudaStream_t st,
+                               int* launches) {
+  int rc = track ? dispatch_sw<true>(ref, reads, ab.wtasks, reinterpret_cast<const uint32_t*>(ab.counters + 7), reads.n, ab.wres, ab.counters + CTR_WORK_TRACK, sm_count, st)
+                 : CATT_OK;
   if (rc) return rc;
   finish_kernel<<<(unsigned)((reads.n + 127) / 128), 128, 0, st>>>(ref, reads, ab.wtasks, ab.wres, recs, ab.gapped_list, ab.counters);
   CATT_CUDA(cudaGetLastError());
@@ -848,7 +860,7 @@ static int launch_after_select(const RefDev& ref, const ReadsDev& reads, AlignBu
   if ((rc = smem_optin(traceback_kernel, 220 * 1024, optin))) return rc;
   traceback_kernel<<<sm_count * 4, 32, smem, st>>>(ref, reads, ab.gapped_list, ab.counters, recs);
   CATT_CUDA(cudaGetLastError());
-  *launches += 3;
+  *launches += track ? 3 : 2;
   return CATT_OK;
 }
 
@@ -856,17 +868,17 @@ int launch_select(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, ca
                   int sm_count, cudaStream_t st, int* launches) {
   if (reads.n == 0) return CATT_OK;
   select_kernel<0><<<(unsigned)((reads.n + 127) / 128), 128, 0, st>>>(ref, reads, ab.candbits, ab.canonbits, ab.tasks, ab.task_off, ab.task_score,
-                                                                      ab.cap_tasks, first_ordinal, min_score, recs, ab.wtasks, ab.counters, nullptr, nullptr, nullptr);
+                                                                      ab.cap_tasks, first_ordinal, min_score, recs, ab.wtasks, ab.counters, nullptr, nullptr, nullptr, ab.wres);
   CATT_CUDA(cudaGetLastError());
   *launches += 1;
-  return launch_after_select(ref, reads, ab, recs, sm_count, st, launches);
+  return launch_after_select(ref, reads, ab, recs, !ref.direct, sm_count, st, launches);
 }
 
 // the selection split at the tie-break (select_kernel MODE 1 / 2): `tied` = reads.n x CW words, `mxs` / `ncands` = reads.n each
 int launch_select_pre(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, uint32_t* tied, int16_t* mxs, int16_t* ncands, cudaStream_t st, int* launches) {
   if (reads.n == 0) return CATT_OK;
   select_kernel<1><<<(unsigned)((reads.n + 127) / 128), 128, 0, st>>>(ref, reads, ab.candbits, ab.canonbits, ab.tasks, ab.task_off, ab.task_score,
-                                                                      ab.cap_tasks, 0, 0, nullptr, nullptr, ab.counters, tied, mxs, ncands);
+                                                                      ab.cap_tasks, 0, 0, nullptr, nullptr, ab.counters, tied, mxs, ncands, nullptr);
   CATT_CUDA(cudaGetLastError());
   *launches += 1;
   return CATT_OK;
@@ -875,10 +887,10 @@ int launch_select_post(const RefDev& ref, const ReadsDev& reads, AlignBuffers& a
                        int64_t first_ordinal, int min_score, int sm_count, cudaStream_t st, int* launches) {
   if (reads.n == 0) return CATT_OK;
   select_kernel<2><<<(unsigned)((reads.n + 127) / 128), 128, 0, st>>>(ref, reads, nullptr, nullptr, nullptr, nullptr, nullptr, 0, first_ordinal, min_score,
-                                                                      recs, ab.wtasks, ab.counters, tied, mxs, ncands);
+                                                                      recs, ab.wtasks, ab.counters, tied, mxs, ncands, nullptr);
   CATT_CUDA(cudaGetLastError());
   *launches += 1;
-  return launch_after_select(ref, reads, ab, recs, sm_count, st, launches);
+  return launch_after_select(ref, reads, ab, recs, true, sm_count, st, launches);     // the front half's keys are gone: TRACK pass on the winners
 }
 
 int launch_sw_pairs(const RefDev& ref, const ReadsDev& reads, const int32_t* d_rid, const int32_t* d_strand, int32_t* d_out3,
