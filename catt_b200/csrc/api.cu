@@ -43,7 +43,7 @@ int ensure_align_buffers(AlignBuffers& ab, const RefDev& ref, int64_t n) {
   if (!ab.counters) CATT_CUDA(cudaMalloc(&ab.counters, N_COUNTERS * sizeof(unsigned long long)));
   if (n <= ab.cap_reads) return CATT_OK;
   cudaFree(ab.candbits); cudaFree(ab.canonbits); cudaFree(ab.ntask); cudaFree(ab.task_off); cudaFree(ab.gapped_list);
-  cudaFree(ab.wtasks); cudaFree(ab.wres);
+  cudaFree(ab.wtasks); cudaFree(ab.wres); cudaFree(ab.worder); cudaFree(ab.whist);
   ab.cap_reads = n + n / 8 + 64;
   CATT_CUDA(cudaMalloc(&ab.candbits, ab.cap_reads * ref.CW * sizeof(uint32_t)));
   CATT_CUDA(cudaMalloc(&ab.canonbits, ab.cap_reads * ref.CW * sizeof(uint32_t)));
@@ -52,12 +52,14 @@ int ensure_align_buffers(AlignBuffers& ab, const RefDev& ref, int64_t n) {
   CATT_CUDA(cudaMalloc(&ab.gapped_list, ab.cap_reads * sizeof(uint32_t)));
   CATT_CUDA(cudaMalloc(&ab.wtasks, ab.cap_reads * sizeof(SwTask)));
   CATT_CUDA(cudaMalloc(&ab.wres, ab.cap_reads * 2 * sizeof(uint32_t)));
+  CATT_CUDA(cudaMalloc(&ab.worder, (ab.cap_reads + MAX_REC + 2) * sizeof(uint32_t)));
+  CATT_CUDA(cudaMalloc(&ab.whist, (2 * MAX_REC + 4) * sizeof(uint32_t)));
   return CATT_OK;
 }
 
 void free_align_buffers(AlignBuffers& ab) {
   cudaFree(ab.candbits); cudaFree(ab.canonbits); cudaFree(ab.ntask); cudaFree(ab.task_off); cudaFree(ab.tasks); cudaFree(ab.task_score);
-  cudaFree(ab.gapped_list); cudaFree(ab.wtasks); cudaFree(ab.wres); cudaFree(ab.counters); cudaFree(ab.cub_tmp);
+  cudaFree(ab.gapped_list); cudaFree(ab.wtasks); cudaFree(ab.wres); cudaFree(ab.worder); cudaFree(ab.whist); cudaFree(ab.counters); cudaFree(ab.cub_tmp);
   cudaFree(ab.seed_scratch);
   ab = AlignBuffers{};
 }

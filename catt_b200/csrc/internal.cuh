@@ -160,6 +160,8 @@ struct AlignBuffers {       // per reference set, sized for one batch
   uint32_t* task_score = nullptr;  // per task: scoreA | scoreB << 16
   SwTask* wtasks = nullptr;        // n: the winning candidate of every mapped read (compacted), input of the TRACK pass
   uint32_t* wres = nullptr;        // 2 per winner: score<<20 | (1023-ei)<<10 | (1023-ej)
+  uint32_t* worder = nullptr;      // n + MAX_REC + 2: winner indices grouped by record, bins padded to even sizes (sw.cu: dispatch_track2)
+  uint32_t* whist = nullptr;       // MAX_REC counts, MAX_REC cursors, slot count
   uint32_t* gapped_list = nullptr; // read indices whose winner needs the traceback kernel
   unsigned long long* counters = nullptr;  // [0] cand, [1] cells, [2] n_gapped, [3] hits, [4] seed redo, [6] seed overflow,
                                            // [7] winners, [8] cells computed (canonical records), [9] task-buffer overflow

@@ -488,6 +488,272 @@ int dispatch_sw_bulk(const RefDev& ref, const ReadsDev& reads, const SwTask* tas
   return CATT_E_LIMIT;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// TRACK pass, profile version: the end cell of every winner whose score is already known (bulk pass + selection).
+// The winners are grouped by record first (counting sort, bins padded to even sizes), so a task = two reads against the SAME
+// record and the G lanes keep ONE record profile in shared memory - prof[q][column] = +1 / -2 as a 32-bit integer, rebuilt
+// only when the group moves on to the next record (a bin holds thousands of winners).  Each half looks its own read base up:
+//   t = H(i-1,j-1) + prof[q_lo][j] + (prof[q_hi][j] << 16)
+// (the sign-extended low score borrows from nothing above bit 15 because the biased H is >= 2: the same carry argument as
+// sw_row, resolved by integer multiply-add on the FMA pipe).  Two read rows per step like sw_bulk2_kernel.  Since the maximum S is
+// known, "the first cell reaching the maximum" is the first cell that EQUALS S: one packed compare per row; the column search
+// runs once per read and lane.  out[k] = pack_key(S, i, j) of winner k - what finish_kernel reads.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr uint32_t NO_WINNER = 0xFFFFFFFFu;
+
+__global__ void whist_kernel(int64_t n, const SwTask* __restrict__ wtasks, const unsigned long long* __restrict__ counters, uint32_t* __restrict__ hist) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = k < n && k < (int64_t)counters[7];
+  const unsigned act = __ballot_sync(FULL, live);
+  if (!live) return;
+  const int bin = wtasks[k].a >> 1;
+  const unsigned peers = __match_any_sync(act, bin);
+  if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], (uint32_t)__popc(peers));
+}
+
+// one block: bins -> even-padded offsets; cursor[bin] = first slot, the odd bins' last slot is marked empty, *nslots = total
+__global__ void wscan_kernel(int nrec, const uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor, uint32_t* __restrict__ order,
+                             uint32_t* __restrict__ nslots) {
+  __shared__ uint32_t sh[MAX_REC + 1];
+  const int b = threadIdx.x;
+  const uint32_t c = b < nrec ? hist[b] : 0u;
+  sh[b] = (c + 1u) & ~1u;
+  __syncthreads();
+  if (b == 0) { uint32_t run = 0; for (int i = 0; i < nrec; i++) { const uint32_t v = sh[i]; sh[i] = run; run += v; } sh[nrec] = run; }
+  __syncthreads();
+  if (b < nrec) { cursor[b] = sh[b]; if (c & 1u) order[sh[b] + c] = NO_WINNER; }
+  if (b == 0) *nslots = sh[nrec];
+}
+
+__global__ void wscatter_kernel(int64_t n, const SwTask* __restrict__ wtasks, const unsigned long long* __restrict__ counters, uint32_t* __restrict__ cursor,
+                                uint32_t* __restrict__ order) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = k < n && k < (int64_t)counters[7];
+  const unsigned act = __ballot_sync(FULL, live);
+  if (!live) return;
+  const int bin = wtasks[k].a >> 1, lane = threadIdx.x & 31;
+  const unsigned peers = __match_any_sync(act, bin);
+  const int leader = __ffs(peers) - 1;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(&cursor[bin], (uint32_t)__popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  order[base + __popc(peers & ((1u << lane) - 1u))] = (uint32_t)k;
+}
+
+template <int G, int C>
+__global__ void __launch_bounds__(SW_THREADS) sw_track2_kernel(RefDev ref, ReadsDev reads, const SwTask* __restrict__ wtasks,
+                                                               const uint32_t* __restrict__ order, const uint32_t* __restrict__ nslots_dev,
+                                                               uint32_t* __restrict__ out, int ml, unsigned long long* __restrict__ work) {
+  constexpr int GPW = 32 / G;
+  constexpr int GPB = GPW * (SW_THREADS / 32);
+  constexpr int CH = (C + 3) / 4;
+  constexpr int ROWW = G * CH * 4;
+  constexpr int PROFW = 5 * ROWW;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int64_t ntasks = (int64_t)(*nslots_dev >> 1);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane % G, grp = lane / G;
+  const int slot = warp * GPW + grp;
+  int32_t* prof = reinterpret_cast<int32_t*>(smem_raw) + (size_t)slot * PROFW;
+  uint16_t* qarr = reinterpret_cast<uint16_t*>(smem_raw + (size_t)GPB * PROFW * 4 + (size_t)slot * ml);   // ml bytes: 4 x 3-bit read codes per row pair
+  const uint32_t prof_base = smem_u32(prof) + (uint32_t)g * 16u;
+  const uint8_t* __restrict__ Tb = ref.Tb;
+  const uint32_t neg7 = NEG7 ^ (uint32_t)((unsigned long long)ml >> 30);        // == NEG7, opaque to constant propagation
+  int cur_rid = -1;
+
+  for (;;) {
+    const int64_t base = next_tasks(work, GPW, lane);
+    if (base >= ntasks) break;
+    const int64_t t = base + grp;
+    const bool live = t < ntasks;
+    int m = 0;
+    uint32_t ka = NO_WINNER, kb = NO_WINNER, tgt = 0x7FFF7FFFu;
+    if (live) {
+      ka = order[2 * t]; kb = order[2 * t + 1];
+      const SwTask ta = wtasks[ka];
+      const SwTask tb = kb != NO_WINNER ? wtasks[kb] : ta;
+      const int rid = ta.a >> 1;
+      if (rid != cur_rid) {                                 // the group's record profile (rare: winners are grouped by record)
+        cur_rid = rid;
+        const int oa = ref.rec_off[rid], la = ref.rec_len[rid];
+        #pragma unroll
+        for (int c = 0; c < C; c++) {
+          const int j = g * C + c;
+          const int ba = j < la ? (int)Tb[oa + j] : 7;
+          int32_t* dst = prof + ((c >> 2) * G + g) * 4 + (c & 3);
+          #pragma unroll
+          for (int q = 0; q < 4; q++) dst[q * ROWW] = q == ba ? 1 : -2;
+          dst[4 * ROWW] = -1;
+        }
+      }
+      const int ma = reads.len[ta.read], mb = kb != NO_WINNER ? reads.len[tb.read] : 0;
+      m = max(ma, mb);
+      const uint32_t* __restrict__ wa = reads.words + reads.off[ta.read];
+      const uint32_t* __restrict__ na = wa + read_base_words(ma);
+      const uint32_t* __restrict__ wb = reads.words + reads.off[tb.read];
+      const uint32_t* __restrict__ nb = wb + read_base_words(reads.len[tb.read]);
+      const int sa = ta.a & 1, sb = tb.a & 1;
+      const int rows2 = (m + 1) >> 1;
+      for (int i2 = g; i2 < rows2; i2 += G) {                // rows past a read's end score -1 everywhere (they cannot reach S)
+        const int i = 2 * i2;
+        const uint32_t a0 = i < ma ? read_code(wa, na, ma, i, sa) : 4u, a1 = i + 1 < ma ? read_code(wa, na, ma, i + 1, sa) : 4u;
+        const uint32_t b0 = i < mb ? read_code(wb, nb, mb, i, sb) : 4u, b1 = i + 1 < mb ? read_code(wb, nb, mb, i + 1, sb) : 4u;
+        qarr[i2] = (uint16_t)(a0 | (a1 << 3) | (b0 << 6) | (b1 << 9));
+      }
+      tgt = ((uint32_t)ta.b + 2u) | ((kb != NO_WINNER ? (uint32_t)tb.b + 2u : 0x7FFFu) << 16);
+    }
+    __syncwarp();
+    const int rows2 = (m + 1) >> 1;
+    int steps = live ? rows2 + G - 1 : 0;
+    #pragma unroll
+    for (int d = 16; d; d >>= 1) steps = max(steps, __shfl_xor_sync(FULL, steps, d));
+
+    uint32_t Hp[C], E[C];
+    #pragma unroll
+    for (int c = 0; c < C; c++) { Hp[c] = TWO2; E[c] = TWO2; }
+    uint32_t lastH0 = TWO2, lastH1 = TWO2, lastF0 = TWO2, lastF1 = TWO2, diag_in = TWO2;
+    uint32_t key_lo = 0, key_hi = 0;                        // (1023 - i) << 10 | (1023 - j) of this lane's first cell equal to S
+    const uint32_t q_base = smem_u32(qarr);
+    for (int st = 0; st < steps; st++) {
+      uint32_t inH0 = __shfl_up_sync(FULL, lastH0, 1, G);
+      uint32_t inH1 = __shfl_up_sync(FULL, lastH1, 1, G);
+      uint32_t inF0 = __shfl_up_sync(FULL, lastF0, 1, G);
+      uint32_t inF1 = __shfl_up_sync(FULL, lastF1, 1, G);
+      if (g == 0) { inH0 = TWO2; inH1 = TWO2; inF0 = TWO2; inF1 = TWO2; }
+      const int i2 = st - g;
+      if (i2 >= 0 && i2 < rows2) {
+        uint32_t qq;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(qq) : "r"(q_base + 2u * (uint32_t)i2));
+        const uint32_t r0l = prof_base + (qq & 7u) * (uint32_t)(ROWW * 4), r1l = prof_base + ((qq >> 3) & 7u) * (uint32_t)(ROWW * 4);
+        const uint32_t r0h = prof_base + ((qq >> 6) & 7u) * (uint32_t)(ROWW * 4), r1h = prof_base + (qq >> 9) * (uint32_t)(ROWW * 4);
+        uint32_t hd0 = diag_in, f0 = inF0;
+        uint32_t hd1 = inH0, f1 = inF1;
+        diag_in = inH1;
+        uint32_t h0v[C];
+        uint32_t rb0 = TWO2, rb1 = TWO2;
+        #pragma unroll
+        for (int ch = 0; ch < CH; ch++) {
+          int32_t l0[4], l1[4], u0[4], u1[4];
+          asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(l0[0]), "=r"(l0[1]), "=r"(l0[2]), "=r"(l0[3]) : "r"(r0l + (uint32_t)(ch * G * 16)));
+          asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(u0[0]), "=r"(u0[1]), "=r"(u0[2]), "=r"(u0[3]) : "r"(r0h + (uint32_t)(ch * G * 16)));
+          asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(l1[0]), "=r"(l1[1]), "=r"(l1[2]), "=r"(l1[3]) : "r"(r1l + (uint32_t)(ch * G * 16)));
+          asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(u1[0]), "=r"(u1[1]), "=r"(u1[2]), "=r"(u1[3]) : "r"(r1h + (uint32_t)(ch * G * 16)));
+          #pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int c = 4 * ch + k;
+            if (c < C) {
+              const uint32_t t0 = (uint32_t)(u0[k] * 65536 + (int32_t)(hd0 + (uint32_t)l0[k]));
+              const uint32_t h0 = __vimax3_s16x2(t0, E[c], f0);
+              hd0 = Hp[c];
+              const uint32_t hm0 = __viaddmax_s16x2(h0, neg7, TWO2);
+              const uint32_t e0 = __viaddmax_s16x2(E[c], NEG1, hm0);
+              f0 = __viaddmax_s16x2(f0, NEG1, hm0);
+              const uint32_t t1 = (uint32_t)(u1[k] * 65536 + (int32_t)(hd1 + (uint32_t)l1[k]));
+              const uint32_t h1 = __vimax3_s16x2(t1, e0, f1);
+              hd1 = h0;
+              const uint32_t hm1 = __viaddmax_s16x2(h1, neg7, TWO2);
+              E[c] = __viaddmax_s16x2(e0, NEG1, hm1);
+              f1 = __viaddmax_s16x2(f1, NEG1, hm1);
+              Hp[c] = h1;
+              h0v[c] = h0;
+              if (c & 1) { rb0 = __vimax3_s16x2(rb0, h0v[c - 1], h0); rb1 = __vimax3_s16x2(rb1, Hp[c - 1], h1); }
+              else if (c == C - 1) { rb0 = __vimax3_s16x2(rb0, h0, h0); rb1 = __vimax3_s16x2(rb1, h1, h1); }
+            }
+          }
+        }
+        lastH0 = h0v[C - 1]; lastH1 = Hp[C - 1];
+        lastF0 = f0; lastF1 = f1;
+        // first cell equal to the known maximum, per half (row 2*i2 before row 2*i2+1; within a row the lowest column)
+        const uint32_t d0 = tgt - rb0;                      // per half >= 0 (S is the maximum), no borrow between the halves
+        if ((d0 & 0xffffu) == 0u || d0 < 0x10000u) {
+          if ((d0 & 0xffffu) == 0u) {
+            int jj = 0;
+            #pragma unroll
+            for (int c = C - 1; c >= 0; c--) if ((h0v[c] & 0xffffu) == (tgt & 0xffffu)) jj = c;
+            key_lo = ((uint32_t)(1023 - 2 * i2) << 10) | (uint32_t)(1023 - (g * C + jj));
+            tgt |= 0x7FFFu;
+          }
+          if (d0 < 0x10000u) {
+            int jj = 0;
+            #pragma unroll
+            for (int c = C - 1; c >= 0; c--) if ((h0v[c] >> 16) == (tgt >> 16)) jj = c;
+            key_hi = ((uint32_t)(1023 - 2 * i2) << 10) | (uint32_t)(1023 - (g * C + jj));
+            tgt |= 0x7FFF0000u;
+          }
+        }
+        const uint32_t d1 = tgt - rb1;
+        if ((d1 & 0xffffu) == 0u || d1 < 0x10000u) {
+          if ((d1 & 0xffffu) == 0u) {
+            int jj = 0;
+            #pragma unroll
+            for (int c = C - 1; c >= 0; c--) if ((Hp[c] & 0xffffu) == (tgt & 0xffffu)) jj = c;
+            key_lo = ((uint32_t)(1023 - (2 * i2 + 1)) << 10) | (uint32_t)(1023 - (g * C + jj));
+            tgt |= 0x7FFFu;
+          }
+          if (d1 < 0x10000u) {
+            int jj = 0;
+            #pragma unroll
+            for (int c = C - 1; c >= 0; c--) if ((Hp[c] >> 16) == (tgt >> 16)) jj = c;
+            key_hi = ((uint32_t)(1023 - (2 * i2 + 1)) << 10) | (uint32_t)(1023 - (g * C + jj));
+            tgt |= 0x7FFF0000u;
+          }
+        }
+      }
+    }
+    #pragma unroll
+    for (int d = G / 2; d; d >>= 1) {
+      key_lo = max(key_lo, __shfl_xor_sync(FULL, key_lo, d, G));
+      key_hi = max(key_hi, __shfl_xor_sync(FULL, key_hi, d, G));
+    }
+    if (live && g == 0) {
+      out[ka] = ((uint32_t)wtasks[ka].b << 20) | key_lo;
+      if (kb != NO_WINNER) out[kb] = ((uint32_t)wtasks[kb].b << 20) | key_hi;
+    }
+    __syncwarp();
+  }
+}
+
+template <int G, int C>
+int launch_sw_track2(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int sm_count, cudaStream_t st) {
+  constexpr int GPB = (32 / G) * (SW_THREADS / 32);
+  constexpr int PROFW = 5 * G * ((C + 3) / 4) * 4;
+  const int ml = (reads.max_len + 1 + 15) & ~15;                 // qarr bytes per task: one u16 per row pair
+  const size_t smem = (size_t)GPB * (PROFW * 4 + ml);
+  auto k = sw_track2_kernel<G, C>;
+  static std::atomic<unsigned long long> optin{0};
+  int per_sm = 0;
+  { const int rc = smem_optin(k, 200 * 1024, optin); if (rc) return rc; }
+  CATT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, SW_THREADS, smem));
+  if (per_sm < 1) per_sm = 1;
+  const int64_t want = ((reads.n + ref.nrec) / 2 + GPB) / GPB;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)sm_count * per_sm, want));
+  k<<<grid, SW_THREADS, smem, st>>>(ref, reads, ab.wtasks, ab.worder, ab.whist + 2 * MAX_REC, ab.wres, ml, ab.counters + CTR_WORK_TRACK);
+  CATT_CUDA(cudaGetLastError());
+  return CATT_OK;
+}
+
+// end cells of the winners in ab.wtasks (scores in SwTask::b): grouping by record + the profile TRACK kernel
+int dispatch_track2(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int sm_count, cudaStream_t st, int* launches) {
+  const int64_t n = reads.n;
+  uint32_t* hist = ab.whist;                       // [MAX_REC] counts, [MAX_REC] cursors, [1] slots
+  CATT_CUDA(cudaMemsetAsync(hist, 0, MAX_REC * sizeof(uint32_t), st));
+  whist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, ab.wtasks, ab.counters, hist);
+  wscan_kernel<<<1, MAX_REC, 0, st>>>(ref.nrec, hist, hist + MAX_REC, ab.worder, hist + 2 * MAX_REC);
+  wscatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, ab.wtasks, ab.counters, hist + MAX_REC, ab.worder);
+  CATT_CUDA(cudaGetLastError());
+  *launches += 4;
+  const int len = ref.maxlen;
+  if (len <= 32) return launch_sw_track2<4, 8>(ref, reads, ab, sm_count, st);
+  if (len <= 48) return launch_sw_track2<4, 12>(ref, reads, ab, sm_count, st);
+  if (len <= 64) return launch_sw_track2<8, 8>(ref, reads, ab, sm_count, st);
+  if (len <= 100) return launch_sw_track2<4, 25>(ref, reads, ab, sm_count, st);
+  if (len <= 104) return launch_sw_track2<8, 13>(ref, reads, ab, sm_count, st);
+  if (len <= 160) return launch_sw_track2<8, 20>(ref, reads, ab, sm_count, st);
+  if (len <= 320) return launch_sw_track2<16, 20>(ref, reads, ab, sm_count, st);
+  set_error("record length %d exceeds the SW kernel's tiling", len);
+  return CATT_E_LIMIT;
+}
+
 template <bool TRACK>
 int dispatch_sw(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks, const uint32_t* ntasks_dev, int64_t cap, uint32_t* res,
                 unsigned long long* work, int sm_count, cudaStream_t st) {
@@ -552,7 +818,7 @@ __global__ void select_kernel(RefDev ref, ReadsDev reads, const uint32_t* __rest
         a.rid = win_c >> 1; a.strand = (int16_t)(win_c & 1); a.mapped = 1; a.ntied = (int16_t)ntied;
         my_hit = 1;
         const unsigned long long k = atomicAdd(&counters[7], 1ull);
-        wtasks[k] = SwTask{(uint32_t)r, (uint16_t)win_c, (uint16_t)0xFFFF};
+        wtasks[k] = SwTask{(uint32_t)r, (uint16_t)win_c, (uint16_t)mx};
       }
       recs[r] = a;
     }
@@ -628,7 +894,7 @@ __global__ void select_kernel(RefDev ref, ReadsDev reads, const uint32_t* __rest
         a.rid = win_c >> 1; a.strand = (int16_t)(win_c & 1); a.mapped = 1; a.ntied = (int16_t)ntied;
         my_hit = 1;
         const unsigned long long k = atomicAdd(&counters[7], 1ull);
-        wtasks[k] = SwTask{(uint32_t)r, (uint16_t)win_c, (uint16_t)0xFFFF};
+        wtasks[k] = SwTask{(uint32_t)r, (uint16_t)win_c, (uint16_t)mx};      // b = the winner's score (dispatch_track2)
         if (ref.direct) wres[k] = win_key;           // the winner's end cell is already known: no TRACK pass (launch_select)
       }
       recs[r] = a;
@@ -792,6 +1058,10 @@ __global__ void make_pair_tasks(int64_t n, const int32_t* rid, const int32_t* st
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) tasks[i] = SwTask{(uint32_t)i, (uint16_t)(rid[i] * 2 + (strand[i] & 1)), (uint16_t)0xFFFF};
 }
+__global__ void pair_scores_kernel(int64_t n, const uint32_t* res, SwTask* tasks) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) tasks[i].b = (uint16_t)(res[i] >> 20);
+}
 __global__ void unpack_pair_res(int64_t n, const uint32_t* res, int32_t* out3) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
@@ -846,8 +1116,12 @@ int launch_sw(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int sm
 // TRACK pass on the winners, CIGAR facts, traceback of the gapped ones: everything after the winner of every read is known
 static int launch_after_select(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, catt_aln* recs, bool track, int sm_count, cudaStream_t st,
                                int* launches) {
-  int rc = track ? dispatch_sw<true>(ref, reads, ab.wtasks, reinterpret_cast<const uint32_t*>(ab.counters + 7), reads.n, ab.wres, ab.counters + CTR_WORK_TRACK, sm_count, st)
-                 : CATT_OK;
+  static const bool old_track = getenv("CATT_OLD_TRACK") != nullptr;       // A/B switch: the PRMT kernel on unsorted winners
+  int rc = CATT_OK;
+  if (track && old_track)
+    rc = dispatch_sw<true>(ref, reads, ab.wtasks, reinterpret_cast<const uint32_t*>(ab.counters + 7), reads.n, ab.wres, ab.counters + CTR_WORK_TRACK, sm_count, st);
+  else if (track)
+    rc = dispatch_track2(ref, reads, ab, sm_count, st, launches);
   if (rc) return rc;
   finish_kernel<<<(unsigned)((reads.n + 127) / 128), 128, 0, st>>>(ref, reads, ab.wtasks, ab.wres, recs, ab.gapped_list, ab.counters);
   CATT_CUDA(cudaGetLastError());
@@ -907,12 +1181,31 @@ int launch_sw_pairs(const RefDev& ref, const ReadsDev& reads, const int32_t* d_r
   CATT_CUDA(cudaMemcpyAsync(d_n, n32, sizeof n32, cudaMemcpyHostToDevice, st));
   make_pair_tasks<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, d_rid, d_strand, tasks);
   int rc = dispatch_sw<true>(ref, reads, tasks, d_n, n, res, reinterpret_cast<unsigned long long*>(d_n + 2), sm_count, st);
+  // the scores are known now: the same pairs through the grouped profile kernel (what Stage A runs on the V winners); its end
+  // cells are the ones returned
+  AlignBuffers ab2;
+  if (rc == CATT_OK && !getenv("CATT_OLD_TRACK")) {
+    unsigned long long hc[N_COUNTERS] = {0};
+    hc[7] = (unsigned long long)n;
+    int launches = 0;
+    if (cudaMalloc(&ab2.counters, sizeof hc) != cudaSuccess || cudaMalloc(&ab2.worder, (n + MAX_REC + 2) * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc(&ab2.whist, (2 * MAX_REC + 4) * sizeof(uint32_t)) != cudaSuccess || cudaMalloc(&ab2.wres, n * sizeof(uint32_t)) != cudaSuccess) {
+      set_error("sw_pairs: out of device memory"); rc = CATT_E_CUDA;
+    } else {
+      cudaMemcpyAsync(ab2.counters, hc, sizeof hc, cudaMemcpyHostToDevice, st);
+      pair_scores_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, res, tasks);
+      ab2.wtasks = tasks;
+      rc = dispatch_track2(ref, reads, ab2, sm_count, st, &launches);
+      if (rc == CATT_OK) cudaMemcpyAsync(res, ab2.wres, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st);
+    }
+  }
   if (rc == CATT_OK) {
     unpack_pair_res<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, res, d_out3);
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) rc = cuda_fail(e, "sw_pairs", __FILE__, __LINE__);
   }
   cudaFree(tasks); cudaFree(res); cudaFree(d_n);
+  cudaFree(ab2.counters); cudaFree(ab2.worder); cudaFree(ab2.whist); cudaFree(ab2.wres);
   return rc;
 }
 
