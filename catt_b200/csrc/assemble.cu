@@ -806,11 +806,9 @@ int stage_b(catt_ctx* c, int64_t n, const NamesDev& names, const ReadsDev& reads
   if (run_pool) {
     const uint64_t slots = std::max<uint64_t>(1024, (uint64_t)M * 11ull * 2ull);
     KmerTable tab{};
-    if ((rc = ensure(c, SB_TAB_KEYS, (int64_t)slots, &tab.keys)) || (rc = ensure(c, SB_TAB_VALS, (int64_t)slots, &tab.vals)) ||
-        (rc = ensure(c, SB_XOUT, n_partial, &xout))) return rc;
+    if ((rc = ensure(c, SB_TAB_KEYS, (int64_t)slots, &tab.slots)) || (rc = ensure(c, SB_XOUT, n_partial, &xout))) return rc;
     tab.sub_slots = slots; tab.nsub = 1;
-    CATT_CUDA(cudaMemsetAsync(tab.keys, 0xff, slots * sizeof(unsigned long long), st));
-    CATT_CUDA(cudaMemsetAsync(tab.vals, 0, slots * sizeof(unsigned long long), st));
+    CATT_CUDA(cudaMemsetAsync(tab.slots, 0xff, slots * sizeof(ulonglong2), st));
     CATT_CUDA(cudaEventRecord(c->ev[0], st));
     if ((rc = launch_pool(reads, pitems, M, k, tab, c->sm_count, st, launches))) return rc;
     CATT_CUDA(cudaEventRecord(c->ev[1], st));
@@ -1337,10 +1335,9 @@ int stage_b_sharded(catt_ctx* c, const ShardIn& in, const NamesDev& names, const
     tab.sub_slots = std::max<uint64_t>(1024, ((uint64_t)M * 11ull * 3ull / 2ull + N - 1) / N);
     const uint64_t slots = tab.sub_slots * (uint64_t)N;
     unsigned long long* cursor; PoolEntry *sendb, *recvb;
-    if ((rc = ensure(c, SB_TAB_KEYS, (int64_t)slots, &tab.keys)) || (rc = ensure(c, SB_TAB_VALS, (int64_t)slots, &tab.vals)) ||
+    if ((rc = ensure(c, SB_TAB_KEYS, (int64_t)slots, &tab.slots)) ||
         (rc = ensure(c, SB_XOUT, n_partial, &xout)) || (rc = ensure_sh(c, SH_CURSOR, 2 * N, &cursor)) || (rc = ensure_sh(c, SH_SEND, ml * 11, &sendb))) return rc;
-    CATT_CUDA(cudaMemsetAsync(tab.keys + (uint64_t)me * tab.sub_slots, 0xff, tab.sub_slots * sizeof(unsigned long long), st));
-    CATT_CUDA(cudaMemsetAsync(tab.vals + (uint64_t)me * tab.sub_slots, 0, tab.sub_slots * sizeof(unsigned long long), st));
+    CATT_CUDA(cudaMemsetAsync(tab.slots + (uint64_t)me * tab.sub_slots, 0xff, tab.sub_slots * sizeof(ulonglong2), st));
     CATT_CUDA(cudaMemsetAsync(cursor, 0, (size_t)2 * N * sizeof(unsigned long long), st));
     CATT_CUDA(cudaEventRecord(c->ev[0], st));
     if ((rc = launch_pool_emit(reads, pitems, ml, k, tab, 0, cursor, nullptr, c->sm_count, st, launches))) return rc;
@@ -1364,11 +1361,10 @@ int stage_b_sharded(catt_ctx* c, const ShardIn& in, const NamesDev& names, const
     CATT_CUDA(cudaEventRecord(c->ev[3], st));
     comm_bytes(CATT_COLL_KMER_A2A);
     if ((rc = launch_pool_insert(recvb, (int64_t)(rtot / sizeof(PoolEntry)), tab, c->sm_count, st, launches))) return rc;
-    std::vector<size_t> gc(N, (size_t)tab.sub_slots * 8), gd(N);
-    for (int r = 0; r < N; r++) gd[r] = (size_t)r * tab.sub_slots * 8;
+    std::vector<size_t> gc(N, (size_t)tab.sub_slots * sizeof(ulonglong2)), gd(N);
+    for (int r = 0; r < N; r++) gd[r] = (size_t)r * tab.sub_slots * sizeof(ulonglong2);
     CATT_CUDA(cudaEventRecord(c->ev[4], st));
-    if ((rc = comm->allgatherv(tab.keys + (uint64_t)me * tab.sub_slots, tab.keys, gc.data(), gd.data(), st)) ||
-        (rc = comm->allgatherv(tab.vals + (uint64_t)me * tab.sub_slots, tab.vals, gc.data(), gd.data(), st))) return rc;
+    if ((rc = comm->allgatherv(tab.slots + (uint64_t)me * tab.sub_slots, tab.slots, gc.data(), gd.data(), st))) return rc;
     CATT_CUDA(cudaEventRecord(c->ev[1], st));
     comm_bytes(CATT_COLL_KMER_TABLE);
     if ((rc = launch_extend(reads, c->d_finder, pitems, partial_idx, n_partial, k, tab, xout, reinterpret_cast<uint32_t*>(cnt + C_RESCUED), c->sm_count, st, launches))) return rc;

@@ -234,7 +234,9 @@ struct OutDesc {           // everything the host needs to materialise one Myrea
   int32_t pad_;
 };
 // open addressing, `nsub` sub-tables of `sub_slots` slots back to back (one GPU: nsub == 1); see pool.cu for the addressing
-struct KmerTable { unsigned long long* keys; unsigned long long* vals; uint64_t sub_slots; uint32_t nsub; };
+// slot = {key, ~value}: one 16-byte word, so a lookup touches one 32-byte sector and an insert's CAS + update hit the same one.
+// The value is stored inverted (an all-ones memset is the empty table: key = EMPTY, value = 0) and raised with atomicMin.
+struct KmerTable { ulonglong2* slots; uint64_t sub_slots; uint32_t nsub; };
 struct PoolEntry { unsigned long long key, val; };    // one (k-mer, order << 8 | position) pair on its way to the GPU that owns the key
 constexpr int KMER_MAX = 31;                            // one 2-bit packed u64 per k-mer, ~0 = empty slot
 int launch_pool(const ReadsDev& reads, const PoolItem* d_items, int64_t n, int kmer, KmerTable tab, int sm_count, cudaStream_t st, int* launches);

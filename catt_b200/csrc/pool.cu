@@ -39,8 +39,9 @@ __device__ __forceinline__ void table_put_h(const KmerTable& t, uint64_t key, ui
   const uint64_t base = (uint64_t)table_sub(t, h) * t.sub_slots;
   uint64_t slot = __umul64hi(h, t.sub_slots);
   while (true) {
-    const unsigned long long prev = atomicCAS(&t.keys[base + slot], EMPTY, (unsigned long long)key);
-    if (prev == EMPTY || prev == key) { atomicMax(&t.vals[base + slot], val); return; }
+    unsigned long long* p = reinterpret_cast<unsigned long long*>(t.slots + base + slot);
+    const unsigned long long prev = atomicCAS(p, EMPTY, (unsigned long long)key);
+    if (prev == EMPTY || prev == key) { atomicMin(p + 1, ~val); return; }
     if (++slot == t.sub_slots) slot = 0;
   }
 }
@@ -65,9 +66,9 @@ __device__ __forceinline__ int table_get(const KmerTable& t, uint64_t key, uint6
   const uint64_t base = (uint64_t)table_sub(t, h) * t.sub_slots;
   uint64_t slot = __umul64hi(h, t.sub_slots);
   while (true) {
-    const unsigned long long k = t.keys[base + slot];
-    if (k == EMPTY) return 0;
-    if (k == key) return (int)(t.vals[base + slot] & 0xff);
+    const ulonglong2 s = __ldg(t.slots + base + slot);        // the table is complete and read-only by now
+    if (s.x == EMPTY) return 0;
+    if (s.x == key) return (int)(~s.y & 0xff);
     if (++slot == t.sub_slots) slot = 0;
   }
 }
@@ -143,18 +144,80 @@ __global__ void __launch_bounds__(256) pool_insert_kernel(const PoolEntry* __res
   }
 }
 
-struct ExtWarp {
-  uint8_t seq[MAX_READ + 160];
-  uint8_t ext[EXT_MAX + 8];
-  FinderScratch fs;
-};
 
 __device__ __forceinline__ bool ratio_ok(int x, int y) { return x > y ? (x <= 10 * y) : (10 * x >= y); }   // catt.jl:341
 
-// one warp per partial read (cdr3 == "None"): greedy walk over the table, then finder!(array) on the extended read
-__global__ void __launch_bounds__(PW * 32) extend_kernel(ReadsDev reads, const FinderDev* __restrict__ gfd, const PoolItem* __restrict__ items,
-                                                         const uint32_t* __restrict__ partial_idx, int64_t n_partial, int k, KmerTable tab,
-                                                         ExtendOut* __restrict__ out, uint32_t* __restrict__ rescued) {
+// The greedy walk over the table (extend_right! / extend_left!, catt.jl:341-424) is a chain of dependent random lookups - one HBM
+// round trip per added base, up to ~100 bases - so it is latency bound and wants as many chains in flight as the SM can hold:
+// FOUR lanes per partial read (one candidate base each), eight reads per warp.  The start k-mer comes straight from the packed
+// words (kmer_at); the added bases go to ExtendOut::ext2, 16 per word.  The extended reads then go through finder!(array) one
+// warp per read (extend_finish_kernel).
+__global__ void __launch_bounds__(PW * 32) extend_walk_kernel(ReadsDev reads, const PoolItem* __restrict__ items, const uint32_t* __restrict__ partial_idx,
+                                                              int64_t n_partial, int k, KmerTable tab, ExtendOut* __restrict__ out) {
+  const int lane = threadIdx.x & 31, c = lane & 3, grp = lane >> 2;
+  const uint64_t kmask = (k >= 32) ? ~0ull : ((1ull << (2 * k)) - 1);
+  uint64_t gkey = 0;
+  for (int i = 0; i < k; i++) gkey = (gkey << 2) | 2;
+  const int64_t ngroups = (int64_t)gridDim.x * PW * 8;
+  for (int64_t it0 = ((int64_t)blockIdx.x * PW + (threadIdx.x >> 5)) * 8; it0 < n_partial; it0 += ngroups) {
+    const int64_t it = it0 + grp;
+    bool active = false;
+    int side = 0, len0 = 0, cur = 0, n_ext = 0;
+    uint64_t seg = 0;
+    if (it < n_partial) {
+      const PoolItem pi = items[partial_idx[it]];
+      side = pi.side; len0 = pi.seq_len;
+      if (len0 >= k) {
+        const int s0 = side == 0 ? len0 - k : 0;
+        seg = kmer_at(reads.words + reads.off[pi.read], reads.len[pi.read], pi.seq_off + s0, k, pi.strand);
+        cur = table_get(tab, seg, gkey);                     // (the four lanes of the group read the same slot: one sector)
+        active = 1 < 151 - len0;
+      }
+    }
+    uint32_t wv = 0;                                         // the 16 bases being collected (meaningful on the group's first lane)
+    while (__any_sync(FULL, active)) {
+      // candidates in A,C,G,T order: right -> bw_neighbors(seg) = c + seg[1:k-1]; left -> fw_neighbors(seg) = seg[2:k] + c
+      const uint64_t cand = side == 0 ? (((uint64_t)c << (2 * (k - 1))) | (seg >> 2)) : (((seg << 2) | (uint64_t)c) & kmask);
+      int val = 0;
+      if (active) val = table_get(tab, cand, gkey);
+      // stable sort by value descending, then the first that passes == max value among passing, ties -> smallest c
+      const bool pass = active && val != 0 && ratio_ok(val, cur) && cand != seg;
+      int key = pass ? ((val << 2) | (3 - c)) : 0;
+      key = max(key, __shfl_xor_sync(FULL, key, 1));
+      key = max(key, __shfl_xor_sync(FULL, key, 2));
+      if (active) {
+        if (key) {
+          const int cw = 3 - (key & 3);
+          seg = side == 0 ? (((uint64_t)cw << (2 * (k - 1))) | (seg >> 2)) : (((seg << 2) | (uint64_t)cw) & kmask);
+          cur = key >> 2;
+          wv |= (uint32_t)cw << (2 * (n_ext & 15));
+          n_ext++;
+          if ((n_ext & 15) == 0) { if (c == 0) out[it].ext2[(n_ext >> 4) - 1] = wv; wv = 0; }
+          active = n_ext + 1 < 151 - len0;                   // idx = n_ext + 1 in the reference's loop
+        } else {
+          active = false;
+        }
+      }
+    }
+    if (it < n_partial && c == 0) {
+      ExtendOut* o = &out[it];
+      int w = n_ext >> 4;
+      if (n_ext & 15) o->ext2[w++] = wv;
+      for (; w < EXT_WORDS; w++) o->ext2[w] = 0;
+      o->n_ext = (int16_t)n_ext;
+    }
+  }
+}
+
+struct ExtWarp {
+  uint8_t seq[MAX_READ + 160 + EXT_MAX + 8];
+  FinderScratch fs;
+};
+
+// one warp per partial read: the extended read (right: seq * ext, left: reverse(ext) * seq), then finder!(array) on it
+__global__ void __launch_bounds__(PW * 32) extend_finish_kernel(ReadsDev reads, const FinderDev* __restrict__ gfd, const PoolItem* __restrict__ items,
+                                                                const uint32_t* __restrict__ partial_idx, int64_t n_partial,
+                                                                ExtendOut* __restrict__ out, uint32_t* __restrict__ rescued) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FinderDev* fd = reinterpret_cast<FinderDev*>(smem_raw);
   ExtWarp* wsall = reinterpret_cast<ExtWarp*>(smem_raw + sizeof(FinderDev));
@@ -163,71 +226,30 @@ __global__ void __launch_bounds__(PW * 32) extend_kernel(ReadsDev reads, const F
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   ExtWarp& ws = wsall[warp];
-  const uint64_t kmask = (k >= 32) ? ~0ull : ((1ull << (2 * k)) - 1);
-  uint64_t gkey = 0;
-  for (int i = 0; i < k; i++) gkey = (gkey << 2) | 2;
   for (int64_t it = (int64_t)blockIdx.x * PW + warp; it < n_partial; it += (int64_t)gridDim.x * PW) {
     const PoolItem pi = items[partial_idx[it]];
     const int m = reads.len[pi.read];
     const uint32_t* __restrict__ w = reads.words + reads.off[pi.read];
     const uint32_t* __restrict__ nm = w + read_base_words(m);
     const int len0 = pi.seq_len;
+    ExtendOut* o = &out[it];
+    const int n_ext = o->n_ext;
     // the slice sits at offset 152 so that a left extension can be prepended in place
     uint8_t* base = ws.seq + 152;
     for (int i = lane; i < len0; i += 32) base[i] = (uint8_t)sam_code(w, nm, m, pi.seq_off + i, pi.strand);
-    __syncwarp();
-    ExtendOut* o = &out[it];
-    int n_ext = 0;
-    if (len0 >= k) {
-      uint64_t seg = 0;
-      const int s0 = pi.side == 0 ? len0 - k : 0;
-      for (int i = 0; i < k; i++) seg = (seg << 2) | base[s0 + i];
-      int cur = table_get(tab, seg, gkey);
-      int idx = 1;
-      bool flag = true;
-      while (idx < 151 - len0 && flag) {
-        // candidates c in A,C,G,T order: right -> bw_neighbors(seg) = c + seg[1:k-1]; left -> fw_neighbors(seg) = seg[2:k] + c
-        const int c = lane & 3;
-        const uint64_t cand = pi.side == 0 ? (((uint64_t)c << (2 * (k - 1))) | (seg >> 2)) : (((seg << 2) | (uint64_t)c) & kmask);
-        int val = 0;
-        if (lane < 4) val = table_get(tab, cand, gkey);
-        // stable sort by value descending, then the first that passes == max value among passing, ties -> smallest c
-        const bool pass = lane < 4 && val != 0 && ratio_ok(val, cur) && cand != seg;
-        int key = pass ? ((val << 2) | (3 - c)) : 0;
-        key = max(key, __shfl_xor_sync(FULL, key, 1));
-        key = max(key, __shfl_xor_sync(FULL, key, 2));
-        key = __shfl_sync(FULL, key, 0);
-        flag = false;
-        if (key) {
-          const int cw = 3 - (key & 3);
-          seg = pi.side == 0 ? (((uint64_t)cw << (2 * (k - 1))) | (seg >> 2)) : (((seg << 2) | (uint64_t)cw) & kmask);
-          cur = key >> 2;
-          if (lane == 0) ws.ext[n_ext] = (uint8_t)cw;
-          n_ext++; idx++;
-          flag = true;
-        }
-      }
-    }
-    __syncwarp();
-    // build the extended read: right -> seq * ext ; left -> reverse(ext) * seq
     uint8_t* ext_seq = base;
     if (pi.side == 0) {
-      for (int i = lane; i < n_ext; i += 32) base[len0 + i] = ws.ext[i];
+      for (int i = lane; i < n_ext; i += 32) base[len0 + i] = (uint8_t)((o->ext2[i >> 4] >> (2 * (i & 15))) & 3u);
     } else {
       ext_seq = base - n_ext;
-      for (int i = lane; i < n_ext; i += 32) ext_seq[i] = ws.ext[n_ext - 1 - i];
+      for (int i = lane; i < n_ext; i += 32) { const int e = n_ext - 1 - i; ext_seq[i] = (uint8_t)((o->ext2[e >> 4] >> (2 * (e & 15))) & 3u); }
     }
     __syncwarp();
     int lo, l3;
     const bool able = finder_warp(ext_seq, len0 + n_ext, *fd, true, ws.fs, lane, &lo, &l3);
     if (lane == 0) {
-      o->n_ext = (int16_t)n_ext; o->cdr3_off = (int16_t)lo; o->cdr3_len = (int16_t)l3; o->able = able;
+      o->cdr3_off = (int16_t)lo; o->cdr3_len = (int16_t)l3; o->able = able;
       if (lo >= 0) atomicAdd(rescued, 1u);
-    }
-    if (lane < EXT_WORDS) {
-      uint32_t wv = 0;
-      for (int b = 0; b < 16; b++) { const int i = lane * 16 + b; if (i < n_ext) wv |= (uint32_t)(ws.ext[i] & 3) << (2 * b); }
-      o->ext2[lane] = wv;
     }
     __syncwarp();
   }
@@ -302,14 +324,17 @@ int launch_pool_insert(const PoolEntry* d_in, int64_t n, KmerTable tab, int sm_c
 int launch_extend(const ReadsDev& reads, const FinderDev* d_finder, const PoolItem* d_items, const uint32_t* d_partial_idx,
                   int64_t n_partial, int kmer, KmerTable tab, ExtendOut* d_out, uint32_t* d_rescued, int sm_count, cudaStream_t st, int* launches) {
   if (n_partial == 0) return CATT_OK;
+  const int gridw = (int)std::min<int64_t>((n_partial + PW * 8 - 1) / (PW * 8), (int64_t)sm_count * 16);
+  extend_walk_kernel<<<gridw, PW * 32, 0, st>>>(reads, d_items, d_partial_idx, n_partial, kmer, tab, d_out);
+  CATT_CUDA(cudaGetLastError());
   const size_t smem = sizeof(FinderDev) + sizeof(ExtWarp) * PW;
   static std::atomic<unsigned long long> optin{0};
-  int rc = smem_optin(extend_kernel, (int)smem, optin);
+  int rc = smem_optin(extend_finish_kernel, (int)smem, optin);
   if (rc) return rc;
   const int grid = (int)std::min<int64_t>((n_partial + PW - 1) / PW, (int64_t)sm_count * 8);
-  extend_kernel<<<grid, PW * 32, smem, st>>>(reads, d_finder, d_items, d_partial_idx, n_partial, kmer, tab, d_out, d_rescued);
+  extend_finish_kernel<<<grid, PW * 32, smem, st>>>(reads, d_finder, d_items, d_partial_idx, n_partial, d_out, d_rescued);
   CATT_CUDA(cudaGetLastError());
-  *launches += 1;
+  *launches += 2;
   return CATT_OK;
 }
 
