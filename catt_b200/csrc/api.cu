@@ -299,7 +299,10 @@ int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool
   catt_info local{};
   int64_t queued_reads = 0;
   bool hook_done = false;
+  const bool trace_chunks = getenv("CATT_TRACE_CHUNKS") != nullptr;
+  double tt_launch = 0, tt_stage = 0, tt_join = 0, tt_finish = 0;
   for (int64_t ci = 0; ci < nchunks; ci++) {
+    const double tc0 = now_ms();
     const Chunk ch = chunks[ci];
     const ReadsDev rv = dr.view(ch.i0, ch.cnt);
     CATT_CUDA(cudaStreamWaitEvent(st, c->ev_h2d[ci & 1], 0));
@@ -310,20 +313,27 @@ int stage_a_stream(catt_ctx* c, const HostReads& hr, int64_t first_ordinal, bool
       for (int which = 0; which < 2; which++)
         if ((rc = align_queue(c, which, rv, c->recs_all[which].as<catt_aln>() + ch.i0, ch.ordinal, launches))) return rc;
     }
+    const double tc1 = now_ms();
     if (ci + 1 < nchunks && (rc = stage_chunk(ci + 1))) return rc;
+    const double tc2 = now_ms();
     queued_reads += ch.cnt;
     if (under_kernels && !hook_done && (queued_reads >= 200000 || ci + 1 == nchunks)) {      // host work hidden under this chunk's kernels
       hook_done = true;
       if ((rc = under_kernels())) return rc;
     }
     if ((rc = join_streams(c))) return rc;
+    const double tc3 = now_ms();
     if (align) {
       const int64_t v0 = local.v_hits, j0 = local.j_hits;
       for (int which = 0; which < 2; which++)
         if ((rc = align_finish(c, which, rv, c->recs_all[which].as<catt_aln>() + ch.i0, ch.ordinal, &local, launches))) return rc;
       fh->v[ch.file] += local.v_hits - v0; fh->j[ch.file] += local.j_hits - j0;
     }
+    tt_launch += tc1 - tc0; tt_stage += tc2 - tc1; tt_join += tc3 - tc2; tt_finish += now_ms() - tc3;
   }
+  if (trace_chunks)
+    fprintf(stderr, "[catt trace] stage_a_stream: %lld chunks; host ms: launch %.1f, stage next %.1f, wait for the GPU %.1f, counters %.1f\n",
+            (long long)nchunks, tt_launch, tt_stage, tt_join, tt_finish);
   CATT_CUDA(cudaStreamSynchronize(st));
   CATT_CUDA(cudaStreamSynchronize(cs));
   c->last_n = n; c->last_words = (int64_t)total_words; c->last_max_len = max_len;

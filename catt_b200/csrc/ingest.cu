@@ -62,6 +62,16 @@ __global__ void record_kernel(const char* __restrict__ text, long long t0, const
 }
 
 // one warp per read: lane k builds base word k (16 bases) and, for k < mask words, N-mask word k (32 bases)
+// One warp per read, 32 bases per step: every lane loads one character (one coalesced request per step), and three ballots give
+// the N-mask word and the two bit planes of the codes; two lanes interleave the planes into the step's two 2-bit words.
+__device__ __forceinline__ uint32_t spread16(uint32_t x) {        // bit i of the low half -> bit 2i
+  x &= 0xffffu;
+  x = (x | (x << 8)) & 0x00ff00ffu;
+  x = (x | (x << 4)) & 0x0f0f0f0fu;
+  x = (x | (x << 2)) & 0x33333333u;
+  x = (x | (x << 1)) & 0x55555555u;
+  return x;
+}
 __global__ void __launch_bounds__(256) pack_kernel(const char* __restrict__ text, const long long* __restrict__ seq_beg,
                                                    const int32_t* __restrict__ len, const uint32_t* __restrict__ off, long long n,
                                                    uint32_t* __restrict__ words) {
@@ -70,18 +80,14 @@ __global__ void __launch_bounds__(256) pack_kernel(const char* __restrict__ text
     const int l = len[r];
     const char* __restrict__ s = text + seq_beg[r];
     uint32_t* __restrict__ b = words + off[r];
-    const int bw = read_base_words(l), mw = read_mask_words(l);
-    for (int k = lane; k < bw; k += 32) {
-      uint32_t w = 0;
-      const int lim = min(16, l - 16 * k);
-      for (int j = 0; j < lim; j++) { const uint32_t c = nt_code(s[16 * k + j]); w |= (c & 3u) << (2 * j); }
-      b[k] = w;
-    }
-    for (int k = lane; k < mw; k += 32) {
-      uint32_t w = 0;
-      const int lim = min(32, l - 32 * k);
-      for (int j = 0; j < lim; j++) w |= (uint32_t)(nt_code(s[32 * k + j]) > 3) << j;
-      b[bw + k] = w;
+    const int bw = read_base_words(l);
+    for (int i0 = 0; i0 < l; i0 += 32) {
+      const int i = i0 + lane;
+      const uint32_t c = i < l ? nt_code(s[i]) : 0u;
+      const uint32_t p0 = __ballot_sync(0xffffffffu, c & 1u), p1 = __ballot_sync(0xffffffffu, c & 2u), pn = __ballot_sync(0xffffffffu, c > 3u);
+      const int k = (i0 >> 4) + lane;                             // lanes 0 and 1: the two base words of this step
+      if (lane < 2 && k < bw) b[k] = spread16(p0 >> (16 * lane)) | (spread16(p1 >> (16 * lane)) << 1);
+      if (lane == 2) b[bw + (i0 >> 5)] = pn;
     }
   }
 }
