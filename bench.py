@@ -103,6 +103,14 @@ def ncu_pipe_alu():
         return None
 
 
+def ncu_facts():
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            return json.load(fh)
+    except Exception:
+        return {}
+
+
 def roofline_other(infos, length, world, n_total):
     """The two HBM-side kernels of SURVEY 8d against the measured copy bandwidth (MEASURED_PEAKS.json, else the recipe's fallback).
     Algorithmic bytes: seeding = packed read in (ceil(L/4) + ceil(L/8) B) + the two candidate bitmaps and the task count out per
@@ -121,8 +129,16 @@ def roofline_other(infos, length, world, n_total):
     pool_bytes = 16 * 11 * (i["vpart"] + i["jpart"]) / world
     out = {}
     if ms_seed > 0:
+        # instruction-issue bound (one warp per read, tables L2-resident): the HBM yardstick SURVEY gave it reads 0.003 and says
+        # nothing, so the line carries what bounds it - warp instructions per read and issue-slot use from the committed ncu capture
         a = world * seed_bytes / (ms_seed * 1e-3) / 1e9
-        out["seed_kernel"] = {"bound": "hbm", "achieved": a, "peak": peak * world, "unit": "GB/s", "frac": a / (peak * world), "peak_source": src}
+        f = ncu_facts()
+        step_ms = sum(x["ms_seed"] + x["ms_sw"] + x["ms_select"] + x["ms_order"] + x["ms_extract"] + x["ms_pool"] for x in infos) / len(infos)
+        out["seed_kernel"] = {"bound": "instruction issue", "ms_per_step": ms_seed, "share_of_step": ms_seed / step_ms if step_ms else None,
+                              "ns_per_read_per_gpu": 1e6 * ms_seed / n,
+                              "warp_instr_per_read": f.get("seed_kernel_warp_instr_per_read"), "issue_active_pct": f.get("seed_kernel_issue_active_pct"),
+                              "lanes_per_instr": f.get("seed_kernel_lanes_per_instr"), "hbm_gbs_algorithmic": a,
+                              "note": "V reference set, both seeding launches; ncu figures from profiles/traffic.json (" + str(f.get("_source")) + ")"}
     if ms_pool > 0:
         a = world * pool_bytes / (ms_pool * 1e-3) / 1e9
         out["pool_kernel"] = {"bound": "hbm", "achieved": a, "peak": peak * world, "unit": "GB/s", "frac": a / (peak * world), "peak_source": src}
@@ -458,10 +474,11 @@ def main():
                        "stage_a_ms_slowest_rank": info["ms_stage_a_max"], "stage_a_ms_fastest_rank": info["ms_stage_a_min"],
                        "collectives": coll_block(infos), "collectives_e2e": coll_block(e2e_infos),
                        "transport": "NCCL (library-owned communicator, ncclCommInitRank) over NVLink" if world > 1 else "none (one GPU)"},
-        "roofline": {"bound": "alu", "kernel": "sw_bulk2_kernel<4,25> (V) + <4,8> (J)", "achieved": achieved / 1e12, "peak": peak / 1e12,
+        "roofline": {"bound": "alu", "kernel": "sw_bulk2_kernel<4,25> (V reference set; the J set goes through sw_score_kernel<4,8,TRACK> once per candidate)", "achieved": achieved / 1e12, "peak": peak / 1e12,
                      "unit": "Tiop/s", "frac": achieved / peak, "frac_executed": executed / peak, "traffic": ncu_traffic(),
                      "cells_algorithmic_v": int(cells), "cells_computed_v": int(info["cells_computed_v"]),
-                     "alu_instr_per_cell_pair": 4.5, "ncu_pipe_alu_pct": ncu_pipe_alu(),
+                     "alu_instr_per_cell_pair": 4.5, "ncu_pipe_alu_pct": ncu_pipe_alu(), "ncu_issue_active_pct": ncu_facts().get("sw_bulk2_kernel_issue_active_pct"),
+                     "traffic_note": "dram bytes read + written by ONE launch of the ncu capture (" + str(ncu_facts().get("_source")) + "); a bench launch covers a 1 M-read chunk",
                      "note": "achieved = 12 int ops x ALGORITHMIC DP cells of the V reference set (every scored (read, record, strand) pair, len x len) / its SW kernel time; "
                              "frac_executed counts only the cells the kernel computes (byte-identical records are scored once); the kernel issues 4.5 ALU-pipe "
                              "instructions per cell pair where the 12-op model implies 6, so neither is pipe utilisation - ncu_pipe_alu_pct is (profiles/); "

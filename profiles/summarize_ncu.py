@@ -79,7 +79,25 @@ def traffic(path):
         b = float(r[rd].replace(",", "")) * scale[units[rd]] + float(r[wr].replace(",", "")) * scale[units[wr]]
         if name not in res or b > res[name]:
             res[name] = b
-    res["_source"] = os.path.basename(path) + " (ncu --set full, 262144 x 150 bp reads per launch)"
+    # the largest launch of the DP and seeding kernels: pipe utilisation, issue slots, warp instructions (per read for seeding:
+    # argv[3] = reads in that launch)
+    hdrs = {h: i for i, h in enumerate(hdr)}
+    def num(r, m):
+        return float(r[hdrs[m]].replace(",", ""))
+    big = {}
+    for r in rows[2:]:
+        nm = r[kn].split("<")[0].split("::")[-1].split("(")[0]
+        if nm not in big or num(r, "gpu__time_duration.sum") > num(big[nm], "gpu__time_duration.sum"):
+            big[nm] = r
+    if "sw_bulk2_kernel" in big:
+        res["sw_bulk2_kernel_pipe_alu_pct"] = round(num(big["sw_bulk2_kernel"], "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"), 1)
+        res["sw_bulk2_kernel_issue_active_pct"] = round(num(big["sw_bulk2_kernel"], "smsp__issue_active.avg.pct_of_peak_sustained_active"), 1)
+    if "seed_kernel" in big:
+        res["seed_kernel_issue_active_pct"] = round(num(big["seed_kernel"], "smsp__issue_active.avg.pct_of_peak_sustained_active"), 1)
+        res["seed_kernel_lanes_per_instr"] = round(num(big["seed_kernel"], "smsp__thread_inst_executed_per_inst_executed.ratio"), 1)
+        if len(sys.argv) > 3:
+            res["seed_kernel_warp_instr_per_read"] = round(num(big["seed_kernel"], "smsp__inst_executed.sum") / float(sys.argv[3]))
+    res["_source"] = os.path.basename(path) + " (ncu --set full; largest launch of each kernel" + (f", {sys.argv[3]} x 150 bp reads" if len(sys.argv) > 3 else "") + ")"
     with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "traffic.json"), "w") as fh:
         json.dump(res, fh, indent=1)
     print(json.dumps(res, indent=1))
