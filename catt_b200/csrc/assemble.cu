@@ -42,12 +42,27 @@ __device__ __forceinline__ int trimmed_len(const char* s, int l) {            //
   return l;
 }
 
-// ---- QNAME set: slot_of[i] = equivalence class of read i's trimmed name (only for reads with a V or J hit) ------------
-__global__ void name_kernel(int64_t n, NamesDev nd, const catt_aln* __restrict__ rv, const catt_aln* __restrict__ rj, int32_t* owner,
+// ---- QNAME classes and the dedup, without a sorted rank ----------------------------------------------------------------------------
+// `samtools sort -t AS | view -F 2308 | tac | awk '!a[$1]++'` keeps, per trimmed QNAME, the record that comes first in the final
+// order.  The sort key (AS, tid, pos, strand, input index) is unique per record, so "first in descending order" is simply the class's
+// LARGEST key: every mapped read raises its class's V and J maxima when it enters the QNAME set (one 32-byte slot per class:
+// owner, max V key, max J key - one sector), a second pass in input order compares each record with its class (kept = its key is
+// the maximum; shared = the class has a V and a J record) and only then are the keys sorted - to place the kept records, not to
+// decide them.  Non-kept records sort as 0; the `shared` flag rides in bit 62, above the 61 sorted bits.
+struct QClass { unsigned long long maxv, maxj; uint32_t owner; uint32_t pad_[3]; };      // owner = read index + 1 of the first inserter
+constexpr unsigned long long KEY_SHARED = 1ull << 62;
+
+__device__ __forceinline__ unsigned long long sam_key(const catt_aln& a, uint32_t i) {
+  return ((unsigned long long)(uint16_t)a.as << 51) | ((unsigned long long)(uint32_t)a.rid << 42) | ((unsigned long long)(uint16_t)a.rb << 33) |
+         ((unsigned long long)(a.strand & 1) << 32) | (unsigned long long)i;
+}
+
+__global__ void name_kernel(int64_t n, NamesDev nd, const catt_aln* __restrict__ rv, const catt_aln* __restrict__ rj, QClass* __restrict__ cls,
                             uint32_t mask, uint32_t* __restrict__ slot_of) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  if (!(rv[i].mapped || rj[i].mapped)) { slot_of[i] = INF; return; }
+  const catt_aln av = rv[i], aj = rj[i];
+  if (!(av.mapped || aj.mapped)) { slot_of[i] = INF; return; }
   const char* s = nd.s + nd.beg[i];
   const int l = trimmed_len(s, (int)(nd.end[i] - nd.beg[i]));
   uint64_t h = 0xcbf29ce484222325ull;
@@ -55,61 +70,59 @@ __global__ void name_kernel(int64_t n, NamesDev nd, const catt_aln* __restrict__
   h ^= h >> 32; h *= 0xd6e8feb86659fd93ull; h ^= h >> 32;
   uint32_t slot = (uint32_t)h & mask;
   while (true) {
-    int32_t o = atomicCAS(&owner[slot], -1, (int32_t)i);
-    if (o == -1 || o == (int32_t)i) break;
-    const char* t = nd.s + nd.beg[o];
-    const int lt = trimmed_len(t, (int)(nd.end[o] - nd.beg[o]));
+    const uint32_t o = atomicCAS(&cls[slot].owner, 0u, (uint32_t)i + 1u);
+    if (o == 0u || o == (uint32_t)i + 1u) break;
+    const char* t = nd.s + nd.beg[o - 1];
+    const int lt = trimmed_len(t, (int)(nd.end[o - 1] - nd.beg[o - 1]));
     bool same = lt == l;
     for (int k = 0; same && k < l; k++) same = s[k] == t[k];
     if (same) break;
     slot = (slot + 1) & mask;
   }
   slot_of[i] = slot;
+  if (av.mapped) atomicMax(&cls[slot].maxv, sam_key(av, (uint32_t)i));
+  if (aj.mapped) atomicMax(&cls[slot].maxj, sam_key(aj, (uint32_t)i));
 }
 
-// ---- sort keys of the mapped records --------------------------------------------------------------------------------
-__global__ void key_kernel(int64_t n, const catt_aln* __restrict__ recs, unsigned long long* __restrict__ keys,
-                           unsigned long long* __restrict__ counter) {
+// input order: the sort keys of the mapped records (0 for a record that lost its QNAME to a better one), kept counts, and the sums
+// samtools stats takes over the final V list
+__global__ void kept_kernel(int64_t n, const catt_aln* __restrict__ rv, const catt_aln* __restrict__ rj, const int32_t* __restrict__ len,
+                            const uint32_t* __restrict__ slot_of, const QClass* __restrict__ cls, unsigned long long* __restrict__ keys_v,
+                            unsigned long long* __restrict__ keys_j, unsigned long long* __restrict__ cnt) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool m = i < n && recs[i].mapped;
-  const unsigned bal = __ballot_sync(FULL, m);
-  if (!bal) return;
   const int lane = threadIdx.x & 31;
-  unsigned long long base = 0;
-  if (lane == __ffs(bal) - 1) base = atomicAdd(counter, (unsigned long long)__popc(bal));
-  base = __shfl_sync(FULL, base, __ffs(bal) - 1);
-  if (m) {
-    const catt_aln a = recs[i];
-    keys[base + __popc(bal & ((1u << lane) - 1))] = ((unsigned long long)(uint16_t)a.as << 51) | ((unsigned long long)(uint32_t)a.rid << 42) |
-                                                    ((unsigned long long)(uint16_t)a.rb << 33) | ((unsigned long long)(a.strand & 1) << 32) |
-                                                    (unsigned long long)(uint32_t)i;
+  bool mv = false, mj = false;
+  unsigned long long kv = 0, kj = 0, sl = 0, sn = 0, sm = 0;
+  if (i < n) {
+    const catt_aln av = rv[i], aj = rj[i];
+    mv = av.mapped; mj = aj.mapped;
+    if (mv || mj) {
+      const QClass c = cls[slot_of[i]];
+      const unsigned long long sh = (c.maxv != 0 && c.maxj != 0) ? KEY_SHARED : 0ull;
+      if (mv) { const unsigned long long k = sam_key(av, (uint32_t)i); if (k == c.maxv) { kv = k | sh; sl = (unsigned long long)len[i]; sn = (unsigned long long)av.nm; sm = (unsigned long long)av.mi; } }
+      if (mj) { const unsigned long long k = sam_key(aj, (uint32_t)i); if (k == c.maxj) kj = k | sh; }
+    }
   }
-}
-
-__global__ void minrank_kernel(int64_t nm, const unsigned long long* __restrict__ sorted, const uint32_t* __restrict__ slot_of,
-                               uint32_t* __restrict__ minrank) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < nm) atomicMin(&minrank[slot_of[(uint32_t)sorted[r]]], (uint32_t)r);
-}
-
-// kept = first record of its QNAME in sorted order; the V list also feeds samtools stats' sums
-__global__ void flag_kernel(int64_t nm, const unsigned long long* __restrict__ sorted, const uint32_t* __restrict__ slot_of,
-                            const uint32_t* __restrict__ minrank, const catt_aln* __restrict__ recs, const int32_t* __restrict__ len,
-                            int stats, uint32_t* __restrict__ flag, unsigned long long* __restrict__ cnt) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned long long sl = 0, sn = 0, sm = 0;
-  if (r < nm) {
-    const uint32_t idx = (uint32_t)sorted[r];
-    const bool kept = minrank[slot_of[idx]] == (uint32_t)r;
-    flag[r] = kept;
-    if (kept && stats) { sl = (unsigned long long)len[idx]; sn = (unsigned long long)recs[idx].nm; sm = (unsigned long long)recs[idx].mi; }
-  } else if (r == nm) {
-    flag[r] = 0;
+  const unsigned bv = __ballot_sync(FULL, mv), bj = __ballot_sync(FULL, mj);
+  const unsigned fv = __ballot_sync(FULL, kv != 0), fj = __ballot_sync(FULL, kj != 0);
+  if (bv) {
+    unsigned long long base = 0;
+    const int leader = __ffs(bv) - 1;
+    if (lane == leader) { base = atomicAdd(&cnt[C_NMAP_V], (unsigned long long)__popc(bv)); if (fv) atomicAdd(&cnt[C_F_V], (unsigned long long)__popc(fv)); }
+    base = __shfl_sync(FULL, base, leader);
+    if (mv) keys_v[base + __popc(bv & ((1u << lane) - 1))] = kv;
   }
-  if (stats) {
+  if (bj) {
+    unsigned long long base = 0;
+    const int leader = __ffs(bj) - 1;
+    if (lane == leader) { base = atomicAdd(&cnt[C_NMAP_J], (unsigned long long)__popc(bj)); if (fj) atomicAdd(&cnt[C_F_J], (unsigned long long)__popc(fj)); }
+    base = __shfl_sync(FULL, base, leader);
+    if (mj) keys_j[base + __popc(bj & ((1u << lane) - 1))] = kj;
+  }
+  if (fv) {
     #pragma unroll
     for (int d = 16; d; d >>= 1) { sl += __shfl_xor_sync(FULL, sl, d); sn += __shfl_xor_sync(FULL, sn, d); sm += __shfl_xor_sync(FULL, sm, d); }
-    if ((threadIdx.x & 31) == 0 && sl) { atomicAdd(&cnt[C_SUM_LEN], sl); atomicAdd(&cnt[C_SUM_NM], sn); atomicAdd(&cnt[C_SUM_MI], sm); }
+    if (lane == 0) { atomicAdd(&cnt[C_SUM_LEN], sl); atomicAdd(&cnt[C_SUM_NM], sn); atomicAdd(&cnt[C_SUM_MI], sm); }
   }
 }
 
@@ -127,22 +140,21 @@ __device__ __forceinline__ uint32_t chunk_pos(uint32_t nr, uint32_t F, uint32_t 
   return start + (nr - first) / T;
 }
 
-// kept records in the reference's processing order; records of shared QNAMEs leave the part lists and (J side) seed the pairs
-__global__ void order_kernel(int64_t nm, const unsigned long long* __restrict__ sorted, const uint32_t* __restrict__ flag,
-                             const uint32_t* __restrict__ kpos, int T, const uint32_t* __restrict__ slot_of,
-                             const uint32_t* __restrict__ minv, const uint32_t* __restrict__ minj, int which, NamesDev nd,
-                             uint32_t* __restrict__ ord_idx, uint32_t* __restrict__ ord_flag, uint32_t* __restrict__ pair_j,
+// kept records in the reference's processing order (rank r among the kept = position in the descending sort; the zero keys of the
+// dropped records sort behind them); records of shared QNAMEs leave the part lists and (J side) seed the pairs
+__global__ void order_kernel(int64_t nm, const unsigned long long* __restrict__ sorted, const unsigned long long* __restrict__ n_kept, int T, int which,
+                             NamesDev nd, uint32_t* __restrict__ ord_idx, uint32_t* __restrict__ ord_flag, uint32_t* __restrict__ pair_j,
                              unsigned long long* __restrict__ cnt) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = r < nm && flag[r];
+  const unsigned long long key = r < nm ? sorted[r] : 0ull;
+  const bool live = key != 0;
   bool pair = false;
   uint32_t idx = 0;
   if (live) {
-    const uint32_t F = kpos[nm];
-    idx = (uint32_t)sorted[r];
-    const uint32_t y = chunk_pos(kpos[r] + 1, F, (uint32_t)T);
-    const uint32_t slot = slot_of[idx];
-    const bool shared = minv[slot] != INF && minj[slot] != INF;
+    const uint32_t F = (uint32_t)*n_kept;
+    idx = (uint32_t)key;
+    const uint32_t y = chunk_pos((uint32_t)r + 1, F, (uint32_t)T);
+    const bool shared = (key & KEY_SHARED) != 0;
     ord_idx[y] = idx;
     ord_flag[y] = !shared;
     pair = which == 1 && shared;
@@ -163,9 +175,7 @@ __global__ void order_kernel(int64_t nm, const unsigned long long* __restrict__ 
   if (pair) pair_j[base + __popc(bal & ((1u << lane) - 1))] = idx;
 }
 
-__global__ void collect_kernel(const uint32_t* kpos_v, int64_t nm_v, const uint32_t* kpos_j, int64_t nm_j, const uint32_t* opos_v,
-                               const uint32_t* opos_j, unsigned long long* cnt) {
-  cnt[C_F_V] = nm_v ? kpos_v[nm_v] : 0; cnt[C_F_J] = nm_j ? kpos_j[nm_j] : 0;
+__global__ void collect_kernel(int64_t nm_v, int64_t nm_j, const uint32_t* opos_v, const uint32_t* opos_j, unsigned long long* cnt) {
   cnt[C_NV] = nm_v ? opos_v[nm_v] : 0; cnt[C_NJ] = nm_j ? opos_j[nm_j] : 0;
 }
 
@@ -197,14 +207,12 @@ __global__ void part_item_kernel(int64_t F, const uint32_t* __restrict__ ord_idx
   items[opos[y]] = make_item(recs[idx], lo + idx, kind);
 }
 
-__global__ void pair_item_kernel(int64_t np, const uint32_t* __restrict__ pair_j, const uint32_t* __restrict__ slot_of,
-                                 const uint32_t* __restrict__ minv, const unsigned long long* __restrict__ sorted_v,
-                                 const catt_aln* __restrict__ rv, const catt_aln* __restrict__ rj, uint32_t lo,
-                                 ExtractItem* __restrict__ items) {
+__global__ void pair_item_kernel(int64_t np, const uint32_t* __restrict__ pair_j, const uint32_t* __restrict__ slot_of, const QClass* __restrict__ cls,
+                                 const catt_aln* __restrict__ rv, const catt_aln* __restrict__ rj, uint32_t lo, ExtractItem* __restrict__ items) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= np) return;
   const uint32_t ji = pair_j[p];
-  const uint32_t vi = (uint32_t)sorted_v[minv[slot_of[ji]]];
+  const uint32_t vi = (uint32_t)cls[slot_of[ji]].maxv;          // the kept V record of the QNAME: its key ends in the read index
   ExtractItem it = make_item(rv[vi], lo + vi, 2);
   const catt_aln b = rj[ji];
   it.read2 = lo + ji; it.j_m_end = b.m_end; it.j_rid = (int16_t)b.rid; it.j_strand = b.strand;
@@ -531,24 +539,21 @@ int upload_names(catt_ctx* c, int64_t n, const char* names, const int64_t* name_
 // ---- per-file ordering: names -> SAM order -> QNAME dedup -> share_name -> work items --------------------------------------
 // (read_alignrs, catt.jl:210-326, up to the point where records become Myreads)
 struct OrderScratch {
-  uint32_t* slot_of; int32_t* owner; uint32_t* minr[2]; uint64_t cap;
-  unsigned long long *keys_a, *sorted[2];
-  uint32_t *flag, *kpos[2], *ord_idx[2], *ord_flag[2], *opos[2], *pair_a, *pair_b;
+  uint32_t* slot_of; QClass* cls; uint64_t cap;
+  unsigned long long *keys[2], *sorted[2];
+  uint32_t *ord_idx[2], *ord_flag[2], *opos[2], *pair_a, *pair_b;
 };
 struct OrderOut { int64_t F[2], n_v, n_p, n_j; };
 
 static int order_alloc(catt_ctx* c, int64_t max_reads, int64_t max_v, int64_t max_j, OrderScratch* S) {
   int rc;
   uint64_t cap = 1024;
-  while (cap < (uint64_t)(max_v + max_j) * 2 + 2) cap <<= 1;
+  while (cap < (uint64_t)std::min<int64_t>(max_reads, max_v + max_j) * 2 + 2) cap <<= 1;      // one class per mapped read at most
   if (cap > 0x80000000ull) { set_error("too many mapped reads for the QNAME table"); return CATT_E_LIMIT; }
   S->cap = cap;
-  if ((rc = ensure(c, SB_SLOT_OF, max_reads, &S->slot_of)) || (rc = ensure(c, SB_OWNER, (int64_t)cap, &S->owner)) ||
-      (rc = ensure(c, SB_MINV, (int64_t)cap, &S->minr[0])) || (rc = ensure(c, SB_MINJ, (int64_t)cap, &S->minr[1]))) return rc;
-  const int64_t nmax = std::max(max_v, max_j);
-  if ((rc = ensure(c, SB_KEYS_A, nmax, &S->keys_a)) || (rc = ensure(c, SB_SORT_V, max_v, &S->sorted[0])) ||
-      (rc = ensure(c, SB_SORT_J, max_j, &S->sorted[1])) || (rc = ensure(c, SB_FLAG, nmax + 1, &S->flag)) || (rc = ensure(c, SB_KPOS_V, max_v + 1, &S->kpos[0])) ||
-      (rc = ensure(c, SB_KPOS_J, max_j + 1, &S->kpos[1])) || (rc = ensure(c, SB_ORD_IDX_V, max_v + 1, &S->ord_idx[0])) ||
+  if ((rc = ensure(c, SB_SLOT_OF, max_reads, &S->slot_of)) || (rc = ensure(c, SB_OWNER, (int64_t)cap, &S->cls))) return rc;
+  if ((rc = ensure(c, SB_KEYS_A, max_v + 1, &S->keys[0])) || (rc = ensure(c, SB_MINV, max_j + 1, &S->keys[1])) || (rc = ensure(c, SB_SORT_V, max_v + 1, &S->sorted[0])) ||
+      (rc = ensure(c, SB_SORT_J, max_j + 1, &S->sorted[1])) || (rc = ensure(c, SB_ORD_IDX_V, max_v + 1, &S->ord_idx[0])) ||
       (rc = ensure(c, SB_ORD_IDX_J, max_j + 1, &S->ord_idx[1])) || (rc = ensure(c, SB_ORD_FLAG_V, max_v + 1, &S->ord_flag[0])) ||
       (rc = ensure(c, SB_ORD_FLAG_J, max_j + 1, &S->ord_flag[1])) ||
       (rc = ensure(c, SB_OPOS_V, max_v + 1, &S->opos[0])) || (rc = ensure(c, SB_OPOS_J, max_j + 1, &S->opos[1])) ||
@@ -567,40 +572,28 @@ static int order_file(catt_ctx* c, const OrderScratch& S, int64_t nf, const Name
   int& k = *kmer;
   CATT_CUDA(cudaMemsetAsync(cnt, 0, C_COUNT * sizeof(unsigned long long), st));
   if (nm[0] + nm[1] > 0) {
-    CATT_CUDA(cudaMemsetAsync(S.owner, 0xff, S.cap * sizeof(int32_t), st));
-    CATT_CUDA(cudaMemsetAsync(S.minr[0], 0xff, S.cap * sizeof(uint32_t), st));
-    CATT_CUDA(cudaMemsetAsync(S.minr[1], 0xff, S.cap * sizeof(uint32_t), st));
-    name_kernel<<<nblk(nf), 256, 0, st>>>(nf, nd, rec[0], rec[1], S.owner, (uint32_t)(S.cap - 1), S.slot_of);
+    CATT_CUDA(cudaMemsetAsync(S.cls, 0, S.cap * sizeof(QClass), st));
+    name_kernel<<<nblk(nf), 256, 0, st>>>(nf, nd, rec[0], rec[1], S.cls, (uint32_t)(S.cap - 1), S.slot_of);
+    kept_kernel<<<nblk(nf), 256, 0, st>>>(nf, rec[0], rec[1], len, S.slot_of, S.cls, S.keys[0], S.keys[1], cnt);
     CATT_CUDA(cudaGetLastError());
-    *launches += 1;
+    *launches += 2;
   }
-  // per reference set: sorted final SAM order, QNAME dedup
+  // per reference set: the final SAM order of the kept records, then their places in the reference's processing order
   for (int which = 0; which < 2; which++) {
     if (nm[which] == 0) continue;
-    key_kernel<<<nblk(nf), 256, 0, st>>>(nf, rec[which], S.keys_a, cnt + C_NMAP_V + which);
-    CATT_CUDA(cudaGetLastError());
     size_t need = 0;
-    CATT_CUDA(cub::DeviceRadixSort::SortKeysDescending(nullptr, need, S.keys_a, S.sorted[which], nm[which], 0, 61, st));
+    CATT_CUDA(cub::DeviceRadixSort::SortKeysDescending(nullptr, need, S.keys[which], S.sorted[which], nm[which], 0, 61, st));
     if ((rc = ensure_cub(c, need))) return rc;
     need = c->sb[SB_CUB].cap;
-    CATT_CUDA(cub::DeviceRadixSort::SortKeysDescending(c->sb[SB_CUB].p, need, S.keys_a, S.sorted[which], nm[which], 0, 61, st));
-    minrank_kernel<<<nblk(nm[which]), 256, 0, st>>>(nm[which], S.sorted[which], S.slot_of, S.minr[which]);
-    CATT_CUDA(cudaGetLastError());
-    *launches += 10;     // key, radix sort (histogram + 7 onesweep passes), minrank
-  }
-  for (int which = 0; which < 2; which++) {
-    if (nm[which] == 0) continue;
-    flag_kernel<<<nblk(nm[which] + 1), 256, 0, st>>>(nm[which], S.sorted[which], S.slot_of, S.minr[which], rec[which], len, which == 0, S.flag, cnt);
-    CATT_CUDA(cudaGetLastError());
-    if ((rc = scan_u32(c, S.flag, S.kpos[which], nm[which] + 1, st))) return rc;
+    CATT_CUDA(cub::DeviceRadixSort::SortKeysDescending(c->sb[SB_CUB].p, need, S.keys[which], S.sorted[which], nm[which], 0, 61, st));
     CATT_CUDA(cudaMemsetAsync(S.ord_flag[which], 0, (size_t)(nm[which] + 1) * sizeof(uint32_t), st));
-    order_kernel<<<nblk(nm[which]), 256, 0, st>>>(nm[which], S.sorted[which], S.flag, S.kpos[which], c->nthreads, S.slot_of, S.minr[0], S.minr[1], which, nd,
-                                                  S.ord_idx[which], S.ord_flag[which], S.pair_a, cnt);
+    order_kernel<<<nblk(nm[which]), 256, 0, st>>>(nm[which], S.sorted[which], cnt + C_F_V + which, c->nthreads, which, nd, S.ord_idx[which], S.ord_flag[which],
+                                                  S.pair_a, cnt);
     CATT_CUDA(cudaGetLastError());
     if ((rc = scan_u32(c, S.ord_flag[which], S.opos[which], nm[which] + 1, st))) return rc;
-    *launches += 6;
+    *launches += 12;     // radix sort (histogram + 7 onesweep passes), order, scan
   }
-  collect_kernel<<<1, 1, 0, st>>>(S.kpos[0], nm[0], S.kpos[1], nm[1], S.opos[0], S.opos[1], cnt);
+  collect_kernel<<<1, 1, 0, st>>>(nm[0], nm[1], S.opos[0], S.opos[1], cnt);
   CATT_CUDA(cudaGetLastError());
   *launches += 1;
   CATT_CUDA(cudaMemcpyAsync(hcnt, cnt, C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -641,11 +634,13 @@ static int order_file(catt_ctx* c, const OrderScratch& S, int64_t nf, const Name
     for (int d = digits - 1; d >= 0; d--) {
       pair_key_kernel<<<nblk(n_p), 256, 0, st>>>(n_p, pairs, nd, d, pk_a);
       CATT_CUDA(cudaGetLastError());
+      // the last digit of the longest name holds fewer than 8 characters: the zero padding below them needs no passes
+      const int lo_bit = 64 - 8 * (int)std::min<unsigned long long>(8, hcnt[C_MAXNAME] - 8ull * (unsigned)d);
       size_t need = 0;
-      CATT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, pk_a, pk_b, pairs, other, n_p, 0, 64, st));
+      CATT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, pk_a, pk_b, pairs, other, n_p, lo_bit, 64, st));
       if ((rc = ensure_cub(c, need))) return rc;
       need = c->sb[SB_CUB].cap;
-      CATT_CUDA(cub::DeviceRadixSort::SortPairs(c->sb[SB_CUB].p, need, pk_a, pk_b, pairs, other, n_p, 0, 64, st));
+      CATT_CUDA(cub::DeviceRadixSort::SortPairs(c->sb[SB_CUB].p, need, pk_a, pk_b, pairs, other, n_p, lo_bit, 64, st));
       std::swap(pairs, other);
       *launches += 10;
     }
@@ -659,7 +654,7 @@ static int order_file(catt_ctx* c, const OrderScratch& S, int64_t nf, const Name
     *launches += 1;
   }
   if (n_p > 0) {
-    pair_item_kernel<<<nblk(n_p), 256, 0, st>>>(n_p, pairs, S.slot_of, S.minr[0], S.sorted[0], rec[0], rec[1], read_base, seg + n_v);
+    pair_item_kernel<<<nblk(n_p), 256, 0, st>>>(n_p, pairs, S.slot_of, S.cls, rec[0], rec[1], read_base, seg + n_v);
     CATT_CUDA(cudaGetLastError());
     *launches += 1;
   }
