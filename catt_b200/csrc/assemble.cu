@@ -635,7 +635,7 @@ static int order_file(catt_ctx* c, const OrderScratch& S, int64_t nf, const Name
       pair_key_kernel<<<nblk(n_p), 256, 0, st>>>(n_p, pairs, nd, d, pk_a);
       CATT_CUDA(cudaGetLastError());
       // the last digit of the longest name holds fewer than 8 characters: the zero padding below them needs no passes
-      const int lo_bit = 64 - 8 * (int)std::min<unsigned long long>(8, hcnt[C_MAXNAME] - 8ull * (unsigned)d);
+      const int lo_bit = 64 - 8 * (int)std::min<unsigned long long>(8, std::max<unsigned long long>(hcnt[C_MAXNAME], 8ull * (unsigned)d + 1) - 8ull * (unsigned)d);
       size_t need = 0;
       CATT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, pk_a, pk_b, pairs, other, n_p, lo_bit, 64, st));
       if ((rc = ensure_cub(c, need))) return rc;
