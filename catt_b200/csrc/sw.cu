@@ -333,6 +333,32 @@ int launch_sw_t(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks, c
 // each per LDS.128 (conflict free, also across the skewed rows, whose profile rows are 128-byte multiples apart).  That moves 1
 // of the 5.5 ALU-pipe instructions per cell pair to the otherwise idle LSU pipe.
 // ---------------------------------------------------------------------------------------------------------------
+// Shared-memory layout of one task's profile (bulk and grouped TRACK kernels).  A profile row (one read symbol) holds the lane
+// groups' 16-byte words chunk by chunk: word (chunk, g) at chunk * G * 16 + g * 16.  With G = 4 two tasks share each 128-byte bank
+// phase of an LDS.128, so they must sit in different 64-byte halves WHATEVER rows they read: rows are padded to multiples of 128
+// bytes and the task stride is an odd multiple of 64.  (With the natural 448-byte rows of the 4 x 25 tiling the half depended on
+// the read symbol: ncu counted 1.2 - 2 wavefronts per ideal one.)  A column count that is not a multiple of 4 keeps its last C % 4
+// columns in a small tail [symbol][lane][column] read with scalar loads instead of padding every row by a chunk.
+template <int G, int C>
+struct ProfLayout {
+  static constexpr int CHF = C / 4, TAIL = C % 4;
+  static constexpr int ROW_RAW = G * CHF * 16;
+  static constexpr int ROWB = G == 4 ? ((ROW_RAW + 127) & ~127) : ROW_RAW;
+  static constexpr int TAIL_ROWB = G * TAIL * 4;
+  static constexpr int SLOT_RAW = 5 * ROWB + 5 * TAIL_ROWB;
+  static constexpr int SLOTB = G == 4 ? ((SLOT_RAW + 63) / 128) * 128 + 64 : ((SLOT_RAW + 15) & ~15);
+  // word index (from the profile base, in 32-bit words) of symbol q, lane g, column c
+  __device__ static __forceinline__ int word(int q, int g, int c) {
+    return c < 4 * CHF ? q * (ROWB / 4) + ((c >> 2) * G + g) * 4 + (c & 3) : 5 * (ROWB / 4) + q * (TAIL_ROWB / 4) + g * TAIL + (c - 4 * CHF);
+  }
+};
+// per-task stride of the read-code arrays, in bytes: a word count of 9 mod 32 puts the eight tasks of a warp nine banks apart
+__host__ __device__ inline int qarr_stride(int max_len) {
+  int w = (max_len + 1 + 3) / 4;
+  w += (9 - w % 32 + 32) % 32;
+  return 4 * w;
+}
+
 // Two rows per wavefront step: lane g works on read rows 2(st-g) and 2(st-g)+1 for its C columns, column by column, the second
 // row one cell behind the first.  Same cells, same operations per cell - but two independent F chains per thread (the ALU pipe
 // was stalling on the 3-instruction dependency chain of a single row) and half as many shuffles / loop iterations per row.
@@ -342,9 +368,7 @@ __global__ void __launch_bounds__(SW_THREADS) sw_bulk2_kernel(RefDev ref, ReadsD
                                                               uint32_t* __restrict__ out, int ml, unsigned long long* __restrict__ work) {
   constexpr int GPW = 32 / G;
   constexpr int GPB = GPW * (SW_THREADS / 32);
-  constexpr int CH = (C + 3) / 4;
-  constexpr int ROWW = G * CH * 4;
-  constexpr int PROFW = 5 * ROWW;
+  using L = ProfLayout<G, C>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int64_t ntasks = (int64_t)*ntasks_dev;
   if (ntasks > ntasks_cap) return;
@@ -352,9 +376,10 @@ __global__ void __launch_bounds__(SW_THREADS) sw_bulk2_kernel(RefDev ref, ReadsD
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane % G, grp = lane / G;
   const int slot = warp * GPW + grp;
-  uint32_t* prof = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)slot * PROFW;
-  uint8_t* qarr = smem_raw + (size_t)GPB * PROFW * 4 + (size_t)slot * ml;       // ml is even and > max_len
+  uint32_t* prof = reinterpret_cast<uint32_t*>(smem_raw + (size_t)slot * L::SLOTB);
+  uint8_t* qarr = smem_raw + (size_t)GPB * L::SLOTB + (size_t)slot * ml;       // ml is even and > max_len
   const uint32_t prof_base = smem_u32(prof) + (uint32_t)g * 16u;
+  const uint32_t tail_base = smem_u32(prof) + (uint32_t)(5 * L::ROWB + g * L::TAIL * 4);
   const uint8_t* __restrict__ Tb = ref.Tb;
   const uint32_t neg7 = NEG7 ^ (uint32_t)((unsigned long long)ntasks_cap >> 62);   // == NEG7, opaque to constant propagation
 
@@ -379,13 +404,12 @@ __global__ void __launch_bounds__(SW_THREADS) sw_bulk2_kernel(RefDev ref, ReadsD
       for (int c = 0; c < C; c++) {
         const int j = g * C + c;
         const int ba = j < la ? (int)Tb[oa + j] : 7, bb = j < lb ? (int)Tb[ob + j] : 7;
-        uint32_t* dst = prof + ((c >> 2) * G + g) * 4 + (c & 3);
         #pragma unroll
         for (int q = 0; q < 4; q++) {
           const int sa = q == ba ? 1 : -2, sb = (q == bb ? 1 : -2) - (sa < 0);
-          dst[q * ROWW] = ((uint32_t)sb << 16) | ((uint32_t)sa & 0xFFFFu);
+          prof[L::word(q, g, c)] = ((uint32_t)sb << 16) | ((uint32_t)sa & 0xFFFFu);
         }
-        dst[4 * ROWW] = 0xFFFEFFFFu;
+        prof[L::word(4, g, c)] = 0xFFFEFFFFu;
       }
     }
     __syncwarp();
@@ -409,37 +433,43 @@ __global__ void __launch_bounds__(SW_THREADS) sw_bulk2_kernel(RefDev ref, ReadsD
       if (i2 >= 0 && i2 < rows2) {
         uint32_t qq;
         asm volatile("ld.shared.u16 %0, [%1];" : "=r"(qq) : "r"(q_base + 2u * (uint32_t)i2));
-        const uint32_t row0 = prof_base + (qq & 0xffu) * (uint32_t)(ROWW * 4);
-        const uint32_t row1 = prof_base + (qq >> 8) * (uint32_t)(ROWW * 4);
+        const uint32_t q0 = qq & 0xffu, q1 = qq >> 8;
+        const uint32_t row0 = prof_base + q0 * (uint32_t)L::ROWB;
+        const uint32_t row1 = prof_base + q1 * (uint32_t)L::ROWB;
         uint32_t hd0 = diag_in, f0 = inF0;    // row 2*i2:   diagonal = H(row-1, left neighbour's last column)
         uint32_t hd1 = inH0, f1 = inF1;       // row 2*i2+1: diagonal = H(row 2*i2, left neighbour's last column)
         diag_in = inH1;
         uint32_t h0 = TWO2;
+        auto cell = [&](int c, uint32_t sc0, uint32_t sc1) {
+          const uint32_t t0 = hd0 + sc0;                             // packed adds as plain 32-bit adds (see sw_row)
+          h0 = __vimax3_s16x2(t0, E[c], f0);
+          hd0 = Hp[c];
+          const uint32_t hm0 = __viaddmax_s16x2(h0, neg7, TWO2);
+          const uint32_t e0 = __viaddmax_s16x2(E[c], NEG1, hm0);
+          f0 = __viaddmax_s16x2(f0, NEG1, hm0);
+          const uint32_t t1 = hd1 + sc1;
+          const uint32_t h1 = __vimax3_s16x2(t1, e0, f1);
+          hd1 = h0;
+          const uint32_t hm1 = __viaddmax_s16x2(h1, neg7, TWO2);
+          E[c] = __viaddmax_s16x2(e0, NEG1, hm1);
+          f1 = __viaddmax_s16x2(f1, NEG1, hm1);
+          Hp[c] = h1;
+          best = __vimax3_s16x2(best, h0, h1);
+        };
         #pragma unroll
-        for (int ch = 0; ch < CH; ch++) {
+        for (int ch = 0; ch < L::CHF; ch++) {
           uint32_t s0[4], s1[4];
           asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(s0[0]), "=r"(s0[1]), "=r"(s0[2]), "=r"(s0[3]) : "r"(row0 + (uint32_t)(ch * G * 16)));
           asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(s1[0]), "=r"(s1[1]), "=r"(s1[2]), "=r"(s1[3]) : "r"(row1 + (uint32_t)(ch * G * 16)));
           #pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const int c = 4 * ch + k;
-            if (c < C) {
-              const uint32_t t0 = hd0 + s0[k];                       // packed adds as plain 32-bit adds (see sw_row)
-              h0 = __vimax3_s16x2(t0, E[c], f0);
-              hd0 = Hp[c];
-              const uint32_t hm0 = __viaddmax_s16x2(h0, neg7, TWO2);
-              const uint32_t e0 = __viaddmax_s16x2(E[c], NEG1, hm0);
-              f0 = __viaddmax_s16x2(f0, NEG1, hm0);
-              const uint32_t t1 = hd1 + s1[k];
-              const uint32_t h1 = __vimax3_s16x2(t1, e0, f1);
-              hd1 = h0;
-              const uint32_t hm1 = __viaddmax_s16x2(h1, neg7, TWO2);
-              E[c] = __viaddmax_s16x2(e0, NEG1, hm1);
-              f1 = __viaddmax_s16x2(f1, NEG1, hm1);
-              Hp[c] = h1;
-              best = __vimax3_s16x2(best, h0, h1);
-            }
-          }
+          for (int k = 0; k < 4; k++) cell(4 * ch + k, s0[k], s1[k]);
+        }
+        #pragma unroll
+        for (int k = 0; k < L::TAIL; k++) {
+          uint32_t a0, a1;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a0) : "r"(tail_base + q0 * (uint32_t)L::TAIL_ROWB + (uint32_t)(k * 4)));
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a1) : "r"(tail_base + q1 * (uint32_t)L::TAIL_ROWB + (uint32_t)(k * 4)));
+          cell(4 * L::CHF + k, a0, a1);
         }
         lastH0 = h0; lastH1 = Hp[C - 1];
         lastF0 = f0; lastF1 = f1;
@@ -456,9 +486,8 @@ template <int G, int C>
 int launch_sw_bulk(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks, const uint32_t* ntasks_dev, int64_t cap, uint32_t* res,
                    unsigned long long* work, int sm_count, cudaStream_t st) {
   constexpr int GPB = (32 / G) * (SW_THREADS / 32);
-  constexpr int PROFW = 5 * G * ((C + 3) / 4) * 4;
-  const int ml = (reads.max_len + 1 + 15) & ~15;                 // room for the phantom row of odd-length reads
-  const size_t smem = (size_t)GPB * (PROFW * 4 + ml);
+  const int ml = qarr_stride(reads.max_len);                     // room for the phantom row of odd-length reads
+  const size_t smem = (size_t)GPB * (ProfLayout<G, C>::SLOTB + ml);
   auto k = sw_bulk2_kernel<G, C>;
   static std::atomic<unsigned long long> optin{0};
   int per_sm = 0;
@@ -546,17 +575,16 @@ __global__ void __launch_bounds__(SW_THREADS) sw_track2_kernel(RefDev ref, Reads
                                                                uint32_t* __restrict__ out, int ml, unsigned long long* __restrict__ work) {
   constexpr int GPW = 32 / G;
   constexpr int GPB = GPW * (SW_THREADS / 32);
-  constexpr int CH = (C + 3) / 4;
-  constexpr int ROWW = G * CH * 4;
-  constexpr int PROFW = 5 * ROWW;
+  using L = ProfLayout<G, C>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int64_t ntasks = (int64_t)(*nslots_dev >> 1);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane % G, grp = lane / G;
   const int slot = warp * GPW + grp;
-  int32_t* prof = reinterpret_cast<int32_t*>(smem_raw) + (size_t)slot * PROFW;
-  uint16_t* qarr = reinterpret_cast<uint16_t*>(smem_raw + (size_t)GPB * PROFW * 4 + (size_t)slot * ml);   // ml bytes: 4 x 3-bit read codes per row pair
+  int32_t* prof = reinterpret_cast<int32_t*>(smem_raw + (size_t)slot * L::SLOTB);
+  uint16_t* qarr = reinterpret_cast<uint16_t*>(smem_raw + (size_t)GPB * L::SLOTB + (size_t)slot * ml);   // ml bytes: 4 x 3-bit read codes per row pair
   const uint32_t prof_base = smem_u32(prof) + (uint32_t)g * 16u;
+  const uint32_t tail_base = smem_u32(prof) + (uint32_t)(5 * L::ROWB + g * L::TAIL * 4);
   const uint8_t* __restrict__ Tb = ref.Tb;
   const uint32_t neg7 = NEG7 ^ (uint32_t)((unsigned long long)ml >> 30);        // == NEG7, opaque to constant propagation
   int cur_rid = -1;
@@ -580,10 +608,9 @@ __global__ void __launch_bounds__(SW_THREADS) sw_track2_kernel(RefDev ref, Reads
         for (int c = 0; c < C; c++) {
           const int j = g * C + c;
           const int ba = j < la ? (int)Tb[oa + j] : 7;
-          int32_t* dst = prof + ((c >> 2) * G + g) * 4 + (c & 3);
           #pragma unroll
-          for (int q = 0; q < 4; q++) dst[q * ROWW] = q == ba ? 1 : -2;
-          dst[4 * ROWW] = -1;
+          for (int q = 0; q < 4; q++) prof[L::word(q, g, c)] = q == ba ? 1 : -2;
+          prof[L::word(4, g, c)] = -1;
         }
       }
       const int ma = reads.len[ta.read], mb = kb != NO_WINNER ? reads.len[tb.read] : 0;
@@ -624,42 +651,50 @@ __global__ void __launch_bounds__(SW_THREADS) sw_track2_kernel(RefDev ref, Reads
       if (i2 >= 0 && i2 < rows2) {
         uint32_t qq;
         asm volatile("ld.shared.u16 %0, [%1];" : "=r"(qq) : "r"(q_base + 2u * (uint32_t)i2));
-        const uint32_t r0l = prof_base + (qq & 7u) * (uint32_t)(ROWW * 4), r1l = prof_base + ((qq >> 3) & 7u) * (uint32_t)(ROWW * 4);
-        const uint32_t r0h = prof_base + ((qq >> 6) & 7u) * (uint32_t)(ROWW * 4), r1h = prof_base + (qq >> 9) * (uint32_t)(ROWW * 4);
+        const uint32_t q0l = qq & 7u, q1l = (qq >> 3) & 7u, q0h = (qq >> 6) & 7u, q1h = qq >> 9;
+        const uint32_t r0l = prof_base + q0l * (uint32_t)L::ROWB, r1l = prof_base + q1l * (uint32_t)L::ROWB;
+        const uint32_t r0h = prof_base + q0h * (uint32_t)L::ROWB, r1h = prof_base + q1h * (uint32_t)L::ROWB;
         uint32_t hd0 = diag_in, f0 = inF0;
         uint32_t hd1 = inH0, f1 = inF1;
         diag_in = inH1;
         uint32_t h0v[C];
         uint32_t rb0 = TWO2, rb1 = TWO2;
+        auto cell = [&](int c, int32_t lo0, int32_t hi0, int32_t lo1, int32_t hi1) {
+          const uint32_t t0 = (uint32_t)(hi0 * 65536 + (int32_t)(hd0 + (uint32_t)lo0));
+          const uint32_t h0 = __vimax3_s16x2(t0, E[c], f0);
+          hd0 = Hp[c];
+          const uint32_t hm0 = __viaddmax_s16x2(h0, neg7, TWO2);
+          const uint32_t e0 = __viaddmax_s16x2(E[c], NEG1, hm0);
+          f0 = __viaddmax_s16x2(f0, NEG1, hm0);
+          const uint32_t t1 = (uint32_t)(hi1 * 65536 + (int32_t)(hd1 + (uint32_t)lo1));
+          const uint32_t h1 = __vimax3_s16x2(t1, e0, f1);
+          hd1 = h0;
+          const uint32_t hm1 = __viaddmax_s16x2(h1, neg7, TWO2);
+          E[c] = __viaddmax_s16x2(e0, NEG1, hm1);
+          f1 = __viaddmax_s16x2(f1, NEG1, hm1);
+          Hp[c] = h1;
+          h0v[c] = h0;
+          if (c & 1) { rb0 = __vimax3_s16x2(rb0, h0v[c - 1], h0); rb1 = __vimax3_s16x2(rb1, Hp[c - 1], h1); }
+          else if (c == C - 1) { rb0 = __vimax3_s16x2(rb0, h0, h0); rb1 = __vimax3_s16x2(rb1, h1, h1); }
+        };
         #pragma unroll
-        for (int ch = 0; ch < CH; ch++) {
+        for (int ch = 0; ch < L::CHF; ch++) {
           int32_t l0[4], l1[4], u0[4], u1[4];
           asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(l0[0]), "=r"(l0[1]), "=r"(l0[2]), "=r"(l0[3]) : "r"(r0l + (uint32_t)(ch * G * 16)));
           asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(u0[0]), "=r"(u0[1]), "=r"(u0[2]), "=r"(u0[3]) : "r"(r0h + (uint32_t)(ch * G * 16)));
           asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(l1[0]), "=r"(l1[1]), "=r"(l1[2]), "=r"(l1[3]) : "r"(r1l + (uint32_t)(ch * G * 16)));
           asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(u1[0]), "=r"(u1[1]), "=r"(u1[2]), "=r"(u1[3]) : "r"(r1h + (uint32_t)(ch * G * 16)));
           #pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const int c = 4 * ch + k;
-            if (c < C) {
-              const uint32_t t0 = (uint32_t)(u0[k] * 65536 + (int32_t)(hd0 + (uint32_t)l0[k]));
-              const uint32_t h0 = __vimax3_s16x2(t0, E[c], f0);
-              hd0 = Hp[c];
-              const uint32_t hm0 = __viaddmax_s16x2(h0, neg7, TWO2);
-              const uint32_t e0 = __viaddmax_s16x2(E[c], NEG1, hm0);
-              f0 = __viaddmax_s16x2(f0, NEG1, hm0);
-              const uint32_t t1 = (uint32_t)(u1[k] * 65536 + (int32_t)(hd1 + (uint32_t)l1[k]));
-              const uint32_t h1 = __vimax3_s16x2(t1, e0, f1);
-              hd1 = h0;
-              const uint32_t hm1 = __viaddmax_s16x2(h1, neg7, TWO2);
-              E[c] = __viaddmax_s16x2(e0, NEG1, hm1);
-              f1 = __viaddmax_s16x2(f1, NEG1, hm1);
-              Hp[c] = h1;
-              h0v[c] = h0;
-              if (c & 1) { rb0 = __vimax3_s16x2(rb0, h0v[c - 1], h0); rb1 = __vimax3_s16x2(rb1, Hp[c - 1], h1); }
-              else if (c == C - 1) { rb0 = __vimax3_s16x2(rb0, h0, h0); rb1 = __vimax3_s16x2(rb1, h1, h1); }
-            }
-          }
+          for (int k = 0; k < 4; k++) cell(4 * ch + k, l0[k], u0[k], l1[k], u1[k]);
+        }
+        #pragma unroll
+        for (int k = 0; k < L::TAIL; k++) {
+          int32_t a0, b0, a1, b1;
+          asm volatile("ld.shared.s32 %0, [%1];" : "=r"(a0) : "r"(tail_base + q0l * (uint32_t)L::TAIL_ROWB + (uint32_t)(k * 4)));
+          asm volatile("ld.shared.s32 %0, [%1];" : "=r"(b0) : "r"(tail_base + q0h * (uint32_t)L::TAIL_ROWB + (uint32_t)(k * 4)));
+          asm volatile("ld.shared.s32 %0, [%1];" : "=r"(a1) : "r"(tail_base + q1l * (uint32_t)L::TAIL_ROWB + (uint32_t)(k * 4)));
+          asm volatile("ld.shared.s32 %0, [%1];" : "=r"(b1) : "r"(tail_base + q1h * (uint32_t)L::TAIL_ROWB + (uint32_t)(k * 4)));
+          cell(4 * L::CHF + k, a0, b0, a1, b1);
         }
         lastH0 = h0v[C - 1]; lastH1 = Hp[C - 1];
         lastF0 = f0; lastF1 = f1;
@@ -716,9 +751,8 @@ __global__ void __launch_bounds__(SW_THREADS) sw_track2_kernel(RefDev ref, Reads
 template <int G, int C>
 int launch_sw_track2(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int sm_count, cudaStream_t st) {
   constexpr int GPB = (32 / G) * (SW_THREADS / 32);
-  constexpr int PROFW = 5 * G * ((C + 3) / 4) * 4;
-  const int ml = (reads.max_len + 1 + 15) & ~15;                 // qarr bytes per task: one u16 per row pair
-  const size_t smem = (size_t)GPB * (PROFW * 4 + ml);
+  const int ml = qarr_stride(reads.max_len);                     // qarr bytes per task: one u16 per row pair
+  const size_t smem = (size_t)GPB * (ProfLayout<G, C>::SLOTB + ml);
   auto k = sw_track2_kernel<G, C>;
   static std::atomic<unsigned long long> optin{0};
   int per_sm = 0;
