@@ -32,6 +32,7 @@ constexpr uint32_t NEG1 = 0xFFFFFFFFu;   // (-1,-1)
 constexpr uint32_t NEG7 = 0xFFF9FFF9u;   // (-7,-7): first gap base = open 6 + extend 1
 constexpr uint32_t MINV = 0x80008000u;   // (-32768,-32768)
 constexpr uint32_t TWO2 = 0x00020002u;   // the +2 bias of every DP quantity
+constexpr int BULK_RUN = 4;              // consecutive tasks per lane group and work-cursor grab in the bulk kernel
 
 __device__ __forceinline__ uint64_t hash_64(uint64_t key) {   // bwa's tie-break hash
   key += ~(key << 32);
@@ -383,32 +384,56 @@ __global__ void __launch_bounds__(SW_THREADS) sw_bulk2_kernel(RefDev ref, ReadsD
   const uint8_t* __restrict__ Tb = ref.Tb;
   const uint32_t neg7 = NEG7 ^ (uint32_t)((unsigned long long)ntasks_cap >> 62);   // == NEG7, opaque to constant propagation
 
+  // A warp takes BULK_RUN tasks per lane group at a time and every group works through CONSECUTIVE ones: the tasks of a read are
+  // adjacent in the list (about seven per read for hs TRBV), so the group's read-code array is rebuilt only when the read or the
+  // strand changes
+  int64_t cur_read = -1;
+  int cur_strand = -1, cur_m = 0;
   for (;;) {
-    const int64_t base = next_tasks(work, GPW, lane);
-    if (base >= ntasks) break;
-    const int64_t t = base + grp;
+    const int64_t base0 = next_tasks(work, GPW * BULK_RUN, lane);
+    if (base0 >= ntasks) break;
+   #pragma unroll 1
+   for (int kk = 0; kk < BULK_RUN; kk++) {
+    const int64_t t = base0 + (int64_t)grp * BULK_RUN + kk;
+    if (base0 + kk >= ntasks) break;                    // (warp-uniform: no group has a task kk any more)
     const bool live = t < ntasks;
     int m = 0;
     if (live) {
       const SwTask tk = tasks[t];
       const int strand = tk.a & 1;
-      m = reads.len[tk.read];
-      const uint32_t* __restrict__ w = reads.words + reads.off[tk.read];
-      const uint32_t* __restrict__ nm = w + read_base_words(m);
-      for (int i = g; i < m; i += G) qarr[i] = (uint8_t)read_code(w, nm, m, i, strand);
-      if (g == 0 && (m & 1)) qarr[m] = 4;               // the phantom last row of an odd-length read scores -1 everywhere
+      if ((int64_t)tk.read != cur_read || strand != cur_strand) {
+        cur_read = tk.read; cur_strand = strand;
+        cur_m = reads.len[tk.read];
+        const uint32_t* __restrict__ w = reads.words + reads.off[tk.read];
+        const uint32_t* __restrict__ nm = w + read_base_words(cur_m);
+        for (int i = g; i < cur_m; i += G) qarr[i] = (uint8_t)read_code(w, nm, cur_m, i, strand);
+        if (g == 0 && (cur_m & 1)) qarr[cur_m] = 4;     // the phantom last row of an odd-length read scores -1 everywhere
+      }
+      m = cur_m;
       const int ra = tk.a >> 1, oa = ref.rec_off[ra], la = ref.rec_len[ra];
       int ob = 0, lb = 0;
       if (tk.b != 0xFFFF) { const int rb = tk.b >> 1; ob = ref.rec_off[rb]; lb = ref.rec_len[rb]; }
+      // profile word of read symbol q for a column holding bases (ba, bb); four columns go out as one 16-byte store
+      auto pw = [](int q, int ba, int bb) -> uint32_t {
+        const int sa = q == ba ? 1 : -2, sb = (q == bb ? 1 : -2) - (sa < 0);
+        return ((uint32_t)sb << 16) | ((uint32_t)sa & 0xFFFFu);
+      };
       #pragma unroll
-      for (int c = 0; c < C; c++) {
-        const int j = g * C + c;
+      for (int ch = 0; ch < L::CHF; ch++) {
+        int ba[4], bb[4];
+        #pragma unroll
+        for (int k = 0; k < 4; k++) { const int j = g * C + 4 * ch + k; ba[k] = j < la ? (int)Tb[oa + j] : 7; bb[k] = j < lb ? (int)Tb[ob + j] : 7; }
+        #pragma unroll
+        for (int q = 0; q < 4; q++)
+          *reinterpret_cast<uint4*>(prof + L::word(q, g, 4 * ch)) = make_uint4(pw(q, ba[0], bb[0]), pw(q, ba[1], bb[1]), pw(q, ba[2], bb[2]), pw(q, ba[3], bb[3]));
+        *reinterpret_cast<uint4*>(prof + L::word(4, g, 4 * ch)) = make_uint4(0xFFFEFFFFu, 0xFFFEFFFFu, 0xFFFEFFFFu, 0xFFFEFFFFu);
+      }
+      #pragma unroll
+      for (int k = 0; k < L::TAIL; k++) {
+        const int c = 4 * L::CHF + k, j = g * C + c;
         const int ba = j < la ? (int)Tb[oa + j] : 7, bb = j < lb ? (int)Tb[ob + j] : 7;
         #pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const int sa = q == ba ? 1 : -2, sb = (q == bb ? 1 : -2) - (sa < 0);
-          prof[L::word(q, g, c)] = ((uint32_t)sb << 16) | ((uint32_t)sa & 0xFFFFu);
-        }
+        for (int q = 0; q < 4; q++) prof[L::word(q, g, c)] = pw(q, ba, bb);
         prof[L::word(4, g, c)] = 0xFFFEFFFFu;
       }
     }
@@ -479,6 +504,7 @@ __global__ void __launch_bounds__(SW_THREADS) sw_bulk2_kernel(RefDev ref, ReadsD
     for (int d = G / 2; d; d >>= 1) best = __vimax_s16x2_relu(best, __shfl_xor_sync(FULL, best, d, G));
     if (live && g == 0) out[t] = best - TWO2;
     __syncwarp();
+   }
   }
 }
 
