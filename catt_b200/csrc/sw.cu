@@ -818,7 +818,8 @@ template <bool TRACK>
 int dispatch_sw(const RefDev& ref, const ReadsDev& reads, const SwTask* tasks, const uint32_t* ntasks_dev, int64_t cap, uint32_t* res,
                 unsigned long long* work, int sm_count, cudaStream_t st) {
   const int n = ref.maxlen;
-  static const int tile32 = getenv("CATT_TILE32") ? atoi(getenv("CATT_TILE32")) : 4;
+  const char* t32 = n <= 32 ? getenv("CATT_TILE32") : nullptr;              // A/B switch, see INTEGRATION.md
+  const int tile32 = t32 ? atoi(t32) : 4;
   if (n <= 32 && tile32 == 2) return launch_sw_t<2, 16, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, work, sm_count, st);
   if (n <= 32 && tile32 == 1) return launch_sw_t<1, 32, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, work, sm_count, st);
   if (n <= 32) return launch_sw_t<4, 8, TRACK>(ref, reads, tasks, ntasks_dev, cap, res, work, sm_count, st);
@@ -1176,7 +1177,7 @@ int launch_sw(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, int sm
 // TRACK pass on the winners, CIGAR facts, traceback of the gapped ones: everything after the winner of every read is known
 static int launch_after_select(const RefDev& ref, const ReadsDev& reads, AlignBuffers& ab, catt_aln* recs, bool track, int sm_count, cudaStream_t st,
                                int* launches) {
-  static const bool old_track = getenv("CATT_OLD_TRACK") != nullptr;       // A/B switch: the PRMT kernel on unsorted winners
+  const bool old_track = getenv("CATT_OLD_TRACK") != nullptr;              // A/B switch: the PRMT kernel on unsorted winners
   int rc = CATT_OK;
   if (track && old_track)
     rc = dispatch_sw<true>(ref, reads, ab.wtasks, reinterpret_cast<const uint32_t*>(ab.counters + 7), reads.n, ab.wres, ab.counters + CTR_WORK_TRACK, sm_count, st);

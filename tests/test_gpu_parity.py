@@ -117,6 +117,23 @@ def test_alignment_records_testsample(ctx, O, orefs, sample):
     assert int(v["mapped"].sum()) == 2653 and int(j["mapped"].sum()) == 1752
 
 
+@pytest.mark.parametrize("env", [{"CATT_OLD_TRACK": "1"}, {"CATT_NO_DIRECT": "1"}, {"CATT_OLD_TRACK": "1", "CATT_NO_DIRECT": "1"}, {"CATT_TILE32": "2"}])
+def test_alternative_kernels_give_the_same_records(trb, O, orefs, sample, monkeypatch, env):
+    """The A/B switches select the previous kernels (TRACK pass by the PRMT kernel on unsorted winners; J sets through the bulk
+    pass + TRACK pass; another lane tiling for short records): every path must produce the oracle's records, i.e. the grouped
+    profile TRACK kernel, the direct J pass and the old kernels all agree cell for cell."""
+    from catt_b200.host import Catt
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    c = Catt(chain_cfg=trb, device=0)
+    try:
+        v, j = c.align_shard(sample[1])
+        assert_records_equal(v, orefs[0].align(sample[1]), O)
+        assert_records_equal(j, orefs[1].align(sample[1]), O)
+    finally:
+        c.close()
+
+
 def test_first_ordinal_shifts_the_tie_break(ctx, O, orefs, sample):
     """bwa's hash tie-break uses the GLOBAL read ordinal: a shard must reproduce it through first_ordinal."""
     sub = sample[1][3000:3800]
