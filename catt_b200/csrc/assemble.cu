@@ -5,8 +5,8 @@
 // the alignment records Stage A left in HBM (ctx->recs_all), so no per-read data crosses PCIe until the final lists:
 //   * `samtools sort -t AS | view -F 2308 | tac | awk '!a[$1]++'` (catt.jl:45-48): one 61-bit radix key
 //     (AS, tid, pos, strand, input index) sorted descending == descending (AS, tid, pos, strand) with later input first
-//     on complete ties; the awk dedup is an atomicMin of the sorted rank per trimmed QNAME (QNAMEs live in a device
-//     hash set, compared byte-exactly on every hash hit)                                                  [SURVEY A7]
+//     on complete ties; the awk dedup keeps the record with the LARGEST key of its trimmed QNAME (QNAMEs live in a device
+//     hash set, compared byte-exactly on every hash hit; name_kernel / kept_kernel below)                  [SURVEY A7]
 //   * get_kmer_fromsam / get_err_fromsam (catt.jl:153-184): device sums, formatted on the host as samtools stats
 //     prints them                                                                                          [SURVEY A8]
 //   * share_name, the NR % nthreads chunk order (closed form), the name-sorted both-mapped pairing (LSD radix sort over
